@@ -1,0 +1,154 @@
+/*
+ * mcbrat_cuda.h -- C ABI of the B200-native photon-tracing path of MCBRaT3D.
+ *
+ * Drop-in boundary: these entry points are what a thin ISO_C_BINDING layer inside the
+ * reference's Fortran module procedures binds to (fortran/mcbrat_cuda_mod.f90 and
+ * INTEGRATION.md show the binding).  Reference citations use
+ *   INT = Integrators/monteCarloRadiativeTransfer.f95   OPT = src/opticalProperties.f95
+ *   ILL = src/monteCarloIllumination.f95                EMI = src/emissionAndBroadBandWeights.f95
+ *   DRV = Drivers/monteCarloDriver.f95
+ *
+ * Conventions
+ *   - every function returns 0 on success, non-zero on failure; mcb_last_error() gives the
+ *     text the Fortran shim hands to setStateToFailure(status, ...) (ErrorMessages.f95:225).
+ *   - arrays use the reference's Fortran layout, x fastest: a(ix,iy,iz) is
+ *     a[(ix-1) + nx*((iy-1) + ny*(iz-1))]; 4-D arrays add the component as slowest index;
+ *     tables are values(step, entry), step fastest; indices are 1-based.
+ *   - the library COPIES on every mcb_set_* (staged once into HBM) and never retains a
+ *     host pointer; results are written into caller-provided buffers; any output pointer
+ *     may be NULL (Fortran `optional`).
+ *   - one handle per (process, GPU); calls on one handle are serialised by the caller.
+ *   - plain pointers and sizes only: no torch / C++ types cross this boundary.
+ */
+#ifndef MCBRAT_CUDA_H
+#define MCBRAT_CUDA_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct mcb_handle mcb_handle;
+
+enum { MCB_ARITH_FAST = 0, MCB_ARITH_REFERENCE = 1 };
+
+/* Algorithmic choices: the optional arguments of specifyParameters (INT:1046-1073) that
+ * the photon loop reads.  Defaults (mcb_default_options) are the integrator's (INT:53-96). */
+typedef struct {
+  int32_t useRayTracing;                    /* INT:53; only 1 (ray tracing) is implemented     */
+  int32_t useRussianRoulette;               /* INT:55                                          */
+  float   russianRouletteW;                 /* INT:56                                          */
+  int32_t useRussianRouletteForIntensity;   /* INT:90                                          */
+  float   zetaMin;                          /* INT:91                                          */
+  int32_t useHybridPhaseFunsForIntenCalcs;  /* INT:85                                          */
+  int32_t numOrdersOrigPhaseFunIntenCalcs;  /* INT:87                                          */
+  int32_t limitIntensityContributions;      /* INT:94                                          */
+  float   maxIntensityContribution;         /* INT:95                                          */
+  float   LW_flag;                          /* INT:68; > 0 switches on emission bookkeeping    */
+  int32_t arithmetic;                       /* MCB_ARITH_FAST (default) | MCB_ARITH_REFERENCE  */
+  int32_t reserved[5];
+} mcb_options;
+
+/* Event counters of the last batch (algorithmic-bytes accounting). */
+typedef struct {
+  int64_t photons, crossings, scatters, surfaceHits, topExits, bad,
+          leRays, leCrossings, rouletteKills, reserved[7];
+} mcb_counters;
+
+/* Trace record (fixed-random-number single-photon harness, north-star criterion (a)). */
+enum {
+  MCB_EV_BIRTH = 1, MCB_EV_SCATTER = 2, MCB_EV_SURFACE = 3, MCB_EV_EXIT_TOP = 4,
+  MCB_EV_KILLED_SURFACE = 5, MCB_EV_KILLED_ROULETTE = 6, MCB_EV_BAD = 7,
+  MCB_EV_LOCAL_ESTIMATE = 8, MCB_EV_RN_EXHAUSTED = 9
+};
+typedef struct {
+  int32_t photon, kind, ix, iy, iz, component, phaseIndex, angleIndex, order, nrn;
+  float   weight, tau;
+  double  path, x, y, z;
+  float   dir[3];
+  int32_t pad;
+} mcb_event;
+
+/* ---- lifetime -------------------------------------------------------------------------- */
+/* new_Integrator INT:129-132 / finalize_Integrator INT:1486 own the handle in the shim. */
+int mcb_create(int device, mcb_handle **out);
+int mcb_destroy(mcb_handle *h);
+int mcb_last_error(const mcb_handle *h, char *buf, int len);
+int mcb_version(void);
+/* Run on a caller-owned CUDA stream (cudaStream_t passed as void*); NULL = the handle's own. */
+int mcb_set_stream(mcb_handle *h, void *cudaStream);
+int mcb_synchronize(mcb_handle *h);
+
+/* ---- staging: replaces the per-batch getInfo_Domain copies at INT:434-443, 1668-1673 --- */
+/* grid edges: new_Integrator's getInfo_Domain(xPosition, yPosition, zPosition), INT:147-157 */
+int mcb_set_grid(mcb_handle *h, int nx, int ny, int nz,
+                 const double *xEdges, const double *yEdges, const double *zEdges);
+/* getInfo_Domain(albedo, totalExt, cumExt, ssa, phaseFuncI), INT:441-443 */
+int mcb_set_optics(mcb_handle *h, int nc, const double *totalExt, const double *cumExt,
+                   const double *ssa, const int32_t *phaseIdx, double albedo);
+/* getInfo_Domain(inversePhaseFuncs) INT:443 <- tabulateInversePhaseFunctions INT:280 */
+int mcb_set_inverse_table(mcb_handle *h, int comp, int nS, int nE, const float *T);
+/* getInfo_Domain(tabPhase, tabOrigPhase) INT:1672-1673 <- tabulateForwardPhaseFunctions INT:282 */
+int mcb_set_forward_table(mcb_handle *h, int comp, int nS, int nE, const float *P, const float *Porig);
+/* specifyParameters(intensityMus, intensityPhis): direction cosines as INT:1267-1269 builds them;
+ * nDir = 0 switches intensity off (specifyParameters(computeIntensity=.false.), INT:1278-1284) */
+int mcb_set_views(mcb_handle *h, int nDir, const float *dirCos);
+void mcb_default_options(mcb_options *o);
+int mcb_set_options(mcb_handle *h, const mcb_options *o);
+
+/* ---- photon sources: replace new_PhotonStream + getNextPhoton (ILL:62-101, 431-522, 561-590)
+ * The stream is never materialised; each photon samples its own start on the device.        */
+int mcb_set_solar_source(mcb_handle *h, float solarMu, float solarAzimuthDeg);
+/* Weights from emission_weighting (EMI:424-550): voxelCDF(nx,ny,nz), fracAtmsPower          */
+int mcb_set_thermal_source(mcb_handle *h, double fracAtmsPower, const double *voxelCDF);
+/* device build of the same CDF from the staged optics (EMI:498-522); temps(nx,ny,nz) in K   */
+int mcb_build_thermal_source(mcb_handle *h, const double *temps, double lambda_um,
+                             double surfaceTemp, double *fracAtmsPower, double *totalFlux);
+
+/* ---- computeRadiativeTransfer (INT:209-218) ------------------------------------------- */
+/* Zero the tallies (INT:247-272) and trace nPhotons photons with global ids
+ * [firstPhotonId, firstPhotonId + nPhotons) of the stream `seed` (counter-based RNG: the
+ * result does not depend on how a run is split into batches or GPUs).  Asynchronous on the
+ * handle's stream; *nProcessed = photons started (INT:833, includes those later dropped).  */
+int mcb_run_batch(mcb_handle *h, int64_t nPhotons, uint64_t seed, uint64_t firstPhotonId,
+                  int64_t *nProcessed);
+/* Same without zeroing: adds another range of photons to the current tallies. */
+int mcb_accumulate_batch(mcb_handle *h, int64_t nPhotons, uint64_t seed, uint64_t firstPhotonId,
+                         int64_t *nProcessed);
+/* Device time of the last run/accumulate call (CUDA events on the launch stream), ms.    */
+int mcb_last_batch_ms(mcb_handle *h, float *ms);
+int mcb_get_counters(mcb_handle *h, mcb_counters *c);
+
+/* ---- reportResults (INT:845-865) ---------------------------------------------------- */
+/* Normalised exactly as computeRadiativeTransfer does (INT:294-388).  nPhotonsNormalise <= 0
+ * uses the handle's own photon count; a multi-GPU run passes the global count after the
+ * reduce.  Sizes: flux*(nx,ny); volumeAbsorption(nx,ny,nz); intensity(nx,ny,nDir);
+ * intensityByComponent(nx,ny,nDir,0:nc).  Synchronises the stream.                       */
+int mcb_get_results(mcb_handle *h, int64_t nPhotonsNormalise,
+                    float *fluxUp, float *fluxDown, float *fluxAbsorbed,
+                    float *volumeAbsorption, float *intensity, float *intensityByComponent);
+/* The packed f64 tally buffer on the device: [fluxUp|fluxDown|fluxAbsorbed : 3*nx*ny]
+ * [volumeAbsorption : nx*ny*nz][intensity : nx*ny*nDir][intensityByComponent : nx*ny*nDir*(nc+1)]
+ * [intensityExcess : nDir*(nc+1)][photons started : 1].  This is what one NCCL/MPI sum-reduce
+ * replaces sumAcrossProcesses with (DRV:1151-1166).                                      */
+int mcb_tally_buffer(mcb_handle *h, void **devicePtr, int64_t *nDoubles);
+int mcb_get_raw_tallies(mcb_handle *h, double *out, int64_t nDoubles);
+
+/* ---- trace harness ------------------------------------------------------------------ */
+/* Photon p is born from and transported with rn[p*rnStride ...] (source draws first, then the
+ * computeRT order).  Always reference arithmetic.  Events of photon 0 come first,
+ * then photon 1, ...; at most maxEventsPerPhoton per photon, eventCap in total.  Tallies are
+ * left as raw sums of the traced photons (read with mcb_get_raw_tallies).                */
+int mcb_run_trace(mcb_handle *h, int64_t nPhotons, const float *rn, int64_t rnStride,
+                  int32_t maxEventsPerPhoton, mcb_event *events, int64_t eventCap,
+                  int64_t *nEvents);
+
+/* ---- testing aid ------------------------------------------------------------------- */
+/* The first n 32-bit outputs of the Philox4x32-10 stream of (seed, photon id).          */
+int mcb_debug_philox(mcb_handle *h, uint64_t seed, uint64_t photon, int n, uint32_t *out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

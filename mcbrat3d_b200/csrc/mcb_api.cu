@@ -1,0 +1,594 @@
+// mcb_api.cu -- the C ABI (include/mcbrat_cuda.h): handle, staging into HBM, launches,
+// normalisation and read-back.  No photon arithmetic happens on the host.
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "mcb_device.cuh"
+
+// launchers implemented next to their kernels
+void mcb_launch_reference_batch(const DevDomain &P, long long nPhotons, uint64_t seed, uint64_t firstPhotonId,
+                                int numSMs, cudaStream_t stream);
+void mcb_launch_trace(const DevDomain &P, long long nPhotons, const float *rn, long long rnStride,
+                      mcb_event *events, int maxEventsPerPhoton, int *eventCount, cudaStream_t stream);
+void mcb_launch_fast_batch(const DevDomain &P, long long nPhotons, uint64_t seed, uint64_t firstPhotonId,
+                           int numSMs, unsigned long long *workCounter, cudaStream_t stream);
+void mcb_launch_philox_kat(uint64_t seed, uint64_t photon, int n, uint32_t *out, cudaStream_t stream);
+
+struct mcb_handle {
+  int device = 0;
+  int numSMs = 148;
+  cudaStream_t ownStream = nullptr, stream = nullptr;
+  cudaEvent_t evStart = nullptr, evStop = nullptr;
+  bool timed = false;
+  std::string err;
+  DevDomain P;
+  bool haveGrid = false, haveOptics = false, haveSource = false;
+  bool haveInv[MCB_MAX_COMP] = {false}, haveFwd[MCB_MAX_COMP] = {false};
+  std::vector<double> xE, yE, zE;
+  std::vector<void *> owned;              // every device allocation, freed in mcb_destroy
+  // re-stageable slots (freed on re-set)
+  void *dXE = nullptr, *dYE = nullptr, *dZE = nullptr;
+  void *dTotalExt = nullptr, *dCumExt = nullptr, *dSsa = nullptr, *dPhaseIdx = nullptr;
+  void *dExt32 = nullptr, *dCum32 = nullptr, *dSsa32 = nullptr, *dIdx16 = nullptr;
+  void *dInv[MCB_MAX_COMP] = {nullptr}, *dFwd[MCB_MAX_COMP] = {nullptr}, *dFwdOrig[MCB_MAX_COMP] = {nullptr};
+  int invE[MCB_MAX_COMP] = {0}, fwdE[MCB_MAX_COMP] = {0};
+  void *dVoxelCDF = nullptr;
+  double *dTally = nullptr; long long nTally = 0;
+  unsigned long long *dCounters = nullptr;     // CNT_N counters + 1 work counter
+  double *hTally = nullptr; long long hTallyCap = 0;   // pinned
+};
+
+#define FAIL(h, ...)                                                     \
+  do {                                                                   \
+    char _b[512]; snprintf(_b, sizeof(_b), __VA_ARGS__);                 \
+    if (h) (h)->err = _b;                                                \
+    return 1;                                                            \
+  } while (0)
+#define CK(h, call)                                                      \
+  do {                                                                   \
+    cudaError_t _e = (call);                                             \
+    if (_e != cudaSuccess) FAIL(h, "%s: %s", #call, cudaGetErrorString(_e)); \
+  } while (0)
+
+static int stage(mcb_handle *h, void **slot, const void *src, size_t bytes) {
+  CK(h, cudaSetDevice(h->device));
+  if (*slot) { cudaFree(*slot); *slot = nullptr; }
+  CK(h, cudaMalloc(slot, bytes ? bytes : 16));
+  if (src && bytes) CK(h, cudaMemcpyAsync(*slot, src, bytes, cudaMemcpyHostToDevice, h->stream));
+  CK(h, cudaStreamSynchronize(h->stream));       // the library never retains the host pointer
+  return 0;
+}
+
+static double sp64h(double x) {
+  x = std::fabs(x);
+  if (x == 0.0) return 2.2250738585072014e-308;
+  double s = std::nextafter(x, INFINITY) - x;
+  return s < 2.2250738585072014e-308 ? 2.2250738585072014e-308 : s;
+}
+
+extern "C" {
+
+int mcb_version(void) { return 100; }
+
+void mcb_default_options(mcb_options *o) {          // INT:53-96
+  memset(o, 0, sizeof(*o));
+  o->useRayTracing = 1; o->useRussianRoulette = 1; o->russianRouletteW = 1.0f;
+  o->useRussianRouletteForIntensity = 0; o->zetaMin = 0.3f;
+  o->useHybridPhaseFunsForIntenCalcs = 0; o->numOrdersOrigPhaseFunIntenCalcs = 0;
+  o->limitIntensityContributions = 0; o->maxIntensityContribution = 3.402823466e+38f;
+  o->LW_flag = -1.0f; o->arithmetic = MCB_ARITH_FAST;
+}
+
+int mcb_create(int device, mcb_handle **out) {
+  if (!out) return 1;
+  *out = nullptr;
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || count <= 0) return 2;   // no CPU fallback
+  if (device < 0 || device >= count) return 3;
+  mcb_handle *h = new mcb_handle();
+  h->device = device;
+  memset(&h->P, 0, sizeof(h->P));
+  mcb_default_options(&h->P.opt);
+  if (cudaSetDevice(device) != cudaSuccess) { delete h; return 4; }
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) h->numSMs = prop.multiProcessorCount;
+  if (cudaStreamCreateWithFlags(&h->ownStream, cudaStreamNonBlocking) != cudaSuccess) { delete h; return 5; }
+  h->stream = h->ownStream;
+  cudaEventCreate(&h->evStart); cudaEventCreate(&h->evStop);
+  if (cudaMalloc((void **)&h->dCounters, sizeof(unsigned long long) * 32) != cudaSuccess) { delete h; return 6; }
+  cudaMemset(h->dCounters, 0, sizeof(unsigned long long) * 32);
+  h->P.counters = h->dCounters;
+  *out = h;
+  return 0;
+}
+
+int mcb_destroy(mcb_handle *h) {
+  if (!h) return 0;
+  cudaSetDevice(h->device);
+  cudaStreamSynchronize(h->stream);
+  void *slots[] = {h->dXE, h->dYE, h->dZE, h->dTotalExt, h->dCumExt, h->dSsa, h->dPhaseIdx,
+                   h->dExt32, h->dCum32, h->dSsa32, h->dIdx16, h->dVoxelCDF, h->dTally, h->dCounters};
+  for (void *p : slots) if (p) cudaFree(p);
+  for (int c = 0; c < MCB_MAX_COMP; ++c) {
+    if (h->dInv[c]) cudaFree(h->dInv[c]);
+    if (h->dFwd[c]) cudaFree(h->dFwd[c]);
+    if (h->dFwdOrig[c]) cudaFree(h->dFwdOrig[c]);
+  }
+  if (h->hTally) cudaFreeHost(h->hTally);
+  cudaEventDestroy(h->evStart); cudaEventDestroy(h->evStop);
+  cudaStreamDestroy(h->ownStream);
+  delete h;
+  return 0;
+}
+
+int mcb_last_error(const mcb_handle *h, char *buf, int len) {
+  if (!buf || len <= 0) return 1;
+  const char *s = h ? h->err.c_str() : "invalid handle";
+  snprintf(buf, (size_t)len, "%s", s);
+  return 0;
+}
+
+int mcb_set_stream(mcb_handle *h, void *cudaStream) {
+  if (!h) return 1;
+  h->stream = cudaStream ? (cudaStream_t)cudaStream : h->ownStream;
+  return 0;
+}
+
+int mcb_synchronize(mcb_handle *h) {
+  if (!h) return 1;
+  CK(h, cudaSetDevice(h->device));
+  CK(h, cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+int mcb_set_grid(mcb_handle *h, int nx, int ny, int nz,
+                 const double *xEdges, const double *yEdges, const double *zEdges) {
+  if (!h) return 1;
+  if (nx < 1 || ny < 1 || nz < 1 || !xEdges || !yEdges || !zEdges) FAIL(h, "mcb_set_grid: bad arguments");
+  for (int i = 0; i < nx; ++i) if (!(xEdges[i + 1] > xEdges[i])) FAIL(h, "new_Domain: Positions must be increasing, unique.");
+  for (int i = 0; i < ny; ++i) if (!(yEdges[i + 1] > yEdges[i])) FAIL(h, "new_Domain: Positions must be increasing, unique.");
+  for (int i = 0; i < nz; ++i) if (!(zEdges[i + 1] > zEdges[i])) FAIL(h, "new_Domain: Positions must be increasing, unique.");
+  h->xE.assign(xEdges, xEdges + nx + 1); h->yE.assign(yEdges, yEdges + ny + 1); h->zE.assign(zEdges, zEdges + nz + 1);
+  if (stage(h, &h->dXE, xEdges, sizeof(double) * (nx + 1))) return 1;
+  if (stage(h, &h->dYE, yEdges, sizeof(double) * (ny + 1))) return 1;
+  if (stage(h, &h->dZE, zEdges, sizeof(double) * (nz + 1))) return 1;
+  DevDomain &P = h->P;
+  P.nx = nx; P.ny = ny; P.nz = nz;
+  P.xE = (const double *)h->dXE; P.yE = (const double *)h->dYE; P.zE = (const double *)h->dZE;
+  P.x0 = xEdges[0]; P.y0 = yEdges[0]; P.z0 = zEdges[0];
+  P.xMax = xEdges[nx]; P.yMax = yEdges[ny]; P.zMax = zEdges[nz];
+  // new_Integrator INT:163-181: spacing held in default-real locals (quirk q1)
+  const float deltaX = (float)(xEdges[1] - xEdges[0]), deltaY = (float)(yEdges[1] - yEdges[0]),
+              deltaZ = (float)(zEdges[1] - zEdges[0]);
+  bool xyReg = true, zReg = true;
+  for (int i = 0; i < nx; ++i)
+    if (!(std::fabs((xEdges[i + 1] - xEdges[i]) - (double)deltaX) <= 2.0 * sp64h(xEdges[i + 1]))) xyReg = false;
+  for (int i = 0; i < ny; ++i)
+    if (!(std::fabs((yEdges[i + 1] - yEdges[i]) - (double)deltaY) <= 2.0 * sp64h(yEdges[i + 1]))) xyReg = false;
+  for (int i = 0; i < nz; ++i)
+    if (!(std::fabs((zEdges[i + 1] - zEdges[i]) - (double)deltaZ) <= sp64h(zEdges[i + 1]))) zReg = false;
+  P.xyRegular = xyReg ? 1 : 0; P.zRegular = zReg ? 1 : 0;
+  P.deltaX = xyReg ? (double)deltaX : 0.0; P.deltaY = xyReg ? (double)deltaY : 0.0;
+  P.deltaZ = zReg ? (double)deltaZ : 0.0;
+  P.invDx = xyReg ? 1.0f / deltaX : 0.0f; P.invDy = xyReg ? 1.0f / deltaY : 0.0f;
+  P.invDz = zReg ? 1.0f / deltaZ : 0.0f;
+  h->haveGrid = true; h->haveOptics = false; h->haveSource = false;
+  return 0;
+}
+
+int mcb_set_optics(mcb_handle *h, int nc, const double *totalExt, const double *cumExt,
+                   const double *ssa, const int32_t *phaseIdx, double albedo) {
+  if (!h) return 1;
+  if (!h->haveGrid) FAIL(h, "mcb_set_optics: call mcb_set_grid first");
+  if (nc < 1 || nc > MCB_MAX_COMP) FAIL(h, "mcb_set_optics: number of components must be 1..%d", MCB_MAX_COMP);
+  if (!totalExt || !cumExt || !ssa || !phaseIdx) FAIL(h, "mcb_set_optics: null array");
+  DevDomain &P = h->P;
+  const size_t cells = (size_t)P.nx * P.ny * P.nz;
+  for (size_t i = 0; i < cells; ++i) if (!(totalExt[i] >= 0.0)) FAIL(h, "addOpticalComponent: extinction must be >= 0.");
+  for (size_t i = 0; i < cells * nc; ++i) {
+    if (!(ssa[i] >= 0.0 && ssa[i] <= 1.0)) FAIL(h, "addOpticalComponent: singleScatteringAlbedo must be between 0 and 1");
+    if (phaseIdx[i] < 0 || phaseIdx[i] > 65535) FAIL(h, "addOpticalComponent: phase function index is out of bounds");
+  }
+  if (stage(h, &h->dTotalExt, totalExt, sizeof(double) * cells)) return 1;
+  if (stage(h, &h->dCumExt, cumExt, sizeof(double) * cells * nc)) return 1;
+  if (stage(h, &h->dSsa, ssa, sizeof(double) * cells * nc)) return 1;
+  if (stage(h, &h->dPhaseIdx, phaseIdx, sizeof(int32_t) * cells * nc)) return 1;
+  {  // packed single-precision copies for the fast kernel
+    std::vector<float> e32(cells), c32(cells * nc), s32(cells * nc);
+    std::vector<uint16_t> i16(cells * nc);
+    for (size_t i = 0; i < cells; ++i) e32[i] = (float)totalExt[i];
+    for (size_t i = 0; i < cells * nc; ++i) { c32[i] = (float)cumExt[i]; s32[i] = (float)ssa[i]; i16[i] = (uint16_t)phaseIdx[i]; }
+    if (stage(h, &h->dExt32, e32.data(), sizeof(float) * cells)) return 1;
+    if (stage(h, &h->dCum32, c32.data(), sizeof(float) * cells * nc)) return 1;
+    if (stage(h, &h->dSsa32, s32.data(), sizeof(float) * cells * nc)) return 1;
+    if (stage(h, &h->dIdx16, i16.data(), sizeof(uint16_t) * cells * nc)) return 1;
+  }
+  P.nc = nc; P.albedo = albedo;
+  P.totalExt = (const double *)h->dTotalExt; P.cumExt = (const double *)h->dCumExt;
+  P.ssa = (const double *)h->dSsa; P.phaseIdx = (const int32_t *)h->dPhaseIdx;
+  P.ext32 = (const float *)h->dExt32; P.cum32 = (const float *)h->dCum32;
+  P.ssa32 = (const float *)h->dSsa32; P.idx16 = (const uint16_t *)h->dIdx16;
+  for (int c = 0; c < MCB_MAX_COMP; ++c) { h->haveInv[c] = false; h->haveFwd[c] = false; }
+  h->haveOptics = true;
+  return 0;
+}
+
+int mcb_set_inverse_table(mcb_handle *h, int comp, int nS, int nE, const float *T) {
+  if (!h) return 1;
+  if (!h->haveOptics) FAIL(h, "mcb_set_inverse_table: call mcb_set_optics first");
+  if (comp < 1 || comp > h->P.nc || nS < 2 || nE < 1 || !T) FAIL(h, "mcb_set_inverse_table: bad arguments");
+  const int c = comp - 1;
+  if (stage(h, &h->dInv[c], T, sizeof(float) * (size_t)nS * nE)) return 1;
+  h->P.inv[c] = (const float *)h->dInv[c]; h->P.invS[c] = nS; h->invE[c] = nE; h->haveInv[c] = true;
+  return 0;
+}
+
+int mcb_set_forward_table(mcb_handle *h, int comp, int nS, int nE, const float *Pf, const float *Porig) {
+  if (!h) return 1;
+  if (!h->haveOptics) FAIL(h, "mcb_set_forward_table: call mcb_set_optics first");
+  if (comp < 1 || comp > h->P.nc || nS < 2 || nE < 1 || !Pf) FAIL(h, "mcb_set_forward_table: bad arguments");
+  const int c = comp - 1;
+  if (stage(h, &h->dFwd[c], Pf, sizeof(float) * (size_t)nS * nE)) return 1;
+  if (stage(h, &h->dFwdOrig[c], Porig ? Porig : Pf, sizeof(float) * (size_t)nS * nE)) return 1;
+  h->P.fwd[c] = (const float *)h->dFwd[c]; h->P.fwdOrig[c] = (const float *)h->dFwdOrig[c];
+  h->P.fwdS[c] = nS; h->fwdE[c] = nE; h->haveFwd[c] = true;
+  return 0;
+}
+
+int mcb_set_views(mcb_handle *h, int nDir, const float *dirCos) {
+  if (!h) return 1;
+  if (nDir < 0 || nDir > MCB_MAX_DIR) FAIL(h, "specifyParameters: at most %d intensity directions", MCB_MAX_DIR);
+  if (nDir > 0 && !dirCos) FAIL(h, "specifyParameters: Can't compute intensity without specifying directions.");
+  for (int i = 0; i < nDir; ++i)
+    if (std::fabs(dirCos[3 * i + 2]) < 1.17549435e-38f)
+      FAIL(h, "specifyParameters: intensityMus can't be 0 (directly sideways)");
+  h->P.nDir = nDir;
+  for (int i = 0; i < 3 * nDir; ++i) h->P.viewDir[i] = dirCos[i];
+  return 0;
+}
+
+int mcb_set_options(mcb_handle *h, const mcb_options *o) {
+  if (!h || !o) return 1;
+  if (!o->useRayTracing) FAIL(h, "specifyParameters: useRayTracing=.false. (maximum cross-section) is not implemented");
+  if (o->zetaMin < 0.0f) FAIL(h, "specifyParameters: zetaMin must be >= 0.");
+  if (o->arithmetic != MCB_ARITH_FAST && o->arithmetic != MCB_ARITH_REFERENCE) FAIL(h, "mcb_set_options: unknown arithmetic mode");
+  h->P.opt = *o;
+  return 0;
+}
+
+int mcb_set_solar_source(mcb_handle *h, float solarMu, float solarAzimuthDeg) {   // ILL:62-101
+  if (!h) return 1;
+  if (solarAzimuthDeg < 0.0f || solarAzimuthDeg > 360.0f) FAIL(h, "setIllumination: solarAzimuth out of bounds");
+  if (std::fabs(solarMu) > 1.0f || std::fabs(solarMu) <= 1.17549435e-38f) FAIL(h, "setIllumination: solarMu out of bounds");
+  h->P.source = 0;
+  h->P.solarMu = -std::fabs(solarMu);                                             // ILL:95
+  const float pi32 = (float)std::acos(-1.0);
+  volatile float t = solarAzimuthDeg * pi32;                                      // ILL:96, single precision
+  h->P.solarPhi = t / 180.0f;
+  h->haveSource = true;
+  return 0;
+}
+
+int mcb_set_thermal_source(mcb_handle *h, double fracAtmsPower, const double *voxelCDF) {  // ILL:431-522
+  if (!h) return 1;
+  if (!h->haveGrid) FAIL(h, "mcb_set_thermal_source: call mcb_set_grid first");
+  if (!voxelCDF) FAIL(h, "mcb_set_thermal_source: null CDF");
+  const size_t cells = (size_t)h->P.nx * h->P.ny * h->P.nz;
+  if (stage(h, &h->dVoxelCDF, voxelCDF, sizeof(double) * cells)) return 1;
+  h->P.source = 1; h->P.fracAtmsPower = fracAtmsPower; h->P.voxelCDF = (const double *)h->dVoxelCDF;
+  h->haveSource = true;
+  return 0;
+}
+
+// emission_weightingNEW EMI:424-550 on the staged optics.  Setup-time staging code: the
+// Kahan prefix sum runs on the host over arrays read back from HBM.
+int mcb_build_thermal_source(mcb_handle *h, const double *temps, double lambda_um,
+                             double surfaceTemp, double *fracAtmsPowerOut, double *totalFluxOut) {
+  if (!h) return 1;
+  if (!h->haveOptics) FAIL(h, "emission_weighting: domain hasn't been initialized.");
+  if (!temps) FAIL(h, "emission_weighting: null temperature array");
+  const DevDomain &P = h->P;
+  const int nx = P.nx, ny = P.ny, nz = P.nz, nc = P.nc;
+  const size_t cells = (size_t)nx * ny * nz;
+  std::vector<double> totalExt(cells), cumExt(cells * nc), ssa(cells * nc), cdf(cells, 0.0);
+  CK(h, cudaSetDevice(h->device));
+  CK(h, cudaMemcpy(totalExt.data(), P.totalExt, sizeof(double) * cells, cudaMemcpyDeviceToHost));
+  CK(h, cudaMemcpy(cumExt.data(), P.cumExt, sizeof(double) * cells * nc, cudaMemcpyDeviceToHost));
+  CK(h, cudaMemcpy(ssa.data(), P.ssa, sizeof(double) * cells * nc, cudaMemcpyDeviceToHost));
+  const double hP = 6.62606957e-34, cL = 2.99792458e+8, kB = 1.3806488e-23;
+  const double a = 2.0 * hP * (cL * cL);
+  const double Pi = 4.0 * std::atan(1.0);
+  const double emiss = 1.0 - P.albedo;
+  const double lambda = lambda_um / 1.0e6;
+  const double b = hP * cL / (kB * lambda);
+  const double areaX = h->xE[nx] - h->xE[0], areaY = h->yE[ny] - h->yE[0];
+  double sfcPower = 0.0;
+  if (!(emiss == 0.0 || surfaceTemp == 0.0)) {
+    const double sfcPlanckRad = (a / (std::pow(lambda, 5.0) * (std::exp(b / surfaceTemp) - 1.0))) / 1.0e6;
+    sfcPower = Pi * emiss * sfcPlanckRad * areaX * areaY * (1000.0 * 1000.0);
+  }
+  bool anyCold = false;
+  for (size_t i = 0; i < cells; ++i) if (temps[i] <= 0.0) anyCold = true;
+  double previous = 0.0, corr = 0.0;
+  if (!anyCold) {
+    for (int iz = 0; iz < nz; ++iz) {
+      const double dz = h->zE[iz + 1] - h->zE[iz];
+      for (size_t k = 0; k < (size_t)nx * ny; ++k) {
+        const size_t cell = k + (size_t)nx * ny * iz;
+        const double planck = (a / (std::pow(lambda, 5.0) * (std::exp(b / temps[cell]) - 1.0))) / 1.0e6;
+        double sumSsaExt = 0.0;
+        for (int j = 0; j < nc; ++j) {
+          const double extj = j == 0 ? totalExt[cell] * cumExt[cell]
+                                     : totalExt[cell] * (cumExt[cell + cells * j] - cumExt[cell + cells * (j - 1)]);
+          sumSsaExt += ssa[cell + cells * j] * extj;
+        }
+        const double totalAbsCoef = totalExt[cell] - sumSsaExt;
+        const double corr_contrib = (4.0 * Pi * planck * totalAbsCoef * dz) - corr;      // Kahan, EMI:505-509
+        const double temp_sum = previous + corr_contrib;
+        corr = (temp_sum - previous) - corr_contrib;
+        previous = temp_sum;
+        cdf[cell] = previous;
+      }
+    }
+  }
+  double atmsPower = 0.0, frac = 0.0;
+  const double last = cdf[cells - 1];
+  if (last > 0.0) {                                                                       // EMI:512-521
+    atmsPower = last * areaX * areaY * (1000.0 * 1000.0) / (double)(nx * ny);
+    for (size_t i = 0; i < cells; ++i) cdf[i] = cdf[i] / last;
+    cdf[cells - 1] = 1.0;
+    frac = atmsPower / (atmsPower + sfcPower);
+  }
+  if (atmsPower + sfcPower == 0.0)
+    FAIL(h, "emission_weightingNEW: Neither surface nor atmosphere will emitt photons since total power is 0. Not a valid solution");
+  if (fracAtmsPowerOut) *fracAtmsPowerOut = frac;
+  if (totalFluxOut) *totalFluxOut = (atmsPower + sfcPower) / (areaX * areaY * (1000.0 * 1000.0));
+  return mcb_set_thermal_source(h, frac, cdf.data());
+}
+
+static int ensure_tallies(mcb_handle *h) {
+  DevDomain &P = h->P;
+  const long long cols = (long long)P.nx * P.ny, cells = cols * P.nz;
+  P.offFluxUp = 0; P.offFluxDown = cols; P.offFluxAbs = 2 * cols; P.offVolAbs = 3 * cols;
+  P.offInt = P.offVolAbs + cells;
+  P.offIntByComp = P.offInt + cols * P.nDir;
+  P.offExcess = P.offIntByComp + cols * P.nDir * (P.nc + 1);
+  P.offPhotons = P.offExcess + (long long)P.nDir * (P.nc + 1);
+  const long long need = P.offPhotons + 1;
+  if (need != h->nTally || !h->dTally) {
+    if (h->dTally) cudaFree(h->dTally);
+    h->dTally = nullptr;
+    CK(h, cudaMalloc((void **)&h->dTally, sizeof(double) * need));
+    CK(h, cudaMemsetAsync(h->dTally, 0, sizeof(double) * need, h->stream));
+    h->nTally = need;
+  }
+  P.tally = h->dTally;
+  return 0;
+}
+
+static int check_ready(mcb_handle *h) {
+  if (!h->haveGrid || !h->haveOptics) FAIL(h, "computeRadiativeTransfer: problem not completely specified.");
+  if (!h->haveSource) FAIL(h, "getNextPhoton: photons have not been initialized.");
+  for (int c = 0; c < h->P.nc; ++c) {
+    if (!h->haveInv[c]) FAIL(h, "computeRadiativeTransfer: no inverse phase function table for component %d", c + 1);
+    if (h->P.nDir > 0 && !h->haveFwd[c]) FAIL(h, "computeRadiativeTransfer: no forward phase function table for component %d", c + 1);
+  }
+  return 0;
+}
+
+static int run(mcb_handle *h, long long nPhotons, uint64_t seed, uint64_t firstPhotonId, bool zero, int64_t *nProcessed) {
+  if (!h) return 1;
+  if (nProcessed) *nProcessed = 0;
+  if (check_ready(h)) return 1;
+  if (nPhotons < 0) FAIL(h, "setIllumination: must ask for non-negative number of photons.");
+  CK(h, cudaSetDevice(h->device));
+  if (ensure_tallies(h)) return 1;
+  DevDomain &P = h->P;
+  if (zero) {                                                    // INT:247-272
+    CK(h, cudaMemsetAsync(h->dTally, 0, sizeof(double) * h->nTally, h->stream));
+    CK(h, cudaMemsetAsync(h->dCounters, 0, sizeof(unsigned long long) * 32, h->stream));
+  } else {
+    CK(h, cudaMemsetAsync(h->dCounters + CNT_N, 0, sizeof(unsigned long long), h->stream));
+  }
+  if (nPhotons == 0) FAIL(h, "computeRadiativeTransfer: Didn't process any photons.");   // INT:835-836
+  CK(h, cudaEventRecord(h->evStart, h->stream));
+  if (P.opt.arithmetic == MCB_ARITH_REFERENCE)
+    mcb_launch_reference_batch(P, nPhotons, seed, firstPhotonId, h->numSMs, h->stream);
+  else
+    mcb_launch_fast_batch(P, nPhotons, seed, firstPhotonId, h->numSMs, h->dCounters + CNT_N, h->stream);
+  CK(h, cudaGetLastError());
+  CK(h, cudaEventRecord(h->evStop, h->stream));
+  h->timed = true;
+  if (nProcessed) *nProcessed = nPhotons;
+  return 0;
+}
+
+int mcb_run_batch(mcb_handle *h, int64_t nPhotons, uint64_t seed, uint64_t firstPhotonId, int64_t *nProcessed) {
+  return run(h, nPhotons, seed, firstPhotonId, true, nProcessed);
+}
+int mcb_accumulate_batch(mcb_handle *h, int64_t nPhotons, uint64_t seed, uint64_t firstPhotonId, int64_t *nProcessed) {
+  return run(h, nPhotons, seed, firstPhotonId, false, nProcessed);
+}
+
+int mcb_last_batch_ms(mcb_handle *h, float *ms) {
+  if (!h || !ms) return 1;
+  if (!h->timed) FAIL(h, "mcb_last_batch_ms: no batch has run");
+  CK(h, cudaSetDevice(h->device));
+  CK(h, cudaEventSynchronize(h->evStop));
+  CK(h, cudaEventElapsedTime(ms, h->evStart, h->evStop));
+  return 0;
+}
+
+int mcb_get_counters(mcb_handle *h, mcb_counters *c) {
+  if (!h || !c) return 1;
+  CK(h, cudaSetDevice(h->device));
+  CK(h, cudaStreamSynchronize(h->stream));
+  unsigned long long v[CNT_N];
+  CK(h, cudaMemcpy(v, h->dCounters, sizeof(v), cudaMemcpyDeviceToHost));
+  memset(c, 0, sizeof(*c));
+  c->photons = (int64_t)v[CNT_PHOTONS]; c->crossings = (int64_t)v[CNT_CROSSINGS];
+  c->scatters = (int64_t)v[CNT_SCATTERS]; c->surfaceHits = (int64_t)v[CNT_SURFACE];
+  c->topExits = (int64_t)v[CNT_TOP]; c->bad = (int64_t)v[CNT_BAD];
+  c->leRays = (int64_t)v[CNT_LE_RAYS]; c->leCrossings = (int64_t)v[CNT_LE_CROSSINGS];
+  c->rouletteKills = (int64_t)v[CNT_RR_KILLS];
+  return 0;
+}
+
+int mcb_tally_buffer(mcb_handle *h, void **devicePtr, int64_t *nDoubles) {
+  if (!h) return 1;
+  if (!h->haveGrid || !h->haveOptics) FAIL(h, "mcb_tally_buffer: problem not completely specified.");
+  CK(h, cudaSetDevice(h->device));
+  if (ensure_tallies(h)) return 1;
+  if (devicePtr) *devicePtr = (void *)h->dTally;
+  if (nDoubles) *nDoubles = h->nTally;
+  return 0;
+}
+
+static int fetch_tallies(mcb_handle *h) {
+  CK(h, cudaSetDevice(h->device));
+  if (!h->dTally) FAIL(h, "reportResults: no results available");
+  if (h->hTallyCap < h->nTally) {
+    if (h->hTally) cudaFreeHost(h->hTally);
+    h->hTally = nullptr;
+    CK(h, cudaMallocHost((void **)&h->hTally, sizeof(double) * h->nTally));
+    h->hTallyCap = h->nTally;
+  }
+  CK(h, cudaMemcpyAsync(h->hTally, h->dTally, sizeof(double) * h->nTally, cudaMemcpyDeviceToHost, h->stream));
+  CK(h, cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+int mcb_get_raw_tallies(mcb_handle *h, double *out, int64_t nDoubles) {
+  if (!h || !out) return 1;
+  if (fetch_tallies(h)) return 1;
+  if (nDoubles < h->nTally) FAIL(h, "mcb_get_raw_tallies: buffer too small (%lld needed)", h->nTally);
+  memcpy(out, h->hTally, sizeof(double) * h->nTally);
+  return 0;
+}
+
+int mcb_get_results(mcb_handle *h, int64_t nPhotonsNormalise,
+                    float *fluxUp, float *fluxDown, float *fluxAbsorbed,
+                    float *volumeAbsorption, float *intensity, float *intensityByComponent) {
+  if (!h) return 1;
+  if (fetch_tallies(h)) return 1;
+  const DevDomain &P = h->P;
+  double *T = h->hTally;
+  const int numX = P.nx, numY = P.ny, numZ = P.nz, nDir = P.nDir, nc = P.nc;
+  const size_t cols = (size_t)numX * numY;
+  const double numPhotonsProcessed = nPhotonsNormalise > 0 ? (double)nPhotonsNormalise : T[P.offPhotons];
+  if (!(numPhotonsProcessed > 0)) FAIL(h, "computeRadiativeTransfer: Didn't process any photons.");
+  if ((intensity || intensityByComponent) && nDir == 0) FAIL(h, "reportResults: intensity information not available");
+
+  if (nDir > 0 && P.opt.limitIntensityContributions) {           // INT:294-322
+    for (int j = 0; j <= nc; ++j)
+      for (int d = 0; d < nDir; ++d) {
+        const double excess = T[P.offExcess + d + (long long)nDir * j];
+        if (excess > 0.0) {
+          double *byc = T + P.offIntByComp + cols * ((size_t)d + (size_t)nDir * j);
+          double s = 0.0;
+          for (size_t i = 0; i < cols; ++i) s += byc[i];
+          for (size_t i = 0; i < cols; ++i) {
+            const double add = (byc[i] / s) * excess;
+            T[P.offInt + i + cols * d] += add;
+            byc[i] += add;
+          }
+          T[P.offExcess + d + (long long)nDir * j] = 0.0;
+        }
+      }
+  }
+  // numPhotonsPerColumn, default real (INT:328-343, quirk q11)
+  std::vector<float> nppc(cols);
+  if (P.xyRegular) {
+    const float v = (float)numPhotonsProcessed / (float)(numX * numY);
+    for (size_t i = 0; i < cols; ++i) nppc[i] = v;
+  } else {
+    for (int j = 0; j < numY; ++j)
+      for (int i = 0; i < numX; ++i) {
+        const float frac = (float)(((h->yE[j + 1] - h->yE[j]) * (h->xE[i + 1] - h->xE[i])) /
+                                   ((h->xE[numX] - h->xE[0]) * (h->yE[numY] - h->yE[0])));
+        nppc[i + (size_t)numX * j] = frac * (float)numPhotonsProcessed;
+      }
+  }
+  if (fluxUp) for (size_t i = 0; i < cols; ++i) fluxUp[i] = (float)T[P.offFluxUp + i] / nppc[i];            // INT:348-350
+  if (fluxDown) for (size_t i = 0; i < cols; ++i) fluxDown[i] = (float)T[P.offFluxDown + i] / nppc[i];
+  if (fluxAbsorbed) for (size_t i = 0; i < cols; ++i) fluxAbsorbed[i] = (float)T[P.offFluxAbs + i] / nppc[i];
+  if (volumeAbsorption)                                                                                    // INT:361-364
+    for (int k = 0; k < numZ; ++k) {
+      const double dz = h->zE[k + 1] - h->zE[k];
+      for (size_t i = 0; i < cols; ++i)
+        volumeAbsorption[i + cols * k] =
+            (float)((double)(float)T[P.offVolAbs + i + cols * k] / ((double)nppc[i] * dz * (double)1000.0f));
+    }
+  if (intensity)                                                                                           // INT:369-372
+    for (int d = 0; d < nDir; ++d)
+      for (size_t i = 0; i < cols; ++i) intensity[i + cols * d] = (float)T[P.offInt + i + cols * d] / nppc[i];
+  if (intensityByComponent)                                                  // INT:375-379: component 0 is NOT normalised (q12)
+    for (int j = 0; j <= nc; ++j)
+      for (int d = 0; d < nDir; ++d)
+        for (size_t i = 0; i < cols; ++i) {
+          const size_t k = i + cols * ((size_t)d + (size_t)nDir * j);
+          const float raw = (float)T[P.offIntByComp + k];
+          intensityByComponent[k] = j == 0 ? raw : raw / nppc[i];
+        }
+  return 0;
+}
+
+int mcb_run_trace(mcb_handle *h, int64_t nPhotons, const float *rn, int64_t rnStride,
+                  int32_t maxEventsPerPhoton, mcb_event *events, int64_t eventCap, int64_t *nEvents) {
+  if (!h) return 1;
+  if (nEvents) *nEvents = 0;
+  if (check_ready(h)) return 1;
+  if (nPhotons <= 0 || !rn || rnStride <= 0 || maxEventsPerPhoton <= 0 || !events) FAIL(h, "mcb_run_trace: bad arguments");
+  CK(h, cudaSetDevice(h->device));
+  if (ensure_tallies(h)) return 1;
+  CK(h, cudaMemsetAsync(h->dTally, 0, sizeof(double) * h->nTally, h->stream));
+  CK(h, cudaMemsetAsync(h->dCounters, 0, sizeof(unsigned long long) * 32, h->stream));
+  float *dRn = nullptr; mcb_event *dEv = nullptr; int *dCount = nullptr;
+  const size_t nRn = (size_t)nPhotons * rnStride, nEv = (size_t)nPhotons * maxEventsPerPhoton;
+  CK(h, cudaMalloc((void **)&dRn, sizeof(float) * nRn));
+  CK(h, cudaMalloc((void **)&dEv, sizeof(mcb_event) * nEv));
+  CK(h, cudaMalloc((void **)&dCount, sizeof(int) * nPhotons));
+  CK(h, cudaMemcpyAsync(dRn, rn, sizeof(float) * nRn, cudaMemcpyHostToDevice, h->stream));
+  CK(h, cudaMemsetAsync(dCount, 0, sizeof(int) * nPhotons, h->stream));
+  mcb_launch_trace(h->P, nPhotons, dRn, rnStride, dEv, maxEventsPerPhoton, dCount, h->stream);
+  CK(h, cudaGetLastError());
+  std::vector<int> count((size_t)nPhotons);
+  std::vector<mcb_event> ev(nEv);
+  CK(h, cudaMemcpyAsync(count.data(), dCount, sizeof(int) * nPhotons, cudaMemcpyDeviceToHost, h->stream));
+  CK(h, cudaMemcpyAsync(ev.data(), dEv, sizeof(mcb_event) * nEv, cudaMemcpyDeviceToHost, h->stream));
+  CK(h, cudaStreamSynchronize(h->stream));
+  cudaFree(dRn); cudaFree(dEv); cudaFree(dCount);
+  int64_t total = 0;
+  for (int64_t p = 0; p < nPhotons; ++p) {
+    const int n = count[p] < maxEventsPerPhoton ? count[p] : maxEventsPerPhoton;
+    for (int k = 0; k < n; ++k) {
+      if (total < eventCap) events[total] = ev[(size_t)p * maxEventsPerPhoton + k];
+      total++;
+    }
+  }
+  if (nEvents) *nEvents = total;
+  {  // photons started, for mcb_get_results on traced batches
+    const double np = (double)nPhotons;
+    CK(h, cudaMemcpy(h->dTally + h->P.offPhotons, &np, sizeof(double), cudaMemcpyHostToDevice));
+  }
+  return 0;
+}
+
+// debugging aid used by the tests: the raw Philox4x32-10 stream of one photon
+int mcb_debug_philox(mcb_handle *h, uint64_t seed, uint64_t photon, int n, uint32_t *out) {
+  if (!h || !out || n <= 0) return 1;
+  CK(h, cudaSetDevice(h->device));
+  uint32_t *d = nullptr;
+  CK(h, cudaMalloc((void **)&d, sizeof(uint32_t) * n));
+  mcb_launch_philox_kat(seed, photon, n, d, h->stream);
+  CK(h, cudaGetLastError());
+  CK(h, cudaMemcpyAsync(out, d, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost, h->stream));
+  CK(h, cudaStreamSynchronize(h->stream));
+  cudaFree(d);
+  return 0;
+}
+
+}  // extern "C"
