@@ -42,7 +42,7 @@ struct InjectedReal {               // trace harness: numbers supplied by the ca
   const float *p; long long n, pos; bool ex; int nd;
   __device__ __forceinline__ float real() {
     nd++;
-    if (pos >= n) { ex = true; return 0.5f; }
+    if (pos >= n) { ex = true; return 0.25f; }
     return p[pos++];
   }
   __device__ __forceinline__ bool exhausted() const { return ex; }

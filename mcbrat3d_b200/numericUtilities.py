@@ -31,8 +31,9 @@ def spacing64(x):
 def findIndex(value, table, firstGuess=None) -> int:
     """``findIndex`` (NUM:206-315): 1-based i with table(i) <= value < table(i+1).
 
-    Hunt from ``firstGuess`` when given, then bisection; returns 0 below the table and
-    ``size(table)`` at or beyond its end, exactly like the reference.
+    Hunt from ``firstGuess`` when given, then bisection.  As in the reference: 0 below the table
+    (without a guess; with one the hunt never ends there), ``size(table)`` at or beyond its end
+    with a guess, ``size(table) - 1`` without.
     """
     n = len(table)
     if firstGuess is not None:

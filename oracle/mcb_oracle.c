@@ -121,7 +121,7 @@ double orc_rng_double(orc_rng *r) {                         /* RNG:277-292 */
 float orc_rng_real(orc_rng *r) {                            /* RNG:294-301 */
   r->ndrawn++;
   if (r->mode == 1) {
-    if (r->pos >= r->ninj) { r->exhausted = 1; return 0.5f; }
+    if (r->pos >= r->ninj) { r->exhausted = 1; return 0.25f; }
     return r->inj[r->pos++];
   }
   return (float)orc_rng_double(r);

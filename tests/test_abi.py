@@ -1,0 +1,75 @@
+"""The C-ABI library builds, loads and exports every symbol include/mcbrat_cuda.h declares.
+No compute call is made here (no GPU in this container)."""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import pytest
+
+from mcbrat3d_b200 import _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "mcbrat_cuda.h")
+
+
+def _declared():
+    text = open(HEADER).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(mcb_[a-z_0-9]+)\s*\(", text)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    if not os.path.exists(_lib.LIB_PATH):
+        subprocess.check_call(["make", "-C", os.path.dirname(_lib.LIB_PATH)], stdout=subprocess.DEVNULL,
+                              stderr=subprocess.DEVNULL)
+    return C.CDLL(_lib.LIB_PATH)
+
+
+def test_header_declares_what_the_binding_lists():
+    assert _declared() == sorted(_lib.EXPORTS)
+
+
+def test_library_exports_every_declared_symbol(lib):
+    for name in _declared():
+        assert hasattr(lib, name), "missing export " + name
+
+
+def test_only_sm_100a_code_is_embedded():
+    out = subprocess.run(["cuobjdump", "-lelf", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    archs = set(re.findall(r"sm_\d+a?", out))
+    assert archs == {"sm_100a"}, archs
+
+
+def test_struct_layouts_match_header():
+    assert C.sizeof(_lib.mcb_options) == 64
+    assert C.sizeof(_lib.mcb_counters) == 128
+    assert _lib.EVENT_DTYPE.itemsize == 96
+    assert _lib.EVENT_DTYPE.fields["path"][1] == 48 and _lib.EVENT_DTYPE.fields["dir"][1] == 80
+
+
+def test_create_fails_loudly_without_a_gpu(lib):
+    """No CPU fallback: without a CUDA device mcb_create reports an error and hands back no handle."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    h = C.c_void_p()
+    lib.mcb_create.argtypes = [C.c_int, C.POINTER(C.c_void_p)]
+    rc = lib.mcb_create(0, C.byref(h))
+    assert rc != 0 and not h.value
+    from mcbrat3d_b200 import domains
+    from mcbrat3d_b200.monteCarloRadiativeTransfer import new_Integrator
+    d, _ = domains.homogeneous_slab()
+    with pytest.raises(_lib.McbError):
+        new_Integrator(d)
+
+
+def test_product_never_imports_the_oracle():
+    """The oracle is test infrastructure: nothing under mcbrat3d_b200/ may reference it."""
+    pkg = os.path.join(ROOT, "mcbrat3d_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in text.lower(), os.path.join(dirpath, f)

@@ -1,0 +1,91 @@
+"""North-star criterion (a): with injected random numbers the CUDA reference-arithmetic kernel
+reproduces the oracle's cell indices, event sequence and table look-ups bit-exactly, and path
+lengths / weights within 1e-6 relative.  Everything goes through the C ABI."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from common import assert_events_equal, injected_randoms, oracle_weights, trace_cases
+from mcbrat3d_b200 import _lib
+from mcbrat3d_b200.monteCarloIllumination import new_PhotonStream
+from mcbrat3d_b200.monteCarloRadiativeTransfer import (finalize_Integrator, new_Integrator, specifyParameters,
+                                                       tracePhotons)
+from mcbrat3d_b200.RandomNumbersForMC import new_RandomNumberSequence
+
+pytestmark = pytest.mark.gpu
+
+CASES = trace_cases()
+
+
+@pytest.mark.parametrize("name,dom,case,source", CASES, ids=[c[0] for c in CASES])
+@pytest.mark.parametrize("views,rr", [(False, False), (True, False), (True, True)], ids=["flux", "le", "le_rr"])
+def test_trace_parity(orc, name, dom, case, source, views, rr):
+    g = new_Integrator(dom)
+    try:
+        if views:
+            mus = case.get("intensityMus", [1.0, 0.5]); phis = case.get("intensityPhis", [0.0, 0.0])
+            specifyParameters(g, intensityMus=mus, intensityPhis=phis, computeIntensity=True,
+                              useRussianRouletteForIntensity=rr, zetaMin=0.3)
+        specifyParameters(g, minInverseTableSize=10001, minForwardTableSize=10001,
+                          LW_flag=1.0 if source else -1.0)
+        od = orc.OracleDomain(dom, tableSize=10001, forward=views)
+        og = orc.OracleIntegrator(od, useRussianRouletteForIntensity=int(rr), zetaMin=0.3,
+                                  LW_flag=1.0 if source else -1.0)
+        if views:
+            og.set_view_cosines(g.intensityDirections)
+        n, stride = 1500, 400
+        rn = injected_randoms(n, stride, seed=hash(name) % 1000)
+        rs = new_RandomNumberSequence([10, 1, 0])
+        if source == 0:
+            ps = new_PhotonStream(case["solarMu"], case["solarAzimuth"], n, rs)
+            want = og.trace(rn, 0, case["solarMu"], case["solarAzimuth"], maxEvents=n * 1024)
+        else:
+            w = oracle_weights(orc, od, dom)
+            ps = new_PhotonStream(theseWeights=w, numberOfPhotons=n, randomNumbers=rs)
+            want = og.trace(rn, 1, fracAtmsPower=w.fracAtmsPower, voxelCDF=w.voxelWeights, maxEvents=n * 1024)
+        got, raw = tracePhotons(g, dom, ps, rn, maxEventsPerPhoton=1024)
+        assert len(want) > 5 * n
+        assert_events_equal(got, want, "%s views=%s rr=%s" % (name, views, rr))
+        # the tallies of the traced photons agree too (f64 sums on the GPU, f32 in the oracle)
+        ot = og.raw_tallies()
+        np.testing.assert_allclose(raw[: ot.size], ot, rtol=2e-5, atol=2e-4)
+        assert raw[-1] == n
+    finally:
+        finalize_Integrator(g)
+
+
+def test_trace_matches_committed_golden(orc):
+    """The committed fixture (tests/golden/trace_T_irr.npz, written by tests/golden/make_golden.py
+    from the oracle) pins both implementations against drift."""
+    import os
+    from mcbrat3d_b200 import domains
+    fx = np.load(os.path.join(os.path.dirname(__file__), "golden", "trace_T_irr.npz"))
+    dom, case = domains.irregular_test_domain()
+    g = new_Integrator(dom)
+    try:
+        specifyParameters(g, intensityMus=case["intensityMus"], intensityPhis=case["intensityPhis"],
+                          computeIntensity=True, minInverseTableSize=9001, minForwardTableSize=9001)
+        rs = new_RandomNumberSequence([10, 1, 0])
+        rn = fx["rn"]
+        ps = new_PhotonStream(case["solarMu"], case["solarAzimuth"], rn.shape[0], rs)
+        got, _ = tracePhotons(g, dom, ps, rn, maxEventsPerPhoton=1024)
+        assert_events_equal(got, fx["events"], "golden T_irr")
+    finally:
+        finalize_Integrator(g)
+
+
+def test_philox_known_answer():
+    """Philox4x32-10 KAT (Random123 kat_vectors): counter 0, key 0 -> 6627e8d5 e169c58d bc57ac4c 9b00dbd8;
+    counter/key all-ones -> 408f276d 41c83b0e a20bc7c6 6d5451fd."""
+    from mcbrat3d_b200 import domains
+    dom, _ = domains.homogeneous_slab()
+    g = new_Integrator(dom)
+    try:
+        out = (C.c_uint32 * 8)()
+        assert g._lib.mcb_debug_philox(g.handle, 0, 0, 8, out) == 0
+        assert [hex(v) for v in out[:4]] == ["0x6627e8d5", "0xe169c58d", "0xbc57ac4c", "0x9b00dbd8"]
+        # the next block bumps counter word 2 (draw block), not the photon id
+        assert list(out[4:]) != list(out[:4])
+    finally:
+        finalize_Integrator(g)

@@ -1,0 +1,145 @@
+"""Pin the oracle with physical invariants: the reference ships no fixtures, so
+these closed-form properties are what anchors the restatement of computeRT / the marcher."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from mcbrat3d_b200 import domains
+
+
+def _fin(orc, st, key, tot, nb):
+    m, e = orc.finalise(st[key], 1.0, tot, nb)
+    return m, e
+
+
+def test_energy_closure_solar(orc):
+    """Fup + (1 - A) Fdn + Fabs = 1 (INT:221-223: absorption agrees with the flux divergence)."""
+    d, case = domains.homogeneous_slab(ssa=0.99, albedo=0.2)
+    g = orc.OracleIntegrator(orc.OracleDomain(d, tableSize=9001))
+    nb = 16
+    tot, st = g.run_batches(nb, 5000, solarMu=0.5, solarAzimuth=0.0)
+    up, eu = _fin(orc, st, "meanFluxUpStats", tot, nb)
+    dn, ed = _fin(orc, st, "meanFluxDownStats", tot, nb)
+    ab, ea = _fin(orc, st, "meanFluxAbsorbedStats", tot, nb)
+    closure = up[0] + 0.8 * dn[0] + ab[0]
+    # Russian roulette makes the closure a statistical identity, not an exact one
+    assert abs(closure - 1.0) < 4.0 * np.sqrt(eu[0] ** 2 + (0.8 * ed[0]) ** 2 + ea[0] ** 2) + 1e-3
+
+
+def test_beer_law_direct_beam(orc):
+    """Pure absorber: every photon is absorbed at its first event, so Fdn = exp(-tau/mu0)."""
+    tau, mu0 = 2.0, 0.5
+    d, case = domains.homogeneous_slab(ssa=0.0, tau=tau, albedo=0.0)
+    g = orc.OracleIntegrator(orc.OracleDomain(d, tableSize=9001))
+    nb = 20
+    tot, st = g.run_batches(nb, 5000, solarMu=mu0, solarAzimuth=0.0)
+    dn, ed = _fin(orc, st, "meanFluxDownStats", tot, nb)
+    up, _ = _fin(orc, st, "meanFluxUpStats", tot, nb)
+    ab, _ = _fin(orc, st, "meanFluxAbsorbedStats", tot, nb)
+    want = np.exp(-tau / mu0)
+    assert abs(dn[0] - want) < 4.0 * ed[0] + 1e-4
+    assert up[0] == 0.0
+    assert abs(dn[0] + ab[0] - 1.0) < 1e-5           # no roulette variance here: weight 1 or 0
+
+
+def test_absorption_profile_sums_to_column_absorption(orc):
+    """sum_k volumeAbsorption(:,:,k) dz_k 1000 = fluxAbsorbed (INT:361-364 normalisation)."""
+    d, case = domains.homogeneous_slab(ssa=0.9, tau=4.0)
+    od = orc.OracleDomain(d, tableSize=9001)
+    g = orc.OracleIntegrator(od)
+    lib = orc.load()
+    rng = orc.orc_rng()
+    key = (C.c_uint32 * 3)(10, 1, 0)
+    lib.orc_rng_init_array(C.byref(rng), key, 3)
+    lib.orc_photons_directional.restype = C.c_void_p
+    lib.orc_photons_directional.argtypes = [C.c_float, C.c_float, C.c_int64, C.POINTER(orc.orc_rng)]
+    lib.orc_compute_radiative_transfer.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(orc.orc_rng), C.c_void_p,
+                                                   C.c_int64, C.c_int, C.POINTER(C.c_int64)]
+    lib.orc_report_results.argtypes = [C.c_void_p] + [C.POINTER(C.c_float)] * 10
+    ph = lib.orc_photons_directional(0.5, 0.0, 20000, C.byref(rng))
+    done = C.c_int64(0)
+    assert lib.orc_compute_radiative_transfer(g.ptr, od.ptr, C.byref(rng), ph, 20000, 1, C.byref(done)) == 0
+    assert done.value == 20000
+    n = 20
+    fab = np.zeros((n, n), np.float32); vol = np.zeros((n, n, n), np.float32); prof = np.zeros(n, np.float32)
+    mab = C.c_float(0)
+    lib.orc_report_results(g.ptr, None, None, C.byref(mab), None, None, fab.ctypes.data_as(C.POINTER(C.c_float)),
+                           prof.ctypes.data_as(C.POINTER(C.c_float)), vol.ctypes.data_as(C.POINTER(C.c_float)), None, None)
+    dz = 0.0625
+    np.testing.assert_allclose(vol.sum(axis=0) * dz * 1000.0, fab, rtol=2e-4, atol=1e-6)
+    np.testing.assert_allclose(prof.sum() * dz * 1000.0, mab.value, rtol=2e-4)
+
+
+def test_lw_isothermal_closure(orc):
+    """Isothermal medium over a black surface at the same temperature: net absorbed - emitted = 0
+    everywhere in expectation, i.e. mean fluxAbsorbed (with the -1 emission term, INT:505-508)
+    balances against what leaves through the top."""
+    d, case = domains.homogeneous_lw(ssa=0.5, tau=5.0, albedo=0.0, atmTemp=290.0, sfcTemp=290.0)
+    od = orc.OracleDomain(d, tableSize=9001)
+    frac, cdf, flux = od.emission_weighting(d.temps, d.lambda_um, 290.0)
+    assert 0.0 < frac < 1.0 and cdf[-1, -1, -1] == 1.0 and np.all(np.diff(cdf.ravel()) >= 0)
+    g = orc.OracleIntegrator(od, LW_flag=1.0)
+    nb = 16
+    tot, st = g.run_batches(nb, 5000, source=1, fracAtmsPower=frac, voxelCDF=cdf)
+    up, eu = _fin(orc, st, "meanFluxUpStats", tot, nb)
+    dn, ed = _fin(orc, st, "meanFluxDownStats", tot, nb)
+    ab, ea = _fin(orc, st, "meanFluxAbsorbedStats", tot, nb)
+    # photons: fraction `frac` born in the atmosphere (-1 each), all end absorbed, at the surface, or out the top
+    # energy bookkeeping: (absorbed in atmosphere - emitted by atmosphere) + surface absorption + escape = surface emission
+    closure = ab[0] + dn[0] + up[0]
+    assert abs(closure - (1.0 - frac)) < 4.0 * np.sqrt(eu[0] ** 2 + ed[0] ** 2 + ea[0] ** 2) + 2e-3
+    # isothermal + black surface: upwelling flux at the top equals the black-body flux, i.e. the
+    # escaping fraction of emitted power is pi B / (total emitted per unit area)
+    planck_flux_fraction = (1.0 - frac)          # surface emits pi*B*area; it is the (1-frac) share
+    assert abs(up[0] - planck_flux_fraction) < 4.0 * eu[0] + 5e-3
+
+
+def test_march_vertical_optical_depth(orc):
+    """A vertical ray through the slab accumulates exactly tau; oblique rays tau/mu; x/y wrap."""
+    lib = orc.load()
+    d, _ = domains.homogeneous_slab(ssa=1.0, tau=10.0)
+    od = orc.OracleDomain(d, tableSize=9001)
+    for mu, phi in ((-1.0, 0.0), (-0.5, 0.3), (-0.2, 2.0), (0.7, 4.0)):
+        dirv = np.zeros(3, np.float32)
+        lib.orc_make_direction_cosines(C.c_float(mu), C.c_float(phi), dirv.ctypes.data_as(C.POINTER(C.c_float)))
+        x, y = C.c_double(0.3), C.c_double(0.7)
+        z = C.c_double(1.25 - 1e-9 if mu < 0 else 1e-9)
+        ix, iy, iz = C.c_int(5), C.c_int(12), C.c_int(20 if mu < 0 else 1)
+        path, cross = C.c_double(0), C.c_int64(0)
+        ext = lib.orc_march(od.ptr, dirv.ctypes.data_as(C.POINTER(C.c_float)), C.byref(x), C.byref(y), C.byref(z),
+                            C.byref(ix), C.byref(iy), C.byref(iz), 0, 0.0, C.byref(path), C.byref(cross))
+        assert ext == pytest.approx(10.0 / abs(mu), rel=2e-6)
+        assert path.value == pytest.approx(1.25 / abs(mu), rel=1e-6)
+        assert (iz.value == 0) if mu < 0 else (iz.value == 21)
+        assert 1 <= ix.value <= 20 and 1 <= iy.value <= 20
+        assert 0.0 <= x.value <= 1.25 and 0.0 <= y.value <= 1.25
+
+
+def test_march_stops_at_target(orc):
+    lib = orc.load()
+    d, _ = domains.homogeneous_slab(ssa=1.0, tau=10.0)
+    od = orc.OracleDomain(d, tableSize=9001)
+    dirv = np.array([0.0, 0.0, -1.0], np.float32)
+    x, y, z = C.c_double(0.3), C.c_double(0.7), C.c_double(1.2)
+    ix, iy, iz = C.c_int(5), C.c_int(12), C.c_int(20)
+    path, cross = C.c_double(0), C.c_int64(0)
+    ext = lib.orc_march(od.ptr, dirv.ctypes.data_as(C.POINTER(C.c_float)), C.byref(x), C.byref(y), C.byref(z),
+                        C.byref(ix), C.byref(iy), C.byref(iz), 1, 3.0, C.byref(path), C.byref(cross))
+    assert ext == 3.0
+    assert z.value == pytest.approx(1.2 - 3.0 / 8.0, rel=1e-6)
+    assert iz.value == int((1.2 - 0.375) / 0.0625) + 1
+
+
+def test_regular_grid_detection_quirk_q1(orc):
+    """new_Integrator keeps the spacing in default reals (INT:140, 163-181): a grid counts as
+    regular only if its spacing is exactly representable in single precision."""
+    d, _ = domains.homogeneous_slab()
+    h = orc.OracleIntegrator(orc.OracleDomain(d, tableSize=9001)).head()
+    assert h.xyRegularlySpaced == 1 and h.zRegularlySpaced == 1 and h.deltaX == 0.0625
+    di, _ = domains.irregular_test_domain()
+    hi = orc.OracleIntegrator(orc.OracleDomain(di, tableSize=9001)).head()
+    assert hi.xyRegularlySpaced == 0 and hi.zRegularlySpaced == 0
+    dl, _ = domains.step_cloud()
+    hl = orc.OracleIntegrator(orc.OracleDomain(dl, tableSize=9001)).head()
+    assert hl.xyRegularlySpaced == 1 and hl.zRegularlySpaced == 1 and hl.deltaX == 15.625
