@@ -6,13 +6,16 @@
 //     counter (warp-aggregated atomic) so no lane idles while photons remain;
 //   * ray marching (accumulateExtinctionAlongPath, OPT:1656-1815) as a parametric
 //     Amanatides-Woo DDA in single precision: per cell one dependent gather of the packed
-//     f32 extinction, one compare, one face update from shared-memory-staged edges; no
-//     divides inside the cell loop; periodic x/y handled by shifting the leg origin;
-//   * warp-level regrouping: lanes march together and park when they reach an event
+//     f32 extinction and a branch-free face update (all three axes predicated, no divides
+//     in the cell loop); regular grids step their face distances incrementally, irregular
+//     grids read shared-memory-staged edges; periodic x/y shift the leg origin;
+//   * warp-level regrouping: lanes march in bursts and park when they reach an event
 //     (scatter / surface); the event code runs once enough lanes are parked, so the
 //     expensive scatter path executes with many active lanes instead of one or two;
 //   * Philox4x32-10 per-photon streams (mcb_device.cuh) instead of a sequential MT19937;
-//   * tallies as f64 reductions into the packed tally buffer (RED.ADD.F64).
+//   * tallies: shared-memory-privatised f32 atomics flushed once per block when the column /
+//     cell grid is small enough to be an atomic hot spot, f64 RED.ADD to the packed tally
+//     buffer otherwise.
 // Results agree with the reference arithmetic statistically (north-star criterion (b));
 // bit-level trace parity is the job of mcb_reference.cu.
 #include "mcb_device.cuh"
@@ -25,10 +28,39 @@ namespace mcbfast {
 
 enum { ST_DEAD = 0, ST_MARCH = 1, ST_SCATTER = 2, ST_SURFACE = 3, ST_DONE = 4 };
 
+// launch-time layout of the dynamic shared memory
+struct SmemPlan {
+  int edgesOff;            // float[nx+1 + ny+1 + nz+1] (irregular grids only; -1 otherwise)
+  int fluxOff;             // float[3*cols]  privatised fluxUp|fluxDown|fluxAbs   (-1: global atomics)
+  int volOff;              // float[cells]   privatised volumeAbsorption           (-1: global atomics)
+  int intOff;              // float[cols*nDir] privatised intensity                (-1: global atomics)
+  int totalFloats;
+};
+
 struct Rng {
-  Philox g;
-  __device__ __forceinline__ float real() {          // f32 in [0,1] built from 32 bits (RNG:286-300)
-    return __uint2float_rn(g.next_u32()) * 2.3283064365386963e-10f;
+  uint32_t c0, c1, blk, b0, b1, b2, b3;
+  int have;
+  __device__ __forceinline__ void init(uint64_t photon) {
+    c0 = (uint32_t)photon; c1 = (uint32_t)(photon >> 32); blk = 0; have = 0;
+  }
+  __device__ __forceinline__ void refill(uint32_t k0, uint32_t k1) {
+    uint32_t x0 = c0, x1 = c1, x2 = blk, x3 = 0u, a = k0, b = k1;
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+      const uint32_t hi0 = __umulhi(0xD2511F53u, x0), lo0 = 0xD2511F53u * x0;
+      const uint32_t hi1 = __umulhi(0xCD9E8D57u, x2), lo1 = 0xCD9E8D57u * x2;
+      const uint32_t y0 = hi1 ^ x1 ^ a, y2 = hi0 ^ x3 ^ b;
+      x0 = y0; x1 = lo1; x2 = y2; x3 = lo0;
+      a += 0x9E3779B9u; b += 0xBB67AE85u;
+    }
+    b0 = x0; b1 = x1; b2 = x2; b3 = x3; blk++; have = 4;
+  }
+  // f32 in [0,1] built from 32 bits (RNG:286-300)
+  __device__ __forceinline__ float real(uint32_t k0, uint32_t k1) {
+    if (have == 0) refill(k0, k1);
+    have--;
+    const uint32_t r = b0; b0 = b1; b1 = b2; b2 = b3;
+    return __uint2float_rn(r) * 2.3283064365386963e-10f;
   }
 };
 
@@ -41,51 +73,77 @@ struct Ray {
   int ix, iy, iz;          // 0-based cell
 };
 
-struct Grid {              // shared-memory staged edges (f32)
-  const float *sx, *sy, *sz;
+struct Grid {
+  const float *sx, *sy, *sz;     // shared-memory edges (irregular grids)
   int nx, ny, nz;
-  float Lx, Ly;
+  float x0, y0, z0, Lx, Ly, Lz;
+  float hx, hy, hz;              // regular spacing
 };
 
 __device__ __forceinline__ float safe_rcp(float d) {
   return fabsf(d) >= 2.0f * TINY32 ? 1.0f / d : FLT_MAX;      // OPT:1705-1712 zero-direction guard
 }
 
+template <bool REG>
+__device__ __forceinline__ float edge_x(const Grid &G, int i) { return REG ? fmaf((float)i, G.hx, G.x0) : G.sx[i]; }
+template <bool REG>
+__device__ __forceinline__ float edge_y(const Grid &G, int i) { return REG ? fmaf((float)i, G.hy, G.y0) : G.sy[i]; }
+template <bool REG>
+__device__ __forceinline__ float edge_z(const Grid &G, int i) { return REG ? fmaf((float)i, G.hz, G.z0) : G.sz[i]; }
+
+template <bool REG>
 __device__ __forceinline__ void ray_start(Ray &r, const Grid &G) {
   r.rx = safe_rcp(r.dx); r.ry = safe_rcp(r.dy); r.rz = safe_rcp(r.dz);
   r.t = 0.0f;
-  r.tx = r.rx == FLT_MAX ? FLT_MAX : (G.sx[r.ix + (r.dx >= 0.0f ? 1 : 0)] - r.ox) * r.rx;
-  r.ty = r.ry == FLT_MAX ? FLT_MAX : (G.sy[r.iy + (r.dy >= 0.0f ? 1 : 0)] - r.oy) * r.ry;
-  r.tz = r.rz == FLT_MAX ? FLT_MAX : (G.sz[r.iz + (r.dz >= 0.0f ? 1 : 0)] - r.oz) * r.rz;
+  r.tx = r.rx == FLT_MAX ? FLT_MAX : fmaxf((edge_x<REG>(G, r.ix + (r.dx >= 0.0f ? 1 : 0)) - r.ox) * r.rx, 0.0f);
+  r.ty = r.ry == FLT_MAX ? FLT_MAX : fmaxf((edge_y<REG>(G, r.iy + (r.dy >= 0.0f ? 1 : 0)) - r.oy) * r.ry, 0.0f);
+  r.tz = r.rz == FLT_MAX ? FLT_MAX : fmaxf((edge_z<REG>(G, r.iz + (r.dz >= 0.0f ? 1 : 0)) - r.oz) * r.rz, 0.0f);
 }
 
-// Advance across the face(s) reached at distance tmin.  Returns 0 inside, 1 out the top, 2 out the bottom.
+// Cross the face(s) reached at distance tmin: branch-free on all three axes (every lane runs the
+// same instructions; the axis actually crossed is selected by predicates).  Returns 0 inside,
+// 1 out the top, 2 out the bottom.
+template <bool REG>
 __device__ __forceinline__ int ray_advance(Ray &r, const Grid &G, float tmin) {
   r.t = tmin;
-  if (r.tx <= tmin) {
-    if (r.dx >= 0.0f) { if (++r.ix >= G.nx) { r.ix = 0; r.ox -= G.Lx; } r.tx = (G.sx[r.ix + 1] - r.ox) * r.rx; }
-    else              { if (--r.ix < 0) { r.ix = G.nx - 1; r.ox += G.Lx; } r.tx = (G.sx[r.ix] - r.ox) * r.rx; }
+  {
+    const bool c = r.tx <= tmin, pos = r.dx >= 0.0f;
+    int i = r.ix + (c ? (pos ? 1 : -1) : 0);
+    float o = r.ox;
+    if (i >= G.nx) { i = 0; o -= G.Lx; }
+    if (i < 0) { i = G.nx - 1; o += G.Lx; }
+    const float nt = REG ? r.tx + G.hx * fabsf(r.rx) : (G.sx[i + (pos ? 1 : 0)] - o) * r.rx;
+    r.tx = c ? nt : r.tx; r.ix = i; r.ox = o;
   }
-  if (r.ty <= tmin) {
-    if (r.dy >= 0.0f) { if (++r.iy >= G.ny) { r.iy = 0; r.oy -= G.Ly; } r.ty = (G.sy[r.iy + 1] - r.oy) * r.ry; }
-    else              { if (--r.iy < 0) { r.iy = G.ny - 1; r.oy += G.Ly; } r.ty = (G.sy[r.iy] - r.oy) * r.ry; }
+  {
+    const bool c = r.ty <= tmin, pos = r.dy >= 0.0f;
+    int i = r.iy + (c ? (pos ? 1 : -1) : 0);
+    float o = r.oy;
+    if (i >= G.ny) { i = 0; o -= G.Ly; }
+    if (i < 0) { i = G.ny - 1; o += G.Ly; }
+    const float nt = REG ? r.ty + G.hy * fabsf(r.ry) : (G.sy[i + (pos ? 1 : 0)] - o) * r.ry;
+    r.ty = c ? nt : r.ty; r.iy = i; r.oy = o;
   }
-  if (r.tz <= tmin) {
-    if (r.dz >= 0.0f) { if (++r.iz >= G.nz) return 1; r.tz = (G.sz[r.iz + 1] - r.oz) * r.rz; }
-    else              { if (--r.iz < 0) return 2; r.tz = (G.sz[r.iz] - r.oz) * r.rz; }
+  {
+    const bool c = r.tz <= tmin, pos = r.dz >= 0.0f;
+    const int i = r.iz + (c ? (pos ? 1 : -1) : 0);
+    if ((unsigned)i >= (unsigned)G.nz) return pos ? 1 : 2;
+    const float nt = REG ? r.tz + G.hz * fabsf(r.rz) : (G.sz[i + (pos ? 1 : 0)] - r.oz) * r.rz;
+    r.tz = c ? nt : r.tz; r.iz = i;
   }
   return 0;
 }
 
 // Trace to the boundary or to an optical-depth target (the local-estimate rays, INT:1734-1739,
-// 1764-1795).  Returns the accumulated optical depth; *where = 0 stopped at target, 1 top, 2 bottom.
+// 1764-1795).  Returns the accumulated optical depth; where = 0 stopped at target, 1 top, 2 bottom.
+template <bool REG>
 __device__ float ray_trace(Ray &r, const Grid &G, const float *__restrict__ ext32, bool hasTarget, float target,
                            int &where, unsigned &crossings) {
   float ext = 0.0f;
   for (;;) {
     const float tmin = fminf(r.tx, fminf(r.ty, r.tz));
     const float s = fmaxf(tmin - r.t, 0.0f);
-    const float sig = __ldg(&ext32[(size_t)r.ix + (size_t)G.nx * ((size_t)r.iy + (size_t)G.ny * (size_t)r.iz)]);
+    const float sig = __ldg(&ext32[r.ix + G.nx * (r.iy + G.ny * r.iz)]);
     crossings++;
     const float e2 = fmaf(s, sig, ext);
     if (hasTarget && e2 > target) {
@@ -94,18 +152,12 @@ __device__ float ray_trace(Ray &r, const Grid &G, const float *__restrict__ ext3
       return target;
     }
     ext = e2;
-    const int out = ray_advance(r, G, tmin);
+    const int out = ray_advance<REG>(r, G, tmin);
     if (out) { where = out; return ext; }
   }
 }
 
-__device__ __forceinline__ int find_cell(const float *e, int n, float x, int guess) {
-  int i = min(max(guess, 0), n - 1);
-  while (i > 0 && x < e[i]) --i;
-  while (i < n - 1 && x >= e[i + 1]) ++i;
-  return i;
-}
-__device__ __forceinline__ int find_cell_bisect(const float *e, int n, float x) {
+__device__ __forceinline__ int find_cell(const float *e, int n, float x) {
   int lo = 0, hi = n;                      // e[lo] <= x < e[hi]
   while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (x >= e[mid]) lo = mid; else hi = mid; }
   return lo;
@@ -128,13 +180,34 @@ __device__ __forceinline__ int cdf_search(const double *__restrict__ table, int 
   return hi;                                // 1-based
 }
 
-struct Counts { unsigned c[CNT_N]; };
+// ---- tallies ------------------------------------------------------------------------------
+struct Tally {
+  float *sFlux, *sVol, *sInt;       // shared-memory privatised copies (or nullptr)
+  int cols;
+};
+__device__ __forceinline__ void add_flux(const DevDomain &P, const Tally &T, int which, int col, float v) {
+  if (T.sFlux) atomicAdd(&T.sFlux[which * T.cols + col], v);
+  else atomicAdd(&P.tally[(which == 0 ? P.offFluxUp : which == 1 ? P.offFluxDown : P.offFluxAbs) + col], (double)v);
+}
+__device__ __forceinline__ void add_vol(const DevDomain &P, const Tally &T, int cell, float v) {
+  if (T.sVol) atomicAdd(&T.sVol[cell], v);
+  else atomicAdd(&P.tally[P.offVolAbs + cell], (double)v);
+}
+__device__ __forceinline__ void add_intensity(const DevDomain &P, const Tally &T, int dir, int col, int comp, float v) {
+  if (T.sInt) atomicAdd(&T.sInt[dir * T.cols + col], v);
+  else atomicAdd(&P.tally[P.offInt + col + (long long)T.cols * dir], (double)v);
+  atomicAdd(&P.tally[P.offIntByComp + col + (long long)T.cols * (dir + (long long)P.nDir * comp)], (double)v);
+}
+
+struct Counts { unsigned crossings, scatters, leRays, leCrossings; };
 
 // computeIntensityContribution (INT:1623-1832) for one event, all view directions.
-__device__ void local_estimate(const DevDomain &P, const Grid &G, Rng &rng, const Ray &r0, float px, float py, float pz,
+template <bool REG>
+__device__ void local_estimate(const DevDomain &P, const Grid &G, const Tally &T, Rng &rng, uint32_t k0, uint32_t k1,
+                               const Ray &r0, float px, float py, float pz,
                                float w, int component, int tallyComponent, int order, Counts &cnt) {
-  const size_t cols = (size_t)P.nx * P.ny;
-  const size_t cell = (size_t)r0.ix + (size_t)P.nx * ((size_t)r0.iy + (size_t)P.ny * (size_t)r0.iz);
+  const int cell = r0.ix + G.nx * (r0.iy + G.ny * r0.iz);
+  const size_t cells = (size_t)P.nx * P.ny * P.nz;
   for (int i = 0; i < P.nDir; ++i) {
     const float vx = P.viewDir[3 * i], vy = P.viewDir[3 * i + 1], vz = P.viewDir[3 * i + 2];
     float npf;
@@ -147,7 +220,7 @@ __device__ void local_estimate(const DevDomain &P, const Grid &G, Rng &rng, cons
       proj = fminf(fmaxf(proj, -1.0f), 1.0f);
       const float ang = acosf(proj);
       const int c = component - 1;
-      const int pidx = (int)__ldg(&P.idx16[cell + (size_t)P.nx * P.ny * P.nz * c]);
+      const int pidx = (int)__ldg(&P.idx16[cell + cells * c]);
       const float *tab = ((P.opt.useHybridPhaseFunsForIntenCalcs && order <= P.opt.numOrdersOrigPhaseFunIntenCalcs)
                               ? P.fwdOrig[c] : P.fwd[c]) + (size_t)(pidx - 1) * P.fwdS[c];
       const int nS = P.fwdS[c];                                                  // INT:1855-1870
@@ -165,33 +238,32 @@ __device__ void local_estimate(const DevDomain &P, const Grid &G, Rng &rng, cons
     Ray r;
     r.ox = px; r.oy = py; r.oz = pz; r.dx = vx; r.dy = vy; r.dz = vz;
     r.ix = r0.ix; r.iy = r0.iy; r.iz = r0.iz;
-    ray_start(r, G);
+    ray_start<REG>(r, G);
     int where = 0;
     float contribution;
-    cnt.c[CNT_LE_RAYS]++;
+    cnt.leRays++;
     if (!P.opt.useRussianRouletteForIntensity) {                                 // INT:1729-1752
-      const float tau = ray_trace(r, G, P.ext32, false, 0.0f, where, cnt.c[CNT_LE_CROSSINGS]);
+      const float tau = ray_trace<REG>(r, G, P.ext32, false, 0.0f, where, cnt.leCrossings);
       contribution = w * npf * __expf(-tau);
     } else {                                                                     // INT:1753-1813
-      const float tauFree = -__logf(fmaxf(TINY32, rng.real()));
+      const float tauFree = -__logf(fmaxf(TINY32, rng.real(k0, k1)));
       if (PI32 * npf <= P.opt.zetaMin) {                                         // Iwabuchi (2006) Eq 13
-        ray_trace(r, G, P.ext32, true, tauFree, where, cnt.c[CNT_LE_CROSSINGS]);
-        const float test = rng.real();
+        ray_trace<REG>(r, G, P.ext32, true, tauFree, where, cnt.leCrossings);
+        const float test = rng.real(k0, k1);
         contribution = (test <= PI32 * npf / P.opt.zetaMin && where == 1) ? w * P.opt.zetaMin / PI32 : 0.0f;
       } else {                                                                   // Eq 14
         const float tauMax = -__logf(P.opt.zetaMin / fmaxf(TINY32, PI32 * npf));
-        const float tau = ray_trace(r, G, P.ext32, true, tauMax, where, cnt.c[CNT_LE_CROSSINGS]);
+        const float tau = ray_trace<REG>(r, G, P.ext32, true, tauMax, where, cnt.leCrossings);
         if (where == 1) {
           contribution = w * npf * __expf(-tau);
         } else if (where == 0) {
           // continue from where the first trace stopped (INT:1793-1795)
           r.ox = fmaf(r.t, r.dx, r.ox); r.oy = fmaf(r.t, r.dy, r.oy); r.oz = fmaf(r.t, r.dz, r.oz);
-          ray_start(r, G);
-          ray_trace(r, G, P.ext32, true, tauFree, where, cnt.c[CNT_LE_CROSSINGS]);
+          ray_start<REG>(r, G);
+          ray_trace<REG>(r, G, P.ext32, true, tauFree, where, cnt.leCrossings);
           contribution = where == 1 ? w * P.opt.zetaMin / PI32 : 0.0f;
         } else {
-          contribution = 0.0f;       // left through the bottom before tauMax: zIndexF < zIndexMax
-          // (the reference then traces on with tauFree from z0 and still finds zIndexF < zIndexMax)
+          contribution = 0.0f;       // left through the surface before tauMax (zIndexF < zIndexMax)
         }
       }
     }
@@ -201,33 +273,47 @@ __device__ void local_estimate(const DevDomain &P, const Grid &G, Rng &rng, cons
                 (double)(contribution - P.opt.maxIntensityContribution));
       contribution = P.opt.maxIntensityContribution;
     }
-    if (contribution != 0.0f) {
-      const size_t col = (size_t)r.ix + (size_t)P.nx * (size_t)r.iy;
-      atomicAdd(&P.tally[P.offInt + col + cols * i], (double)contribution);
-      atomicAdd(&P.tally[P.offIntByComp + col + cols * ((size_t)i + (size_t)P.nDir * tallyComponent)], (double)contribution);
-    }
+    if (contribution != 0.0f) add_intensity(P, T, i, r.ix + G.nx * r.iy, tallyComponent, contribution);
   }
 }
 
-template <int THREADS>
-__global__ void __launch_bounds__(THREADS)
+template <int THREADS, bool REG>
+__global__ void __launch_bounds__(THREADS, REG ? 5 : 4)
 batch_kernel(const __grid_constant__ DevDomain P, long long nPhotons, uint64_t seed, uint64_t firstPhotonId,
-             unsigned long long *workCounter, int parkThreshold) {
+             unsigned long long *workCounter, int parkThreshold, const SmemPlan plan) {
   extern __shared__ float smem[];
-  float *sx = smem, *sy = sx + (P.nx + 1), *sz = sy + (P.ny + 1);
-  for (int i = threadIdx.x; i <= P.nx; i += THREADS) sx[i] = (float)P.xE[i];
-  for (int i = threadIdx.x; i <= P.ny; i += THREADS) sy[i] = (float)P.yE[i];
-  for (int i = threadIdx.x; i <= P.nz; i += THREADS) sz[i] = (float)P.zE[i];
+  __shared__ unsigned sCnt[CNT_N];
+  const int cols = P.nx * P.ny, cells = cols * P.nz;
+  Grid G;
+  G.nx = P.nx; G.ny = P.ny; G.nz = P.nz;
+  G.x0 = (float)P.x0; G.y0 = (float)P.y0; G.z0 = (float)P.z0;
+  G.Lx = (float)(P.xMax - P.x0); G.Ly = (float)(P.yMax - P.y0); G.Lz = (float)(P.zMax - P.z0);
+  G.hx = (float)P.deltaX; G.hy = (float)P.deltaY; G.hz = (float)P.deltaZ;
+  G.sx = G.sy = G.sz = nullptr;
+  if (!REG) {
+    float *sx = smem + plan.edgesOff, *sy = sx + (P.nx + 1), *sz = sy + (P.ny + 1);
+    for (int i = threadIdx.x; i <= P.nx; i += THREADS) sx[i] = (float)P.xE[i];
+    for (int i = threadIdx.x; i <= P.ny; i += THREADS) sy[i] = (float)P.yE[i];
+    for (int i = threadIdx.x; i <= P.nz; i += THREADS) sz[i] = (float)P.zE[i];
+    G.sx = sx; G.sy = sy; G.sz = sz;
+  }
+  Tally T;
+  T.cols = cols;
+  T.sFlux = plan.fluxOff >= 0 ? smem + plan.fluxOff : nullptr;
+  T.sVol = plan.volOff >= 0 ? smem + plan.volOff : nullptr;
+  T.sInt = plan.intOff >= 0 ? smem + plan.intOff : nullptr;
+  if (T.sFlux) for (int i = threadIdx.x; i < 3 * cols; i += THREADS) T.sFlux[i] = 0.0f;
+  if (T.sVol) for (int i = threadIdx.x; i < cells; i += THREADS) T.sVol[i] = 0.0f;
+  if (T.sInt) for (int i = threadIdx.x; i < cols * P.nDir; i += THREADS) T.sInt[i] = 0.0f;
+  if (threadIdx.x < CNT_N) sCnt[threadIdx.x] = 0u;
   __syncthreads();
-  Grid G{sx, sy, sz, P.nx, P.ny, P.nz, sx[P.nx] - sx[0], sy[P.ny] - sy[0]};
+
   const int lane = threadIdx.x & 31;
-  const size_t cols = (size_t)P.nx * P.ny, cells = cols * P.nz;
   const float *__restrict__ ext32 = P.ext32;
+  const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+  const float zTop = G.z0 + G.Lz;
 
-  Counts cnt;
-#pragma unroll
-  for (int i = 0; i < CNT_N; ++i) cnt.c[i] = 0;
-
+  Counts cnt{0u, 0u, 0u, 0u};
   Rng rng;
   Ray r;
   float w = 0.0f, tau = 0.0f, ext = 0.0f;
@@ -246,65 +332,67 @@ batch_kernel(const __grid_constant__ DevDomain P, long long nPhotons, uint64_t s
         if (state == ST_DEAD) {
           const unsigned long long p = base + (unsigned long long)__popc(dead & ((1u << lane) - 1u));
           if (p < (unsigned long long)nPhotons) {
-            rng.g.init(seed, firstPhotonId + p);
+            rng.init(firstPhotonId + p);
             float x01, y01, z01, mu, phi;
             if (P.source == 0) {                                               // ILL:88-96
-              x01 = rng.real(); y01 = rng.real(); z01 = 1.0f - FLT_EPSILON;
+              x01 = rng.real(k0, k1); y01 = rng.real(k0, k1); z01 = 1.0f - FLT_EPSILON;
               mu = P.solarMu; phi = P.solarPhi;
             } else {                                                           // ILL:481-515
-              const float RN = rng.real();
+              const float RN = rng.real(k0, k1);
               if ((double)RN > P.fracAtmsPower) {
-                x01 = rng.real(); y01 = rng.real();
-                do { mu = sqrtf(rng.real()); } while (!(fabsf(mu) > 2.0f * TINY32));
-                phi = rng.real() * 2.0f * PI32;
+                x01 = rng.real(k0, k1); y01 = rng.real(k0, k1);
+                do { mu = sqrtf(rng.real(k0, k1)); } while (!(fabsf(mu) > 2.0f * TINY32));
+                phi = rng.real(k0, k1) * 2.0f * PI32;
                 z01 = 0.0f;
               } else {
-                const float q = rng.real();
+                const float q = rng.real(k0, k1);
                 const double *levelBase = P.voxelCDF + (size_t)(P.nx - 1) + (size_t)P.nx * (size_t)(P.ny - 1);
                 const int ik = cdf_search(levelBase, P.nz, (long long)cols, q);
-                const double *colBase = P.voxelCDF + (size_t)(P.nx - 1) + cols * (size_t)(ik - 1);
+                const double *colBase = P.voxelCDF + (size_t)(P.nx - 1) + (size_t)cols * (size_t)(ik - 1);
                 const int ij = cdf_search(colBase, P.ny, P.nx, q);
                 const double *voxBase = P.voxelCDF + (size_t)P.nx * ((size_t)(ij - 1) + (size_t)P.ny * (size_t)(ik - 1));
                 const int ii = cdf_search(voxBase, P.nx, 1, q);
                 // uniform inside the chosen cell, nudged off its faces (ILL:500-505)
-                z01 = ((float)(ik - 1) + fminf(fmaxf(rng.real(), 1e-6f), 1.0f - 1e-6f)) / (float)P.nz;
-                x01 = ((float)(ii - 1) + fminf(rng.real(), 1.0f - 1e-6f)) / (float)P.nx;
-                y01 = ((float)(ij - 1) + fminf(rng.real(), 1.0f - 1e-6f)) / (float)P.ny;
-                do { mu = 1.0f - 2.0f * rng.real(); } while (!(fabsf(mu) > 2.0f * TINY32));
-                phi = rng.real() * 2.0f * PI32;
+                z01 = ((float)(ik - 1) + fminf(fmaxf(rng.real(k0, k1), 1e-6f), 1.0f - 1e-6f)) / (float)P.nz;
+                x01 = ((float)(ii - 1) + fminf(rng.real(k0, k1), 1.0f - 1e-6f)) / (float)P.nx;
+                y01 = ((float)(ij - 1) + fminf(rng.real(k0, k1), 1.0f - 1e-6f)) / (float)P.ny;
+                do { mu = 1.0f - 2.0f * rng.real(k0, k1); } while (!(fabsf(mu) > 2.0f * TINY32));
+                phi = rng.real(k0, k1) * 2.0f * PI32;
               }
             }
             dir_from(mu, phi, r.dx, r.dy, r.dz);
             w = 1.0f; order = 0;
-            // INT:478-494: unit square -> domain; thermal z01 indexes the (possibly irregular) level directly
-            r.ox = sx[0] + x01 * G.Lx; r.oy = sy[0] + y01 * G.Ly;
-            if (P.xyRegular) {
-              r.ix = find_cell(sx, P.nx, r.ox, (int)(x01 * (float)P.nx));
-              r.iy = find_cell(sy, P.ny, r.oy, (int)(y01 * (float)P.ny));
+            // INT:478-494: unit square -> domain
+            r.ox = fmaf(x01, G.Lx, G.x0); r.oy = fmaf(y01, G.Ly, G.y0);
+            if (REG) {
+              r.ix = min((int)(x01 * (float)P.nx), P.nx - 1);
+              r.iy = min((int)(y01 * (float)P.ny), P.ny - 1);
+              r.oz = fmaf(z01, G.Lz, G.z0);
+              r.iz = min((int)(z01 * (float)P.nz), P.nz - 1);
             } else {
-              r.ix = find_cell_bisect(sx, P.nx, r.ox);
-              r.iy = find_cell_bisect(sy, P.ny, r.oy);
+              r.ix = find_cell(G.sx, P.nx, r.ox);
+              r.iy = find_cell(G.sy, P.ny, r.oy);
+              if (P.zRegular) {
+                r.oz = fmaf(z01, G.Lz, G.z0);
+                r.iz = find_cell(G.sz, P.nz, r.oz);
+              } else {                                                         // INT:491-493
+                const float zs = z01 * (float)P.nz;
+                r.iz = min((int)zs, P.nz - 1);
+                r.oz = G.sz[r.iz] + (zs - (float)r.iz) * (G.sz[r.iz + 1] - G.sz[r.iz]);
+              }
             }
-            if (P.zRegular) {
-              r.oz = sz[0] + z01 * (sz[P.nz] - sz[0]);
-              r.iz = find_cell(sz, P.nz, r.oz, (int)(z01 * (float)P.nz));
-            } else {                                                           // INT:491-493
-              const float zs = z01 * (float)P.nz;
-              r.iz = min((int)zs, P.nz - 1);
-              r.oz = sz[r.iz] + (zs - (float)r.iz) * (sz[r.iz + 1] - sz[r.iz]);
-            }
-            cnt.c[CNT_PHOTONS]++;
+            atomicAdd(&sCnt[CNT_PHOTONS], 1u);
             if (P.opt.LW_flag > 0.0f) {                                        // INT:504-542
               if (r.oz > 0.0f) {
-                atomicAdd(&P.tally[P.offFluxAbs + (size_t)r.ix + (size_t)P.nx * (size_t)r.iy], -1.0);
-                atomicAdd(&P.tally[P.offVolAbs + (size_t)r.ix + (size_t)P.nx * ((size_t)r.iy + (size_t)P.ny * (size_t)r.iz)], -1.0);
+                add_flux(P, T, 2, r.ix + P.nx * r.iy, -1.0f);
+                add_vol(P, T, r.ix + P.nx * (r.iy + P.ny * r.iz), -1.0f);
               }
               if (P.nDir > 0)
-                local_estimate(P, G, rng, r, r.ox, r.oy, r.oz, w, r.oz == 0.0f ? 0 : -1, 0, order, cnt);
+                local_estimate<REG>(P, G, T, rng, k0, k1, r, r.ox, r.oy, r.oz, w, r.oz == 0.0f ? 0 : -1, 0, order, cnt);
             }
-            tau = -__logf(fmaxf(TINY32, rng.real()));                          // INT:554
+            tau = -__logf(fmaxf(TINY32, rng.real(k0, k1)));                    // INT:554
             ext = 0.0f;
-            ray_start(r, G);
+            ray_start<REG>(r, G);
             state = ST_MARCH;
           } else {
             state = ST_DONE;
@@ -317,31 +405,33 @@ batch_kernel(const __grid_constant__ DevDomain P, long long nPhotons, uint64_t s
     }
     if (__all_sync(FULL, state == ST_DONE)) break;
 
-    // ---- march phase: cross cells until enough lanes are parked at an event ----
+    // ---- march phase: cross cells in bursts until enough lanes are parked at an event ----
     for (;;) {
-      const bool marching = state == ST_MARCH;
-      const unsigned mk = __ballot_sync(FULL, marching);
+      const unsigned mk = __ballot_sync(FULL, state == ST_MARCH);
       const unsigned live = __ballot_sync(FULL, state != ST_DONE);
       // stop when nobody marches, or when the parked (event/dead) lanes reach the threshold
       if (mk == 0u || __popc(live & ~mk) >= parkThreshold) break;
-      if (marching) {
-        const float tmin = fminf(r.tx, fminf(r.ty, r.tz));
-        const float s = fmaxf(tmin - r.t, 0.0f);
-        const float sig = __ldg(&ext32[(size_t)r.ix + (size_t)P.nx * ((size_t)r.iy + (size_t)P.ny * (size_t)r.iz)]);
-        cnt.c[CNT_CROSSINGS]++;
-        const float e2 = fmaf(s, sig, ext);
-        if (e2 > tau) {                                                        // OPT:1729-1738
-          r.t += (tau - ext) / sig;
-          state = ST_SCATTER;
-        } else {
-          ext = e2;
-          const int out = ray_advance(r, G, tmin);
-          if (out == 1) {                                                      // INT:573-617
-            atomicAdd(&P.tally[P.offFluxUp + (size_t)r.ix + (size_t)P.nx * (size_t)r.iy], (double)w);
-            cnt.c[CNT_TOP]++;
-            state = ST_DEAD;
-          } else if (out == 2) {
-            state = ST_SURFACE;
+#pragma unroll 1
+      for (int burst = 0; burst < 4; ++burst) {
+        if (state == ST_MARCH) {
+          const float tmin = fminf(r.tx, fminf(r.ty, r.tz));
+          const float s = fmaxf(tmin - r.t, 0.0f);
+          const float sig = __ldg(&ext32[r.ix + P.nx * (r.iy + P.ny * r.iz)]);
+          cnt.crossings++;
+          const float e2 = fmaf(s, sig, ext);
+          if (e2 > tau) {                                                      // OPT:1729-1738
+            r.t += (tau - ext) / sig;
+            state = ST_SCATTER;
+          } else {
+            ext = e2;
+            const int out = ray_advance<REG>(r, G, tmin);
+            if (out == 1) {                                                    // INT:573-617
+              add_flux(P, T, 0, r.ix + P.nx * r.iy, w);
+              atomicAdd(&sCnt[CNT_TOP], 1u);
+              state = ST_DEAD;
+            } else if (out == 2) {
+              state = ST_SURFACE;
+            }
           }
         }
       }
@@ -349,55 +439,53 @@ batch_kernel(const __grid_constant__ DevDomain P, long long nPhotons, uint64_t s
 
     // ---- event phase ----
     if (state == ST_SURFACE) {                                                 // INT:619-702
-      const size_t col = (size_t)r.ix + (size_t)P.nx * (size_t)r.iy;
-      atomicAdd(&P.tally[P.offFluxDown + col], (double)w);
-      cnt.c[CNT_SURFACE]++;
+      add_flux(P, T, 1, r.ix + P.nx * r.iy, w);
+      atomicAdd(&sCnt[CNT_SURFACE], 1u);
       order++;
       float mu;
-      do { mu = sqrtf(rng.real()); } while (!(fabsf(mu) > 2.0f * TINY32));
-      const float phi = 2.0f * PI32 * rng.real();
+      do { mu = sqrtf(rng.real(k0, k1)); } while (!(fabsf(mu) > 2.0f * TINY32));
+      const float phi = 2.0f * PI32 * rng.real(k0, k1);
       w = (float)((double)w * P.albedo);
       if (w <= TINY32) {
         state = ST_DEAD;
       } else {
-        const float px = fmaf(r.t, r.dx, r.ox), py = fmaf(r.t, r.dy, r.oy);
-        r.ox = px; r.oy = py; r.oz = sz[0]; r.iz = 0;
+        r.ox = fmaf(r.t, r.dx, r.ox); r.oy = fmaf(r.t, r.dy, r.oy); r.oz = G.z0; r.iz = 0;
         dir_from(mu, phi, r.dx, r.dy, r.dz);
-        if (P.nDir > 0) local_estimate(P, G, rng, r, r.ox, r.oy, r.oz, w, 0, 0, order, cnt);
-        tau = -__logf(fmaxf(TINY32, rng.real()));
+        if (P.nDir > 0) local_estimate<REG>(P, G, T, rng, k0, k1, r, r.ox, r.oy, r.oz, w, 0, 0, order, cnt);
+        tau = -__logf(fmaxf(TINY32, rng.real(k0, k1)));
         ext = 0.0f;
-        ray_start(r, G);
+        ray_start<REG>(r, G);
         state = ST_MARCH;
       }
     } else if (state == ST_SCATTER) {                                          // INT:703-821
       order++;
-      cnt.c[CNT_SCATTERS]++;
-      const size_t cell = (size_t)r.ix + (size_t)P.nx * ((size_t)r.iy + (size_t)P.ny * (size_t)r.iz);
-      const float rnComp = rng.real();                                         // drawn even when nc == 1 (INT:759)
+      cnt.scatters++;
+      const int cell = r.ix + P.nx * (r.iy + P.ny * r.iz);
+      const float rnComp = rng.real(k0, k1);                                   // drawn even when nc == 1 (INT:759)
       int comp = 1;
       for (int c = 1; c < P.nc; ++c)                                           // findIndex on (0, cumExt(:)), NUM:262-315
-        if (rnComp >= __ldg(&P.cum32[cell + cells * (size_t)(c - 1)])) comp = c + 1;
-      const float ssa = __ldg(&P.ssa32[cell + cells * (size_t)(comp - 1)]);
+        if (rnComp >= __ldg(&P.cum32[cell + (size_t)cells * (size_t)(c - 1)])) comp = c + 1;
+      const float ssa = __ldg(&P.ssa32[cell + (size_t)cells * (size_t)(comp - 1)]);
       if (ssa < 1.0f) {                                                        // INT:765-771
-        const double absorbed = (double)w * (1.0 - (double)ssa);
-        atomicAdd(&P.tally[P.offFluxAbs + (size_t)r.ix + (size_t)P.nx * (size_t)r.iy], absorbed);
-        atomicAdd(&P.tally[P.offVolAbs + cell], absorbed);
+        const float absorbed = w * (1.0f - ssa);
+        add_flux(P, T, 2, r.ix + P.nx * r.iy, absorbed);
+        add_vol(P, T, cell, absorbed);
         w *= ssa;
       }
       const float px = fmaf(r.t, r.dx, r.ox), py = fmaf(r.t, r.dy, r.oy), pz = fmaf(r.t, r.dz, r.oz);
-      if (P.nDir > 0) local_estimate(P, G, rng, r, px, py, pz, w, comp, comp, order, cnt);   // INT:776-800
+      if (P.nDir > 0) local_estimate<REG>(P, G, T, rng, k0, k1, r, px, py, pz, w, comp, comp, order, cnt);   // INT:776-800
       if (P.opt.useRussianRoulette && w < P.opt.russianRouletteW * 0.5f) {     // INT:805-811
-        if (rng.real() >= w / P.opt.russianRouletteW) w = 0.0f; else w = P.opt.russianRouletteW;
+        if (rng.real(k0, k1) >= w / P.opt.russianRouletteW) w = 0.0f; else w = P.opt.russianRouletteW;
       }
       if (w <= TINY32) {
-        cnt.c[CNT_RR_KILLS]++;
+        atomicAdd(&sCnt[CNT_RR_KILLS], 1u);
         state = ST_DEAD;
       } else {
         const int c = comp - 1;
-        const int pidx = (int)__ldg(&P.idx16[cell + cells * (size_t)c]);
+        const int pidx = (int)__ldg(&P.idx16[cell + (size_t)cells * (size_t)c]);
         const int nS = P.invS[c];
         const float *tab = P.inv[c] + (size_t)(pidx - 1) * nS;
-        const float rn = rng.real();                                           // computeScatteringAngle INT:1594-1621
+        const float rn = rng.real(k0, k1);                                     // computeScatteringAngle INT:1594-1621
         const int k = (int)(rn * (float)nS) + 1;
         float theta;
         if (k < nS) {
@@ -410,8 +498,8 @@ batch_kernel(const __grid_constant__ DevDomain P, long long nPhotons, uint64_t s
         __sincosf(theta, &sinT, &cosT);
         float AX, AY, D;                                                       // next_direct INT:1921-1948
         do {
-          AX = 1.0f - 2.0f * rng.real();
-          AY = 1.0f - 2.0f * rng.real();
+          AX = 1.0f - 2.0f * rng.real(k0, k1);
+          AY = 1.0f - 2.0f * rng.real(k0, k1);
           D = AX * AX + AY * AY;
         } while (D > 1.0f);
         float B = sinT * rsqrtf(D);
@@ -422,21 +510,43 @@ batch_kernel(const __grid_constant__ DevDomain P, long long nPhotons, uint64_t s
         const float ndz = r.dz * cosT - copysignf(fabsf(B), r.dz * B);
         r.ox = px; r.oy = py; r.oz = pz;
         r.dx = ndx; r.dy = ndy; r.dz = ndz;
-        tau = -__logf(fmaxf(TINY32, rng.real()));
+        tau = -__logf(fmaxf(TINY32, rng.real(k0, k1)));
         ext = 0.0f;
-        ray_start(r, G);
+        ray_start<REG>(r, G);
         state = ST_MARCH;
       }
     }
   }
+  (void)zTop;
 
-  // ---- flush event counters: warp shuffle reduce, one atomic per warp ----
+  // ---- flush: event counters (warp shuffle reduce, one atomic per warp) ----
+  {
+    unsigned long long v[4] = {cnt.crossings, cnt.scatters, cnt.leRays, cnt.leCrossings};
+    const int slot[4] = {CNT_CROSSINGS, CNT_SCATTERS, CNT_LE_RAYS, CNT_LE_CROSSINGS};
 #pragma unroll
-  for (int i = 0; i < CNT_N; ++i) {
-    unsigned long long v = cnt.c[i];
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(FULL, v, o);
-    if (lane == 0 && v) atomicAdd(&P.counters[i], v);
+    for (int i = 0; i < 4; ++i) {
+      for (int o = 16; o > 0; o >>= 1) v[i] += __shfl_down_sync(FULL, v[i], o);
+      if (lane == 0 && v[i]) atomicAdd(&P.counters[slot[i]], v[i]);
+    }
   }
+  __syncthreads();
+  if (threadIdx.x < CNT_N && sCnt[threadIdx.x]) atomicAdd(&P.counters[threadIdx.x], (unsigned long long)sCnt[threadIdx.x]);
+  // ---- flush: privatised tallies, once per block, into the f64 tally buffer ----
+  if (T.sFlux)
+    for (int i = threadIdx.x; i < 3 * cols; i += THREADS) {
+      const float v = T.sFlux[i];
+      if (v != 0.0f) atomicAdd(&P.tally[P.offFluxUp + i], (double)v);       // fluxUp|fluxDown|fluxAbs are contiguous
+    }
+  if (T.sVol)
+    for (int i = threadIdx.x; i < cells; i += THREADS) {
+      const float v = T.sVol[i];
+      if (v != 0.0f) atomicAdd(&P.tally[P.offVolAbs + i], (double)v);
+    }
+  if (T.sInt)
+    for (int i = threadIdx.x; i < cols * P.nDir; i += THREADS) {
+      const float v = T.sInt[i];
+      if (v != 0.0f) atomicAdd(&P.tally[P.offInt + i], (double)v);
+    }
   if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&P.tally[P.offPhotons], (double)nPhotons);
 }
 
@@ -448,22 +558,43 @@ __global__ void philox_kat_kernel(uint64_t seed, uint64_t photon, int n, uint32_
 
 }  // namespace mcbfast
 
+#include <cstdlib>
+
+template <bool REG>
+static void launch(const DevDomain &P, long long nPhotons, uint64_t seed, uint64_t firstPhotonId, int numSMs,
+                   unsigned long long *workCounter, cudaStream_t stream) {
+  constexpr int THREADS = 128;
+  auto kernel = mcbfast::batch_kernel<THREADS, REG>;
+  // shared-memory plan: privatise the tallies when the column / cell grid is small enough to be an
+  // atomic hot spot (homogeneous slabs, the 32-column step cloud); large grids spread their
+  // atomics over many L2 lines and go straight to the f64 buffer.
+  const int cols = P.nx * P.ny, cells = cols * P.nz;
+  mcbfast::SmemPlan plan{-1, -1, -1, -1, 0};
+  int off = 0;
+  if (!REG) { plan.edgesOff = off; off += P.nx + P.ny + P.nz + 3; }
+  const int budgetFloats = 9 * 1024;            // 36 KB per block keeps >= 5 blocks/SM resident
+  if (3 * cols <= 3 * 1024 && off + 3 * cols <= budgetFloats) { plan.fluxOff = off; off += 3 * cols; }
+  if (cells <= 8192 && off + cells <= budgetFloats) { plan.volOff = off; off += cells; }
+  if (P.nDir > 0 && cols * P.nDir <= 2048 && off + cols * P.nDir <= budgetFloats) { plan.intOff = off; off += cols * P.nDir; }
+  plan.totalFloats = off;
+  const size_t smem = sizeof(float) * (size_t)off;
+  cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+  int blocksPerSM = 1;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocksPerSM, kernel, THREADS, smem) != cudaSuccess || blocksPerSM < 1)
+    blocksPerSM = 1;
+  const long long want = (nPhotons + THREADS - 1) / THREADS;
+  const long long cap = (long long)numSMs * blocksPerSM;    // persistent: every CTA resident, whole waves only
+  const int blocks = (int)(want < cap ? want : cap);
+  static int park = -1;
+  if (park < 0) { const char *e = getenv("MCB_PARK_THRESHOLD"); park = e ? atoi(e) : 16; if (park < 1) park = 1; if (park > 32) park = 32; }
+  kernel<<<blocks, THREADS, smem, stream>>>(P, nPhotons, seed, firstPhotonId, workCounter, park, plan);
+}
+
 void mcb_launch_fast_batch(const DevDomain &P, long long nPhotons, uint64_t seed, uint64_t firstPhotonId,
                            int numSMs, unsigned long long *workCounter, cudaStream_t stream) {
   if (nPhotons <= 0) return;
-  constexpr int THREADS = 128;
-  const size_t smem = sizeof(float) * (size_t)(P.nx + P.ny + P.nz + 3);
-  static int blocksPerSM = 0;
-  if (blocksPerSM == 0) {
-    cudaFuncSetAttribute(mcbfast::batch_kernel<THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocksPerSM, mcbfast::batch_kernel<THREADS>, THREADS, smem) != cudaSuccess ||
-        blocksPerSM < 1)
-      blocksPerSM = 1;
-  }
-  long long want = (nPhotons + THREADS - 1) / THREADS;
-  long long cap = (long long)numSMs * blocksPerSM;          // persistent: every CTA resident, whole waves only
-  const int blocks = (int)(want < cap ? want : cap);
-  mcbfast::batch_kernel<THREADS><<<blocks, THREADS, smem, stream>>>(P, nPhotons, seed, firstPhotonId, workCounter, 12);
+  if (P.xyRegular && P.zRegular) launch<true>(P, nPhotons, seed, firstPhotonId, numSMs, workCounter, stream);
+  else launch<false>(P, nPhotons, seed, firstPhotonId, numSMs, workCounter, stream);
 }
 
 void mcb_launch_philox_kat(uint64_t seed, uint64_t photon, int n, uint32_t *out, cudaStream_t stream) {
