@@ -1,0 +1,182 @@
+! mcbrat_cuda_mod.f90 -- ISO_C_BINDING interface to libmcbrat_cuda.so (include/mcbrat_cuda.h).
+!
+! This is the reference-side binding a maintainer adds to MCBRaT3D: the module below is `use`d
+! by Integrators/monteCarloRadiativeTransfer.f95, whose public procedures keep their signatures
+! (INT:129-132, 209-218, 845-865, 1046-1073, 1486) while their bodies call these routines.
+! NOTE: no Fortran compiler exists in the build image of this repository, so this file is
+! reviewed but not compiled here; tests exercise the identical C ABI through ctypes.
+module mcbrat_cuda
+  use, intrinsic :: iso_c_binding
+  implicit none
+  private
+
+  integer(c_int), parameter, public :: MCB_ARITH_FAST = 0, MCB_ARITH_REFERENCE = 1
+
+  type, bind(C), public :: mcb_options
+    integer(c_int32_t) :: useRayTracing
+    integer(c_int32_t) :: useRussianRoulette
+    real(c_float)      :: russianRouletteW
+    integer(c_int32_t) :: useRussianRouletteForIntensity
+    real(c_float)      :: zetaMin
+    integer(c_int32_t) :: useHybridPhaseFunsForIntenCalcs
+    integer(c_int32_t) :: numOrdersOrigPhaseFunIntenCalcs
+    integer(c_int32_t) :: limitIntensityContributions
+    real(c_float)      :: maxIntensityContribution
+    real(c_float)      :: LW_flag
+    integer(c_int32_t) :: arithmetic
+    integer(c_int32_t) :: reserved(5)
+  end type mcb_options
+
+  public :: mcb_create, mcb_destroy, mcb_last_error, mcb_set_grid, mcb_set_optics, mcb_set_inverse_table, &
+            mcb_set_forward_table, mcb_set_views, mcb_default_options, mcb_set_options,                  &
+            mcb_set_solar_source, mcb_set_thermal_source, mcb_run_batch, mcb_get_results,                &
+            mcb_tally_buffer, mcb_synchronize, mcb_status_to_message
+
+  interface
+    integer(c_int) function mcb_create(device, handle) bind(C, name="mcb_create")
+      import :: c_int, c_ptr
+      integer(c_int), value :: device
+      type(c_ptr), intent(out) :: handle
+    end function
+    integer(c_int) function mcb_destroy(handle) bind(C, name="mcb_destroy")
+      import :: c_int, c_ptr
+      type(c_ptr), value :: handle
+    end function
+    integer(c_int) function mcb_last_error(handle, buf, len) bind(C, name="mcb_last_error")
+      import :: c_int, c_ptr, c_char
+      type(c_ptr), value :: handle
+      character(kind=c_char), intent(out) :: buf(*)
+      integer(c_int), value :: len
+    end function
+    integer(c_int) function mcb_synchronize(handle) bind(C, name="mcb_synchronize")
+      import :: c_int, c_ptr
+      type(c_ptr), value :: handle
+    end function
+    integer(c_int) function mcb_set_grid(handle, nx, ny, nz, xEdges, yEdges, zEdges) bind(C, name="mcb_set_grid")
+      import :: c_int, c_ptr, c_double
+      type(c_ptr), value :: handle
+      integer(c_int), value :: nx, ny, nz
+      real(c_double), intent(in) :: xEdges(*), yEdges(*), zEdges(*)
+    end function
+    integer(c_int) function mcb_set_optics(handle, nc, totalExt, cumExt, ssa, phaseIdx, albedo) &
+        bind(C, name="mcb_set_optics")
+      import :: c_int, c_ptr, c_double, c_int32_t
+      type(c_ptr), value :: handle
+      integer(c_int), value :: nc
+      real(c_double), intent(in) :: totalExt(*), cumExt(*), ssa(*)
+      integer(c_int32_t), intent(in) :: phaseIdx(*)
+      real(c_double), value :: albedo
+    end function
+    integer(c_int) function mcb_set_inverse_table(handle, comp, nS, nE, T) bind(C, name="mcb_set_inverse_table")
+      import :: c_int, c_ptr, c_float
+      type(c_ptr), value :: handle
+      integer(c_int), value :: comp, nS, nE
+      real(c_float), intent(in) :: T(*)
+    end function
+    integer(c_int) function mcb_set_forward_table(handle, comp, nS, nE, P, Porig) bind(C, name="mcb_set_forward_table")
+      import :: c_int, c_ptr, c_float
+      type(c_ptr), value :: handle
+      integer(c_int), value :: comp, nS, nE
+      real(c_float), intent(in) :: P(*), Porig(*)
+    end function
+    integer(c_int) function mcb_set_views(handle, nDir, dirCos) bind(C, name="mcb_set_views")
+      import :: c_int, c_ptr, c_float
+      type(c_ptr), value :: handle
+      integer(c_int), value :: nDir
+      real(c_float), intent(in) :: dirCos(*)
+    end function
+    subroutine mcb_default_options(o) bind(C, name="mcb_default_options")
+      import :: mcb_options
+      type(mcb_options), intent(out) :: o
+    end subroutine
+    integer(c_int) function mcb_set_options(handle, o) bind(C, name="mcb_set_options")
+      import :: c_int, c_ptr, mcb_options
+      type(c_ptr), value :: handle
+      type(mcb_options), intent(in) :: o
+    end function
+    integer(c_int) function mcb_set_solar_source(handle, solarMu, solarAzimuthDeg) bind(C, name="mcb_set_solar_source")
+      import :: c_int, c_ptr, c_float
+      type(c_ptr), value :: handle
+      real(c_float), value :: solarMu, solarAzimuthDeg
+    end function
+    integer(c_int) function mcb_set_thermal_source(handle, fracAtmsPower, voxelCDF) bind(C, name="mcb_set_thermal_source")
+      import :: c_int, c_ptr, c_double
+      type(c_ptr), value :: handle
+      real(c_double), value :: fracAtmsPower
+      real(c_double), intent(in) :: voxelCDF(*)
+    end function
+    integer(c_int) function mcb_run_batch(handle, nPhotons, seed, firstPhotonId, nProcessed) bind(C, name="mcb_run_batch")
+      import :: c_int, c_ptr, c_int64_t
+      type(c_ptr), value :: handle
+      integer(c_int64_t), value :: nPhotons, seed, firstPhotonId
+      integer(c_int64_t), intent(out) :: nProcessed
+    end function
+    integer(c_int) function mcb_get_results(handle, nPhotonsNormalise, fluxUp, fluxDown, fluxAbsorbed, &
+                                            volumeAbsorption, intensity, intensityByComponent) bind(C, name="mcb_get_results")
+      import :: c_int, c_ptr, c_int64_t
+      type(c_ptr), value :: handle
+      integer(c_int64_t), value :: nPhotonsNormalise
+      type(c_ptr), value :: fluxUp, fluxDown, fluxAbsorbed, volumeAbsorption, intensity, intensityByComponent
+    end function
+    integer(c_int) function mcb_tally_buffer(handle, devicePtr, nDoubles) bind(C, name="mcb_tally_buffer")
+      import :: c_int, c_ptr, c_int64_t
+      type(c_ptr), value :: handle
+      type(c_ptr), intent(out) :: devicePtr
+      integer(c_int64_t), intent(out) :: nDoubles
+    end function
+  end interface
+
+contains
+
+  ! Non-zero return code -> the text handed to setStateToFailure(status, ...) (ErrorMessages.f95:225)
+  function mcb_status_to_message(handle) result(msg)
+    type(c_ptr), intent(in) :: handle
+    character(len=512) :: msg
+    character(kind=c_char) :: buf(512)
+    integer :: i, rc
+    msg = ""
+    rc = mcb_last_error(handle, buf, 512_c_int)
+    do i = 1, 512
+      if (buf(i) == c_null_char) exit
+      msg(i:i) = buf(i)
+    end do
+  end function mcb_status_to_message
+
+end module mcbrat_cuda
+
+! ---------------------------------------------------------------------------------------------
+! How the reference's procedures call it (sketch of the replaced bodies; signatures unchanged):
+!
+!   type integrator            ! INT:40-117 gains one member
+!     type(c_ptr) :: gpu = c_null_ptr
+!     integer(8)  :: nextPhotonId = 0
+!   end type
+!
+!   function new_Integrator(atmosphere, status) result(new)                      ! INT:129-201
+!     ... existing getInfo_Domain calls for xPosition/yPosition/zPosition ...
+!     if (mcb_create(0_c_int, new%gpu) /= 0) call setStateToFailure(status, "new_Integrator: no CUDA device")
+!     if (mcb_set_grid(new%gpu, numX, numY, numZ, new%xPosition, new%yPosition, new%zPosition) /= 0) &
+!       call setStateToFailure(status, "new_Integrator: " // trim(mcb_status_to_message(new%gpu)))
+!   end function
+!
+!   subroutine computeRadiativeTransfer(thisIntegrator, thisDomain, randomNumbers, incomingPhotons, &
+!                                       numPhotonsPerBatch, numPhotonsProcessed, status)              ! INT:209-218
+!     call tabulateInversePhaseFunctions(thisDomain, thisIntegrator%minInverseTableSize, status)      ! INT:280 (host)
+!     call getInfo_Domain(thisDomain, albedo=albedo, totalExt=totalExt, cumExt=cumExt, ssa=ssa, &
+!                         phaseFuncI=phaseFuncI, inversePhaseFuncs=inversePhaseFuncs, status=status)  ! INT:441-443
+!     rc = mcb_set_optics(thisIntegrator%gpu, numComps, totalExt, cumExt, ssa, phaseFuncI, albedo)    ! once per domain
+!     do i = 1, numComps
+!       rc = mcb_set_inverse_table(thisIntegrator%gpu, i, size(inversePhaseFuncs(i)%values, 1), &
+!                                  size(inversePhaseFuncs(i)%values, 2), inversePhaseFuncs(i)%values)
+!     end do
+!     rc = mcb_set_solar_source(thisIntegrator%gpu, solarMu, solarAzimuth)     ! or mcb_set_thermal_source
+!     rc = mcb_run_batch(thisIntegrator%gpu, min(numPhotonsPerBatch, photonsLeft), seed, &
+!                        thisIntegrator%nextPhotonId, numPhotonsProcessed)
+!     if (rc /= 0) call setStateToFailure(status, "computeRadiativeTransfer: " // &
+!                                         trim(mcb_status_to_message(thisIntegrator%gpu)))
+!     thisIntegrator%nextPhotonId = thisIntegrator%nextPhotonId + numPhotonsProcessed
+!     rc = mcb_get_results(thisIntegrator%gpu, 0_c_int64_t, c_loc(thisIntegrator%fluxUp), c_loc(thisIntegrator%fluxDown), &
+!                          c_loc(thisIntegrator%fluxAbsorbed), c_loc(thisIntegrator%volumeAbsorption), &
+!                          c_loc(thisIntegrator%intensity), c_loc(thisIntegrator%intensityByComponent))
+!     ! reportResults (INT:845-1042) is unchanged: it copies out of thisIntegrator%fluxUp etc.
+!   end subroutine
