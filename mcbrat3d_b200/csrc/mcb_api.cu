@@ -173,8 +173,10 @@ int mcb_set_grid(mcb_handle *h, int nx, int ny, int nz,
   P.xyRegular = xyReg ? 1 : 0; P.zRegular = zReg ? 1 : 0;
   P.deltaX = xyReg ? (double)deltaX : 0.0; P.deltaY = xyReg ? (double)deltaY : 0.0;
   P.deltaZ = zReg ? (double)deltaZ : 0.0;
-  P.invDx = xyReg ? 1.0f / deltaX : 0.0f; P.invDy = xyReg ? 1.0f / deltaY : 0.0f;
-  P.invDz = zReg ? 1.0f / deltaZ : 0.0f;
+  P.fx0 = (float)P.x0; P.fy0 = (float)P.y0; P.fz0 = (float)P.z0;
+  P.fLx = (float)(P.xMax - P.x0); P.fLy = (float)(P.yMax - P.y0); P.fLz = (float)(P.zMax - P.z0);
+  P.fhx = (float)P.deltaX; P.fhy = (float)P.deltaY; P.fhz = (float)P.deltaZ;
+  P.finvLx = 1.0f / P.fLx; P.finvLy = 1.0f / P.fLy;
   h->haveGrid = true; h->haveOptics = false; h->haveSource = false;
   return 0;
 }
@@ -434,6 +436,11 @@ int mcb_get_counters(mcb_handle *h, mcb_counters *c) {
   c->topExits = (int64_t)v[CNT_TOP]; c->bad = (int64_t)v[CNT_BAD];
   c->leRays = (int64_t)v[CNT_LE_RAYS]; c->leCrossings = (int64_t)v[CNT_LE_CROSSINGS];
   c->rouletteKills = (int64_t)v[CNT_RR_KILLS];
+  c->reserved[0] = (int64_t)v[CNT_SURFACE_KILLS];                      // photons absorbed by the surface (weight <= tiny)
+  // the fast kernel does not count top exits while marching: every photon ends at the top, at the
+  // surface (weight <= tiny), by roulette, or is dropped as bad
+  if (h->P.opt.arithmetic == MCB_ARITH_FAST)
+    c->topExits = c->photons - c->rouletteKills - c->reserved[0] - c->bad;
   return 0;
 }
 

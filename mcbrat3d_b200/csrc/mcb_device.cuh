@@ -29,7 +29,8 @@ struct DevDomain {
   const float *ext32;                         // (nx,ny,nz)
   const float *cum32, *ssa32;                 // (nx,ny,nz,nc)
   const uint16_t *idx16;                      // (nx,ny,nz,nc)
-  float invDx, invDy, invDz;                  // regular-grid reciprocals (fast kernel)
+  float fx0, fy0, fz0, fLx, fLy, fLz;         // single-precision grid scalars (fast kernel, constant bank)
+  float fhx, fhy, fhz, finvLx, finvLy;
   // ---- tables ----
   const float *inv[MCB_MAX_COMP];  int invS[MCB_MAX_COMP];
   const float *fwd[MCB_MAX_COMP];  const float *fwdOrig[MCB_MAX_COMP];  int fwdS[MCB_MAX_COMP];
@@ -50,7 +51,7 @@ struct DevDomain {
 };
 
 enum { CNT_PHOTONS = 0, CNT_CROSSINGS, CNT_SCATTERS, CNT_SURFACE, CNT_TOP, CNT_BAD,
-       CNT_LE_RAYS, CNT_LE_CROSSINGS, CNT_RR_KILLS, CNT_N };
+       CNT_LE_RAYS, CNT_LE_CROSSINGS, CNT_RR_KILLS, CNT_SURFACE_KILLS, CNT_N };
 
 // ---------------------------------------------------------------------------------------
 // Philox4x32-10 counter-based generator (Salmon et al. 2011).  One stream per photon:

@@ -38,12 +38,13 @@ struct SmemPlan {
 };
 
 struct Rng {
-  uint32_t c0, c1, blk, b0, b1, b2, b3;
-  int have;
-  __device__ __forceinline__ void init(uint64_t photon) {
-    c0 = (uint32_t)photon; c1 = (uint32_t)(photon >> 32); blk = 0; have = 0;
-  }
-  __device__ __forceinline__ void refill(uint32_t k0, uint32_t k1) {
+  uint32_t c0, c1, blk;
+  __device__ __forceinline__ void init(uint64_t photon) { c0 = (uint32_t)photon; c1 = (uint32_t)(photon >> 32); blk = 0; }
+  // One Philox4x32-10 block = four uniform reals.  Every call site is reached by all the lanes that
+  // take part in the event together, so the ten rounds run convergently (v2 refilled inside real():
+  // each lane ran dry at a different draw and the rounds executed with 3-5 active lanes, 19 % of all
+  // warp instructions).
+  __device__ __forceinline__ float4 block(uint32_t k0, uint32_t k1) {
     uint32_t x0 = c0, x1 = c1, x2 = blk, x3 = 0u, a = k0, b = k1;
 #pragma unroll
     for (int r = 0; r < 10; ++r) {
@@ -53,19 +54,15 @@ struct Rng {
       x0 = y0; x1 = lo1; x2 = y2; x3 = lo0;
       a += 0x9E3779B9u; b += 0xBB67AE85u;
     }
-    b0 = x0; b1 = x1; b2 = x2; b3 = x3; blk++; have = 4;
-  }
-  // f32 in [0,1] built from 32 bits (RNG:286-300)
-  __device__ __forceinline__ float real(uint32_t k0, uint32_t k1) {
-    if (have == 0) refill(k0, k1);
-    have--;
-    const uint32_t r = b0; b0 = b1; b1 = b2; b2 = b3;
-    return __uint2float_rn(r) * 2.3283064365386963e-10f;
+    blk++;
+    // f32 in [0,1] built from 32 bits (RNG:286-300)
+    return make_float4(__uint2float_rn(x0) * 2.3283064365386963e-10f, __uint2float_rn(x1) * 2.3283064365386963e-10f,
+                       __uint2float_rn(x2) * 2.3283064365386963e-10f, __uint2float_rn(x3) * 2.3283064365386963e-10f);
   }
 };
 
 struct Ray {
-  float ox, oy, oz;        // leg origin (x, y shifted by whole domain periods when wrapping)
+  float ox, oy, oz;        // leg origin (irregular grids: x, y shifted by whole domain periods when wrapping)
   float dx, dy, dz;        // direction cosines
   float rx, ry, rz;        // reciprocal direction cosines (FLT_MAX-guarded)
   float t;                 // distance along the leg
@@ -74,62 +71,93 @@ struct Ray {
 };
 
 struct Grid {
-  const float *sx, *sy, *sz;     // shared-memory edges (irregular grids)
-  int nx, ny, nz;
-  float x0, y0, z0, Lx, Ly, Lz;
-  float hx, hy, hz;              // regular spacing
-};
+  const float *sx, *sy, *sz;     // shared-memory edges (irregular grids); every scalar of the grid is a
+};                               // single-precision field of the DevDomain parameter block (constant bank)
 
 __device__ __forceinline__ float safe_rcp(float d) {
-  return fabsf(d) >= 2.0f * TINY32 ? 1.0f / d : FLT_MAX;      // OPT:1705-1712 zero-direction guard
+  return fabsf(d) >= 2.0f * TINY32 ? __fdividef(1.0f, d) : FLT_MAX;      // OPT:1705-1712 zero-direction guard
 }
 
 template <bool REG>
-__device__ __forceinline__ float edge_x(const Grid &G, int i) { return REG ? fmaf((float)i, G.hx, G.x0) : G.sx[i]; }
+__device__ __forceinline__ float edge_x(const DevDomain &P, const Grid &G, int i) { return REG ? fmaf((float)i, P.fhx, P.fx0) : G.sx[i]; }
 template <bool REG>
-__device__ __forceinline__ float edge_y(const Grid &G, int i) { return REG ? fmaf((float)i, G.hy, G.y0) : G.sy[i]; }
+__device__ __forceinline__ float edge_y(const DevDomain &P, const Grid &G, int i) { return REG ? fmaf((float)i, P.fhy, P.fy0) : G.sy[i]; }
 template <bool REG>
-__device__ __forceinline__ float edge_z(const Grid &G, int i) { return REG ? fmaf((float)i, G.hz, G.z0) : G.sz[i]; }
+__device__ __forceinline__ float edge_z(const DevDomain &P, const Grid &G, int i) { return REG ? fmaf((float)i, P.fhz, P.fz0) : G.sz[i]; }
 
 template <bool REG>
-__device__ __forceinline__ void ray_start(Ray &r, const Grid &G) {
+__device__ __forceinline__ void ray_start(Ray &r, const DevDomain &P, const Grid &G) {
   r.rx = safe_rcp(r.dx); r.ry = safe_rcp(r.dy); r.rz = safe_rcp(r.dz);
   r.t = 0.0f;
-  r.tx = r.rx == FLT_MAX ? FLT_MAX : fmaxf((edge_x<REG>(G, r.ix + (r.dx >= 0.0f ? 1 : 0)) - r.ox) * r.rx, 0.0f);
-  r.ty = r.ry == FLT_MAX ? FLT_MAX : fmaxf((edge_y<REG>(G, r.iy + (r.dy >= 0.0f ? 1 : 0)) - r.oy) * r.ry, 0.0f);
-  r.tz = r.rz == FLT_MAX ? FLT_MAX : fmaxf((edge_z<REG>(G, r.iz + (r.dz >= 0.0f ? 1 : 0)) - r.oz) * r.rz, 0.0f);
+  r.tx = r.rx == FLT_MAX ? FLT_MAX : fmaxf((edge_x<REG>(P, G, r.ix + (r.dx >= 0.0f ? 1 : 0)) - r.ox) * r.rx, 0.0f);
+  r.ty = r.ry == FLT_MAX ? FLT_MAX : fmaxf((edge_y<REG>(P, G, r.iy + (r.dy >= 0.0f ? 1 : 0)) - r.oy) * r.ry, 0.0f);
+  r.tz = r.rz == FLT_MAX ? FLT_MAX : fmaxf((edge_z<REG>(P, G, r.iz + (r.dz >= 0.0f ? 1 : 0)) - r.oz) * r.rz, 0.0f);
+}
+
+// Position on the leg, folded back into the periodic domain.  Regular grids never shift the origin
+// while marching (their face distances are incremental), so the fold happens here, once per event.
+template <bool REG>
+__device__ __forceinline__ void ray_position(const Ray &r, const DevDomain &P, float &px, float &py, float &pz) {
+  px = fmaf(r.t, r.dx, r.ox); py = fmaf(r.t, r.dy, r.oy); pz = fmaf(r.t, r.dz, r.oz);
+  if (REG) {
+    px -= P.fLx * floorf((px - P.fx0) * P.finvLx);
+    py -= P.fLy * floorf((py - P.fy0) * P.finvLy);
+  }
 }
 
 // Cross the face(s) reached at distance tmin: branch-free on all three axes (every lane runs the
 // same instructions; the axis actually crossed is selected by predicates).  Returns 0 inside,
 // 1 out the top, 2 out the bottom.
 template <bool REG>
-__device__ __forceinline__ int ray_advance(Ray &r, const Grid &G, float tmin) {
+__device__ __forceinline__ int ray_advance(Ray &r, const DevDomain &P, const Grid &G, float tmin) {
   r.t = tmin;
-  {
-    const bool c = r.tx <= tmin, pos = r.dx >= 0.0f;
-    int i = r.ix + (c ? (pos ? 1 : -1) : 0);
-    float o = r.ox;
-    if (i >= G.nx) { i = 0; o -= G.Lx; }
-    if (i < 0) { i = G.nx - 1; o += G.Lx; }
-    const float nt = REG ? r.tx + G.hx * fabsf(r.rx) : (G.sx[i + (pos ? 1 : 0)] - o) * r.rx;
-    r.tx = c ? nt : r.tx; r.ix = i; r.ox = o;
-  }
-  {
-    const bool c = r.ty <= tmin, pos = r.dy >= 0.0f;
-    int i = r.iy + (c ? (pos ? 1 : -1) : 0);
-    float o = r.oy;
-    if (i >= G.ny) { i = 0; o -= G.Ly; }
-    if (i < 0) { i = G.ny - 1; o += G.Ly; }
-    const float nt = REG ? r.ty + G.hy * fabsf(r.ry) : (G.sy[i + (pos ? 1 : 0)] - o) * r.ry;
-    r.ty = c ? nt : r.ty; r.iy = i; r.oy = o;
-  }
-  {
-    const bool c = r.tz <= tmin, pos = r.dz >= 0.0f;
-    const int i = r.iz + (c ? (pos ? 1 : -1) : 0);
-    if ((unsigned)i >= (unsigned)G.nz) return pos ? 1 : 2;
-    const float nt = REG ? r.tz + G.hz * fabsf(r.rz) : (G.sz[i + (pos ? 1 : 0)] - r.oz) * r.rz;
-    r.tz = c ? nt : r.tz; r.iz = i;
+  if (REG) {
+    {
+      const bool c = r.tx <= tmin;
+      int i = r.ix + (c ? (r.dx >= 0.0f ? 1 : -1) : 0);
+      i = i >= P.nx ? 0 : i;
+      i = i < 0 ? P.nx - 1 : i;
+      r.tx = c ? fmaf(P.fhx, fabsf(r.rx), r.tx) : r.tx; r.ix = i;
+    }
+    {
+      const bool c = r.ty <= tmin;
+      int i = r.iy + (c ? (r.dy >= 0.0f ? 1 : -1) : 0);
+      i = i >= P.ny ? 0 : i;
+      i = i < 0 ? P.ny - 1 : i;
+      r.ty = c ? fmaf(P.fhy, fabsf(r.ry), r.ty) : r.ty; r.iy = i;
+    }
+    {
+      const bool c = r.tz <= tmin, pos = r.dz >= 0.0f;
+      const int i = r.iz + (c ? (pos ? 1 : -1) : 0);
+      if ((unsigned)i >= (unsigned)P.nz) return pos ? 1 : 2;
+      r.tz = c ? fmaf(P.fhz, fabsf(r.rz), r.tz) : r.tz; r.iz = i;
+    }
+  } else {
+    {
+      const bool c = r.tx <= tmin, pos = r.dx >= 0.0f;
+      int i = r.ix + (c ? (pos ? 1 : -1) : 0);
+      float o = r.ox;
+      if (i >= P.nx) { i = 0; o -= P.fLx; }
+      if (i < 0) { i = P.nx - 1; o += P.fLx; }
+      const float nt = (G.sx[i + (pos ? 1 : 0)] - o) * r.rx;
+      r.tx = c ? nt : r.tx; r.ix = i; r.ox = o;
+    }
+    {
+      const bool c = r.ty <= tmin, pos = r.dy >= 0.0f;
+      int i = r.iy + (c ? (pos ? 1 : -1) : 0);
+      float o = r.oy;
+      if (i >= P.ny) { i = 0; o -= P.fLy; }
+      if (i < 0) { i = P.ny - 1; o += P.fLy; }
+      const float nt = (G.sy[i + (pos ? 1 : 0)] - o) * r.ry;
+      r.ty = c ? nt : r.ty; r.iy = i; r.oy = o;
+    }
+    {
+      const bool c = r.tz <= tmin, pos = r.dz >= 0.0f;
+      const int i = r.iz + (c ? (pos ? 1 : -1) : 0);
+      if ((unsigned)i >= (unsigned)P.nz) return pos ? 1 : 2;
+      const float nt = (G.sz[i + (pos ? 1 : 0)] - r.oz) * r.rz;
+      r.tz = c ? nt : r.tz; r.iz = i;
+    }
   }
   return 0;
 }
@@ -137,22 +165,22 @@ __device__ __forceinline__ int ray_advance(Ray &r, const Grid &G, float tmin) {
 // Trace to the boundary or to an optical-depth target (the local-estimate rays, INT:1734-1739,
 // 1764-1795).  Returns the accumulated optical depth; where = 0 stopped at target, 1 top, 2 bottom.
 template <bool REG>
-__device__ float ray_trace(Ray &r, const Grid &G, const float *__restrict__ ext32, bool hasTarget, float target,
+__device__ float ray_trace(Ray &r, const DevDomain &P, const Grid &G, const float *__restrict__ ext32, bool hasTarget, float target,
                            int &where, unsigned &crossings) {
   float ext = 0.0f;
   for (;;) {
     const float tmin = fminf(r.tx, fminf(r.ty, r.tz));
     const float s = fmaxf(tmin - r.t, 0.0f);
-    const float sig = __ldg(&ext32[r.ix + G.nx * (r.iy + G.ny * r.iz)]);
+    const float sig = __ldg(&ext32[r.ix + P.nx * (r.iy + P.ny * r.iz)]);
     crossings++;
     const float e2 = fmaf(s, sig, ext);
     if (hasTarget && e2 > target) {
-      r.t += (target - ext) / sig;
+      r.t += __fdividef(target - ext, sig);
       where = 0;
       return target;
     }
     ext = e2;
-    const int out = ray_advance<REG>(r, G, tmin);
+    const int out = ray_advance<REG>(r, P, G, tmin);
     if (out) { where = out; return ext; }
   }
 }
@@ -206,8 +234,9 @@ template <bool REG>
 __device__ void local_estimate(const DevDomain &P, const Grid &G, const Tally &T, Rng &rng, uint32_t k0, uint32_t k1,
                                const Ray &r0, float px, float py, float pz,
                                float w, int component, int tallyComponent, int order, Counts &cnt) {
-  const int cell = r0.ix + G.nx * (r0.iy + G.ny * r0.iz);
+  const int cell = r0.ix + P.nx * (r0.iy + P.ny * r0.iz);
   const size_t cells = (size_t)P.nx * P.ny * P.nz;
+  float4 u = make_float4(0.f, 0.f, 0.f, 0.f);
   for (int i = 0; i < P.nDir; ++i) {
     const float vx = P.viewDir[3 * i], vy = P.viewDir[3 * i + 1], vz = P.viewDir[3 * i + 2];
     float npf;
@@ -238,29 +267,32 @@ __device__ void local_estimate(const DevDomain &P, const Grid &G, const Tally &T
     Ray r;
     r.ox = px; r.oy = py; r.oz = pz; r.dx = vx; r.dy = vy; r.dz = vz;
     r.ix = r0.ix; r.iy = r0.iy; r.iz = r0.iz;
-    ray_start<REG>(r, G);
+    ray_start<REG>(r, P, G);
     int where = 0;
     float contribution;
     cnt.leRays++;
     if (!P.opt.useRussianRouletteForIntensity) {                                 // INT:1729-1752
-      const float tau = ray_trace<REG>(r, G, P.ext32, false, 0.0f, where, cnt.leCrossings);
+      const float tau = ray_trace<REG>(r, P, G, P.ext32, false, 0.0f, where, cnt.leCrossings);
       contribution = w * npf * __expf(-tau);
     } else {                                                                     // INT:1753-1813
-      const float tauFree = -__logf(fmaxf(TINY32, rng.real(k0, k1)));
+      if ((i & 1) == 0) u = rng.block(k0, k1);          // one Philox block serves two directions
+      const float uFree = (i & 1) ? u.z : u.x, uTest = (i & 1) ? u.w : u.y;
+      const float tauFree = -__logf(fmaxf(TINY32, uFree));
       if (PI32 * npf <= P.opt.zetaMin) {                                         // Iwabuchi (2006) Eq 13
-        ray_trace<REG>(r, G, P.ext32, true, tauFree, where, cnt.leCrossings);
-        const float test = rng.real(k0, k1);
-        contribution = (test <= PI32 * npf / P.opt.zetaMin && where == 1) ? w * P.opt.zetaMin / PI32 : 0.0f;
+        ray_trace<REG>(r, P, G, P.ext32, true, tauFree, where, cnt.leCrossings);
+        contribution = (uTest <= PI32 * npf / P.opt.zetaMin && where == 1) ? w * P.opt.zetaMin / PI32 : 0.0f;
       } else {                                                                   // Eq 14
         const float tauMax = -__logf(P.opt.zetaMin / fmaxf(TINY32, PI32 * npf));
-        const float tau = ray_trace<REG>(r, G, P.ext32, true, tauMax, where, cnt.leCrossings);
+        const float tau = ray_trace<REG>(r, P, G, P.ext32, true, tauMax, where, cnt.leCrossings);
         if (where == 1) {
           contribution = w * npf * __expf(-tau);
         } else if (where == 0) {
           // continue from where the first trace stopped (INT:1793-1795)
-          r.ox = fmaf(r.t, r.dx, r.ox); r.oy = fmaf(r.t, r.dy, r.oy); r.oz = fmaf(r.t, r.dz, r.oz);
-          ray_start<REG>(r, G);
-          ray_trace<REG>(r, G, P.ext32, true, tauFree, where, cnt.leCrossings);
+          float qx, qy, qz;
+          ray_position<REG>(r, P, qx, qy, qz);
+          r.ox = qx; r.oy = qy; r.oz = qz;
+          ray_start<REG>(r, P, G);
+          ray_trace<REG>(r, P, G, P.ext32, true, tauFree, where, cnt.leCrossings);
           contribution = where == 1 ? w * P.opt.zetaMin / PI32 : 0.0f;
         } else {
           contribution = 0.0f;       // left through the surface before tauMax (zIndexF < zIndexMax)
@@ -273,22 +305,17 @@ __device__ void local_estimate(const DevDomain &P, const Grid &G, const Tally &T
                 (double)(contribution - P.opt.maxIntensityContribution));
       contribution = P.opt.maxIntensityContribution;
     }
-    if (contribution != 0.0f) add_intensity(P, T, i, r.ix + G.nx * r.iy, tallyComponent, contribution);
+    if (contribution != 0.0f) add_intensity(P, T, i, r.ix + P.nx * r.iy, tallyComponent, contribution);
   }
 }
 
-template <int THREADS, bool REG>
-__global__ void __launch_bounds__(THREADS, REG ? 5 : 4)
+template <int THREADS, bool REG, int MINBLOCKS>
+__global__ void __launch_bounds__(THREADS, MINBLOCKS)
 batch_kernel(const __grid_constant__ DevDomain P, long long nPhotons, uint64_t seed, uint64_t firstPhotonId,
              unsigned long long *workCounter, int parkThreshold, const SmemPlan plan) {
   extern __shared__ float smem[];
-  __shared__ unsigned sCnt[CNT_N];
   const int cols = P.nx * P.ny, cells = cols * P.nz;
   Grid G;
-  G.nx = P.nx; G.ny = P.ny; G.nz = P.nz;
-  G.x0 = (float)P.x0; G.y0 = (float)P.y0; G.z0 = (float)P.z0;
-  G.Lx = (float)(P.xMax - P.x0); G.Ly = (float)(P.yMax - P.y0); G.Lz = (float)(P.zMax - P.z0);
-  G.hx = (float)P.deltaX; G.hy = (float)P.deltaY; G.hz = (float)P.deltaZ;
   G.sx = G.sy = G.sz = nullptr;
   if (!REG) {
     float *sx = smem + plan.edgesOff, *sy = sx + (P.nx + 1), *sz = sy + (P.ny + 1);
@@ -305,18 +332,17 @@ batch_kernel(const __grid_constant__ DevDomain P, long long nPhotons, uint64_t s
   if (T.sFlux) for (int i = threadIdx.x; i < 3 * cols; i += THREADS) T.sFlux[i] = 0.0f;
   if (T.sVol) for (int i = threadIdx.x; i < cells; i += THREADS) T.sVol[i] = 0.0f;
   if (T.sInt) for (int i = threadIdx.x; i < cols * P.nDir; i += THREADS) T.sInt[i] = 0.0f;
-  if (threadIdx.x < CNT_N) sCnt[threadIdx.x] = 0u;
   __syncthreads();
 
   const int lane = threadIdx.x & 31;
   const float *__restrict__ ext32 = P.ext32;
   const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
-  const float zTop = G.z0 + G.Lz;
 
   Counts cnt{0u, 0u, 0u, 0u};
+  unsigned nSurface = 0u, nSurfaceKills = 0u, nRouletteKills = 0u;     // warp-uniform (ballot counts)
   Rng rng;
   Ray r;
-  float w = 0.0f, tau = 0.0f, ext = 0.0f;
+  float w = 0.0f, tau = 0.0f, ext = 0.0f, sigEv = 1.0f;
   int order = 0;
   int state = ST_DEAD;
   bool more = true;                      // photons may remain in the global counter
@@ -333,19 +359,21 @@ batch_kernel(const __grid_constant__ DevDomain P, long long nPhotons, uint64_t s
           const unsigned long long p = base + (unsigned long long)__popc(dead & ((1u << lane) - 1u));
           if (p < (unsigned long long)nPhotons) {
             rng.init(firstPhotonId + p);
-            float x01, y01, z01, mu, phi;
+            const float4 u = rng.block(k0, k1);
+            float x01, y01, z01, mu, phi, uTau;
             if (P.source == 0) {                                               // ILL:88-96
-              x01 = rng.real(k0, k1); y01 = rng.real(k0, k1); z01 = 1.0f - FLT_EPSILON;
+              x01 = u.x; y01 = u.y; z01 = 1.0f - FLT_EPSILON; uTau = u.z;
               mu = P.solarMu; phi = P.solarPhi;
             } else {                                                           // ILL:481-515
-              const float RN = rng.real(k0, k1);
-              if ((double)RN > P.fracAtmsPower) {
-                x01 = rng.real(k0, k1); y01 = rng.real(k0, k1);
-                do { mu = sqrtf(rng.real(k0, k1)); } while (!(fabsf(mu) > 2.0f * TINY32));
-                phi = rng.real(k0, k1) * 2.0f * PI32;
+              const float4 v = rng.block(k0, k1);
+              uTau = v.w;
+              if ((double)u.x > P.fracAtmsPower) {                             // surface emission
+                x01 = u.y; y01 = u.z;
+                mu = sqrtf(fmaxf(u.w, 1.0e-30f));                              // ILL:489-491 retries on mu ~ 0
+                phi = v.x * 2.0f * PI32;
                 z01 = 0.0f;
-              } else {
-                const float q = rng.real(k0, k1);
+              } else {                                                         // atmospheric emission
+                const float q = u.y;
                 const double *levelBase = P.voxelCDF + (size_t)(P.nx - 1) + (size_t)P.nx * (size_t)(P.ny - 1);
                 const int ik = cdf_search(levelBase, P.nz, (long long)cols, q);
                 const double *colBase = P.voxelCDF + (size_t)(P.nx - 1) + (size_t)cols * (size_t)(ik - 1);
@@ -353,27 +381,28 @@ batch_kernel(const __grid_constant__ DevDomain P, long long nPhotons, uint64_t s
                 const double *voxBase = P.voxelCDF + (size_t)P.nx * ((size_t)(ij - 1) + (size_t)P.ny * (size_t)(ik - 1));
                 const int ii = cdf_search(voxBase, P.nx, 1, q);
                 // uniform inside the chosen cell, nudged off its faces (ILL:500-505)
-                z01 = ((float)(ik - 1) + fminf(fmaxf(rng.real(k0, k1), 1e-6f), 1.0f - 1e-6f)) / (float)P.nz;
-                x01 = ((float)(ii - 1) + fminf(rng.real(k0, k1), 1.0f - 1e-6f)) / (float)P.nx;
-                y01 = ((float)(ij - 1) + fminf(rng.real(k0, k1), 1.0f - 1e-6f)) / (float)P.ny;
-                do { mu = 1.0f - 2.0f * rng.real(k0, k1); } while (!(fabsf(mu) > 2.0f * TINY32));
-                phi = rng.real(k0, k1) * 2.0f * PI32;
+                z01 = ((float)(ik - 1) + fminf(fmaxf(u.z, 1e-6f), 1.0f - 1e-6f)) / (float)P.nz;
+                x01 = ((float)(ii - 1) + fminf(u.w, 1.0f - 1e-6f)) / (float)P.nx;
+                y01 = ((float)(ij - 1) + fminf(v.x, 1.0f - 1e-6f)) / (float)P.ny;
+                mu = 1.0f - 2.0f * v.y;                                        // ILL:507-509 retries on mu ~ 0
+                if (!(fabsf(mu) > 2.0f * TINY32)) mu = 1.0e-30f;
+                phi = v.z * 2.0f * PI32;
               }
             }
             dir_from(mu, phi, r.dx, r.dy, r.dz);
             w = 1.0f; order = 0;
             // INT:478-494: unit square -> domain
-            r.ox = fmaf(x01, G.Lx, G.x0); r.oy = fmaf(y01, G.Ly, G.y0);
+            r.ox = fmaf(x01, P.fLx, P.fx0); r.oy = fmaf(y01, P.fLy, P.fy0);
             if (REG) {
               r.ix = min((int)(x01 * (float)P.nx), P.nx - 1);
               r.iy = min((int)(y01 * (float)P.ny), P.ny - 1);
-              r.oz = fmaf(z01, G.Lz, G.z0);
+              r.oz = fmaf(z01, P.fLz, P.fz0);
               r.iz = min((int)(z01 * (float)P.nz), P.nz - 1);
             } else {
               r.ix = find_cell(G.sx, P.nx, r.ox);
               r.iy = find_cell(G.sy, P.ny, r.oy);
               if (P.zRegular) {
-                r.oz = fmaf(z01, G.Lz, G.z0);
+                r.oz = fmaf(z01, P.fLz, P.fz0);
                 r.iz = find_cell(G.sz, P.nz, r.oz);
               } else {                                                         // INT:491-493
                 const float zs = z01 * (float)P.nz;
@@ -381,7 +410,6 @@ batch_kernel(const __grid_constant__ DevDomain P, long long nPhotons, uint64_t s
                 r.oz = G.sz[r.iz] + (zs - (float)r.iz) * (G.sz[r.iz + 1] - G.sz[r.iz]);
               }
             }
-            atomicAdd(&sCnt[CNT_PHOTONS], 1u);
             if (P.opt.LW_flag > 0.0f) {                                        // INT:504-542
               if (r.oz > 0.0f) {
                 add_flux(P, T, 2, r.ix + P.nx * r.iy, -1.0f);
@@ -390,9 +418,9 @@ batch_kernel(const __grid_constant__ DevDomain P, long long nPhotons, uint64_t s
               if (P.nDir > 0)
                 local_estimate<REG>(P, G, T, rng, k0, k1, r, r.ox, r.oy, r.oz, w, r.oz == 0.0f ? 0 : -1, 0, order, cnt);
             }
-            tau = -__logf(fmaxf(TINY32, rng.real(k0, k1)));                    // INT:554
+            tau = -__logf(fmaxf(TINY32, uTau));                                // INT:554
             ext = 0.0f;
-            ray_start<REG>(r, G);
+            ray_start<REG>(r, P, G);
             state = ST_MARCH;
           } else {
             state = ST_DONE;
@@ -419,52 +447,55 @@ batch_kernel(const __grid_constant__ DevDomain P, long long nPhotons, uint64_t s
           const float sig = __ldg(&ext32[r.ix + P.nx * (r.iy + P.ny * r.iz)]);
           cnt.crossings++;
           const float e2 = fmaf(s, sig, ext);
-          if (e2 > tau) {                                                      // OPT:1729-1738
-            r.t += (tau - ext) / sig;
+          if (e2 > tau) {                                                      // OPT:1729-1738; the step itself is
+            sigEv = sig;                                                       // finished in the event phase
             state = ST_SCATTER;
           } else {
             ext = e2;
-            const int out = ray_advance<REG>(r, G, tmin);
-            if (out == 1) {                                                    // INT:573-617
-              add_flux(P, T, 0, r.ix + P.nx * r.iy, w);
-              atomicAdd(&sCnt[CNT_TOP], 1u);
-              state = ST_DEAD;
-            } else if (out == 2) {
-              state = ST_SURFACE;
-            }
+            const int out = ray_advance<REG>(r, P, G, tmin);
+            if (out) state = out == 1 ? ST_DEAD + 16 : ST_SURFACE;             // 16: "left through the top", tallied below
           }
         }
       }
     }
 
     // ---- event phase ----
+    if (state == ST_DEAD + 16) {                                               // INT:573-617
+      float px, py, pz;
+      (void)px; (void)py; (void)pz;
+      add_flux(P, T, 0, r.ix + P.nx * r.iy, w);
+      state = ST_DEAD;
+    }
+    nSurface += __popc(__ballot_sync(FULL, state == ST_SURFACE));
     if (state == ST_SURFACE) {                                                 // INT:619-702
       add_flux(P, T, 1, r.ix + P.nx * r.iy, w);
-      atomicAdd(&sCnt[CNT_SURFACE], 1u);
       order++;
-      float mu;
-      do { mu = sqrtf(rng.real(k0, k1)); } while (!(fabsf(mu) > 2.0f * TINY32));
-      const float phi = 2.0f * PI32 * rng.real(k0, k1);
+      const float4 u = rng.block(k0, k1);
+      const float mu = sqrtf(fmaxf(u.x, 1.0e-30f));                            // INT:655-662 retries on mu ~ 0
+      const float phi = 2.0f * PI32 * u.y;
       w = (float)((double)w * P.albedo);
       if (w <= TINY32) {
-        state = ST_DEAD;
+        state = ST_DEAD + 32;                                                  // 32: absorbed by the surface
       } else {
-        r.ox = fmaf(r.t, r.dx, r.ox); r.oy = fmaf(r.t, r.dy, r.oy); r.oz = G.z0; r.iz = 0;
+        float px, py, pz;
+        ray_position<REG>(r, P, px, py, pz);
+        r.ox = px; r.oy = py; r.oz = P.fz0; r.iz = 0;
         dir_from(mu, phi, r.dx, r.dy, r.dz);
         if (P.nDir > 0) local_estimate<REG>(P, G, T, rng, k0, k1, r, r.ox, r.oy, r.oz, w, 0, 0, order, cnt);
-        tau = -__logf(fmaxf(TINY32, rng.real(k0, k1)));
+        tau = -__logf(fmaxf(TINY32, u.z));
         ext = 0.0f;
-        ray_start<REG>(r, G);
+        ray_start<REG>(r, P, G);
         state = ST_MARCH;
       }
     } else if (state == ST_SCATTER) {                                          // INT:703-821
       order++;
       cnt.scatters++;
+      r.t += __fdividef(tau - ext, sigEv);                                     // OPT:1731
       const int cell = r.ix + P.nx * (r.iy + P.ny * r.iz);
-      const float rnComp = rng.real(k0, k1);                                   // drawn even when nc == 1 (INT:759)
+      const float4 u = rng.block(k0, k1);                                      // component, roulette, angle, next tau
       int comp = 1;
       for (int c = 1; c < P.nc; ++c)                                           // findIndex on (0, cumExt(:)), NUM:262-315
-        if (rnComp >= __ldg(&P.cum32[cell + (size_t)cells * (size_t)(c - 1)])) comp = c + 1;
+        if (u.x >= __ldg(&P.cum32[cell + (size_t)cells * (size_t)(c - 1)])) comp = c + 1;
       const float ssa = __ldg(&P.ssa32[cell + (size_t)cells * (size_t)(comp - 1)]);
       if (ssa < 1.0f) {                                                        // INT:765-771
         const float absorbed = w * (1.0f - ssa);
@@ -472,20 +503,20 @@ batch_kernel(const __grid_constant__ DevDomain P, long long nPhotons, uint64_t s
         add_vol(P, T, cell, absorbed);
         w *= ssa;
       }
-      const float px = fmaf(r.t, r.dx, r.ox), py = fmaf(r.t, r.dy, r.oy), pz = fmaf(r.t, r.dz, r.oz);
+      float px, py, pz;
+      ray_position<REG>(r, P, px, py, pz);
       if (P.nDir > 0) local_estimate<REG>(P, G, T, rng, k0, k1, r, px, py, pz, w, comp, comp, order, cnt);   // INT:776-800
       if (P.opt.useRussianRoulette && w < P.opt.russianRouletteW * 0.5f) {     // INT:805-811
-        if (rng.real(k0, k1) >= w / P.opt.russianRouletteW) w = 0.0f; else w = P.opt.russianRouletteW;
+        if (u.y >= w / P.opt.russianRouletteW) w = 0.0f; else w = P.opt.russianRouletteW;
       }
       if (w <= TINY32) {
-        atomicAdd(&sCnt[CNT_RR_KILLS], 1u);
-        state = ST_DEAD;
+        state = ST_DEAD + 48;                                                  // 48: killed by roulette
       } else {
         const int c = comp - 1;
         const int pidx = (int)__ldg(&P.idx16[cell + (size_t)cells * (size_t)c]);
         const int nS = P.invS[c];
         const float *tab = P.inv[c] + (size_t)(pidx - 1) * nS;
-        const float rn = rng.real(k0, k1);                                     // computeScatteringAngle INT:1594-1621
+        const float rn = u.z;                                                  // computeScatteringAngle INT:1594-1621
         const int k = (int)(rn * (float)nS) + 1;
         float theta;
         if (k < nS) {
@@ -497,27 +528,31 @@ batch_kernel(const __grid_constant__ DevDomain P, long long nPhotons, uint64_t s
         float sinT, cosT;
         __sincosf(theta, &sinT, &cosT);
         float AX, AY, D;                                                       // next_direct INT:1921-1948
-        do {
-          AX = 1.0f - 2.0f * rng.real(k0, k1);
-          AY = 1.0f - 2.0f * rng.real(k0, k1);
-          D = AX * AX + AY * AY;
-        } while (D > 1.0f);
+        for (;;) {                                                             // one block = two tries
+          const float4 v = rng.block(k0, k1);
+          AX = 1.0f - 2.0f * v.x; AY = 1.0f - 2.0f * v.y; D = AX * AX + AY * AY;
+          if (D <= 1.0f) break;
+          AX = 1.0f - 2.0f * v.z; AY = 1.0f - 2.0f * v.w; D = AX * AX + AY * AY;
+          if (D <= 1.0f) break;
+        }
         float B = sinT * rsqrtf(D);
         AX *= B; AY *= B;
         B = r.dx * AX - r.dy * AY;
-        D = cosT - B / (1.0f + fabsf(r.dz));
+        D = cosT - __fdividef(B, 1.0f + fabsf(r.dz));
         const float ndx = r.dx * D + AX, ndy = r.dy * D - AY;
         const float ndz = r.dz * cosT - copysignf(fabsf(B), r.dz * B);
         r.ox = px; r.oy = py; r.oz = pz;
         r.dx = ndx; r.dy = ndy; r.dz = ndz;
-        tau = -__logf(fmaxf(TINY32, rng.real(k0, k1)));
+        tau = -__logf(fmaxf(TINY32, u.w));
         ext = 0.0f;
-        ray_start<REG>(r, G);
+        ray_start<REG>(r, P, G);
         state = ST_MARCH;
       }
     }
+    nSurfaceKills += __popc(__ballot_sync(FULL, state == ST_DEAD + 32));
+    nRouletteKills += __popc(__ballot_sync(FULL, state == ST_DEAD + 48));
+    if (state > ST_DONE) state = ST_DEAD;
   }
-  (void)zTop;
 
   // ---- flush: event counters (warp shuffle reduce, one atomic per warp) ----
   {
@@ -528,9 +563,13 @@ batch_kernel(const __grid_constant__ DevDomain P, long long nPhotons, uint64_t s
       for (int o = 16; o > 0; o >>= 1) v[i] += __shfl_down_sync(FULL, v[i], o);
       if (lane == 0 && v[i]) atomicAdd(&P.counters[slot[i]], v[i]);
     }
+    if (lane == 0) {                       // warp-uniform ballot counts
+      if (nSurface) atomicAdd(&P.counters[CNT_SURFACE], (unsigned long long)nSurface);
+      if (nRouletteKills) atomicAdd(&P.counters[CNT_RR_KILLS], (unsigned long long)nRouletteKills);
+      if (nSurfaceKills) atomicAdd(&P.counters[CNT_SURFACE_KILLS], (unsigned long long)nSurfaceKills);
+    }
   }
   __syncthreads();
-  if (threadIdx.x < CNT_N && sCnt[threadIdx.x]) atomicAdd(&P.counters[threadIdx.x], (unsigned long long)sCnt[threadIdx.x]);
   // ---- flush: privatised tallies, once per block, into the f64 tally buffer ----
   if (T.sFlux)
     for (int i = threadIdx.x; i < 3 * cols; i += THREADS) {
@@ -547,7 +586,10 @@ batch_kernel(const __grid_constant__ DevDomain P, long long nPhotons, uint64_t s
       const float v = T.sInt[i];
       if (v != 0.0f) atomicAdd(&P.tally[P.offInt + i], (double)v);
     }
-  if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&P.tally[P.offPhotons], (double)nPhotons);
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    atomicAdd(&P.tally[P.offPhotons], (double)nPhotons);
+    atomicAdd(&P.counters[CNT_PHOTONS], (unsigned long long)nPhotons);
+  }
 }
 
 __global__ void philox_kat_kernel(uint64_t seed, uint64_t photon, int n, uint32_t *out) {
@@ -560,11 +602,11 @@ __global__ void philox_kat_kernel(uint64_t seed, uint64_t photon, int n, uint32_
 
 #include <cstdlib>
 
-template <bool REG>
+template <bool REG, int MINBLOCKS>
 static void launch(const DevDomain &P, long long nPhotons, uint64_t seed, uint64_t firstPhotonId, int numSMs,
                    unsigned long long *workCounter, cudaStream_t stream) {
   constexpr int THREADS = 128;
-  auto kernel = mcbfast::batch_kernel<THREADS, REG>;
+  auto kernel = mcbfast::batch_kernel<THREADS, REG, MINBLOCKS>;
   // shared-memory plan: privatise the tallies when the column / cell grid is small enough to be an
   // atomic hot spot (homogeneous slabs, the 32-column step cloud); large grids spread their
   // atomics over many L2 lines and go straight to the f64 buffer.
@@ -572,7 +614,7 @@ static void launch(const DevDomain &P, long long nPhotons, uint64_t seed, uint64
   mcbfast::SmemPlan plan{-1, -1, -1, -1, 0};
   int off = 0;
   if (!REG) { plan.edgesOff = off; off += P.nx + P.ny + P.nz + 3; }
-  const int budgetFloats = 9 * 1024;            // 36 KB per block keeps >= 5 blocks/SM resident
+  const int budgetFloats = 9 * 1024;            // 36 KB per block keeps >= 6 blocks/SM resident
   if (3 * cols <= 3 * 1024 && off + 3 * cols <= budgetFloats) { plan.fluxOff = off; off += 3 * cols; }
   if (cells <= 8192 && off + cells <= budgetFloats) { plan.volOff = off; off += cells; }
   if (P.nDir > 0 && cols * P.nDir <= 2048 && off + cols * P.nDir <= budgetFloats) { plan.intOff = off; off += cols * P.nDir; }
@@ -593,8 +635,15 @@ static void launch(const DevDomain &P, long long nPhotons, uint64_t seed, uint64
 void mcb_launch_fast_batch(const DevDomain &P, long long nPhotons, uint64_t seed, uint64_t firstPhotonId,
                            int numSMs, unsigned long long *workCounter, cudaStream_t stream) {
   if (nPhotons <= 0) return;
-  if (P.xyRegular && P.zRegular) launch<true>(P, nPhotons, seed, firstPhotonId, numSMs, workCounter, stream);
-  else launch<false>(P, nPhotons, seed, firstPhotonId, numSMs, workCounter, stream);
+  static int occ = -1;               // register budget variant (tuning knob; default chosen from measurements)
+  if (occ < 0) { const char *e = getenv("MCB_BLOCKS_PER_SM"); occ = e ? atoi(e) : 6; }
+  if (P.xyRegular && P.zRegular) {
+    if (occ >= 8) launch<true, 8>(P, nPhotons, seed, firstPhotonId, numSMs, workCounter, stream);
+    else if (occ <= 5) launch<true, 5>(P, nPhotons, seed, firstPhotonId, numSMs, workCounter, stream);
+    else launch<true, 6>(P, nPhotons, seed, firstPhotonId, numSMs, workCounter, stream);
+  } else {
+    launch<false, 4>(P, nPhotons, seed, firstPhotonId, numSMs, workCounter, stream);
+  }
 }
 
 void mcb_launch_philox_kat(uint64_t seed, uint64_t photon, int n, uint32_t *out, cudaStream_t stream) {

@@ -113,25 +113,32 @@ def test_three_sigma_against_oracle(orc, name, make, source, views, n, arithmeti
                       np.maximum(oe, gerr["meanIntensity"]), 3.0)
 
 
-def test_fast_and_reference_arithmetic_agree_closely():
-    """Same Philox stream per photon: the two kernels follow the same histories except where
-    single-precision marching flips an event, so the means agree far inside the Monte Carlo error."""
+def test_fast_and_reference_arithmetic_agree():
+    """The two kernels share the per-photon Philox key but draw from it in a different order (the
+    fast kernel takes whole blocks at warp-convergent points), so their histories are independent
+    samples of the same problem: means agree within 4 sigma of the combined binomial error."""
     dom, case = domains.homogeneous_slab(ssa=0.99)
     out = {}
+    n = 1000000
     for arith in (MCB_ARITH_FAST, MCB_ARITH_REFERENCE):
         g = new_Integrator(dom)
         specifyParameters(g, minInverseTableSize=10001, arithmetic=arith)
         rs = new_RandomNumberSequence([10, 1, 0])
-        n = 400000
         ps = new_PhotonStream(0.5, 0.0, n, rs)
         computeRadiativeTransfer(g, dom, rs, ps, n)
         out[arith] = (reportResults(g, meanFluxUp=True, meanFluxDown=True, meanFluxAbsorbed=True), getCounters(g))
         finalize_Integrator(g)
     a, b = out[MCB_ARITH_FAST], out[MCB_ARITH_REFERENCE]
     for q in ("meanFluxUp", "meanFluxDown", "meanFluxAbsorbed"):
-        assert abs(float(a[0][q]) - float(b[0][q])) < 2e-4
-    assert abs(a[1]["scatters"] - b[1]["scatters"]) < 1e-3 * b[1]["scatters"]
+        p = float(b[0][q])
+        sigma = np.sqrt(2.0 * p * (1.0 - p) / n)            # weights are <= 1: binomial bound
+        assert abs(float(a[0][q]) - p) < 4.0 * sigma, (q, float(a[0][q]), p, sigma)
+    assert abs(a[1]["scatters"] - b[1]["scatters"]) < 5e-3 * b[1]["scatters"]
+    assert abs(a[1]["crossings"] - b[1]["crossings"]) < 5e-3 * b[1]["crossings"]
     assert a[1]["bad"] == 0
+    # every photon ends somewhere: top + roulette + absorbed at the surface (+ bad) = photons
+    for c in (a[1], b[1]):
+        assert c["photons"] == n
 
 
 def test_result_independent_of_batch_split():
