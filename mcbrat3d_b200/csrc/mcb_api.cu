@@ -144,6 +144,16 @@ int mcb_synchronize(mcb_handle *h) {
   return 0;
 }
 
+// Division by a launch-invariant divisor d for dividends n < 2^31 (Granlund & Montgomery 1994):
+// with l = ceil(log2 d) and M = ceil(2^(31+l) / d) < 2^32, floor(n / d) = (M * n) >> (31 + l).
+static void magic_divisor(uint32_t d, uint32_t *M, int *S) {
+  int l = 0;
+  while ((1ull << l) < d) ++l;
+  const unsigned long long num = 1ull << (31 + l);
+  *M = (uint32_t)((num + d - 1) / d);
+  *S = 31 + l;
+}
+
 int mcb_set_grid(mcb_handle *h, int nx, int ny, int nz,
                  const double *xEdges, const double *yEdges, const double *zEdges) {
   if (!h) return 1;
@@ -177,6 +187,9 @@ int mcb_set_grid(mcb_handle *h, int nx, int ny, int nz,
   P.fLx = (float)(P.xMax - P.x0); P.fLy = (float)(P.yMax - P.y0); P.fLz = (float)(P.zMax - P.z0);
   P.fhx = (float)P.deltaX; P.fhy = (float)P.deltaY; P.fhz = (float)P.deltaZ;
   P.finvLx = 1.0f / P.fLx; P.finvLy = 1.0f / P.fLy;
+  if ((long long)nx * ny * nz >= (1LL << 31)) FAIL(h, "mcb_set_grid: more than 2^31 cells");
+  magic_divisor((uint32_t)nx * (uint32_t)ny, &P.divColsM, &P.divColsS);
+  magic_divisor((uint32_t)nx, &P.divNxM, &P.divNxS);
   h->haveGrid = true; h->haveOptics = false; h->haveSource = false;
   return 0;
 }

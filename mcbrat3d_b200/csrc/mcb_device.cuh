@@ -31,6 +31,8 @@ struct DevDomain {
   const uint16_t *idx16;                      // (nx,ny,nz,nc)
   float fx0, fy0, fz0, fLx, fLy, fLz;         // single-precision grid scalars (fast kernel, constant bank)
   float fhx, fhy, fhz, finvLx, finvLy;
+  uint32_t divColsM, divNxM;                  // cell -> (ix,iy,iz): q = (M * n) >> S, exact for n < 2^31
+  int divColsS, divNxS;
   // ---- tables ----
   const float *inv[MCB_MAX_COMP];  int invS[MCB_MAX_COMP];
   const float *fwd[MCB_MAX_COMP];  const float *fwdOrig[MCB_MAX_COMP];  int fwdS[MCB_MAX_COMP];

@@ -94,47 +94,48 @@ __device__ __forceinline__ void ray_start(Ray &r, const DevDomain &P, const Grid
   r.tz = r.rz == FLT_MAX ? FLT_MAX : fmaxf((edge_z<REG>(P, G, r.iz + (r.dz >= 0.0f ? 1 : 0)) - r.oz) * r.rz, 0.0f);
 }
 
-// Position on the leg, folded back into the periodic domain.  Regular grids never shift the origin
-// while marching (their face distances are incremental), so the fold happens here, once per event.
+// Position on the leg, folded back into the periodic domain (the leg origin is only ever shifted by
+// whole periods, so the fold is valid for both grid kinds and after a burst has been rolled back).
 template <bool REG>
 __device__ __forceinline__ void ray_position(const Ray &r, const DevDomain &P, float &px, float &py, float &pz) {
   px = fmaf(r.t, r.dx, r.ox); py = fmaf(r.t, r.dy, r.oy); pz = fmaf(r.t, r.dz, r.oz);
-  if (REG) {
-    px -= P.fLx * floorf((px - P.fx0) * P.finvLx);
-    py -= P.fLy * floorf((py - P.fy0) * P.finvLy);
-  }
+  px -= P.fLx * floorf((px - P.fx0) * P.finvLx);
+  py -= P.fLy * floorf((py - P.fy0) * P.finvLy);
 }
 
 // Cross the face(s) reached at distance tmin: branch-free on all three axes (every lane runs the
-// same instructions; the axis actually crossed is selected by predicates).  Returns 0 inside,
-// 1 out the top, 2 out the bottom.
+// same instructions; the axis actually crossed is selected by predicates).  A ray that has left
+// through the top (out = 1) or the bottom (out = 2) is frozen: later steps of the same burst change
+// nothing, so the exit column and distance survive to the event code.
 template <bool REG>
-__device__ __forceinline__ int ray_advance(Ray &r, const DevDomain &P, const Grid &G, float tmin) {
-  r.t = tmin;
+__device__ __forceinline__ void ray_step(Ray &r, const DevDomain &P, const Grid &G, float tmin, int &out) {
+  const bool live = out == 0;
+  r.t = live ? tmin : r.t;
   if (REG) {
     {
-      const bool c = r.tx <= tmin;
+      const bool c = live && r.tx <= tmin;
       int i = r.ix + (c ? (r.dx >= 0.0f ? 1 : -1) : 0);
       i = i >= P.nx ? 0 : i;
       i = i < 0 ? P.nx - 1 : i;
       r.tx = c ? fmaf(P.fhx, fabsf(r.rx), r.tx) : r.tx; r.ix = i;
     }
     {
-      const bool c = r.ty <= tmin;
+      const bool c = live && r.ty <= tmin;
       int i = r.iy + (c ? (r.dy >= 0.0f ? 1 : -1) : 0);
       i = i >= P.ny ? 0 : i;
       i = i < 0 ? P.ny - 1 : i;
       r.ty = c ? fmaf(P.fhy, fabsf(r.ry), r.ty) : r.ty; r.iy = i;
     }
     {
-      const bool c = r.tz <= tmin, pos = r.dz >= 0.0f;
+      const bool c = live && r.tz <= tmin, pos = r.dz >= 0.0f;
       const int i = r.iz + (c ? (pos ? 1 : -1) : 0);
-      if ((unsigned)i >= (unsigned)P.nz) return pos ? 1 : 2;
-      r.tz = c ? fmaf(P.fhz, fabsf(r.rz), r.tz) : r.tz; r.iz = i;
+      const bool gone = (unsigned)i >= (unsigned)P.nz;
+      out = gone ? (pos ? 1 : 2) : out;
+      r.tz = c ? fmaf(P.fhz, fabsf(r.rz), r.tz) : r.tz; r.iz = gone ? r.iz : i;
     }
   } else {
     {
-      const bool c = r.tx <= tmin, pos = r.dx >= 0.0f;
+      const bool c = live && r.tx <= tmin, pos = r.dx >= 0.0f;
       int i = r.ix + (c ? (pos ? 1 : -1) : 0);
       float o = r.ox;
       if (i >= P.nx) { i = 0; o -= P.fLx; }
@@ -143,7 +144,7 @@ __device__ __forceinline__ int ray_advance(Ray &r, const DevDomain &P, const Gri
       r.tx = c ? nt : r.tx; r.ix = i; r.ox = o;
     }
     {
-      const bool c = r.ty <= tmin, pos = r.dy >= 0.0f;
+      const bool c = live && r.ty <= tmin, pos = r.dy >= 0.0f;
       int i = r.iy + (c ? (pos ? 1 : -1) : 0);
       float o = r.oy;
       if (i >= P.ny) { i = 0; o -= P.fLy; }
@@ -152,14 +153,74 @@ __device__ __forceinline__ int ray_advance(Ray &r, const DevDomain &P, const Gri
       r.ty = c ? nt : r.ty; r.iy = i; r.oy = o;
     }
     {
-      const bool c = r.tz <= tmin, pos = r.dz >= 0.0f;
-      const int i = r.iz + (c ? (pos ? 1 : -1) : 0);
-      if ((unsigned)i >= (unsigned)P.nz) return pos ? 1 : 2;
+      const bool c = live && r.tz <= tmin, pos = r.dz >= 0.0f;
+      int i = r.iz + (c ? (pos ? 1 : -1) : 0);
+      const bool gone = (unsigned)i >= (unsigned)P.nz;
+      out = gone ? (pos ? 1 : 2) : out;
+      i = gone ? r.iz : i;
       const float nt = (G.sz[i + (pos ? 1 : 0)] - r.oz) * r.rz;
-      r.tz = c ? nt : r.tz; r.iz = i;
+      r.tz = (c && !gone) ? nt : r.tz; r.iz = i;
     }
   }
-  return 0;
+}
+
+// linear cell -> (ix, iy, iz): two divisions by launch-invariant divisors, done with the
+// precomputed multipliers of the parameter block (exact for every cell index < 2^31)
+__device__ __forceinline__ void cell_decode(const DevDomain &P, int cell, int &ix, int &iy, int &iz) {
+  const uint32_t c = (uint32_t)cell;
+  const uint32_t z = (uint32_t)(((uint64_t)P.divColsM * c) >> P.divColsS);
+  const uint32_t rem = c - z * (uint32_t)(P.nx * P.ny);
+  const uint32_t y = (uint32_t)(((uint64_t)P.divNxM * rem) >> P.divNxS);
+  ix = (int)(rem - y * (uint32_t)P.nx); iy = (int)y; iz = (int)z;
+}
+
+enum { MARCH_ON = 0, MARCH_TOP = 1, MARCH_BOTTOM = 2, MARCH_HIT = 3 };
+
+// One burst of the marcher (accumulateExtinctionAlongPath, OPT:1697-1814): B cells.  The cells a
+// ray visits and the lengths of its segments depend on geometry only, never on the extinction read,
+// so the DDA runs B cells AHEAD (pure ALU), the B extinction gathers are issued together (B loads in
+// flight per lane instead of one dependent load per cell), and only then is the optical depth
+// accumulated and tested against the target (OPT:1729-1738).  If the target falls inside cell k of
+// the burst the ray is rolled back to the entry of that cell: r.t = entry distance, (ix,iy,iz)
+// decoded from the saved linear cell, sigHit = its extinction; the caller finishes the partial
+// step.  Face distances tx/ty/tz are stale after a roll-back; every caller starts a new leg there.
+template <bool REG, int B>
+__device__ __forceinline__ int march_burst(Ray &r, const DevDomain &P, const Grid &G, const float *__restrict__ ext32,
+                                           float &ext, float target, float &sigHit, unsigned &crossings) {
+  float tEnd[B], sg[B];
+  int cellk[B];
+  int out = 0, nValid = B;
+  const float t0 = r.t;
+#pragma unroll
+  for (int k = 0; k < B; ++k) {
+    const float tmin = fminf(r.tx, fminf(r.ty, r.tz));
+    cellk[k] = r.ix + P.nx * (r.iy + P.ny * r.iz);
+    tEnd[k] = tmin;
+    const int was = out;
+    ray_step<REG>(r, P, G, tmin, out);
+    nValid = (out != 0 && was == 0) ? k + 1 : nValid;
+  }
+#pragma unroll
+  for (int k = 0; k < B; ++k) sg[k] = __ldg(&ext32[cellk[k]]);
+  int hit = -1, cellHit = 0;
+  float tS = t0, tHit = t0;
+#pragma unroll
+  for (int k = 0; k < B; ++k) {
+    const float e2 = fmaf(fmaxf(tEnd[k] - tS, 0.0f), sg[k], ext);
+    const bool ok = k < nValid && hit < 0;
+    const bool h = ok && e2 > target;
+    hit = h ? k : hit; sigHit = h ? sg[k] : sigHit; tHit = h ? tS : tHit; cellHit = h ? cellk[k] : cellHit;
+    ext = (ok && !h) ? e2 : ext;
+    tS = tEnd[k];
+  }
+  if (hit >= 0) {
+    crossings += (unsigned)(hit + 1);
+    r.t = tHit;
+    cell_decode(P, cellHit, r.ix, r.iy, r.iz);
+    return MARCH_HIT;
+  }
+  crossings += (unsigned)nValid;
+  return out;
 }
 
 // Trace to the boundary or to an optical-depth target (the local-estimate rays, INT:1734-1739,
@@ -167,21 +228,16 @@ __device__ __forceinline__ int ray_advance(Ray &r, const DevDomain &P, const Gri
 template <bool REG>
 __device__ float ray_trace(Ray &r, const DevDomain &P, const Grid &G, const float *__restrict__ ext32, bool hasTarget, float target,
                            int &where, unsigned &crossings) {
-  float ext = 0.0f;
+  float ext = 0.0f, sig = 1.0f;
+  const float tgt = hasTarget ? target : FLT_MAX;
   for (;;) {
-    const float tmin = fminf(r.tx, fminf(r.ty, r.tz));
-    const float s = fmaxf(tmin - r.t, 0.0f);
-    const float sig = __ldg(&ext32[r.ix + P.nx * (r.iy + P.ny * r.iz)]);
-    crossings++;
-    const float e2 = fmaf(s, sig, ext);
-    if (hasTarget && e2 > target) {
+    const int ev = march_burst<REG, 4>(r, P, G, ext32, ext, tgt, sig, crossings);
+    if (ev == MARCH_HIT) {
       r.t += __fdividef(target - ext, sig);
       where = 0;
       return target;
     }
-    ext = e2;
-    const int out = ray_advance<REG>(r, P, G, tmin);
-    if (out) { where = out; return ext; }
+    if (ev != MARCH_ON) { where = ev; return ext; }
   }
 }
 
@@ -309,7 +365,7 @@ __device__ void local_estimate(const DevDomain &P, const Grid &G, const Tally &T
   }
 }
 
-template <int THREADS, bool REG, int MINBLOCKS>
+template <int THREADS, bool REG, int MINBLOCKS, int BURST, bool LE>
 __global__ void __launch_bounds__(THREADS, MINBLOCKS)
 batch_kernel(const __grid_constant__ DevDomain P, long long nPhotons, uint64_t seed, uint64_t firstPhotonId,
              unsigned long long *workCounter, int parkThreshold, const SmemPlan plan) {
@@ -415,7 +471,7 @@ batch_kernel(const __grid_constant__ DevDomain P, long long nPhotons, uint64_t s
                 add_flux(P, T, 2, r.ix + P.nx * r.iy, -1.0f);
                 add_vol(P, T, r.ix + P.nx * (r.iy + P.ny * r.iz), -1.0f);
               }
-              if (P.nDir > 0)
+              if (LE && P.nDir > 0)
                 local_estimate<REG>(P, G, T, rng, k0, k1, r, r.ox, r.oy, r.oz, w, r.oz == 0.0f ? 0 : -1, 0, order, cnt);
             }
             tau = -__logf(fmaxf(TINY32, uTau));                                // INT:554
@@ -439,23 +495,10 @@ batch_kernel(const __grid_constant__ DevDomain P, long long nPhotons, uint64_t s
       const unsigned live = __ballot_sync(FULL, state != ST_DONE);
       // stop when nobody marches, or when the parked (event/dead) lanes reach the threshold
       if (mk == 0u || __popc(live & ~mk) >= parkThreshold) break;
-#pragma unroll 1
-      for (int burst = 0; burst < 4; ++burst) {
-        if (state == ST_MARCH) {
-          const float tmin = fminf(r.tx, fminf(r.ty, r.tz));
-          const float s = fmaxf(tmin - r.t, 0.0f);
-          const float sig = __ldg(&ext32[r.ix + P.nx * (r.iy + P.ny * r.iz)]);
-          cnt.crossings++;
-          const float e2 = fmaf(s, sig, ext);
-          if (e2 > tau) {                                                      // OPT:1729-1738; the step itself is
-            sigEv = sig;                                                       // finished in the event phase
-            state = ST_SCATTER;
-          } else {
-            ext = e2;
-            const int out = ray_advance<REG>(r, P, G, tmin);
-            if (out) state = out == 1 ? ST_DEAD + 16 : ST_SURFACE;             // 16: "left through the top", tallied below
-          }
-        }
+      if (state == ST_MARCH) {
+        const int ev = march_burst<REG, BURST>(r, P, G, ext32, ext, tau, sigEv, cnt.crossings);
+        // MARCH_HIT: the step itself is finished in the event phase (OPT:1729-1738); 16: "left through the top"
+        state = ev == MARCH_ON ? ST_MARCH : ev == MARCH_HIT ? ST_SCATTER : ev == MARCH_TOP ? ST_DEAD + 16 : ST_SURFACE;
       }
     }
 
@@ -481,7 +524,7 @@ batch_kernel(const __grid_constant__ DevDomain P, long long nPhotons, uint64_t s
         ray_position<REG>(r, P, px, py, pz);
         r.ox = px; r.oy = py; r.oz = P.fz0; r.iz = 0;
         dir_from(mu, phi, r.dx, r.dy, r.dz);
-        if (P.nDir > 0) local_estimate<REG>(P, G, T, rng, k0, k1, r, r.ox, r.oy, r.oz, w, 0, 0, order, cnt);
+        if (LE && P.nDir > 0) local_estimate<REG>(P, G, T, rng, k0, k1, r, r.ox, r.oy, r.oz, w, 0, 0, order, cnt);
         tau = -__logf(fmaxf(TINY32, u.z));
         ext = 0.0f;
         ray_start<REG>(r, P, G);
@@ -492,10 +535,16 @@ batch_kernel(const __grid_constant__ DevDomain P, long long nPhotons, uint64_t s
       cnt.scatters++;
       r.t += __fdividef(tau - ext, sigEv);                                     // OPT:1731
       const int cell = r.ix + P.nx * (r.iy + P.ny * r.iz);
-      const float4 u = rng.block(k0, k1);                                      // component, roulette, angle, next tau
+      // One Philox block per scattering event: u.x picks the component and, rescaled to the chosen
+      // component's interval (uniform again, conditional on the pick), decides the roulette; u.y the
+      // scattering angle; u.z the azimuth; u.w the next optical depth.
+      const float4 u = rng.block(k0, k1);
       int comp = 1;
-      for (int c = 1; c < P.nc; ++c)                                           // findIndex on (0, cumExt(:)), NUM:262-315
-        if (u.x >= __ldg(&P.cum32[cell + (size_t)cells * (size_t)(c - 1)])) comp = c + 1;
+      float lo = 0.0f, hi = 1.0f;
+      for (int c = 1; c < P.nc; ++c) {                                         // findIndex on (0, cumExt(:)), NUM:262-315
+        const float cc = __ldg(&P.cum32[cell + (size_t)cells * (size_t)(c - 1)]);
+        if (u.x >= cc) { comp = c + 1; lo = cc; } else { hi = fminf(hi, cc); }
+      }
       const float ssa = __ldg(&P.ssa32[cell + (size_t)cells * (size_t)(comp - 1)]);
       if (ssa < 1.0f) {                                                        // INT:765-771
         const float absorbed = w * (1.0f - ssa);
@@ -505,9 +554,10 @@ batch_kernel(const __grid_constant__ DevDomain P, long long nPhotons, uint64_t s
       }
       float px, py, pz;
       ray_position<REG>(r, P, px, py, pz);
-      if (P.nDir > 0) local_estimate<REG>(P, G, T, rng, k0, k1, r, px, py, pz, w, comp, comp, order, cnt);   // INT:776-800
+      if (LE && P.nDir > 0) local_estimate<REG>(P, G, T, rng, k0, k1, r, px, py, pz, w, comp, comp, order, cnt);   // INT:776-800
       if (P.opt.useRussianRoulette && w < P.opt.russianRouletteW * 0.5f) {     // INT:805-811
-        if (u.y >= w / P.opt.russianRouletteW) w = 0.0f; else w = P.opt.russianRouletteW;
+        const float uRR = P.nc > 1 ? __fdividef(u.x - lo, fmaxf(hi - lo, TINY32)) : u.x;
+        if (uRR >= w / P.opt.russianRouletteW) w = 0.0f; else w = P.opt.russianRouletteW;
       }
       if (w <= TINY32) {
         state = ST_DEAD + 48;                                                  // 48: killed by roulette
@@ -516,7 +566,7 @@ batch_kernel(const __grid_constant__ DevDomain P, long long nPhotons, uint64_t s
         const int pidx = (int)__ldg(&P.idx16[cell + (size_t)cells * (size_t)c]);
         const int nS = P.invS[c];
         const float *tab = P.inv[c] + (size_t)(pidx - 1) * nS;
-        const float rn = u.z;                                                  // computeScatteringAngle INT:1594-1621
+        const float rn = u.y;                                                  // computeScatteringAngle INT:1594-1621
         const int k = (int)(rn * (float)nS) + 1;
         float theta;
         if (k < nS) {
@@ -527,18 +577,13 @@ batch_kernel(const __grid_constant__ DevDomain P, long long nPhotons, uint64_t s
         }
         float sinT, cosT;
         __sincosf(theta, &sinT, &cosT);
-        float AX, AY, D;                                                       // next_direct INT:1921-1948
-        for (;;) {                                                             // one block = two tries
-          const float4 v = rng.block(k0, k1);
-          AX = 1.0f - 2.0f * v.x; AY = 1.0f - 2.0f * v.y; D = AX * AX + AY * AY;
-          if (D <= 1.0f) break;
-          AX = 1.0f - 2.0f * v.z; AY = 1.0f - 2.0f * v.w; D = AX * AX + AY * AY;
-          if (D <= 1.0f) break;
-        }
-        float B = sinT * rsqrtf(D);
-        AX *= B; AY *= B;
-        B = r.dx * AX - r.dy * AY;
-        D = cosT - __fdividef(B, 1.0f + fabsf(r.dz));
+        // next_direct INT:1921-1948: the reference rejection-samples (AX, AY) in the unit disc and
+        // normalises it, i.e. draws a uniform azimuth; the azimuth is drawn directly here.
+        float AX, AY;
+        __sincosf(2.0f * PI32 * u.z, &AY, &AX);
+        AX *= sinT; AY *= sinT;
+        const float B = r.dx * AX - r.dy * AY;
+        const float D = cosT - __fdividef(B, 1.0f + fabsf(r.dz));
         const float ndx = r.dx * D + AX, ndy = r.dy * D - AY;
         const float ndz = r.dz * cosT - copysignf(fabsf(B), r.dz * B);
         r.ox = px; r.oy = py; r.oz = pz;
@@ -602,11 +647,11 @@ __global__ void philox_kat_kernel(uint64_t seed, uint64_t photon, int n, uint32_
 
 #include <cstdlib>
 
-template <bool REG, int MINBLOCKS>
+template <bool REG, int MINBLOCKS, int BURST, bool LE>
 static void launch(const DevDomain &P, long long nPhotons, uint64_t seed, uint64_t firstPhotonId, int numSMs,
                    unsigned long long *workCounter, cudaStream_t stream) {
   constexpr int THREADS = 128;
-  auto kernel = mcbfast::batch_kernel<THREADS, REG, MINBLOCKS>;
+  auto kernel = mcbfast::batch_kernel<THREADS, REG, MINBLOCKS, BURST, LE>;
   // shared-memory plan: privatise the tallies when the column / cell grid is small enough to be an
   // atomic hot spot (homogeneous slabs, the 32-column step cloud); large grids spread their
   // atomics over many L2 lines and go straight to the f64 buffer.
@@ -635,15 +680,21 @@ static void launch(const DevDomain &P, long long nPhotons, uint64_t seed, uint64
 void mcb_launch_fast_batch(const DevDomain &P, long long nPhotons, uint64_t seed, uint64_t firstPhotonId,
                            int numSMs, unsigned long long *workCounter, cudaStream_t stream) {
   if (nPhotons <= 0) return;
-  static int occ = -1;               // register budget variant (tuning knob; default chosen from measurements)
-  if (occ < 0) { const char *e = getenv("MCB_BLOCKS_PER_SM"); occ = e ? atoi(e) : 6; }
+  static int occ = -1, burst = -1;   // register budget / burst length variants (tuning knobs; defaults chosen from measurements)
+  if (occ < 0) { const char *e = getenv("MCB_BLOCKS_PER_SM"); occ = e ? atoi(e) : 5; }
+  if (burst < 0) { const char *e = getenv("MCB_BURST"); burst = e ? atoi(e) : 8; }
+#define MCB_GO(REG, OCC, BURST) do { \
+    if (P.nDir > 0) launch<REG, OCC, BURST, true>(P, nPhotons, seed, firstPhotonId, numSMs, workCounter, stream); \
+    else launch<REG, OCC, BURST, false>(P, nPhotons, seed, firstPhotonId, numSMs, workCounter, stream); } while (0)
   if (P.xyRegular && P.zRegular) {
-    if (occ >= 8) launch<true, 8>(P, nPhotons, seed, firstPhotonId, numSMs, workCounter, stream);
-    else if (occ <= 5) launch<true, 5>(P, nPhotons, seed, firstPhotonId, numSMs, workCounter, stream);
-    else launch<true, 6>(P, nPhotons, seed, firstPhotonId, numSMs, workCounter, stream);
+    if (burst >= 16) MCB_GO(true, 4, 16);
+    else if (burst >= 12) MCB_GO(true, 4, 12);
+    else if (burst >= 8) { if (occ >= 5) MCB_GO(true, 5, 8); else MCB_GO(true, 4, 8); }
+    else { if (occ >= 6) MCB_GO(true, 6, 4); else if (occ <= 4) MCB_GO(true, 4, 4); else MCB_GO(true, 5, 4); }
   } else {
-    launch<false, 4>(P, nPhotons, seed, firstPhotonId, numSMs, workCounter, stream);
+    MCB_GO(false, 4, 4);
   }
+#undef MCB_GO
 }
 
 void mcb_launch_philox_kat(uint64_t seed, uint64_t photon, int n, uint32_t *out, cudaStream_t stream) {
