@@ -186,10 +186,14 @@ int mcb_set_grid(mcb_handle *h, int nx, int ny, int nz,
   P.fx0 = (float)P.x0; P.fy0 = (float)P.y0; P.fz0 = (float)P.z0;
   P.fLx = (float)(P.xMax - P.x0); P.fLy = (float)(P.yMax - P.y0); P.fLz = (float)(P.zMax - P.z0);
   P.fhx = (float)P.deltaX; P.fhy = (float)P.deltaY; P.fhz = (float)P.deltaZ;
-  P.finvLx = 1.0f / P.fLx; P.finvLy = 1.0f / P.fLy;
-  if ((long long)nx * ny * nz >= (1LL << 31)) FAIL(h, "mcb_set_grid: more than 2^31 cells");
-  magic_divisor((uint32_t)nx * (uint32_t)ny, &P.divColsM, &P.divColsS);
-  magic_divisor((uint32_t)nx, &P.divNxM, &P.divNxS);
+  P.finvLx = 1.0f / P.fLx; P.finvLy = 1.0f / P.fLy; P.fzMax = (float)P.zMax;
+  P.finvhx = xyReg ? 1.0f / P.fhx : 0.0f; P.finvhy = xyReg ? 1.0f / P.fhy : 0.0f;
+  // padded extinction field: MCB_GHOST cells on every side (see mcb_set_optics)
+  P.nxp = nx + 2 * MCB_GHOST; P.nyp = ny + 2 * MCB_GHOST;
+  if ((long long)P.nxp * P.nyp * (nz + 2 * MCB_GHOST) >= (1LL << 31)) FAIL(h, "mcb_set_grid: more than 2^31 cells");
+  P.ghostOrigin = MCB_GHOST + P.nxp * (MCB_GHOST + P.nyp * MCB_GHOST);
+  magic_divisor((uint32_t)P.nxp * (uint32_t)P.nyp, &P.divSliceM, &P.divSliceS);
+  magic_divisor((uint32_t)P.nxp, &P.divRowM, &P.divRowS);
   h->haveGrid = true; h->haveOptics = false; h->haveSource = false;
   return 0;
 }
@@ -212,11 +216,22 @@ int mcb_set_optics(mcb_handle *h, int nc, const double *totalExt, const double *
   if (stage(h, &h->dSsa, ssa, sizeof(double) * cells * nc)) return 1;
   if (stage(h, &h->dPhaseIdx, phaseIdx, sizeof(int32_t) * cells * nc)) return 1;
   {  // packed single-precision copies for the fast kernel
-    std::vector<float> e32(cells), c32(cells * nc), s32(cells * nc);
+    // extinction with its ghost shell: x and y continue periodically (OPT:1782-1796 becomes data instead
+    // of per-cell tests), the layers above the top and below the surface are empty (OPT:1801-1812)
+    const int G = MCB_GHOST, nxp = P.nxp, nyp = P.nyp, nzp = P.nz + 2 * G;
+    std::vector<float> e32((size_t)nxp * nyp * nzp, 0.0f), c32(cells * nc), s32(cells * nc);
     std::vector<uint16_t> i16(cells * nc);
-    for (size_t i = 0; i < cells; ++i) e32[i] = (float)totalExt[i];
+    std::vector<int> mx(nxp), my(nyp);
+    for (int i = 0; i < nxp; ++i) mx[i] = (((i - G) % P.nx) + P.nx) % P.nx;
+    for (int j = 0; j < nyp; ++j) my[j] = (((j - G) % P.ny) + P.ny) % P.ny;
+    for (int k = 0; k < P.nz; ++k)
+      for (int j = 0; j < nyp; ++j) {
+        const double *src = totalExt + (size_t)P.nx * ((size_t)my[j] + (size_t)P.ny * k);
+        float *dst = e32.data() + (size_t)nxp * ((size_t)j + (size_t)nyp * (k + G));
+        for (int i = 0; i < nxp; ++i) dst[i] = (float)src[mx[i]];
+      }
     for (size_t i = 0; i < cells * nc; ++i) { c32[i] = (float)cumExt[i]; s32[i] = (float)ssa[i]; i16[i] = (uint16_t)phaseIdx[i]; }
-    if (stage(h, &h->dExt32, e32.data(), sizeof(float) * cells)) return 1;
+    if (stage(h, &h->dExt32, e32.data(), sizeof(float) * e32.size())) return 1;
     if (stage(h, &h->dCum32, c32.data(), sizeof(float) * cells * nc)) return 1;
     if (stage(h, &h->dSsa32, s32.data(), sizeof(float) * cells * nc)) return 1;
     if (stage(h, &h->dIdx16, i16.data(), sizeof(uint16_t) * cells * nc)) return 1;
@@ -224,7 +239,7 @@ int mcb_set_optics(mcb_handle *h, int nc, const double *totalExt, const double *
   P.nc = nc; P.albedo = albedo;
   P.totalExt = (const double *)h->dTotalExt; P.cumExt = (const double *)h->dCumExt;
   P.ssa = (const double *)h->dSsa; P.phaseIdx = (const int32_t *)h->dPhaseIdx;
-  P.ext32 = (const float *)h->dExt32; P.cum32 = (const float *)h->dCum32;
+  P.extp = (const float *)h->dExt32 + P.ghostOrigin; P.cum32 = (const float *)h->dCum32;
   P.ssa32 = (const float *)h->dSsa32; P.idx16 = (const uint16_t *)h->dIdx16;
   for (int c = 0; c < MCB_MAX_COMP; ++c) { h->haveInv[c] = false; h->haveFwd[c] = false; }
   h->haveOptics = true;
@@ -283,6 +298,10 @@ int mcb_set_solar_source(mcb_handle *h, float solarMu, float solarAzimuthDeg) { 
   const float pi32 = (float)std::acos(-1.0);
   volatile float t = solarAzimuthDeg * pi32;                                      // ILL:96, single precision
   h->P.solarPhi = t / 180.0f;
+  {                                                                               // INT:1876-1894
+    const float mu = h->P.solarMu, st = std::sqrt(std::fmax(1.0f - mu * mu, 0.0f));
+    h->P.solarDir[0] = st * std::cos(h->P.solarPhi); h->P.solarDir[1] = st * std::sin(h->P.solarPhi); h->P.solarDir[2] = mu;
+  }
   h->haveSource = true;
   return 0;
 }

@@ -12,6 +12,7 @@
 
 #define MCB_MAX_COMP 8          // optical components per domain (the reference's decks use <= 4)
 #define MCB_MAX_DIR 32          // view directions kept in the parameter block
+#define MCB_GHOST 8             // ghost cells on every side of the packed extinction field = longest marching burst
 
 struct DevDomain {
   // ---- grid (OPT:77-83, INT:60-66) ----
@@ -26,13 +27,16 @@ struct DevDomain {
   const int32_t *phaseIdx;                    // (nx,ny,nz,nc)
   double albedo;
   // ---- packed single-precision copies for the fast kernel ----
-  const float *ext32;                         // (nx,ny,nz)
+  const float *extp;                          // padded (nx+2G, ny+2G, nz+2G) extinction field with its ghost shell
+                                              // (periodic replicas in x, y; zeros above and below), pointing AT the
+                                              // first real cell: cell (ix,iy,iz) is extp[ix + nxp*(iy + nyp*iz)]
+  int nxp, nyp, ghostOrigin;                  // padded row / slice lengths; linear offset of the first real cell
   const float *cum32, *ssa32;                 // (nx,ny,nz,nc)
   const uint16_t *idx16;                      // (nx,ny,nz,nc)
   float fx0, fy0, fz0, fLx, fLy, fLz;         // single-precision grid scalars (fast kernel, constant bank)
-  float fhx, fhy, fhz, finvLx, finvLy;
-  uint32_t divColsM, divNxM;                  // cell -> (ix,iy,iz): q = (M * n) >> S, exact for n < 2^31
-  int divColsS, divNxS;
+  float fhx, fhy, fhz, finvLx, finvLy, finvhx, finvhy, fzMax;
+  uint32_t divSliceM, divRowM;                // padded cell -> (ix,iy,iz): q = (M * n) >> S, exact for n < 2^31
+  int divSliceS, divRowS;
   // ---- tables ----
   const float *inv[MCB_MAX_COMP];  int invS[MCB_MAX_COMP];
   const float *fwd[MCB_MAX_COMP];  const float *fwdOrig[MCB_MAX_COMP];  int fwdS[MCB_MAX_COMP];
@@ -44,6 +48,7 @@ struct DevDomain {
   // ---- source ----
   int source;                                 // 0 solar, 1 thermal
   float solarMu, solarPhi;                    // ILL:95-96 values
+  float solarDir[3];                          // their direction cosines (INT:1876-1894)
   double fracAtmsPower;
   const double *voxelCDF;                     // (nx,ny,nz)
   // ---- tallies: packed f64 buffer ----

@@ -5,13 +5,16 @@
 //   * one persistent kernel, one photon per lane, lanes refilled from a global photon
 //     counter (warp-aggregated atomic) so no lane idles while photons remain;
 //   * ray marching (accumulateExtinctionAlongPath, OPT:1656-1815) as a parametric
-//     Amanatides-Woo DDA in single precision: per cell one dependent gather of the packed
-//     f32 extinction and a branch-free face update (all three axes predicated, no divides
-//     in the cell loop); regular grids step their face distances incrementally, irregular
-//     grids read shared-memory-staged edges; periodic x/y shift the leg origin;
-//   * warp-level regrouping: lanes march in bursts and park when they reach an event
-//     (scatter / surface); the event code runs once enough lanes are parked, so the
-//     expensive scatter path executes with many active lanes instead of one or two;
+//     Amanatides-Woo DDA in single precision that runs AHEAD of the extinction reads: the cells a
+//     ray visits depend on geometry only, so a burst of B cells is stepped with pure ALU work, the
+//     B gathers are issued together, and only then is optical depth accumulated and tested.  The
+//     packed f32 extinction field carries a ghost shell (periodic replicas in x and y, empty cells
+//     above and below), so the per-cell step has no wrap or exit tests at all -- those run once per
+//     burst;
+//   * warp-level regrouping: lanes march in bursts and park when they reach an event (scatter /
+//     surface / exit); once enough lanes are parked ONE event phase runs for all of them: tallies,
+//     absorption, roulette, rebirth of finished lanes, one Philox block, the new direction, one
+//     leg set-up -- so the expensive code executes once, with many active lanes;
 //   * Philox4x32-10 per-photon streams (mcb_device.cuh) instead of a sequential MT19937;
 //   * tallies: shared-memory-privatised f32 atomics flushed once per block when the column /
 //     cell grid is small enough to be an atomic hot spot, f64 RED.ADD to the packed tally
@@ -25,12 +28,13 @@ namespace mcbfast {
 #define FULL 0xffffffffu
 #define PI32 3.14159265358979312f
 #define TINY32 FLT_MIN
+#define GH MCB_GHOST
 
-enum { ST_DEAD = 0, ST_MARCH = 1, ST_SCATTER = 2, ST_SURFACE = 3, ST_DONE = 4 };
+enum { ST_DEAD = 0, ST_MARCH = 1, ST_SCATTER = 2, ST_SURFACE = 3, ST_TOP = 4, ST_BORN = 5, ST_DONE = 6 };
 
 // launch-time layout of the dynamic shared memory
 struct SmemPlan {
-  int edgesOff;            // float[nx+1 + ny+1 + nz+1] (irregular grids only; -1 otherwise)
+  int edgesOff;            // float[(nx+1+2G) + (ny+1+2G) + (nz+1+2G)] ghost-extended edges (irregular grids; -1 otherwise)
   int fluxOff;             // float[3*cols]  privatised fluxUp|fluxDown|fluxAbs   (-1: global atomics)
   int volOff;              // float[cells]   privatised volumeAbsorption           (-1: global atomics)
   int intOff;              // float[cols*nDir] privatised intensity                (-1: global atomics)
@@ -41,9 +45,7 @@ struct Rng {
   uint32_t c0, c1, blk;
   __device__ __forceinline__ void init(uint64_t photon) { c0 = (uint32_t)photon; c1 = (uint32_t)(photon >> 32); blk = 0; }
   // One Philox4x32-10 block = four uniform reals.  Every call site is reached by all the lanes that
-  // take part in the event together, so the ten rounds run convergently (v2 refilled inside real():
-  // each lane ran dry at a different draw and the rounds executed with 3-5 active lanes, 19 % of all
-  // warp instructions).
+  // take part in the event phase together, so the ten rounds run convergently.
   __device__ __forceinline__ float4 block(uint32_t k0, uint32_t k1) {
     uint32_t x0 = c0, x1 = c1, x2 = blk, x3 = 0u, a = k0, b = k1;
 #pragma unroll
@@ -67,15 +69,20 @@ struct Ray {
   float rx, ry, rz;        // reciprocal direction cosines (FLT_MAX-guarded)
   float t;                 // distance along the leg
   float tx, ty, tz;        // distance along the leg at which the next x/y/z face is met
-  int ix, iy, iz;          // 0-based cell
+  int ix, iy, iz;          // 0-based cell; inside a burst x, y may run into the periodic ghost shell
 };
 
 struct Grid {
-  const float *sx, *sy, *sz;     // shared-memory edges (irregular grids); every scalar of the grid is a
-};                               // single-precision field of the DevDomain parameter block (constant bank)
+  const float *sx, *sy, *sz;     // shared-memory edges (irregular grids), pointing at edge 0 of ghost-extended
+};                               // arrays; every scalar of the grid is a field of the DevDomain parameter block
 
+__device__ __forceinline__ float rcp_approx(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 __device__ __forceinline__ float safe_rcp(float d) {
-  return fabsf(d) >= 2.0f * TINY32 ? __fdividef(1.0f, d) : FLT_MAX;      // OPT:1705-1712 zero-direction guard
+  return fabsf(d) >= 2.0f * TINY32 ? rcp_approx(d) : FLT_MAX;            // OPT:1705-1712 zero-direction guard
 }
 
 template <bool REG>
@@ -96,155 +103,144 @@ __device__ __forceinline__ void ray_start(Ray &r, const DevDomain &P, const Grid
 
 // Position on the leg, folded back into the periodic domain (the leg origin is only ever shifted by
 // whole periods, so the fold is valid for both grid kinds and after a burst has been rolled back).
-template <bool REG>
 __device__ __forceinline__ void ray_position(const Ray &r, const DevDomain &P, float &px, float &py, float &pz) {
   px = fmaf(r.t, r.dx, r.ox); py = fmaf(r.t, r.dy, r.oy); pz = fmaf(r.t, r.dz, r.oz);
   px -= P.fLx * floorf((px - P.fx0) * P.finvLx);
   py -= P.fLy * floorf((py - P.fy0) * P.finvLy);
 }
 
-// Cross the face(s) reached at distance tmin: branch-free on all three axes (every lane runs the
-// same instructions; the axis actually crossed is selected by predicates).  A ray that has left
-// through the top (out = 1) or the bottom (out = 2) is frozen: later steps of the same burst change
-// nothing, so the exit column and distance survive to the event code.
-template <bool REG>
-__device__ __forceinline__ void ray_step(Ray &r, const DevDomain &P, const Grid &G, float tmin, int &out) {
-  const bool live = out == 0;
-  r.t = live ? tmin : r.t;
-  if (REG) {
-    {
-      const bool c = live && r.tx <= tmin;
-      int i = r.ix + (c ? (r.dx >= 0.0f ? 1 : -1) : 0);
-      i = i >= P.nx ? 0 : i;
-      i = i < 0 ? P.nx - 1 : i;
-      r.tx = c ? fmaf(P.fhx, fabsf(r.rx), r.tx) : r.tx; r.ix = i;
-    }
-    {
-      const bool c = live && r.ty <= tmin;
-      int i = r.iy + (c ? (r.dy >= 0.0f ? 1 : -1) : 0);
-      i = i >= P.ny ? 0 : i;
-      i = i < 0 ? P.ny - 1 : i;
-      r.ty = c ? fmaf(P.fhy, fabsf(r.ry), r.ty) : r.ty; r.iy = i;
-    }
-    {
-      const bool c = live && r.tz <= tmin, pos = r.dz >= 0.0f;
-      const int i = r.iz + (c ? (pos ? 1 : -1) : 0);
-      const bool gone = (unsigned)i >= (unsigned)P.nz;
-      out = gone ? (pos ? 1 : 2) : out;
-      r.tz = c ? fmaf(P.fhz, fabsf(r.rz), r.tz) : r.tz; r.iz = gone ? r.iz : i;
-    }
-  } else {
-    {
-      const bool c = live && r.tx <= tmin, pos = r.dx >= 0.0f;
-      int i = r.ix + (c ? (pos ? 1 : -1) : 0);
-      float o = r.ox;
-      if (i >= P.nx) { i = 0; o -= P.fLx; }
-      if (i < 0) { i = P.nx - 1; o += P.fLx; }
-      const float nt = (G.sx[i + (pos ? 1 : 0)] - o) * r.rx;
-      r.tx = c ? nt : r.tx; r.ix = i; r.ox = o;
-    }
-    {
-      const bool c = live && r.ty <= tmin, pos = r.dy >= 0.0f;
-      int i = r.iy + (c ? (pos ? 1 : -1) : 0);
-      float o = r.oy;
-      if (i >= P.ny) { i = 0; o -= P.fLy; }
-      if (i < 0) { i = P.ny - 1; o += P.fLy; }
-      const float nt = (G.sy[i + (pos ? 1 : 0)] - o) * r.ry;
-      r.ty = c ? nt : r.ty; r.iy = i; r.oy = o;
-    }
-    {
-      const bool c = live && r.tz <= tmin, pos = r.dz >= 0.0f;
-      int i = r.iz + (c ? (pos ? 1 : -1) : 0);
-      const bool gone = (unsigned)i >= (unsigned)P.nz;
-      out = gone ? (pos ? 1 : 2) : out;
-      i = gone ? r.iz : i;
-      const float nt = (G.sz[i + (pos ? 1 : 0)] - r.oz) * r.rz;
-      r.tz = (c && !gone) ? nt : r.tz; r.iz = i;
-    }
-  }
+__device__ __forceinline__ int find_cell(const float *e, int n, float x) {
+  int lo = 0, hi = n;                      // e[lo] <= x < e[hi]
+  while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (x >= e[mid]) lo = mid; else hi = mid; }
+  return lo;
 }
 
-// linear cell -> (ix, iy, iz): two divisions by launch-invariant divisors, done with the
-// precomputed multipliers of the parameter block (exact for every cell index < 2^31)
-__device__ __forceinline__ void cell_decode(const DevDomain &P, int cell, int &ix, int &iy, int &iz) {
-  const uint32_t c = (uint32_t)cell;
-  const uint32_t z = (uint32_t)(((uint64_t)P.divColsM * c) >> P.divColsS);
-  const uint32_t rem = c - z * (uint32_t)(P.nx * P.ny);
-  const uint32_t y = (uint32_t)(((uint64_t)P.divNxM * rem) >> P.divNxS);
-  ix = (int)(rem - y * (uint32_t)P.nx); iy = (int)y; iz = (int)z;
+// fold a cell index that ran into the periodic ghost shell back into [0, n)
+__device__ __forceinline__ int wrap_index(int i, int n) {
+  if (i < 0) { do i += n; while (i < 0); }
+  else if (i >= n) { do i -= n; while (i >= n); }
+  return i;
+}
+
+// padded linear cell (relative to the first real cell) -> (ix, iy, iz): two divisions by
+// launch-invariant divisors with the precomputed multipliers of the parameter block (exact for every
+// padded cell index < 2^31); x, y come back folded into the domain.
+__device__ __forceinline__ void cell_decode(const DevDomain &P, int rel, int &ix, int &iy, int &iz) {
+  const uint32_t c = (uint32_t)(rel + P.ghostOrigin);
+  const uint32_t z = (uint32_t)(((uint64_t)P.divSliceM * c) >> P.divSliceS);
+  const uint32_t rem = c - z * (uint32_t)(P.nxp * P.nyp);
+  const uint32_t y = (uint32_t)(((uint64_t)P.divRowM * rem) >> P.divRowS);
+  ix = wrap_index((int)(rem - y * (uint32_t)P.nxp) - GH, P.nx);
+  iy = wrap_index((int)y - GH, P.ny);
+  iz = (int)z - GH;
 }
 
 enum { MARCH_ON = 0, MARCH_TOP = 1, MARCH_BOTTOM = 2, MARCH_HIT = 3 };
 
 // One burst of the marcher (accumulateExtinctionAlongPath, OPT:1697-1814): B cells.  The cells a
 // ray visits and the lengths of its segments depend on geometry only, never on the extinction read,
-// so the DDA runs B cells AHEAD (pure ALU), the B extinction gathers are issued together (B loads in
-// flight per lane instead of one dependent load per cell), and only then is the optical depth
-// accumulated and tested against the target (OPT:1729-1738).  If the target falls inside cell k of
-// the burst the ray is rolled back to the entry of that cell: r.t = entry distance, (ix,iy,iz)
-// decoded from the saved linear cell, sigHit = its extinction; the caller finishes the partial
-// step.  Face distances tx/ty/tz are stale after a roll-back; every caller starts a new leg there.
+// so the DDA runs B cells AHEAD (pure ALU; per axis one compare, one predicated index step and one
+// predicated face-distance step), the B extinction gathers are issued together (B loads in flight
+// per lane instead of one dependent load per cell), and only then is the optical depth accumulated
+// and tested against the target (OPT:1729-1738).  Inside the burst the indices may run up to B cells
+// into the ghost shell of the padded extinction field: periodic replicas in x and y (so no wrap test
+// per cell, OPT:1782-1796), empty cells above the top and below the surface (so no exit test per
+// cell, OPT:1801-1812, and no false hits there).  After the burst:
+//   * the target fell inside cell k: the ray is put AT the event (r.t = distance where the target
+//     optical depth is met, (ix,iy,iz) decoded from the saved padded cell) -> MARCH_HIT.  Face
+//     distances tx/ty/tz are stale then; every caller starts a new leg there;
+//   * the ray left through the top / the surface: r.t = distance to that boundary, (ix,iy) = column of
+//     the exit point -> MARCH_TOP / MARCH_BOTTOM;
+//   * otherwise x, y are folded back into the domain -> MARCH_ON.
 template <bool REG, int B>
-__device__ __forceinline__ int march_burst(Ray &r, const DevDomain &P, const Grid &G, const float *__restrict__ ext32,
-                                           float &ext, float target, float &sigHit, unsigned &crossings) {
-  float tEnd[B], sg[B];
-  int cellk[B];
-  int out = 0, nValid = B;
+__device__ __forceinline__ int march_burst(Ray &r, const DevDomain &P, const Grid &G, const float *__restrict__ extp,
+                                           float &ext, float target, unsigned &crossings) {
+  float tE[B], sg[B];
+  int ck[B];
   const float t0 = r.t;
+  const int sx = r.dx >= 0.0f ? 1 : -1, sy = r.dy >= 0.0f ? 1 : -1, sz = r.dz >= 0.0f ? 1 : -1;
 #pragma unroll
   for (int k = 0; k < B; ++k) {
-    const float tmin = fminf(r.tx, fminf(r.ty, r.tz));
-    cellk[k] = r.ix + P.nx * (r.iy + P.ny * r.iz);
-    tEnd[k] = tmin;
-    const int was = out;
-    ray_step<REG>(r, P, G, tmin, out);
-    nValid = (out != 0 && was == 0) ? k + 1 : nValid;
+    const float tmin = fminf(fminf(r.tx, r.ty), r.tz);
+    ck[k] = r.ix + P.nxp * (r.iy + P.nyp * r.iz);
+    tE[k] = tmin;
+    if (REG) {
+      { const bool c = r.tx <= tmin; r.ix += c ? sx : 0; r.tx = c ? fmaf(P.fhx, fabsf(r.rx), r.tx) : r.tx; }
+      { const bool c = r.ty <= tmin; r.iy += c ? sy : 0; r.ty = c ? fmaf(P.fhy, fabsf(r.ry), r.ty) : r.ty; }
+      { const bool c = r.tz <= tmin; r.iz += c ? sz : 0; r.tz = c ? fmaf(P.fhz, fabsf(r.rz), r.tz) : r.tz; }
+    } else {
+      { const bool c = r.tx <= tmin; r.ix += c ? sx : 0; const float nt = (G.sx[r.ix + (sx > 0 ? 1 : 0)] - r.ox) * r.rx; r.tx = c ? nt : r.tx; }
+      { const bool c = r.ty <= tmin; r.iy += c ? sy : 0; const float nt = (G.sy[r.iy + (sy > 0 ? 1 : 0)] - r.oy) * r.ry; r.ty = c ? nt : r.ty; }
+      { const bool c = r.tz <= tmin; r.iz += c ? sz : 0; const float nt = (G.sz[r.iz + (sz > 0 ? 1 : 0)] - r.oz) * r.rz; r.tz = c ? nt : r.tz; }
+    }
   }
 #pragma unroll
-  for (int k = 0; k < B; ++k) sg[k] = __ldg(&ext32[cellk[k]]);
-  int hit = -1, cellHit = 0;
-  float tS = t0, tHit = t0;
+  for (int k = 0; k < B; ++k) sg[k] = __ldg(extp + ck[k]);
+  float acc = ext, tS = t0;
+  bool found = false;
+  float hT = 0.0f, hE = 0.0f, hS = 1.0f;
+  int hC = 0, hK = 0;
 #pragma unroll
   for (int k = 0; k < B; ++k) {
-    const float e2 = fmaf(fmaxf(tEnd[k] - tS, 0.0f), sg[k], ext);
-    const bool ok = k < nValid && hit < 0;
-    const bool h = ok && e2 > target;
-    hit = h ? k : hit; sigHit = h ? sg[k] : sigHit; tHit = h ? tS : tHit; cellHit = h ? cellk[k] : cellHit;
-    ext = (ok && !h) ? e2 : ext;
-    tS = tEnd[k];
+    const float en = fmaf(tE[k] - tS, sg[k], acc);
+    const bool h = !found && en > target;
+    hT = h ? tE[k] : hT; hE = h ? en : hE; hS = h ? sg[k] : hS; hC = h ? ck[k] : hC; hK = h ? k : hK;
+    found = found || h;
+    acc = en; tS = tE[k];
   }
-  if (hit >= 0) {
-    crossings += (unsigned)(hit + 1);
-    r.t = tHit;
-    cell_decode(P, cellHit, r.ix, r.iy, r.iz);
+  if (found) {
+    crossings += (unsigned)(hK + 1);
+    r.t = hT - __fdividef(hE - target, hS);          // where the target optical depth is met (OPT:1731)
+    cell_decode(P, hC, r.ix, r.iy, r.iz);
     return MARCH_HIT;
   }
-  crossings += (unsigned)nValid;
-  return out;
+  ext = acc;
+  if ((unsigned)r.iz >= (unsigned)P.nz) {              // left the domain during this burst
+    const bool top = r.iz > 0;
+    const float tX = ((top ? P.fzMax : P.fz0) - r.oz) * r.rz;
+    unsigned nv = 1u;                                  // cells entered before the boundary was reached
+#pragma unroll
+    for (int k = 1; k < B; ++k) nv += tE[k - 1] < tX ? 1u : 0u;
+    crossings += nv;
+    r.t = tX;
+    float px, py, pz;
+    ray_position(r, P, px, py, pz);
+    if (REG) {
+      r.ix = min(max((int)((px - P.fx0) * P.finvhx), 0), P.nx - 1);
+      r.iy = min(max((int)((py - P.fy0) * P.finvhy), 0), P.ny - 1);
+    } else {
+      r.ix = find_cell(G.sx, P.nx, px);
+      r.iy = find_cell(G.sy, P.ny, py);
+    }
+    r.iz = top ? P.nz - 1 : 0;
+    return top ? MARCH_TOP : MARCH_BOTTOM;
+  }
+  crossings += (unsigned)B;
+  r.t = tS;
+  if (REG) {
+    r.ix = wrap_index(r.ix, P.nx);
+    r.iy = wrap_index(r.iy, P.ny);
+  } else {                                             // keep (edge - origin) invariant under the fold
+    while (r.ix < 0) { r.ix += P.nx; r.ox += P.fLx; }
+    while (r.ix >= P.nx) { r.ix -= P.nx; r.ox -= P.fLx; }
+    while (r.iy < 0) { r.iy += P.ny; r.oy += P.fLy; }
+    while (r.iy >= P.ny) { r.iy -= P.ny; r.oy -= P.fLy; }
+  }
+  return MARCH_ON;
 }
 
 // Trace to the boundary or to an optical-depth target (the local-estimate rays, INT:1734-1739,
 // 1764-1795).  Returns the accumulated optical depth; where = 0 stopped at target, 1 top, 2 bottom.
 template <bool REG>
-__device__ float ray_trace(Ray &r, const DevDomain &P, const Grid &G, const float *__restrict__ ext32, bool hasTarget, float target,
+__device__ float ray_trace(Ray &r, const DevDomain &P, const Grid &G, const float *__restrict__ extp, bool hasTarget, float target,
                            int &where, unsigned &crossings) {
-  float ext = 0.0f, sig = 1.0f;
+  float ext = 0.0f;
   const float tgt = hasTarget ? target : FLT_MAX;
   for (;;) {
-    const int ev = march_burst<REG, 4>(r, P, G, ext32, ext, tgt, sig, crossings);
-    if (ev == MARCH_HIT) {
-      r.t += __fdividef(target - ext, sig);
-      where = 0;
-      return target;
-    }
+    const int ev = march_burst<REG, 4>(r, P, G, extp, ext, tgt, crossings);
+    if (ev == MARCH_HIT) { where = 0; return target; }
     if (ev != MARCH_ON) { where = ev; return ext; }
   }
-}
-
-__device__ __forceinline__ int find_cell(const float *e, int n, float x) {
-  int lo = 0, hi = n;                      // e[lo] <= x < e[hi]
-  while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (x >= e[mid]) lo = mid; else hi = mid; }
-  return lo;
 }
 
 __device__ __forceinline__ void dir_from(float mu, float phi, float &dx, float &dy, float &dz) {  // INT:1876-1894
@@ -328,27 +324,27 @@ __device__ void local_estimate(const DevDomain &P, const Grid &G, const Tally &T
     float contribution;
     cnt.leRays++;
     if (!P.opt.useRussianRouletteForIntensity) {                                 // INT:1729-1752
-      const float tau = ray_trace<REG>(r, P, G, P.ext32, false, 0.0f, where, cnt.leCrossings);
+      const float tau = ray_trace<REG>(r, P, G, P.extp, false, 0.0f, where, cnt.leCrossings);
       contribution = w * npf * __expf(-tau);
     } else {                                                                     // INT:1753-1813
       if ((i & 1) == 0) u = rng.block(k0, k1);          // one Philox block serves two directions
       const float uFree = (i & 1) ? u.z : u.x, uTest = (i & 1) ? u.w : u.y;
       const float tauFree = -__logf(fmaxf(TINY32, uFree));
       if (PI32 * npf <= P.opt.zetaMin) {                                         // Iwabuchi (2006) Eq 13
-        ray_trace<REG>(r, P, G, P.ext32, true, tauFree, where, cnt.leCrossings);
+        ray_trace<REG>(r, P, G, P.extp, true, tauFree, where, cnt.leCrossings);
         contribution = (uTest <= PI32 * npf / P.opt.zetaMin && where == 1) ? w * P.opt.zetaMin / PI32 : 0.0f;
       } else {                                                                   // Eq 14
         const float tauMax = -__logf(P.opt.zetaMin / fmaxf(TINY32, PI32 * npf));
-        const float tau = ray_trace<REG>(r, P, G, P.ext32, true, tauMax, where, cnt.leCrossings);
+        const float tau = ray_trace<REG>(r, P, G, P.extp, true, tauMax, where, cnt.leCrossings);
         if (where == 1) {
           contribution = w * npf * __expf(-tau);
         } else if (where == 0) {
           // continue from where the first trace stopped (INT:1793-1795)
           float qx, qy, qz;
-          ray_position<REG>(r, P, qx, qy, qz);
+          ray_position(r, P, qx, qy, qz);
           r.ox = qx; r.oy = qy; r.oz = qz;
           ray_start<REG>(r, P, G);
-          ray_trace<REG>(r, P, G, P.ext32, true, tauFree, where, cnt.leCrossings);
+          ray_trace<REG>(r, P, G, P.extp, true, tauFree, where, cnt.leCrossings);
           contribution = where == 1 ? w * P.opt.zetaMin / PI32 : 0.0f;
         } else {
           contribution = 0.0f;       // left through the surface before tauMax (zIndexF < zIndexMax)
@@ -370,14 +366,32 @@ __global__ void __launch_bounds__(THREADS, MINBLOCKS)
 batch_kernel(const __grid_constant__ DevDomain P, long long nPhotons, uint64_t seed, uint64_t firstPhotonId,
              unsigned long long *workCounter, int parkThreshold, const SmemPlan plan) {
   extern __shared__ float smem[];
+  __shared__ unsigned sCnt[4];            // rare events: surface hits, surface kills, roulette kills
   const int cols = P.nx * P.ny, cells = cols * P.nz;
   Grid G;
   G.sx = G.sy = G.sz = nullptr;
   if (!REG) {
-    float *sx = smem + plan.edgesOff, *sy = sx + (P.nx + 1), *sz = sy + (P.ny + 1);
-    for (int i = threadIdx.x; i <= P.nx; i += THREADS) sx[i] = (float)P.xE[i];
-    for (int i = threadIdx.x; i <= P.ny; i += THREADS) sy[i] = (float)P.yE[i];
-    for (int i = threadIdx.x; i <= P.nz; i += THREADS) sz[i] = (float)P.zE[i];
+    // ghost-extended edges: x, y continue periodically, z continues with the boundary spacing
+    float *sx = smem + plan.edgesOff + GH, *sy = sx + (P.nx + 1 + 2 * GH), *sz = sy + (P.ny + 1 + 2 * GH);
+    for (int i = (int)threadIdx.x - GH; i <= P.nx + GH; i += THREADS) {
+      const int j = i < 0 ? i + P.nx * ((-i + P.nx - 1) / P.nx) : i;          // j in [0, ...)
+      const int q = j / P.nx, m = j - q * P.nx;
+      const int shift = (i < 0 ? -((-i + P.nx - 1) / P.nx) : 0) + q;
+      sx[i] = (float)(P.xE[m] + (double)shift * (P.xMax - P.x0));
+    }
+    for (int i = (int)threadIdx.x - GH; i <= P.ny + GH; i += THREADS) {
+      const int j = i < 0 ? i + P.ny * ((-i + P.ny - 1) / P.ny) : i;
+      const int q = j / P.ny, m = j - q * P.ny;
+      const int shift = (i < 0 ? -((-i + P.ny - 1) / P.ny) : 0) + q;
+      sy[i] = (float)(P.yE[m] + (double)shift * (P.yMax - P.y0));
+    }
+    for (int i = (int)threadIdx.x - GH; i <= P.nz + GH; i += THREADS) {
+      double e;
+      if (i < 0) e = P.zE[0] + (double)i * (P.zE[1] - P.zE[0]);
+      else if (i > P.nz) e = P.zE[P.nz] + (double)(i - P.nz) * (P.zE[P.nz] - P.zE[P.nz - 1]);
+      else e = P.zE[i];
+      sz[i] = (float)e;
+    }
     G.sx = sx; G.sy = sy; G.sz = sz;
   }
   Tally T;
@@ -388,162 +402,51 @@ batch_kernel(const __grid_constant__ DevDomain P, long long nPhotons, uint64_t s
   if (T.sFlux) for (int i = threadIdx.x; i < 3 * cols; i += THREADS) T.sFlux[i] = 0.0f;
   if (T.sVol) for (int i = threadIdx.x; i < cells; i += THREADS) T.sVol[i] = 0.0f;
   if (T.sInt) for (int i = threadIdx.x; i < cols * P.nDir; i += THREADS) T.sInt[i] = 0.0f;
+  if (threadIdx.x < 4) sCnt[threadIdx.x] = 0u;
   __syncthreads();
 
   const int lane = threadIdx.x & 31;
-  const float *__restrict__ ext32 = P.ext32;
+  const float *__restrict__ extp = P.extp;
   const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
 
   Counts cnt{0u, 0u, 0u, 0u};
-  unsigned nSurface = 0u, nSurfaceKills = 0u, nRouletteKills = 0u;     // warp-uniform (ballot counts)
   Rng rng;
   Ray r;
-  float w = 0.0f, tau = 0.0f, ext = 0.0f, sigEv = 1.0f;
+  float w = 0.0f, tau = 0.0f, ext = 0.0f, uNext = 0.0f;
   int order = 0;
   int state = ST_DEAD;
   bool more = true;                      // photons may remain in the global counter
 
   for (;;) {
-    // ---- refill dead lanes: one atomic per warp (getNextPhoton, ILL:561-590) ----
-    {
-      const unsigned dead = __ballot_sync(FULL, state == ST_DEAD);
-      if (dead && more) {
-        unsigned long long base = 0;
-        if (lane == 0) base = atomicAdd(workCounter, (unsigned long long)__popc(dead));
-        base = __shfl_sync(FULL, base, 0);
-        if (state == ST_DEAD) {
-          const unsigned long long p = base + (unsigned long long)__popc(dead & ((1u << lane) - 1u));
-          if (p < (unsigned long long)nPhotons) {
-            rng.init(firstPhotonId + p);
-            const float4 u = rng.block(k0, k1);
-            float x01, y01, z01, mu, phi, uTau;
-            if (P.source == 0) {                                               // ILL:88-96
-              x01 = u.x; y01 = u.y; z01 = 1.0f - FLT_EPSILON; uTau = u.z;
-              mu = P.solarMu; phi = P.solarPhi;
-            } else {                                                           // ILL:481-515
-              const float4 v = rng.block(k0, k1);
-              uTau = v.w;
-              if ((double)u.x > P.fracAtmsPower) {                             // surface emission
-                x01 = u.y; y01 = u.z;
-                mu = sqrtf(fmaxf(u.w, 1.0e-30f));                              // ILL:489-491 retries on mu ~ 0
-                phi = v.x * 2.0f * PI32;
-                z01 = 0.0f;
-              } else {                                                         // atmospheric emission
-                const float q = u.y;
-                const double *levelBase = P.voxelCDF + (size_t)(P.nx - 1) + (size_t)P.nx * (size_t)(P.ny - 1);
-                const int ik = cdf_search(levelBase, P.nz, (long long)cols, q);
-                const double *colBase = P.voxelCDF + (size_t)(P.nx - 1) + (size_t)cols * (size_t)(ik - 1);
-                const int ij = cdf_search(colBase, P.ny, P.nx, q);
-                const double *voxBase = P.voxelCDF + (size_t)P.nx * ((size_t)(ij - 1) + (size_t)P.ny * (size_t)(ik - 1));
-                const int ii = cdf_search(voxBase, P.nx, 1, q);
-                // uniform inside the chosen cell, nudged off its faces (ILL:500-505)
-                z01 = ((float)(ik - 1) + fminf(fmaxf(u.z, 1e-6f), 1.0f - 1e-6f)) / (float)P.nz;
-                x01 = ((float)(ii - 1) + fminf(u.w, 1.0f - 1e-6f)) / (float)P.nx;
-                y01 = ((float)(ij - 1) + fminf(v.x, 1.0f - 1e-6f)) / (float)P.ny;
-                mu = 1.0f - 2.0f * v.y;                                        // ILL:507-509 retries on mu ~ 0
-                if (!(fabsf(mu) > 2.0f * TINY32)) mu = 1.0e-30f;
-                phi = v.z * 2.0f * PI32;
-              }
-            }
-            dir_from(mu, phi, r.dx, r.dy, r.dz);
-            w = 1.0f; order = 0;
-            // INT:478-494: unit square -> domain
-            r.ox = fmaf(x01, P.fLx, P.fx0); r.oy = fmaf(y01, P.fLy, P.fy0);
-            if (REG) {
-              r.ix = min((int)(x01 * (float)P.nx), P.nx - 1);
-              r.iy = min((int)(y01 * (float)P.ny), P.ny - 1);
-              r.oz = fmaf(z01, P.fLz, P.fz0);
-              r.iz = min((int)(z01 * (float)P.nz), P.nz - 1);
-            } else {
-              r.ix = find_cell(G.sx, P.nx, r.ox);
-              r.iy = find_cell(G.sy, P.ny, r.oy);
-              if (P.zRegular) {
-                r.oz = fmaf(z01, P.fLz, P.fz0);
-                r.iz = find_cell(G.sz, P.nz, r.oz);
-              } else {                                                         // INT:491-493
-                const float zs = z01 * (float)P.nz;
-                r.iz = min((int)zs, P.nz - 1);
-                r.oz = G.sz[r.iz] + (zs - (float)r.iz) * (G.sz[r.iz + 1] - G.sz[r.iz]);
-              }
-            }
-            if (P.opt.LW_flag > 0.0f) {                                        // INT:504-542
-              if (r.oz > 0.0f) {
-                add_flux(P, T, 2, r.ix + P.nx * r.iy, -1.0f);
-                add_vol(P, T, r.ix + P.nx * (r.iy + P.ny * r.iz), -1.0f);
-              }
-              if (LE && P.nDir > 0)
-                local_estimate<REG>(P, G, T, rng, k0, k1, r, r.ox, r.oy, r.oz, w, r.oz == 0.0f ? 0 : -1, 0, order, cnt);
-            }
-            tau = -__logf(fmaxf(TINY32, uTau));                                // INT:554
-            ext = 0.0f;
-            ray_start<REG>(r, P, G);
-            state = ST_MARCH;
-          } else {
-            state = ST_DONE;
-          }
-        }
-        if (base + (unsigned long long)__popc(dead) >= (unsigned long long)nPhotons) more = false;
-      } else if (dead && !more) {
-        if (state == ST_DEAD) state = ST_DONE;
-      }
-    }
-    if (__all_sync(FULL, state == ST_DONE)) break;
-
-    // ---- march phase: cross cells in bursts until enough lanes are parked at an event ----
-    for (;;) {
-      const unsigned mk = __ballot_sync(FULL, state == ST_MARCH);
-      const unsigned live = __ballot_sync(FULL, state != ST_DONE);
-      // stop when nobody marches, or when the parked (event/dead) lanes reach the threshold
-      if (mk == 0u || __popc(live & ~mk) >= parkThreshold) break;
-      if (state == ST_MARCH) {
-        const int ev = march_burst<REG, BURST>(r, P, G, ext32, ext, tau, sigEv, cnt.crossings);
-        // MARCH_HIT: the step itself is finished in the event phase (OPT:1729-1738); 16: "left through the top"
-        state = ev == MARCH_ON ? ST_MARCH : ev == MARCH_HIT ? ST_SCATTER : ev == MARCH_TOP ? ST_DEAD + 16 : ST_SURFACE;
-      }
-    }
-
-    // ---- event phase ----
-    if (state == ST_DEAD + 16) {                                               // INT:573-617
-      float px, py, pz;
-      (void)px; (void)py; (void)pz;
+    // =========================== event phase: every lane that is not marching ===========================
+    float px = 0.0f, py = 0.0f, pz = 0.0f;
+    int comp = 1, cell = 0;
+    if (state == ST_TOP) {                                                     // INT:573-617
       add_flux(P, T, 0, r.ix + P.nx * r.iy, w);
       state = ST_DEAD;
-    }
-    nSurface += __popc(__ballot_sync(FULL, state == ST_SURFACE));
-    if (state == ST_SURFACE) {                                                 // INT:619-702
+    } else if (state == ST_SURFACE) {                                          // INT:619-702
       add_flux(P, T, 1, r.ix + P.nx * r.iy, w);
+      atomicAdd(&sCnt[0], 1u);
       order++;
-      const float4 u = rng.block(k0, k1);
-      const float mu = sqrtf(fmaxf(u.x, 1.0e-30f));                            // INT:655-662 retries on mu ~ 0
-      const float phi = 2.0f * PI32 * u.y;
       w = (float)((double)w * P.albedo);
       if (w <= TINY32) {
-        state = ST_DEAD + 32;                                                  // 32: absorbed by the surface
+        atomicAdd(&sCnt[1], 1u);                                               // absorbed by the surface
+        state = ST_DEAD;
       } else {
-        float px, py, pz;
-        ray_position<REG>(r, P, px, py, pz);
-        r.ox = px; r.oy = py; r.oz = P.fz0; r.iz = 0;
-        dir_from(mu, phi, r.dx, r.dy, r.dz);
-        if (LE && P.nDir > 0) local_estimate<REG>(P, G, T, rng, k0, k1, r, r.ox, r.oy, r.oz, w, 0, 0, order, cnt);
-        tau = -__logf(fmaxf(TINY32, u.z));
-        ext = 0.0f;
-        ray_start<REG>(r, P, G);
-        state = ST_MARCH;
+        ray_position(r, P, px, py, pz);
+        pz = P.fz0;
+        if (LE && P.nDir > 0) local_estimate<REG>(P, G, T, rng, k0, k1, r, px, py, pz, w, 0, 0, order, cnt);
       }
-    } else if (state == ST_SCATTER) {                                          // INT:703-821
+    } else if (state == ST_SCATTER) {                                          // INT:703-811
       order++;
       cnt.scatters++;
-      r.t += __fdividef(tau - ext, sigEv);                                     // OPT:1731
-      const int cell = r.ix + P.nx * (r.iy + P.ny * r.iz);
-      // One Philox block per scattering event: u.x picks the component and, rescaled to the chosen
-      // component's interval (uniform again, conditional on the pick), decides the roulette; u.y the
-      // scattering angle; u.z the azimuth; u.w the next optical depth.
-      const float4 u = rng.block(k0, k1);
-      int comp = 1;
+      cell = r.ix + P.nx * (r.iy + P.ny * r.iz);
+      // uNext (drawn with the previous event's block) picks the component and, rescaled to the chosen
+      // component's interval (uniform again, conditional on the pick), decides the roulette
       float lo = 0.0f, hi = 1.0f;
       for (int c = 1; c < P.nc; ++c) {                                         // findIndex on (0, cumExt(:)), NUM:262-315
         const float cc = __ldg(&P.cum32[cell + (size_t)cells * (size_t)(c - 1)]);
-        if (u.x >= cc) { comp = c + 1; lo = cc; } else { hi = fminf(hi, cc); }
+        if (uNext >= cc) { comp = c + 1; lo = cc; } else { hi = fminf(hi, cc); }
       }
       const float ssa = __ldg(&P.ssa32[cell + (size_t)cells * (size_t)(comp - 1)]);
       if (ssa < 1.0f) {                                                        // INT:765-771
@@ -552,21 +455,111 @@ batch_kernel(const __grid_constant__ DevDomain P, long long nPhotons, uint64_t s
         add_vol(P, T, cell, absorbed);
         w *= ssa;
       }
-      float px, py, pz;
-      ray_position<REG>(r, P, px, py, pz);
+      ray_position(r, P, px, py, pz);
       if (LE && P.nDir > 0) local_estimate<REG>(P, G, T, rng, k0, k1, r, px, py, pz, w, comp, comp, order, cnt);   // INT:776-800
       if (P.opt.useRussianRoulette && w < P.opt.russianRouletteW * 0.5f) {     // INT:805-811
-        const float uRR = P.nc > 1 ? __fdividef(u.x - lo, fmaxf(hi - lo, TINY32)) : u.x;
+        const float uRR = P.nc > 1 ? __fdividef(uNext - lo, fmaxf(hi - lo, TINY32)) : uNext;
         if (uRR >= w / P.opt.russianRouletteW) w = 0.0f; else w = P.opt.russianRouletteW;
       }
       if (w <= TINY32) {
-        state = ST_DEAD + 48;                                                  // 48: killed by roulette
-      } else {
+        atomicAdd(&sCnt[2], 1u);                                               // killed by roulette
+        state = ST_DEAD;
+      }
+    }
+    // ---- finished lanes take the next photons: one atomic per warp (getNextPhoton, ILL:561-590) ----
+    {
+      const unsigned dead = __ballot_sync(FULL, state == ST_DEAD);
+      if (dead) {
+        if (more) {
+          unsigned long long base = 0;
+          if (lane == 0) base = atomicAdd(workCounter, (unsigned long long)__popc(dead));
+          base = __shfl_sync(FULL, base, 0);
+          if (state == ST_DEAD) {
+            const unsigned long long p = base + (unsigned long long)__popc(dead & ((1u << lane) - 1u));
+            if (p < (unsigned long long)nPhotons) { rng.init(firstPhotonId + p); state = ST_BORN; }
+            else state = ST_DONE;
+          }
+          if (base + (unsigned long long)__popc(dead) >= (unsigned long long)nPhotons) more = false;
+        } else if (state == ST_DEAD) {
+          state = ST_DONE;
+        }
+      }
+    }
+    if (__all_sync(FULL, state == ST_DONE)) break;
+    // ---- one Philox block for every parked lane: (angle | position, azimuth | position, next optical depth, next pick) ----
+    if (state != ST_MARCH && state != ST_DONE) {
+      const float4 u = rng.block(k0, k1);
+      float uTau = u.z;
+      if (state == ST_BORN) {
+        float x01, y01, z01;
+        w = 1.0f; order = 0;
+        if (P.source == 0) {                                                   // ILL:88-96
+          x01 = u.x; y01 = u.y; z01 = 1.0f - FLT_EPSILON;
+          r.dx = P.solarDir[0]; r.dy = P.solarDir[1]; r.dz = P.solarDir[2];
+        } else {                                                               // ILL:481-515
+          const float4 v = rng.block(k0, k1);
+          float mu, phi;
+          if ((double)u.x > P.fracAtmsPower) {                                 // surface emission
+            x01 = u.y; y01 = v.w;
+            mu = sqrtf(fmaxf(v.x, 1.0e-30f));                                  // ILL:489-491 retries on mu ~ 0
+            phi = v.y * 2.0f * PI32;
+            z01 = 0.0f;
+          } else {                                                             // atmospheric emission
+            const float q = u.y;
+            const double *levelBase = P.voxelCDF + (size_t)(P.nx - 1) + (size_t)P.nx * (size_t)(P.ny - 1);
+            const int ik = cdf_search(levelBase, P.nz, (long long)cols, q);
+            const double *colBase = P.voxelCDF + (size_t)(P.nx - 1) + (size_t)cols * (size_t)(ik - 1);
+            const int ij = cdf_search(colBase, P.ny, P.nx, q);
+            const double *voxBase = P.voxelCDF + (size_t)P.nx * ((size_t)(ij - 1) + (size_t)P.ny * (size_t)(ik - 1));
+            const int ii = cdf_search(voxBase, P.nx, 1, q);
+            // uniform inside the chosen cell, nudged off its faces (ILL:500-505)
+            const float4 v2 = rng.block(k0, k1);
+            z01 = ((float)(ik - 1) + fminf(fmaxf(v2.x, 1e-6f), 1.0f - 1e-6f)) / (float)P.nz;
+            x01 = ((float)(ii - 1) + fminf(v2.y, 1.0f - 1e-6f)) / (float)P.nx;
+            y01 = ((float)(ij - 1) + fminf(v2.z, 1.0f - 1e-6f)) / (float)P.ny;
+            mu = 1.0f - 2.0f * v.x;                                            // ILL:507-509 retries on mu ~ 0
+            if (!(fabsf(mu) > 2.0f * TINY32)) mu = 1.0e-30f;
+            phi = v.y * 2.0f * PI32;
+          }
+          dir_from(mu, phi, r.dx, r.dy, r.dz);
+        }
+        // INT:478-494: unit square -> domain
+        px = fmaf(x01, P.fLx, P.fx0); py = fmaf(y01, P.fLy, P.fy0);
+        if (REG) {
+          r.ix = min((int)(x01 * (float)P.nx), P.nx - 1);
+          r.iy = min((int)(y01 * (float)P.ny), P.ny - 1);
+          pz = fmaf(z01, P.fLz, P.fz0);
+          r.iz = min((int)(z01 * (float)P.nz), P.nz - 1);
+        } else {
+          r.ix = find_cell(G.sx, P.nx, px);
+          r.iy = find_cell(G.sy, P.ny, py);
+          if (P.zRegular) {
+            pz = fmaf(z01, P.fLz, P.fz0);
+            r.iz = find_cell(G.sz, P.nz, pz);
+          } else {                                                             // INT:491-493
+            const float zs = z01 * (float)P.nz;
+            r.iz = min((int)zs, P.nz - 1);
+            pz = G.sz[r.iz] + (zs - (float)r.iz) * (G.sz[r.iz + 1] - G.sz[r.iz]);
+          }
+        }
+        if (P.opt.LW_flag > 0.0f) {                                            // INT:504-542
+          if (pz > 0.0f) {
+            add_flux(P, T, 2, r.ix + P.nx * r.iy, -1.0f);
+            add_vol(P, T, r.ix + P.nx * (r.iy + P.ny * r.iz), -1.0f);
+          }
+          if (LE && P.nDir > 0)
+            local_estimate<REG>(P, G, T, rng, k0, k1, r, px, py, pz, w, pz == 0.0f ? 0 : -1, 0, order, cnt);
+        }
+      } else if (state == ST_SURFACE) {                                        // INT:655-676
+        const float mu = sqrtf(fmaxf(u.x, 1.0e-30f));                          // retries on mu ~ 0
+        dir_from(mu, 2.0f * PI32 * u.y, r.dx, r.dy, r.dz);
+        r.iz = 0;
+      } else {                                                                 // ST_SCATTER, INT:813-819
         const int c = comp - 1;
         const int pidx = (int)__ldg(&P.idx16[cell + (size_t)cells * (size_t)c]);
         const int nS = P.invS[c];
         const float *tab = P.inv[c] + (size_t)(pidx - 1) * nS;
-        const float rn = u.y;                                                  // computeScatteringAngle INT:1594-1621
+        const float rn = u.x;                                                  // computeScatteringAngle INT:1594-1621
         const int k = (int)(rn * (float)nS) + 1;
         float theta;
         if (k < nS) {
@@ -580,23 +573,33 @@ batch_kernel(const __grid_constant__ DevDomain P, long long nPhotons, uint64_t s
         // next_direct INT:1921-1948: the reference rejection-samples (AX, AY) in the unit disc and
         // normalises it, i.e. draws a uniform azimuth; the azimuth is drawn directly here.
         float AX, AY;
-        __sincosf(2.0f * PI32 * u.z, &AY, &AX);
+        __sincosf(2.0f * PI32 * u.y, &AY, &AX);
         AX *= sinT; AY *= sinT;
         const float B = r.dx * AX - r.dy * AY;
         const float D = cosT - __fdividef(B, 1.0f + fabsf(r.dz));
         const float ndx = r.dx * D + AX, ndy = r.dy * D - AY;
         const float ndz = r.dz * cosT - copysignf(fabsf(B), r.dz * B);
-        r.ox = px; r.oy = py; r.oz = pz;
         r.dx = ndx; r.dy = ndy; r.dz = ndz;
-        tau = -__logf(fmaxf(TINY32, u.w));
-        ext = 0.0f;
-        ray_start<REG>(r, P, G);
-        state = ST_MARCH;
+      }
+      // ---- common: start the next leg ----
+      r.ox = px; r.oy = py; r.oz = pz;
+      tau = -__logf(fmaxf(TINY32, uTau));                                      // INT:554
+      uNext = u.w;
+      ext = 0.0f;
+      ray_start<REG>(r, P, G);
+      state = ST_MARCH;
+    }
+
+    // =========================== march phase: bursts until enough lanes are parked ===========================
+    for (;;) {
+      const unsigned mk = __ballot_sync(FULL, state == ST_MARCH);
+      const unsigned live = __ballot_sync(FULL, state != ST_DONE);
+      if (mk == 0u || __popc(live & ~mk) >= parkThreshold) break;
+      if (state == ST_MARCH) {
+        const int ev = march_burst<REG, BURST>(r, P, G, extp, ext, tau, cnt.crossings);
+        state = ev == MARCH_ON ? ST_MARCH : ev == MARCH_HIT ? ST_SCATTER : ev == MARCH_TOP ? ST_TOP : ST_SURFACE;
       }
     }
-    nSurfaceKills += __popc(__ballot_sync(FULL, state == ST_DEAD + 32));
-    nRouletteKills += __popc(__ballot_sync(FULL, state == ST_DEAD + 48));
-    if (state > ST_DONE) state = ST_DEAD;
   }
 
   // ---- flush: event counters (warp shuffle reduce, one atomic per warp) ----
@@ -608,13 +611,13 @@ batch_kernel(const __grid_constant__ DevDomain P, long long nPhotons, uint64_t s
       for (int o = 16; o > 0; o >>= 1) v[i] += __shfl_down_sync(FULL, v[i], o);
       if (lane == 0 && v[i]) atomicAdd(&P.counters[slot[i]], v[i]);
     }
-    if (lane == 0) {                       // warp-uniform ballot counts
-      if (nSurface) atomicAdd(&P.counters[CNT_SURFACE], (unsigned long long)nSurface);
-      if (nRouletteKills) atomicAdd(&P.counters[CNT_RR_KILLS], (unsigned long long)nRouletteKills);
-      if (nSurfaceKills) atomicAdd(&P.counters[CNT_SURFACE_KILLS], (unsigned long long)nSurfaceKills);
-    }
   }
   __syncthreads();
+  if (threadIdx.x == 0) {
+    if (sCnt[0]) atomicAdd(&P.counters[CNT_SURFACE], (unsigned long long)sCnt[0]);
+    if (sCnt[1]) atomicAdd(&P.counters[CNT_SURFACE_KILLS], (unsigned long long)sCnt[1]);
+    if (sCnt[2]) atomicAdd(&P.counters[CNT_RR_KILLS], (unsigned long long)sCnt[2]);
+  }
   // ---- flush: privatised tallies, once per block, into the f64 tally buffer ----
   if (T.sFlux)
     for (int i = threadIdx.x; i < 3 * cols; i += THREADS) {
@@ -658,7 +661,7 @@ static void launch(const DevDomain &P, long long nPhotons, uint64_t seed, uint64
   const int cols = P.nx * P.ny, cells = cols * P.nz;
   mcbfast::SmemPlan plan{-1, -1, -1, -1, 0};
   int off = 0;
-  if (!REG) { plan.edgesOff = off; off += P.nx + P.ny + P.nz + 3; }
+  if (!REG) { plan.edgesOff = off; off += P.nx + P.ny + P.nz + 3 + 6 * MCB_GHOST; }
   const int budgetFloats = 9 * 1024;            // 36 KB per block keeps >= 6 blocks/SM resident
   if (3 * cols <= 3 * 1024 && off + 3 * cols <= budgetFloats) { plan.fluxOff = off; off += 3 * cols; }
   if (cells <= 8192 && off + cells <= budgetFloats) { plan.volOff = off; off += cells; }
@@ -681,18 +684,16 @@ void mcb_launch_fast_batch(const DevDomain &P, long long nPhotons, uint64_t seed
                            int numSMs, unsigned long long *workCounter, cudaStream_t stream) {
   if (nPhotons <= 0) return;
   static int occ = -1, burst = -1;   // register budget / burst length variants (tuning knobs; defaults chosen from measurements)
-  if (occ < 0) { const char *e = getenv("MCB_BLOCKS_PER_SM"); occ = e ? atoi(e) : 5; }
+  if (occ < 0) { const char *e = getenv("MCB_BLOCKS_PER_SM"); occ = e ? atoi(e) : 6; }
   if (burst < 0) { const char *e = getenv("MCB_BURST"); burst = e ? atoi(e) : 8; }
 #define MCB_GO(REG, OCC, BURST) do { \
     if (P.nDir > 0) launch<REG, OCC, BURST, true>(P, nPhotons, seed, firstPhotonId, numSMs, workCounter, stream); \
     else launch<REG, OCC, BURST, false>(P, nPhotons, seed, firstPhotonId, numSMs, workCounter, stream); } while (0)
-  if (P.xyRegular && P.zRegular) {
-    if (burst >= 16) MCB_GO(true, 4, 16);
-    else if (burst >= 12) MCB_GO(true, 4, 12);
-    else if (burst >= 8) { if (occ >= 5) MCB_GO(true, 5, 8); else MCB_GO(true, 4, 8); }
+  if (P.xyRegular && P.zRegular) {            // burst length <= MCB_GHOST (the ghost shell is that deep)
+    if (burst >= 8) { if (occ >= 6) MCB_GO(true, 6, 8); else if (occ <= 4) MCB_GO(true, 4, 8); else MCB_GO(true, 5, 8); }
     else { if (occ >= 6) MCB_GO(true, 6, 4); else if (occ <= 4) MCB_GO(true, 4, 4); else MCB_GO(true, 5, 4); }
   } else {
-    MCB_GO(false, 4, 4);
+    if (burst >= 8) MCB_GO(false, 4, 8); else MCB_GO(false, 4, 4);
   }
 #undef MCB_GO
 }
