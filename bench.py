@@ -121,23 +121,60 @@ def run_reference(args):
 # clocks sampling during the timed region
 # ----------------------------------------------------------------------------------------------
 class ClockSampler:
+    """SM clock and throttle reasons sampled DURING the timed region: NVML in-process every 10 ms
+    (nvidia-smi as a fallback, ~10 samples/s)."""
     Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
     def __init__(self, index):
         self.index = index; self.samples = []; self.stop = False; self.t = None
+        self.nvml = None; self.dev = None; self.max_mhz = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            # NVML enumerates physical devices: honour CUDA_VISIBLE_DEVICES when it is a plain index list
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = index
+            if vis:
+                ids = [v.strip() for v in vis.split(",") if v.strip()]
+                if index < len(ids) and ids[index].isdigit():
+                    phys = int(ids[index])
+            self.dev = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.dev, pynvml.NVML_CLOCK_SM))
+            self.nvml = pynvml
+        except Exception:
+            self.nvml = None
+
+    def _sample_nvml(self):
+        n = self.nvml
+        mhz = float(n.nvmlDeviceGetClockInfo(self.dev, n.NVML_CLOCK_SM))
+        r = int(n.nvmlDeviceGetCurrentClocksEventReasons(self.dev)) if hasattr(n, "nvmlDeviceGetCurrentClocksEventReasons") \
+            else int(n.nvmlDeviceGetCurrentClocksThrottleReasons(self.dev))
+        flags = [bool(r & 0x8), bool(r & 0x40), bool(r & 0x20), bool(r & 0x4)]   # hw_slowdown, hw_thermal, sw_thermal, sw_power_cap
+        try:
+            pw = n.nvmlDeviceGetPowerUsage(self.dev) / 1000.0
+        except Exception:
+            pw = None
+        return [mhz, self.max_mhz] + flags + [pw]
+
+    def _sample_smi(self):
+        out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                              "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+        parts = [p.strip() for p in out.strip().split(",")]
+        if len(parts) < 6:
+            return None
+        return [float(parts[0]), float(parts[1])] + [p.lower().startswith("active") for p in parts[2:6]] + [None]
 
     def _run(self):
         while not self.stop:
             try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
-                parts = [p.strip() for p in out.strip().split(",")]
-                if len(parts) >= 6:
-                    self.samples.append(parts)
+                s = self._sample_nvml() if self.nvml else self._sample_smi()
+                if s:
+                    self.samples.append(s)
             except Exception:
                 pass
-            time.sleep(0.1)
+            time.sleep(0.01 if self.nvml else 0.1)
 
     def __enter__(self):
         self.t = threading.Thread(target=self._run, daemon=True); self.t.start(); return self
@@ -148,11 +185,12 @@ class ClockSampler:
     def summary(self):
         if not self.samples:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
-        sm = sorted(float(s[0]) for s in self.samples)
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(s[2 + i].lower().startswith("active") for s in self.samples)]
-        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.samples[0][1]), "reasons": reasons,
-                "samples": len(sm)}
+        sm = sorted(s[0] for s in self.samples)
+        reasons = [n for i, n in enumerate(self.NAMES) if any(s[2 + i] for s in self.samples)]
+        pw = [s[6] for s in self.samples if s[6] is not None]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_min_mhz": sm[0], "sm_max_mhz": float(self.samples[0][1]), "reasons": reasons,
+                "samples": len(sm), "power_w_max": max(pw) if pw else None,
+                "source": "nvml" if self.nvml else "nvidia-smi"}
 
 
 def algorithmic_bytes(c, nc):
@@ -252,8 +290,10 @@ def run_ours(args):
         setattr(dom, name, tbuf.numpy().reshape(a.shape))
     h2d = sum(p.numel() * p.element_size() for p in pinned.values()) + sum(T.nbytes for T in dom.inversePhaseFunctions)
     cells = dom.numX * dom.numY * dom.numZ
-    h2d += cells * (4 + 4 * g.numComps + 4 * g.numComps + 2 * g.numComps)       # packed single-precision copies
-    d2h = int(tally.numel()) * 8
+    cols = dom.numX * dom.numY
+    # the packed single-precision copies are produced in HBM (csrc/mcb_stage.cu), they do not cross PCIe;
+    # reportResults brings back the normalised f32 arrays asked for below, not the f64 tally buffer
+    d2h = 4 * (3 * cols + cells + (cols * len(case["intensityMus"]) if args.views else 0))
     e2e_steps = max(1, min(args.steps, 3))
 
     def e2e_step(i):

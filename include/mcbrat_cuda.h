@@ -105,6 +105,8 @@ int mcb_set_thermal_source(mcb_handle *h, double fracAtmsPower, const double *vo
 /* device build of the same CDF from the staged optics (EMI:498-522); temps(nx,ny,nz) in K   */
 int mcb_build_thermal_source(mcb_handle *h, const double *temps, double lambda_um,
                              double surfaceTemp, double *fracAtmsPower, double *totalFlux);
+/* read the staged Weights back (voxelWeights EMI:56-57, fracAtmsPower); either pointer may be NULL */
+int mcb_get_thermal_source(mcb_handle *h, double *fracAtmsPower, double *voxelCDF, int64_t nDoubles);
 
 /* ---- computeRadiativeTransfer (INT:209-218) ------------------------------------------- */
 /* Zero the tallies (INT:247-272) and trace nPhotons photons with global ids

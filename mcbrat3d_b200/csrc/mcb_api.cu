@@ -3,6 +3,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <map>
 #include <string>
 #include <vector>
 
@@ -16,6 +17,14 @@ void mcb_launch_trace(const DevDomain &P, long long nPhotons, const float *rn, l
 void mcb_launch_fast_batch(const DevDomain &P, long long nPhotons, uint64_t seed, uint64_t firstPhotonId,
                            int numSMs, unsigned long long *workCounter, cudaStream_t stream);
 void mcb_launch_philox_kat(uint64_t seed, uint64_t photon, int n, uint32_t *out, cudaStream_t stream);
+// mcb_stage.cu: device-side packing / validation, normalisation, emission CDF
+void mcb_launch_pack_optics(const DevDomain &P, float *e32, float *c32, float *s32, uint16_t *i16, int *flags,
+                            int numSMs, cudaStream_t stream);
+void mcb_launch_normalise(const DevDomain &P, float numPhotons, float *out, int numSMs, cudaStream_t stream);
+long long mcb_emission_tiles(long long cells);
+void mcb_launch_emission_cdf(const DevDomain &P, const double *temps, double a, double b, double lambda5, void *scratch,
+                             double *cdf, int *flags, int numSMs, cudaStream_t stream);
+void mcb_launch_emission_normalise(double *cdf, long long cells, const void *total, int numSMs, cudaStream_t stream);
 
 struct mcb_handle {
   int device = 0;
@@ -28,14 +37,15 @@ struct mcb_handle {
   bool haveGrid = false, haveOptics = false, haveSource = false;
   bool haveInv[MCB_MAX_COMP] = {false}, haveFwd[MCB_MAX_COMP] = {false};
   std::vector<double> xE, yE, zE;
-  std::vector<void *> owned;              // every device allocation, freed in mcb_destroy
+  std::map<void **, size_t> slotBytes;    // capacity of every re-stageable slot (reused while large enough)
   // re-stageable slots (freed on re-set)
   void *dXE = nullptr, *dYE = nullptr, *dZE = nullptr;
   void *dTotalExt = nullptr, *dCumExt = nullptr, *dSsa = nullptr, *dPhaseIdx = nullptr;
   void *dExt32 = nullptr, *dCum32 = nullptr, *dSsa32 = nullptr, *dIdx16 = nullptr;
   void *dInv[MCB_MAX_COMP] = {nullptr}, *dFwd[MCB_MAX_COMP] = {nullptr}, *dFwdOrig[MCB_MAX_COMP] = {nullptr};
   int invE[MCB_MAX_COMP] = {0}, fwdE[MCB_MAX_COMP] = {0};
-  void *dVoxelCDF = nullptr;
+  void *dVoxelCDF = nullptr, *dTemps = nullptr, *dScratch = nullptr, *dResults = nullptr;
+  int *dFlags = nullptr;
   double *dTally = nullptr; long long nTally = 0;
   unsigned long long *dCounters = nullptr;     // CNT_N counters + 1 work counter
   double *hTally = nullptr; long long hTallyCap = 0;   // pinned
@@ -53,13 +63,32 @@ struct mcb_handle {
     if (_e != cudaSuccess) FAIL(h, "%s: %s", #call, cudaGetErrorString(_e)); \
   } while (0)
 
-static int stage(mcb_handle *h, void **slot, const void *src, size_t bytes) {
+// Make *slot a device buffer of at least `bytes` (kept while large enough: re-staging a domain of the
+// same shape does no cudaMalloc / cudaFree, which would serialise the device).
+static int reserve(mcb_handle *h, void **slot, size_t bytes) {
   CK(h, cudaSetDevice(h->device));
+  if (bytes == 0) bytes = 16;
+  auto it = h->slotBytes.find(slot);
+  if (*slot && it != h->slotBytes.end() && it->second >= bytes) return 0;
   if (*slot) { cudaFree(*slot); *slot = nullptr; }
-  CK(h, cudaMalloc(slot, bytes ? bytes : 16));
-  if (src && bytes) CK(h, cudaMemcpyAsync(*slot, src, bytes, cudaMemcpyHostToDevice, h->stream));
-  CK(h, cudaStreamSynchronize(h->stream));       // the library never retains the host pointer
+  CK(h, cudaMalloc(slot, bytes));
+  h->slotBytes[slot] = bytes;
   return 0;
+}
+
+// Copy a host array into a slot, asynchronously on the handle's stream.  Every mcb_set_* ends with
+// settle(): the library never retains the host pointer.
+static int stage_async(mcb_handle *h, void **slot, const void *src, size_t bytes) {
+  if (reserve(h, slot, bytes)) return 1;
+  if (src && bytes) CK(h, cudaMemcpyAsync(*slot, src, bytes, cudaMemcpyHostToDevice, h->stream));
+  return 0;
+}
+static int settle(mcb_handle *h) {
+  CK(h, cudaStreamSynchronize(h->stream));
+  return 0;
+}
+static int stage(mcb_handle *h, void **slot, const void *src, size_t bytes) {
+  return stage_async(h, slot, src, bytes) || settle(h);
 }
 
 static double sp64h(double x) {
@@ -101,6 +130,7 @@ int mcb_create(int device, mcb_handle **out) {
   if (cudaMalloc((void **)&h->dCounters, sizeof(unsigned long long) * 32) != cudaSuccess) { delete h; return 6; }
   cudaMemset(h->dCounters, 0, sizeof(unsigned long long) * 32);
   h->P.counters = h->dCounters;
+  if (cudaMalloc((void **)&h->dFlags, sizeof(int) * 4) != cudaSuccess) { delete h; return 6; }
   *out = h;
   return 0;
 }
@@ -110,7 +140,8 @@ int mcb_destroy(mcb_handle *h) {
   cudaSetDevice(h->device);
   cudaStreamSynchronize(h->stream);
   void *slots[] = {h->dXE, h->dYE, h->dZE, h->dTotalExt, h->dCumExt, h->dSsa, h->dPhaseIdx,
-                   h->dExt32, h->dCum32, h->dSsa32, h->dIdx16, h->dVoxelCDF, h->dTally, h->dCounters};
+                   h->dExt32, h->dCum32, h->dSsa32, h->dIdx16, h->dVoxelCDF, h->dTally, h->dCounters,
+                   h->dTemps, h->dScratch, h->dResults, (void *)h->dFlags};
   for (void *p : slots) if (p) cudaFree(p);
   for (int c = 0; c < MCB_MAX_COMP; ++c) {
     if (h->dInv[c]) cudaFree(h->dInv[c]);
@@ -206,41 +237,35 @@ int mcb_set_optics(mcb_handle *h, int nc, const double *totalExt, const double *
   if (!totalExt || !cumExt || !ssa || !phaseIdx) FAIL(h, "mcb_set_optics: null array");
   DevDomain &P = h->P;
   const size_t cells = (size_t)P.nx * P.ny * P.nz;
-  for (size_t i = 0; i < cells; ++i) if (!(totalExt[i] >= 0.0)) FAIL(h, "addOpticalComponent: extinction must be >= 0.");
-  for (size_t i = 0; i < cells * nc; ++i) {
-    if (!(ssa[i] >= 0.0 && ssa[i] <= 1.0)) FAIL(h, "addOpticalComponent: singleScatteringAlbedo must be between 0 and 1");
-    if (phaseIdx[i] < 0 || phaseIdx[i] > 65535) FAIL(h, "addOpticalComponent: phase function index is out of bounds");
-  }
-  if (stage(h, &h->dTotalExt, totalExt, sizeof(double) * cells)) return 1;
-  if (stage(h, &h->dCumExt, cumExt, sizeof(double) * cells * nc)) return 1;
-  if (stage(h, &h->dSsa, ssa, sizeof(double) * cells * nc)) return 1;
-  if (stage(h, &h->dPhaseIdx, phaseIdx, sizeof(int32_t) * cells * nc)) return 1;
-  {  // packed single-precision copies for the fast kernel
-    // extinction with its ghost shell: x and y continue periodically (OPT:1782-1796 becomes data instead
-    // of per-cell tests), the layers above the top and below the surface are empty (OPT:1801-1812)
-    const int G = MCB_GHOST, nxp = P.nxp, nyp = P.nyp, nzp = P.nz + 2 * G;
-    std::vector<float> e32((size_t)nxp * nyp * nzp, 0.0f), c32(cells * nc), s32(cells * nc);
-    std::vector<uint16_t> i16(cells * nc);
-    std::vector<int> mx(nxp), my(nyp);
-    for (int i = 0; i < nxp; ++i) mx[i] = (((i - G) % P.nx) + P.nx) % P.nx;
-    for (int j = 0; j < nyp; ++j) my[j] = (((j - G) % P.ny) + P.ny) % P.ny;
-    for (int k = 0; k < P.nz; ++k)
-      for (int j = 0; j < nyp; ++j) {
-        const double *src = totalExt + (size_t)P.nx * ((size_t)my[j] + (size_t)P.ny * k);
-        float *dst = e32.data() + (size_t)nxp * ((size_t)j + (size_t)nyp * (k + G));
-        for (int i = 0; i < nxp; ++i) dst[i] = (float)src[mx[i]];
-      }
-    for (size_t i = 0; i < cells * nc; ++i) { c32[i] = (float)cumExt[i]; s32[i] = (float)ssa[i]; i16[i] = (uint16_t)phaseIdx[i]; }
-    if (stage(h, &h->dExt32, e32.data(), sizeof(float) * e32.size())) return 1;
-    if (stage(h, &h->dCum32, c32.data(), sizeof(float) * cells * nc)) return 1;
-    if (stage(h, &h->dSsa32, s32.data(), sizeof(float) * cells * nc)) return 1;
-    if (stage(h, &h->dIdx16, i16.data(), sizeof(uint16_t) * cells * nc)) return 1;
-  }
+  h->haveOptics = false;
+  // The four host arrays cross PCIe once, as they are; the packed single-precision copies the fast kernel reads
+  // (ghost-shelled extinction: periodic replicas in x, y -- OPT:1782-1796 becomes data instead of per-cell tests --
+  // and empty layers above and below, OPT:1801-1812) and the argument checks of addOpticalComponent are produced
+  // in HBM by mcb_stage.cu.
+  if (stage_async(h, &h->dTotalExt, totalExt, sizeof(double) * cells)) return 1;
+  if (stage_async(h, &h->dCumExt, cumExt, sizeof(double) * cells * nc)) return 1;
+  if (stage_async(h, &h->dSsa, ssa, sizeof(double) * cells * nc)) return 1;
+  if (stage_async(h, &h->dPhaseIdx, phaseIdx, sizeof(int32_t) * cells * nc)) return 1;
+  const size_t padded = (size_t)P.nxp * P.nyp * (P.nz + 2 * MCB_GHOST);
+  if (reserve(h, &h->dExt32, sizeof(float) * padded)) return 1;
+  if (reserve(h, &h->dCum32, sizeof(float) * cells * nc)) return 1;
+  if (reserve(h, &h->dSsa32, sizeof(float) * cells * nc)) return 1;
+  if (reserve(h, &h->dIdx16, sizeof(uint16_t) * cells * nc)) return 1;
   P.nc = nc; P.albedo = albedo;
   P.totalExt = (const double *)h->dTotalExt; P.cumExt = (const double *)h->dCumExt;
   P.ssa = (const double *)h->dSsa; P.phaseIdx = (const int32_t *)h->dPhaseIdx;
   P.extp = (const float *)h->dExt32 + P.ghostOrigin; P.cum32 = (const float *)h->dCum32;
   P.ssa32 = (const float *)h->dSsa32; P.idx16 = (const uint16_t *)h->dIdx16;
+  CK(h, cudaMemsetAsync(h->dFlags, 0, sizeof(int) * 4, h->stream));
+  mcb_launch_pack_optics(P, (float *)h->dExt32, (float *)h->dCum32, (float *)h->dSsa32, (uint16_t *)h->dIdx16, h->dFlags,
+                         h->numSMs, h->stream);
+  CK(h, cudaGetLastError());
+  int flags = 0;
+  CK(h, cudaMemcpyAsync(&flags, h->dFlags, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  if (settle(h)) return 1;
+  if (flags & 1) FAIL(h, "addOpticalComponent: extinction must be >= 0.");
+  if (flags & 2) FAIL(h, "addOpticalComponent: singleScatteringAlbedo must be between 0 and 1");
+  if (flags & 4) FAIL(h, "addOpticalComponent: phase function index is out of bounds");
   for (int c = 0; c < MCB_MAX_COMP; ++c) { h->haveInv[c] = false; h->haveFwd[c] = false; }
   h->haveOptics = true;
   return 0;
@@ -317,70 +342,77 @@ int mcb_set_thermal_source(mcb_handle *h, double fracAtmsPower, const double *vo
   return 0;
 }
 
-// emission_weightingNEW EMI:424-550 on the staged optics.  Setup-time staging code: the
-// Kahan prefix sum runs on the host over arrays read back from HBM.
+// emission_weightingNEW EMI:424-550 on the staged optics: Planck emission per cell and the prefix sum
+// over cells run on the device (mcb_stage.cu); only the total comes back for the power bookkeeping.
 int mcb_build_thermal_source(mcb_handle *h, const double *temps, double lambda_um,
                              double surfaceTemp, double *fracAtmsPowerOut, double *totalFluxOut) {
   if (!h) return 1;
   if (!h->haveOptics) FAIL(h, "emission_weighting: domain hasn't been initialized.");
   if (!temps) FAIL(h, "emission_weighting: null temperature array");
   const DevDomain &P = h->P;
-  const int nx = P.nx, ny = P.ny, nz = P.nz, nc = P.nc;
-  const size_t cells = (size_t)nx * ny * nz;
-  std::vector<double> totalExt(cells), cumExt(cells * nc), ssa(cells * nc), cdf(cells, 0.0);
-  CK(h, cudaSetDevice(h->device));
-  CK(h, cudaMemcpy(totalExt.data(), P.totalExt, sizeof(double) * cells, cudaMemcpyDeviceToHost));
-  CK(h, cudaMemcpy(cumExt.data(), P.cumExt, sizeof(double) * cells * nc, cudaMemcpyDeviceToHost));
-  CK(h, cudaMemcpy(ssa.data(), P.ssa, sizeof(double) * cells * nc, cudaMemcpyDeviceToHost));
+  const int nx = P.nx, ny = P.ny;
+  const long long cells = (long long)nx * ny * P.nz;
   const double hP = 6.62606957e-34, cL = 2.99792458e+8, kB = 1.3806488e-23;
   const double a = 2.0 * hP * (cL * cL);
   const double Pi = 4.0 * std::atan(1.0);
   const double emiss = 1.0 - P.albedo;
   const double lambda = lambda_um / 1.0e6;
   const double b = hP * cL / (kB * lambda);
+  const double lambda5 = std::pow(lambda, 5.0);
   const double areaX = h->xE[nx] - h->xE[0], areaY = h->yE[ny] - h->yE[0];
   double sfcPower = 0.0;
   if (!(emiss == 0.0 || surfaceTemp == 0.0)) {
-    const double sfcPlanckRad = (a / (std::pow(lambda, 5.0) * (std::exp(b / surfaceTemp) - 1.0))) / 1.0e6;
+    const double sfcPlanckRad = (a / (lambda5 * (std::exp(b / surfaceTemp) - 1.0))) / 1.0e6;
     sfcPower = Pi * emiss * sfcPlanckRad * areaX * areaY * (1000.0 * 1000.0);
   }
-  bool anyCold = false;
-  for (size_t i = 0; i < cells; ++i) if (temps[i] <= 0.0) anyCold = true;
-  double previous = 0.0, corr = 0.0;
-  if (!anyCold) {
-    for (int iz = 0; iz < nz; ++iz) {
-      const double dz = h->zE[iz + 1] - h->zE[iz];
-      for (size_t k = 0; k < (size_t)nx * ny; ++k) {
-        const size_t cell = k + (size_t)nx * ny * iz;
-        const double planck = (a / (std::pow(lambda, 5.0) * (std::exp(b / temps[cell]) - 1.0))) / 1.0e6;
-        double sumSsaExt = 0.0;
-        for (int j = 0; j < nc; ++j) {
-          const double extj = j == 0 ? totalExt[cell] * cumExt[cell]
-                                     : totalExt[cell] * (cumExt[cell + cells * j] - cumExt[cell + cells * (j - 1)]);
-          sumSsaExt += ssa[cell + cells * j] * extj;
-        }
-        const double totalAbsCoef = totalExt[cell] - sumSsaExt;
-        const double corr_contrib = (4.0 * Pi * planck * totalAbsCoef * dz) - corr;      // Kahan, EMI:505-509
-        const double temp_sum = previous + corr_contrib;
-        corr = (temp_sum - previous) - corr_contrib;
-        previous = temp_sum;
-        cdf[cell] = previous;
-      }
-    }
+  const long long tiles = mcb_emission_tiles(cells);
+  if (stage_async(h, &h->dTemps, temps, sizeof(double) * cells)) return 1;
+  if (reserve(h, &h->dScratch, sizeof(double) * 2 * (size_t)(tiles + 1))) return 1;
+  if (reserve(h, &h->dVoxelCDF, sizeof(double) * cells)) return 1;
+  CK(h, cudaMemsetAsync(h->dFlags, 0, sizeof(int) * 4, h->stream));
+  mcb_launch_emission_cdf(P, (const double *)h->dTemps, a, b, lambda5, h->dScratch, (double *)h->dVoxelCDF, h->dFlags,
+                          h->numSMs, h->stream);
+  CK(h, cudaGetLastError());
+  int flags = 0;
+  double total[2] = {0.0, 0.0};
+  CK(h, cudaMemcpyAsync(&flags, h->dFlags, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  CK(h, cudaMemcpyAsync(total, (const double *)h->dScratch + 2 * tiles, sizeof(total), cudaMemcpyDeviceToHost, h->stream));
+  if (settle(h)) return 1;
+  double last = total[0];
+  if (flags & 8) {                                   // a temperature <= 0: the atmosphere does not emit (EMI:498)
+    last = 0.0;
+    CK(h, cudaMemsetAsync(h->dVoxelCDF, 0, sizeof(double) * cells, h->stream));
   }
   double atmsPower = 0.0, frac = 0.0;
-  const double last = cdf[cells - 1];
   if (last > 0.0) {                                                                       // EMI:512-521
     atmsPower = last * areaX * areaY * (1000.0 * 1000.0) / (double)(nx * ny);
-    for (size_t i = 0; i < cells; ++i) cdf[i] = cdf[i] / last;
-    cdf[cells - 1] = 1.0;
+    mcb_launch_emission_normalise((double *)h->dVoxelCDF, cells, (const double *)h->dScratch + 2 * tiles, h->numSMs, h->stream);
+    CK(h, cudaGetLastError());
     frac = atmsPower / (atmsPower + sfcPower);
   }
+  if (settle(h)) return 1;
   if (atmsPower + sfcPower == 0.0)
     FAIL(h, "emission_weightingNEW: Neither surface nor atmosphere will emitt photons since total power is 0. Not a valid solution");
   if (fracAtmsPowerOut) *fracAtmsPowerOut = frac;
   if (totalFluxOut) *totalFluxOut = (atmsPower + sfcPower) / (areaX * areaY * (1000.0 * 1000.0));
-  return mcb_set_thermal_source(h, frac, cdf.data());
+  h->P.source = 1; h->P.fracAtmsPower = frac; h->P.voxelCDF = (const double *)h->dVoxelCDF;
+  h->haveSource = true;
+  return 0;
+}
+
+// the emission CDF currently staged (voxelWeights of type(Weights), EMI:56-57)
+int mcb_get_thermal_source(mcb_handle *h, double *fracAtmsPower, double *voxelCDF, int64_t nDoubles) {
+  if (!h) return 1;
+  if (!h->haveSource || h->P.source != 1) FAIL(h, "mcb_get_thermal_source: no thermal source is staged");
+  const long long cells = (long long)h->P.nx * h->P.ny * h->P.nz;
+  if (fracAtmsPower) *fracAtmsPower = h->P.fracAtmsPower;
+  if (voxelCDF) {
+    if (nDoubles < cells) FAIL(h, "mcb_get_thermal_source: buffer too small (%lld needed)", cells);
+    CK(h, cudaSetDevice(h->device));
+    CK(h, cudaMemcpyAsync(voxelCDF, h->dVoxelCDF, sizeof(double) * cells, cudaMemcpyDeviceToHost, h->stream));
+    if (settle(h)) return 1;
+  }
+  return 0;
 }
 
 static int ensure_tallies(mcb_handle *h) {
@@ -512,67 +544,31 @@ int mcb_get_results(mcb_handle *h, int64_t nPhotonsNormalise,
                     float *fluxUp, float *fluxDown, float *fluxAbsorbed,
                     float *volumeAbsorption, float *intensity, float *intensityByComponent) {
   if (!h) return 1;
-  if (fetch_tallies(h)) return 1;
+  CK(h, cudaSetDevice(h->device));
+  if (!h->dTally) FAIL(h, "reportResults: no results available");
   const DevDomain &P = h->P;
-  double *T = h->hTally;
-  const int numX = P.nx, numY = P.ny, numZ = P.nz, nDir = P.nDir, nc = P.nc;
-  const size_t cols = (size_t)numX * numY;
-  const double numPhotonsProcessed = nPhotonsNormalise > 0 ? (double)nPhotonsNormalise : T[P.offPhotons];
-  if (!(numPhotonsProcessed > 0)) FAIL(h, "computeRadiativeTransfer: Didn't process any photons.");
+  const int nDir = P.nDir, nc = P.nc;
+  const size_t cols = (size_t)P.nx * P.ny, cells = cols * P.nz;
   if ((intensity || intensityByComponent) && nDir == 0) FAIL(h, "reportResults: intensity information not available");
-
-  if (nDir > 0 && P.opt.limitIntensityContributions) {           // INT:294-322
-    for (int j = 0; j <= nc; ++j)
-      for (int d = 0; d < nDir; ++d) {
-        const double excess = T[P.offExcess + d + (long long)nDir * j];
-        if (excess > 0.0) {
-          double *byc = T + P.offIntByComp + cols * ((size_t)d + (size_t)nDir * j);
-          double s = 0.0;
-          for (size_t i = 0; i < cols; ++i) s += byc[i];
-          for (size_t i = 0; i < cols; ++i) {
-            const double add = (byc[i] / s) * excess;
-            T[P.offInt + i + cols * d] += add;
-            byc[i] += add;
-          }
-          T[P.offExcess + d + (long long)nDir * j] = 0.0;
-        }
-      }
+  double numPhotonsProcessed = (double)nPhotonsNormalise;
+  if (nPhotonsNormalise <= 0) {
+    CK(h, cudaMemcpyAsync(&numPhotonsProcessed, h->dTally + P.offPhotons, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    if (settle(h)) return 1;
   }
-  // numPhotonsPerColumn, default real (INT:328-343, quirk q11)
-  std::vector<float> nppc(cols);
-  if (P.xyRegular) {
-    const float v = (float)numPhotonsProcessed / (float)(numX * numY);
-    for (size_t i = 0; i < cols; ++i) nppc[i] = v;
-  } else {
-    for (int j = 0; j < numY; ++j)
-      for (int i = 0; i < numX; ++i) {
-        const float frac = (float)(((h->yE[j + 1] - h->yE[j]) * (h->xE[i + 1] - h->xE[i])) /
-                                   ((h->xE[numX] - h->xE[0]) * (h->yE[numY] - h->yE[0])));
-        nppc[i + (size_t)numX * j] = frac * (float)numPhotonsProcessed;
-      }
-  }
-  if (fluxUp) for (size_t i = 0; i < cols; ++i) fluxUp[i] = (float)T[P.offFluxUp + i] / nppc[i];            // INT:348-350
-  if (fluxDown) for (size_t i = 0; i < cols; ++i) fluxDown[i] = (float)T[P.offFluxDown + i] / nppc[i];
-  if (fluxAbsorbed) for (size_t i = 0; i < cols; ++i) fluxAbsorbed[i] = (float)T[P.offFluxAbs + i] / nppc[i];
-  if (volumeAbsorption)                                                                                    // INT:361-364
-    for (int k = 0; k < numZ; ++k) {
-      const double dz = h->zE[k + 1] - h->zE[k];
-      for (size_t i = 0; i < cols; ++i)
-        volumeAbsorption[i + cols * k] =
-            (float)((double)(float)T[P.offVolAbs + i + cols * k] / ((double)nppc[i] * dz * (double)1000.0f));
-    }
-  if (intensity)                                                                                           // INT:369-372
-    for (int d = 0; d < nDir; ++d)
-      for (size_t i = 0; i < cols; ++i) intensity[i + cols * d] = (float)T[P.offInt + i + cols * d] / nppc[i];
-  if (intensityByComponent)                                                  // INT:375-379: component 0 is NOT normalised (q12)
-    for (int j = 0; j <= nc; ++j)
-      for (int d = 0; d < nDir; ++d)
-        for (size_t i = 0; i < cols; ++i) {
-          const size_t k = i + cols * ((size_t)d + (size_t)nDir * j);
-          const float raw = (float)T[P.offIntByComp + k];
-          intensityByComponent[k] = j == 0 ? raw : raw / nppc[i];
-        }
-  return 0;
+  if (!(numPhotonsProcessed > 0)) FAIL(h, "computeRadiativeTransfer: Didn't process any photons.");
+  // INT:294-388 on the device: the f64 tallies become the reference's single-precision, normalised arrays
+  // in HBM; only the arrays asked for cross PCIe.
+  if (reserve(h, &h->dResults, sizeof(float) * (size_t)P.offExcess)) return 1;
+  float *out = (float *)h->dResults;
+  mcb_launch_normalise(P, (float)numPhotonsProcessed, out, h->numSMs, h->stream);
+  CK(h, cudaGetLastError());
+  struct { float *dst; long long off; size_t n; } parts[] = {
+      {fluxUp, P.offFluxUp, cols}, {fluxDown, P.offFluxDown, cols}, {fluxAbsorbed, P.offFluxAbs, cols},
+      {volumeAbsorption, P.offVolAbs, cells}, {intensity, P.offInt, cols * nDir},
+      {intensityByComponent, P.offIntByComp, cols * nDir * (size_t)(nc + 1)}};
+  for (auto &q : parts)
+    if (q.dst && q.n) CK(h, cudaMemcpyAsync(q.dst, out + q.off, sizeof(float) * q.n, cudaMemcpyDeviceToHost, h->stream));
+  return settle(h);
 }
 
 int mcb_run_trace(mcb_handle *h, int64_t nPhotons, const float *rn, int64_t rnStride,

@@ -1,0 +1,272 @@
+// mcb_stage.cu -- device-side staging and read-back kernels (sm_100a).
+//
+// The reference's host arrays cross PCIe once, in their own layout and precision; everything
+// derived from them is produced in HBM:
+//   * pack_extinction_kernel / pack_components_kernel: the fast kernel's packed single-precision
+//     copies (ghost-shelled f32 extinction, f32 cumulative extinction and albedo, u16 phase index)
+//     and the argument checks of addOpticalComponent (OPT:614-700) as device-side flags;
+//   * normalise_kernel: computeRadiativeTransfer's normalisation (INT:328-388) from the packed f64
+//     tally buffer straight into the single-precision arrays reportResults hands back;
+//   * redistribute_excess_kernel: INT:294-322;
+//   * emission_*_kernel: the emission CDF of emission_weightingNEW (EMI:498-522) as a three-pass
+//     prefix sum in double-double arithmetic (the reference Kahan-sums sequentially; both round the
+//     exact prefix sums to f64 to within one unit in the last place).
+// All of it is HBM-streaming work: coalesced grid-stride loops, grids sized in multiples of the SM count.
+#include "mcb_device.cuh"
+
+namespace mcbstage {
+
+enum { FLAG_EXT = 1, FLAG_SSA = 2, FLAG_IDX = 4, FLAG_TEMP = 8 };
+
+__global__ void pack_extinction_kernel(const double *__restrict__ totalExt, float *__restrict__ e32,
+                                       int nx, int ny, int nz, int G, int *flags) {
+  const int nxp = nx + 2 * G, nyp = ny + 2 * G, nzp = nz + 2 * G;
+  const long long total = (long long)nxp * nyp * nzp;
+  int bad = 0;
+  for (long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x; p < total; p += (long long)gridDim.x * blockDim.x) {
+    const int i = (int)(p % nxp);
+    const long long q = p / nxp;
+    const int j = (int)(q % nyp), k = (int)(q / nyp);
+    float v = 0.0f;                                              // empty layers above the top and below the surface
+    if (k >= G && k < nz + G) {
+      int mx = (i - G) % nx; mx += mx < 0 ? nx : 0;                // periodic replicas in x and y (OPT:1782-1796)
+      int my = (j - G) % ny; my += my < 0 ? ny : 0;
+      const double e = totalExt[mx + (long long)nx * (my + (long long)ny * (k - G))];
+      if (!(e >= 0.0)) bad = FLAG_EXT;
+      v = (float)e;
+    }
+    e32[p] = v;
+  }
+  if (bad) atomicOr(flags, bad);
+}
+
+__global__ void pack_components_kernel(const double *__restrict__ cumExt, const double *__restrict__ ssa,
+                                       const int32_t *__restrict__ phaseIdx, float *__restrict__ c32,
+                                       float *__restrict__ s32, uint16_t *__restrict__ i16, long long n, int *flags) {
+  int bad = 0;
+  for (long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x; p < n; p += (long long)gridDim.x * blockDim.x) {
+    const double s = ssa[p];
+    const int32_t ix = phaseIdx[p];
+    if (!(s >= 0.0 && s <= 1.0)) bad |= FLAG_SSA;
+    if (ix < 0 || ix > 65535) bad |= FLAG_IDX;
+    c32[p] = (float)cumExt[p]; s32[p] = (float)s; i16[p] = (uint16_t)ix;
+  }
+  if (bad) atomicOr(flags, bad);
+}
+
+// INT:294-322: one block per (direction, component) slot with a positive excess
+__global__ void redistribute_excess_kernel(DevDomain P) {
+  const int slot = blockIdx.x;                           // d + nDir * j
+  const int d = slot % P.nDir;
+  const long long cols = (long long)P.nx * P.ny;
+  double *excessP = P.tally + P.offExcess + slot;
+  const double excess = *excessP;
+  if (!(excess > 0.0)) return;
+  double *byc = P.tally + P.offIntByComp + cols * slot;
+  __shared__ double part[256];
+  double s = 0.0;
+  for (long long i = threadIdx.x; i < cols; i += blockDim.x) s += byc[i];
+  part[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = blockDim.x / 2; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) part[threadIdx.x] += part[threadIdx.x + o];
+    __syncthreads();
+  }
+  const double total = part[0];
+  for (long long i = threadIdx.x; i < cols; i += blockDim.x) {
+    const double add = (byc[i] / total) * excess;
+    atomicAdd(&P.tally[P.offInt + i + cols * d], add);   // several components feed one direction
+    byc[i] += add;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) *excessP = 0.0;
+}
+
+// INT:328-388.  out mirrors the tally buffer up to offExcess, as single precision.
+__global__ void normalise_kernel(DevDomain P, float numPhotons, float *__restrict__ out) {
+  const long long cols = (long long)P.nx * P.ny;
+  const long long total = P.offExcess;
+  const double areaAll = (P.xMax - P.x0) * (P.yMax - P.y0);
+  for (long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x; p < total; p += (long long)gridDim.x * blockDim.x) {
+    const long long col = p % cols;
+    float nppc;                                                     // numPhotonsPerColumn, default real (quirk q11)
+    if (P.xyRegular) {
+      nppc = __fdiv_rn(numPhotons, (float)(P.nx * P.ny));
+    } else {                                                        // INT:334-342
+      const int i = (int)(col % P.nx), j = (int)(col / P.nx);
+      const float frac = (float)(((P.yE[j + 1] - P.yE[j]) * (P.xE[i + 1] - P.xE[i])) / areaAll);
+      nppc = __fmul_rn(frac, numPhotons);
+    }
+    const float raw = (float)P.tally[p];
+    float v;
+    if (p >= P.offVolAbs && p < P.offInt) {                         // INT:361-364
+      const int k = (int)((p - P.offVolAbs) / cols);
+      const double dz = P.zE[k + 1] - P.zE[k];
+      v = (float)((double)raw / ((double)nppc * dz * 1000.0));
+    } else if (p >= P.offIntByComp && (p - P.offIntByComp) < cols * P.nDir) {
+      v = raw;                                                      // component 0 is NOT normalised (quirk q12)
+    } else {
+      v = __fdiv_rn(raw, nppc);                                     // INT:348-350, 369-379
+    }
+    out[p] = v;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// emission CDF (EMI:498-522)
+// ---------------------------------------------------------------------------------------------
+struct dd { double hi, lo; };
+__device__ __forceinline__ dd dd_add(dd a, dd b) {              // Knuth two-sum, then renormalise
+  const double s = __dadd_rn(a.hi, b.hi);
+  const double bb = __dadd_rn(s, -a.hi);
+  const double e = __dadd_rn(__dadd_rn(a.hi, -__dadd_rn(s, -bb)), __dadd_rn(b.hi, -bb));
+  const double lo = __dadd_rn(e, __dadd_rn(a.lo, b.lo));
+  dd r; r.hi = __dadd_rn(s, lo); r.lo = __dadd_rn(lo, -__dadd_rn(r.hi, -s)); return r;
+}
+
+#define EMI_TILE 2048            // cells per block
+#define EMI_THREADS 256
+#define EMI_PER (EMI_TILE / EMI_THREADS)
+
+__device__ __forceinline__ double emission_term(const DevDomain &P, const double *__restrict__ temps, long long cell,
+                                                long long cells, double a, double b, double lambda5, int *flags) {
+  const double T = temps[cell];
+  if (!(T > 0.0)) { atomicOr(flags, FLAG_TEMP); return 0.0; }
+  const long long cols = (long long)P.nx * P.ny;
+  const int iz = (int)(cell / cols);
+  const double dz = P.zE[iz + 1] - P.zE[iz];
+  const double planck = (a / (lambda5 * (exp(b / T) - 1.0))) / 1.0e6;                     // EMI:503
+  const double ext = P.totalExt[cell];
+  double sumSsaExt = 0.0, prev = 0.0;
+  for (int j = 0; j < P.nc; ++j) {                                                         // EMI:504
+    const double cj = P.cumExt[cell + cells * j];
+    sumSsaExt += P.ssa[cell + cells * j] * (ext * (cj - prev));
+    prev = cj;
+  }
+  return 4.0 * 3.14159265358979323846 * planck * (ext - sumSsaExt) * dz;                  // EMI:505
+}
+
+// pass 1: per-tile totals (double-double)
+__global__ void emission_tile_sums_kernel(DevDomain P, const double *__restrict__ temps, long long cells,
+                                          double a, double b, double lambda5, dd *tileSums, int *flags) {
+  __shared__ dd part[EMI_THREADS];
+  const long long base = (long long)blockIdx.x * EMI_TILE;
+  dd s; s.hi = 0.0; s.lo = 0.0;
+  for (int k = 0; k < EMI_PER; ++k) {
+    const long long cell = base + (long long)threadIdx.x * EMI_PER + k;
+    if (cell < cells) { dd t; t.hi = emission_term(P, temps, cell, cells, a, b, lambda5, flags); t.lo = 0.0; s = dd_add(s, t); }
+  }
+  part[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = EMI_THREADS / 2; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) part[threadIdx.x] = dd_add(part[threadIdx.x], part[threadIdx.x + o]);
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) tileSums[blockIdx.x] = part[0];
+}
+
+// pass 2: exclusive scan of the tile totals (one block, sequential over chunks of blockDim tiles)
+__global__ void emission_scan_tiles_kernel(dd *tileSums, int nTiles, dd *total) {
+  __shared__ dd buf[1024];
+  dd carry; carry.hi = 0.0; carry.lo = 0.0;
+  for (int base = 0; base < nTiles; base += blockDim.x) {
+    const int i = base + threadIdx.x;
+    dd v; v.hi = 0.0; v.lo = 0.0;
+    if (i < nTiles) v = tileSums[i];
+    buf[threadIdx.x] = v;
+    __syncthreads();
+    for (int o = 1; o < (int)blockDim.x; o <<= 1) {                                       // Hillis-Steele inclusive scan
+      dd t; t.hi = 0.0; t.lo = 0.0;
+      if ((int)threadIdx.x >= o) t = buf[threadIdx.x - o];
+      __syncthreads();
+      if ((int)threadIdx.x >= o) buf[threadIdx.x] = dd_add(buf[threadIdx.x], t);
+      __syncthreads();
+    }
+    dd incl = dd_add(carry, buf[threadIdx.x]);
+    dd excl = threadIdx.x == 0 ? carry : dd_add(carry, buf[threadIdx.x - 1]);
+    if (i < nTiles) tileSums[i] = excl;
+    __syncthreads();
+    carry = dd_add(carry, buf[blockDim.x - 1]);
+    (void)incl;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *total = carry;
+}
+
+// pass 3: inclusive prefix sums inside each tile, rounded to f64 (un-normalised CDF)
+__global__ void emission_prefix_kernel(DevDomain P, const double *__restrict__ temps, long long cells,
+                                       double a, double b, double lambda5, const dd *tileSums, double *cdf, int *flags) {
+  __shared__ dd part[EMI_THREADS];
+  const long long base = (long long)blockIdx.x * EMI_TILE;
+  dd loc[EMI_PER];
+  dd s; s.hi = 0.0; s.lo = 0.0;
+  for (int k = 0; k < EMI_PER; ++k) {
+    const long long cell = base + (long long)threadIdx.x * EMI_PER + k;
+    if (cell < cells) { dd t; t.hi = emission_term(P, temps, cell, cells, a, b, lambda5, flags); t.lo = 0.0; s = dd_add(s, t); }
+    loc[k] = s;
+  }
+  part[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = 1; o < EMI_THREADS; o <<= 1) {
+    dd t; t.hi = 0.0; t.lo = 0.0;
+    if ((int)threadIdx.x >= o) t = part[threadIdx.x - o];
+    __syncthreads();
+    if ((int)threadIdx.x >= o) part[threadIdx.x] = dd_add(part[threadIdx.x], t);
+    __syncthreads();
+  }
+  dd offset = tileSums[blockIdx.x];
+  if (threadIdx.x > 0) offset = dd_add(offset, part[threadIdx.x - 1]);
+  for (int k = 0; k < EMI_PER; ++k) {
+    const long long cell = base + (long long)threadIdx.x * EMI_PER + k;
+    if (cell < cells) { const dd v = dd_add(offset, loc[k]); cdf[cell] = v.hi; }
+  }
+}
+
+// EMI:515-521: normalise, force the last entry to 1
+__global__ void emission_normalise_kernel(double *cdf, long long cells, const dd *total) {
+  const double last = total->hi;
+  for (long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x; p < cells; p += (long long)gridDim.x * blockDim.x)
+    cdf[p] = p == cells - 1 ? 1.0 : cdf[p] / last;
+}
+
+}  // namespace mcbstage
+
+static int stream_grid(long long n, int threads, int numSMs) {
+  const long long want = (n + threads - 1) / threads;
+  const long long cap = (long long)numSMs * 8;                     // whole waves of resident CTAs
+  return (int)(want < cap ? (want < 1 ? 1 : want) : cap);
+}
+
+void mcb_launch_pack_optics(const DevDomain &P, float *e32, float *c32, float *s32, uint16_t *i16, int *flags,
+                            int numSMs, cudaStream_t stream) {
+  const long long padded = (long long)P.nxp * P.nyp * (P.nz + 2 * MCB_GHOST);
+  const long long n = (long long)P.nx * P.ny * P.nz * P.nc;
+  mcbstage::pack_extinction_kernel<<<stream_grid(padded, 256, numSMs), 256, 0, stream>>>(P.totalExt, e32, P.nx, P.ny, P.nz,
+                                                                                         MCB_GHOST, flags);
+  mcbstage::pack_components_kernel<<<stream_grid(n, 256, numSMs), 256, 0, stream>>>(P.cumExt, P.ssa, P.phaseIdx, c32, s32,
+                                                                                    i16, n, flags);
+}
+
+void mcb_launch_normalise(const DevDomain &P, float numPhotons, float *out, int numSMs, cudaStream_t stream) {
+  if (P.nDir > 0 && P.opt.limitIntensityContributions)
+    mcbstage::redistribute_excess_kernel<<<P.nDir * (P.nc + 1), 256, 0, stream>>>(P);
+  mcbstage::normalise_kernel<<<stream_grid(P.offExcess, 256, numSMs), 256, 0, stream>>>(P, numPhotons, out);
+}
+
+// returns the number of tiles; scratch must hold (tiles + 1) double-double values
+long long mcb_emission_tiles(long long cells) { return (cells + EMI_TILE - 1) / EMI_TILE; }
+
+void mcb_launch_emission_cdf(const DevDomain &P, const double *temps, double a, double b, double lambda5, void *scratch,
+                             double *cdf, int *flags, int numSMs, cudaStream_t stream) {
+  const long long cells = (long long)P.nx * P.ny * P.nz;
+  const int tiles = (int)mcb_emission_tiles(cells);
+  mcbstage::dd *tileSums = (mcbstage::dd *)scratch, *total = tileSums + tiles;
+  mcbstage::emission_tile_sums_kernel<<<tiles, EMI_THREADS, 0, stream>>>(P, temps, cells, a, b, lambda5, tileSums, flags);
+  mcbstage::emission_scan_tiles_kernel<<<1, 1024, 0, stream>>>(tileSums, tiles, total);
+  mcbstage::emission_prefix_kernel<<<tiles, EMI_THREADS, 0, stream>>>(P, temps, cells, a, b, lambda5, tileSums, cdf, flags);
+}
+
+void mcb_launch_emission_normalise(double *cdf, long long cells, const void *total, int numSMs, cudaStream_t stream) {
+  mcbstage::emission_normalise_kernel<<<stream_grid(cells, 256, numSMs), 256, 0, stream>>>(cdf, cells,
+                                                                                           (const mcbstage::dd *)total);
+}

@@ -17,6 +17,7 @@ class Weights:
     voxelWeights: Optional[np.ndarray] = None      # (nz, ny, nx) CDF in x-fastest order
     fracAtmsPower: float = 0.0
     spectrIntgrFlux: float = 0.0                   # W m^-2 (monochromatic, EMI:536-538)
+    deviceOwner: Optional[object] = None           # the integrator whose HBM holds the CDF (device-built weights)
 
     @property
     def levelWeights(self):                        # voxelWeights(nx, ny, :)
@@ -34,13 +35,56 @@ def new_Weights(numX=None, numY=None, numZ=None, numLambda=1) -> Weights:
     return Weights(voxelWeights=np.zeros((numZ, numY, numX), dtype=np.float64))
 
 
-def emission_weighting(thisDomain, theseWeights: Weights, sfcTemp: float) -> float:
+def emission_weighting_device(thisDomain, theseWeights: Weights, sfcTemp: float, thisIntegrator) -> float:
+    """``emission_weightingNEW`` (EMI:424-550) on the GPU: the domain's optics are already in the
+    integrator's HBM, the temperatures are uploaded, Planck emission and the prefix sum over cells run
+    in ``csrc/mcb_stage.cu``; the CDF never visits the host (``fetchVoxelWeights`` reads it back on
+    request).  Returns totalFlux."""
+    import ctypes as C
+
+    from . import _lib
+    from .monteCarloRadiativeTransfer import _stage_domain
+    g = thisIntegrator
+    if thisDomain.totalExt is None:
+        raise ValueError("emission_weighting: domain hasn't been initialized.")
+    _stage_domain(g, thisDomain)
+    temps = np.ascontiguousarray(thisDomain.temps, dtype=np.float64)
+    frac = C.c_double(0.0); flux = C.c_double(0.0)
+    g._check(g._lib.mcb_build_thermal_source(g.handle, _lib.ptr(temps, C.c_double), float(thisDomain.lambda_um),
+                                             float(sfcTemp), C.byref(frac), C.byref(flux)), "emission_weighting")
+    theseWeights.voxelWeights = None
+    theseWeights.fracAtmsPower = float(frac.value)
+    theseWeights.spectrIntgrFlux = float(flux.value)
+    theseWeights.deviceOwner = g
+    g._stagedSource = ("bbemission-device", id(theseWeights))
+    return theseWeights.spectrIntgrFlux
+
+
+def fetchVoxelWeights(theseWeights: Weights) -> np.ndarray:
+    """The CDF of device-built weights, copied back as ``(nz, ny, nx)``."""
+    import ctypes as C
+
+    from . import _lib
+    g = theseWeights.deviceOwner
+    if g is None:
+        return theseWeights.voxelWeights
+    out = np.empty((g.numZ, g.numY, g.numX), dtype=np.float64)
+    g._check(g._lib.mcb_get_thermal_source(g.handle, None, _lib.ptr(out, C.c_double), out.size), "fetchVoxelWeights")
+    return out
+
+
+def emission_weighting(thisDomain, theseWeights: Weights, sfcTemp: float, thisIntegrator=None) -> float:
     """``emission_weightingNEW`` (EMI:424-550) for the domain's wavelength; returns totalFlux.
+
+    With ``thisIntegrator`` the build runs on that integrator's GPU (``emission_weighting_device``);
+    without it this is the NumPy staging producer.
 
     The running sum is compensated (Kahan) in the reference (EMI:505-509); here the same
     per-voxel terms are accumulated with ``math.fsum``-grade accuracy via a long-double
     cumulative sum, which agrees with the compensated sum to the last bit or two.
     """
+    if thisIntegrator is not None:
+        return emission_weighting_device(thisDomain, theseWeights, sfcTemp, thisIntegrator)
     h = 6.62606957e-34; c = 2.99792458e+8; k = 1.3806488e-23
     a = 2.0 * h * c ** 2.0
     Pi = 4.0 * np.arctan(1.0)
@@ -81,5 +125,6 @@ def emission_weighting(thisDomain, theseWeights: Weights, sfcTemp: float) -> flo
         raise ValueError("emission_weightingNEW: Neither surface nor atmosphere will emitt photons "
                          "since total power is 0. Not a valid solution")
     theseWeights.voxelWeights = np.ascontiguousarray(cdf)
+    theseWeights.deviceOwner = None
     theseWeights.spectrIntgrFlux = (atmsPower + sfcPower) / (areaX * areaY * (1000.0 ** 2.0))
     return theseWeights.spectrIntgrFlux

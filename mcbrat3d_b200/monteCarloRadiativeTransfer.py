@@ -208,6 +208,11 @@ def _stage_source(g: integrator, photons: photonStream) -> None:
             g._check(g._lib.mcb_set_solar_source(g._h, photons.solarMu, photons.solarAzimuth), "new_PhotonStream")
     else:
         w = photons.weights
+        if w.deviceOwner is not None:                      # built in this integrator's HBM (emission_weighting_device)
+            key = ("bbemission-device", id(w))
+            if w.deviceOwner is not g or g._stagedSource != key:
+                raise McbError("new_PhotonStream: device-built weights belong to another integrator or were replaced")
+            return
         key = ("bbemission", id(w.voxelWeights), w.fracAtmsPower)
         if g._stagedSource != key:
             g._check(g._lib.mcb_set_thermal_source(g._h, float(w.fracAtmsPower), _lib.ptr(w.voxelWeights, C.c_double)),

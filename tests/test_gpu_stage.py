@@ -1,0 +1,164 @@
+"""Device-side staging and read-back (csrc/mcb_stage.cu) against the oracle / a NumPy restatement:
+argument checks of addOpticalComponent, the normalisation of INT:328-388 (bit-exact, single
+precision), the excess redistribution of INT:294-322, and the emission CDF of EMI:498-522."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from mcbrat3d_b200 import _lib, domains
+from mcbrat3d_b200.emissionAndBroadBandWeights import Weights, emission_weighting, fetchVoxelWeights
+from mcbrat3d_b200.monteCarloIllumination import new_PhotonStream
+from mcbrat3d_b200.monteCarloRadiativeTransfer import (computeRadiativeTransfer, finalize_Integrator, new_Integrator,
+                                                       reportResults, specifyParameters)
+from mcbrat3d_b200.RandomNumbersForMC import new_RandomNumberSequence
+
+pytestmark = pytest.mark.gpu
+f32 = np.float32
+
+
+def _raw(g):
+    dptr = C.c_void_p(); nd = C.c_int64(0)
+    g._check(g._lib.mcb_tally_buffer(g.handle, C.byref(dptr), C.byref(nd)), "tally")
+    raw = np.empty(nd.value, dtype=np.float64)
+    g._check(g._lib.mcb_get_raw_tallies(g.handle, _lib.ptr(raw, C.c_double), nd.value), "raw")
+    return raw
+
+
+def _set_optics(g, d, **over):
+    a = dict(totalExt=d.totalExt, cumulativeExt=d.cumulativeExt, ssa=d.ssa, phaseFunctionIndex=d.phaseFunctionIndex)
+    a.update(over)
+    return g._lib.mcb_set_optics(g.handle, d.cumulativeExt.shape[0], _lib.ptr(a["totalExt"], C.c_double),
+                                 _lib.ptr(a["cumulativeExt"], C.c_double), _lib.ptr(a["ssa"], C.c_double),
+                                 _lib.ptr(a["phaseFunctionIndex"], C.c_int32), 0.0)
+
+
+def test_optics_argument_checks_run_on_device():
+    d, _ = domains.step_cloud()
+    d.getOpticalPropertiesByComponent()
+    g = new_Integrator(d)
+    buf = C.create_string_buffer(256)
+    try:
+        bad = d.totalExt.copy(); bad.ravel()[17] = -1.0
+        assert _set_optics(g, d, totalExt=bad) != 0
+        g._lib.mcb_last_error(g.handle, buf, 256); assert b"extinction must be >= 0" in buf.value
+        bad = d.ssa.copy(); bad.ravel()[5] = 1.5
+        assert _set_optics(g, d, ssa=bad) != 0
+        g._lib.mcb_last_error(g.handle, buf, 256); assert b"singleScatteringAlbedo must be between 0 and 1" in buf.value
+        bad = d.ssa.copy(); bad.ravel()[5] = np.nan
+        assert _set_optics(g, d, ssa=bad) != 0
+        bad = d.phaseFunctionIndex.copy(); bad.ravel()[3] = -2
+        assert _set_optics(g, d, phaseFunctionIndex=bad) != 0
+        g._lib.mcb_last_error(g.handle, buf, 256); assert b"phase function index is out of bounds" in buf.value
+        # a failed staging leaves the problem unspecified, a good one repairs it
+        done = C.c_int64(0)
+        assert g._lib.mcb_set_solar_source(g.handle, 0.5, 0.0) == 0
+        assert g._lib.mcb_run_batch(g.handle, 10, 1, 0, C.byref(done)) != 0
+        assert _set_optics(g, d) == 0
+    finally:
+        finalize_Integrator(g)
+
+
+@pytest.mark.parametrize("which", ["regular", "irregular"])
+def test_normalisation_bit_exact(which):
+    """reportResults' arrays == the reference's normalisation (INT:328-388) applied in NumPy to the raw
+    f64 tallies, bit for bit (quirks q11, q12 included)."""
+    if which == "regular":
+        d, case = domains.step_cloud(ssa=0.9, solarMu=0.5)
+    else:
+        d, case = domains.irregular_test_domain()
+    g = new_Integrator(d)
+    try:
+        specifyParameters(g, intensityMus=[1.0, 0.5], intensityPhis=[0.0, 180.0], computeIntensity=True)
+        rs = new_RandomNumberSequence(3)
+        n = 30011
+        ps = new_PhotonStream(case["solarMu"], case["solarAzimuth"], n, rs)
+        assert computeRadiativeTransfer(g, d, rs, ps, n) == n
+        r = reportResults(g, fluxUp=True, fluxDown=True, fluxAbsorbed=True, volumeAbsorption=True, intensity=True,
+                          intensityByComponent=True)
+        raw = _raw(g)
+        nx, ny, nz, nc, nDir = g.numX, g.numY, g.numZ, g.numComps, 2
+        cols = nx * ny
+        N = f32(n)
+        if which == "regular":
+            nppc = np.full((ny, nx), N / f32(nx * ny), dtype=f32)
+        else:
+            dx = np.diff(d.xPosition); dy = np.diff(d.yPosition)
+            area = (d.xPosition[-1] - d.xPosition[0]) * (d.yPosition[-1] - d.yPosition[0])
+            nppc = ((dy[:, None] * dx[None, :]) / area).astype(f32) * N
+        o = 0
+        for name in ("fluxUp", "fluxDown", "fluxAbsorbed"):
+            want = raw[o:o + cols].astype(f32).reshape(ny, nx) / nppc
+            assert np.array_equal(r[name], want), name
+            o += cols
+        vol = raw[o:o + cols * nz].astype(f32).reshape(nz, ny, nx); o += cols * nz
+        dz = np.diff(d.zPosition)[:, None, None]
+        want = (vol.astype(np.float64) / (nppc.astype(np.float64)[None] * dz * 1000.0)).astype(f32)
+        assert np.array_equal(r["volumeAbsorption"], want)
+        inten = raw[o:o + cols * nDir].astype(f32).reshape(nDir, ny, nx); o += cols * nDir
+        assert np.array_equal(r["intensity"], inten / nppc[None])
+        byc = raw[o:o + cols * nDir * (nc + 1)].astype(f32).reshape(nc + 1, nDir, ny, nx)
+        want = byc.copy(); want[1:] = byc[1:] / nppc[None, None]
+        assert np.array_equal(r["intensityByComponent"], want)
+        assert r["intensity"].sum() > 0
+    finally:
+        finalize_Integrator(g)
+
+
+def test_excess_redistribution_conserves_radiance():
+    """limitIntensityContributions (INT:1815-1826, 294-322): capped contributions are handed back in
+    proportion to each component's map, so the domain-mean radiance does not change."""
+    d, case = domains.step_cloud(ssa=1.0, solarMu=0.5)
+    out = []
+    for limit in (False, True):
+        g = new_Integrator(d)
+        try:
+            specifyParameters(g, intensityMus=[1.0, 0.5], intensityPhis=[0.0, 0.0], computeIntensity=True,
+                              limitIntensityContributions=limit, maxIntensityContribution=0.05)
+            rs = new_RandomNumberSequence(7)
+            n = 100000
+            ps = new_PhotonStream(case["solarMu"], case["solarAzimuth"], n, rs)
+            computeRadiativeTransfer(g, d, rs, ps, n)
+            r1 = reportResults(g, meanIntensity=True, intensityByComponent=True, intensity=True)
+            r2 = reportResults(g, meanIntensity=True)                 # idempotent: the excess was zeroed
+            assert np.array_equal(r1["meanIntensity"], r2["meanIntensity"])
+            assert np.allclose(r1["intensity"], r1["intensityByComponent"].sum(axis=0), rtol=2e-5)
+            out.append(r1["meanIntensity"].astype(np.float64))
+        finally:
+            finalize_Integrator(g)
+    assert np.allclose(out[0], out[1], rtol=1e-5), out
+
+
+@pytest.mark.parametrize("name", ["C4", "T_irr"])
+def test_emission_cdf_built_on_device_matches_oracle(orc, name):
+    d, case = domains.homogeneous_lw() if name == "C4" else domains.irregular_test_domain()
+    d.getOpticalPropertiesByComponent()
+    sfcTemp = case.get("surfaceTemp", 300.0)
+    frac, cdf, flux = orc.OracleDomain(d, tableSize=9001).emission_weighting(d.temps, d.lambda_um, sfcTemp)
+    g = new_Integrator(d)
+    try:
+        w = Weights()
+        got_flux = emission_weighting(d, w, sfcTemp, thisIntegrator=g)
+        got = fetchVoxelWeights(w)
+        assert got.shape == cdf.shape
+        assert got.ravel()[-1] == 1.0
+        assert np.all(np.diff(got.ravel()) >= 0.0)
+        assert np.allclose(got, cdf, rtol=1e-12, atol=0.0)
+        assert abs(w.fracAtmsPower - frac) <= 1e-12 * abs(frac)
+        assert abs(got_flux - flux) <= 1e-12 * abs(flux)
+        # and it drives the thermal source: one batch, isothermal-ish closure is covered by test_gpu_stats
+        specifyParameters(g, LW_flag=1.0)
+        rs = new_RandomNumberSequence(11)
+        ps = new_PhotonStream(theseWeights=w, numberOfPhotons=20000, randomNumbers=rs)
+        assert computeRadiativeTransfer(g, d, rs, ps, 20000) == 20000
+        # a cold cell switches the atmosphere off (EMI:498) -> only the surface emits
+        cold = d.temps.copy(); cold.ravel()[3] = 0.0
+        d2 = d; keep = d.temps; d2.temps = cold
+        try:
+            w2 = Weights()
+            emission_weighting(d2, w2, sfcTemp, thisIntegrator=g)
+            assert w2.fracAtmsPower == 0.0 and not fetchVoxelWeights(w2).any()
+        finally:
+            d2.temps = keep
+    finally:
+        finalize_Integrator(g)
