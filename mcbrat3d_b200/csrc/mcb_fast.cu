@@ -115,10 +115,17 @@ __device__ __forceinline__ int find_cell(const float *e, int n, float x) {
   return lo;
 }
 
-// fold a cell index that ran into the periodic ghost shell back into [0, n)
+// fold a cell index that ran into the periodic ghost shell (|excursion| <= MCB_GHOST) back into [0, n).
+// n is launch-invariant: grids at least as wide as the shell need one conditional add each way; only
+// narrower ones (the 1-column step cloud) can be several periods off.
 __device__ __forceinline__ int wrap_index(int i, int n) {
-  if (i < 0) { do i += n; while (i < 0); }
-  else if (i >= n) { do i -= n; while (i >= n); }
+  if (n >= GH) {
+    i += i < 0 ? n : 0;
+    i -= i >= n ? n : 0;
+  } else {
+    while (i < 0) i += n;
+    while (i >= n) i -= n;
+  }
   return i;
 }
 
@@ -176,21 +183,24 @@ __device__ __forceinline__ int march_burst(Ray &r, const DevDomain &P, const Gri
   }
 #pragma unroll
   for (int k = 0; k < B; ++k) sg[k] = __ldg(extp + ck[k]);
-  float acc = ext, tS = t0;
+  // accumulate until the target is passed (OPT:1729-1738); from there on acc / tS stay frozen at the
+  // ENTRY of the hit cell, so only its extinction and index have to be carried along
+  float acc = ext, tS = t0, hS = 1.0f;
+  int hC = 0;
+  unsigned nIn = 0u;                                   // cells entered up to and including the hit cell
   bool found = false;
-  float hT = 0.0f, hE = 0.0f, hS = 1.0f;
-  int hC = 0, hK = 0;
 #pragma unroll
   for (int k = 0; k < B; ++k) {
     const float en = fmaf(tE[k] - tS, sg[k], acc);
     const bool h = !found && en > target;
-    hT = h ? tE[k] : hT; hE = h ? en : hE; hS = h ? sg[k] : hS; hC = h ? ck[k] : hC; hK = h ? k : hK;
+    hS = h ? sg[k] : hS; hC = h ? ck[k] : hC;
     found = found || h;
-    acc = en; tS = tE[k];
+    nIn += found && !h ? 0u : 1u;
+    acc = found ? acc : en; tS = found ? tS : tE[k];
   }
   if (found) {
-    crossings += (unsigned)(hK + 1);
-    r.t = hT - __fdividef(hE - target, hS);          // where the target optical depth is met (OPT:1731)
+    crossings += nIn;
+    r.t = tS + __fdividef(target - acc, hS);           // where the target optical depth is met (OPT:1731)
     cell_decode(P, hC, r.ix, r.iy, r.iz);
     return MARCH_HIT;
   }
@@ -684,14 +694,14 @@ void mcb_launch_fast_batch(const DevDomain &P, long long nPhotons, uint64_t seed
                            int numSMs, unsigned long long *workCounter, cudaStream_t stream) {
   if (nPhotons <= 0) return;
   static int occ = -1, burst = -1;   // register budget / burst length variants (tuning knobs; defaults chosen from measurements)
-  if (occ < 0) { const char *e = getenv("MCB_BLOCKS_PER_SM"); occ = e ? atoi(e) : 6; }
+  if (occ < 0) { const char *e = getenv("MCB_BLOCKS_PER_SM"); occ = e ? atoi(e) : 8; }
   if (burst < 0) { const char *e = getenv("MCB_BURST"); burst = e ? atoi(e) : 8; }
 #define MCB_GO(REG, OCC, BURST) do { \
     if (P.nDir > 0) launch<REG, OCC, BURST, true>(P, nPhotons, seed, firstPhotonId, numSMs, workCounter, stream); \
     else launch<REG, OCC, BURST, false>(P, nPhotons, seed, firstPhotonId, numSMs, workCounter, stream); } while (0)
   if (P.xyRegular && P.zRegular) {            // burst length <= MCB_GHOST (the ghost shell is that deep)
-    if (burst >= 8) { if (occ >= 6) MCB_GO(true, 6, 8); else if (occ <= 4) MCB_GO(true, 4, 8); else MCB_GO(true, 5, 8); }
-    else { if (occ >= 6) MCB_GO(true, 6, 4); else if (occ <= 4) MCB_GO(true, 4, 4); else MCB_GO(true, 5, 4); }
+    if (burst >= 8) { if (occ >= 8) MCB_GO(true, 8, 8); else if (occ >= 6) MCB_GO(true, 6, 8); else if (occ <= 4) MCB_GO(true, 4, 8); else MCB_GO(true, 5, 8); }
+    else { if (occ >= 8) MCB_GO(true, 8, 4); else if (occ >= 6) MCB_GO(true, 6, 4); else if (occ <= 4) MCB_GO(true, 4, 4); else MCB_GO(true, 5, 4); }
   } else {
     if (burst >= 8) MCB_GO(false, 4, 8); else MCB_GO(false, 4, 4);
   }
