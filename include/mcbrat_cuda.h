@@ -36,7 +36,7 @@ enum { MCB_ARITH_FAST = 0, MCB_ARITH_REFERENCE = 1 };
 /* Algorithmic choices: the optional arguments of specifyParameters (INT:1046-1073) that
  * the photon loop reads.  Defaults (mcb_default_options) are the integrator's (INT:53-96). */
 typedef struct {
-  int32_t useRayTracing;                    /* INT:53; only 1 (ray tracing) is implemented     */
+  int32_t useRayTracing;                    /* INT:53; 0 = maximum cross-section (INT:564-571) */
   int32_t useRussianRoulette;               /* INT:55                                          */
   float   russianRouletteW;                 /* INT:56                                          */
   int32_t useRussianRouletteForIntensity;   /* INT:90                                          */
@@ -60,7 +60,7 @@ typedef struct {
 enum {
   MCB_EV_BIRTH = 1, MCB_EV_SCATTER = 2, MCB_EV_SURFACE = 3, MCB_EV_EXIT_TOP = 4,
   MCB_EV_KILLED_SURFACE = 5, MCB_EV_KILLED_ROULETTE = 6, MCB_EV_BAD = 7,
-  MCB_EV_LOCAL_ESTIMATE = 8, MCB_EV_RN_EXHAUSTED = 9
+  MCB_EV_LOCAL_ESTIMATE = 8, MCB_EV_RN_EXHAUSTED = 9, MCB_EV_NULL_COLLISION = 10
 };
 typedef struct {
   int32_t photon, kind, ix, iy, iz, component, phaseIndex, angleIndex, order, nrn;

@@ -260,9 +260,14 @@ int mcb_set_optics(mcb_handle *h, int nc, const double *totalExt, const double *
   mcb_launch_pack_optics(P, (float *)h->dExt32, (float *)h->dCum32, (float *)h->dSsa32, (uint16_t *)h->dIdx16, h->dFlags,
                          h->numSMs, h->stream);
   CK(h, cudaGetLastError());
-  int flags = 0;
-  CK(h, cudaMemcpyAsync(&flags, h->dFlags, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  int flags4[4] = {0, 0, 0, 0};
+  CK(h, cudaMemcpyAsync(flags4, h->dFlags, sizeof(flags4), cudaMemcpyDeviceToHost, h->stream));
   if (settle(h)) return 1;
+  const int flags = flags4[0];
+  {
+    double emax; memcpy(&emax, &flags4[2], sizeof(double));
+    P.maxExtinction = (float)emax;                                       // INT:448, default real
+  }
   if (flags & 1) FAIL(h, "addOpticalComponent: extinction must be >= 0.");
   if (flags & 2) FAIL(h, "addOpticalComponent: singleScatteringAlbedo must be between 0 and 1");
   if (flags & 4) FAIL(h, "addOpticalComponent: phase function index is out of bounds");
@@ -307,7 +312,6 @@ int mcb_set_views(mcb_handle *h, int nDir, const float *dirCos) {
 
 int mcb_set_options(mcb_handle *h, const mcb_options *o) {
   if (!h || !o) return 1;
-  if (!o->useRayTracing) FAIL(h, "specifyParameters: useRayTracing=.false. (maximum cross-section) is not implemented");
   if (o->zetaMin < 0.0f) FAIL(h, "specifyParameters: zetaMin must be >= 0.");
   if (o->arithmetic != MCB_ARITH_FAST && o->arithmetic != MCB_ARITH_REFERENCE) FAIL(h, "mcb_set_options: unknown arithmetic mode");
   h->P.opt = *o;
@@ -461,7 +465,11 @@ static int run(mcb_handle *h, long long nPhotons, uint64_t seed, uint64_t firstP
   }
   if (nPhotons == 0) FAIL(h, "computeRadiativeTransfer: Didn't process any photons.");   // INT:835-836
   CK(h, cudaEventRecord(h->evStart, h->stream));
-  if (P.opt.arithmetic == MCB_ARITH_REFERENCE)
+  if (!P.opt.useRayTracing && !(P.maxExtinction > 0.0f))
+    FAIL(h, "computeRadiativeTransfer: maximum cross-section needs a domain with extinction > 0");
+  // the maximum cross-section branch (INT:564-571) exists in reference arithmetic only: as shipped it never
+  // refreshes the photon's cell indices after a move, which is reproduced verbatim and is not a throughput path
+  if (P.opt.arithmetic == MCB_ARITH_REFERENCE || !P.opt.useRayTracing)
     mcb_launch_reference_batch(P, nPhotons, seed, firstPhotonId, h->numSMs, h->stream);
   else
     mcb_launch_fast_batch(P, nPhotons, seed, firstPhotonId, h->numSMs, h->dCounters + CNT_N, h->stream);

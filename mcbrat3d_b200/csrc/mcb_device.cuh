@@ -26,6 +26,7 @@ struct DevDomain {
   const double *cumExt, *ssa;                 // (nx,ny,nz,nc)
   const int32_t *phaseIdx;                    // (nx,ny,nz,nc)
   double albedo;
+  float maxExtinction;                        // real(maxval(totalExt)), INT:448 (maximum cross-section only)
   // ---- packed single-precision copies for the fast kernel ----
   const float *extp;                          // padded (nx+2G, ny+2G, nz+2G) extinction field with its ghost shell
                                               // (periodic replicas in x, y; zeros above and below), pointing AT the

@@ -344,6 +344,18 @@ __device__ void intensityContribution(const DevDomain &P, float photonWeight,
 }
 
 // One photon: source sampling (ILL:62-101 / ILL:431-522) + computeRT's loop body (INT:463-823)
+// makePeriodic INT:1898-1917: the result is DEFAULT REAL (quirk q15), the bounds are real(8)
+__device__ float makePeriodic(double a, double aMin, double aMax) {
+  float m = (float)a;
+  for (;;) {
+    if ((double)m <= aMax && (double)m > aMin) break;
+    if ((double)m > aMax) m = (float)((double)m - (aMax - aMin));
+    else if ((double)m == aMin) m = (float)aMax;
+    else m = (float)((double)m + (aMax - aMin));
+  }
+  return m;
+}
+
 template <class RNG, bool TRACE>
 __device__ void photon_history(const DevDomain &P, RNG &rng, TraceSink &ts, Counts &cnt) {
   const int numX = P.nx, numY = P.ny, numZ = P.nz, numComps = P.nc;
@@ -430,14 +442,27 @@ __device__ void photon_history(const DevDomain &P, RNG &rng, TraceSink &ts, Coun
     }
     const float u = rng.real();
     const float tauToTravel = -f_log(fmaxf(TINY32, u));                        // INT:554
-    double path;
-    const float tauAccumulated = march(P, directionCosines, xPos, yPos, zPos, xIndex, yIndex, zIndex,
-                                       true, tauToTravel, path, cnt.c[CNT_CROSSINGS]);   // INT:559-561
-    if (tauAccumulated < 0.0f) {                                               // INT:562-563
-      cnt.c[CNT_BAD]++;
-      emit<TRACE>(ts, rng, MCB_EV_BAD, xIndex, yIndex, zIndex, 0, 0, 0, scatteringOrder,
-                  photonWeight, tauToTravel, path, xPos, yPos, zPos, directionCosines);
-      return;
+    double path = 0.0;
+    const bool useMaxCrossSection = !P.opt.useRayTracing;                      // INT:445
+    if (!useMaxCrossSection) {
+      const float tauAccumulated = march(P, directionCosines, xPos, yPos, zPos, xIndex, yIndex, zIndex,
+                                         true, tauToTravel, path, cnt.c[CNT_CROSSINGS]);   // INT:559-561
+      if (tauAccumulated < 0.0f) {                                             // INT:562-563
+        cnt.c[CNT_BAD]++;
+        emit<TRACE>(ts, rng, MCB_EV_BAD, xIndex, yIndex, zIndex, 0, 0, 0, scatteringOrder,
+                    photonWeight, tauToTravel, path, xPos, yPos, zPos, directionCosines);
+        return;
+      }
+    } else {                                       // INT:564-571; the cell indices are NOT refreshed here (sic)
+      xPos = (double)makePeriodic(xPos + (double)(directionCosines[0] * tauToTravel / P.maxExtinction), P.x0, P.xMax);
+      yPos = (double)makePeriodic(yPos + (double)(directionCosines[1] * tauToTravel / P.maxExtinction), P.y0, P.yMax);
+      zPos = zPos + (double)(directionCosines[2] * tauToTravel / P.maxExtinction);
+    }
+    if (useMaxCrossSection && (zPos >= P.zMax || zPos <= P.z0 + sp64(P.z0))) {  // INT:578-585, 624-631: trace back to the boundary
+      const double zB = zPos >= P.zMax ? P.zMax : P.z0;
+      xPos = (double)makePeriodic(xPos - (double)directionCosines[0] * fabs((zPos - zB) / (double)directionCosines[2]), P.x0, P.xMax);
+      yPos = (double)makePeriodic(yPos - (double)directionCosines[1] * fabs((zPos - zB) / (double)directionCosines[2]), P.y0, P.yMax);
+      findXYIndicies(P, xPos, yPos, xIndex, yIndex);
     }
     const size_t colIdx = (size_t)(xIndex - 1) + (size_t)numX * (size_t)(yIndex - 1);
     if (zPos >= P.zMax) {                                                      // INT:573-617
@@ -471,6 +496,14 @@ __device__ void photon_history(const DevDomain &P, RNG &rng, TraceSink &ts, Coun
         intensityContribution<RNG, TRACE>(P, photonWeight, xPos, yPos, zPos, xIndex, yIndex, zIndex,
                                           directionCosines, 0, 0, rng, scatteringOrder, ts, cnt);
     } else {                                                                   // INT:703-821
+      if (useMaxCrossSection) {                                                // INT:709-710: physical or mathematical event
+        const float rnPhys = rng.real();
+        if (!((double)rnPhys < P.totalExt[CELL(P, xIndex, yIndex, zIndex)] / (double)P.maxExtinction)) {
+          emit<TRACE>(ts, rng, MCB_EV_NULL_COLLISION, xIndex, yIndex, zIndex, 0, 0, 0, scatteringOrder,
+                      photonWeight, tauToTravel, path, xPos, yPos, zPos, directionCosines);
+          continue;
+        }
+      }
       scatteringOrder = scatteringOrder + 1;
       cnt.c[CNT_SCATTERS]++;
       if (P.totalExt[CELL(P, xIndex, yIndex, zIndex)] <= 0.0) {                // INT:728-754

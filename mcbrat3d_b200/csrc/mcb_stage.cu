@@ -18,11 +18,14 @@ namespace mcbstage {
 
 enum { FLAG_EXT = 1, FLAG_SSA = 2, FLAG_IDX = 4, FLAG_TEMP = 8 };
 
+// flags[0]: argument-check bits; flags[2..3] (as one u64): bit pattern of maxval(totalExt) -- non-negative
+// doubles order like their bit patterns, so an integer atomicMax does the reduction (INT:448)
 __global__ void pack_extinction_kernel(const double *__restrict__ totalExt, float *__restrict__ e32,
                                        int nx, int ny, int nz, int G, int *flags) {
   const int nxp = nx + 2 * G, nyp = ny + 2 * G, nzp = nz + 2 * G;
   const long long total = (long long)nxp * nyp * nzp;
   int bad = 0;
+  double emax = 0.0;
   for (long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x; p < total; p += (long long)gridDim.x * blockDim.x) {
     const int i = (int)(p % nxp);
     const long long q = p / nxp;
@@ -33,11 +36,15 @@ __global__ void pack_extinction_kernel(const double *__restrict__ totalExt, floa
       int my = (j - G) % ny; my += my < 0 ? ny : 0;
       const double e = totalExt[mx + (long long)nx * (my + (long long)ny * (k - G))];
       if (!(e >= 0.0)) bad = FLAG_EXT;
+      emax = e > emax ? e : emax;
       v = (float)e;
     }
     e32[p] = v;
   }
   if (bad) atomicOr(flags, bad);
+  for (int o = 16; o > 0; o >>= 1) { const double t = __shfl_down_sync(0xffffffffu, emax, o); emax = t > emax ? t : emax; }
+  if ((threadIdx.x & 31) == 0 && emax > 0.0)
+    atomicMax((unsigned long long *)(flags + 2), (unsigned long long)__double_as_longlong(emax));
 }
 
 __global__ void pack_components_kernel(const double *__restrict__ cumExt, const double *__restrict__ ssa,

@@ -717,6 +717,18 @@ static void add_intensity(orc_integrator *g, const float *contributions, const i
 }
 
 /* computeRT INT:393-841 (ray-tracing branch) */
+/* makePeriodic INT:1898-1917: the function result is DEFAULT REAL (quirk q15), the bounds are real(8) */
+static float makePeriodic(double a, double aMin, double aMax) {
+  float m = (float)a;
+  for (;;) {
+    if ((double)m <= aMax && (double)m > aMin) break;
+    if ((double)m > aMax) m = (float)((double)m - (aMax - aMin));
+    else if ((double)m == aMin) m = (float)aMax;
+    else m = (float)((double)m + (aMax - aMin));
+  }
+  return m;
+}
+
 static int computeRT(orc_integrator *g, const orc_domain *d, orc_rng *r, orc_photons *ph,
                      int64_t numPhotonsPerBatch, int64_t *numPhotonsProcessed) {
   const int numX = d->nx, numY = d->ny, numZ = d->nz, numComps = d->nc;
@@ -732,6 +744,15 @@ static int computeRT(orc_integrator *g, const orc_domain *d, orc_rng *r, orc_pho
   double *cumTable = (double *)malloc(sizeof(double) * (numComps + 1));
   int64_t nPhotons = 0; int nBad = 0;
   (void)numY;
+  /* INT:445-448: maximum cross-section (Marchuk 1980) instead of ray tracing; maxExtinction is DEFAULT REAL */
+  const int useRayTracing = g->opt.useRayTracing, useMaxCrossSection = !useRayTracing;
+  float maxExtinction = 0.0f;
+  if (useMaxCrossSection) {
+    double m = d->totalExt[0];
+    const size_t cells = (size_t)numX * numY * numZ;
+    for (size_t i = 1; i < cells; ++i) if (d->totalExt[i] > m) m = d->totalExt[i];
+    maxExtinction = (float)m;
+  }
 
   while (nPhotons < numPhotonsPerBatch) {                                   /* photonLoop INT:463 */
     if (!(ph->current > 0 && ph->current <= ph->n)) break;                  /* morePhotonsExist ILL:540-546 */
@@ -785,15 +806,26 @@ static int computeRT(orc_integrator *g, const orc_domain *d, orc_rng *r, orc_pho
       float u = orc_rng_real(r);
       float tauToTravel = -f_log(u > TINY32 ? u : TINY32);                  /* INT:554 */
       double path = 0.0;
-      float tauAccumulated = orc_march(d, directionCosines, &xPos, &yPos, &zPos, &xIndex, &yIndex, &zIndex,
-                                       1, tauToTravel, &path, &g->cnt.crossings);  /* INT:559-561 */
-      if (tauAccumulated < 0.0f) {                                          /* INT:562-563 */
-        nBad = nBad + 1; g->cnt.bad++;
-        trace_event(g, r, photonNo, ORC_EV_BAD, xIndex, yIndex, zIndex, 0, 0, 0, scatteringOrder,
-                    photonWeight, tauToTravel, path, xPos, yPos, zPos, directionCosines);
-        break;
+      if (useRayTracing) {
+        float tauAccumulated = orc_march(d, directionCosines, &xPos, &yPos, &zPos, &xIndex, &yIndex, &zIndex,
+                                         1, tauToTravel, &path, &g->cnt.crossings);  /* INT:559-561 */
+        if (tauAccumulated < 0.0f) {                                        /* INT:562-563 */
+          nBad = nBad + 1; g->cnt.bad++;
+          trace_event(g, r, photonNo, ORC_EV_BAD, xIndex, yIndex, zIndex, 0, 0, 0, scatteringOrder,
+                      photonWeight, tauToTravel, path, xPos, yPos, zPos, directionCosines);
+          break;
+        }
+      } else {                                                              /* INT:564-571; the cell indices are NOT refreshed (sic) */
+        xPos = (double)makePeriodic(xPos + (double)(directionCosines[0] * tauToTravel / maxExtinction), x0, xMax);
+        yPos = (double)makePeriodic(yPos + (double)(directionCosines[1] * tauToTravel / maxExtinction), y0, yMax);
+        zPos = zPos + (double)(directionCosines[2] * tauToTravel / maxExtinction);
       }
       if (zPos >= zMax) {                                                   /* INT:573-617 */
+        if (useMaxCrossSection) {                                           /* INT:578-585: trace back to the domain top */
+          xPos = (double)makePeriodic(xPos - (double)directionCosines[0] * fabs((zPos - zMax) / (double)directionCosines[2]), x0, xMax);
+          yPos = (double)makePeriodic(yPos - (double)directionCosines[1] * fabs((zPos - zMax) / (double)directionCosines[2]), y0, yMax);
+          findXYIndicies(g, xPos, yPos, &xIndex, &yIndex);
+        }
         size_t col = (size_t)(xIndex - 1) + (size_t)numX * (size_t)(yIndex - 1);
         g->fluxUp[col] = g->fluxUp[col] + photonWeight;
         g->cnt.topExits++;
@@ -801,6 +833,11 @@ static int computeRT(orc_integrator *g, const orc_domain *d, orc_rng *r, orc_pho
                     photonWeight, tauToTravel, path, xPos, yPos, zPos, directionCosines);
         break;
       } else if (zPos <= z0 + sp64(z0)) {                                   /* INT:619-702 */
+        if (useMaxCrossSection) {                                           /* INT:624-631: trace back to the domain base */
+          xPos = (double)makePeriodic(xPos - (double)directionCosines[0] * fabs((zPos - z0) / (double)directionCosines[2]), x0, xMax);
+          yPos = (double)makePeriodic(yPos - (double)directionCosines[1] * fabs((zPos - z0) / (double)directionCosines[2]), y0, yMax);
+          findXYIndicies(g, xPos, yPos, &xIndex, &yIndex);
+        }
         zIndex = 1;
         zPos = z0 + sp64(z0);
         size_t col = (size_t)(xIndex - 1) + (size_t)numX * (size_t)(yIndex - 1);
@@ -829,6 +866,14 @@ static int computeRT(orc_integrator *g, const orc_domain *d, orc_rng *r, orc_pho
           add_intensity(g, contributions, xIndexF, yIndexF, 0);
         }
       } else {                                                              /* scattering event INT:703-821 */
+        if (useMaxCrossSection) {                                           /* INT:709-710: "physical" or "mathematical" event */
+          const float rnPhys = orc_rng_real(r);
+          if (!((double)rnPhys < d->totalExt[CELL(d, xIndex, yIndex, zIndex)] / (double)maxExtinction)) {
+            trace_event(g, r, photonNo, ORC_EV_NULL_COLLISION, xIndex, yIndex, zIndex, 0, 0, 0, scatteringOrder,
+                        photonWeight, tauToTravel, path, xPos, yPos, zPos, directionCosines);
+            continue;
+          }
+        }
         scatteringOrder = scatteringOrder + 1;
         g->cnt.scatters++;
         if (d->totalExt[CELL(d, xIndex, yIndex, zIndex)] <= 0.0) {          /* INT:728-754 */

@@ -53,7 +53,7 @@ int orc_findCDFIndex(float value, const double *table, int n, int stride);      
 enum {
   ORC_EV_BIRTH = 1, ORC_EV_SCATTER = 2, ORC_EV_SURFACE = 3, ORC_EV_EXIT_TOP = 4,
   ORC_EV_KILLED_SURFACE = 5, ORC_EV_KILLED_ROULETTE = 6, ORC_EV_BAD = 7,
-  ORC_EV_LOCAL_ESTIMATE = 8, ORC_EV_RN_EXHAUSTED = 9
+  ORC_EV_LOCAL_ESTIMATE = 8, ORC_EV_RN_EXHAUSTED = 9, ORC_EV_NULL_COLLISION = 10
 };
 
 typedef struct {
@@ -120,7 +120,7 @@ double orc_emission_weighting(const orc_domain *d, const double *temps, double l
 
 /* ---- integrator (monteCarloRadiativeTransfer.f95 type(integrator), INT:40-117) ------ */
 typedef struct {
-  int useRayTracing;                 /* only .true. is restated                         */
+  int useRayTracing;                 /* .false. = maximum cross-section, INT:564-571   */
   int useRussianRoulette;
   float RussianRouletteW;
   int useRussianRouletteForIntensity;

@@ -37,8 +37,7 @@ def test_parameter_checks_and_missing_tables():
             specifyParameters(g, intensityMus=[0.0], intensityPhis=[0.0])
         with pytest.raises(ValueError, match="Both or neither"):
             specifyParameters(g, intensityMus=[0.5])
-        with pytest.raises(_lib.McbError, match="maximum cross-section"):
-            specifyParameters(g, useRayTracing=False)
+        specifyParameters(g, useRayTracing=False)           # maximum cross-section (INT:564-571) is accepted
         specifyParameters(g, useRayTracing=True)
         with pytest.raises(_lib.McbError, match="intensity information not available"):
             reportResults(g, meanIntensity=True)

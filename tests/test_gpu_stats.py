@@ -113,6 +113,37 @@ def test_three_sigma_against_oracle(orc, name, make, source, views, n, arithmeti
                       np.maximum(oe, gerr["meanIntensity"]), 3.0)
 
 
+def test_max_cross_section_three_sigma(orc):
+    """Maximum cross-section transport (useRayTracing=.false.) on the homogeneous slab, where the
+    reference's stale cell indices are harmless: fluxes within 3 sigma of the oracle AND of ray tracing."""
+    dom, case = domains.homogeneous_slab(ssa=0.99)
+    n, nb = 6000, 32
+    od = orc.OracleDomain(dom, tableSize=10001)
+    res = {}
+    for rt in (0, 1):
+        og = orc.OracleIntegrator(od, useRayTracing=rt)
+        tot, st = og.run_batches(nb, n, source=0, iseed=10, rank=1, thread=0, solarMu=case["solarMu"],
+                                 solarAzimuth=case["solarAzimuth"])
+        res[rt] = {q: orc.finalise(st[q + "Stats"], 1.0, tot, nb) for q in ("meanFluxUp", "meanFluxDown", "meanFluxAbsorbed")}
+    g = new_Integrator(dom)
+    try:
+        specifyParameters(g, minInverseTableSize=10001, useRayTracing=False)
+        rs = new_RandomNumberSequence([10, 1, 0])
+        bs = BatchStatistics()
+        for _ in range(nb):
+            ps = new_PhotonStream(case["solarMu"], case["solarAzimuth"], n, rs)
+            done = computeRadiativeTransfer(g, dom, rs, ps, n)
+            bs.accumulate(reportResults(g, meanFluxUp=True, meanFluxDown=True, meanFluxAbsorbed=True), done)
+        gmean, gerr = bs.finalise(1.0)
+        c = getCounters(g)
+        assert c["crossings"] == 0 and c["scatters"] > 0
+    finally:
+        finalize_Integrator(g)
+    for q in ("meanFluxUp", "meanFluxDown", "meanFluxAbsorbed"):
+        assert_within("max-xsec vs oracle " + q, gmean[q], gerr[q], res[0][q][0], res[0][q][1], 3.0)
+        assert_within("max-xsec vs ray tracing " + q, gmean[q], gerr[q], res[1][q][0], res[1][q][1], 3.5)
+
+
 def test_fast_and_reference_arithmetic_agree():
     """The two kernels share the per-photon Philox key but draw from it in a different order (the
     fast kernel takes whole blocks at warp-convergent points), so their histories are independent

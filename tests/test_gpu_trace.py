@@ -55,6 +55,37 @@ def test_trace_parity(orc, name, dom, case, source, views, rr):
         finalize_Integrator(g)
 
 
+@pytest.mark.parametrize("name,dom,case,source", [c for c in CASES if c[0] in ("C1", "T_irr", "C2")],
+                         ids=[c[0] for c in CASES if c[0] in ("C1", "T_irr", "C2")])
+@pytest.mark.parametrize("views", [False, True], ids=["flux", "le"])
+def test_trace_parity_max_cross_section(orc, name, dom, case, source, views):
+    """useRayTracing=.false. (INT:564-571, 578-585, 624-631, 709-710; makePeriodic returns default real,
+    quirk q15): same bit-exact criterion, including the mathematical (null) collisions."""
+    g = new_Integrator(dom)
+    try:
+        if views:
+            mus = case.get("intensityMus", [1.0, 0.5]); phis = case.get("intensityPhis", [0.0, 0.0])
+            specifyParameters(g, intensityMus=mus, intensityPhis=phis, computeIntensity=True)
+        specifyParameters(g, minInverseTableSize=10001, minForwardTableSize=10001, useRayTracing=False)
+        od = orc.OracleDomain(dom, tableSize=10001, forward=views)
+        og = orc.OracleIntegrator(od, useRayTracing=0)
+        if views:
+            og.set_view_cosines(g.intensityDirections)
+        n, stride = 800, 600
+        rn = injected_randoms(n, stride, seed=7 + hash(name) % 1000)
+        rs = new_RandomNumberSequence([10, 1, 0])
+        ps = new_PhotonStream(case["solarMu"], case["solarAzimuth"], n, rs)
+        want = og.trace(rn, 0, case["solarMu"], case["solarAzimuth"], maxEvents=n * 2048)
+        got, raw = tracePhotons(g, dom, ps, rn, maxEventsPerPhoton=2048)
+        assert len(want) > 3 * n
+        assert (want["kind"] == 10).any() or name == "C1"         # heterogeneous domains see null collisions
+        assert_events_equal(got, want, "%s max-xsec views=%s" % (name, views))
+        ot = og.raw_tallies()
+        np.testing.assert_allclose(raw[: ot.size], ot, rtol=2e-5, atol=2e-4)
+    finally:
+        finalize_Integrator(g)
+
+
 def test_trace_matches_committed_golden(orc):
     """The committed fixture (tests/golden/trace_T_irr.npz, written by tests/golden/make_golden.py
     from the oracle) pins both implementations against drift."""

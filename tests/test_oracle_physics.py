@@ -143,3 +143,33 @@ def test_regular_grid_detection_quirk_q1(orc):
     dl, _ = domains.step_cloud()
     hl = orc.OracleIntegrator(orc.OracleDomain(dl, tableSize=9001)).head()
     assert hl.xyRegularlySpaced == 1 and hl.zRegularlySpaced == 1 and hl.deltaX == 15.625
+
+
+def test_max_cross_section_equals_ray_tracing_on_homogeneous_slab(orc):
+    """INT:564-571, 709-710: on a homogeneous domain every Woodcock event is physical and the
+    reference's stale cell indices are harmless, so the two transport modes sample the same problem."""
+    dom, case = domains.homogeneous_slab(ssa=0.99)
+    od = orc.OracleDomain(dom, tableSize=9001)
+    res = {}
+    for rt in (1, 0):
+        og = orc.OracleIntegrator(od, useRayTracing=rt)
+        tot, st = og.run_batches(16, 3000, source=0, solarMu=case["solarMu"], solarAzimuth=case["solarAzimuth"])
+        res[rt] = [orc.finalise(st[q + "Stats"], 1.0, tot, 16) for q in ("meanFluxUp", "meanFluxDown", "meanFluxAbsorbed")]
+    for (m1, e1), (m0, e0) in zip(res[1], res[0]):
+        assert abs(m1[0] - m0[0]) < 3.5 * np.hypot(e1[0], e0[0])
+    closure = res[0][0][0][0] + 0.8 * res[0][1][0][0] + res[0][2][0][0]
+    assert abs(closure - 1.0) < 5e-3
+
+
+def test_make_periodic_is_single_precision(orc):
+    """Quirk q15: with injected random numbers the x position after a maximum cross-section move is a
+    float (makePeriodic returns default real), and mathematical collisions are traced."""
+    dom, case = domains.irregular_test_domain()
+    od = orc.OracleDomain(dom, tableSize=9001)
+    og = orc.OracleIntegrator(od, useRayTracing=0)
+    rn = np.random.default_rng(3).random((100, 600), dtype=np.float32)
+    ev = og.trace(rn, 0, case["solarMu"], case["solarAzimuth"], maxEvents=100 * 2048)
+    null = ev[ev["kind"] == 10]
+    assert len(null) > 0
+    assert np.array_equal(null["x"], null["x"].astype(np.float32).astype(np.float64))
+    assert np.array_equal(null["y"], null["y"].astype(np.float32).astype(np.float64))
