@@ -118,6 +118,25 @@ int mcb_run_batch(mcb_handle *h, int64_t nPhotons, uint64_t seed, uint64_t first
 /* Same without zeroing: adds another range of photons to the current tallies. */
 int mcb_accumulate_batch(mcb_handle *h, int64_t nPhotons, uint64_t seed, uint64_t firstPhotonId,
                          int64_t *nProcessed);
+/* ---- the driver's batch loop and statistics (DRV:949-1052, 1188-1228) on the device --------
+ * mcb_run_batches runs numBatches batches back to back (batch b traces photon ids firstPhotonId +
+ * b*photonsPerBatch ...): after each batch the normalised results are folded into first and second
+ * moments weighted by the photons of the batch (meanFlux*Stats, flux*Stats, absorbedProfileStats,
+ * absorbedVolumeStats, RadianceStats of DRV:1023-1052).  Nothing returns to the host between batches.
+ * Moments add across GPUs/ranks exactly as the driver's sumAcrossProcesses does (DRV:1151-1166):
+ * mcb_stats_buffer exposes the f64 device buffer [moment1 : n][moment2 : n][totalNumPhotons]
+ * [batchesCompleted] for one sum-reduce.  mcb_get_statistics finalises as DRV:1188-1228; every
+ * output is stats(..., 1:2) in the Fortran layout (block of means, then block of standard errors);
+ * meanFluxStats is (3,2): up, down, absorbed.  Any output pointer may be NULL.                     */
+int mcb_stats_reset(mcb_handle *h);
+int mcb_run_batches(mcb_handle *h, int64_t numBatches, int64_t photonsPerBatch, uint64_t seed,
+                    uint64_t firstPhotonId, int64_t *nProcessed);
+int mcb_stats_buffer(mcb_handle *h, void **devicePtr, int64_t *nDoubles);
+int mcb_get_statistics(mcb_handle *h, double solarFlux, double *meanFluxStats, double *fluxUpStats,
+                       double *fluxDownStats, double *fluxAbsorbedStats, double *absorbedProfileStats,
+                       double *absorbedVolumeStats, double *radianceStats,
+                       int64_t *totalNumPhotons, int64_t *batchesCompleted);
+
 /* Device time of the last run/accumulate call (CUDA events on the launch stream), ms.    */
 int mcb_last_batch_ms(mcb_handle *h, float *ms);
 int mcb_get_counters(mcb_handle *h, mcb_counters *c);

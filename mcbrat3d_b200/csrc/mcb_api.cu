@@ -25,6 +25,11 @@ long long mcb_emission_tiles(long long cells);
 void mcb_launch_emission_cdf(const DevDomain &P, const double *temps, double a, double b, double lambda5, void *scratch,
                              double *cdf, int *flags, int numSMs, cudaStream_t stream);
 void mcb_launch_emission_normalise(double *cdf, long long cells, const void *total, int numSMs, cudaStream_t stream);
+long long mcb_stats_elements(const DevDomain &P);
+void mcb_launch_stats_accumulate(const DevDomain &P, const float *results, double *stats, double weight, int numSMs,
+                                 cudaStream_t stream);
+void mcb_launch_stats_finalise(const double *stats, long long n, double solarFlux, double *out, int numSMs,
+                               cudaStream_t stream);
 
 struct mcb_handle {
   int device = 0;
@@ -46,6 +51,7 @@ struct mcb_handle {
   int invE[MCB_MAX_COMP] = {0}, fwdE[MCB_MAX_COMP] = {0};
   void *dVoxelCDF = nullptr, *dTemps = nullptr, *dScratch = nullptr, *dResults = nullptr;
   int *dFlags = nullptr;
+  void *dStats = nullptr, *dStatsOut = nullptr; long long nStats = 0;   // batch statistics: moments, finalised copy
   double *dTally = nullptr; long long nTally = 0;
   unsigned long long *dCounters = nullptr;     // CNT_N counters + 1 work counter
   double *hTally = nullptr; long long hTallyCap = 0;   // pinned
@@ -141,7 +147,7 @@ int mcb_destroy(mcb_handle *h) {
   cudaStreamSynchronize(h->stream);
   void *slots[] = {h->dXE, h->dYE, h->dZE, h->dTotalExt, h->dCumExt, h->dSsa, h->dPhaseIdx,
                    h->dExt32, h->dCum32, h->dSsa32, h->dIdx16, h->dVoxelCDF, h->dTally, h->dCounters,
-                   h->dTemps, h->dScratch, h->dResults, (void *)h->dFlags};
+                   h->dTemps, h->dScratch, h->dResults, (void *)h->dFlags, h->dStats, h->dStatsOut};
   for (void *p : slots) if (p) cudaFree(p);
   for (int c = 0; c < MCB_MAX_COMP; ++c) {
     if (h->dInv[c]) cudaFree(h->dInv[c]);
@@ -449,7 +455,8 @@ static int check_ready(mcb_handle *h) {
   return 0;
 }
 
-static int run(mcb_handle *h, long long nPhotons, uint64_t seed, uint64_t firstPhotonId, bool zero, int64_t *nProcessed) {
+static int run(mcb_handle *h, long long nPhotons, uint64_t seed, uint64_t firstPhotonId, bool zero, int64_t *nProcessed,
+               bool zeroCounters = true, bool timeIt = true) {
   if (!h) return 1;
   if (nProcessed) *nProcessed = 0;
   if (check_ready(h)) return 1;
@@ -459,12 +466,11 @@ static int run(mcb_handle *h, long long nPhotons, uint64_t seed, uint64_t firstP
   DevDomain &P = h->P;
   if (zero) {                                                    // INT:247-272
     CK(h, cudaMemsetAsync(h->dTally, 0, sizeof(double) * h->nTally, h->stream));
-    CK(h, cudaMemsetAsync(h->dCounters, 0, sizeof(unsigned long long) * 32, h->stream));
-  } else {
-    CK(h, cudaMemsetAsync(h->dCounters + CNT_N, 0, sizeof(unsigned long long), h->stream));
+    if (zeroCounters) CK(h, cudaMemsetAsync(h->dCounters, 0, sizeof(unsigned long long) * 32, h->stream));
   }
+  if (!(zero && zeroCounters)) CK(h, cudaMemsetAsync(h->dCounters + CNT_N, 0, sizeof(unsigned long long), h->stream));
   if (nPhotons == 0) FAIL(h, "computeRadiativeTransfer: Didn't process any photons.");   // INT:835-836
-  CK(h, cudaEventRecord(h->evStart, h->stream));
+  if (timeIt) CK(h, cudaEventRecord(h->evStart, h->stream));
   if (!P.opt.useRayTracing && !(P.maxExtinction > 0.0f))
     FAIL(h, "computeRadiativeTransfer: maximum cross-section needs a domain with extinction > 0");
   // the maximum cross-section branch (INT:564-571) exists in reference arithmetic only: as shipped it never
@@ -474,8 +480,7 @@ static int run(mcb_handle *h, long long nPhotons, uint64_t seed, uint64_t firstP
   else
     mcb_launch_fast_batch(P, nPhotons, seed, firstPhotonId, h->numSMs, h->dCounters + CNT_N, h->stream);
   CK(h, cudaGetLastError());
-  CK(h, cudaEventRecord(h->evStop, h->stream));
-  h->timed = true;
+  if (timeIt) { CK(h, cudaEventRecord(h->evStop, h->stream)); h->timed = true; }
   if (nProcessed) *nProcessed = nPhotons;
   return 0;
 }
@@ -485,6 +490,98 @@ int mcb_run_batch(mcb_handle *h, int64_t nPhotons, uint64_t seed, uint64_t first
 }
 int mcb_accumulate_batch(mcb_handle *h, int64_t nPhotons, uint64_t seed, uint64_t firstPhotonId, int64_t *nProcessed) {
   return run(h, nPhotons, seed, firstPhotonId, false, nProcessed);
+}
+
+// ---- the driver's batch loop with its statistics on the device (DRV:949-1052, 1188-1228) ----
+static int ensure_stats(mcb_handle *h) {
+  if (ensure_tallies(h)) return 1;
+  const long long n = mcb_stats_elements(h->P);
+  if (n != h->nStats || !h->dStats) {
+    if (reserve(h, &h->dStats, sizeof(double) * (size_t)(2 * n + 2))) return 1;
+    if (reserve(h, &h->dStatsOut, sizeof(double) * (size_t)(2 * n))) return 1;
+    CK(h, cudaMemsetAsync(h->dStats, 0, sizeof(double) * (size_t)(2 * n + 2), h->stream));
+    h->nStats = n;
+  }
+  return 0;
+}
+
+int mcb_stats_reset(mcb_handle *h) {
+  if (!h) return 1;
+  if (!h->haveGrid || !h->haveOptics) FAIL(h, "mcb_stats_reset: problem not completely specified.");
+  CK(h, cudaSetDevice(h->device));
+  if (ensure_stats(h)) return 1;
+  CK(h, cudaMemsetAsync(h->dStats, 0, sizeof(double) * (size_t)(2 * h->nStats + 2), h->stream));
+  return 0;
+}
+
+int mcb_run_batches(mcb_handle *h, int64_t numBatches, int64_t photonsPerBatch, uint64_t seed, uint64_t firstPhotonId,
+                    int64_t *nProcessed) {
+  if (!h) return 1;
+  if (nProcessed) *nProcessed = 0;
+  if (check_ready(h)) return 1;
+  if (numBatches < 1 || photonsPerBatch < 1) FAIL(h, "mcb_run_batches: numBatches and photonsPerBatch must be positive");
+  CK(h, cudaSetDevice(h->device));
+  if (ensure_stats(h)) return 1;
+  if (reserve(h, &h->dResults, sizeof(float) * (size_t)h->P.offExcess)) return 1;
+  CK(h, cudaMemsetAsync(h->dCounters, 0, sizeof(unsigned long long) * 32, h->stream));
+  CK(h, cudaEventRecord(h->evStart, h->stream));
+  for (int64_t b = 0; b < numBatches; ++b) {
+    // one batch = computeRadiativeTransfer + reportResults + the moment updates of DRV:1023-1052; nothing
+    // leaves the device and the host does not wait between batches
+    if (run(h, photonsPerBatch, seed, firstPhotonId + (uint64_t)b * (uint64_t)photonsPerBatch, true, nullptr, false, false))
+      return 1;
+    mcb_launch_normalise(h->P, (float)photonsPerBatch, (float *)h->dResults, h->numSMs, h->stream);
+    mcb_launch_stats_accumulate(h->P, (const float *)h->dResults, (double *)h->dStats, (double)photonsPerBatch, h->numSMs,
+                                h->stream);
+    CK(h, cudaGetLastError());
+  }
+  CK(h, cudaEventRecord(h->evStop, h->stream));
+  h->timed = true;
+  if (nProcessed) *nProcessed = numBatches * photonsPerBatch;
+  return 0;
+}
+
+int mcb_stats_buffer(mcb_handle *h, void **devicePtr, int64_t *nDoubles) {
+  if (!h) return 1;
+  if (!h->haveGrid || !h->haveOptics) FAIL(h, "mcb_stats_buffer: problem not completely specified.");
+  CK(h, cudaSetDevice(h->device));
+  if (ensure_stats(h)) return 1;
+  if (devicePtr) *devicePtr = h->dStats;
+  if (nDoubles) *nDoubles = 2 * h->nStats + 2;
+  return 0;
+}
+
+int mcb_get_statistics(mcb_handle *h, double solarFlux, double *meanFluxStats, double *fluxUpStats, double *fluxDownStats,
+                       double *fluxAbsorbedStats, double *absorbedProfileStats, double *absorbedVolumeStats,
+                       double *radianceStats, int64_t *totalNumPhotons, int64_t *batchesCompleted) {
+  if (!h) return 1;
+  CK(h, cudaSetDevice(h->device));
+  if (!h->dStats || h->nStats == 0) FAIL(h, "mcb_get_statistics: no batches have run");
+  const DevDomain &P = h->P;
+  const long long n = h->nStats;
+  if (radianceStats && P.nDir == 0) FAIL(h, "reportResults: intensity information not available");
+  double book[2] = {0.0, 0.0};
+  CK(h, cudaMemcpyAsync(book, (const double *)h->dStats + 2 * n, sizeof(book), cudaMemcpyDeviceToHost, h->stream));
+  if (settle(h)) return 1;
+  if (totalNumPhotons) *totalNumPhotons = (int64_t)book[0];
+  if (batchesCompleted) *batchesCompleted = (int64_t)book[1];
+  if (!(book[1] >= 2.0)) FAIL(h, "mcb_get_statistics: at least two batches are needed for a standard error");
+  double *out = (double *)h->dStatsOut;
+  mcb_launch_stats_finalise((const double *)h->dStats, n, solarFlux, out, h->numSMs, h->stream);
+  CK(h, cudaGetLastError());
+  const size_t cols = (size_t)P.nx * P.ny, cells = cols * P.nz;
+  // every output is stats(..., 1:2) in the Fortran layout: the block of means, then the block of standard errors
+  struct { double *dst; long long off; size_t cnt; } parts[] = {
+      {meanFluxStats, 0, 3}, {fluxUpStats, 3, cols}, {fluxDownStats, 3 + (long long)cols, cols},
+      {fluxAbsorbedStats, 3 + 2 * (long long)cols, cols}, {absorbedProfileStats, 3 + 3 * (long long)cols, (size_t)P.nz},
+      {absorbedVolumeStats, 3 + 3 * (long long)cols + P.nz, cells},
+      {radianceStats, 3 + 3 * (long long)cols + P.nz + (long long)cells, cols * (size_t)P.nDir}};
+  for (auto &q : parts)
+    if (q.dst && q.cnt) {
+      CK(h, cudaMemcpyAsync(q.dst, out + q.off, sizeof(double) * q.cnt, cudaMemcpyDeviceToHost, h->stream));
+      CK(h, cudaMemcpyAsync(q.dst + q.cnt, out + n + q.off, sizeof(double) * q.cnt, cudaMemcpyDeviceToHost, h->stream));
+    }
+  return settle(h);
 }
 
 int mcb_last_batch_ms(mcb_handle *h, float *ms) {

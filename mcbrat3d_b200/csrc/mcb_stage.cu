@@ -120,6 +120,68 @@ __global__ void normalise_kernel(DevDomain P, float numPhotons, float *__restric
 }
 
 // ---------------------------------------------------------------------------------------------
+// batch statistics (DRV:1023-1052, 1188-1228)
+// ---------------------------------------------------------------------------------------------
+// Moment buffer (f64): first moments [0, n), second moments [n, 2n), then totalNumPhotons, batchesCompleted.
+// Element order inside a moment block:
+//   [meanFluxUp, meanFluxDown, meanFluxAbsorbed][fluxUp|fluxDown|fluxAbsorbed : 3*cols][absorbedProfile : nz]
+//   [absorbedVolume : cells][radiance : cols*nDir]
+__device__ __forceinline__ void add_moments(double *stats, long long n, long long i, float x, double weight) {
+  const double xd = (double)x;
+  stats[i] += xd * weight;                                           // stats(:,1) += x * numPhotonsProcessed
+  stats[n + i] += weight * (xd * xd);                                // stats(:,2) += numPhotonsProcessed * x**2
+}
+
+// element-wise quantities: one thread per element, results = the normalised single-precision arrays
+__global__ void stats_accumulate_kernel(DevDomain P, const float *__restrict__ results, double *stats, long long n,
+                                        double weight) {
+  const long long cols = (long long)P.nx * P.ny, cells = cols * P.nz;
+  const long long nFlux = 3 * cols, nRad = cols * P.nDir;
+  const long long total = nFlux + cells + nRad;
+  for (long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x; p < total; p += (long long)gridDim.x * blockDim.x) {
+    long long src, dst;
+    if (p < nFlux) { src = P.offFluxUp + p; dst = 3 + p; }
+    else if (p < nFlux + cells) { src = P.offVolAbs + (p - nFlux); dst = 3 + nFlux + P.nz + (p - nFlux); }
+    else { src = P.offInt + (p - nFlux - cells); dst = 3 + nFlux + P.nz + cells + (p - nFlux - cells); }
+    add_moments(stats, n, dst, results[src], weight);
+  }
+}
+
+// reduced quantities (reportResults INT:881-884, 966): block b < 3 -> domain mean of fluxUp/Down/Absorbed,
+// block 3 + k -> absorbedProfile(k) = sum(volumeAbsorption(:,:,k)) / numColumns, in single precision
+__global__ void stats_reduce_kernel(DevDomain P, const float *__restrict__ results, double *stats, long long n,
+                                    double weight, int bookkeeping) {
+  __shared__ double part[256];
+  const long long cols = (long long)P.nx * P.ny;
+  const int b = blockIdx.x;
+  const float *src = results + (b < 3 ? P.offFluxUp + (long long)b * cols : P.offVolAbs + (long long)(b - 3) * cols);
+  double s = 0.0;
+  for (long long i = threadIdx.x; i < cols; i += blockDim.x) s += (double)src[i];
+  part[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = blockDim.x / 2; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) part[threadIdx.x] += part[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    const float mean = __fdiv_rn((float)part[0], (float)cols);
+    add_moments(stats, n, b < 3 ? b : 3 + 3 * cols + (b - 3), mean, weight);
+    if (b == 0 && bookkeeping) { stats[2 * n] += weight; stats[2 * n + 1] += 1.0; }
+  }
+}
+
+// DRV:1188-1228: moments -> [mean | standard error]
+__global__ void stats_finalise_kernel(const double *__restrict__ stats, long long n, double solarFlux, double *out) {
+  const double total = stats[2 * n], batches = stats[2 * n + 1];
+  for (long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x; p < n; p += (long long)gridDim.x * blockDim.x) {
+    const double m1 = solarFlux * stats[p] / total;
+    const double m2 = solarFlux * (solarFlux * stats[n + p] / total);
+    out[p] = m1;
+    out[n + p] = sqrt(fmax(0.0, m2 - m1 * m1) / (batches - 1.0));
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // emission CDF (EMI:498-522)
 // ---------------------------------------------------------------------------------------------
 struct dd { double hi, lo; };
@@ -258,6 +320,23 @@ void mcb_launch_normalise(const DevDomain &P, float numPhotons, float *out, int 
   if (P.nDir > 0 && P.opt.limitIntensityContributions)
     mcbstage::redistribute_excess_kernel<<<P.nDir * (P.nc + 1), 256, 0, stream>>>(P);
   mcbstage::normalise_kernel<<<stream_grid(P.offExcess, 256, numSMs), 256, 0, stream>>>(P, numPhotons, out);
+}
+
+long long mcb_stats_elements(const DevDomain &P) {
+  const long long cols = (long long)P.nx * P.ny;
+  return 3 + 3 * cols + P.nz + cols * P.nz + cols * P.nDir;
+}
+
+void mcb_launch_stats_accumulate(const DevDomain &P, const float *results, double *stats, double weight, int numSMs,
+                                 cudaStream_t stream) {
+  const long long n = mcb_stats_elements(P);
+  mcbstage::stats_accumulate_kernel<<<stream_grid(n, 256, numSMs), 256, 0, stream>>>(P, results, stats, n, weight);
+  mcbstage::stats_reduce_kernel<<<3 + P.nz, 256, 0, stream>>>(P, results, stats, n, weight, 1);
+}
+
+void mcb_launch_stats_finalise(const double *stats, long long n, double solarFlux, double *out, int numSMs,
+                               cudaStream_t stream) {
+  mcbstage::stats_finalise_kernel<<<stream_grid(n, 256, numSMs), 256, 0, stream>>>(stats, n, solarFlux, out);
 }
 
 // returns the number of tiles; scratch must hold (tiles + 1) double-double values

@@ -120,3 +120,24 @@ def sumTalliesAcrossProcesses(thisIntegrator, root: int = 0) -> None:
     t = tallyTensor(thisIntegrator)
     dist.reduce(t, dst=root, op=dist.ReduceOp.SUM)
     torch.cuda.synchronize(thisIntegrator.device)
+
+
+def statisticsTensor(thisIntegrator) -> torch.Tensor:
+    """The device-side batch-statistics buffer (``mcb_stats_buffer``: first moments, second moments,
+    totalNumPhotons, batchesCompleted) as a CUDA tensor aliasing the library's memory."""
+    ptr = C.c_void_p()
+    n = C.c_int64(0)
+    thisIntegrator._check(thisIntegrator._lib.mcb_stats_buffer(thisIntegrator.handle, C.byref(ptr), C.byref(n)),
+                          "statisticsTensor")
+    return torch.as_tensor(_DeviceBuffer(ptr.value, n.value), device="cuda:%d" % thisIntegrator.device)
+
+
+def sumStatisticsAcrossProcesses(thisIntegrator, root: int = 0) -> None:
+    """Moments, photon counts and batch counts add across ranks exactly as the driver's
+    ``sumAcrossProcesses`` calls do (DRV:1151-1166): one reduce of the moment buffer."""
+    if not dist.is_initialized():
+        return
+    thisIntegrator._check(thisIntegrator._lib.mcb_synchronize(thisIntegrator.handle), "sumStatisticsAcrossProcesses")
+    t = statisticsTensor(thisIntegrator)
+    dist.reduce(t, dst=root, op=dist.ReduceOp.SUM)
+    torch.cuda.synchronize(thisIntegrator.device)

@@ -162,3 +162,41 @@ def test_emission_cdf_built_on_device_matches_oracle(orc, name):
             d2.temps = keep
     finally:
         finalize_Integrator(g)
+
+
+@pytest.mark.parametrize("views", [False, True], ids=["flux", "le"])
+def test_device_batch_statistics_match_host_loop(views):
+    """mcb_run_batches + mcb_get_statistics (DRV:949-1052, 1188-1228 on the device) against the host loop
+    computeRadiativeTransfer -> reportResults -> BatchStatistics over the SAME photons."""
+    from mcbrat3d_b200.batchStatistics import BatchStatistics, computeRadiativeTransferBatches, reportStatistics
+    d, case = domains.step_cloud(ssa=0.95, solarMu=0.5)
+    nb, n = 8, 20000
+    g = new_Integrator(d)
+    try:
+        if views:
+            specifyParameters(g, intensityMus=[1.0, 0.5], intensityPhis=[0.0, 180.0], computeIntensity=True)
+        rs = new_RandomNumberSequence(5)
+        bs = BatchStatistics()
+        for _ in range(nb):
+            ps = new_PhotonStream(case["solarMu"], case["solarAzimuth"], n, rs)
+            done = computeRadiativeTransfer(g, d, rs, ps, n)
+            bs.accumulate(reportResults(g, meanFluxUp=True, meanFluxDown=True, meanFluxAbsorbed=True, fluxUp=True,
+                                        fluxDown=True, fluxAbsorbed=True, absorbedProfile=True, volumeAbsorption=True,
+                                        intensity=views), done)
+        hm, he = bs.finalise(2.5)
+        rs2 = new_RandomNumberSequence(5)
+        ps = new_PhotonStream(case["solarMu"], case["solarAzimuth"], nb * n, rs2)
+        assert computeRadiativeTransferBatches(g, d, rs2, ps, n, nb) == nb * n
+        dm, de, tot, done = reportStatistics(g, solarFlux=2.5)
+        assert (tot, done) == (nb * n, nb)
+        for k in hm:
+            np.testing.assert_allclose(dm[k], hm[k], rtol=2e-6, atol=1e-12, err_msg=k)
+            np.testing.assert_allclose(de[k], he[k], rtol=5e-3, atol=1e-8, err_msg=k + " stderr")
+        assert dm["meanFluxUp"] > 0 and de["meanFluxUp"] > 0
+        # a second call adds batches to the same moments
+        ps = new_PhotonStream(case["solarMu"], case["solarAzimuth"], 2 * n, rs2)
+        computeRadiativeTransferBatches(g, d, rs2, ps, n, 2)
+        _, _, tot, done = reportStatistics(g)
+        assert (tot, done) == ((nb + 2) * n, nb + 2)
+    finally:
+        finalize_Integrator(g)
