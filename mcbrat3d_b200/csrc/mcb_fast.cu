@@ -38,6 +38,7 @@ struct SmemPlan {
   int fluxOff;             // float[3*cols]  privatised fluxUp|fluxDown|fluxAbs   (-1: global atomics)
   int volOff;              // float[cells]   privatised volumeAbsorption           (-1: global atomics)
   int intOff;              // float[cols*nDir] privatised intensity                (-1: global atomics)
+  int leOff;               // per warp: LE_WORDS x 32 request slots + 32 words of queue state (LE kernels only)
   int totalFloats;
 };
 
@@ -291,84 +292,144 @@ __device__ __forceinline__ void add_intensity(const DevDomain &P, const Tally &T
 
 struct Counts { unsigned crossings, scatters, leRays, leCrossings; };
 
-// computeIntensityContribution (INT:1623-1832) for one event, all view directions.
+// ---- local estimation: computeIntensityContribution (INT:1623-1832) as a warp-wide task queue ----
+// The reference traces the nDir view rays of an event one after the other inside the photon loop.  Here an event
+// POSTS a request (where, which way the photon was heading, weight, component, its Philox counter) into the
+// warp's shared-memory slots; then ALL 32 lanes of the warp -- the marching ones included, they would idle during
+// the event phase anyway -- pull (request, direction) tasks from a warp-local counter until none is left.  Every
+// lane advances its current ray by one burst per iteration, so the marcher code stays convergent while rays of
+// very different lengths are in flight; a lane that finishes a ray tallies it and takes the next task.
+#define LE_WORDS 13
+enum { LE_PX = 0, LE_PY, LE_PZ, LE_DX, LE_DY, LE_DZ, LE_W, LE_IXY, LE_IZO, LE_COMP, LE_C0, LE_C1, LE_BLK };
+enum { PH_IDLE = 0, PH_PLAIN, PH_E13, PH_E14A, PH_E14B };
+
+__device__ __forceinline__ void le_post(float *sle, int lane, const DevDomain &P, Rng &rng, const Ray &r0,
+                                        float px, float py, float pz, float w, int component, int tallyComponent, int order) {
+  sle[LE_PX * 32 + lane] = px; sle[LE_PY * 32 + lane] = py; sle[LE_PZ * 32 + lane] = pz;
+  sle[LE_DX * 32 + lane] = r0.dx; sle[LE_DY * 32 + lane] = r0.dy; sle[LE_DZ * 32 + lane] = r0.dz;
+  sle[LE_W * 32 + lane] = w;
+  sle[LE_IXY * 32 + lane] = __int_as_float(r0.ix | (r0.iy << 16));
+  sle[LE_IZO * 32 + lane] = __int_as_float(r0.iz | (min(order, 65535) << 16));
+  sle[LE_COMP * 32 + lane] = __int_as_float(((component + 1) & 0xff) | (tallyComponent << 8));
+  sle[LE_C0 * 32 + lane] = __uint_as_float(rng.c0); sle[LE_C1 * 32 + lane] = __uint_as_float(rng.c1);
+  sle[LE_BLK * 32 + lane] = __uint_as_float(rng.blk);
+  // the request owns the next ceil(nDir/2) Philox blocks of this photon (one block serves two directions)
+  if (P.opt.useRussianRouletteForIntensity) rng.blk += (uint32_t)((P.nDir + 1) >> 1);
+}
+
 template <bool REG>
-__device__ void local_estimate(const DevDomain &P, const Grid &G, const Tally &T, Rng &rng, uint32_t k0, uint32_t k1,
-                               const Ray &r0, float px, float py, float pz,
-                               float w, int component, int tallyComponent, int order, Counts &cnt) {
-  const int cell = r0.ix + P.nx * (r0.iy + P.ny * r0.iz);
+__device__ void le_run(const DevDomain &P, const Grid &G, const Tally &T, uint32_t k0, uint32_t k1, unsigned posted,
+                       float *sle, unsigned *queue, int lane, Counts &cnt) {
+  const int nDir = P.nDir;
+  const int nTasks = __popc(posted) * nDir;
   const size_t cells = (size_t)P.nx * P.ny * P.nz;
-  float4 u = make_float4(0.f, 0.f, 0.f, 0.f);
-  for (int i = 0; i < P.nDir; ++i) {
-    const float vx = P.viewDir[3 * i], vy = P.viewDir[3 * i + 1], vz = P.viewDir[3 * i + 2];
-    float npf;
-    if (component == 0) {
-      npf = 1.0f / PI32;                                                         // INT:1694
-    } else if (component < 0) {
-      npf = 1.0f / (4.0f * PI32 * fabsf(vz));                                    // INT:1696
-    } else {
-      float proj = r0.dx * vx + r0.dy * vy + r0.dz * vz;                         // INT:1704-1706
-      proj = fminf(fmaxf(proj, -1.0f), 1.0f);
-      const float ang = acosf(proj);
-      const int c = component - 1;
-      const int pidx = (int)__ldg(&P.idx16[cell + cells * c]);
-      const float *tab = ((P.opt.useHybridPhaseFunsForIntenCalcs && order <= P.opt.numOrdersOrigPhaseFunIntenCalcs)
-                              ? P.fwdOrig[c] : P.fwd[c]) + (size_t)(pidx - 1) * P.fwdS[c];
-      const int nS = P.fwdS[c];                                                  // INT:1855-1870
-      const float dTheta = PI32 / (float)(nS - 1);
-      const int ai = (int)(ang / dTheta) + 1;
-      float val;
-      if (ai < nS) {
-        const float wt = 1.0f - (ang - (float)(ai - 1) * dTheta) / dTheta;
-        val = wt * __ldg(&tab[ai - 1]) + (1.0f - wt) * __ldg(&tab[ai]);
+  if (lane == 0) *queue = 0u;
+  __syncwarp();
+  Ray r;
+  r.ox = r.oy = r.oz = 0.0f; r.dx = r.dy = 0.0f; r.dz = 1.0f; r.rx = r.ry = r.rz = FLT_MAX;
+  r.t = 0.0f; r.tx = r.ty = r.tz = FLT_MAX; r.ix = r.iy = r.iz = 0;
+  float ext = 0.0f, tgt = FLT_MAX, w = 0.0f, npf = 0.0f, tauFree = 0.0f, uTest = 0.0f;
+  int phase = PH_IDLE, dir = 0, comps = 0;
+  bool done = false;
+  for (;;) {
+    if (phase == PH_IDLE && !done) {                     // take the next (request, direction) task
+      const int t = (int)atomicAdd(queue, 1u);
+      if (t >= nTasks) {
+        done = true;
       } else {
-        val = __ldg(&tab[nS - 1]);
-      }
-      npf = val / (4.0f * PI32 * fabsf(vz));                                     // INT:1726
-    }
-    Ray r;
-    r.ox = px; r.oy = py; r.oz = pz; r.dx = vx; r.dy = vy; r.dz = vz;
-    r.ix = r0.ix; r.iy = r0.iy; r.iz = r0.iz;
-    ray_start<REG>(r, P, G);
-    int where = 0;
-    float contribution;
-    cnt.leRays++;
-    if (!P.opt.useRussianRouletteForIntensity) {                                 // INT:1729-1752
-      const float tau = ray_trace<REG>(r, P, G, P.extp, false, 0.0f, where, cnt.leCrossings);
-      contribution = w * npf * __expf(-tau);
-    } else {                                                                     // INT:1753-1813
-      if ((i & 1) == 0) u = rng.block(k0, k1);          // one Philox block serves two directions
-      const float uFree = (i & 1) ? u.z : u.x, uTest = (i & 1) ? u.w : u.y;
-      const float tauFree = -__logf(fmaxf(TINY32, uFree));
-      if (PI32 * npf <= P.opt.zetaMin) {                                         // Iwabuchi (2006) Eq 13
-        ray_trace<REG>(r, P, G, P.extp, true, tauFree, where, cnt.leCrossings);
-        contribution = (uTest <= PI32 * npf / P.opt.zetaMin && where == 1) ? w * P.opt.zetaMin / PI32 : 0.0f;
-      } else {                                                                   // Eq 14
-        const float tauMax = -__logf(P.opt.zetaMin / fmaxf(TINY32, PI32 * npf));
-        const float tau = ray_trace<REG>(r, P, G, P.extp, true, tauMax, where, cnt.leCrossings);
-        if (where == 1) {
-          contribution = w * npf * __expf(-tau);
-        } else if (where == 0) {
-          // continue from where the first trace stopped (INT:1793-1795)
-          float qx, qy, qz;
-          ray_position(r, P, qx, qy, qz);
-          r.ox = qx; r.oy = qy; r.oz = qz;
-          ray_start<REG>(r, P, G);
-          ray_trace<REG>(r, P, G, P.extp, true, tauFree, where, cnt.leCrossings);
-          contribution = where == 1 ? w * P.opt.zetaMin / PI32 : 0.0f;
+        const int req = t / nDir;
+        dir = t - req * nDir;
+        const int s = (int)__fns(posted, 0u, req + 1);   // lane that posted the req-th request
+        const float vx = P.viewDir[3 * dir], vy = P.viewDir[3 * dir + 1], vz = P.viewDir[3 * dir + 2];
+        const int ixy = __float_as_int(sle[LE_IXY * 32 + s]), izo = __float_as_int(sle[LE_IZO * 32 + s]);
+        comps = __float_as_int(sle[LE_COMP * 32 + s]);
+        const int component = (comps & 0xff) - 1, order = izo >> 16;
+        r.ix = ixy & 0xffff; r.iy = ixy >> 16; r.iz = izo & 0xffff;
+        w = sle[LE_W * 32 + s];
+        if (component == 0) {
+          npf = 1.0f / PI32;                                                       // INT:1694
+        } else if (component < 0) {
+          npf = 1.0f / (4.0f * PI32 * fabsf(vz));                                  // INT:1696
         } else {
-          contribution = 0.0f;       // left through the surface before tauMax (zIndexF < zIndexMax)
+          float proj = sle[LE_DX * 32 + s] * vx + sle[LE_DY * 32 + s] * vy + sle[LE_DZ * 32 + s] * vz;   // INT:1704-1706
+          proj = fminf(fmaxf(proj, -1.0f), 1.0f);
+          const float ang = acosf(proj);
+          const int c = component - 1;
+          const int cell = r.ix + P.nx * (r.iy + P.ny * r.iz);
+          const int pidx = (int)__ldg(&P.idx16[cell + cells * c]);
+          const float *tab = ((P.opt.useHybridPhaseFunsForIntenCalcs && order <= P.opt.numOrdersOrigPhaseFunIntenCalcs)
+                                  ? P.fwdOrig[c] : P.fwd[c]) + (size_t)(pidx - 1) * P.fwdS[c];
+          const int nS = P.fwdS[c];                                                // INT:1855-1870
+          const float dTheta = PI32 / (float)(nS - 1);
+          const int ai = (int)(ang / dTheta) + 1;
+          float val;
+          if (ai < nS) {
+            const float wt = 1.0f - (ang - (float)(ai - 1) * dTheta) / dTheta;
+            val = wt * __ldg(&tab[ai - 1]) + (1.0f - wt) * __ldg(&tab[ai]);
+          } else {
+            val = __ldg(&tab[nS - 1]);
+          }
+          npf = val / (4.0f * PI32 * fabsf(vz));                                   // INT:1726
+        }
+        r.ox = sle[LE_PX * 32 + s]; r.oy = sle[LE_PY * 32 + s]; r.oz = sle[LE_PZ * 32 + s];
+        r.dx = vx; r.dy = vy; r.dz = vz;
+        ray_start<REG>(r, P, G);
+        ext = 0.0f;
+        cnt.leRays++;
+        if (!P.opt.useRussianRouletteForIntensity) {                               // INT:1729-1752
+          tgt = FLT_MAX; phase = PH_PLAIN;
+        } else {                                                                   // INT:1753-1813
+          Rng q;
+          q.c0 = __float_as_uint(sle[LE_C0 * 32 + s]); q.c1 = __float_as_uint(sle[LE_C1 * 32 + s]);
+          q.blk = __float_as_uint(sle[LE_BLK * 32 + s]) + (uint32_t)(dir >> 1);
+          const float4 u = q.block(k0, k1);
+          const float uFree = (dir & 1) ? u.z : u.x;
+          uTest = (dir & 1) ? u.w : u.y;
+          tauFree = -__logf(fmaxf(TINY32, uFree));
+          if (PI32 * npf <= P.opt.zetaMin) { tgt = tauFree; phase = PH_E13; }       // Iwabuchi (2006) Eq 13
+          else { tgt = -__logf(P.opt.zetaMin / fmaxf(TINY32, PI32 * npf)); phase = PH_E14A; }   // Eq 14
         }
       }
     }
-    if (P.opt.limitIntensityContributions && contribution > P.opt.maxIntensityContribution) {   // INT:1815-1826
-      const int cslot = component < 0 ? 0 : component;
-      atomicAdd(&P.tally[P.offExcess + i + (long long)P.nDir * cslot],
-                (double)(contribution - P.opt.maxIntensityContribution));
-      contribution = P.opt.maxIntensityContribution;
+    if (__all_sync(FULL, done)) break;
+    if (phase != PH_IDLE) {
+      const int ev = march_burst<REG, 4>(r, P, G, P.extp, ext, tgt, cnt.leCrossings);
+      if (ev != MARCH_ON) {
+        float contribution = 0.0f;
+        bool finished = true;
+        if (phase == PH_PLAIN) {
+          contribution = w * npf * __expf(-ext);
+        } else if (phase == PH_E13) {
+          contribution = (ev == MARCH_TOP && uTest <= PI32 * npf / P.opt.zetaMin) ? w * P.opt.zetaMin / PI32 : 0.0f;
+        } else if (phase == PH_E14A) {
+          if (ev == MARCH_TOP) {
+            contribution = w * npf * __expf(-ext);
+          } else if (ev == MARCH_HIT) {                  // continue from where the first trace stopped (INT:1793-1795)
+            float qx, qy, qz;
+            ray_position(r, P, qx, qy, qz);
+            r.ox = qx; r.oy = qy; r.oz = qz;
+            ray_start<REG>(r, P, G);
+            ext = 0.0f; tgt = tauFree; phase = PH_E14B;
+            finished = false;
+          }                                              // left through the surface before tauMax: nothing
+        } else {                                         // PH_E14B
+          contribution = ev == MARCH_TOP ? w * P.opt.zetaMin / PI32 : 0.0f;
+        }
+        if (finished) {
+          const int component = (comps & 0xff) - 1, tallyComponent = comps >> 8;
+          if (P.opt.limitIntensityContributions && contribution > P.opt.maxIntensityContribution) {   // INT:1815-1826
+            const int cslot = component < 0 ? 0 : component;
+            atomicAdd(&P.tally[P.offExcess + dir + (long long)P.nDir * cslot],
+                      (double)(contribution - P.opt.maxIntensityContribution));
+            contribution = P.opt.maxIntensityContribution;
+          }
+          if (contribution != 0.0f) add_intensity(P, T, dir, r.ix + P.nx * r.iy, tallyComponent, contribution);
+          phase = PH_IDLE;
+        }
+      }
     }
-    if (contribution != 0.0f) add_intensity(P, T, i, r.ix + P.nx * r.iy, tallyComponent, contribution);
   }
+  __syncwarp();
 }
 
 template <int THREADS, bool REG, int MINBLOCKS, int BURST, bool LE>
@@ -416,6 +477,12 @@ batch_kernel(const __grid_constant__ DevDomain P, long long nPhotons, uint64_t s
   __syncthreads();
 
   const int lane = threadIdx.x & 31;
+  float *sle = nullptr;
+  unsigned *leQueue = nullptr;
+  if (LE) {
+    sle = smem + plan.leOff + (threadIdx.x >> 5) * (LE_WORDS * 32 + 32);
+    leQueue = (unsigned *)(sle + LE_WORDS * 32);
+  }
   const float *__restrict__ extp = P.extp;
   const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
 
@@ -431,6 +498,7 @@ batch_kernel(const __grid_constant__ DevDomain P, long long nPhotons, uint64_t s
     // =========================== event phase: every lane that is not marching ===========================
     float px = 0.0f, py = 0.0f, pz = 0.0f;
     int comp = 1, cell = 0;
+    bool posted = false;
     if (state == ST_TOP) {                                                     // INT:573-617
       add_flux(P, T, 0, r.ix + P.nx * r.iy, w);
       state = ST_DEAD;
@@ -445,7 +513,7 @@ batch_kernel(const __grid_constant__ DevDomain P, long long nPhotons, uint64_t s
       } else {
         ray_position(r, P, px, py, pz);
         pz = P.fz0;
-        if (LE && P.nDir > 0) local_estimate<REG>(P, G, T, rng, k0, k1, r, px, py, pz, w, 0, 0, order, cnt);
+        if (LE && P.nDir > 0) { le_post(sle, lane, P, rng, r, px, py, pz, w, 0, 0, order); posted = true; }
       }
     } else if (state == ST_SCATTER) {                                          // INT:703-811
       order++;
@@ -466,7 +534,7 @@ batch_kernel(const __grid_constant__ DevDomain P, long long nPhotons, uint64_t s
         w *= ssa;
       }
       ray_position(r, P, px, py, pz);
-      if (LE && P.nDir > 0) local_estimate<REG>(P, G, T, rng, k0, k1, r, px, py, pz, w, comp, comp, order, cnt);   // INT:776-800
+      if (LE && P.nDir > 0) { le_post(sle, lane, P, rng, r, px, py, pz, w, comp, comp, order); posted = true; }   // INT:776-800
       if (P.opt.useRussianRoulette && w < P.opt.russianRouletteW * 0.5f) {     // INT:805-811
         const float uRR = P.nc > 1 ? __fdividef(uNext - lo, fmaxf(hi - lo, TINY32)) : uNext;
         if (uRR >= w / P.opt.russianRouletteW) w = 0.0f; else w = P.opt.russianRouletteW;
@@ -475,6 +543,11 @@ batch_kernel(const __grid_constant__ DevDomain P, long long nPhotons, uint64_t s
         atomicAdd(&sCnt[2], 1u);                                               // killed by roulette
         state = ST_DEAD;
       }
+    }
+    if (LE && P.nDir > 0) {                                                   // the whole warp serves the posted requests
+      const unsigned pm = __ballot_sync(FULL, posted);
+      if (pm) le_run<REG>(P, G, T, k0, k1, pm, sle, leQueue, lane, cnt);
+      posted = false;
     }
     // ---- finished lanes take the next photons: one atomic per warp (getNextPhoton, ILL:561-590) ----
     {
@@ -557,8 +630,7 @@ batch_kernel(const __grid_constant__ DevDomain P, long long nPhotons, uint64_t s
             add_flux(P, T, 2, r.ix + P.nx * r.iy, -1.0f);
             add_vol(P, T, r.ix + P.nx * (r.iy + P.ny * r.iz), -1.0f);
           }
-          if (LE && P.nDir > 0)
-            local_estimate<REG>(P, G, T, rng, k0, k1, r, px, py, pz, w, pz == 0.0f ? 0 : -1, 0, order, cnt);
+          if (LE && P.nDir > 0) { le_post(sle, lane, P, rng, r, px, py, pz, w, pz == 0.0f ? 0 : -1, 0, order); posted = true; }
         }
       } else if (state == ST_SURFACE) {                                        // INT:655-676
         const float mu = sqrtf(fmaxf(u.x, 1.0e-30f));                          // retries on mu ~ 0
@@ -598,6 +670,10 @@ batch_kernel(const __grid_constant__ DevDomain P, long long nPhotons, uint64_t s
       ext = 0.0f;
       ray_start<REG>(r, P, G);
       state = ST_MARCH;
+    }
+    if (LE && P.nDir > 0 && P.opt.LW_flag > 0.0f) {                            // emission at birth (INT:513-542)
+      const unsigned pm = __ballot_sync(FULL, posted);
+      if (pm) le_run<REG>(P, G, T, k0, k1, pm, sle, leQueue, lane, cnt);
     }
 
     // =========================== march phase: bursts until enough lanes are parked ===========================
@@ -669,13 +745,14 @@ static void launch(const DevDomain &P, long long nPhotons, uint64_t seed, uint64
   // atomic hot spot (homogeneous slabs, the 32-column step cloud); large grids spread their
   // atomics over many L2 lines and go straight to the f64 buffer.
   const int cols = P.nx * P.ny, cells = cols * P.nz;
-  mcbfast::SmemPlan plan{-1, -1, -1, -1, 0};
+  mcbfast::SmemPlan plan{-1, -1, -1, -1, -1, 0};
   int off = 0;
   if (!REG) { plan.edgesOff = off; off += P.nx + P.ny + P.nz + 3 + 6 * MCB_GHOST; }
   const int budgetFloats = 9 * 1024;            // 36 KB per block keeps >= 6 blocks/SM resident
   if (3 * cols <= 3 * 1024 && off + 3 * cols <= budgetFloats) { plan.fluxOff = off; off += 3 * cols; }
   if (cells <= 8192 && off + cells <= budgetFloats) { plan.volOff = off; off += cells; }
   if (P.nDir > 0 && cols * P.nDir <= 2048 && off + cols * P.nDir <= budgetFloats) { plan.intOff = off; off += cols * P.nDir; }
+  if (LE) { plan.leOff = off; off += (THREADS / 32) * (LE_WORDS * 32 + 32); }
   plan.totalFloats = off;
   const size_t smem = sizeof(float) * (size_t)off;
   cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
@@ -693,9 +770,12 @@ static void launch(const DevDomain &P, long long nPhotons, uint64_t seed, uint64
 void mcb_launch_fast_batch(const DevDomain &P, long long nPhotons, uint64_t seed, uint64_t firstPhotonId,
                            int numSMs, unsigned long long *workCounter, cudaStream_t stream) {
   if (nPhotons <= 0) return;
-  static int occ = -1, burst = -1;   // register budget / burst length variants (tuning knobs; defaults chosen from measurements)
-  if (occ < 0) { const char *e = getenv("MCB_BLOCKS_PER_SM"); occ = e ? atoi(e) : 8; }
+  // register budget / burst length variants (tuning knobs; defaults chosen from measurements): the flux-only kernel
+  // fits 64 registers (8 CTAs/SM); the local-estimation kernel keeps a second ray per lane and runs best at 6 CTAs/SM (80 registers)
+  static int occEnv = -2, burst = -1;
+  if (occEnv == -2) { const char *e = getenv("MCB_BLOCKS_PER_SM"); occEnv = e ? atoi(e) : -1; }
   if (burst < 0) { const char *e = getenv("MCB_BURST"); burst = e ? atoi(e) : 8; }
+  const int occ = occEnv > 0 ? occEnv : (P.nDir > 0 ? 6 : 8);
 #define MCB_GO(REG, OCC, BURST) do { \
     if (P.nDir > 0) launch<REG, OCC, BURST, true>(P, nPhotons, seed, firstPhotonId, numSMs, workCounter, stream); \
     else launch<REG, OCC, BURST, false>(P, nPhotons, seed, firstPhotonId, numSMs, workCounter, stream); } while (0)
