@@ -87,6 +87,28 @@ int mcb_set_grid(mcb_handle *h, int nx, int ny, int nz,
 /* getInfo_Domain(albedo, totalExt, cumExt, ssa, phaseFuncI), INT:441-443 */
 int mcb_set_optics(mcb_handle *h, int nc, const double *totalExt, const double *cumExt,
                    const double *ssa, const int32_t *phaseIdx, double albedo);
+/* ---- per-wavelength assembly on the device: read_SSPTable's inner loops (OPT:204-299) followed by
+ * getOpticalPropertiesByComponent (OPT:1022-1061).  mcb_set_physical stages the wavelength-independent
+ * state of type(commonDomain) once per run (OPT:63-75): massConc, Reff as (nPhys, nx, ny, nz) with the
+ * component fastest, numConc = numConc(1,1,:) (nz values; NULL without gas components).  Per wavelength
+ * mcb_assemble_optics takes what read_SSPTable reads for one lambdaIndex -- a few hundred bytes per
+ * component -- and builds totalExt, cumExt, ssa, phaseFuncI and the packed copies in HBM; it replaces
+ * mcb_set_optics for that wavelength.  setup != 0 leaves every phase-function index at 1 (OPT:278).     */
+enum { MCB_COMP_VOLEXT = 0, MCB_COMP_ABSXSEC = 1, MCB_COMP_PROFILE = 2 };
+typedef struct {
+  int32_t kind;            /* extType "volExt" | "absXsec" (OPT:203) | explicit horizontally uniform profile  */
+  int32_t physIndex;       /* volExt: 1-based slot of massConc / Reff ("comp-gasComp", OPT:264)               */
+  int32_t nTable;          /* volExt: nReff; otherwise the number of levels                                   */
+  int32_t zLevelBase;      /* 1-based (OPT:201)                                                               */
+  const float *key;        /* volExt: phaseFunctionKeyT(nReff), default real                                   */
+  const double *ext;       /* volExt: ExtinctionT(nReff); absXsec: xsec(nLevels); profile: extinction(nLevels) */
+  const double *ssa;       /* volExt: SingleScatteringAlbedoT(nReff); profile: ssa(nLevels)                    */
+  const int32_t *phaseIdx; /* profile: phaseFunctionIndex(nLevels) (e.g. calc_RayleighScattering, OPT:2052)    */
+} mcb_component;
+int mcb_set_physical(mcb_handle *h, int nPhys, const double *massConc, const double *Reff, const double *numConc);
+int mcb_assemble_optics(mcb_handle *h, int nc, const mcb_component *comps, int setup, double albedo);
+/* the dense arrays currently in HBM, in the domain's layout (any pointer may be NULL) */
+int mcb_get_optics(mcb_handle *h, double *totalExt, double *cumExt, double *ssa, int32_t *phaseIdx);
 /* getInfo_Domain(inversePhaseFuncs) INT:443 <- tabulateInversePhaseFunctions INT:280 */
 int mcb_set_inverse_table(mcb_handle *h, int comp, int nS, int nE, const float *T);
 /* getInfo_Domain(tabPhase, tabOrigPhase) INT:1672-1673 <- tabulateForwardPhaseFunctions INT:282 */

@@ -28,6 +28,15 @@ class mcb_options(C.Structure):
                 ("arithmetic", C.c_int32), ("reserved", C.c_int32 * 5)]
 
 
+class mcb_component(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("physIndex", C.c_int32), ("nTable", C.c_int32), ("zLevelBase", C.c_int32),
+                ("key", C.POINTER(C.c_float)), ("ext", C.POINTER(C.c_double)), ("ssa", C.POINTER(C.c_double)),
+                ("phaseIdx", C.POINTER(C.c_int32))]
+
+
+MCB_COMP_VOLEXT, MCB_COMP_ABSXSEC, MCB_COMP_PROFILE = 0, 1, 2
+
+
 class mcb_counters(C.Structure):
     _fields_ = [(n, C.c_int64) for n in ("photons", "crossings", "scatters", "surfaceHits", "topExits", "bad",
                                          "leRays", "leCrossings", "rouletteKills")] + [("reserved", C.c_int64 * 7)]
@@ -45,7 +54,7 @@ assert EVENT_DTYPE.itemsize == 96
 
 # every symbol include/mcbrat_cuda.h declares
 EXPORTS = ["mcb_create", "mcb_destroy", "mcb_last_error", "mcb_version", "mcb_set_stream", "mcb_synchronize",
-           "mcb_set_grid", "mcb_set_optics", "mcb_set_inverse_table", "mcb_set_forward_table", "mcb_set_views",
+           "mcb_set_grid", "mcb_set_optics", "mcb_set_physical", "mcb_assemble_optics", "mcb_get_optics", "mcb_set_inverse_table", "mcb_set_forward_table", "mcb_set_views",
            "mcb_default_options", "mcb_set_options", "mcb_set_solar_source", "mcb_set_thermal_source",
            "mcb_build_thermal_source", "mcb_get_thermal_source", "mcb_run_batch", "mcb_accumulate_batch", "mcb_stats_reset", "mcb_run_batches",
            "mcb_stats_buffer", "mcb_get_statistics", "mcb_last_batch_ms",
@@ -76,6 +85,9 @@ def load() -> C.CDLL:
     lib.mcb_synchronize.argtypes = [_vp]
     lib.mcb_set_grid.argtypes = [_vp, C.c_int, C.c_int, C.c_int, _dp, _dp, _dp]
     lib.mcb_set_optics.argtypes = [_vp, C.c_int, _dp, _dp, _dp, _ip, C.c_double]
+    lib.mcb_set_physical.argtypes = [_vp, C.c_int, _dp, _dp, _dp]
+    lib.mcb_assemble_optics.argtypes = [_vp, C.c_int, C.POINTER(mcb_component), C.c_int, C.c_double]
+    lib.mcb_get_optics.argtypes = [_vp, _dp, _dp, _dp, _ip]
     lib.mcb_set_inverse_table.argtypes = [_vp, C.c_int, C.c_int, C.c_int, _fp]
     lib.mcb_set_forward_table.argtypes = [_vp, C.c_int, C.c_int, C.c_int, _fp, _fp]
     lib.mcb_set_views.argtypes = [_vp, C.c_int, _fp]

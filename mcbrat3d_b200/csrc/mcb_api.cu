@@ -25,6 +25,12 @@ long long mcb_emission_tiles(long long cells);
 void mcb_launch_emission_cdf(const DevDomain &P, const double *temps, double a, double b, double lambda5, void *scratch,
                              double *cdf, int *flags, int numSMs, cudaStream_t stream);
 void mcb_launch_emission_normalise(double *cdf, long long cells, const void *total, int numSMs, cudaStream_t stream);
+void mcb_launch_assemble_optics(int nx, int ny, int nz, int nc, const int *kind, const int *physIndex, const int *nTable,
+                                const int *zLevelBase, const float *const *key, const double *const *ext,
+                                const double *const *ssa, const int32_t *const *idx, const float *kmin, const float *kmax,
+                                int nPhys, const double *massConc, const double *Reff, const double *numConc, int setup,
+                                double *totalExt, double *cumExt, double *ssaOut, int32_t *phaseIdx, int *flags,
+                                int numSMs, cudaStream_t stream);
 long long mcb_stats_elements(const DevDomain &P);
 void mcb_launch_stats_accumulate(const DevDomain &P, const float *results, double *stats, double weight, int numSMs,
                                  cudaStream_t stream);
@@ -51,6 +57,8 @@ struct mcb_handle {
   int invE[MCB_MAX_COMP] = {0}, fwdE[MCB_MAX_COMP] = {0};
   void *dVoxelCDF = nullptr, *dTemps = nullptr, *dScratch = nullptr, *dResults = nullptr;
   int *dFlags = nullptr;
+  void *dMassConc = nullptr, *dReff = nullptr, *dNumConc = nullptr, *dAsmTables = nullptr;   // physical state (commonDomain)
+  int nPhys = 0; bool havePhysical = false, haveNumConc = false;
   void *dStats = nullptr, *dStatsOut = nullptr; long long nStats = 0;   // batch statistics: moments, finalised copy
   double *dTally = nullptr; long long nTally = 0;
   unsigned long long *dCounters = nullptr;     // CNT_N counters + 1 work counter
@@ -147,7 +155,8 @@ int mcb_destroy(mcb_handle *h) {
   cudaStreamSynchronize(h->stream);
   void *slots[] = {h->dXE, h->dYE, h->dZE, h->dTotalExt, h->dCumExt, h->dSsa, h->dPhaseIdx,
                    h->dExt32, h->dCum32, h->dSsa32, h->dIdx16, h->dVoxelCDF, h->dTally, h->dCounters,
-                   h->dTemps, h->dScratch, h->dResults, (void *)h->dFlags, h->dStats, h->dStatsOut};
+                   h->dTemps, h->dScratch, h->dResults, (void *)h->dFlags, h->dStats, h->dStatsOut,
+                   h->dMassConc, h->dReff, h->dNumConc, h->dAsmTables};
   for (void *p : slots) if (p) cudaFree(p);
   for (int c = 0; c < MCB_MAX_COMP; ++c) {
     if (h->dInv[c]) cudaFree(h->dInv[c]);
@@ -231,9 +240,11 @@ int mcb_set_grid(mcb_handle *h, int nx, int ny, int nz,
   P.ghostOrigin = MCB_GHOST + P.nxp * (MCB_GHOST + P.nyp * MCB_GHOST);
   magic_divisor((uint32_t)P.nxp * (uint32_t)P.nyp, &P.divSliceM, &P.divSliceS);
   magic_divisor((uint32_t)P.nxp, &P.divRowM, &P.divRowS);
-  h->haveGrid = true; h->haveOptics = false; h->haveSource = false;
+  h->haveGrid = true; h->haveOptics = false; h->haveSource = false; h->havePhysical = false;
   return 0;
 }
+
+static int finish_optics(mcb_handle *h, int nc, double albedo, bool zeroFlags = true);
 
 int mcb_set_optics(mcb_handle *h, int nc, const double *totalExt, const double *cumExt,
                    const double *ssa, const int32_t *phaseIdx, double albedo) {
@@ -252,6 +263,14 @@ int mcb_set_optics(mcb_handle *h, int nc, const double *totalExt, const double *
   if (stage_async(h, &h->dCumExt, cumExt, sizeof(double) * cells * nc)) return 1;
   if (stage_async(h, &h->dSsa, ssa, sizeof(double) * cells * nc)) return 1;
   if (stage_async(h, &h->dPhaseIdx, phaseIdx, sizeof(int32_t) * cells * nc)) return 1;
+  return finish_optics(h, nc, albedo);
+}
+
+// The dense f64 arrays are in HBM (uploaded by mcb_set_optics or built by mcb_assemble_optics): derive the packed
+// single-precision copies, run the argument checks, find maxval(totalExt), publish the pointers.
+static int finish_optics(mcb_handle *h, int nc, double albedo, bool zeroFlags) {
+  DevDomain &P = h->P;
+  const size_t cells = (size_t)P.nx * P.ny * P.nz;
   const size_t padded = (size_t)P.nxp * P.nyp * (P.nz + 2 * MCB_GHOST);
   if (reserve(h, &h->dExt32, sizeof(float) * padded)) return 1;
   if (reserve(h, &h->dCum32, sizeof(float) * cells * nc)) return 1;
@@ -262,7 +281,7 @@ int mcb_set_optics(mcb_handle *h, int nc, const double *totalExt, const double *
   P.ssa = (const double *)h->dSsa; P.phaseIdx = (const int32_t *)h->dPhaseIdx;
   P.extp = (const float *)h->dExt32 + P.ghostOrigin; P.cum32 = (const float *)h->dCum32;
   P.ssa32 = (const float *)h->dSsa32; P.idx16 = (const uint16_t *)h->dIdx16;
-  CK(h, cudaMemsetAsync(h->dFlags, 0, sizeof(int) * 4, h->stream));
+  if (zeroFlags) CK(h, cudaMemsetAsync(h->dFlags, 0, sizeof(int) * 4, h->stream));
   mcb_launch_pack_optics(P, (float *)h->dExt32, (float *)h->dCum32, (float *)h->dSsa32, (uint16_t *)h->dIdx16, h->dFlags,
                          h->numSMs, h->stream);
   CK(h, cudaGetLastError());
@@ -274,12 +293,106 @@ int mcb_set_optics(mcb_handle *h, int nc, const double *totalExt, const double *
     double emax; memcpy(&emax, &flags4[2], sizeof(double));
     P.maxExtinction = (float)emax;                                       // INT:448, default real
   }
+  if (flags & 16) FAIL(h, "read_SSPTable: Effective radius outside of table range");
   if (flags & 1) FAIL(h, "addOpticalComponent: extinction must be >= 0.");
   if (flags & 2) FAIL(h, "addOpticalComponent: singleScatteringAlbedo must be between 0 and 1");
   if (flags & 4) FAIL(h, "addOpticalComponent: phase function index is out of bounds");
   for (int c = 0; c < MCB_MAX_COMP; ++c) { h->haveInv[c] = false; h->haveFwd[c] = false; }
   h->haveOptics = true;
   return 0;
+}
+
+// ---- per-wavelength assembly on the device (read_SSPTable OPT:147-343 + getOpticalPropertiesByComponent) ----
+int mcb_set_physical(mcb_handle *h, int nPhys, const double *massConc, const double *Reff, const double *numConc) {
+  if (!h) return 1;
+  if (!h->haveGrid) FAIL(h, "mcb_set_physical: call mcb_set_grid first");
+  if (nPhys < 0 || (nPhys > 0 && (!massConc || !Reff))) FAIL(h, "mcb_set_physical: bad arguments");
+  const size_t cells = (size_t)h->P.nx * h->P.ny * h->P.nz;
+  h->havePhysical = false;
+  if (nPhys > 0) {
+    if (stage_async(h, &h->dMassConc, massConc, sizeof(double) * cells * nPhys)) return 1;
+    if (stage_async(h, &h->dReff, Reff, sizeof(double) * cells * nPhys)) return 1;
+  }
+  h->haveNumConc = numConc != nullptr;
+  if (numConc && stage_async(h, &h->dNumConc, numConc, sizeof(double) * h->P.nz)) return 1;
+  if (settle(h)) return 1;
+  h->nPhys = nPhys; h->havePhysical = true;
+  return 0;
+}
+
+int mcb_assemble_optics(mcb_handle *h, int nc, const mcb_component *comps, int setup, double albedo) {
+  if (!h) return 1;
+  if (!h->havePhysical) FAIL(h, "read_SSPTable: the common physical domain has not been staged (mcb_set_physical)");
+  if (nc < 1 || nc > MCB_MAX_COMP || !comps) FAIL(h, "mcb_assemble_optics: number of components must be 1..%d", MCB_MAX_COMP);
+  DevDomain &P = h->P;
+  const size_t cells = (size_t)P.nx * P.ny * P.nz;
+  h->haveOptics = false;
+  // argument checks that need no data, then one contiguous upload of the small per-wavelength tables
+  size_t bytes = 0;
+  std::vector<size_t> offKey(nc), offExt(nc), offSsa(nc), offIdx(nc);
+  int kind[MCB_MAX_COMP], phys[MCB_MAX_COMP], nTab[MCB_MAX_COMP], zBase[MCB_MAX_COMP];
+  float kmin[MCB_MAX_COMP], kmax[MCB_MAX_COMP];
+  for (int c = 0; c < nc; ++c) {
+    const mcb_component &q = comps[c];
+    kind[c] = q.kind; phys[c] = q.physIndex; nTab[c] = q.nTable; zBase[c] = q.zLevelBase; kmin[c] = kmax[c] = 0.0f;
+    if (q.kind < 0 || q.kind > 2) FAIL(h, "read_SSPTable: unrecognizable extType");
+    if (q.nTable < 1 || !q.ext) FAIL(h, "mcb_assemble_optics: component %d has no table", c + 1);
+    const int nLev = q.kind == MCB_COMP_VOLEXT ? P.nz : q.nTable;
+    if (q.zLevelBase < 1 || q.zLevelBase + nLev - 1 > P.nz)
+      FAIL(h, "addOpticalComponent: arrays don't fit the vertical extent of the domain.");
+    if (q.kind == MCB_COMP_VOLEXT) {
+      if (q.physIndex < 1 || q.physIndex > h->nPhys || q.nTable < 2 || !q.key || !q.ssa)
+        FAIL(h, "mcb_assemble_optics: component %d: bad volExt description", c + 1);
+      kmin[c] = kmax[c] = q.key[0];
+      for (int i = 0; i < q.nTable; ++i) { kmin[c] = std::fmin(kmin[c], q.key[i]); kmax[c] = std::fmax(kmax[c], q.key[i]); }
+    }
+    if (q.kind == MCB_COMP_ABSXSEC && !h->haveNumConc) FAIL(h, "read_SSPTable: absXsec component needs numConc");
+    if (q.kind == MCB_COMP_PROFILE && (!q.ssa || !q.phaseIdx)) FAIL(h, "mcb_assemble_optics: component %d: bad profile", c + 1);
+    auto take = [&](size_t n) { const size_t o = bytes; bytes += (n + 15) & ~(size_t)15; return o; };
+    offExt[c] = take(sizeof(double) * q.nTable);
+    offSsa[c] = q.ssa ? take(sizeof(double) * q.nTable) : 0;
+    offKey[c] = q.key && q.kind == MCB_COMP_VOLEXT ? take(sizeof(float) * q.nTable) : 0;
+    offIdx[c] = q.phaseIdx && q.kind == MCB_COMP_PROFILE ? take(sizeof(int32_t) * q.nTable) : 0;
+  }
+  std::vector<char> blob(bytes, 0);
+  for (int c = 0; c < nc; ++c) {
+    const mcb_component &q = comps[c];
+    memcpy(blob.data() + offExt[c], q.ext, sizeof(double) * q.nTable);
+    if (q.ssa) memcpy(blob.data() + offSsa[c], q.ssa, sizeof(double) * q.nTable);
+    if (q.key && q.kind == MCB_COMP_VOLEXT) memcpy(blob.data() + offKey[c], q.key, sizeof(float) * q.nTable);
+    if (q.phaseIdx && q.kind == MCB_COMP_PROFILE) memcpy(blob.data() + offIdx[c], q.phaseIdx, sizeof(int32_t) * q.nTable);
+  }
+  if (stage(h, &h->dAsmTables, blob.data(), bytes)) return 1;
+  const char *base = (const char *)h->dAsmTables;
+  const float *dKey[MCB_MAX_COMP]; const double *dExt[MCB_MAX_COMP], *dSsa[MCB_MAX_COMP]; const int32_t *dIdx[MCB_MAX_COMP];
+  for (int c = 0; c < nc; ++c) {
+    dExt[c] = (const double *)(base + offExt[c]); dSsa[c] = (const double *)(base + offSsa[c]);
+    dKey[c] = (const float *)(base + offKey[c]); dIdx[c] = (const int32_t *)(base + offIdx[c]);
+  }
+  if (reserve(h, &h->dTotalExt, sizeof(double) * cells)) return 1;
+  if (reserve(h, &h->dCumExt, sizeof(double) * cells * nc)) return 1;
+  if (reserve(h, &h->dSsa, sizeof(double) * cells * nc)) return 1;
+  if (reserve(h, &h->dPhaseIdx, sizeof(int32_t) * cells * nc)) return 1;
+  CK(h, cudaMemsetAsync(h->dFlags, 0, sizeof(int) * 4, h->stream));
+  mcb_launch_assemble_optics(P.nx, P.ny, P.nz, nc, kind, phys, nTab, zBase, dKey, dExt, dSsa, dIdx, kmin, kmax, h->nPhys,
+                             (const double *)h->dMassConc, (const double *)h->dReff, (const double *)h->dNumConc, setup,
+                             (double *)h->dTotalExt, (double *)h->dCumExt, (double *)h->dSsa, (int32_t *)h->dPhaseIdx,
+                             h->dFlags, h->numSMs, h->stream);
+  CK(h, cudaGetLastError());
+  return finish_optics(h, nc, albedo, false);
+}
+
+// the dense arrays currently staged, in the domain's layout (any pointer may be NULL)
+int mcb_get_optics(mcb_handle *h, double *totalExt, double *cumExt, double *ssa, int32_t *phaseIdx) {
+  if (!h) return 1;
+  if (!h->haveOptics) FAIL(h, "mcb_get_optics: no optical properties are staged");
+  CK(h, cudaSetDevice(h->device));
+  const size_t cells = (size_t)h->P.nx * h->P.ny * h->P.nz, nc = (size_t)h->P.nc;
+  if (totalExt) CK(h, cudaMemcpyAsync(totalExt, h->dTotalExt, sizeof(double) * cells, cudaMemcpyDeviceToHost, h->stream));
+  if (cumExt) CK(h, cudaMemcpyAsync(cumExt, h->dCumExt, sizeof(double) * cells * nc, cudaMemcpyDeviceToHost, h->stream));
+  if (ssa) CK(h, cudaMemcpyAsync(ssa, h->dSsa, sizeof(double) * cells * nc, cudaMemcpyDeviceToHost, h->stream));
+  if (phaseIdx) CK(h, cudaMemcpyAsync(phaseIdx, h->dPhaseIdx, sizeof(int32_t) * cells * nc, cudaMemcpyDeviceToHost, h->stream));
+  return settle(h);
 }
 
 int mcb_set_inverse_table(mcb_handle *h, int comp, int nS, int nE, const float *T) {

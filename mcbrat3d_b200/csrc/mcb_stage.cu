@@ -16,7 +16,7 @@
 
 namespace mcbstage {
 
-enum { FLAG_EXT = 1, FLAG_SSA = 2, FLAG_IDX = 4, FLAG_TEMP = 8 };
+enum { FLAG_EXT = 1, FLAG_SSA = 2, FLAG_IDX = 4, FLAG_TEMP = 8, FLAG_REFF = 16 };
 
 // flags[0]: argument-check bits; flags[2..3] (as one u64): bit pattern of maxval(totalExt) -- non-negative
 // doubles order like their bit patterns, so an integer atomicMax does the reduction (INT:448)
@@ -57,6 +57,76 @@ __global__ void pack_components_kernel(const double *__restrict__ cumExt, const 
     if (!(s >= 0.0 && s <= 1.0)) bad |= FLAG_SSA;
     if (ix < 0 || ix > 65535) bad |= FLAG_IDX;
     c32[p] = (float)cumExt[p]; s32[p] = (float)s; i16[p] = (uint16_t)ix;
+  }
+  if (bad) atomicOr(flags, bad);
+}
+
+// ---------------------------------------------------------------------------------------------
+// per-wavelength optical-property assembly: read_SSPTable's inner loops (OPT:204-299) followed by
+// getOpticalPropertiesByComponent (OPT:1022-1061), one thread per cell.  The physical state (mass
+// concentration, effective radius, number concentration) is staged once per run; per wavelength only the
+// few-hundred-byte single-scattering tables cross PCIe and the dense arrays are produced in HBM.
+// ---------------------------------------------------------------------------------------------
+struct AssembleComp {
+  int kind, physIndex, nTable, zLevelBase;
+  const float *key; const double *ext, *ssa; const int32_t *idx;
+  float kmin, kmax;
+};
+struct AssembleArgs { int nc; AssembleComp c[MCB_MAX_COMP]; };
+
+__global__ void assemble_optics_kernel(int nx, int ny, int nz, AssembleArgs A, int nPhys,
+                                       const double *__restrict__ massConc, const double *__restrict__ Reff,
+                                       const double *__restrict__ numConc, int setup,
+                                       double *__restrict__ totalExt, double *__restrict__ cumExt,
+                                       double *__restrict__ ssa, int32_t *__restrict__ phaseIdx, int *flags) {
+  const long long cols = (long long)nx * ny, cells = cols * nz;
+  int bad = 0;
+  for (long long cell = blockIdx.x * (long long)blockDim.x + threadIdx.x; cell < cells; cell += (long long)gridDim.x * blockDim.x) {
+    const int iz = (int)(cell / cols);
+    double e[MCB_MAX_COMP];
+    double run = 0.0;
+#pragma unroll
+    for (int c = 0; c < MCB_MAX_COMP; ++c) {
+      if (c >= A.nc) break;
+      const AssembleComp &q = A.c[c];
+      double ext = 0.0, w = 0.0;
+      int32_t pi = 0;
+      if (q.kind == 0) {                                                       // "volExt", OPT:260-292
+        pi = 1;                                                                // OPT:253-255 defaults
+        const double m = massConc[(long long)(q.physIndex - 1) + (long long)nPhys * cell];
+        const double re = Reff[(long long)(q.physIndex - 1) + (long long)nPhys * cell];
+        if (m > 0.0 && re < (double)q.kmax && re >= (double)q.kmin) {
+          int lo = 0, hi = q.nTable;                                           // findIndex(Reff, REAL(key,8)), NUM:206-260
+          while (!(lo == q.nTable || hi <= lo + 1)) {
+            const int mid = (lo + hi) / 2;
+            if (re >= (double)q.key[mid - 1]) lo = mid; else hi = mid;
+          }
+          const double f = (re - (double)q.key[lo - 1]) / (double)__fsub_rn(q.key[lo], q.key[lo - 1]);   // OPT:272
+          ext = m * ((1 - f) * q.ext[lo - 1] + f * q.ext[lo]);
+          w = (1 - f) * q.ssa[lo - 1] + f * q.ssa[lo];
+          if (!setup) pi = f < 0.5 ? lo : lo + 1;                              // OPT:279-285
+        } else if (m > 0.0) {
+          bad |= FLAG_REFF;                                                    // OPT:288-289
+        }
+      } else {
+        const int k = iz - (q.zLevelBase - 1);
+        if (k >= 0 && k < q.nTable) {
+          if (q.kind == 1) { ext = q.ext[k] * numConc[k] * 1000.0; w = 0.0; pi = 1; }   // "absXsec", OPT:223-227
+          else { ext = q.ext[k]; w = q.ssa[k]; pi = q.idx[k]; }                // horizontally uniform profile
+        }
+      }
+      run = c == 0 ? ext : run + ext;                                          // OPT:1055-1057
+      e[c] = run;
+      ssa[cell + cells * c] = w;
+      phaseIdx[cell + cells * c] = pi;
+    }
+    const double total = run;
+    totalExt[cell] = total;
+#pragma unroll
+    for (int c = 0; c < MCB_MAX_COMP; ++c) {
+      if (c >= A.nc) break;
+      cumExt[cell + cells * c] = total > 2.2250738585072014e-308 ? e[c] / total : e[c];   // OPT:1059-1061
+    }
   }
   if (bad) atomicOr(flags, bad);
 }
@@ -314,6 +384,25 @@ void mcb_launch_pack_optics(const DevDomain &P, float *e32, float *c32, float *s
                                                                                          MCB_GHOST, flags);
   mcbstage::pack_components_kernel<<<stream_grid(n, 256, numSMs), 256, 0, stream>>>(P.cumExt, P.ssa, P.phaseIdx, c32, s32,
                                                                                     i16, n, flags);
+}
+
+// comps: kind, physIndex, nTable, zLevelBase + device pointers to the small tables (already staged)
+void mcb_launch_assemble_optics(int nx, int ny, int nz, int nc, const int *kind, const int *physIndex, const int *nTable,
+                                const int *zLevelBase, const float *const *key, const double *const *ext,
+                                const double *const *ssa, const int32_t *const *idx, const float *kmin, const float *kmax,
+                                int nPhys, const double *massConc, const double *Reff, const double *numConc, int setup,
+                                double *totalExt, double *cumExt, double *ssaOut, int32_t *phaseIdx, int *flags,
+                                int numSMs, cudaStream_t stream) {
+  mcbstage::AssembleArgs A;
+  A.nc = nc;
+  for (int c = 0; c < nc; ++c) {
+    A.c[c].kind = kind[c]; A.c[c].physIndex = physIndex[c]; A.c[c].nTable = nTable[c]; A.c[c].zLevelBase = zLevelBase[c];
+    A.c[c].key = key[c]; A.c[c].ext = ext[c]; A.c[c].ssa = ssa[c]; A.c[c].idx = idx[c];
+    A.c[c].kmin = kmin[c]; A.c[c].kmax = kmax[c];
+  }
+  const long long cells = (long long)nx * ny * nz;
+  mcbstage::assemble_optics_kernel<<<stream_grid(cells, 256, numSMs), 256, 0, stream>>>(
+      nx, ny, nz, A, nPhys, massConc, Reff, numConc, setup, totalExt, cumExt, ssaOut, phaseIdx, flags);
 }
 
 void mcb_launch_normalise(const DevDomain &P, float numPhotons, float *out, int numSMs, cudaStream_t stream) {

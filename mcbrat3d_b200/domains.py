@@ -194,3 +194,46 @@ def bench_domain(nxy=325, nz=150, seed=5, ssa=0.999) -> Tuple[Domain, Dict]:
                           new_PhaseFunctionTable([rayleigh()], key=[0.0]))
     d.getOpticalPropertiesByComponent()
     return d, dict(name="C5_bench", solarMu=0.5, solarAzimuth=0.0, LW_flag=-1.0, numPhotonsPerBatch=10000)
+
+
+def broadband_problem(nxy=24, nz=20, nLambda=6, seed=11, lw=False):
+    """C5-style multi-wavelength input (``run/I3RC_bench_SW.deck`` / ``_LW.deck``): the wavelength-independent physical
+    state of ``type(commonDomain)`` (liquid-water mass concentration and effective radius of one cloud component,
+    molecular number concentration and density profiles) plus an in-memory SSP table with ``nLambda`` wavelength bins
+    (per bin: extinction / albedo of the cloud as functions of effective radius, a keyed set of phase functions, a gas
+    absorption cross-section profile, a surface albedo).  Returns (commonDomain, [SSPTable], case)."""
+    from .opticalProperties import SSPComponent, SSPTable, commonDomain, light_spd
+    rng = np.random.default_rng(seed)
+    dxy, dz = 0.0625, 0.03125 * 4
+    x = dxy * np.arange(nxy + 1, dtype=np.float64)
+    z = dz * np.arange(nz + 1, dtype=np.float64)
+    zc = 0.5 * (z[1:] + z[:-1])
+    g = _gaussian_field(64, rng)[:nxy, :nxy]
+    lwp = np.where(g > np.quantile(g, 0.35), np.exp(0.6 * g), 0.0)               # relative liquid water path per column
+    base, top = nz // 4, nz // 4 + max(2, nz // 3)
+    mass = np.zeros((nz, nxy, nxy)); reff = np.zeros((nz, nxy, nxy))
+    for k in range(base, top):
+        adiab = (k - base + 0.5) / (top - base)                                  # adiabatic-like growth with height
+        mass[k] = 0.06 * lwp.T * adiab                                           # g m^-3
+        reff[k] = np.where(lwp.T > 0, 6.0 + 9.0 * adiab ** (1.0 / 3.0) + 0.5 * rng.random((nxy, nxy)), 0.0)
+    numConc = np.broadcast_to((2.55e25 * np.exp(-zc / 8.0))[:, None, None], (nz, nxy, nxy)).copy()
+    rho = np.broadcast_to((1.225 * np.exp(-zc / 8.0))[:, None, None], (nz, nxy, nxy)).copy()
+    temps = np.broadcast_to((288.0 - 6.5 * zc)[:, None, None], (nz, nxy, nxy)).copy()
+    common = commonDomain(x, x, z, temps, mass[..., None].copy(), reff[..., None].copy(), numConc, rho)
+    lam = np.linspace(8.0, 12.0, nLambda) if lw else np.linspace(0.45, 2.1, nLambda)      # microns
+    freq = light_spd * 1e6 / lam
+    key = np.array([4.0, 6.0, 8.0, 10.0, 13.0, 16.0, 20.0], dtype=f32)
+    extT = np.empty((nLambda, key.size)); ssaT = np.empty((nLambda, key.size)); tabs = []
+    for i in range(nLambda):
+        qext = 2.0 + 0.6 * (lam[i] / key.astype(np.float64)) ** 0.7                      # extinction efficiency ~ 2
+        extT[i] = 750.0 * qext / key.astype(np.float64)                                  # km^-1 per (g m^-3): 3 Q / (4 rho_w r)
+        absorb = (0.02 + 0.4 * (lam[i] / 12.0) ** 2) if lw else 1e-4 * np.exp(3.2 * (lam[i] - 0.45))
+        ssaT[i] = np.clip(1.0 - absorb * np.sqrt(key.astype(np.float64) / 10.0), 0.3, 1.0)
+        tabs.append(new_PhaseFunctionTable([henyeyGreenstein(min(0.8 + 0.005 * float(k), 0.9), 48) for k in key],
+                                           key=key.astype(np.float64)))
+    xsec = np.outer(1e-29 * (1.0 + np.sin(np.arange(nLambda)) ** 2), np.exp(-zc / 2.0))  # m^2 per molecule, (nLambda, nz)
+    albedo = np.full(nLambda, 0.02 if lw else 0.06) + 0.01 * np.arange(nLambda) / max(1, nLambda - 1)
+    table = SSPTable(freq, albedo, [SSPComponent("cloud", "volExt", 1, key, extT, ssaT, tables=tabs),
+                                    SSPComponent("gas", "absXsec", 1, xsec=xsec)])
+    return common, [table], dict(name="C5_broadband", solarMu=0.5, solarAzimuth=0.0, LW_flag=1.0 if lw else -1.0,
+                                 numLambda=nLambda, surfaceTemp=290.0)

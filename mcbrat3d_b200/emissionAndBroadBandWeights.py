@@ -45,7 +45,7 @@ def emission_weighting_device(thisDomain, theseWeights: Weights, sfcTemp: float,
     from . import _lib
     from .monteCarloRadiativeTransfer import _stage_domain
     g = thisIntegrator
-    if thisDomain.totalExt is None:
+    if thisDomain.totalExt is None and getattr(thisDomain, "deviceOwner", None) is None:
         raise ValueError("emission_weighting: domain hasn't been initialized.")
     _stage_domain(g, thisDomain)
     temps = np.ascontiguousarray(thisDomain.temps, dtype=np.float64)

@@ -170,9 +170,14 @@ def specifyParameters(thisIntegrator: integrator, minForwardTableSize=None, minI
 
 def _stage_domain(g: integrator, d: Domain) -> None:
     """What ``computeRT`` copies out of the domain every batch (INT:434-443) -- staged once."""
-    if d.totalExt is None:
+    if getattr(d, "deviceOwner", None) is not None:          # assembled in this integrator's HBM (read_SSPTable)
+        key = ("device", id(d))
+        if d.deviceOwner is not g or g._stagedDomain != key:
+            raise McbError("computeRadiativeTransfer: the domain was assembled on another integrator or has been replaced")
+    elif d.totalExt is None:
         d.getOpticalPropertiesByComponent()
-    key = (id(d), id(d.totalExt))
+    if getattr(d, "deviceOwner", None) is None:
+        key = (id(d), id(d.totalExt))
     if g._stagedDomain != key:
         if (d.numX, d.numY, d.numZ) != (g.numX, g.numY, g.numZ):
             raise McbError("computeRadiativeTransfer: domain and integrator grids differ")

@@ -59,6 +59,7 @@ class Domain:
         self.xyRegularlySpaced = regular(self.xPosition, 2) and regular(self.yPosition, 2)   # OPT:541-545
         self.zRegularlySpaced = regular(self.zPosition, 2)
         self.components: List[opticalComponent] = []
+        self.deviceOwner = None            # integrator whose HBM holds the dense arrays (read_SSPTable on the device)
         self.totalExt: Optional[np.ndarray] = None
         self.cumulativeExt: Optional[np.ndarray] = None
         self.ssa: Optional[np.ndarray] = None
@@ -236,3 +237,178 @@ def computeHybridPhaseFunctions(angles, values, GaussianWidth):
         newValues[e, :t] = P0 * gaussianValues[:t]
         newValues[e, t:] = v[t:]
     return newValues
+
+
+# ---------------------------------------------------------------------------------------
+# type(commonDomain) (OPT:63-75) and read_SSPTable (OPT:147-343)
+# ---------------------------------------------------------------------------------------
+light_spd = 2.99792458E8                   # OPT:27 [m/s]
+
+
+@dataclass
+class commonDomain:
+    """OPT:63-75: what every wavelength shares.  ``massConc``/``Reff`` are (nz, ny, nx, nPhys) so that the C order
+    of the buffer is the reference's ``(component, x, y, z)``; ``rho``/``numConc`` are (nz, ny, nx) of which the
+    reference only ever reads column (1,1,:) (OPT:223, 324)."""
+    xPosition: np.ndarray
+    yPosition: np.ndarray
+    zPosition: np.ndarray
+    temps: np.ndarray
+    massConc: np.ndarray
+    Reff: np.ndarray
+    numConc: Optional[np.ndarray] = None
+    rho: Optional[np.ndarray] = None
+
+
+@dataclass
+class SSPComponent:
+    """One ``ComponentN_*`` group of a single-scattering-property file (OPT:200-246)."""
+    name: str
+    extType: str                              # "volExt" | "absXsec"
+    zLevelBase: int = 1
+    key: Optional[np.ndarray] = None          # phaseFunctionKeyT(nReff), default real
+    extinctionT: Optional[np.ndarray] = None  # (nLambda, nReff)
+    singleScatteringAlbedoT: Optional[np.ndarray] = None
+    xsec: Optional[np.ndarray] = None         # (nLambda, nz)
+    tables: Optional[List[phaseFunctionTable]] = None   # per lambda: read_PhaseFunctionTable (OPT:257)
+
+
+@dataclass
+class SSPTable:
+    """In-memory image of one SSP file (the netCDF container itself is out of scope)."""
+    f_grid: np.ndarray                        # frequencies [Hz], one per lambda index
+    surfaceAlbedo: np.ndarray
+    components: List[SSPComponent]
+
+
+def calc_RayleighScattering(lambda_um, rho, N):
+    """OPT:2052-2086: returns (ext, ssa, phaseInd, table) for one column."""
+    from .scatteringPhaseFunctions import new_PhaseFunctionTable, rayleigh
+    f = 1.060816681; rho0 = 1.275
+    lam = float(lambda_um)
+    Pi8 = np.float64(Pi)                                        # the module's Pi is default real (OPT:26)
+    mr1 = 6.4328E-5 + (2.94981E-2 / (146 - (lam ** (-2)))) + (2.554E-4 / (41 - (lam ** (-2))))
+    rho = np.asarray(rho, dtype=np.float64); N = np.asarray(N, dtype=np.float64)
+    ext = (32.0E27) * f * (Pi8 ** 3) * (rho ** 2) * (mr1 ** 2) / (3.0 * N * (rho0 ** 2) * (lam ** 4))
+    return ext, np.ones_like(ext), np.ones(ext.size, np.int32), new_PhaseFunctionTable([rayleigh()], key=[0.0])
+
+
+def _null_table():
+    from .scatteringPhaseFunctions import new_PhaseFunction, new_PhaseFunctionTable
+    return new_PhaseFunctionTable([new_PhaseFunction(legendreCoefficients=np.array([0.0, 0.0], dtype=f32))], key=[0.0])
+
+
+def read_SSPTable(tables: List[SSPTable], lambdaIndex: int, commonD: commonDomain, setup: bool = False,
+                  calcRayl: bool = False, thisIntegrator=None) -> "Domain":
+    """``read_SSPTable`` (OPT:147-343) for one wavelength (``lambdaIndex`` is 1-based): cloud / aerosol components are
+    interpolated in effective radius from the file's tables, gas components are ``xsec * numConc * 1000``, Rayleigh
+    scattering is added on request, then ``getOpticalPropertiesByComponent`` assembles the dense arrays.
+
+    Without ``thisIntegrator`` this is the NumPy staging producer.  With it, the per-cell loops run on that
+    integrator's GPU (``mcb_set_physical`` once per run, ``mcb_assemble_optics`` per wavelength): the returned Domain
+    carries the component tables and metadata, its dense arrays live in HBM only."""
+    li = int(lambdaIndex) - 1
+    first = tables[0]
+    lam = (light_spd * (10 ** 6)) / float(first.f_grid[li])                      # OPT:199 [microns]
+    d = Domain(commonD.xPosition, commonD.yPosition, commonD.zPosition, temps=commonD.temps,
+               surfaceAlbedo=float(first.surfaceAlbedo[li]), lambda_um=lam)
+    nz, ny, nx = d.numZ, d.numY, d.numX
+    descr = []                                                                    # for the device path
+    comp = 1; gasComp = 0
+    for t in tables:
+        for c in t.components:
+            if c.extType == "absXsec":                                            # OPT:203-221
+                gasComp += 1
+                ext = np.asarray(c.xsec[li], dtype=np.float64) * commonD.numConc[:, 0, 0] * 1000.0
+                if thisIntegrator is None:
+                    d.addOpticalComponent(c.name, ext, np.zeros(nz), np.ones(nz, np.int32), _null_table(),
+                                          zLevelBase=c.zLevelBase)
+                descr.append(dict(kind=1, physIndex=0, zLevelBase=c.zLevelBase, table=_null_table(),
+                                  ext=np.ascontiguousarray(c.xsec[li], dtype=np.float64)))
+            elif c.extType == "volExt":                                           # OPT:222-293
+                key = np.asarray(c.key, dtype=f32)
+                extT = np.ascontiguousarray(c.extinctionT[li], dtype=np.float64)
+                ssaT = np.ascontiguousarray(c.singleScatteringAlbedoT[li], dtype=np.float64)
+                table = _null_table() if setup else c.tables[li]
+                p = comp - gasComp - 1
+                if thisIntegrator is None:
+                    m = commonD.massConc[..., p]; re = commonD.Reff[..., p]
+                    inside = (m > 0.0) & (re < np.float64(key.max())) & (re >= np.float64(key.min()))
+                    if np.any((m > 0.0) & ~inside):
+                        raise ValueError("read_SSPTable: Effective radius outside of table range")
+                    key8 = key.astype(np.float64)
+                    il = np.clip(np.searchsorted(key8, re, side="right"), 1, key.size - 1)      # findIndex: key(il) <= Reff < key(il+1)
+                    f = (re - key8[il - 1]) / (key[il] - key[il - 1]).astype(np.float64)         # OPT:272 (f32 difference)
+                    ext = np.where(inside, m * ((1 - f) * extT[il - 1] + f * extT[il]), 0.0)
+                    ssa = np.where(inside, (1 - f) * ssaT[il - 1] + f * ssaT[il], 0.0)
+                    idx = np.ones((nz, ny, nx), np.int32)
+                    if not setup:
+                        idx = np.where(inside, np.where(f < 0.5, il, il + 1), 1).astype(np.int32)
+                    d.addOpticalComponent(c.name, ext, ssa, idx, table, zLevelBase=c.zLevelBase)
+                descr.append(dict(kind=0, physIndex=p + 1, zLevelBase=c.zLevelBase, table=table, key=key, ext=extT, ssa=ssaT))
+            else:
+                raise ValueError("read_SSPTable: unrecognizable extType")
+            comp += 1
+    if calcRayl and not setup:                                                    # OPT:320-338
+        ext, ssa, idx, table = calc_RayleighScattering(lam, commonD.rho[:, 0, 0], commonD.numConc[:, 0, 0])
+        if thisIntegrator is None:
+            d.addOpticalComponent("Rayleigh Scattering", ext, ssa, idx, table, zLevelBase=1)
+        descr.append(dict(kind=2, physIndex=0, zLevelBase=1, table=table, ext=np.ascontiguousarray(ext),
+                          ssa=np.ascontiguousarray(ssa), idx=np.ascontiguousarray(idx, dtype=np.int32)))
+    if thisIntegrator is None:
+        return d.getOpticalPropertiesByComponent()
+    _assemble_on_device(thisIntegrator, d, commonD, descr, setup)
+    return d
+
+
+def _assemble_on_device(g, d: "Domain", commonD: commonDomain, descr, setup: bool) -> None:
+    import ctypes as C
+
+    from . import _lib
+    if (d.numX, d.numY, d.numZ) != (g.numX, g.numY, g.numZ):
+        raise ValueError("read_SSPTable: domain and integrator grids differ")
+    if getattr(g, "_stagedPhysical", None) != id(commonD):                        # once per run
+        mc = np.ascontiguousarray(commonD.massConc, dtype=np.float64)
+        re = np.ascontiguousarray(commonD.Reff, dtype=np.float64)
+        nPhys = mc.shape[-1] if mc.ndim == 4 else 0
+        nconc = None if commonD.numConc is None else np.ascontiguousarray(commonD.numConc[:, 0, 0], dtype=np.float64)
+        g._check(g._lib.mcb_set_physical(g.handle, nPhys, _lib.ptr(mc, C.c_double), _lib.ptr(re, C.c_double),
+                                         _lib.ptr(nconc, C.c_double)), "read_SSPTable")
+        g._stagedPhysical = id(commonD)
+    arr = (_lib.mcb_component * len(descr))()
+    keep = []
+    for i, q in enumerate(descr):
+        arr[i].kind = q["kind"]; arr[i].physIndex = q["physIndex"]; arr[i].zLevelBase = q["zLevelBase"]
+        arr[i].nTable = q["ext"].size
+        arr[i].ext = _lib.ptr(q["ext"], C.c_double)
+        if "ssa" in q: arr[i].ssa = _lib.ptr(q["ssa"], C.c_double)
+        if "key" in q: arr[i].key = _lib.ptr(q["key"], C.c_float)
+        if "idx" in q: arr[i].phaseIdx = _lib.ptr(q["idx"], C.c_int32)
+        keep.append(q)
+    g._check(g._lib.mcb_assemble_optics(g.handle, len(descr), arr, int(bool(setup)), float(d.surfaceAlbedo)), "read_SSPTable")
+    nc = len(descr)
+    d.forwardTables = [q["table"] for q in descr]
+    d.inversePhaseFunctions = [None] * nc
+    d.tabulatedPhaseFunctions = [None] * nc
+    d.tabulatedOrigPhaseFunctions = [None] * nc
+    d.deviceOwner = g
+    g.numComps = nc
+    g._stagedDomain = ("device", id(d))
+    g._stagedTables = None
+
+
+def fetchOpticalProperties(d: "Domain") -> "Domain":
+    """Copy the dense arrays of a device-assembled Domain back to the host (tests, output)."""
+    import ctypes as C
+
+    from . import _lib
+    g = getattr(d, "deviceOwner", None)
+    if g is None:
+        return d
+    nc = len(d.forwardTables); nz, ny, nx = d.numZ, d.numY, d.numX
+    d.totalExt = np.empty((nz, ny, nx)); d.cumulativeExt = np.empty((nc, nz, ny, nx))
+    d.ssa = np.empty((nc, nz, ny, nx)); d.phaseFunctionIndex = np.empty((nc, nz, ny, nx), np.int32)
+    g._check(g._lib.mcb_get_optics(g.handle, _lib.ptr(d.totalExt, C.c_double), _lib.ptr(d.cumulativeExt, C.c_double),
+                                   _lib.ptr(d.ssa, C.c_double), _lib.ptr(d.phaseFunctionIndex, C.c_int32)),
+             "fetchOpticalProperties")
+    return d

@@ -1142,3 +1142,64 @@ void orc_finalise_stats(double *stats, int64_t n, double solarFlux,
     stats[i + n] = sqrt(var / (double)(batchesCompleted - 1));
   }
 }
+
+/* ------------------------------------------------------------------------------------- */
+/* read_SSPTable inner loops (OPT:204-299) + getOpticalPropertiesByComponent (OPT:1022-1061) */
+/* ------------------------------------------------------------------------------------- */
+int orc_assemble_optics(int nx, int ny, int nz, int nPhys, const double *massConc, const double *Reff,
+                        const double *numConc, int nc, const orc_component *comps, int setup,
+                        double *totalExt, double *cumExt, double *ssa, int32_t *phaseIdx) {
+  const size_t cols = (size_t)nx * ny, cells = cols * nz;
+  int rc = 0;
+  for (int c = 0; c < nc; ++c) {
+    const orc_component *q = &comps[c];
+    double *cumC = cumExt + cells * c, *ssaC = ssa + cells * c;
+    int32_t *idxC = phaseIdx + cells * c;
+    for (size_t i = 0; i < cells; ++i) { cumC[i] = 0.0; ssaC[i] = 0.0; idxC[i] = 0; }
+    const int nLev = q->kind == ORC_COMP_VOLEXT ? nz : q->nTable;
+    if (q->zLevelBase < 1 || q->zLevelBase + nLev - 1 > nz) return 2;              /* OPT:706-708 */
+    if (q->kind == ORC_COMP_VOLEXT) {
+      const int nReff = q->nTable;
+      double *key8 = (double *)malloc(sizeof(double) * nReff);                     /* REAL(key(:),8), OPT:269 */
+      float kmin = q->key[0], kmax = q->key[0];
+      for (int i = 0; i < nReff; ++i) {
+        key8[i] = (double)q->key[i];
+        if (q->key[i] < kmin) kmin = q->key[i];
+        if (q->key[i] > kmax) kmax = q->key[i];
+      }
+      for (size_t cell = 0; cell < cells; ++cell) {                                /* OPT:260-292 */
+        const double m = massConc[(size_t)(q->physIndex - 1) + (size_t)nPhys * cell];
+        const double re = Reff[(size_t)(q->physIndex - 1) + (size_t)nPhys * cell];
+        double e = 0.0, w = 0.0; int32_t pi = 1;                                   /* OPT:253-255 defaults */
+        if (m > 0.0 && re < (double)kmax && re >= (double)kmin) {
+          const int il = orc_findIndexDouble(re, key8, nReff, 0);
+          const double f = (re - (double)q->key[il - 1]) / (double)(q->key[il] - q->key[il - 1]);   /* OPT:272 */
+          e = m * ((1 - f) * q->ext[il - 1] + f * q->ext[il]);
+          w = (1 - f) * q->ssa[il - 1] + f * q->ssa[il];
+          if (!setup) pi = f < 0.5 ? il : il + 1;                                  /* OPT:279-285 */
+        } else if (m > 0.0) {
+          rc = 1;                                                                  /* OPT:288-289 */
+        }
+        cumC[cell] = e; ssaC[cell] = w; idxC[cell] = pi;
+      }
+      free(key8);
+    } else {
+      for (int k = 0; k < nLev; ++k) {
+        const int iz = q->zLevelBase - 1 + k;
+        double e, w; int32_t pi;
+        if (q->kind == ORC_COMP_ABSXSEC) { e = q->ext[k] * numConc[k] * 1000.0; w = 0.0; pi = 1; }   /* OPT:223-227 */
+        else { e = q->ext[k]; w = q->ssa[k]; pi = q->phaseIdx[k]; }
+        for (size_t j = 0; j < cols; ++j) {                                        /* spread(...), OPT:1038-1046 */
+          cumC[j + cols * iz] = e; ssaC[j + cols * iz] = w; idxC[j + cols * iz] = pi;
+        }
+      }
+    }
+  }
+  for (int c = 1; c < nc; ++c)                                                     /* OPT:1055-1057 */
+    for (size_t i = 0; i < cells; ++i) cumExt[i + cells * c] = cumExt[i + cells * c] + cumExt[i + cells * (c - 1)];
+  for (size_t i = 0; i < cells; ++i) totalExt[i] = cumExt[i + cells * (nc - 1)];
+  for (int c = 0; c < nc; ++c)                                                     /* OPT:1059-1061 */
+    for (size_t i = 0; i < cells; ++i)
+      if (totalExt[i] > DBL_MIN) cumExt[i + cells * c] = cumExt[i + cells * c] / totalExt[i];
+  return rc;
+}

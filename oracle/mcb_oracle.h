@@ -207,6 +207,27 @@ int64_t orc_run_batches(orc_integrator *g, const orc_domain *d,
 void orc_finalise_stats(double *stats, int64_t n, double solarFlux,
                         int64_t totalNumPhotons, int64_t batchesCompleted); /* DRV:1188-1228 */
 
+/* ---- per-wavelength optical-property assembly: read_SSPTable's inner loops (OPT:204-299) followed by
+ * getOpticalPropertiesByComponent (OPT:1022-1061).  The netCDF reads are not restated: the caller hands
+ * over what they return for one lambdaIndex.                                                            */
+enum { ORC_COMP_VOLEXT = 0, ORC_COMP_ABSXSEC = 1, ORC_COMP_PROFILE = 2 };
+typedef struct {
+  int32_t kind;            /* extType "volExt" | "absXsec" | an explicit horizontally uniform profile     */
+  int32_t physIndex;       /* volExt: 1-based slot of massConc / Reff ("comp-gasComp", OPT:264)           */
+  int32_t nTable;          /* volExt: nReff; otherwise number of levels                                   */
+  int32_t zLevelBase;      /* 1-based (OPT:201)                                                           */
+  const float *key;        /* volExt: phaseFunctionKeyT(nReff), default real (OPT:164, 243)               */
+  const double *ext;       /* volExt: ExtinctionT(nReff); absXsec: xsec(nLevels); profile: extinction     */
+  const double *ssa;       /* volExt: SingleScatteringAlbedoT(nReff); profile: ssa(nLevels)               */
+  const int32_t *phaseIdx; /* profile: phaseFunctionIndex(nLevels)                                        */
+} orc_component;
+/* massConc, Reff: (nPhys, nx, ny, nz) component fastest (OPT:72-73); numConc: numConc(1,1,:) (OPT:223).
+ * Outputs in the domain's layout.  Returns 0, or 1 = "Effective radius outside of table range" (OPT:289),
+ * 2 = a component does not fit the vertical extent of the domain.                                        */
+int orc_assemble_optics(int nx, int ny, int nz, int nPhys, const double *massConc, const double *Reff,
+                        const double *numConc, int nc, const orc_component *comps, int setup,
+                        double *totalExt, double *cumExt, double *ssa, int32_t *phaseIdx);
+
 #ifdef __cplusplus
 }
 #endif

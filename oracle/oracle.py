@@ -31,6 +31,12 @@ class orc_options(C.Structure):
                 ("LW_flag", C.c_float)]
 
 
+class orc_component(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("physIndex", C.c_int32), ("nTable", C.c_int32), ("zLevelBase", C.c_int32),
+                ("key", C.POINTER(C.c_float)), ("ext", C.POINTER(C.c_double)), ("ssa", C.POINTER(C.c_double)),
+                ("phaseIdx", C.POINTER(C.c_int32))]
+
+
 class orc_counters(C.Structure):
     _fields_ = [(n, C.c_int64) for n in ("photons", "crossings", "scatters", "surfaceHits", "topExits", "bad",
                                          "leRays", "leCrossings", "rouletteKills", "rnDrawn")]
@@ -115,6 +121,8 @@ def load():
     lib.orc_run_batches.restype = C.c_int64
     lib.orc_run_batches.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_float, C.c_double, _dp,
                                     C.c_int, C.c_int, C.c_int, C.c_int64, C.c_int64, C.POINTER(orc_stats)]
+    lib.orc_assemble_optics.argtypes = [C.c_int] * 4 + [_dp, _dp, _dp, C.c_int, C.POINTER(orc_component), C.c_int,
+                                        _dp, _dp, _dp, C.POINTER(C.c_int32)]
     lib.orc_finalise_stats.argtypes = [_dp, C.c_int64, C.c_double, C.c_int64, C.c_int64]
     lib.orc_finalise_stats.restype = None
     lib.orc_march.restype = C.c_float
@@ -251,6 +259,35 @@ class OracleIntegrator:
             self.lib.orc_integrator_free(self.ptr)
         except Exception:
             pass
+
+
+def assemble_optics(nx, ny, nz, massConc, Reff, numConc, comps, setup=False):
+    """read_SSPTable's loops + getOpticalPropertiesByComponent (OPT:204-299, 1022-1061).  ``comps`` is a list of
+    dicts with kind / physIndex / zLevelBase / ext and, by kind, key / ssa / idx (the reference's per-lambda reads).
+    Returns (rc, totalExt, cumExt, ssa, phaseIdx) in the domain's layout."""
+    lib = load()
+    mc = np.ascontiguousarray(massConc, dtype=np.float64); re = np.ascontiguousarray(Reff, dtype=np.float64)
+    nPhys = mc.shape[-1] if mc.ndim == 4 else 0
+    nco = None if numConc is None else np.ascontiguousarray(numConc, dtype=np.float64)
+    arr = (orc_component * len(comps))()
+    keep = []
+    for i, q in enumerate(comps):
+        ext = np.ascontiguousarray(q["ext"], dtype=np.float64); keep.append(ext)
+        arr[i].kind = q["kind"]; arr[i].physIndex = q.get("physIndex", 0); arr[i].zLevelBase = q.get("zLevelBase", 1)
+        arr[i].nTable = ext.size; arr[i].ext = _p(ext, C.c_double)
+        if "ssa" in q:
+            a = np.ascontiguousarray(q["ssa"], dtype=np.float64); keep.append(a); arr[i].ssa = _p(a, C.c_double)
+        if "key" in q:
+            a = np.ascontiguousarray(q["key"], dtype=np.float32); keep.append(a); arr[i].key = _p(a, C.c_float)
+        if "idx" in q:
+            a = np.ascontiguousarray(q["idx"], dtype=np.int32); keep.append(a); arr[i].phaseIdx = _p(a, C.c_int32)
+    nc = len(comps)
+    total = np.empty((nz, ny, nx)); cum = np.empty((nc, nz, ny, nx)); ssa = np.empty((nc, nz, ny, nx))
+    idx = np.empty((nc, nz, ny, nx), np.int32)
+    rc = lib.orc_assemble_optics(nx, ny, nz, nPhys, _p(mc, C.c_double), _p(re, C.c_double), _p(nco, C.c_double), nc, arr,
+                                 int(bool(setup)), _p(total, C.c_double), _p(cum, C.c_double), _p(ssa, C.c_double),
+                                 idx.ctypes.data_as(C.POINTER(C.c_int32)))
+    return rc, total, cum, ssa, idx
 
 
 def finalise(stats: np.ndarray, solarFlux: float, totalNumPhotons: int, batchesCompleted: int):
