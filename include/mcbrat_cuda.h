@@ -130,6 +130,12 @@ int mcb_build_thermal_source(mcb_handle *h, const double *temps, double lambda_u
 /* read the staged Weights back (voxelWeights EMI:56-57, fracAtmsPower); either pointer may be NULL */
 int mcb_get_thermal_source(mcb_handle *h, double *fracAtmsPower, double *voxelCDF, int64_t nDoubles);
 
+/* getFrequencyDistr (EMI:552-573, called at DRV:439-445, 497-503): allocate totalPhotons photons to the
+ * nLambda wavelength bins of a flux CDF -- one uniform draw + findCDFIndex per photon, on the device.
+ * distribution(nLambda) receives the counts (they sum to totalPhotons).                                */
+int mcb_frequency_distribution(mcb_handle *h, int nLambda, const double *cdf, int64_t totalPhotons,
+                               uint64_t seed, int64_t *distribution);
+
 /* ---- computeRadiativeTransfer (INT:209-218) ------------------------------------------- */
 /* Zero the tallies (INT:247-272) and trace nPhotons photons with global ids
  * [firstPhotonId, firstPhotonId + nPhotons) of the stream `seed` (counter-based RNG: the

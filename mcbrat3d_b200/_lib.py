@@ -56,7 +56,7 @@ assert EVENT_DTYPE.itemsize == 96
 EXPORTS = ["mcb_create", "mcb_destroy", "mcb_last_error", "mcb_version", "mcb_set_stream", "mcb_synchronize",
            "mcb_set_grid", "mcb_set_optics", "mcb_set_physical", "mcb_assemble_optics", "mcb_get_optics", "mcb_set_inverse_table", "mcb_set_forward_table", "mcb_set_views",
            "mcb_default_options", "mcb_set_options", "mcb_set_solar_source", "mcb_set_thermal_source",
-           "mcb_build_thermal_source", "mcb_get_thermal_source", "mcb_run_batch", "mcb_accumulate_batch", "mcb_stats_reset", "mcb_run_batches",
+           "mcb_build_thermal_source", "mcb_get_thermal_source", "mcb_frequency_distribution", "mcb_run_batch", "mcb_accumulate_batch", "mcb_stats_reset", "mcb_run_batches",
            "mcb_stats_buffer", "mcb_get_statistics", "mcb_last_batch_ms",
            "mcb_get_counters", "mcb_get_results", "mcb_tally_buffer", "mcb_get_raw_tallies", "mcb_run_trace",
            "mcb_debug_philox"]
@@ -98,6 +98,7 @@ def load() -> C.CDLL:
     lib.mcb_set_thermal_source.argtypes = [_vp, C.c_double, _dp]
     lib.mcb_build_thermal_source.argtypes = [_vp, _dp, C.c_double, C.c_double, _dp, _dp]
     lib.mcb_get_thermal_source.argtypes = [_vp, _dp, _dp, C.c_int64]
+    lib.mcb_frequency_distribution.argtypes = [_vp, C.c_int, _dp, C.c_int64, C.c_uint64, C.POINTER(C.c_int64)]
     lib.mcb_run_batch.argtypes = [_vp, C.c_int64, C.c_uint64, C.c_uint64, C.POINTER(C.c_int64)]
     lib.mcb_accumulate_batch.argtypes = [_vp, C.c_int64, C.c_uint64, C.c_uint64, C.POINTER(C.c_int64)]
     lib.mcb_stats_reset.argtypes = [_vp]

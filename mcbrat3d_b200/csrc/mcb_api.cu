@@ -31,6 +31,8 @@ void mcb_launch_assemble_optics(int nx, int ny, int nz, int nc, const int *kind,
                                 int nPhys, const double *massConc, const double *Reff, const double *numConc, int setup,
                                 double *totalExt, double *cumExt, double *ssaOut, int32_t *phaseIdx, int *flags,
                                 int numSMs, cudaStream_t stream);
+void mcb_launch_frequency_distribution(const double *cdf, int nLambda, long long totalPhotons, uint64_t seed,
+                                       unsigned long long *counts, int numSMs, cudaStream_t stream);
 long long mcb_stats_elements(const DevDomain &P);
 void mcb_launch_stats_accumulate(const DevDomain &P, const float *results, double *stats, double weight, int numSMs,
                                  cudaStream_t stream);
@@ -603,6 +605,27 @@ int mcb_run_batch(mcb_handle *h, int64_t nPhotons, uint64_t seed, uint64_t first
 }
 int mcb_accumulate_batch(mcb_handle *h, int64_t nPhotons, uint64_t seed, uint64_t firstPhotonId, int64_t *nProcessed) {
   return run(h, nPhotons, seed, firstPhotonId, false, nProcessed);
+}
+
+// getFrequencyDistr EMI:552-573: how many of totalPhotons photons fall into each wavelength bin of the flux CDF
+int mcb_frequency_distribution(mcb_handle *h, int nLambda, const double *cdf, int64_t totalPhotons, uint64_t seed,
+                               int64_t *distribution) {
+  if (!h) return 1;
+  if (nLambda < 1 || nLambda > 8192 || !cdf || !distribution || totalPhotons < 0)
+    FAIL(h, "getFrequencyDistr: bad arguments (1..8192 wavelength bins)");
+  if (totalPhotons / 4 / ((long long)h->numSMs * 8) >= (1LL << 30)) FAIL(h, "getFrequencyDistr: too many photons for one call");
+  for (int i = 1; i < nLambda; ++i) if (!(cdf[i] >= cdf[i - 1])) FAIL(h, "getFrequencyDistr: CDF must be non-decreasing");
+  CK(h, cudaSetDevice(h->device));
+  const size_t cdfBytes = sizeof(double) * nLambda;
+  if (reserve(h, &h->dScratch, cdfBytes + sizeof(unsigned long long) * nLambda)) return 1;
+  unsigned long long *dCounts = (unsigned long long *)((char *)h->dScratch + cdfBytes);
+  CK(h, cudaMemcpyAsync(h->dScratch, cdf, cdfBytes, cudaMemcpyHostToDevice, h->stream));
+  CK(h, cudaMemsetAsync(dCounts, 0, sizeof(unsigned long long) * nLambda, h->stream));
+  if (totalPhotons > 0)
+    mcb_launch_frequency_distribution((const double *)h->dScratch, nLambda, totalPhotons, seed, dCounts, h->numSMs, h->stream);
+  CK(h, cudaGetLastError());
+  CK(h, cudaMemcpyAsync(distribution, dCounts, sizeof(int64_t) * nLambda, cudaMemcpyDeviceToHost, h->stream));
+  return settle(h);
 }
 
 // ---- the driver's batch loop with its statistics on the device (DRV:949-1052, 1188-1228) ----

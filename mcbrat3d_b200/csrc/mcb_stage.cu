@@ -252,6 +252,47 @@ __global__ void stats_finalise_kernel(const double *__restrict__ stats, long lon
 }
 
 // ---------------------------------------------------------------------------------------------
+// spectral photon allocation: getFrequencyDistr (EMI:552-573) -- totalPhotons draws, each binned by
+// findCDFIndex (NUM:317-348).  The reference draws them one after the other from its sequential generator
+// (1e10 draws for the bench decks); here draw n is word (n mod 4) of the Philox block with counter
+// (n / 4, 'FREQ') under the run's key, so the histogram does not depend on the grid or on the GPU count.
+// ---------------------------------------------------------------------------------------------
+__global__ void frequency_distribution_kernel(const double *__restrict__ cdf, int nLambda, long long totalPhotons,
+                                              uint64_t seed, unsigned long long *counts) {
+  extern __shared__ unsigned int hist[];
+  for (int i = threadIdx.x; i < nLambda; i += blockDim.x) hist[i] = 0u;
+  __syncthreads();
+  const long long nBlocks = (totalPhotons + 3) / 4;
+  for (long long b = blockIdx.x * (long long)blockDim.x + threadIdx.x; b < nBlocks; b += (long long)gridDim.x * blockDim.x) {
+    uint32_t x0 = (uint32_t)b, x1 = (uint32_t)((unsigned long long)b >> 32), x2 = 0x46524551u, x3 = 0u;
+    uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+      const uint32_t hi0 = __umulhi(0xD2511F53u, x0), lo0 = 0xD2511F53u * x0;
+      const uint32_t hi1 = __umulhi(0xCD9E8D57u, x2), lo1 = 0xCD9E8D57u * x2;
+      const uint32_t y0 = hi1 ^ x1 ^ k0, y2 = hi0 ^ x3 ^ k1;
+      x0 = y0; x1 = lo1; x2 = y2; x3 = lo0;
+      k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    const uint32_t w[4] = {x0, x1, x2, x3};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (4 * b + j >= totalPhotons) break;
+      const double v = (double)(__uint2float_rn(w[j]) * 2.3283064365386963e-10f);    // real in [0, 1], RNG:286-300
+      int lo = 0, hi = nLambda;                                                       // findCDFIndex NUM:317-348
+      while (!(lo == nLambda || hi <= lo + 1)) {
+        const int mid = (lo + hi) / 2;
+        if (v > cdf[mid - 1]) lo = mid; else hi = mid;
+      }
+      atomicAdd(&hist[hi - 1], 1u);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < nLambda; i += blockDim.x)
+    if (hist[i]) atomicAdd(&counts[i], (unsigned long long)hist[i]);
+}
+
+// ---------------------------------------------------------------------------------------------
 // emission CDF (EMI:498-522)
 // ---------------------------------------------------------------------------------------------
 struct dd { double hi, lo; };
@@ -426,6 +467,17 @@ void mcb_launch_stats_accumulate(const DevDomain &P, const float *results, doubl
 void mcb_launch_stats_finalise(const double *stats, long long n, double solarFlux, double *out, int numSMs,
                                cudaStream_t stream) {
   mcbstage::stats_finalise_kernel<<<stream_grid(n, 256, numSMs), 256, 0, stream>>>(stats, n, solarFlux, out);
+}
+
+void mcb_launch_frequency_distribution(const double *cdf, int nLambda, long long totalPhotons, uint64_t seed,
+                                       unsigned long long *counts, int numSMs, cudaStream_t stream) {
+  // per-block shared histogram of 32-bit counters: a block handles < 2^32 photons
+  const long long per = (totalPhotons + 3) / 4;
+  long long blocks = (per + 255) / 256;
+  if (blocks > (long long)numSMs * 8) blocks = (long long)numSMs * 8;
+  if (blocks < 1) blocks = 1;
+  mcbstage::frequency_distribution_kernel<<<(int)blocks, 256, sizeof(unsigned int) * nLambda, stream>>>(cdf, nLambda,
+                                                                                     totalPhotons, seed, counts);
 }
 
 // returns the number of tiles; scratch must hold (tiles + 1) double-double values

@@ -1203,3 +1203,13 @@ int orc_assemble_optics(int nx, int ny, int nz, int nPhys, const double *massCon
       if (totalExt[i] > DBL_MIN) cumExt[i + cells * c] = cumExt[i + cells * c] / totalExt[i];
   return rc;
 }
+
+/* getFrequencyDistrNEW EMI:552-573 */
+void orc_frequency_distribution(int numLambda, const double *CDF, int64_t totalPhotons, orc_rng *r, int64_t *distribution) {
+  for (int i = 0; i < numLambda; ++i) distribution[i] = 0;
+  for (int64_t n = 0; n < totalPhotons; ++n) {
+    const float RN = orc_rng_real(r);
+    const int i = orc_findCDFIndex(RN, CDF, numLambda, 1);
+    distribution[i - 1] = distribution[i - 1] + 1;
+  }
+}

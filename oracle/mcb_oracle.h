@@ -228,6 +228,9 @@ int orc_assemble_optics(int nx, int ny, int nz, int nPhys, const double *massCon
                         const double *numConc, int nc, const orc_component *comps, int setup,
                         double *totalExt, double *cumExt, double *ssa, int32_t *phaseIdx);
 
+/* getFrequencyDistrNEW EMI:552-573: totalPhotons draws binned with findCDFIndex */
+void orc_frequency_distribution(int numLambda, const double *CDF, int64_t totalPhotons, orc_rng *r, int64_t *distribution);
+
 #ifdef __cplusplus
 }
 #endif

@@ -123,6 +123,8 @@ def load():
                                     C.c_int, C.c_int, C.c_int, C.c_int64, C.c_int64, C.POINTER(orc_stats)]
     lib.orc_assemble_optics.argtypes = [C.c_int] * 4 + [_dp, _dp, _dp, C.c_int, C.POINTER(orc_component), C.c_int,
                                         _dp, _dp, _dp, C.POINTER(C.c_int32)]
+    lib.orc_frequency_distribution.argtypes = [C.c_int, _dp, C.c_int64, C.POINTER(orc_rng), C.POINTER(C.c_int64)]
+    lib.orc_frequency_distribution.restype = None
     lib.orc_finalise_stats.argtypes = [_dp, C.c_int64, C.c_double, C.c_int64, C.c_int64]
     lib.orc_finalise_stats.restype = None
     lib.orc_march.restype = C.c_float
@@ -288,6 +290,19 @@ def assemble_optics(nx, ny, nz, massConc, Reff, numConc, comps, setup=False):
                                  int(bool(setup)), _p(total, C.c_double), _p(cum, C.c_double), _p(ssa, C.c_double),
                                  idx.ctypes.data_as(C.POINTER(C.c_int32)))
     return rc, total, cum, ssa, idx
+
+
+def frequency_distribution(CDF, totalPhotons, seed=(10, 0, 0)):
+    """getFrequencyDistr (EMI:552-573) with the reference's MT19937 seeded by init_by_array(seed)."""
+    lib = load()
+    cdf = np.ascontiguousarray(CDF, dtype=np.float64)
+    r = orc_rng()
+    key = (C.c_uint32 * len(seed))(*[int(s) for s in seed])
+    lib.orc_rng_init_array(C.byref(r), key, len(seed))
+    out = np.zeros(cdf.size, dtype=np.int64)
+    lib.orc_frequency_distribution(cdf.size, _p(cdf, C.c_double), int(totalPhotons), C.byref(r),
+                                   out.ctypes.data_as(C.POINTER(C.c_int64)))
+    return out
 
 
 def finalise(stats: np.ndarray, solarFlux: float, totalNumPhotons: int, batchesCompleted: int):
