@@ -111,6 +111,13 @@ int mcb_assemble_optics(mcb_handle *h, int nc, const mcb_component *comps, int s
 int mcb_get_optics(mcb_handle *h, double *totalExt, double *cumExt, double *ssa, int32_t *phaseIdx);
 /* getInfo_Domain(inversePhaseFuncs) INT:443 <- tabulateInversePhaseFunctions INT:280 */
 int mcb_set_inverse_table(mcb_handle *h, int comp, int nS, int nE, const float *T);
+/* computeInversePhaseFuncTable (INV:26-174) on the device instead of on the host: entry e of the component's
+ * phase-function table is handed over at nAngles[e] points increasing in mu (the native angles reversed, or the
+ * phase function at max(nMoments,2) Lobatto nodes, INV:87-112; mus / values concatenated over entries); the CDF,
+ * the nS brackets and the analytic inversions run in HBM.  mcb_get_inverse_table reads a staged table back.   */
+int mcb_build_inverse_table(mcb_handle *h, int comp, int nS, int nE, const int32_t *nAngles,
+                            const float *mus, const float *values);
+int mcb_get_inverse_table(mcb_handle *h, int comp, float *T, int64_t nFloats);
 /* getInfo_Domain(tabPhase, tabOrigPhase) INT:1672-1673 <- tabulateForwardPhaseFunctions INT:282 */
 int mcb_set_forward_table(mcb_handle *h, int comp, int nS, int nE, const float *P, const float *Porig);
 /* specifyParameters(intensityMus, intensityPhis): direction cosines as INT:1267-1269 builds them;

@@ -105,7 +105,7 @@ def runBroadband(thisIntegrator, tables: List[SSPTable], commonD: commonDomain, 
         fluxCDF, solarFlux = solar_Weighting(solarSourceFunction, lambdas, solarMu)
     freqDistr = getFrequencyDistr(g, fluxCDF, totalPhotons, randomNumbers.seed ^ 0x5DEECE66D)
     # ---- the spectral loop (DRV:903-1052) ----
-    specifyParameters(g, LW_flag=1.0 if LW else -1.0)
+    specifyParameters(g, LW_flag=1.0 if LW else -1.0, buildTablesOnDevice=True)
     started = False
     world, rank = numProcs(), thisProc()
     for i in range(1, nLambda + 1):

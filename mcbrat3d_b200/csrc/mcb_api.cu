@@ -31,6 +31,8 @@ void mcb_launch_assemble_optics(int nx, int ny, int nz, int nc, const int *kind,
                                 int nPhys, const double *massConc, const double *Reff, const double *numConc, int setup,
                                 double *totalExt, double *cumExt, double *ssaOut, int32_t *phaseIdx, int *flags,
                                 int numSMs, cudaStream_t stream);
+void mcb_launch_inverse_table(const int *offsets, const float *mus, const float *values, int nEntries, int nSteps, float *out,
+                              float *cdfScratch, cudaStream_t stream);
 void mcb_launch_frequency_distribution(const double *cdf, int nLambda, long long totalPhotons, uint64_t seed,
                                        unsigned long long *counts, int numSMs, cudaStream_t stream);
 long long mcb_stats_elements(const DevDomain &P);
@@ -405,6 +407,48 @@ int mcb_set_inverse_table(mcb_handle *h, int comp, int nS, int nE, const float *
   if (stage(h, &h->dInv[c], T, sizeof(float) * (size_t)nS * nE)) return 1;
   h->P.inv[c] = (const float *)h->dInv[c]; h->P.invS[c] = nS; h->invE[c] = nE; h->haveInv[c] = true;
   return 0;
+}
+
+// computeInversePhaseFuncTable INV:26-64 on the device: entry e is given at nAngles[e] points increasing in mu
+// (mus / values concatenated); the table is built straight into the slot mcb_set_inverse_table would fill.
+int mcb_build_inverse_table(mcb_handle *h, int comp, int nS, int nE, const int32_t *nAngles, const float *mus,
+                            const float *values) {
+  if (!h) return 1;
+  if (!h->haveOptics) FAIL(h, "mcb_build_inverse_table: call mcb_set_optics first");
+  if (comp < 1 || comp > h->P.nc || nS < 2 || nE < 1 || !nAngles || !mus || !values)
+    FAIL(h, "mcb_build_inverse_table: bad arguments");
+  std::vector<int> off(nE + 1, 0);
+  for (int e = 0; e < nE; ++e) {
+    if (nAngles[e] < 2) FAIL(h, "computeInversePhaseFunction: a phase function needs at least two angles");
+    off[e + 1] = off[e] + nAngles[e];
+  }
+  const size_t total = (size_t)off[nE];
+  const int c = comp - 1;
+  // scratch layout: offsets | mus | values | cdf
+  const size_t bOff = (sizeof(int) * (nE + 1) + 15) & ~(size_t)15, bF = sizeof(float) * total;
+  if (reserve(h, &h->dScratch, bOff + 3 * bF)) return 1;
+  char *base = (char *)h->dScratch;
+  CK(h, cudaMemcpyAsync(base, off.data(), sizeof(int) * (nE + 1), cudaMemcpyHostToDevice, h->stream));
+  CK(h, cudaMemcpyAsync(base + bOff, mus, bF, cudaMemcpyHostToDevice, h->stream));
+  CK(h, cudaMemcpyAsync(base + bOff + bF, values, bF, cudaMemcpyHostToDevice, h->stream));
+  if (reserve(h, &h->dInv[c], sizeof(float) * (size_t)nS * nE)) return 1;
+  mcb_launch_inverse_table((const int *)base, (const float *)(base + bOff), (const float *)(base + bOff + bF), nE, nS,
+                           (float *)h->dInv[c], (float *)(base + bOff + 2 * bF), h->stream);
+  CK(h, cudaGetLastError());
+  if (settle(h)) return 1;
+  h->P.inv[c] = (const float *)h->dInv[c]; h->P.invS[c] = nS; h->invE[c] = nE; h->haveInv[c] = true;
+  return 0;
+}
+
+int mcb_get_inverse_table(mcb_handle *h, int comp, float *T, int64_t nFloats) {
+  if (!h || !T) return 1;
+  if (comp < 1 || comp > h->P.nc || !h->haveInv[comp - 1]) FAIL(h, "mcb_get_inverse_table: no table for this component");
+  const int c = comp - 1;
+  const int64_t n = (int64_t)h->P.invS[c] * h->invE[c];
+  if (nFloats < n) FAIL(h, "mcb_get_inverse_table: buffer too small (%lld needed)", (long long)n);
+  CK(h, cudaSetDevice(h->device));
+  CK(h, cudaMemcpyAsync(T, h->dInv[c], sizeof(float) * n, cudaMemcpyDeviceToHost, h->stream));
+  return settle(h);
 }
 
 int mcb_set_forward_table(mcb_handle *h, int comp, int nS, int nE, const float *Pf, const float *Porig) {

@@ -252,6 +252,96 @@ __global__ void stats_finalise_kernel(const double *__restrict__ stats, long lon
 }
 
 // ---------------------------------------------------------------------------------------------
+// inverse phase-function tables: computeInversePhaseFunction INV:113-168, one block per table entry.
+// Input: the phase function at nAngles points increasing in mu (native angles, or Lobatto nodes, INV:87-112).
+// The trapezoid CDF is a sequential single-precision sum (thread 0, a few hundred terms); the nSteps brackets
+// and the analytic inversions are independent and spread over the block.  On a non-decreasing CDF the
+// reference's hunt (findIndex with the previous bracket as first guess) finds the unique index with
+// cdf(index) <= p < cdf(index+1), i.e. a plain bisection; a CDF that decreases somewhere (negative phase
+// function values) is searched sequentially with the reference's own sequence of guesses.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float sp32(float x) {                  // spacing(real)
+  x = fabsf(x);
+  if (x == 0.0f) return FLT_MIN;
+  const float s = nextafterf(x, INFINITY) - x;
+  return s < FLT_MIN ? FLT_MIN : s;
+}
+
+__device__ int find_index_real(float value, const float *table, int n, int firstGuess) {   // NUM:150-204
+  int lowerBound, upperBound, increment;
+  if (firstGuess > 0) {
+    lowerBound = firstGuess; increment = 1;
+    for (;;) {
+      upperBound = min(lowerBound + increment, n);
+      if (lowerBound == n || (table[lowerBound - 1] <= value && table[upperBound - 1] > value)) break;
+      if (table[lowerBound - 1] > value) { upperBound = lowerBound; lowerBound = max(upperBound - increment, 1); }
+      else lowerBound = upperBound;
+      increment *= 2;
+    }
+  } else {
+    lowerBound = 0; upperBound = n;
+  }
+  while (!(lowerBound == n || upperBound <= lowerBound + 1)) {
+    const int midPoint = (lowerBound + upperBound) / 2;
+    if (value >= table[midPoint - 1]) lowerBound = midPoint; else upperBound = midPoint;
+  }
+  return lowerBound;
+}
+
+__device__ __forceinline__ float invert_one(const float *mus, const float *values, const float *cdf, int k, float p) {
+  const float c0 = cdf[k - 1], c1 = cdf[k], v0 = values[k - 1], v1 = values[k], m0 = mus[k - 1], m1 = mus[k];
+  float arg;
+  if (c1 - c0 <= sp32(c0)) arg = m0;                                                       // INV:149-150
+  else if (fabsf(v0 - v1) <= sp32(v0)) arg = m0 + (m1 - m0) * (p - c0) / (c1 - c0);        // INV:154-157
+  else arg = m0 + (m1 - m0) / (v0 - v1) * (v0 - sqrtf(((c1 - p) * (v0 * v0) + (p - c0) * (v1 * v1)) / (c1 - c0)));
+  arg = fminf(fmaxf(arg, -1.0f), 1.0f);
+  return (float)acos((double)arg);
+}
+
+__global__ void inverse_table_kernel(const int *__restrict__ offsets, const float *__restrict__ musAll,
+                                     const float *__restrict__ valuesAll, int nSteps, float *__restrict__ out,
+                                     float *__restrict__ cdfAll) {
+  const int e = blockIdx.x;
+  const int n = offsets[e + 1] - offsets[e];
+  const float *mus = musAll + offsets[e], *values = valuesAll + offsets[e];
+  float *cdf = cdfAll + offsets[e];
+  float *table = out + (size_t)e * nSteps;
+  __shared__ int monotonic;
+  if (threadIdx.x == 0) {
+    float c = 0.0f;
+    cdf[0] = 0.0f;
+    for (int i = 1; i < n; ++i) { c = c + (mus[i] - mus[i - 1]) * 0.5f * (values[i] + values[i - 1]); cdf[i] = c; }   // INV:118-121
+    const float last = c;
+    int mono = 1;
+    float prev = 0.0f;
+    for (int i = 0; i < n; ++i) {                                                          // INV:125
+      const float v = cdf[i] / last;
+      cdf[i] = v;
+      if (i > 0 && v < prev) mono = 0;
+      prev = v;
+    }
+    monotonic = mono;
+  }
+  __syncthreads();
+  if (monotonic) {
+    for (int i = 1 + (int)threadIdx.x; i <= nSteps - 1; i += blockDim.x) {                 // INV:137-167
+      const float p = (float)(i - 1) / (float)(nSteps - 1);
+      int lo = 0, hi = n;                                                                  // last k with cdf(k) <= p
+      while (hi > lo + 1) { const int mid = (lo + hi) / 2; if (p >= cdf[mid - 1]) lo = mid; else hi = mid; }
+      table[i - 1] = invert_one(mus, values, cdf, lo, p);
+    }
+  } else if (threadIdx.x == 0) {
+    int k = find_index_real(0.0f, cdf, n, 0);
+    for (int i = 1; i <= nSteps - 1; ++i) {
+      const float p = (float)(i - 1) / (float)(nSteps - 1);
+      if (i > 1) k = find_index_real(p, cdf, n, k);
+      table[i - 1] = invert_one(mus, values, cdf, min(k, n - 1), p);
+    }
+  }
+  if (threadIdx.x == 0) table[nSteps - 1] = 0.0f;                                          // INV:168
+}
+
+// ---------------------------------------------------------------------------------------------
 // spectral photon allocation: getFrequencyDistr (EMI:552-573) -- totalPhotons draws, each binned by
 // findCDFIndex (NUM:317-348).  The reference draws them one after the other from its sequential generator
 // (1e10 draws for the bench decks); here draw n is word (n mod 4) of the Philox block with counter
@@ -467,6 +557,11 @@ void mcb_launch_stats_accumulate(const DevDomain &P, const float *results, doubl
 void mcb_launch_stats_finalise(const double *stats, long long n, double solarFlux, double *out, int numSMs,
                                cudaStream_t stream) {
   mcbstage::stats_finalise_kernel<<<stream_grid(n, 256, numSMs), 256, 0, stream>>>(stats, n, solarFlux, out);
+}
+
+void mcb_launch_inverse_table(const int *offsets, const float *mus, const float *values, int nEntries, int nSteps, float *out,
+                              float *cdfScratch, cudaStream_t stream) {
+  mcbstage::inverse_table_kernel<<<nEntries, 256, 0, stream>>>(offsets, mus, values, nSteps, out, cdfScratch);
 }
 
 void mcb_launch_frequency_distribution(const double *cdf, int nLambda, long long totalPhotons, uint64_t seed,

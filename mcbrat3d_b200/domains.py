@@ -204,11 +204,14 @@ def broadband_problem(nxy=24, nz=20, nLambda=6, seed=11, lw=False):
     absorption cross-section profile, a surface albedo).  Returns (commonDomain, [SSPTable], case)."""
     from .opticalProperties import SSPComponent, SSPTable, commonDomain, light_spd
     rng = np.random.default_rng(seed)
-    dxy, dz = 0.0625, 0.03125 * 4
+    dxy, dz = 0.0625, 2.5 / nz                       # 2.5 km deep (0.125-km layers at nz = 20; f32-exact for nz = 20, 40, 80, 160)
     x = dxy * np.arange(nxy + 1, dtype=np.float64)
     z = dz * np.arange(nz + 1, dtype=np.float64)
     zc = 0.5 * (z[1:] + z[:-1])
-    g = _gaussian_field(64, rng)[:nxy, :nxy]
+    n2 = 64
+    while n2 < nxy:
+        n2 *= 2
+    g = _gaussian_field(n2, rng)[:nxy, :nxy]
     lwp = np.where(g > np.quantile(g, 0.35), np.exp(0.6 * g), 0.0)               # relative liquid water path per column
     base, top = nz // 4, nz // 4 + max(2, nz // 3)
     mass = np.zeros((nz, nxy, nxy)); reff = np.zeros((nz, nxy, nxy))

@@ -22,6 +22,38 @@ def _acos32(x):
     return np.arccos(np.asarray(x, dtype=np.float64)).astype(f32)
 
 
+def find_cdf_brackets(cdf: np.ndarray, nSteps: int) -> np.ndarray:
+    """INV:131-135: ``indicies(i) = findIndex((i-1)/(nSteps-1), cdf, firstGuess = indicies(i-1))``.
+
+    On a non-decreasing table the hunt/bisection of NUM:206-260 returns the unique index with
+    ``cdf(index) <= p < cdf(index+1)`` whatever the first guess, which is one vectorised search; a table that
+    decreases somewhere (a truncated Legendre series can go negative) is searched with the reference's own
+    sequence of guesses."""
+    if np.all(np.diff(cdf) >= 0):
+        p = np.arange(nSteps, dtype=f32) / f32(nSteps - 1)
+        return np.minimum(np.searchsorted(cdf, p, side="right"), cdf.size).astype(np.int64)
+    indicies = np.empty(nSteps, dtype=np.int64)
+    indicies[0] = findIndex(f32(0.0), cdf)
+    for i in range(2, nSteps + 1):
+        p = f32(f32(i - 1) / f32(nSteps - 1))
+        indicies[i - 1] = findIndex(p, cdf, firstGuess=int(indicies[i - 2]))
+    return indicies
+
+
+def inversion_inputs(thisPhaseFunction: phaseFunction):
+    """The (mus, values) pairs the inversion works on (INV:87-112): native angles reversed to increasing mu, or
+    the phase function evaluated at ``max(nMoments, 2)`` Lobatto nodes."""
+    if not thisPhaseFunction.storedAsLegendre():
+        angles = thisPhaseFunction.scatteringAngle
+        values = getPhaseFunctionValues(thisPhaseFunction, angles)
+        mus = np.cos(angles[::-1].astype(np.float64)).astype(f32)
+        return mus, np.ascontiguousarray(values[::-1], dtype=f32)
+    nAngles = max(thisPhaseFunction.legendreCoefficients.size, 2)
+    mus, _ = computeLobattoTerms(nAngles)
+    values = getPhaseFunctionValues(thisPhaseFunction, _acos32(mus[::-1]))
+    return np.ascontiguousarray(mus, dtype=f32), np.ascontiguousarray(values[::-1], dtype=f32)
+
+
 def computeInversePhaseFunction(thisPhaseFunction: phaseFunction, nSteps: int) -> np.ndarray:
     """INV:66-174.  Returns ``inverseTable(nSteps)`` in single precision."""
     if not thisPhaseFunction.storedAsLegendre():
@@ -42,11 +74,7 @@ def computeInversePhaseFunction(thisPhaseFunction: phaseFunction, nSteps: int) -
         cdf[i] = f32(cdf[i - 1] + (mus[i] - mus[i - 1]) * f32(0.5) * (values[i] + values[i - 1]))
     cdf = (cdf / cdf[nAngles - 1]).astype(f32)
 
-    indicies = np.empty(nSteps, dtype=np.int64)
-    indicies[0] = findIndex(f32(0.0), cdf)
-    for i in range(2, nSteps + 1):                                # INV:131-135
-        p = f32(f32(i - 1) / f32(nSteps - 1))
-        indicies[i - 1] = findIndex(p, cdf, firstGuess=int(indicies[i - 2]))
+    indicies = find_cdf_brackets(cdf, nSteps)
 
     out = np.zeros(nSteps, dtype=f32)
     i = np.arange(1, nSteps, dtype=np.int64)                      # INV:137-167, vectorised over i

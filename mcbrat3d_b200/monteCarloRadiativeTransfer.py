@@ -56,6 +56,7 @@ class integrator:
         self.intensityDirections: Optional[np.ndarray] = None       # (nDir, 3)
         self.numX = self.numY = self.numZ = 0
         self.numComps = 0
+        self.buildTablesOnDevice = False                             # inverse tables: NumPy mirror, or csrc/mcb_stage.cu
         self._stagedDomain = None
         self._stagedTables = None
         self._stagedSource = None
@@ -109,10 +110,12 @@ def specifyParameters(thisIntegrator: integrator, minForwardTableSize=None, minI
                       hybridPhaseFunWidth: Optional[float] = None, numOrdersOrigPhaseFunIntenCalcs: Optional[int] = None,
                       limitIntensityContributions: Optional[bool] = None, maxIntensityContribution: Optional[float] = None,
                       LW_flag: Optional[float] = None, numComps: Optional[int] = None,
-                      arithmetic: Optional[int] = None) -> None:
+                      arithmetic: Optional[int] = None, buildTablesOnDevice: Optional[bool] = None) -> None:
     """``specifyParameters`` (INT:1046-1337): same optional arguments, same checks.
 
-    ``arithmetic`` is the one addition: ``MCB_ARITH_FAST`` (default) or ``MCB_ARITH_REFERENCE``.
+    ``arithmetic`` is one addition: ``MCB_ARITH_FAST`` (default) or ``MCB_ARITH_REFERENCE``;
+    ``buildTablesOnDevice`` the other: the inverse phase-function tables of INV:66-174 are then built by
+    ``mcb_build_inverse_table`` in HBM instead of by the NumPy mirror (the default).
     ``surfaceBDRF`` and ``recScatOrd``/``numRecScatOrd`` are not supported (the driver never
     installs a BDRF, INT:667-674; the by-order tallies are commented out in the reference).
     """
@@ -155,6 +158,9 @@ def specifyParameters(thisIntegrator: integrator, minForwardTableSize=None, minI
         o.maxIntensityContribution = float(maxIntensityContribution)
     if LW_flag is not None: o.LW_flag = float(LW_flag)
     if arithmetic is not None: o.arithmetic = int(arithmetic)
+    if buildTablesOnDevice is not None:
+        g.buildTablesOnDevice = bool(buildTablesOnDevice)
+        g._stagedTables = None
     if intensityMus is not None:                                           # INT:1245-1271
         dirs = np.stack([makeDirectionCosines(m, f32(p) * Pi / f32(180.0)) for m, p in zip(mus, phis)], axis=0)
         g.intensityDirections = np.ascontiguousarray(dirs, dtype=f32)
@@ -189,16 +195,29 @@ def _stage_domain(g: integrator, d: Domain) -> None:
         g._stagedDomain = key
         g._stagedTables = None
     # INT:280-285: (re)tabulate only if missing or too coarse, then stage
-    d.tabulateInversePhaseFunctions(g.minInverseTableSize)
+    onDevice = g.buildTablesOnDevice
+    if not onDevice:
+        d.tabulateInversePhaseFunctions(g.minInverseTableSize)
     if g.computeIntensity:
         d.tabulateForwardPhaseFunctions(g.minForwardTableSize, bool(g.options.useHybridPhaseFunsForIntenCalcs),
                                         g.hybridPhaseFunWidth)
-    tkey = (key, tuple(id(t) for t in d.inversePhaseFunctions),
+    tkey = (key, onDevice, g.minInverseTableSize if onDevice else tuple(id(t) for t in d.inversePhaseFunctions),
             tuple(id(t) for t in d.tabulatedPhaseFunctions) if g.computeIntensity else None)
     if g._stagedTables != tkey:
-        for c, T in enumerate(d.inversePhaseFunctions):
-            g._check(g._lib.mcb_set_inverse_table(g._h, c + 1, T.shape[1], T.shape[0], _lib.ptr(T, C.c_float)),
-                     "tabulateInversePhaseFunctions")
+        if onDevice:
+            from .inversePhaseFunctions import inversion_inputs
+            for c, tab in enumerate(d.forwardTables):
+                pairs = [inversion_inputs(pf) for pf in tab.phaseFunctions]
+                nAng = np.array([m.size for m, _ in pairs], dtype=np.int32)
+                mus = np.ascontiguousarray(np.concatenate([m for m, _ in pairs]), dtype=f32)
+                vals = np.ascontiguousarray(np.concatenate([v for _, v in pairs]), dtype=f32)
+                g._check(g._lib.mcb_build_inverse_table(g._h, c + 1, int(g.minInverseTableSize), len(pairs),
+                                                        _lib.ptr(nAng, C.c_int32), _lib.ptr(mus, C.c_float),
+                                                        _lib.ptr(vals, C.c_float)), "tabulateInversePhaseFunctions")
+        else:
+            for c, T in enumerate(d.inversePhaseFunctions):
+                g._check(g._lib.mcb_set_inverse_table(g._h, c + 1, T.shape[1], T.shape[0], _lib.ptr(T, C.c_float)),
+                         "tabulateInversePhaseFunctions")
         if g.computeIntensity:
             for c, (Pf, Po) in enumerate(zip(d.tabulatedPhaseFunctions, d.tabulatedOrigPhaseFunctions)):
                 g._check(g._lib.mcb_set_forward_table(g._h, c + 1, Pf.shape[1], Pf.shape[0], _lib.ptr(Pf, C.c_float),

@@ -1213,3 +1213,65 @@ void orc_frequency_distribution(int numLambda, const double *CDF, int64_t totalP
     distribution[i - 1] = distribution[i - 1] + 1;
   }
 }
+
+/* findIndexReal NUM:150-204: the single-precision twin of findIndexDouble */
+static int findIndexReal(float value, const float *table, int n, int firstGuess) {
+#define T1(i) table[(i) - 1]
+  int lowerBound, upperBound, midPoint, increment;
+  if (firstGuess > 0) {
+    lowerBound = firstGuess; increment = 1;
+    for (;;) {
+      upperBound = lowerBound + increment < n ? lowerBound + increment : n;
+      if (lowerBound == n || (T1(lowerBound) <= value && T1(upperBound) > value)) break;
+      if (T1(lowerBound) > value) {
+        upperBound = lowerBound;
+        lowerBound = upperBound - increment > 1 ? upperBound - increment : 1;
+      } else {
+        lowerBound = upperBound;
+      }
+      increment *= 2;
+    }
+  } else {
+    lowerBound = 0; upperBound = n;
+  }
+  for (;;) {
+    if (lowerBound == n || upperBound <= lowerBound + 1) break;
+    midPoint = (lowerBound + upperBound) / 2;
+    if (value >= T1(midPoint)) lowerBound = midPoint; else upperBound = midPoint;
+  }
+  return lowerBound;
+#undef T1
+}
+
+/* computeInversePhaseFunction INV:113-168 (arguments of acos outside [-1, 1] are clamped, as the host mirror does) */
+void orc_inverse_phase_function(int nAngles, const float *mus, const float *values, int nSteps, float *inverseTable) {
+  float *cdf = (float *)malloc(sizeof(float) * nAngles);
+  int *indicies = (int *)malloc(sizeof(int) * nSteps);
+  cdf[0] = 0.0f;
+  for (int i = 1; i < nAngles; ++i)                                            /* INV:118-121 */
+    cdf[i] = cdf[i - 1] + (mus[i] - mus[i - 1]) * 0.5f * (values[i] + values[i - 1]);
+  const float last = cdf[nAngles - 1];
+  for (int i = 0; i < nAngles; ++i) cdf[i] = cdf[i] / last;                    /* INV:125 */
+  indicies[0] = findIndexReal(0.0f, cdf, nAngles, 0);                          /* INV:129-135 */
+  for (int i = 2; i <= nSteps; ++i) {
+    const float probabilityValue = (float)(i - 1) / (float)(nSteps - 1);
+    indicies[i - 1] = findIndexReal(probabilityValue, cdf, nAngles, indicies[i - 2]);
+  }
+  for (int i = 1; i <= nSteps - 1; ++i) {                                      /* INV:137-167 */
+    const float p = (float)(i - 1) / (float)(nSteps - 1);
+    const int k = indicies[i - 1];                                             /* 1-based */
+    const float c0 = cdf[k - 1], c1 = cdf[k], v0 = values[k - 1], v1 = values[k], m0 = mus[k - 1], m1 = mus[k];
+    float arg;
+    if (c1 - c0 <= sp32(c0)) {
+      arg = m0;
+    } else if (fabsf(v0 - v1) <= sp32(v0)) {
+      arg = m0 + (m1 - m0) * (p - c0) / (c1 - c0);
+    } else {
+      arg = m0 + (m1 - m0) / (v0 - v1) * (v0 - sqrtf(((c1 - p) * (v0 * v0) + (p - c0) * (v1 * v1)) / (c1 - c0)));
+    }
+    arg = arg < -1.0f ? -1.0f : (arg > 1.0f ? 1.0f : arg);
+    inverseTable[i - 1] = f_acos(arg);
+  }
+  inverseTable[nSteps - 1] = 0.0f;                                             /* INV:168 */
+  free(cdf); free(indicies);
+}

@@ -231,6 +231,11 @@ int orc_assemble_optics(int nx, int ny, int nz, int nPhys, const double *massCon
 /* getFrequencyDistrNEW EMI:552-573: totalPhotons draws binned with findCDFIndex */
 void orc_frequency_distribution(int numLambda, const double *CDF, int64_t totalPhotons, orc_rng *r, int64_t *distribution);
 
+/* computeInversePhaseFunction INV:113-168 once the phase function is known at nAngles points increasing in mu
+ * (native angles reversed, or max(nMoments,2) Lobatto nodes, INV:87-112): trapezoid CDF in mu, the bracket of every
+ * probability (i-1)/(nSteps-1) by findIndex with the previous bracket as first guess, analytic inversion.         */
+void orc_inverse_phase_function(int nAngles, const float *mus, const float *values, int nSteps, float *inverseTable);
+
 #ifdef __cplusplus
 }
 #endif

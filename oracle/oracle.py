@@ -125,6 +125,8 @@ def load():
                                         _dp, _dp, _dp, C.POINTER(C.c_int32)]
     lib.orc_frequency_distribution.argtypes = [C.c_int, _dp, C.c_int64, C.POINTER(orc_rng), C.POINTER(C.c_int64)]
     lib.orc_frequency_distribution.restype = None
+    lib.orc_inverse_phase_function.argtypes = [C.c_int, _fp, _fp, C.c_int, _fp]
+    lib.orc_inverse_phase_function.restype = None
     lib.orc_finalise_stats.argtypes = [_dp, C.c_int64, C.c_double, C.c_int64, C.c_int64]
     lib.orc_finalise_stats.restype = None
     lib.orc_march.restype = C.c_float
@@ -302,6 +304,15 @@ def frequency_distribution(CDF, totalPhotons, seed=(10, 0, 0)):
     out = np.zeros(cdf.size, dtype=np.int64)
     lib.orc_frequency_distribution(cdf.size, _p(cdf, C.c_double), int(totalPhotons), C.byref(r),
                                    out.ctypes.data_as(C.POINTER(C.c_int64)))
+    return out
+
+
+def inverse_phase_function(mus, values, nSteps):
+    """computeInversePhaseFunction INV:113-168 on (mus, values) increasing in mu."""
+    lib = load()
+    m = np.ascontiguousarray(mus, dtype=np.float32); v = np.ascontiguousarray(values, dtype=np.float32)
+    out = np.empty(int(nSteps), dtype=np.float32)
+    lib.orc_inverse_phase_function(m.size, _p(m, C.c_float), _p(v, C.c_float), int(nSteps), _p(out, C.c_float))
     return out
 
 

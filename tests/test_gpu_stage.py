@@ -200,3 +200,42 @@ def test_device_batch_statistics_match_host_loop(views):
         assert (tot, done) == ((nb + 2) * n, nb + 2)
     finally:
         finalize_Integrator(g)
+
+
+def test_inverse_tables_built_on_device_match_oracle(orc):
+    """computeInversePhaseFunction (INV:113-168) as a kernel, against the oracle's C
+    restatement -- Legendre (Lobatto nodes), tabulated (native angles) and the 2-moment Rayleigh function."""
+    from mcbrat3d_b200.inversePhaseFunctions import inversion_inputs
+    d, case = domains.landsat_cloud(ssa=0.99, nxy=16, mie=True)
+    g = new_Integrator(d)
+    try:
+        specifyParameters(g, minInverseTableSize=10001, buildTablesOnDevice=True)
+        rs = new_RandomNumberSequence(2)
+        ps = new_PhotonStream(case["solarMu"], case["solarAzimuth"], 50000, rs)
+        assert computeRadiativeTransfer(g, d, rs, ps, 50000) == 50000      # the run uses the device-built tables
+        r_dev = reportResults(g, meanFluxUp=True, meanFluxDown=True, meanFluxAbsorbed=True)
+        total = mismatch = 0
+        for c, tab in enumerate(d.forwardTables):
+            nE = len(tab.phaseFunctions)
+            got = np.empty((nE, 10001), dtype=f32)
+            g._check(g._lib.mcb_get_inverse_table(g.handle, c + 1, _lib.ptr(got, C.c_float), got.size), "get")
+            for e, pf in enumerate(tab.phaseFunctions):
+                mus, vals = inversion_inputs(pf)
+                want = orc.inverse_phase_function(mus, vals, 10001)
+                assert want[0] == f32(np.pi) or abs(want[0] - np.pi) < 1e-6
+                assert got[e, -1] == 0.0
+                bad = got[e] != want
+                mismatch += int(bad.sum()); total += want.size
+                if bad.any():                                                # double-precision acos is 1 ulp, not exact
+                    assert np.abs(got[e][bad] - want[bad]).max() <= 2.4e-7 * np.maximum(want[bad], 1.0).max()
+        assert mismatch <= 1e-4 * total, (mismatch, total)
+        # host-built tables give the same transport result (same photons, same tables up to the ulps above)
+        specifyParameters(g, buildTablesOnDevice=False)
+        rs = new_RandomNumberSequence(2)
+        ps = new_PhotonStream(case["solarMu"], case["solarAzimuth"], 50000, rs)
+        computeRadiativeTransfer(g, d, rs, ps, 50000)
+        r_host = reportResults(g, meanFluxUp=True, meanFluxDown=True, meanFluxAbsorbed=True)
+        for k in r_dev:
+            assert abs(float(r_dev[k]) - float(r_host[k])) < 2e-4
+    finally:
+        finalize_Integrator(g)

@@ -90,3 +90,27 @@ def test_hybrid_phase_function_keeps_normalisation_and_tail():
     integ = lambda f: np.sum(0.5 * (f[1:] + f[:-1]) * (mu[:-1] - mu[1:]))
     assert abs(integ(h[0].astype(float)) - integ(v[0].astype(float))) < 5e-3
     assert h[0, 0] < v[0, 0]                                    # the forward peak is flattened
+
+
+def test_oracle_inverse_builder_matches_numpy_mirror(orc):
+    """INV:113-168 restated in C (oracle) and vectorised in NumPy (host mirror): identical tables."""
+    from mcbrat3d_b200 import domains
+    from mcbrat3d_b200.inversePhaseFunctions import computeInversePhaseFunction, inversion_inputs
+    d, _ = domains.landsat_cloud(ssa=0.99, nxy=16, mie=True)
+    n = 0
+    for tab in d.forwardTables:
+        for pf in tab.phaseFunctions[::4]:
+            mus, vals = inversion_inputs(pf)
+            assert np.array_equal(orc.inverse_phase_function(mus, vals, 9001), computeInversePhaseFunction(pf, 9001))
+            n += 1
+    assert n >= 4
+    # a CDF that decreases somewhere takes the reference's sequential hunt in both
+    mus = np.linspace(-1, 1, 9).astype(np.float32)
+    vals = np.array([1, 2, -1.5, 0.5, 3, 1, 0.2, 2, 4], dtype=np.float32)
+    from mcbrat3d_b200.inversePhaseFunctions import find_cdf_brackets
+    cdf = np.zeros(9, np.float32)
+    for i in range(1, 9):
+        cdf[i] = np.float32(cdf[i - 1] + (mus[i] - mus[i - 1]) * np.float32(0.5) * (vals[i] + vals[i - 1]))
+    cdf = (cdf / cdf[-1]).astype(np.float32)
+    assert np.any(np.diff(cdf) < 0)
+    assert find_cdf_brackets(cdf, 101).min() >= 1
