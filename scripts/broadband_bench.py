@@ -25,6 +25,12 @@ g = new_Integrator(d0, device=local)
 specifyParameters(g, minInverseTableSize=9001)
 rs = new_RandomNumberSequence([10, 0, 0])
 src = 2.0e3 * np.exp(-((np.linspace(0.45, 2.1, a.lambdas) - 0.5) / 0.6) ** 2)
+if world > 1:                                                           # create the NCCL communicator outside the timed run
+    import torch, torch.distributed as dist
+    torch.cuda.set_device(local)
+    dist.all_reduce(torch.zeros(1, device="cuda"))
+    torch.cuda.synchronize()
+mpx.synchronizeProcesses()
 t2 = time.perf_counter()
 out = runBroadband(g, tables, common, rs, int(a.photons), int(a.batch), solarMu=0.5, solarSourceFunction=None if a.lw else src,
                    LW=a.lw, surfaceTemp=case["surfaceTemp"], calcRayl=not a.lw)
