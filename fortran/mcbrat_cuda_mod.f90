@@ -27,10 +27,23 @@ module mcbrat_cuda
     integer(c_int32_t) :: reserved(5)
   end type mcb_options
 
+  ! one wavelength's description of an optical component for mcb_assemble_optics (read_SSPTable OPT:200-246)
+  integer(c_int32_t), parameter, public :: MCB_COMP_VOLEXT = 0, MCB_COMP_ABSXSEC = 1, MCB_COMP_PROFILE = 2
+  type, bind(C), public :: mcb_component
+    integer(c_int32_t) :: kind, physIndex, nTable, zLevelBase
+    type(c_ptr)        :: key        ! real(c_float)(nReff)        -- c_loc(key)
+    type(c_ptr)        :: ext        ! real(c_double)(nTable)
+    type(c_ptr)        :: ssa        ! real(c_double)(nTable)
+    type(c_ptr)        :: phaseIdx   ! integer(c_int32_t)(nTable)
+  end type mcb_component
+
   public :: mcb_create, mcb_destroy, mcb_last_error, mcb_set_grid, mcb_set_optics, mcb_set_inverse_table, &
             mcb_set_forward_table, mcb_set_views, mcb_default_options, mcb_set_options,                  &
             mcb_set_solar_source, mcb_set_thermal_source, mcb_run_batch, mcb_get_results,                &
-            mcb_tally_buffer, mcb_synchronize, mcb_status_to_message
+            mcb_tally_buffer, mcb_synchronize, mcb_status_to_message,                                    &
+            mcb_set_physical, mcb_assemble_optics, mcb_get_optics, mcb_build_inverse_table,              &
+            mcb_build_thermal_source, mcb_frequency_distribution, mcb_accumulate_batch,                  &
+            mcb_stats_reset, mcb_run_batches, mcb_stats_buffer, mcb_get_statistics
 
   interface
     integer(c_int) function mcb_create(device, handle) bind(C, name="mcb_create")
@@ -123,6 +136,86 @@ module mcbrat_cuda
       type(c_ptr), value :: handle
       type(c_ptr), intent(out) :: devicePtr
       integer(c_int64_t), intent(out) :: nDoubles
+    end function
+    ! ---- read_SSPTable on the device: commonDomain once (OPT:63-75), then one call per wavelength ----
+    integer(c_int) function mcb_set_physical(handle, nPhys, massConc, Reff, numConc) bind(C, name="mcb_set_physical")
+      import :: c_int, c_ptr, c_double
+      type(c_ptr), value :: handle
+      integer(c_int), value :: nPhys
+      real(c_double), intent(in) :: massConc(*), Reff(*)      ! commonD%massConc(comp,x,y,z), commonD%Reff
+      real(c_double), intent(in) :: numConc(*)                ! commonD%numConc(1,1,:)
+    end function
+    integer(c_int) function mcb_assemble_optics(handle, nc, comps, setup, albedo) bind(C, name="mcb_assemble_optics")
+      import :: c_int, c_ptr, c_double, mcb_component
+      type(c_ptr), value :: handle
+      integer(c_int), value :: nc, setup
+      type(mcb_component), intent(in) :: comps(*)
+      real(c_double), value :: albedo
+    end function
+    integer(c_int) function mcb_get_optics(handle, totalExt, cumExt, ssa, phaseIdx) bind(C, name="mcb_get_optics")
+      import :: c_int, c_ptr
+      type(c_ptr), value :: handle, totalExt, cumExt, ssa, phaseIdx     ! c_loc(array) or c_null_ptr
+    end function
+    integer(c_int) function mcb_build_inverse_table(handle, comp, nS, nE, nAngles, mus, values) &
+        bind(C, name="mcb_build_inverse_table")
+      import :: c_int, c_ptr, c_float, c_int32_t
+      type(c_ptr), value :: handle
+      integer(c_int), value :: comp, nS, nE
+      integer(c_int32_t), intent(in) :: nAngles(*)
+      real(c_float), intent(in) :: mus(*), values(*)
+    end function
+    ! ---- emission_weighting (EMI:424-550) and getFrequencyDistr (EMI:552-573) on the device ----
+    integer(c_int) function mcb_build_thermal_source(handle, temps, lambda_um, surfaceTemp, fracAtmsPower, totalFlux) &
+        bind(C, name="mcb_build_thermal_source")
+      import :: c_int, c_ptr, c_double
+      type(c_ptr), value :: handle
+      real(c_double), intent(in) :: temps(*)
+      real(c_double), value :: lambda_um, surfaceTemp
+      real(c_double), intent(out) :: fracAtmsPower, totalFlux
+    end function
+    integer(c_int) function mcb_frequency_distribution(handle, nLambda, cdf, totalPhotons, seed, distribution) &
+        bind(C, name="mcb_frequency_distribution")
+      import :: c_int, c_ptr, c_double, c_int64_t
+      type(c_ptr), value :: handle
+      integer(c_int), value :: nLambda
+      real(c_double), intent(in) :: cdf(*)
+      integer(c_int64_t), value :: totalPhotons, seed
+      integer(c_int64_t), intent(out) :: distribution(*)
+    end function
+    ! ---- the driver's batch loop and statistics (DRV:949-1052, 1188-1228) on the device ----
+    integer(c_int) function mcb_accumulate_batch(handle, nPhotons, seed, firstPhotonId, nProcessed) &
+        bind(C, name="mcb_accumulate_batch")
+      import :: c_int, c_ptr, c_int64_t
+      type(c_ptr), value :: handle
+      integer(c_int64_t), value :: nPhotons, seed, firstPhotonId
+      integer(c_int64_t), intent(out) :: nProcessed
+    end function
+    integer(c_int) function mcb_stats_reset(handle) bind(C, name="mcb_stats_reset")
+      import :: c_int, c_ptr
+      type(c_ptr), value :: handle
+    end function
+    integer(c_int) function mcb_run_batches(handle, numBatches, photonsPerBatch, seed, firstPhotonId, nProcessed) &
+        bind(C, name="mcb_run_batches")
+      import :: c_int, c_ptr, c_int64_t
+      type(c_ptr), value :: handle
+      integer(c_int64_t), value :: numBatches, photonsPerBatch, seed, firstPhotonId
+      integer(c_int64_t), intent(out) :: nProcessed
+    end function
+    integer(c_int) function mcb_stats_buffer(handle, devicePtr, nDoubles) bind(C, name="mcb_stats_buffer")
+      import :: c_int, c_ptr, c_int64_t
+      type(c_ptr), value :: handle
+      type(c_ptr), intent(out) :: devicePtr
+      integer(c_int64_t), intent(out) :: nDoubles
+    end function
+    integer(c_int) function mcb_get_statistics(handle, solarFlux, meanFluxStats, fluxUpStats, fluxDownStats, &
+        fluxAbsorbedStats, absorbedProfileStats, absorbedVolumeStats, radianceStats, totalNumPhotons, batchesCompleted) &
+        bind(C, name="mcb_get_statistics")
+      import :: c_int, c_ptr, c_double, c_int64_t
+      type(c_ptr), value :: handle
+      real(c_double), value :: solarFlux
+      type(c_ptr), value :: meanFluxStats, fluxUpStats, fluxDownStats, fluxAbsorbedStats, absorbedProfileStats, &
+                            absorbedVolumeStats, radianceStats        ! c_loc(stats array) or c_null_ptr
+      integer(c_int64_t), intent(out) :: totalNumPhotons, batchesCompleted
     end function
   end interface
 
