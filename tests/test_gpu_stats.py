@@ -225,3 +225,52 @@ def test_full_size_landsat_invariants():
         assert r["fluxUp"].min() >= 0 and r["fluxDown"].min() >= 0
     finally:
         finalize_Integrator(g)
+
+
+def _tiny_domain(nx, ny, nz, tau=3.0, ssa=0.9, albedo=0.5, dx=0.25, dz=0.125):
+    from mcbrat3d_b200.opticalProperties import Domain
+    from mcbrat3d_b200.scatteringPhaseFunctions import henyeyGreenstein, new_PhaseFunctionTable
+    x = dx * np.arange(nx + 1); y = dx * np.arange(ny + 1); z = dz * np.arange(nz + 1)
+    d = Domain(x, y, z, surfaceAlbedo=albedo)
+    rng = np.random.default_rng(nx * 100 + ny * 10 + nz)
+    ext = (tau / (nz * dz)) * (0.5 + rng.random((nz, ny, nx)))
+    d.addOpticalComponent("cloud", ext, np.full(ext.shape, ssa), np.ones(ext.shape, np.int32),
+                          new_PhaseFunctionTable([henyeyGreenstein(0.7, 32)], key=[1.0]))
+    d.getOpticalPropertiesByComponent()
+    return d
+
+
+EDGE = [("single_column", 1, 1, 6, 0.5, 0.0), ("single_cell", 1, 1, 1, 0.8, 40.0), ("one_layer", 5, 3, 1, 1.0, 0.0),
+        ("narrow_x", 2, 9, 4, 0.3, 315.0), ("vertical_sun", 3, 3, 5, 1.0, 90.0)]
+
+
+@pytest.mark.parametrize("name,nx,ny,nz,mu0,phi0", EDGE, ids=[e[0] for e in EDGE])
+def test_degenerate_grids_three_sigma(orc, name, nx, ny, nz, mu0, phi0):
+    """Grids narrower than the ghost shell, a single column, a single layer, overhead sun and oblique azimuths:
+    the periodic replicas wrap several times inside one burst (OPT:1782-1796), exits happen in the first cell."""
+    dom = _tiny_domain(nx, ny, nz)
+    case = dict(solarMu=mu0, solarAzimuth=phi0)
+    n, nb = 4000, 24
+    ores, _ = oracle_batches(orc, dom, case, nb, n, 0)
+    gmean, gerr = gpu_batches(dom, case, MCB_ARITH_FAST, nb, n, 0)
+    for q in ("meanFluxUp", "meanFluxDown", "meanFluxAbsorbed"):
+        assert_within("%s %s" % (name, q), gmean[q], gerr[q], ores[q][0], ores[q][1], 3.5)
+    closure = gmean["meanFluxUp"] + 0.5 * gmean["meanFluxDown"] + gmean["meanFluxAbsorbed"]
+    assert abs(float(np.ravel(closure)[0]) - 1.0) < 5e-3
+
+
+def test_conservative_scattering_and_reflecting_surface(orc):
+    """ssa = 1 and albedo = 1: nothing is absorbed, every photon leaves through the top, however long it takes."""
+    dom = _tiny_domain(4, 4, 4, tau=2.0, ssa=1.0, albedo=1.0)
+    g = new_Integrator(dom)
+    try:
+        rs = new_RandomNumberSequence(9)
+        n = 200000
+        ps = new_PhotonStream(0.7, 20.0, n, rs)
+        assert computeRadiativeTransfer(g, dom, rs, ps, n) == n
+        r = reportResults(g, meanFluxUp=True, meanFluxAbsorbed=True)
+        c = getCounters(g)
+        assert c["bad"] == 0 and c["rouletteKills"] == 0
+        assert abs(float(r["meanFluxUp"]) - 1.0) < 1e-5 and float(r["meanFluxAbsorbed"]) == 0.0
+    finally:
+        finalize_Integrator(g)
