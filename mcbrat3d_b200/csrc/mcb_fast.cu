@@ -117,10 +117,11 @@ __device__ __forceinline__ int find_cell(const float *e, int n, float x) {
 }
 
 // fold a cell index that ran into the periodic ghost shell (|excursion| <= MCB_GHOST) back into [0, n).
-// n is launch-invariant: grids at least as wide as the shell need one conditional add each way; only
+// WIDE grids (nx, ny >= MCB_GHOST, decided at launch) need one conditional add each way and no branch; only
 // narrower ones (the 1-column step cloud) can be several periods off.
+template <bool WIDE>
 __device__ __forceinline__ int wrap_index(int i, int n) {
-  if (n >= GH) {
+  if (WIDE) {
     i += i < 0 ? n : 0;
     i -= i >= n ? n : 0;
   } else {
@@ -133,17 +134,19 @@ __device__ __forceinline__ int wrap_index(int i, int n) {
 // padded linear cell (relative to the first real cell) -> (ix, iy, iz): two divisions by
 // launch-invariant divisors with the precomputed multipliers of the parameter block (exact for every
 // padded cell index < 2^31); x, y come back folded into the domain.
+template <bool WIDE>
 __device__ __forceinline__ void cell_decode(const DevDomain &P, int rel, int &ix, int &iy, int &iz) {
   const uint32_t c = (uint32_t)(rel + P.ghostOrigin);
   const uint32_t z = (uint32_t)(((uint64_t)P.divSliceM * c) >> P.divSliceS);
   const uint32_t rem = c - z * (uint32_t)(P.nxp * P.nyp);
   const uint32_t y = (uint32_t)(((uint64_t)P.divRowM * rem) >> P.divRowS);
-  ix = wrap_index((int)(rem - y * (uint32_t)P.nxp) - GH, P.nx);
-  iy = wrap_index((int)y - GH, P.ny);
+  ix = wrap_index<WIDE>((int)(rem - y * (uint32_t)P.nxp) - GH, P.nx);
+  iy = wrap_index<WIDE>((int)y - GH, P.ny);
   iz = (int)z - GH;
 }
 
-enum { MARCH_ON = 0, MARCH_TOP = 1, MARCH_BOTTOM = 2, MARCH_HIT = 3 };
+// what a burst ends with IS the lane's next state (no translation in the hot loop)
+enum { MARCH_ON = ST_MARCH, MARCH_HIT = ST_SCATTER, MARCH_BOTTOM = ST_SURFACE, MARCH_TOP = ST_TOP };
 
 // One burst of the marcher (accumulateExtinctionAlongPath, OPT:1697-1814): B cells.  The cells a
 // ray visits and the lengths of its segments depend on geometry only, never on the extinction read,
@@ -160,7 +163,7 @@ enum { MARCH_ON = 0, MARCH_TOP = 1, MARCH_BOTTOM = 2, MARCH_HIT = 3 };
 //   * the ray left through the top / the surface: r.t = distance to that boundary, (ix,iy) = column of
 //     the exit point -> MARCH_TOP / MARCH_BOTTOM;
 //   * otherwise x, y are folded back into the domain -> MARCH_ON.
-template <bool REG, int B>
+template <bool REG, bool WIDE, int B>
 __device__ __forceinline__ int march_burst(Ray &r, const DevDomain &P, const Grid &G, const float *__restrict__ extp,
                                            float &ext, float target, unsigned &crossings) {
   float tE[B], sg[B];
@@ -188,21 +191,20 @@ __device__ __forceinline__ int march_burst(Ray &r, const DevDomain &P, const Gri
   // ENTRY of the hit cell, so only its extinction and index have to be carried along
   float acc = ext, tS = t0, hS = 1.0f;
   int hC = 0;
-  unsigned nIn = 0u;                                   // cells entered up to and including the hit cell
+  int hK = B - 1;                                      // burst position of the hit cell
   bool found = false;
 #pragma unroll
   for (int k = 0; k < B; ++k) {
     const float en = fmaf(tE[k] - tS, sg[k], acc);
     const bool h = !found && en > target;
-    hS = h ? sg[k] : hS; hC = h ? ck[k] : hC;
+    hS = h ? sg[k] : hS; hC = h ? ck[k] : hC; hK = h ? k : hK;
     found = found || h;
-    nIn += found && !h ? 0u : 1u;
     acc = found ? acc : en; tS = found ? tS : tE[k];
   }
   if (found) {
-    crossings += nIn;
+    crossings += (unsigned)(hK + 1);               // cells entered up to and including the hit cell
     r.t = tS + __fdividef(target - acc, hS);           // where the target optical depth is met (OPT:1731)
-    cell_decode(P, hC, r.ix, r.iy, r.iz);
+    cell_decode<WIDE>(P, hC, r.ix, r.iy, r.iz);
     return MARCH_HIT;
   }
   ext = acc;
@@ -229,8 +231,8 @@ __device__ __forceinline__ int march_burst(Ray &r, const DevDomain &P, const Gri
   crossings += (unsigned)B;
   r.t = tS;
   if (REG) {
-    r.ix = wrap_index(r.ix, P.nx);
-    r.iy = wrap_index(r.iy, P.ny);
+    r.ix = wrap_index<WIDE>(r.ix, P.nx);
+    r.iy = wrap_index<WIDE>(r.iy, P.ny);
   } else {                                             // keep (edge - origin) invariant under the fold
     while (r.ix < 0) { r.ix += P.nx; r.ox += P.fLx; }
     while (r.ix >= P.nx) { r.ix -= P.nx; r.ox -= P.fLx; }
@@ -238,20 +240,6 @@ __device__ __forceinline__ int march_burst(Ray &r, const DevDomain &P, const Gri
     while (r.iy >= P.ny) { r.iy -= P.ny; r.oy -= P.fLy; }
   }
   return MARCH_ON;
-}
-
-// Trace to the boundary or to an optical-depth target (the local-estimate rays, INT:1734-1739,
-// 1764-1795).  Returns the accumulated optical depth; where = 0 stopped at target, 1 top, 2 bottom.
-template <bool REG>
-__device__ float ray_trace(Ray &r, const DevDomain &P, const Grid &G, const float *__restrict__ extp, bool hasTarget, float target,
-                           int &where, unsigned &crossings) {
-  float ext = 0.0f;
-  const float tgt = hasTarget ? target : FLT_MAX;
-  for (;;) {
-    const int ev = march_burst<REG, 4>(r, P, G, extp, ext, tgt, crossings);
-    if (ev == MARCH_HIT) { where = 0; return target; }
-    if (ev != MARCH_ON) { where = ev; return ext; }
-  }
 }
 
 __device__ __forceinline__ void dir_from(float mu, float phi, float &dx, float &dy, float &dz) {  // INT:1876-1894
@@ -317,7 +305,7 @@ __device__ __forceinline__ void le_post(float *sle, int lane, const DevDomain &P
   if (P.opt.useRussianRouletteForIntensity) rng.blk += (uint32_t)((P.nDir + 1) >> 1);
 }
 
-template <bool REG>
+template <bool REG, bool WIDE>
 __device__ void le_run(const DevDomain &P, const Grid &G, const Tally &T, uint32_t k0, uint32_t k1, unsigned posted,
                        float *sle, unsigned *queue, int lane, Counts &cnt) {
   const int nDir = P.nDir;
@@ -393,7 +381,7 @@ __device__ void le_run(const DevDomain &P, const Grid &G, const Tally &T, uint32
     }
     if (__all_sync(FULL, done)) break;
     if (phase != PH_IDLE) {
-      const int ev = march_burst<REG, 4>(r, P, G, P.extp, ext, tgt, cnt.leCrossings);
+      const int ev = march_burst<REG, WIDE, 4>(r, P, G, P.extp, ext, tgt, cnt.leCrossings);
       if (ev != MARCH_ON) {
         float contribution = 0.0f;
         bool finished = true;
@@ -432,7 +420,7 @@ __device__ void le_run(const DevDomain &P, const Grid &G, const Tally &T, uint32
   __syncwarp();
 }
 
-template <int THREADS, bool REG, int MINBLOCKS, int BURST, bool LE>
+template <int THREADS, bool REG, bool WIDE, int MINBLOCKS, int BURST, bool LE>
 __global__ void __launch_bounds__(THREADS, MINBLOCKS)
 batch_kernel(const __grid_constant__ DevDomain P, long long nPhotons, uint64_t seed, uint64_t firstPhotonId,
              unsigned long long *workCounter, int parkThreshold, const SmemPlan plan) {
@@ -546,7 +534,7 @@ batch_kernel(const __grid_constant__ DevDomain P, long long nPhotons, uint64_t s
     }
     if (LE && P.nDir > 0) {                                                   // the whole warp serves the posted requests
       const unsigned pm = __ballot_sync(FULL, posted);
-      if (pm) le_run<REG>(P, G, T, k0, k1, pm, sle, leQueue, lane, cnt);
+      if (pm) le_run<REG, WIDE>(P, G, T, k0, k1, pm, sle, leQueue, lane, cnt);
       posted = false;
     }
     // ---- finished lanes take the next photons: one atomic per warp (getNextPhoton, ILL:561-590) ----
@@ -673,7 +661,7 @@ batch_kernel(const __grid_constant__ DevDomain P, long long nPhotons, uint64_t s
     }
     if (LE && P.nDir > 0 && P.opt.LW_flag > 0.0f) {                            // emission at birth (INT:513-542)
       const unsigned pm = __ballot_sync(FULL, posted);
-      if (pm) le_run<REG>(P, G, T, k0, k1, pm, sle, leQueue, lane, cnt);
+      if (pm) le_run<REG, WIDE>(P, G, T, k0, k1, pm, sle, leQueue, lane, cnt);
     }
 
     // =========================== march phase: bursts until enough lanes are parked ===========================
@@ -682,8 +670,7 @@ batch_kernel(const __grid_constant__ DevDomain P, long long nPhotons, uint64_t s
       const unsigned live = __ballot_sync(FULL, state != ST_DONE);
       if (mk == 0u || __popc(live & ~mk) >= parkThreshold) break;
       if (state == ST_MARCH) {
-        const int ev = march_burst<REG, BURST>(r, P, G, extp, ext, tau, cnt.crossings);
-        state = ev == MARCH_ON ? ST_MARCH : ev == MARCH_HIT ? ST_SCATTER : ev == MARCH_TOP ? ST_TOP : ST_SURFACE;
+        state = march_burst<REG, WIDE, BURST>(r, P, G, extp, ext, tau, cnt.crossings);
       }
     }
   }
@@ -736,11 +723,11 @@ __global__ void philox_kat_kernel(uint64_t seed, uint64_t photon, int n, uint32_
 
 #include <cstdlib>
 
-template <bool REG, int MINBLOCKS, int BURST, bool LE>
+template <bool REG, bool WIDE, int MINBLOCKS, int BURST, bool LE>
 static void launch(const DevDomain &P, long long nPhotons, uint64_t seed, uint64_t firstPhotonId, int numSMs,
                    unsigned long long *workCounter, cudaStream_t stream) {
   constexpr int THREADS = 128;
-  auto kernel = mcbfast::batch_kernel<THREADS, REG, MINBLOCKS, BURST, LE>;
+  auto kernel = mcbfast::batch_kernel<THREADS, REG, WIDE, MINBLOCKS, BURST, LE>;
   // shared-memory plan: privatise the tallies when the column / cell grid is small enough to be an
   // atomic hot spot (homogeneous slabs, the 32-column step cloud); large grids spread their
   // atomics over many L2 lines and go straight to the f64 buffer.
@@ -780,14 +767,16 @@ void mcb_launch_fast_batch(const DevDomain &P, long long nPhotons, uint64_t seed
   if (occEnv == -2) { const char *e = getenv("MCB_BLOCKS_PER_SM"); occEnv = e ? atoi(e) : -1; }
   if (burst < 0) { const char *e = getenv("MCB_BURST"); burst = e ? atoi(e) : 8; }
   const int occ = occEnv > 0 ? occEnv : (P.nDir > 0 ? 6 : 8);
-#define MCB_GO(REG, OCC, BURST) do { \
-    if (P.nDir > 0) launch<REG, OCC, BURST, true>(P, nPhotons, seed, firstPhotonId, numSMs, workCounter, stream); \
-    else launch<REG, OCC, BURST, false>(P, nPhotons, seed, firstPhotonId, numSMs, workCounter, stream); } while (0)
+#define MCB_GO(REG, WIDE, OCC, BURST) do { \
+    if (P.nDir > 0) launch<REG, WIDE, OCC, BURST, true>(P, nPhotons, seed, firstPhotonId, numSMs, workCounter, stream); \
+    else launch<REG, WIDE, OCC, BURST, false>(P, nPhotons, seed, firstPhotonId, numSMs, workCounter, stream); } while (0)
+  const bool wide = P.nx >= MCB_GHOST && P.ny >= MCB_GHOST;      // no grid period shorter than the ghost shell
   if (P.xyRegular && P.zRegular) {            // burst length <= MCB_GHOST (the ghost shell is that deep)
-    if (burst >= 8) { if (occ >= 8) MCB_GO(true, 8, 8); else if (occ >= 6) MCB_GO(true, 6, 8); else if (occ <= 4) MCB_GO(true, 4, 8); else MCB_GO(true, 5, 8); }
-    else { if (occ >= 8) MCB_GO(true, 8, 4); else if (occ >= 6) MCB_GO(true, 6, 4); else if (occ <= 4) MCB_GO(true, 4, 4); else MCB_GO(true, 5, 4); }
+    if (!wide) { if (P.nDir > 0) MCB_GO(true, false, 6, 8); else MCB_GO(true, false, 8, 8); }
+    else if (burst >= 8) { if (occ >= 8) MCB_GO(true, true, 8, 8); else if (occ >= 6) MCB_GO(true, true, 6, 8); else MCB_GO(true, true, 4, 8); }
+    else { if (occ >= 8) MCB_GO(true, true, 8, 4); else if (occ >= 6) MCB_GO(true, true, 6, 4); else MCB_GO(true, true, 4, 4); }
   } else {
-    if (burst >= 8) MCB_GO(false, 4, 8); else MCB_GO(false, 4, 4);
+    if (burst >= 8) MCB_GO(false, false, 4, 8); else MCB_GO(false, false, 4, 4);
   }
 #undef MCB_GO
 }
