@@ -274,3 +274,29 @@ def test_conservative_scattering_and_reflecting_surface(orc):
         assert abs(float(r["meanFluxUp"]) - 1.0) < 1e-5 and float(r["meanFluxAbsorbed"]) == 0.0
     finally:
         finalize_Integrator(g)
+
+
+def test_crossing_counts_agree_on_cloud_scenes():
+    """Geometric bookkeeping of the burst marcher (roll-back to the hit cell, exits inside a burst, ghost-shell
+    folds) on scenes that are ~2/3 empty: cell crossings and scatterings per photon of the fast kernel equal those
+    of the reference-arithmetic kernel, which visits one cell at a time (OPT:1697-1814)."""
+    for make, n in ((lambda: domains.landsat_cloud(ssa=0.99, nxy=32), 400000), (lambda: domains.bench_domain(nxy=40, nz=48), 300000)):
+        dom, case = make()
+        out = {}
+        for arith in (MCB_ARITH_FAST, MCB_ARITH_REFERENCE):
+            g = new_Integrator(dom)
+            try:
+                specifyParameters(g, minInverseTableSize=10001, arithmetic=arith)
+                rs = new_RandomNumberSequence([10, 1, 0])
+                ps = new_PhotonStream(case["solarMu"], case["solarAzimuth"], n, rs)
+                computeRadiativeTransfer(g, dom, rs, ps, n)
+                out[arith] = (reportResults(g, meanFluxUp=True, meanFluxDown=True, meanFluxAbsorbed=True), getCounters(g))
+            finally:
+                finalize_Integrator(g)
+        a, b = out[MCB_ARITH_FAST], out[MCB_ARITH_REFERENCE]
+        assert abs(a[1]["crossings"] - b[1]["crossings"]) < 4e-3 * b[1]["crossings"], (a[1]["crossings"], b[1]["crossings"])
+        assert abs(a[1]["scatters"] - b[1]["scatters"]) < 6e-3 * b[1]["scatters"]
+        assert a[1]["bad"] == 0
+        for q in ("meanFluxUp", "meanFluxDown", "meanFluxAbsorbed"):
+            p = float(b[0][q])
+            assert abs(float(a[0][q]) - p) < 4.5 * np.sqrt(2.0 * max(p * (1 - p), 1e-4) / n), q
