@@ -1,0 +1,71 @@
+"""The compiled host (host/mcbrat_host.hpp + examples/i3rc_driver.cpp, C++17 straight above the C ABI) against the
+Python host mirror: same decks, same seeds.  CPU: it builds and fails loudly without a GPU.  GPU: its batch
+statistics agree with the Python path within the combined Monte Carlo error."""
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+EXE = os.path.join(ROOT, "examples", "i3rc_driver")
+
+
+def _build():
+    csrc = os.path.join(ROOT, "mcbrat3d_b200", "csrc")
+    if not os.path.exists(os.path.join(csrc, "libmcbrat_cuda.so")):
+        subprocess.check_call(["make", "-C", csrc], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-Wall", "-o", EXE, os.path.join(ROOT, "examples", "i3rc_driver.cpp"),
+                           "-L" + csrc, "-lmcbrat_cuda", "-Wl,-rpath,$ORIGIN/../mcbrat3d_b200/csrc"])
+
+
+def test_compiled_host_builds_and_has_no_cpu_fallback():
+    import torch
+    _build()
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    p = subprocess.run([EXE, "homog", "2", "1000"], capture_output=True, text=True)
+    assert p.returncode != 0 and "no CPU fallback" in p.stderr
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("deck,views", [("homog", 0), ("stepcloud", 0), ("stepcloud", 1)])
+def test_compiled_host_matches_python_host(deck, views):
+    from mcbrat3d_b200 import domains
+    from mcbrat3d_b200.batchStatistics import computeRadiativeTransferBatches, reportStatistics, resetDeviceStatistics
+    from mcbrat3d_b200.monteCarloIllumination import new_PhotonStream
+    from mcbrat3d_b200.monteCarloRadiativeTransfer import finalize_Integrator, new_Integrator, specifyParameters
+    from mcbrat3d_b200.RandomNumbersForMC import new_RandomNumberSequence
+    _build()
+    nb, n = 24, 40000
+    out = subprocess.run([EXE, deck, str(nb), str(n), "10", str(views)], capture_output=True, text=True, check=True).stdout
+    m = re.search(r"first batch: (\d+) photons\s+meanFluxUp (\S+) meanFluxDown (\S+) meanFluxAbsorbed (\S+)", out)
+    assert int(m.group(1)) == n
+    cpp = {k: tuple(float(v) for v in re.search(k + r"\s+(\S+) \+- (\S+)", out).groups())
+           for k in ("Flux Up", "Flux Down", "Flux Absorbed")}
+    assert "batches %d photons %d" % (nb, nb * n) in out
+    dom, case = domains.homogeneous_slab(ssa=0.99) if deck == "homog" else domains.step_cloud(ssa=0.99, solarMu=0.5)
+    g = new_Integrator(dom)
+    try:
+        if views:
+            specifyParameters(g, intensityMus=case["intensityMus"], intensityPhis=case["intensityPhis"], computeIntensity=True,
+                              useRussianRouletteForIntensity=True, zetaMin=0.3)
+        specifyParameters(g, minInverseTableSize=10001)
+        rs = new_RandomNumberSequence([10, 1, 0])
+        rs.nextPhotonId = n                                   # the driver spends its first n photon ids on the single batch
+        ps = new_PhotonStream(0.5, 0.0, nb * n, rs)
+        resetDeviceStatistics(g, dom)
+        computeRadiativeTransferBatches(g, dom, rs, ps, n, nb)
+        mean, err, tot, done = reportStatistics(g)
+    finally:
+        finalize_Integrator(g)
+    for k, q in (("Flux Up", "meanFluxUp"), ("Flux Down", "meanFluxDown"), ("Flux Absorbed", "meanFluxAbsorbed")):
+        sig = np.hypot(cpp[k][1], float(err[q]))
+        assert abs(cpp[k][0] - float(mean[q])) <= 4.0 * sig + 1e-6, (k, cpp[k], float(mean[q]), float(err[q]))
+    albedo = 0.2 if deck == "homog" else 0.0
+    assert abs(cpp["Flux Up"][0] + (1 - albedo) * cpp["Flux Down"][0] + cpp["Flux Absorbed"][0] - 1.0) < 4e-3
+    if views:
+        rad = [float(v) for v in re.findall(r"Radiance view \d+\s+(\S+)", out)]
+        want = mean["intensity"].reshape(5, -1).mean(axis=1)
+        assert len(rad) == 5 and np.allclose(rad, want, rtol=0.05)
