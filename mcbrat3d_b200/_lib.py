@@ -13,7 +13,9 @@ from typing import Optional
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libmcbrat_cuda.so")
+# MCB_LIB_DEBUG=1 loads the bounds-checked build of the throughput kernel (csrc/Makefile target dbg)
+LIB_PATH = os.path.join(_HERE, "csrc", "libmcbrat_cuda_dbg.so" if os.environ.get("MCB_LIB_DEBUG") == "1"
+                        else "libmcbrat_cuda.so")
 
 MCB_ARITH_FAST = 0
 MCB_ARITH_REFERENCE = 1

@@ -242,6 +242,7 @@ int mcb_set_grid(mcb_handle *h, int nx, int ny, int nz,
   P.nxp = nx + 2 * MCB_GHOST; P.nyp = ny + 2 * MCB_GHOST;
   if ((long long)P.nxp * P.nyp * (nz + 2 * MCB_GHOST) >= (1LL << 31)) FAIL(h, "mcb_set_grid: more than 2^31 cells");
   P.ghostOrigin = MCB_GHOST + P.nxp * (MCB_GHOST + P.nyp * MCB_GHOST);
+  P.paddedCells = (long long)P.nxp * P.nyp * (nz + 2 * MCB_GHOST);
   magic_divisor((uint32_t)P.nxp * (uint32_t)P.nyp, &P.divSliceM, &P.divSliceS);
   magic_divisor((uint32_t)P.nxp, &P.divRowM, &P.divRowS);
   h->haveGrid = true; h->haveOptics = false; h->haveSource = false; h->havePhysical = false;
@@ -405,7 +406,7 @@ int mcb_set_inverse_table(mcb_handle *h, int comp, int nS, int nE, const float *
   if (comp < 1 || comp > h->P.nc || nS < 2 || nE < 1 || !T) FAIL(h, "mcb_set_inverse_table: bad arguments");
   const int c = comp - 1;
   if (stage(h, &h->dInv[c], T, sizeof(float) * (size_t)nS * nE)) return 1;
-  h->P.inv[c] = (const float *)h->dInv[c]; h->P.invS[c] = nS; h->invE[c] = nE; h->haveInv[c] = true;
+  h->P.inv[c] = (const float *)h->dInv[c]; h->P.invS[c] = nS; h->invE[c] = nE; h->P.invE[c] = nE; h->haveInv[c] = true;
   return 0;
 }
 
@@ -436,7 +437,7 @@ int mcb_build_inverse_table(mcb_handle *h, int comp, int nS, int nE, const int32
                            (float *)h->dInv[c], (float *)(base + bOff + 2 * bF), h->stream);
   CK(h, cudaGetLastError());
   if (settle(h)) return 1;
-  h->P.inv[c] = (const float *)h->dInv[c]; h->P.invS[c] = nS; h->invE[c] = nE; h->haveInv[c] = true;
+  h->P.inv[c] = (const float *)h->dInv[c]; h->P.invS[c] = nS; h->invE[c] = nE; h->P.invE[c] = nE; h->haveInv[c] = true;
   return 0;
 }
 
@@ -459,7 +460,7 @@ int mcb_set_forward_table(mcb_handle *h, int comp, int nS, int nE, const float *
   if (stage(h, &h->dFwd[c], Pf, sizeof(float) * (size_t)nS * nE)) return 1;
   if (stage(h, &h->dFwdOrig[c], Porig ? Porig : Pf, sizeof(float) * (size_t)nS * nE)) return 1;
   h->P.fwd[c] = (const float *)h->dFwd[c]; h->P.fwdOrig[c] = (const float *)h->dFwdOrig[c];
-  h->P.fwdS[c] = nS; h->fwdE[c] = nE; h->haveFwd[c] = true;
+  h->P.fwdS[c] = nS; h->fwdE[c] = nE; h->P.fwdE[c] = nE; h->haveFwd[c] = true;
   return 0;
 }
 

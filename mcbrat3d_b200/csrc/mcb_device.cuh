@@ -32,6 +32,7 @@ struct DevDomain {
                                               // (periodic replicas in x, y; zeros above and below), pointing AT the
                                               // first real cell: cell (ix,iy,iz) is extp[ix + nxp*(iy + nyp*iz)]
   int nxp, nyp, ghostOrigin;                  // padded row / slice lengths; linear offset of the first real cell
+  long long paddedCells;                      // (nx+2G)(ny+2G)(nz+2G)
   const float *cum32, *ssa32;                 // (nx,ny,nz,nc)
   const uint16_t *idx16;                      // (nx,ny,nz,nc)
   float fx0, fy0, fz0, fLx, fLy, fLz;         // single-precision grid scalars (fast kernel, constant bank)
@@ -39,7 +40,7 @@ struct DevDomain {
   uint32_t divSliceM, divRowM;                // padded cell -> (ix,iy,iz): q = (M * n) >> S, exact for n < 2^31
   int divSliceS, divRowS;
   // ---- tables ----
-  const float *inv[MCB_MAX_COMP];  int invS[MCB_MAX_COMP];
+  const float *inv[MCB_MAX_COMP];  int invS[MCB_MAX_COMP];  int invE[MCB_MAX_COMP], fwdE[MCB_MAX_COMP];   // steps, entries
   const float *fwd[MCB_MAX_COMP];  const float *fwdOrig[MCB_MAX_COMP];  int fwdS[MCB_MAX_COMP];
   // ---- views ----
   int nDir;
@@ -58,8 +59,25 @@ struct DevDomain {
   unsigned long long *counters;               // mcb_counters as 16 x u64
 };
 
+// Bounds-checked build (libmcbrat_cuda_dbg.so, -DMCB_BOUNDS_CHECK): every gather index of the fast kernel is tested
+// against its array and violations are counted in counters[CNT_BAD] (the access is clamped, not made).  The pool
+// has no compute-sanitizer, so tests/test_gpu_bounds.py runs the cases through this build and asserts zero.
+#ifdef MCB_BOUNDS_CHECK
+#define MCB_CHECK_INDEX(P, i, n) mcb_checked_index((P), (long long)(i), (long long)(n))
+__device__ __forceinline__ long long mcb_checked_index(const struct DevDomain &P, long long i, long long n);
+#else
+#define MCB_CHECK_INDEX(P, i, n) (i)
+#endif
+
 enum { CNT_PHOTONS = 0, CNT_CROSSINGS, CNT_SCATTERS, CNT_SURFACE, CNT_TOP, CNT_BAD,
        CNT_LE_RAYS, CNT_LE_CROSSINGS, CNT_RR_KILLS, CNT_SURFACE_KILLS, CNT_N };
+
+#ifdef MCB_BOUNDS_CHECK
+__device__ __forceinline__ long long mcb_checked_index(const DevDomain &P, long long i, long long n) {
+  if (i < 0 || i >= n) { atomicAdd(&P.counters[CNT_BAD], 1ull); return 0; }
+  return i;
+}
+#endif
 
 // ---------------------------------------------------------------------------------------
 // Philox4x32-10 counter-based generator (Salmon et al. 2011).  One stream per photon:

@@ -29,6 +29,12 @@ namespace mcbfast {
 #define PI32 3.14159265358979312f
 #define TINY32 FLT_MIN
 #define GH MCB_GHOST
+// gather of the padded extinction field (rel = index relative to the first real cell; may be negative in the shell)
+#ifdef MCB_BOUNDS_CHECK
+#define EXT_AT(P, extp, rel) __ldg((extp) + (mcb_checked_index((P), (long long)(rel) + (P).ghostOrigin, (P).paddedCells) - (P).ghostOrigin))
+#else
+#define EXT_AT(P, extp, rel) __ldg((extp) + (rel))
+#endif
 
 enum { ST_DEAD = 0, ST_MARCH = 1, ST_SCATTER = 2, ST_SURFACE = 3, ST_TOP = 4, ST_BORN = 5, ST_DONE = 6 };
 
@@ -186,7 +192,7 @@ __device__ __forceinline__ int march_burst(Ray &r, const DevDomain &P, const Gri
     }
   }
 #pragma unroll
-  for (int k = 0; k < B; ++k) sg[k] = __ldg(extp + ck[k]);
+  for (int k = 0; k < B; ++k) sg[k] = EXT_AT(P, extp, ck[k]);
   // accumulate until the target is passed (OPT:1729-1738); from there on acc / tS stay frozen at the
   // ENTRY of the hit cell, so only its extinction and index have to be carried along
   float acc = ext, tS = t0, hS = 1.0f;
@@ -265,14 +271,17 @@ struct Tally {
   int cols;
 };
 __device__ __forceinline__ void add_flux(const DevDomain &P, const Tally &T, int which, int col, float v) {
+  col = (int)MCB_CHECK_INDEX(P, col, T.cols);
   if (T.sFlux) atomicAdd(&T.sFlux[which * T.cols + col], v);
   else atomicAdd(&P.tally[(which == 0 ? P.offFluxUp : which == 1 ? P.offFluxDown : P.offFluxAbs) + col], (double)v);
 }
 __device__ __forceinline__ void add_vol(const DevDomain &P, const Tally &T, int cell, float v) {
+  cell = (int)MCB_CHECK_INDEX(P, cell, (long long)T.cols * P.nz);
   if (T.sVol) atomicAdd(&T.sVol[cell], v);
   else atomicAdd(&P.tally[P.offVolAbs + cell], (double)v);
 }
 __device__ __forceinline__ void add_intensity(const DevDomain &P, const Tally &T, int dir, int col, int comp, float v) {
+  col = (int)MCB_CHECK_INDEX(P, col, T.cols); dir = (int)MCB_CHECK_INDEX(P, dir, P.nDir); comp = (int)MCB_CHECK_INDEX(P, comp, P.nc + 1);
   if (T.sInt) atomicAdd(&T.sInt[dir * T.cols + col], v);
   else atomicAdd(&P.tally[P.offInt + col + (long long)T.cols * dir], (double)v);
   atomicAdd(&P.tally[P.offIntByComp + col + (long long)T.cols * (dir + (long long)P.nDir * comp)], (double)v);
@@ -344,16 +353,16 @@ __device__ void le_run(const DevDomain &P, const Grid &G, const Tally &T, uint32
           const float ang = acosf(proj);
           const int c = component - 1;
           const int cell = r.ix + P.nx * (r.iy + P.ny * r.iz);
-          const int pidx = (int)__ldg(&P.idx16[cell + cells * c]);
+          const int pidx = (int)__ldg(&P.idx16[MCB_CHECK_INDEX(P, cell, cells) + cells * c]);
           const float *tab = ((P.opt.useHybridPhaseFunsForIntenCalcs && order <= P.opt.numOrdersOrigPhaseFunIntenCalcs)
-                                  ? P.fwdOrig[c] : P.fwd[c]) + (size_t)(pidx - 1) * P.fwdS[c];
+                                  ? P.fwdOrig[c] : P.fwd[c]) + (size_t)MCB_CHECK_INDEX(P, pidx - 1, P.fwdE[c]) * P.fwdS[c];
           const int nS = P.fwdS[c];                                                // INT:1855-1870
           const float dTheta = PI32 / (float)(nS - 1);
           const int ai = (int)(ang / dTheta) + 1;
           float val;
           if (ai < nS) {
             const float wt = 1.0f - (ang - (float)(ai - 1) * dTheta) / dTheta;
-            val = wt * __ldg(&tab[ai - 1]) + (1.0f - wt) * __ldg(&tab[ai]);
+            val = wt * __ldg(&tab[MCB_CHECK_INDEX(P, ai - 1, nS)]) + (1.0f - wt) * __ldg(&tab[MCB_CHECK_INDEX(P, ai, nS)]);
           } else {
             val = __ldg(&tab[nS - 1]);
           }
@@ -511,10 +520,10 @@ batch_kernel(const __grid_constant__ DevDomain P, long long nPhotons, uint64_t s
       // component's interval (uniform again, conditional on the pick), decides the roulette
       float lo = 0.0f, hi = 1.0f;
       for (int c = 1; c < P.nc; ++c) {                                         // findIndex on (0, cumExt(:)), NUM:262-315
-        const float cc = __ldg(&P.cum32[cell + (size_t)cells * (size_t)(c - 1)]);
+        const float cc = __ldg(&P.cum32[MCB_CHECK_INDEX(P, cell, cells) + (size_t)cells * (size_t)(c - 1)]);
         if (uNext >= cc) { comp = c + 1; lo = cc; } else { hi = fminf(hi, cc); }
       }
-      const float ssa = __ldg(&P.ssa32[cell + (size_t)cells * (size_t)(comp - 1)]);
+      const float ssa = __ldg(&P.ssa32[MCB_CHECK_INDEX(P, cell, cells) + (size_t)cells * (size_t)(comp - 1)]);
       if (ssa < 1.0f) {                                                        // INT:765-771
         const float absorbed = w * (1.0f - ssa);
         add_flux(P, T, 2, r.ix + P.nx * r.iy, absorbed);
@@ -626,15 +635,15 @@ batch_kernel(const __grid_constant__ DevDomain P, long long nPhotons, uint64_t s
         r.iz = 0;
       } else {                                                                 // ST_SCATTER, INT:813-819
         const int c = comp - 1;
-        const int pidx = (int)__ldg(&P.idx16[cell + (size_t)cells * (size_t)c]);
+        const int pidx = (int)__ldg(&P.idx16[MCB_CHECK_INDEX(P, cell, cells) + (size_t)cells * (size_t)c]);
         const int nS = P.invS[c];
-        const float *tab = P.inv[c] + (size_t)(pidx - 1) * nS;
+        const float *tab = P.inv[c] + (size_t)MCB_CHECK_INDEX(P, pidx - 1, P.invE[c]) * nS;
         const float rn = u.x;                                                  // computeScatteringAngle INT:1594-1621
         const int k = (int)(rn * (float)nS) + 1;
         float theta;
         if (k < nS) {
           const float left = rn - (float)(k - 1) / (float)nS;
-          theta = (1.0f - left) * __ldg(&tab[k - 1]) + left * __ldg(&tab[k]);
+          theta = (1.0f - left) * __ldg(&tab[MCB_CHECK_INDEX(P, k - 1, nS)]) + left * __ldg(&tab[MCB_CHECK_INDEX(P, k, nS)]);
         } else {
           theta = __ldg(&tab[nS - 1]);
         }
