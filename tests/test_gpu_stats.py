@@ -300,3 +300,34 @@ def test_crossing_counts_agree_on_cloud_scenes():
         for q in ("meanFluxUp", "meanFluxDown", "meanFluxAbsorbed"):
             p = float(b[0][q])
             assert abs(float(a[0][q]) - p) < 4.5 * np.sqrt(2.0 * max(p * (1 - p), 1e-4) / n), q
+
+
+def test_hybrid_tables_and_contribution_limit_three_sigma(orc):
+    """The throughput kernel with hybrid forward tables (orders > 1 use the Gaussian-peaked table) and limited
+    contributions redistributed at the end of the batch (INT:294-322): mean radiances within 3 sigma of the oracle."""
+    dom, case = domains.step_cloud(ssa=0.99, solarMu=0.5)
+    n, nb = 1500, 32
+    od = orc.OracleDomain(dom, tableSize=10001, forward=True, hybrid=True, hybridWidth=7.0)
+    og = orc.OracleIntegrator(od, useHybridPhaseFunsForIntenCalcs=1, numOrdersOrigPhaseFunIntenCalcs=1,
+                              limitIntensityContributions=1, maxIntensityContribution=0.5)
+    og.set_views(case["intensityMus"], case["intensityPhis"])
+    tot, st = og.run_batches(nb, n, source=0, iseed=10, rank=1, thread=0, solarMu=case["solarMu"], solarAzimuth=case["solarAzimuth"])
+    cols = dom.numX * dom.numY
+    m, e = orc.finalise(st["radianceStats"], 1.0, tot, nb)
+    om = m.reshape(-1, cols).mean(axis=1); oe = np.sqrt((e.reshape(-1, cols) ** 2).sum(axis=1)) / cols
+    g = new_Integrator(dom)
+    try:
+        specifyParameters(g, intensityMus=case["intensityMus"], intensityPhis=case["intensityPhis"], computeIntensity=True,
+                          useHybridPhaseFunsForIntenCalcs=True, hybridPhaseFunWidth=7.0, numOrdersOrigPhaseFunIntenCalcs=1,
+                          limitIntensityContributions=True, maxIntensityContribution=0.5,
+                          minInverseTableSize=10001, minForwardTableSize=10001)
+        rs = new_RandomNumberSequence([10, 1, 0])
+        bs = BatchStatistics()
+        for _ in range(nb):
+            ps = new_PhotonStream(case["solarMu"], case["solarAzimuth"], n, rs)
+            done = computeRadiativeTransfer(g, dom, rs, ps, n)
+            bs.accumulate(reportResults(g, meanIntensity=True), done)
+        gm, ge = bs.finalise(1.0)
+    finally:
+        finalize_Integrator(g)
+    assert_within("hybrid+limit meanIntensity", gm["meanIntensity"], ge["meanIntensity"], om, np.maximum(oe, ge["meanIntensity"]), 3.0)

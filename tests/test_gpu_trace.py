@@ -120,3 +120,34 @@ def test_philox_known_answer():
         assert list(out[4:]) != list(out[:4])
     finally:
         finalize_Integrator(g)
+
+
+@pytest.mark.parametrize("name,dom,case,source", [c for c in CASES if c[0] in ("C2", "T_irr")],
+                         ids=[c[0] for c in CASES if c[0] in ("C2", "T_irr")])
+def test_trace_parity_hybrid_tables_and_contribution_limit(orc, name, dom, case, source):
+    """Local estimation with the hybrid (Gaussian forward peak) tables for scattering orders above
+    numOrdersOrigPhaseFunIntenCalcs (INT:1715-1724, OPT:1936-2050) and with limited contributions
+    (INT:1815-1826): bit-exact events, and the raw tallies including intensityExcess."""
+    g = new_Integrator(dom)
+    try:
+        mus = case.get("intensityMus", [1.0, 0.5]); phis = case.get("intensityPhis", [0.0, 0.0])
+        specifyParameters(g, intensityMus=mus, intensityPhis=phis, computeIntensity=True,
+                          useHybridPhaseFunsForIntenCalcs=True, hybridPhaseFunWidth=7.0, numOrdersOrigPhaseFunIntenCalcs=2,
+                          limitIntensityContributions=True, maxIntensityContribution=0.05,
+                          minInverseTableSize=10001, minForwardTableSize=10001)
+        od = orc.OracleDomain(dom, tableSize=10001, forward=True, hybrid=True, hybridWidth=7.0)
+        og = orc.OracleIntegrator(od, useHybridPhaseFunsForIntenCalcs=1, numOrdersOrigPhaseFunIntenCalcs=2,
+                                  limitIntensityContributions=1, maxIntensityContribution=0.05)
+        og.set_view_cosines(g.intensityDirections)
+        n, stride = 1000, 400
+        rn = injected_randoms(n, stride, seed=11 + hash(name) % 1000)
+        rs = new_RandomNumberSequence([10, 1, 0])
+        ps = new_PhotonStream(case["solarMu"], case["solarAzimuth"], n, rs)
+        want = og.trace(rn, 0, case["solarMu"], case["solarAzimuth"], maxEvents=n * 1024)
+        got, raw = tracePhotons(g, dom, ps, rn, maxEventsPerPhoton=1024)
+        assert_events_equal(got, want, "%s hybrid+limit" % name)
+        ot = og.raw_tallies()
+        assert ot[-(len(mus) * (od.nc + 1)):].sum() > 0                      # some contribution was capped
+        np.testing.assert_allclose(raw[: ot.size], ot, rtol=2e-5, atol=2e-4)
+    finally:
+        finalize_Integrator(g)
