@@ -118,6 +118,11 @@ int mcb_set_inverse_table(mcb_handle *h, int comp, int nS, int nE, const float *
 int mcb_build_inverse_table(mcb_handle *h, int comp, int nS, int nE, const int32_t *nAngles,
                             const float *mus, const float *values);
 int mcb_get_inverse_table(mcb_handle *h, int comp, float *T, int64_t nFloats);
+/* tabulateForwardPhaseFunctions (OPT:1872-1934) on the device for tables stored as Legendre moments: entry e has
+ * nCoef[e] moments chi_1.. (concatenated in coefs; 0 moments = isotropic); fills tabPhase and tabOrigPhase alike
+ * (hybrid tables, OPT:1936-2050, and angle/value tables are staged with mcb_set_forward_table).                  */
+int mcb_build_forward_table(mcb_handle *h, int comp, int nS, int nE, const int32_t *nCoef, const float *coefs);
+int mcb_get_forward_table(mcb_handle *h, int comp, float *T, int64_t nFloats);
 /* getInfo_Domain(tabPhase, tabOrigPhase) INT:1672-1673 <- tabulateForwardPhaseFunctions INT:282 */
 int mcb_set_forward_table(mcb_handle *h, int comp, int nS, int nE, const float *P, const float *Porig);
 /* specifyParameters(intensityMus, intensityPhis): direction cosines as INT:1267-1269 builds them;

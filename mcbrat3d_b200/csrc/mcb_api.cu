@@ -33,6 +33,8 @@ void mcb_launch_assemble_optics(int nx, int ny, int nz, int nc, const int *kind,
                                 int numSMs, cudaStream_t stream);
 void mcb_launch_inverse_table(const int *offsets, const float *mus, const float *values, int nEntries, int nSteps, float *out,
                               float *cdfScratch, cudaStream_t stream);
+void mcb_launch_forward_table(const int *offsets, const float *coefs, int nEntries, int nSteps, float *out, int numSMs,
+                              cudaStream_t stream);
 void mcb_launch_frequency_distribution(const double *cdf, int nLambda, long long totalPhotons, uint64_t seed,
                                        unsigned long long *counts, int numSMs, cudaStream_t stream);
 long long mcb_stats_elements(const DevDomain &P);
@@ -439,6 +441,44 @@ int mcb_build_inverse_table(mcb_handle *h, int comp, int nS, int nE, const int32
   if (settle(h)) return 1;
   h->P.inv[c] = (const float *)h->dInv[c]; h->P.invS[c] = nS; h->invE[c] = nE; h->P.invE[c] = nE; h->haveInv[c] = true;
   return 0;
+}
+
+// tabulateForwardPhaseFunctions OPT:1872-1934 on the device for a table whose entries are stored as Legendre moments
+// (chi_1.. of entry e: nCoef[e] values, concatenated).  Fills both the table and the "original" table (no hybrid peak).
+int mcb_build_forward_table(mcb_handle *h, int comp, int nS, int nE, const int32_t *nCoef, const float *coefs) {
+  if (!h) return 1;
+  if (!h->haveOptics) FAIL(h, "mcb_build_forward_table: call mcb_set_optics first");
+  if (comp < 1 || comp > h->P.nc || nS < 2 || nE < 1 || !nCoef) FAIL(h, "mcb_build_forward_table: bad arguments");
+  std::vector<int> off(nE + 1, 0);
+  for (int e = 0; e < nE; ++e) { if (nCoef[e] < 0) FAIL(h, "mcb_build_forward_table: bad arguments"); off[e + 1] = off[e] + nCoef[e]; }
+  const size_t total = (size_t)off[nE];
+  if (total > 0 && !coefs) FAIL(h, "mcb_build_forward_table: bad arguments");
+  const int c = comp - 1;
+  const size_t bOff = (sizeof(int) * (nE + 1) + 15) & ~(size_t)15;
+  if (reserve(h, &h->dScratch, bOff + sizeof(float) * (total ? total : 1))) return 1;
+  char *base = (char *)h->dScratch;
+  CK(h, cudaMemcpyAsync(base, off.data(), sizeof(int) * (nE + 1), cudaMemcpyHostToDevice, h->stream));
+  if (total) CK(h, cudaMemcpyAsync(base + bOff, coefs, sizeof(float) * total, cudaMemcpyHostToDevice, h->stream));
+  if (reserve(h, &h->dFwd[c], sizeof(float) * (size_t)nS * nE)) return 1;
+  if (reserve(h, &h->dFwdOrig[c], sizeof(float) * (size_t)nS * nE)) return 1;
+  mcb_launch_forward_table((const int *)base, (const float *)(base + bOff), nE, nS, (float *)h->dFwd[c], h->numSMs, h->stream);
+  CK(h, cudaGetLastError());
+  CK(h, cudaMemcpyAsync(h->dFwdOrig[c], h->dFwd[c], sizeof(float) * (size_t)nS * nE, cudaMemcpyDeviceToDevice, h->stream));
+  if (settle(h)) return 1;
+  h->P.fwd[c] = (const float *)h->dFwd[c]; h->P.fwdOrig[c] = (const float *)h->dFwdOrig[c];
+  h->P.fwdS[c] = nS; h->fwdE[c] = nE; h->P.fwdE[c] = nE; h->haveFwd[c] = true;
+  return 0;
+}
+
+int mcb_get_forward_table(mcb_handle *h, int comp, float *T, int64_t nFloats) {
+  if (!h || !T) return 1;
+  if (comp < 1 || comp > h->P.nc || !h->haveFwd[comp - 1]) FAIL(h, "mcb_get_forward_table: no table for this component");
+  const int c = comp - 1;
+  const int64_t n = (int64_t)h->P.fwdS[c] * h->fwdE[c];
+  if (nFloats < n) FAIL(h, "mcb_get_forward_table: buffer too small (%lld needed)", (long long)n);
+  CK(h, cudaSetDevice(h->device));
+  CK(h, cudaMemcpyAsync(T, h->dFwd[c], sizeof(float) * n, cudaMemcpyDeviceToHost, h->stream));
+  return settle(h);
 }
 
 int mcb_get_inverse_table(mcb_handle *h, int comp, float *T, int64_t nFloats) {

@@ -342,6 +342,35 @@ __global__ void inverse_table_kernel(const int *__restrict__ offsets, const floa
 }
 
 // ---------------------------------------------------------------------------------------------
+// forward (local-estimate) tables: tabulateForwardPhaseFunctions OPT:1872-1934 for Legendre-stored entries -- the
+// phase function at nS equally spaced angles 0..pi, one thread per (entry, angle): upward Legendre recursion
+// (NUM:187-205) and the series sum (SPF:480-498) in the reference's single-precision order.
+// ---------------------------------------------------------------------------------------------
+__global__ void forward_table_kernel(const int *__restrict__ offsets, const float *__restrict__ coefAll, int nE, int nS,
+                                     float *__restrict__ out) {
+  const long long total = (long long)nE * nS;
+  for (long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x; p < total; p += (long long)gridDim.x * blockDim.x) {
+    const int e = (int)(p / nS), i = (int)(p - (long long)e * nS);
+    const int nCoef = offsets[e + 1] - offsets[e];
+    const float *chi = coefAll + offsets[e];
+    float value = 0.5f;                                                             // SPF:486-491 (quirk q14)
+    if (nCoef > 0) {
+      const float angle = (float)i / (float)(nS - 1) * 3.14159265358979312f;        // OPT:1912-1913
+      const float mu = (float)cos((double)angle);
+      float pm1 = 1.0f, pl = mu;
+      value = 1.0f * pm1;
+      value = value + (chi[0] * 3.0f) * pl;
+      for (int l = 1; l < nCoef; ++l) {
+        const float pn = (((float)(2 * l + 1) * mu) * pl - (float)l * pm1) / (float)(l + 1);
+        pm1 = pl; pl = pn;
+        value = value + (chi[l] * (float)(2 * (l + 1) + 1)) * pl;
+      }
+    }
+    out[p] = value;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // spectral photon allocation: getFrequencyDistr (EMI:552-573) -- totalPhotons draws, each binned by
 // findCDFIndex (NUM:317-348).  The reference draws them one after the other from its sequential generator
 // (1e10 draws for the bench decks); here draw n is word (n mod 4) of the Philox block with counter
@@ -562,6 +591,12 @@ void mcb_launch_stats_finalise(const double *stats, long long n, double solarFlu
 void mcb_launch_inverse_table(const int *offsets, const float *mus, const float *values, int nEntries, int nSteps, float *out,
                               float *cdfScratch, cudaStream_t stream) {
   mcbstage::inverse_table_kernel<<<nEntries, 256, 0, stream>>>(offsets, mus, values, nSteps, out, cdfScratch);
+}
+
+void mcb_launch_forward_table(const int *offsets, const float *coefs, int nEntries, int nSteps, float *out, int numSMs,
+                              cudaStream_t stream) {
+  mcbstage::forward_table_kernel<<<stream_grid((long long)nEntries * nSteps, 256, numSMs), 256, 0, stream>>>(offsets, coefs,
+                                                                                                            nEntries, nSteps, out);
 }
 
 void mcb_launch_frequency_distribution(const double *cdf, int nLambda, long long totalPhotons, uint64_t seed,

@@ -198,11 +198,15 @@ def _stage_domain(g: integrator, d: Domain) -> None:
     onDevice = g.buildTablesOnDevice
     if not onDevice:
         d.tabulateInversePhaseFunctions(g.minInverseTableSize)
-    if g.computeIntensity:
-        d.tabulateForwardPhaseFunctions(g.minForwardTableSize, bool(g.options.useHybridPhaseFunsForIntenCalcs),
-                                        g.hybridPhaseFunWidth)
+    # forward tables: Legendre-stored components without the hybrid peak can be tabulated in HBM as well
+    hybrid = bool(g.options.useHybridPhaseFunsForIntenCalcs)
+    fwdOnDevice = [onDevice and not hybrid and all(pf.storedAsLegendre() for pf in tab.phaseFunctions)
+                   for tab in d.forwardTables] if g.computeIntensity else []
+    if g.computeIntensity and not all(fwdOnDevice):
+        d.tabulateForwardPhaseFunctions(g.minForwardTableSize, hybrid, g.hybridPhaseFunWidth)
     tkey = (key, onDevice, g.minInverseTableSize if onDevice else tuple(id(t) for t in d.inversePhaseFunctions),
-            tuple(id(t) for t in d.tabulatedPhaseFunctions) if g.computeIntensity else None)
+            (tuple(fwdOnDevice), g.minForwardTableSize, hybrid, g.hybridPhaseFunWidth,
+             tuple(id(t) for t in d.tabulatedPhaseFunctions)) if g.computeIntensity else None)
     if g._stagedTables != tkey:
         if onDevice:
             from .inversePhaseFunctions import inversion_inputs
@@ -219,9 +223,18 @@ def _stage_domain(g: integrator, d: Domain) -> None:
                 g._check(g._lib.mcb_set_inverse_table(g._h, c + 1, T.shape[1], T.shape[0], _lib.ptr(T, C.c_float)),
                          "tabulateInversePhaseFunctions")
         if g.computeIntensity:
-            for c, (Pf, Po) in enumerate(zip(d.tabulatedPhaseFunctions, d.tabulatedOrigPhaseFunctions)):
-                g._check(g._lib.mcb_set_forward_table(g._h, c + 1, Pf.shape[1], Pf.shape[0], _lib.ptr(Pf, C.c_float),
-                                                      _lib.ptr(Po, C.c_float)), "tabulateForwardPhaseFunctions")
+            for c, tab in enumerate(d.forwardTables):
+                if fwdOnDevice[c]:
+                    nCoef = np.array([pf.legendreCoefficients.size for pf in tab.phaseFunctions], dtype=np.int32)
+                    coefs = np.ascontiguousarray(np.concatenate([pf.legendreCoefficients for pf in tab.phaseFunctions]
+                                                                + [np.zeros(0, f32)]), dtype=f32)
+                    g._check(g._lib.mcb_build_forward_table(g._h, c + 1, int(g.minForwardTableSize), len(tab.phaseFunctions),
+                                                            _lib.ptr(nCoef, C.c_int32), _lib.ptr(coefs, C.c_float)),
+                             "tabulateForwardPhaseFunctions")
+                else:
+                    Pf, Po = d.tabulatedPhaseFunctions[c], d.tabulatedOrigPhaseFunctions[c]
+                    g._check(g._lib.mcb_set_forward_table(g._h, c + 1, Pf.shape[1], Pf.shape[0], _lib.ptr(Pf, C.c_float),
+                                                          _lib.ptr(Po, C.c_float)), "tabulateForwardPhaseFunctions")
         g._stagedTables = tkey
 
 

@@ -1275,3 +1275,21 @@ void orc_inverse_phase_function(int nAngles, const float *mus, const float *valu
   inverseTable[nSteps - 1] = 0.0f;                                             /* INV:168 */
   free(cdf); free(indicies);
 }
+
+/* tabulateForwardPhaseFunctions OPT:1912-1913 + getPhaseFunctionValues SPF:480-498 + computeLegendrePolynomials NUM:187-205 */
+void orc_forward_phase_function(int nCoef, const float *legendreCoefficients, int nS, float *values) {
+  for (int i = 0; i < nS; ++i) {
+    if (nCoef == 0) { values[i] = 0.5f; continue; }                               /* SPF:486-491 */
+    const float angle = (float)i / (float)(nS - 1) * PI32;
+    const float mu = f_cos(angle);
+    float pm1 = 1.0f, p = mu;                                                      /* P_0, P_1 */
+    float value = 1.0f * pm1;                                                      /* (2*0+1) * 1 * P_0 */
+    value = value + (legendreCoefficients[0] * 3.0f) * p;
+    for (int l = 1; l < nCoef; ++l) {
+      const float pn = (((float)(2 * l + 1) * mu) * p - (float)l * pm1) / (float)(l + 1);
+      pm1 = p; p = pn;
+      value = value + (legendreCoefficients[l] * (float)(2 * (l + 1) + 1)) * p;
+    }
+    values[i] = value;
+  }
+}

@@ -236,6 +236,11 @@ void orc_frequency_distribution(int numLambda, const double *CDF, int64_t totalP
  * probability (i-1)/(nSteps-1) by findIndex with the previous bracket as first guess, analytic inversion.         */
 void orc_inverse_phase_function(int nAngles, const float *mus, const float *values, int nSteps, float *inverseTable);
 
+/* tabulateForwardPhaseFunctions OPT:1872-1934 for one Legendre-stored entry: the phase function at nS equally spaced
+ * angles 0..pi (OPT:1912-1913), value = sum (2l+1) chi_l P_l(cos angle) in single precision (SPF:480-498, NUM:187-205);
+ * nCoef = 0 is the isotropic special case with value 1/2 (quirk q14).                                              */
+void orc_forward_phase_function(int nCoef, const float *legendreCoefficients, int nS, float *values);
+
 #ifdef __cplusplus
 }
 #endif

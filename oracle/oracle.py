@@ -127,6 +127,8 @@ def load():
     lib.orc_frequency_distribution.restype = None
     lib.orc_inverse_phase_function.argtypes = [C.c_int, _fp, _fp, C.c_int, _fp]
     lib.orc_inverse_phase_function.restype = None
+    lib.orc_forward_phase_function.argtypes = [C.c_int, _fp, C.c_int, _fp]
+    lib.orc_forward_phase_function.restype = None
     lib.orc_finalise_stats.argtypes = [_dp, C.c_int64, C.c_double, C.c_int64, C.c_int64]
     lib.orc_finalise_stats.restype = None
     lib.orc_march.restype = C.c_float
@@ -313,6 +315,15 @@ def inverse_phase_function(mus, values, nSteps):
     m = np.ascontiguousarray(mus, dtype=np.float32); v = np.ascontiguousarray(values, dtype=np.float32)
     out = np.empty(int(nSteps), dtype=np.float32)
     lib.orc_inverse_phase_function(m.size, _p(m, C.c_float), _p(v, C.c_float), int(nSteps), _p(out, C.c_float))
+    return out
+
+
+def forward_phase_function(legendreCoefficients, nSteps):
+    """tabulateForwardPhaseFunctions OPT:1912-1913 for one Legendre-stored phase function."""
+    lib = load()
+    c = np.ascontiguousarray(legendreCoefficients, dtype=np.float32)
+    out = np.empty(int(nSteps), dtype=np.float32)
+    lib.orc_forward_phase_function(c.size, _p(c, C.c_float), int(nSteps), _p(out, C.c_float))
     return out
 
 

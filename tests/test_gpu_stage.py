@@ -239,3 +239,36 @@ def test_inverse_tables_built_on_device_match_oracle(orc):
             assert abs(float(r_dev[k]) - float(r_host[k])) < 2e-4
     finally:
         finalize_Integrator(g)
+
+
+def test_forward_tables_built_on_device_match_oracle(orc):
+    """tabulateForwardPhaseFunctions (OPT:1872-1934) as a kernel for Legendre-stored tables (HG with 64 moments,
+    the 2-moment Rayleigh function, a mixed two-component domain) against the oracle's C restatement."""
+    for make in (lambda: domains.step_cloud(ssa=0.99, solarMu=0.5), lambda: domains.irregular_test_domain()):
+        d, case = make()
+        g = new_Integrator(d)
+        try:
+            specifyParameters(g, intensityMus=[1.0, 0.5], intensityPhis=[0.0, 90.0], computeIntensity=True,
+                              minInverseTableSize=9001, minForwardTableSize=9001, buildTablesOnDevice=True)
+            rs = new_RandomNumberSequence(4)
+            ps = new_PhotonStream(case["solarMu"], case["solarAzimuth"], 20000, rs)
+            assert computeRadiativeTransfer(g, d, rs, ps, 20000) == 20000
+            r_dev = reportResults(g, meanIntensity=True)
+            total = mismatch = 0
+            for c, tab in enumerate(d.forwardTables):
+                got = np.empty((len(tab.phaseFunctions), 9001), dtype=f32)
+                g._check(g._lib.mcb_get_forward_table(g.handle, c + 1, _lib.ptr(got, C.c_float), got.size), "get")
+                for e, pf in enumerate(tab.phaseFunctions):
+                    want = orc.forward_phase_function(pf.legendreCoefficients, 9001)
+                    bad = got[e] != want
+                    mismatch += int(bad.sum()); total += want.size
+                    np.testing.assert_allclose(got[e], want, rtol=2e-5, atol=1e-6)     # cos() of the device is 1 ulp, not exact
+            assert mismatch <= 2e-3 * total, (mismatch, total)
+            specifyParameters(g, buildTablesOnDevice=False)
+            rs = new_RandomNumberSequence(4)
+            ps = new_PhotonStream(case["solarMu"], case["solarAzimuth"], 20000, rs)
+            computeRadiativeTransfer(g, d, rs, ps, 20000)
+            r_host = reportResults(g, meanIntensity=True)
+            np.testing.assert_allclose(r_dev["meanIntensity"], r_host["meanIntensity"], rtol=2e-3)
+        finally:
+            finalize_Integrator(g)

@@ -114,3 +114,15 @@ def test_oracle_inverse_builder_matches_numpy_mirror(orc):
     cdf = (cdf / cdf[-1]).astype(np.float32)
     assert np.any(np.diff(cdf) < 0)
     assert find_cdf_brackets(cdf, 101).min() >= 1
+
+
+def test_oracle_forward_builder_matches_numpy_mirror(orc):
+    """OPT:1912-1913 + SPF:480-498 + NUM:187-205 restated in C (oracle) and in NumPy (host mirror): identical tables."""
+    from mcbrat3d_b200 import domains
+    for make in (lambda: domains.step_cloud(), lambda: domains.irregular_test_domain()):
+        d, _ = make()
+        d.tabulateForwardPhaseFunctions(9001)
+        for c, tab in enumerate(d.forwardTables):
+            for e, pf in enumerate(tab.phaseFunctions):
+                assert np.array_equal(orc.forward_phase_function(pf.legendreCoefficients, 9001), d.tabulatedOrigPhaseFunctions[c][e])
+    assert np.all(orc.forward_phase_function(np.zeros(0, np.float32), 11) == 0.5)          # quirk q14
