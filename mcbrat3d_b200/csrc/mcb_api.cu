@@ -2,6 +2,7 @@
 // normalisation and read-back.  No photon arithmetic happens on the host.
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <string>
@@ -18,7 +19,7 @@ void mcb_launch_fast_batch(const DevDomain &P, long long nPhotons, uint64_t seed
                            int numSMs, unsigned long long *workCounter, cudaStream_t stream);
 void mcb_launch_philox_kat(uint64_t seed, uint64_t photon, int n, uint32_t *out, cudaStream_t stream);
 // mcb_stage.cu: device-side packing / validation, normalisation, emission CDF
-void mcb_launch_pack_optics(const DevDomain &P, float *e32, float *c32, float *s32, uint16_t *i16, int *flags,
+void mcb_launch_pack_optics(const DevDomain &P, float *e32, uint32_t *rec, int *flags, uint32_t *mask, float *layerExt,
                             int numSMs, cudaStream_t stream);
 void mcb_launch_normalise(const DevDomain &P, float numPhotons, float *out, int numSMs, cudaStream_t stream);
 long long mcb_emission_tiles(long long cells);
@@ -58,7 +59,8 @@ struct mcb_handle {
   // re-stageable slots (freed on re-set)
   void *dXE = nullptr, *dYE = nullptr, *dZE = nullptr;
   void *dTotalExt = nullptr, *dCumExt = nullptr, *dSsa = nullptr, *dPhaseIdx = nullptr;
-  void *dExt32 = nullptr, *dCum32 = nullptr, *dSsa32 = nullptr, *dIdx16 = nullptr;
+  void *dExt32 = nullptr, *dRec = nullptr;
+  void *dExtMask = nullptr, *dLayerExt = nullptr;     // occupancy bitmap of fields too large for L2
   void *dInv[MCB_MAX_COMP] = {nullptr}, *dFwd[MCB_MAX_COMP] = {nullptr}, *dFwdOrig[MCB_MAX_COMP] = {nullptr};
   int invE[MCB_MAX_COMP] = {0}, fwdE[MCB_MAX_COMP] = {0};
   void *dVoxelCDF = nullptr, *dTemps = nullptr, *dScratch = nullptr, *dResults = nullptr;
@@ -160,9 +162,9 @@ int mcb_destroy(mcb_handle *h) {
   cudaSetDevice(h->device);
   cudaStreamSynchronize(h->stream);
   void *slots[] = {h->dXE, h->dYE, h->dZE, h->dTotalExt, h->dCumExt, h->dSsa, h->dPhaseIdx,
-                   h->dExt32, h->dCum32, h->dSsa32, h->dIdx16, h->dVoxelCDF, h->dTally, h->dCounters,
+                   h->dExt32, h->dRec, h->dVoxelCDF, h->dTally, h->dCounters,
                    h->dTemps, h->dScratch, h->dResults, (void *)h->dFlags, h->dStats, h->dStatsOut,
-                   h->dMassConc, h->dReff, h->dNumConc, h->dAsmTables};
+                   h->dMassConc, h->dReff, h->dNumConc, h->dAsmTables, h->dExtMask, h->dLayerExt};
   for (void *p : slots) if (p) cudaFree(p);
   for (int c = 0; c < MCB_MAX_COMP; ++c) {
     if (h->dInv[c]) cudaFree(h->dInv[c]);
@@ -280,16 +282,30 @@ static int finish_optics(mcb_handle *h, int nc, double albedo, bool zeroFlags) {
   const size_t cells = (size_t)P.nx * P.ny * P.nz;
   const size_t padded = (size_t)P.nxp * P.nyp * (P.nz + 2 * MCB_GHOST);
   if (reserve(h, &h->dExt32, sizeof(float) * padded)) return 1;
-  if (reserve(h, &h->dCum32, sizeof(float) * cells * nc)) return 1;
-  if (reserve(h, &h->dSsa32, sizeof(float) * cells * nc)) return 1;
-  if (reserve(h, &h->dIdx16, sizeof(uint16_t) * cells * nc)) return 1;
+  int recShift = 0;                                   // event record: (nc-1) + nc + ceil(nc/2) words, padded to 2^recShift
+  while ((1 << recShift) < 2 * nc - 1 + (nc + 1) / 2) ++recShift;
+  if (reserve(h, &h->dRec, sizeof(uint32_t) * (cells << recShift))) return 1;
   P.nc = nc; P.albedo = albedo;
   P.totalExt = (const double *)h->dTotalExt; P.cumExt = (const double *)h->dCumExt;
   P.ssa = (const double *)h->dSsa; P.phaseIdx = (const int32_t *)h->dPhaseIdx;
-  P.extp = (const float *)h->dExt32 + P.ghostOrigin; P.cum32 = (const float *)h->dCum32;
-  P.ssa32 = (const float *)h->dSsa32; P.idx16 = (const uint16_t *)h->dIdx16;
+  P.extp = (const float *)h->dExt32 + P.ghostOrigin;
+  P.rec = (const uint32_t *)h->dRec; P.recShift = recShift;
+  // Occupancy bitmap: only for fields that do not stay L2-resident (default: padded field > 48 MB; the C3 field,
+  // 15.5 MB, is served by L2 and gains nothing).  MCB_EXT_MASK=0/1 forces it off/on (measurements, tests).
+  {
+    const char *e = getenv("MCB_EXT_MASK");              // read at every staging, so one process can compare both
+    const int maskEnv = e ? atoi(e) : -1;
+    const bool useMask = maskEnv >= 0 ? maskEnv > 0 : sizeof(float) * padded > ((size_t)48 << 20);
+    P.extMask = nullptr; P.layerExt = nullptr;
+    if (useMask) {
+      if (reserve(h, &h->dExtMask, sizeof(uint32_t) * ((padded + 31) / 32))) return 1;
+      if (reserve(h, &h->dLayerExt, sizeof(float) * (size_t)(P.nz + 2 * MCB_GHOST))) return 1;
+      P.extMask = (const uint32_t *)h->dExtMask; P.layerExt = (const float *)h->dLayerExt;
+    }
+  }
   if (zeroFlags) CK(h, cudaMemsetAsync(h->dFlags, 0, sizeof(int) * 4, h->stream));
-  mcb_launch_pack_optics(P, (float *)h->dExt32, (float *)h->dCum32, (float *)h->dSsa32, (uint16_t *)h->dIdx16, h->dFlags,
+  mcb_launch_pack_optics(P, (float *)h->dExt32, (uint32_t *)h->dRec, h->dFlags,
+                         (uint32_t *)P.extMask, (float *)P.layerExt,
                          h->numSMs, h->stream);
   CK(h, cudaGetLastError());
   int flags4[4] = {0, 0, 0, 0};

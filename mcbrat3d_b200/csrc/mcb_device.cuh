@@ -33,8 +33,17 @@ struct DevDomain {
                                               // first real cell: cell (ix,iy,iz) is extp[ix + nxp*(iy + nyp*iz)]
   int nxp, nyp, ghostOrigin;                  // padded row / slice lengths; linear offset of the first real cell
   long long paddedCells;                      // (nx+2G)(ny+2G)(nz+2G)
-  const float *cum32, *ssa32;                 // (nx,ny,nz,nc)
-  const uint16_t *idx16;                      // (nx,ny,nz,nc)
+  // Fields too large for L2 (C5: 93 MB) carry an occupancy bitmap: bit p of extMask (p = absolute padded cell) is set
+  // where the cell's extinction differs from its layer's clear-sky value layerExt[iz + G] (the layer minimum; 0 in the
+  // ghost layers).  The marcher reads the bitmap (1 bit per cell, L1/L2-resident) and gathers extp only where the bit
+  // is set, so clear-sky cells -- most of a cloud scene -- never go to HBM.  Exact: both branches give (float)totalExt.
+  const uint32_t *extMask;                    // ceil(paddedCells / 32) words, or nullptr
+  const float *layerExt;                      // nz + 2G values
+  // one record per cell with everything a scattering event reads, so an event costs ONE gather (a 32 B sector for
+  // nc <= 3) instead of a dependent chain through three arrays: 2^recShift u32 words =
+  // [f32 cumExt(c), c = 1..nc-1][f32 ssa(c), c = 1..nc][u16 phase index pairs], zero-padded
+  const uint32_t *rec;
+  int recShift;
   float fx0, fy0, fz0, fLx, fLy, fLz;         // single-precision grid scalars (fast kernel, constant bank)
   float fhx, fhy, fhz, finvLx, finvLy, finvhx, finvhy, fzMax;
   uint32_t divSliceM, divRowM;                // padded cell -> (ix,iy,iz): q = (M * n) >> S, exact for n < 2^31

@@ -169,11 +169,15 @@ enum { MARCH_ON = ST_MARCH, MARCH_HIT = ST_SCATTER, MARCH_BOTTOM = ST_SURFACE, M
 //   * the ray left through the top / the surface: r.t = distance to that boundary, (ix,iy) = column of
 //     the exit point -> MARCH_TOP / MARCH_BOTTOM;
 //   * otherwise x, y are folded back into the domain -> MARCH_ON.
-template <bool REG, bool WIDE, int B>
+//
+// MASK (fields too large for L2): the geometry loop also fetches, per cell, the occupancy-bitmap word and the layer's
+// clear-sky extinction (both L1/L2-resident); the gather of the big field is then issued only where the bit is set.
+template <bool REG, bool WIDE, int B, bool MASK>
 __device__ __forceinline__ int march_burst(Ray &r, const DevDomain &P, const Grid &G, const float *__restrict__ extp,
                                            float &ext, float target, unsigned &crossings) {
   float tE[B], sg[B];
   int ck[B];
+  uint32_t mw[MASK ? B : 1];
   const float t0 = r.t;
   const int sx = r.dx >= 0.0f ? 1 : -1, sy = r.dy >= 0.0f ? 1 : -1, sz = r.dz >= 0.0f ? 1 : -1;
 #pragma unroll
@@ -181,6 +185,10 @@ __device__ __forceinline__ int march_burst(Ray &r, const DevDomain &P, const Gri
     const float tmin = fminf(fminf(r.tx, r.ty), r.tz);
     ck[k] = r.ix + P.nxp * (r.iy + P.nyp * r.iz);
     tE[k] = tmin;
+    if (MASK) {
+      mw[k] = __ldg(P.extMask + MCB_CHECK_INDEX(P, (uint32_t)(ck[k] + P.ghostOrigin) >> 5, (P.paddedCells + 31) >> 5));
+      sg[k] = __ldg(P.layerExt + MCB_CHECK_INDEX(P, r.iz + GH, P.nz + 2 * GH));
+    }
     if (REG) {
       { const bool c = r.tx <= tmin; r.ix += c ? sx : 0; r.tx = c ? fmaf(P.fhx, fabsf(r.rx), r.tx) : r.tx; }
       { const bool c = r.ty <= tmin; r.iy += c ? sy : 0; r.ty = c ? fmaf(P.fhy, fabsf(r.ry), r.ty) : r.ty; }
@@ -192,7 +200,13 @@ __device__ __forceinline__ int march_burst(Ray &r, const DevDomain &P, const Gri
     }
   }
 #pragma unroll
-  for (int k = 0; k < B; ++k) sg[k] = EXT_AT(P, extp, ck[k]);
+  for (int k = 0; k < B; ++k) {
+    if (MASK) {                                        // bit p of the bitmap: the shift count wraps modulo 32
+      if (__funnelshift_r(mw[k], 0u, (uint32_t)(ck[k] + P.ghostOrigin)) & 1u) sg[k] = EXT_AT(P, extp, ck[k]);
+    } else {
+      sg[k] = EXT_AT(P, extp, ck[k]);
+    }
+  }
   // accumulate until the target is passed (OPT:1729-1738); from there on acc / tS stay frozen at the
   // ENTRY of the hit cell, so only its extinction and index have to be carried along
   float acc = ext, tS = t0, hS = 1.0f;
@@ -301,25 +315,25 @@ enum { LE_PX = 0, LE_PY, LE_PZ, LE_DX, LE_DY, LE_DZ, LE_W, LE_IXY, LE_IZO, LE_CO
 enum { PH_IDLE = 0, PH_PLAIN, PH_E13, PH_E14A, PH_E14B };
 
 __device__ __forceinline__ void le_post(float *sle, int lane, const DevDomain &P, Rng &rng, const Ray &r0,
-                                        float px, float py, float pz, float w, int component, int tallyComponent, int order) {
+                                        float px, float py, float pz, float w, int component, int tallyComponent, int order,
+                                        int pidx) {
   sle[LE_PX * 32 + lane] = px; sle[LE_PY * 32 + lane] = py; sle[LE_PZ * 32 + lane] = pz;
   sle[LE_DX * 32 + lane] = r0.dx; sle[LE_DY * 32 + lane] = r0.dy; sle[LE_DZ * 32 + lane] = r0.dz;
   sle[LE_W * 32 + lane] = w;
   sle[LE_IXY * 32 + lane] = __int_as_float(r0.ix | (r0.iy << 16));
   sle[LE_IZO * 32 + lane] = __int_as_float(r0.iz | (min(order, 65535) << 16));
-  sle[LE_COMP * 32 + lane] = __int_as_float(((component + 1) & 0xff) | (tallyComponent << 8));
+  sle[LE_COMP * 32 + lane] = __int_as_float(((component + 1) & 0xff) | ((tallyComponent & 0xff) << 8) | (pidx << 16));
   sle[LE_C0 * 32 + lane] = __uint_as_float(rng.c0); sle[LE_C1 * 32 + lane] = __uint_as_float(rng.c1);
   sle[LE_BLK * 32 + lane] = __uint_as_float(rng.blk);
   // the request owns the next ceil(nDir/2) Philox blocks of this photon (one block serves two directions)
   if (P.opt.useRussianRouletteForIntensity) rng.blk += (uint32_t)((P.nDir + 1) >> 1);
 }
 
-template <bool REG, bool WIDE>
+template <bool REG, bool WIDE, bool MASK>
 __device__ void le_run(const DevDomain &P, const Grid &G, const Tally &T, uint32_t k0, uint32_t k1, unsigned posted,
                        float *sle, unsigned *queue, int lane, Counts &cnt) {
   const int nDir = P.nDir;
   const int nTasks = __popc(posted) * nDir;
-  const size_t cells = (size_t)P.nx * P.ny * P.nz;
   if (lane == 0) *queue = 0u;
   __syncwarp();
   Ray r;
@@ -352,8 +366,7 @@ __device__ void le_run(const DevDomain &P, const Grid &G, const Tally &T, uint32
           proj = fminf(fmaxf(proj, -1.0f), 1.0f);
           const float ang = acosf(proj);
           const int c = component - 1;
-          const int cell = r.ix + P.nx * (r.iy + P.ny * r.iz);
-          const int pidx = (int)__ldg(&P.idx16[MCB_CHECK_INDEX(P, cell, cells) + cells * c]);
+          const int pidx = (int)((uint32_t)comps >> 16);                           // phase-function entry of the event's cell
           const float *tab = ((P.opt.useHybridPhaseFunsForIntenCalcs && order <= P.opt.numOrdersOrigPhaseFunIntenCalcs)
                                   ? P.fwdOrig[c] : P.fwd[c]) + (size_t)MCB_CHECK_INDEX(P, pidx - 1, P.fwdE[c]) * P.fwdS[c];
           const int nS = P.fwdS[c];                                                // INT:1855-1870
@@ -390,7 +403,7 @@ __device__ void le_run(const DevDomain &P, const Grid &G, const Tally &T, uint32
     }
     if (__all_sync(FULL, done)) break;
     if (phase != PH_IDLE) {
-      const int ev = march_burst<REG, WIDE, 4>(r, P, G, P.extp, ext, tgt, cnt.leCrossings);
+      const int ev = march_burst<REG, WIDE, 4, MASK>(r, P, G, P.extp, ext, tgt, cnt.leCrossings);
       if (ev != MARCH_ON) {
         float contribution = 0.0f;
         bool finished = true;
@@ -413,7 +426,7 @@ __device__ void le_run(const DevDomain &P, const Grid &G, const Tally &T, uint32
           contribution = ev == MARCH_TOP ? w * P.opt.zetaMin / PI32 : 0.0f;
         }
         if (finished) {
-          const int component = (comps & 0xff) - 1, tallyComponent = comps >> 8;
+          const int component = (comps & 0xff) - 1, tallyComponent = (comps >> 8) & 0xff;
           if (P.opt.limitIntensityContributions && contribution > P.opt.maxIntensityContribution) {   // INT:1815-1826
             const int cslot = component < 0 ? 0 : component;
             atomicAdd(&P.tally[P.offExcess + dir + (long long)P.nDir * cslot],
@@ -429,7 +442,7 @@ __device__ void le_run(const DevDomain &P, const Grid &G, const Tally &T, uint32
   __syncwarp();
 }
 
-template <int THREADS, bool REG, bool WIDE, int MINBLOCKS, int BURST, bool LE>
+template <int THREADS, bool REG, bool WIDE, int MINBLOCKS, int BURST, bool LE, bool MASK>
 __global__ void __launch_bounds__(THREADS, MINBLOCKS)
 batch_kernel(const __grid_constant__ DevDomain P, long long nPhotons, uint64_t seed, uint64_t firstPhotonId,
              unsigned long long *workCounter, int parkThreshold, const SmemPlan plan) {
@@ -494,7 +507,7 @@ batch_kernel(const __grid_constant__ DevDomain P, long long nPhotons, uint64_t s
   for (;;) {
     // =========================== event phase: every lane that is not marching ===========================
     float px = 0.0f, py = 0.0f, pz = 0.0f;
-    int comp = 1, cell = 0;
+    int comp = 1, cell = 0, pidx = 0;
     bool posted = false;
     if (state == ST_TOP) {                                                     // INT:573-617
       add_flux(P, T, 0, r.ix + P.nx * r.iy, w);
@@ -510,7 +523,7 @@ batch_kernel(const __grid_constant__ DevDomain P, long long nPhotons, uint64_t s
       } else {
         ray_position(r, P, px, py, pz);
         pz = P.fz0;
-        if (LE && P.nDir > 0) { le_post(sle, lane, P, rng, r, px, py, pz, w, 0, 0, order); posted = true; }
+        if (LE && P.nDir > 0) { le_post(sle, lane, P, rng, r, px, py, pz, w, 0, 0, order, 0); posted = true; }
       }
     } else if (state == ST_SCATTER) {                                          // INT:703-811
       order++;
@@ -518,12 +531,28 @@ batch_kernel(const __grid_constant__ DevDomain P, long long nPhotons, uint64_t s
       cell = r.ix + P.nx * (r.iy + P.ny * r.iz);
       // uNext (drawn with the previous event's block) picks the component and, rescaled to the chosen
       // component's interval (uniform again, conditional on the pick), decides the roulette
-      float lo = 0.0f, hi = 1.0f;
-      for (int c = 1; c < P.nc; ++c) {                                         // findIndex on (0, cumExt(:)), NUM:262-315
-        const float cc = __ldg(&P.cum32[MCB_CHECK_INDEX(P, cell, cells) + (size_t)cells * (size_t)(c - 1)]);
-        if (uNext >= cc) { comp = c + 1; lo = cc; } else { hi = fminf(hi, cc); }
+      float lo = 0.0f, hi = 1.0f, ssa;
+      {                                                                        // the cell's event record: ONE gather
+        const uint32_t *R = P.rec + ((size_t)MCB_CHECK_INDEX(P, cell, cells) << P.recShift);
+        if (P.nc == 1) {
+          const uint2 v = __ldg(reinterpret_cast<const uint2 *>(R));
+          ssa = __uint_as_float(v.x); pidx = (int)(v.y & 0xffffu);
+        } else if (P.nc == 2) {
+          const uint4 v = __ldg(reinterpret_cast<const uint4 *>(R));
+          const float cc = __uint_as_float(v.x);                               // findIndex on (0, cumExt(:)), NUM:262-315
+          if (uNext >= cc) { comp = 2; lo = cc; } else { hi = cc; }
+          ssa = __uint_as_float(comp == 1 ? v.y : v.z);
+          pidx = (int)(comp == 1 ? (v.w & 0xffffu) : (v.w >> 16));
+        } else {
+          for (int c = 1; c < P.nc; ++c) {
+            const float cc = __uint_as_float(__ldg(R + (c - 1)));
+            if (uNext >= cc) { comp = c + 1; lo = cc; } else { hi = fminf(hi, cc); }
+          }
+          ssa = __uint_as_float(__ldg(R + (P.nc - 1) + (comp - 1)));
+          const uint32_t pw = __ldg(R + (2 * P.nc - 1) + ((comp - 1) >> 1));
+          pidx = (int)(((comp - 1) & 1) ? (pw >> 16) : (pw & 0xffffu));
+        }
       }
-      const float ssa = __ldg(&P.ssa32[MCB_CHECK_INDEX(P, cell, cells) + (size_t)cells * (size_t)(comp - 1)]);
       if (ssa < 1.0f) {                                                        // INT:765-771
         const float absorbed = w * (1.0f - ssa);
         add_flux(P, T, 2, r.ix + P.nx * r.iy, absorbed);
@@ -531,7 +560,7 @@ batch_kernel(const __grid_constant__ DevDomain P, long long nPhotons, uint64_t s
         w *= ssa;
       }
       ray_position(r, P, px, py, pz);
-      if (LE && P.nDir > 0) { le_post(sle, lane, P, rng, r, px, py, pz, w, comp, comp, order); posted = true; }   // INT:776-800
+      if (LE && P.nDir > 0) { le_post(sle, lane, P, rng, r, px, py, pz, w, comp, comp, order, pidx); posted = true; }   // INT:776-800
       if (P.opt.useRussianRoulette && w < P.opt.russianRouletteW * 0.5f) {     // INT:805-811
         const float uRR = P.nc > 1 ? __fdividef(uNext - lo, fmaxf(hi - lo, TINY32)) : uNext;
         if (uRR >= w / P.opt.russianRouletteW) w = 0.0f; else w = P.opt.russianRouletteW;
@@ -543,7 +572,7 @@ batch_kernel(const __grid_constant__ DevDomain P, long long nPhotons, uint64_t s
     }
     if (LE && P.nDir > 0) {                                                   // the whole warp serves the posted requests
       const unsigned pm = __ballot_sync(FULL, posted);
-      if (pm) le_run<REG, WIDE>(P, G, T, k0, k1, pm, sle, leQueue, lane, cnt);
+      if (pm) le_run<REG, WIDE, MASK>(P, G, T, k0, k1, pm, sle, leQueue, lane, cnt);
       posted = false;
     }
     // ---- finished lanes take the next photons: one atomic per warp (getNextPhoton, ILL:561-590) ----
@@ -627,7 +656,7 @@ batch_kernel(const __grid_constant__ DevDomain P, long long nPhotons, uint64_t s
             add_flux(P, T, 2, r.ix + P.nx * r.iy, -1.0f);
             add_vol(P, T, r.ix + P.nx * (r.iy + P.ny * r.iz), -1.0f);
           }
-          if (LE && P.nDir > 0) { le_post(sle, lane, P, rng, r, px, py, pz, w, pz == 0.0f ? 0 : -1, 0, order); posted = true; }
+          if (LE && P.nDir > 0) { le_post(sle, lane, P, rng, r, px, py, pz, w, pz == 0.0f ? 0 : -1, 0, order, 0); posted = true; }
         }
       } else if (state == ST_SURFACE) {                                        // INT:655-676
         const float mu = sqrtf(fmaxf(u.x, 1.0e-30f));                          // retries on mu ~ 0
@@ -635,7 +664,6 @@ batch_kernel(const __grid_constant__ DevDomain P, long long nPhotons, uint64_t s
         r.iz = 0;
       } else {                                                                 // ST_SCATTER, INT:813-819
         const int c = comp - 1;
-        const int pidx = (int)__ldg(&P.idx16[MCB_CHECK_INDEX(P, cell, cells) + (size_t)cells * (size_t)c]);
         const int nS = P.invS[c];
         const float *tab = P.inv[c] + (size_t)MCB_CHECK_INDEX(P, pidx - 1, P.invE[c]) * nS;
         const float rn = u.x;                                                  // computeScatteringAngle INT:1594-1621
@@ -670,7 +698,7 @@ batch_kernel(const __grid_constant__ DevDomain P, long long nPhotons, uint64_t s
     }
     if (LE && P.nDir > 0 && P.opt.LW_flag > 0.0f) {                            // emission at birth (INT:513-542)
       const unsigned pm = __ballot_sync(FULL, posted);
-      if (pm) le_run<REG, WIDE>(P, G, T, k0, k1, pm, sle, leQueue, lane, cnt);
+      if (pm) le_run<REG, WIDE, MASK>(P, G, T, k0, k1, pm, sle, leQueue, lane, cnt);
     }
 
     // =========================== march phase: bursts until enough lanes are parked ===========================
@@ -679,7 +707,7 @@ batch_kernel(const __grid_constant__ DevDomain P, long long nPhotons, uint64_t s
       const unsigned live = __ballot_sync(FULL, state != ST_DONE);
       if (mk == 0u || __popc(live & ~mk) >= parkThreshold) break;
       if (state == ST_MARCH) {
-        state = march_burst<REG, WIDE, BURST>(r, P, G, extp, ext, tau, cnt.crossings);
+        state = march_burst<REG, WIDE, BURST, MASK>(r, P, G, extp, ext, tau, cnt.crossings);
       }
     }
   }
@@ -732,11 +760,11 @@ __global__ void philox_kat_kernel(uint64_t seed, uint64_t photon, int n, uint32_
 
 #include <cstdlib>
 
-template <bool REG, bool WIDE, int MINBLOCKS, int BURST, bool LE>
+template <bool REG, bool WIDE, int MINBLOCKS, int BURST, bool LE, bool MASK = false>
 static void launch(const DevDomain &P, long long nPhotons, uint64_t seed, uint64_t firstPhotonId, int numSMs,
                    unsigned long long *workCounter, cudaStream_t stream) {
   constexpr int THREADS = 128;
-  auto kernel = mcbfast::batch_kernel<THREADS, REG, WIDE, MINBLOCKS, BURST, LE>;
+  auto kernel = mcbfast::batch_kernel<THREADS, REG, WIDE, MINBLOCKS, BURST, LE, MASK>;
   // shared-memory plan: privatise the tallies when the column / cell grid is small enough to be an
   // atomic hot spot (homogeneous slabs, the 32-column step cloud); large grids spread their
   // atomics over many L2 lines and go straight to the f64 buffer.
@@ -781,6 +809,11 @@ void mcb_launch_fast_batch(const DevDomain &P, long long nPhotons, uint64_t seed
     else launch<REG, WIDE, OCC, BURST, false>(P, nPhotons, seed, firstPhotonId, numSMs, workCounter, stream); } while (0)
   const bool wide = P.nx >= MCB_GHOST && P.ny >= MCB_GHOST;      // no grid period shorter than the ghost shell
   if (P.xyRegular && P.zRegular) {            // burst length <= MCB_GHOST (the ghost shell is that deep)
+    if (wide && P.extMask) {                  // field too large for L2: occupancy-bitmap variants (80 / 64 registers)
+      if (P.nDir > 0) launch<true, true, 6, 8, true, true>(P, nPhotons, seed, firstPhotonId, numSMs, workCounter, stream);
+      else if (occEnv >= 8) launch<true, true, 8, 8, false, true>(P, nPhotons, seed, firstPhotonId, numSMs, workCounter, stream);
+      else launch<true, true, 6, 8, false, true>(P, nPhotons, seed, firstPhotonId, numSMs, workCounter, stream);
+    } else
     if (!wide) { if (P.nDir > 0) MCB_GO(true, false, 6, 8); else MCB_GO(true, false, 8, 8); }
     else if (burst >= 8) { if (occ >= 8) MCB_GO(true, true, 8, 8); else if (occ >= 6) MCB_GO(true, true, 6, 8); else MCB_GO(true, true, 4, 8); }
     else { if (occ >= 8) MCB_GO(true, true, 8, 4); else if (occ >= 6) MCB_GO(true, true, 6, 4); else MCB_GO(true, true, 4, 4); }

@@ -47,16 +47,60 @@ __global__ void pack_extinction_kernel(const double *__restrict__ totalExt, floa
     atomicMax((unsigned long long *)(flags + 2), (unsigned long long)__double_as_longlong(emax));
 }
 
+// clear-sky value of every padded layer: the layer minimum of the packed field (ghost layers: 0).  One block per layer.
+__global__ void layer_min_kernel(const float *__restrict__ e32, int nxp, int nyp, float *__restrict__ layerExt) {
+  __shared__ float s[32];
+  const float *L = e32 + (long long)blockIdx.x * nxp * nyp;
+  float m = FLT_MAX;
+  for (int i = threadIdx.x; i < nxp * nyp; i += blockDim.x) m = fminf(m, L[i]);
+  for (int o = 16; o > 0; o >>= 1) m = fminf(m, __shfl_down_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    m = threadIdx.x < (blockDim.x >> 5) ? s[threadIdx.x] : FLT_MAX;
+    for (int o = 16; o > 0; o >>= 1) m = fminf(m, __shfl_down_sync(0xffffffffu, m, o));
+    if (threadIdx.x == 0) layerExt[blockIdx.x] = m;
+  }
+}
+
+// occupancy bitmap of the padded field: bit p set where e32[p] differs from its layer's clear-sky value.
+// One warp builds one 32-bit word per iteration with a ballot (coalesced read, one store per warp).
+__global__ void occupancy_mask_kernel(const float *__restrict__ e32, const float *__restrict__ layerExt, long long total,
+                                      int slice, uint32_t *__restrict__ mask) {
+  const long long words = (total + 31) >> 5;
+  const int lane = threadIdx.x & 31;
+  const long long warp = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (long long w = warp; w < words; w += nwarps) {
+    const long long p = (w << 5) + lane;
+    bool bit = false;
+    if (p < total) bit = e32[p] != layerExt[p / slice];
+    const unsigned m = __ballot_sync(0xffffffffu, bit);
+    if (lane == 0) mask[w] = m;
+  }
+}
+
 __global__ void pack_components_kernel(const double *__restrict__ cumExt, const double *__restrict__ ssa,
-                                       const int32_t *__restrict__ phaseIdx, float *__restrict__ c32,
-                                       float *__restrict__ s32, uint16_t *__restrict__ i16, long long n, int *flags) {
+                                       const int32_t *__restrict__ phaseIdx, uint32_t *__restrict__ rec, int recShift,
+                                       long long cells, int nc, int *flags) {
+  // per-cell event record (mcb_device.cuh): [cumExt(1..nc-1)][ssa(1..nc)][phase index pairs], zero-padded to 2^recShift
   int bad = 0;
-  for (long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x; p < n; p += (long long)gridDim.x * blockDim.x) {
-    const double s = ssa[p];
-    const int32_t ix = phaseIdx[p];
-    if (!(s >= 0.0 && s <= 1.0)) bad |= FLAG_SSA;
-    if (ix < 0 || ix > 65535) bad |= FLAG_IDX;
-    c32[p] = (float)cumExt[p]; s32[p] = (float)s; i16[p] = (uint16_t)ix;
+  const int words = 1 << recShift;
+  for (long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x; p < cells; p += (long long)gridDim.x * blockDim.x) {
+    uint32_t *R = rec + (p << recShift);
+    int w = 0;
+    for (int c = 0; c < nc - 1; ++c) R[w++] = __float_as_uint((float)cumExt[p + cells * c]);
+    for (int c = 0; c < nc; ++c) {
+      const double s = ssa[p + cells * c];
+      if (!(s >= 0.0 && s <= 1.0)) bad |= FLAG_SSA;
+      R[w++] = __float_as_uint((float)s);
+    }
+    for (int c = 0; c < nc; c += 2) {
+      const int32_t i0 = phaseIdx[p + cells * c], i1 = c + 1 < nc ? phaseIdx[p + cells * (c + 1)] : 0;
+      if (i0 < 0 || i0 > 65535 || i1 < 0 || i1 > 65535) bad |= FLAG_IDX;
+      R[w++] = ((uint32_t)i0 & 0xffffu) | ((uint32_t)i1 << 16);
+    }
+    for (; w < words; ++w) R[w] = 0u;
   }
   if (bad) atomicOr(flags, bad);
 }
@@ -536,14 +580,19 @@ static int stream_grid(long long n, int threads, int numSMs) {
   return (int)(want < cap ? (want < 1 ? 1 : want) : cap);
 }
 
-void mcb_launch_pack_optics(const DevDomain &P, float *e32, float *c32, float *s32, uint16_t *i16, int *flags,
-                            int numSMs, cudaStream_t stream) {
+void mcb_launch_pack_optics(const DevDomain &P, float *e32, uint32_t *rec, int *flags,
+                            uint32_t *mask, float *layerExt, int numSMs, cudaStream_t stream) {
   const long long padded = (long long)P.nxp * P.nyp * (P.nz + 2 * MCB_GHOST);
-  const long long n = (long long)P.nx * P.ny * P.nz * P.nc;
+  const long long n = (long long)P.nx * P.ny * P.nz;
   mcbstage::pack_extinction_kernel<<<stream_grid(padded, 256, numSMs), 256, 0, stream>>>(P.totalExt, e32, P.nx, P.ny, P.nz,
                                                                                          MCB_GHOST, flags);
-  mcbstage::pack_components_kernel<<<stream_grid(n, 256, numSMs), 256, 0, stream>>>(P.cumExt, P.ssa, P.phaseIdx, c32, s32,
-                                                                                    i16, n, flags);
+  if (mask) {                                         // occupancy bitmap + clear-sky layer values (large fields only)
+    mcbstage::layer_min_kernel<<<P.nz + 2 * MCB_GHOST, 256, 0, stream>>>(e32, P.nxp, P.nyp, layerExt);
+    mcbstage::occupancy_mask_kernel<<<stream_grid(padded, 256, numSMs), 256, 0, stream>>>(e32, layerExt, padded,
+                                                                                          P.nxp * P.nyp, mask);
+  }
+  mcbstage::pack_components_kernel<<<stream_grid(n, 256, numSMs), 256, 0, stream>>>(P.cumExt, P.ssa, P.phaseIdx, rec,
+                                                                                    P.recShift, n, P.nc, flags);
 }
 
 // comps: kind, physIndex, nTable, zLevelBase + device pointers to the small tables (already staged)

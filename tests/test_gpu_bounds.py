@@ -26,8 +26,13 @@ cases = {"C3_small_mie": (domains.landsat_cloud(ssa=0.99, nxy=24, mie=True), Fal
          "C5_small": (domains.bench_domain(nxy=40, nz=48), False, 100000),
          "single_column": ((_tiny_domain(1, 1, 6), dict(solarMu=0.5, solarAzimuth=0.0)), False, 60000),
          "narrow": ((_tiny_domain(2, 9, 3), dict(solarMu=0.3, solarAzimuth=315.0)), False, 60000)}
+cases["C5_small_bitmap"] = cases["C5_small"]
+cases["C5_small_bitmap_views"] = (domains.bench_domain(nxy=24, nz=32), True, 30000)
 out = {}
+import os
 for name, ((dom, case), views, n) in cases.items():
+    os.environ.pop("MCB_EXT_MASK", None)
+    if "bitmap" in name: os.environ["MCB_EXT_MASK"] = "1"      # occupancy-bitmap variants of the marcher
     g = new_Integrator(dom)
     if views:
         specifyParameters(g, intensityMus=case.get("intensityMus", [1.0, 0.5]), intensityPhis=case.get("intensityPhis", [0.0, 0.0]),

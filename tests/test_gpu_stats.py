@@ -172,6 +172,58 @@ def test_fast_and_reference_arithmetic_agree():
         assert c["photons"] == n
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("extra", [1, 2, 3], ids=["nc3", "nc4", "nc5"])
+def test_many_components_fast_vs_reference(extra):
+    """Component pick, single-scattering albedo and phase-function entry come out of ONE per-cell event record in the
+    throughput kernel (vector loads for nc <= 2, the general record walk beyond).  With 3-5 components its fluxes and
+    per-component radiances agree with the reference-arithmetic kernel (which reads the reference's own f64 arrays
+    and is trace-exact against the oracle) within 4 sigma of the batch-to-batch error."""
+    from mcbrat3d_b200.scatteringPhaseFunctions import henyeyGreenstein, new_PhaseFunctionTable
+    dom, case = domains.irregular_test_domain()
+    rng = np.random.default_rng(100 + extra)
+    nz, ny, nx = dom.numZ, dom.numY, dom.numX
+    for e in range(extra):
+        if e % 2 == 0:                                     # a 3-D aerosol-like component with its own two-entry table
+            ext = rng.uniform(0.0, 25.0, size=(nz, ny, nx)); ext[rng.random(ext.shape) < 0.3] = 0.0
+            idx = np.where(ext > 12.0, 2, 1).astype(np.int32); idx[ext == 0] = 0
+            ssa = np.where(ext > 0, 0.8 + 0.05 * e, 0.0)
+            dom.addOpticalComponent("aerosol%d" % e, ext, ssa, idx,
+                                    new_PhaseFunctionTable([henyeyGreenstein(0.7, 48), henyeyGreenstein(0.3, 24)], key=[1.0, 2.0]))
+        else:                                              # a horizontally uniform one over part of the column
+            dom.addOpticalComponent("layer%d" % e, np.array([6.0, 9.0, 4.0, 2.0]), np.full(4, 0.6), np.ones(4, np.int32),
+                                    new_PhaseFunctionTable([henyeyGreenstein(0.5, 32)], key=[0.0]), zLevelBase=3)
+    dom.getOpticalPropertiesByComponent()
+    nc = 2 + extra
+    n, nb = 40000, 12
+    stats = {}
+    for arith in (MCB_ARITH_FAST, MCB_ARITH_REFERENCE):
+        g = new_Integrator(dom)
+        try:
+            specifyParameters(g, intensityMus=case["intensityMus"][:2], intensityPhis=case["intensityPhis"][:2], computeIntensity=True,
+                              minInverseTableSize=10001, minForwardTableSize=10001, arithmetic=arith)
+            rs = new_RandomNumberSequence([21, 1, 0])
+            rows = []
+            for b in range(nb):
+                ps = new_PhotonStream(case["solarMu"], case["solarAzimuth"], n, rs)
+                computeRadiativeTransfer(g, dom, rs, ps, n)
+                r = reportResults(g, meanFluxUp=True, meanFluxDown=True, meanFluxAbsorbed=True, absorbedProfile=True,
+                                  intensityByComponent=True)
+                byc = np.asarray(r["intensityByComponent"], np.float64).reshape(nc + 1, 2, -1).mean(axis=2)
+                rows.append(np.concatenate([[float(r["meanFluxUp"]), float(r["meanFluxDown"]), float(r["meanFluxAbsorbed"])],
+                                            np.asarray(r["absorbedProfile"], np.float64).ravel(), byc[1:].ravel()]))
+            assert getCounters(g)["bad"] == 0
+            rows = np.array(rows)
+            stats[arith] = (rows.mean(axis=0), rows.std(axis=0, ddof=1) / np.sqrt(nb))
+        finally:
+            finalize_Integrator(g)
+    (ma, ea), (mb, eb) = stats[MCB_ARITH_FAST], stats[MCB_ARITH_REFERENCE]
+    assert (mb[3 + nz:] > 0).all(), "every component must contribute radiance"
+    err = np.sqrt(ea ** 2 + eb ** 2)
+    bad = np.abs(ma - mb) > 4.0 * err + 1e-7
+    assert not bad.any(), (np.nonzero(bad)[0], ma[bad], mb[bad], err[bad])
+
+
 def test_result_independent_of_batch_split():
     """Counter-based RNG keyed by the global photon id: one batch of N equals two accumulated
     batches of N/2 (same photons, same histories) -- the property that makes multi-GPU sharding
@@ -300,6 +352,43 @@ def test_crossing_counts_agree_on_cloud_scenes():
         for q in ("meanFluxUp", "meanFluxDown", "meanFluxAbsorbed"):
             p = float(b[0][q])
             assert abs(float(a[0][q]) - p) < 4.5 * np.sqrt(2.0 * max(p * (1 - p), 1e-4) / n), q
+
+
+def test_occupancy_bitmap_is_exact():
+    """Fields too large for L2 are marched through an occupancy bitmap (gather only where the cell differs from its
+    layer's clear-sky extinction).  Both branches deliver (float)totalExt, so the same photons must give
+    the same event counts exactly and the same tallies up to f64 summation order -- with and without views, on a
+    scene with a molecular background in every cell (C5) and on one with truly empty cells (C3)."""
+    import os
+    for make, views, n in ((lambda: domains.bench_domain(nxy=40, nz=48), False, 300000),
+                           (lambda: domains.landsat_cloud(ssa=0.99, nxy=32), False, 300000),
+                           (lambda: domains.bench_domain(nxy=24, nz=32), True, 40000)):
+        dom, case = make()
+        out = {}
+        for mask in ("0", "1"):
+            os.environ["MCB_EXT_MASK"] = mask
+            try:
+                g = new_Integrator(dom)
+                try:
+                    if views:
+                        specifyParameters(g, intensityMus=[1.0, 0.5, 0.5], intensityPhis=[0.0, 0.0, 180.0], computeIntensity=True,
+                                          useRussianRouletteForIntensity=True, zetaMin=0.3, minForwardTableSize=10001)
+                    specifyParameters(g, minInverseTableSize=10001)
+                    rs = new_RandomNumberSequence([10, 1, 0])
+                    ps = new_PhotonStream(case["solarMu"], case["solarAzimuth"], n, rs)
+                    computeRadiativeTransfer(g, dom, rs, ps, n)
+                    res = reportResults(g, fluxUp=True, fluxDown=True, fluxAbsorbed=True, volumeAbsorption=True,
+                                        **(dict(intensity=True) if views else {}))
+                    out[mask] = (res, getCounters(g))
+                finally:
+                    finalize_Integrator(g)
+            finally:
+                os.environ.pop("MCB_EXT_MASK", None)
+        a, b = out["0"], out["1"]
+        for k in ("crossings", "scatters", "leRays", "leCrossings", "bad"):
+            assert a[1][k] == b[1][k], (k, a[1][k], b[1][k])
+        for k in a[0]:
+            np.testing.assert_allclose(np.asarray(b[0][k]), np.asarray(a[0][k]), rtol=1e-5, atol=1e-7, err_msg=k)
 
 
 def test_hybrid_tables_and_contribution_limit_three_sigma(orc):
