@@ -1,0 +1,73 @@
+"""Independent plane-parallel solver (tests only): the adding-doubling method for the azimuthally averaged radiance
+field of a homogeneous slab over a Lambertian surface, written from the textbook equations (van de Hulst 1963;
+Hansen & Travis 1974, section 4) -- it shares no code, no random numbers and no algorithm with the Monte Carlo path.
+
+It is the deterministic answer for the protocol of ``Drivers/planeParallel.f95:242, 269-272`` (tau, omega, g, theta0
+-> Fup, Fdn): SURVEY section 8c lists it as the substitute pin for a reference that ships no golden vectors.  Fluxes
+are fractions of the incident solar flux on a horizontal surface, which is the normalisation of
+``computeRadiativeTransfer`` (INT:328-350).
+
+Discretisation.  Nodes: N Gauss-Legendre points on (0, 1] for each hemisphere plus the solar zenith cosine as an extra
+node of zero weight.  State vector: the hemispheric flux carried by each node, y_i = w_i mu_i I_i; the direct beam is
+the unit vector on the solar node.  For an optically thin layer d
+    T_ij = delta_ij (1 - d / mu_i) + w_i omega d P(mu_i,  mu_j) / (2 mu_j)
+    R_ij =                           w_i omega d P(mu_i, -mu_j) / (2 mu_j)
+with P the azimuth-averaged phase function sum_l (2l+1) chi_l P_l(mu) P_l(mu'), renormalised on the quadrature so that
+each column conserves energy.  Doubling: R2 = R + T (1 - R R)^-1 R T, T2 = T (1 - R R)^-1 T.
+"""
+import numpy as np
+
+
+def _legendre_matrix(lmax, x):
+    P = np.empty((lmax + 1, x.size))
+    P[0] = 1.0
+    if lmax >= 1:
+        P[1] = x
+    for l in range(1, lmax):
+        P[l + 1] = ((2 * l + 1) * x * P[l] - l * P[l - 1]) / (l + 1)
+    return P
+
+
+def slab_fluxes(tau, omega, chi, mu0, albedo=0.0, nStreams=64, thin=1.0e-5):
+    """(Fup at the top, Fdown at the surface incl. the direct beam, absorbed in the slab), per unit incident flux.
+    ``chi``: Legendre coefficients chi_l of the phase function, chi_0 = 1 (Henyey-Greenstein: g**l)."""
+    chi = np.asarray(chi, dtype=np.float64)
+    x, w = np.polynomial.legendre.leggauss(nStreams)
+    mu = np.concatenate([0.5 * (x + 1.0), [mu0]])
+    wt = np.concatenate([0.5 * w, [0.0]])
+    L = chi.size - 1
+    Pl = _legendre_matrix(L, mu)
+    fac = (2 * np.arange(L + 1) + 1) * chi
+    Pf = (Pl * fac[:, None]).T @ Pl                                            # P(mu_i,  mu_j)
+    Pb = (Pl * (fac * (-1.0) ** np.arange(L + 1))[:, None]).T @ Pl             # P(mu_i, -mu_j)
+    norm = 0.5 * (wt[:, None] * (Pf + Pb)).sum(axis=0)                         # should be 1 per column
+    Pf = Pf / norm[None, :]
+    Pb = Pb / norm[None, :]
+    # doublings: the starting layer is `thin` times the smallest node cosine (the single-scattering start is first order)
+    n = max(int(np.ceil(np.log2(max(tau, 1e-300) / (thin * mu.min())))), 0)
+    d = tau / 2.0 ** n
+    T = np.diag(np.exp(-d / mu)) + wt[:, None] * omega * d * Pf / (2.0 * mu[None, :])
+    R = wt[:, None] * omega * d * Pb / (2.0 * mu[None, :])
+    I = np.eye(mu.size)
+    for _ in range(n):
+        G = np.linalg.solve(I - R @ R, np.concatenate([T, R @ T], axis=1))
+        TG, TGR = T @ G[:, :mu.size], T @ G[:, mu.size:]
+        R, T = R + TGR, TG
+    # Lambertian surface: the reflected flux is shared among the nodes like w_i mu_i
+    lam = wt * mu / (wt * mu).sum()
+    Rs = albedo * np.outer(lam, np.ones(mu.size))
+    y0 = np.zeros(mu.size); y0[-1] = 1.0
+    down = np.linalg.solve(I - R @ Rs, T @ y0)                                 # flux reaching the surface, all orders
+    up = R @ y0 + T @ (Rs @ down)
+    fup, fdn = up.sum(), down.sum()
+    return fup, fdn, 1.0 - fup - (1.0 - albedo) * fdn
+
+
+def table_moments(inverseTable, lmax=127):
+    """Legendre moments chi_l of the phase function the photon loop actually samples: computeScatteringAngle
+    (INT:1594-1621) takes entry int(RN * nS) + 1 of the inverse table, i.e. every entry but the last with equal
+    probability.  The reference builds that table from a CDF on only max(nMoments, 2) Lobatto nodes (INV:107-112), so
+    the sampled function is not the analytic one (Henyey-Greenstein g = 0.85, 64 terms -> g_eff = 0.8517); the
+    deterministic solver must be given the same scattering law to be a test of the transport."""
+    theta = np.asarray(inverseTable, dtype=np.float64).reshape(-1)
+    return _legendre_matrix(lmax, np.cos(theta[:-1])).mean(axis=1)

@@ -224,6 +224,37 @@ def test_many_components_fast_vs_reference(extra):
     assert not bad.any(), (np.nonzero(bad)[0], ma[bad], mb[bad], err[bad])
 
 
+@pytest.mark.parametrize("tau,omega,g,mu0,albedo", [(10.0, 0.99, 0.85, 0.5, 0.2), (10.0, 1.0, 0.85, 0.5, 0.2), (1.0, 0.9, 0.0, 1.0, 0.0),
+                                                   (2.0, 0.95, 0.6, 0.3, 0.5), (0.2, 1.0, 0.85, 0.8, 0.0)])
+@pytest.mark.parametrize("arithmetic", [MCB_ARITH_FAST, MCB_ARITH_REFERENCE], ids=["fast", "reference"])
+def test_plane_parallel_fluxes_match_adding_doubling(tau, omega, g, mu0, albedo, arithmetic):
+    """Both CUDA kernels against the deterministic adding-doubling solution of the plane-parallel problem
+    (tests/adding_doubling.py; protocol of Drivers/planeParallel.f95:242, 269-272) at 1.6e7 photons: reflected,
+    transmitted and absorbed flux within 4 sigma of the batch standard error (+2e-4 for the solver's quadrature and
+    the 10001-entry inverse phase table)."""
+    from adding_doubling import slab_fluxes, table_moments
+    dom, case = domains.homogeneous_slab(ssa=omega, tau=tau, albedo=albedo, g=g, n=8, delta=0.125)
+    n, nb = (1000000, 16) if arithmetic == MCB_ARITH_FAST else (250000, 16)
+    g_ = new_Integrator(dom)
+    try:
+        specifyParameters(g_, minInverseTableSize=10001, arithmetic=arithmetic)
+        rs = new_RandomNumberSequence([10, 1, 0])
+        rows = []
+        for b in range(nb):
+            ps = new_PhotonStream(mu0, 0.0, n, rs)
+            computeRadiativeTransfer(g_, dom, rs, ps, n)
+            r = reportResults(g_, meanFluxUp=True, meanFluxDown=True, meanFluxAbsorbed=True)
+            rows.append([float(r["meanFluxUp"]), float(r["meanFluxDown"]), float(r["meanFluxAbsorbed"])])
+        assert getCounters(g_)["bad"] == 0
+    finally:
+        finalize_Integrator(g_)
+    rows = np.array(rows)
+    m, e = rows.mean(axis=0), rows.std(axis=0, ddof=1) / np.sqrt(nb)
+    dom.tabulateInversePhaseFunctions(10001)
+    want = np.array(slab_fluxes(tau, omega, table_moments(dom.inversePhaseFunctions[0]), mu0, albedo, nStreams=96))
+    assert (np.abs(m - want) < 4.0 * e + 2e-4).all(), (m, want, e)
+
+
 def test_result_independent_of_batch_split():
     """Counter-based RNG keyed by the global photon id: one batch of N equals two accumulated
     batches of N/2 (same photons, same histories) -- the property that makes multi-GPU sharding

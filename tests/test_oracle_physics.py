@@ -173,3 +173,27 @@ def test_make_periodic_is_single_precision(orc):
     assert len(null) > 0
     assert np.array_equal(null["x"], null["x"].astype(np.float32).astype(np.float64))
     assert np.array_equal(null["y"], null["y"].astype(np.float32).astype(np.float64))
+
+
+# (tau, omega, g, mu0, surface albedo): the plane-parallel table protocol of Drivers/planeParallel.f95:242, 269-272
+PLANE_PARALLEL = [(10.0, 0.99, 0.85, 0.5, 0.2), (10.0, 1.0, 0.85, 0.5, 0.2), (1.0, 0.9, 0.0, 1.0, 0.0),
+                  (2.0, 0.95, 0.6, 0.3, 0.5), (0.2, 1.0, 0.85, 0.8, 0.0)]
+
+
+@pytest.mark.parametrize("tau,omega,g,mu0,albedo", PLANE_PARALLEL)
+def test_plane_parallel_fluxes_match_adding_doubling(orc, tau, omega, g, mu0, albedo):
+    """An INDEPENDENT pin of the oracle (SURVEY 8c substitute 3): on a horizontally homogeneous slab the 3-D Monte
+    Carlo must reproduce the deterministic adding-doubling solution of the plane-parallel problem
+    (tests/adding_doubling.py: no shared code, no random numbers; it is given the Legendre moments of the scattering
+    law the inverse table encodes, see table_moments) -- reflected, transmitted and absorbed flux within
+    4 sigma of the batch standard error (+2e-4 for the solver's angular quadrature and the 10001-entry phase table)."""
+    from adding_doubling import slab_fluxes, table_moments
+    d, case = domains.homogeneous_slab(ssa=omega, tau=tau, albedo=albedo, g=g, n=8, delta=0.125)
+    og = orc.OracleIntegrator(orc.OracleDomain(d, tableSize=10001))
+    nb = 40
+    tot, st = og.run_batches(nb, 5000, solarMu=mu0, solarAzimuth=0.0, iseed=10, rank=1, thread=0)
+    d.tabulateInversePhaseFunctions(10001)
+    want = slab_fluxes(tau, omega, table_moments(d.inversePhaseFunctions[0]), mu0, albedo, nStreams=96)
+    for name, w in zip(("meanFluxUpStats", "meanFluxDownStats", "meanFluxAbsorbedStats"), want):
+        m, e = _fin(orc, st, name, tot, nb)
+        assert abs(m[0] - w) < 4.0 * e[0] + 2e-4, (name, m[0], w, e[0])
