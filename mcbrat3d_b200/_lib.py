@@ -14,7 +14,9 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 # MCB_LIB_DEBUG=1 loads the bounds-checked build of the throughput kernel (csrc/Makefile target dbg)
+# MCB_LIB_VARIANT=name loads csrc/libmcbrat_cuda_<name>.so (kernel A/B measurements: csrc/Makefile target variant)
 LIB_PATH = os.path.join(_HERE, "csrc", "libmcbrat_cuda_dbg.so" if os.environ.get("MCB_LIB_DEBUG") == "1"
+                        else "libmcbrat_cuda_%s.so" % os.environ["MCB_LIB_VARIANT"] if os.environ.get("MCB_LIB_VARIANT")
                         else "libmcbrat_cuda.so")
 
 MCB_ARITH_FAST = 0

@@ -243,12 +243,25 @@ int mcb_set_grid(mcb_handle *h, int nx, int ny, int nz,
   P.finvLx = 1.0f / P.fLx; P.finvLy = 1.0f / P.fLy; P.fzMax = (float)P.zMax;
   P.finvhx = xyReg ? 1.0f / P.fhx : 0.0f; P.finvhy = xyReg ? 1.0f / P.fhy : 0.0f;
   // padded extinction field: MCB_GHOST cells on every side (see mcb_set_optics)
+#ifdef MCB_BRICK
+  {
+    const int nxp = (nx + 2 * MCB_GHOST + 1) & ~1, nyp = (ny + 2 * MCB_GHOST + 1) & ~1, nzp = (nz + 2 * MCB_GHOST + 1) & ~1;
+    if ((long long)nxp * nyp * nzp >= (1LL << 31)) FAIL(h, "mcb_set_grid: more than 2^31 cells");
+    const int bx = nxp / 2, by = nyp / 2;
+    P.nxp = nxp; P.nyp = nyp; P.cY = 4 * bx; P.cZ = 4 * bx * by;
+    P.paddedCells = (long long)nxp * nyp * nzp;
+    P.ghostOrigin = (int)mcb_brick_address(MCB_GHOST, MCB_GHOST, MCB_GHOST, bx, by);
+    magic_divisor((uint32_t)bx * (uint32_t)by, &P.divSliceM, &P.divSliceS);      // brick index -> (qx, qy, qz)
+    magic_divisor((uint32_t)bx, &P.divRowM, &P.divRowS);
+  }
+#else
   P.nxp = nx + 2 * MCB_GHOST; P.nyp = ny + 2 * MCB_GHOST;
   if ((long long)P.nxp * P.nyp * (nz + 2 * MCB_GHOST) >= (1LL << 31)) FAIL(h, "mcb_set_grid: more than 2^31 cells");
   P.ghostOrigin = MCB_GHOST + P.nxp * (MCB_GHOST + P.nyp * MCB_GHOST);
   P.paddedCells = (long long)P.nxp * P.nyp * (nz + 2 * MCB_GHOST);
   magic_divisor((uint32_t)P.nxp * (uint32_t)P.nyp, &P.divSliceM, &P.divSliceS);
   magic_divisor((uint32_t)P.nxp, &P.divRowM, &P.divRowS);
+#endif
   h->haveGrid = true; h->haveOptics = false; h->haveSource = false; h->havePhysical = false;
   return 0;
 }
@@ -280,7 +293,7 @@ int mcb_set_optics(mcb_handle *h, int nc, const double *totalExt, const double *
 static int finish_optics(mcb_handle *h, int nc, double albedo, bool zeroFlags) {
   DevDomain &P = h->P;
   const size_t cells = (size_t)P.nx * P.ny * P.nz;
-  const size_t padded = (size_t)P.nxp * P.nyp * (P.nz + 2 * MCB_GHOST);
+  const size_t padded = (size_t)P.paddedCells;
   if (reserve(h, &h->dExt32, sizeof(float) * padded)) return 1;
   int recShift = 0;                                   // event record: (nc-1) + nc + ceil(nc/2) words, padded to 2^recShift
   while ((1 << recShift) < 2 * nc - 1 + (nc + 1) / 2) ++recShift;
@@ -299,7 +312,7 @@ static int finish_optics(mcb_handle *h, int nc, double albedo, bool zeroFlags) {
     P.extMask = nullptr; P.layerExt = nullptr;
     if (useMask) {
       if (reserve(h, &h->dExtMask, sizeof(uint32_t) * ((padded + 31) / 32))) return 1;
-      if (reserve(h, &h->dLayerExt, sizeof(float) * (size_t)(P.nz + 2 * MCB_GHOST))) return 1;
+      if (reserve(h, &h->dLayerExt, sizeof(float) * (size_t)(P.nz + 2 * MCB_GHOST + 2))) return 1;
       P.extMask = (const uint32_t *)h->dExtMask; P.layerExt = (const float *)h->dLayerExt;
     }
   }

@@ -32,6 +32,12 @@ struct DevDomain {
                                               // (periodic replicas in x, y; zeros above and below), pointing AT the
                                               // first real cell: cell (ix,iy,iz) is extp[ix + nxp*(iy + nyp*iz)]
   int nxp, nyp, ghostOrigin;                  // padded row / slice lengths; linear offset of the first real cell
+#ifdef MCB_BRICK
+  // bricked layout: the padded field (dimensions rounded up to even) is stored as 2x2x2-cell bricks, one brick per
+  // 32-byte sector, bricks x-fastest: address(i,j,k) = 8*((k>>1)*by + (j>>1))*bx + (i>>1)) + 4*(k&1) + 2*(j&1) + (i&1).
+  // Whatever axis a ray steps along, the next cell is in the same sector half of the time.
+  int cY, cZ;                                 // 4*bx and 4*bx*by: address(i,j,k) = 4i - 3(i&1) + cY j - (cY-2)(j&1) + cZ k - (cZ-4)(k&1)
+#endif
   long long paddedCells;                      // (nx+2G)(ny+2G)(nz+2G)
   // Fields too large for L2 (C5: 93 MB) carry an occupancy bitmap: bit p of extMask (p = absolute padded cell) is set
   // where the cell's extinction differs from its layer's clear-sky value layerExt[iz + G] (the layer minimum; 0 in the
@@ -76,6 +82,12 @@ struct DevDomain {
 __device__ __forceinline__ long long mcb_checked_index(const struct DevDomain &P, long long i, long long n);
 #else
 #define MCB_CHECK_INDEX(P, i, n) (i)
+#endif
+
+#ifdef MCB_BRICK
+__host__ __device__ inline long long mcb_brick_address(int i, int j, int k, int bx, int by) {   // padded coordinates
+  return ((((long long)(k >> 1) * by + (j >> 1)) * bx + (i >> 1)) << 3) | ((k & 1) << 2) | ((j & 1) << 1) | (i & 1);
+}
 #endif
 
 enum { CNT_PHOTONS = 0, CNT_CROSSINGS, CNT_SCATTERS, CNT_SURFACE, CNT_TOP, CNT_BAD,

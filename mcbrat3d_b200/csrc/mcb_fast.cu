@@ -143,13 +143,37 @@ __device__ __forceinline__ int wrap_index(int i, int n) {
 template <bool WIDE>
 __device__ __forceinline__ void cell_decode(const DevDomain &P, int rel, int &ix, int &iy, int &iz) {
   const uint32_t c = (uint32_t)(rel + P.ghostOrigin);
+#ifdef MCB_BRICK
+  const uint32_t b = c >> 3;                                                    // brick; the low three bits are (z, y, x) inside it
+  const uint32_t bz = (uint32_t)(((uint64_t)P.divSliceM * b) >> P.divSliceS);
+  const uint32_t rem = b - bz * (uint32_t)(P.cZ >> 2);
+  const uint32_t by = (uint32_t)(((uint64_t)P.divRowM * rem) >> P.divRowS);
+  const uint32_t bx = rem - by * (uint32_t)(P.cY >> 2);
+  ix = wrap_index<WIDE>((int)(2u * bx + (c & 1u)) - GH, P.nx);
+  iy = wrap_index<WIDE>((int)(2u * by + ((c >> 1) & 1u)) - GH, P.ny);
+  iz = (int)(2u * bz + ((c >> 2) & 1u)) - GH;
+#else
   const uint32_t z = (uint32_t)(((uint64_t)P.divSliceM * c) >> P.divSliceS);
   const uint32_t rem = c - z * (uint32_t)(P.nxp * P.nyp);
   const uint32_t y = (uint32_t)(((uint64_t)P.divRowM * rem) >> P.divRowS);
   ix = wrap_index<WIDE>((int)(rem - y * (uint32_t)P.nxp) - GH, P.nx);
   iy = wrap_index<WIDE>((int)y - GH, P.ny);
   iz = (int)z - GH;
+#endif
 }
+
+#ifdef MCB_BRICK
+// address of cell (ix, iy, iz) relative to the first real cell (the ghost depth is even, so parities carry over)
+__device__ __forceinline__ int brick_rel(const DevDomain &P, int ix, int iy, int iz) {
+  return 4 * ix - 3 * (ix & 1) + P.cY * iy - (P.cY - 2) * (iy & 1) + P.cZ * iz - (P.cZ - 4) * (iz & 1);
+}
+// address step of the next move along one axis: inside the brick (u) or on to the neighbouring brick (S - u);
+// after every move the two alternate: next = s*S - current
+__device__ __forceinline__ int brick_step(int parity, int s, int u, int S) {
+  const int m = (parity != 0) == (s > 0) ? S - u : u;
+  return s > 0 ? m : -m;
+}
+#endif
 
 // what a burst ends with IS the lane's next state (no translation in the hot loop)
 enum { MARCH_ON = ST_MARCH, MARCH_HIT = ST_SCATTER, MARCH_BOTTOM = ST_SURFACE, MARCH_TOP = ST_TOP };
@@ -180,23 +204,53 @@ __device__ __forceinline__ int march_burst(Ray &r, const DevDomain &P, const Gri
   uint32_t mw[MASK ? B : 1];
   const float t0 = r.t;
   const int sx = r.dx >= 0.0f ? 1 : -1, sy = r.dy >= 0.0f ? 1 : -1, sz = r.dz >= 0.0f ? 1 : -1;
+#ifdef MCB_BRICK
+  int a = brick_rel(P, r.ix, r.iy, r.iz);
+  const int SX = 8 * sx, SY = 2 * P.cY * sy, SZ = 2 * P.cZ * sz;
+  int dax = brick_step(r.ix & 1, sx, 1, 8), day = brick_step(r.iy & 1, sy, 2, 2 * P.cY), daz = brick_step(r.iz & 1, sz, 4, 2 * P.cZ);
+#endif
 #pragma unroll
   for (int k = 0; k < B; ++k) {
     const float tmin = fminf(fminf(r.tx, r.ty), r.tz);
+#ifdef MCB_BRICK
+    ck[k] = a;
+#else
     ck[k] = r.ix + P.nxp * (r.iy + P.nyp * r.iz);
+#endif
     tE[k] = tmin;
     if (MASK) {
       mw[k] = __ldg(P.extMask + MCB_CHECK_INDEX(P, (uint32_t)(ck[k] + P.ghostOrigin) >> 5, (P.paddedCells + 31) >> 5));
       sg[k] = __ldg(P.layerExt + MCB_CHECK_INDEX(P, r.iz + GH, P.nz + 2 * GH));
     }
     if (REG) {
-      { const bool c = r.tx <= tmin; r.ix += c ? sx : 0; r.tx = c ? fmaf(P.fhx, fabsf(r.rx), r.tx) : r.tx; }
-      { const bool c = r.ty <= tmin; r.iy += c ? sy : 0; r.ty = c ? fmaf(P.fhy, fabsf(r.ry), r.ty) : r.ty; }
-      { const bool c = r.tz <= tmin; r.iz += c ? sz : 0; r.tz = c ? fmaf(P.fhz, fabsf(r.rz), r.tz) : r.tz; }
+      // one compare and predicated updates per axis, spelled out so that the index step is not widened into a
+      // select followed by an add
+#ifdef MCB_BRICK
+#define MCB_STEP(T, I, S, H, RR, DA, SS) asm("{\n\t.reg .pred p;\n\t.reg .f32 q;\n\tsetp.le.f32 p, %0, %4;\n\tabs.f32 q, %7;\n\t" \
+                                     "@p add.s32 %1, %1, %5;\n\t@p fma.rn.f32 %0, %6, q, %0;\n\t@p add.s32 %2, %2, %3;\n\t@p sub.s32 %3, %8, %3;\n\t}" \
+                                     : "+f"(T), "+r"(I), "+r"(a), "+r"(DA) : "f"(tmin), "r"(S), "f"(H), "f"(RR), "r"(SS))
+      MCB_STEP(r.tx, r.ix, sx, P.fhx, r.rx, dax, SX);
+      MCB_STEP(r.ty, r.iy, sy, P.fhy, r.ry, day, SY);
+      MCB_STEP(r.tz, r.iz, sz, P.fhz, r.rz, daz, SZ);
+#else
+#define MCB_STEP(T, I, S, H, RR) asm("{\n\t.reg .pred p;\n\t.reg .f32 q;\n\tsetp.le.f32 p, %0, %2;\n\tabs.f32 q, %5;\n\t" \
+                                     "@p add.s32 %1, %1, %3;\n\t@p fma.rn.f32 %0, %4, q, %0;\n\t}" \
+                                     : "+f"(T), "+r"(I) : "f"(tmin), "r"(S), "f"(H), "f"(RR))
+      MCB_STEP(r.tx, r.ix, sx, P.fhx, r.rx);
+      MCB_STEP(r.ty, r.iy, sy, P.fhy, r.ry);
+      MCB_STEP(r.tz, r.iz, sz, P.fhz, r.rz);
+#endif
+#undef MCB_STEP
     } else {
+#ifdef MCB_BRICK
+      { const bool c = r.tx <= tmin; r.ix += c ? sx : 0; a += c ? dax : 0; dax = c ? SX - dax : dax; const float nt = (G.sx[r.ix + (sx > 0 ? 1 : 0)] - r.ox) * r.rx; r.tx = c ? nt : r.tx; }
+      { const bool c = r.ty <= tmin; r.iy += c ? sy : 0; a += c ? day : 0; day = c ? SY - day : day; const float nt = (G.sy[r.iy + (sy > 0 ? 1 : 0)] - r.oy) * r.ry; r.ty = c ? nt : r.ty; }
+      { const bool c = r.tz <= tmin; r.iz += c ? sz : 0; a += c ? daz : 0; daz = c ? SZ - daz : daz; const float nt = (G.sz[r.iz + (sz > 0 ? 1 : 0)] - r.oz) * r.rz; r.tz = c ? nt : r.tz; }
+#else
       { const bool c = r.tx <= tmin; r.ix += c ? sx : 0; const float nt = (G.sx[r.ix + (sx > 0 ? 1 : 0)] - r.ox) * r.rx; r.tx = c ? nt : r.tx; }
       { const bool c = r.ty <= tmin; r.iy += c ? sy : 0; const float nt = (G.sy[r.iy + (sy > 0 ? 1 : 0)] - r.oy) * r.ry; r.ty = c ? nt : r.ty; }
       { const bool c = r.tz <= tmin; r.iz += c ? sz : 0; const float nt = (G.sz[r.iz + (sz > 0 ? 1 : 0)] - r.oz) * r.rz; r.tz = c ? nt : r.tz; }
+#endif
     }
   }
 #pragma unroll
