@@ -19,7 +19,8 @@ void mcb_launch_fast_batch(const DevDomain &P, long long nPhotons, uint64_t seed
                            int numSMs, unsigned long long *workCounter, cudaStream_t stream);
 void mcb_launch_philox_kat(uint64_t seed, uint64_t photon, int n, uint32_t *out, cudaStream_t stream);
 // mcb_stage.cu: device-side packing / validation, normalisation, emission CDF
-void mcb_launch_pack_optics(const DevDomain &P, float *e32, uint32_t *rec, int *flags, uint32_t *mask, float *layerExt,
+void mcb_launch_pack_optics(const DevDomain &P, float *linExt, float *brkExt, uint32_t *rec, int *flags,
+                            uint32_t *linMask, uint32_t *brkMask, float *layerExt,
                             int numSMs, cudaStream_t stream);
 void mcb_launch_normalise(const DevDomain &P, float numPhotons, float *out, int numSMs, cudaStream_t stream);
 long long mcb_emission_tiles(long long cells);
@@ -59,8 +60,8 @@ struct mcb_handle {
   // re-stageable slots (freed on re-set)
   void *dXE = nullptr, *dYE = nullptr, *dZE = nullptr;
   void *dTotalExt = nullptr, *dCumExt = nullptr, *dSsa = nullptr, *dPhaseIdx = nullptr;
-  void *dExt32 = nullptr, *dRec = nullptr;
-  void *dExtMask = nullptr, *dLayerExt = nullptr;     // occupancy bitmap of fields too large for L2
+  void *dExt32 = nullptr, *dExtBrick = nullptr, *dRec = nullptr;
+  void *dExtMask = nullptr, *dExtMaskBrick = nullptr, *dLayerExt = nullptr;     // occupancy bitmap of fields too large for L2
   void *dInv[MCB_MAX_COMP] = {nullptr}, *dFwd[MCB_MAX_COMP] = {nullptr}, *dFwdOrig[MCB_MAX_COMP] = {nullptr};
   int invE[MCB_MAX_COMP] = {0}, fwdE[MCB_MAX_COMP] = {0};
   void *dVoxelCDF = nullptr, *dTemps = nullptr, *dScratch = nullptr, *dResults = nullptr;
@@ -164,7 +165,8 @@ int mcb_destroy(mcb_handle *h) {
   void *slots[] = {h->dXE, h->dYE, h->dZE, h->dTotalExt, h->dCumExt, h->dSsa, h->dPhaseIdx,
                    h->dExt32, h->dRec, h->dVoxelCDF, h->dTally, h->dCounters,
                    h->dTemps, h->dScratch, h->dResults, (void *)h->dFlags, h->dStats, h->dStatsOut,
-                   h->dMassConc, h->dReff, h->dNumConc, h->dAsmTables, h->dExtMask, h->dLayerExt};
+                   h->dMassConc, h->dReff, h->dNumConc, h->dAsmTables, h->dExtMask, h->dLayerExt,
+                   h->dExtBrick, h->dExtMaskBrick};
   for (void *p : slots) if (p) cudaFree(p);
   for (int c = 0; c < MCB_MAX_COMP; ++c) {
     if (h->dInv[c]) cudaFree(h->dInv[c]);
@@ -243,25 +245,25 @@ int mcb_set_grid(mcb_handle *h, int nx, int ny, int nz,
   P.finvLx = 1.0f / P.fLx; P.finvLy = 1.0f / P.fLy; P.fzMax = (float)P.zMax;
   P.finvhx = xyReg ? 1.0f / P.fhx : 0.0f; P.finvhy = xyReg ? 1.0f / P.fhy : 0.0f;
   // padded extinction field: MCB_GHOST cells on every side (see mcb_set_optics)
-#ifdef MCB_BRICK
-  {
+  {                                                  // x-fastest layout
+    DevDomain::ExtField &F = P.lin;
+    F.nxp = nx + 2 * MCB_GHOST; F.nyp = ny + 2 * MCB_GHOST; F.cY = F.cZ = 0;
+    F.padded = (long long)F.nxp * F.nyp * (nz + 2 * MCB_GHOST);
+    F.origin = MCB_GHOST + F.nxp * (MCB_GHOST + F.nyp * MCB_GHOST);
+    magic_divisor((uint32_t)F.nxp * (uint32_t)F.nyp, &F.divSliceM, &F.divSliceS);
+    magic_divisor((uint32_t)F.nxp, &F.divRowM, &F.divRowS);
+  }
+  {                                                  // 2x2x2 bricks: padded dimensions rounded up to even
+    DevDomain::ExtField &F = P.brk;
     const int nxp = (nx + 2 * MCB_GHOST + 1) & ~1, nyp = (ny + 2 * MCB_GHOST + 1) & ~1, nzp = (nz + 2 * MCB_GHOST + 1) & ~1;
     if ((long long)nxp * nyp * nzp >= (1LL << 31)) FAIL(h, "mcb_set_grid: more than 2^31 cells");
     const int bx = nxp / 2, by = nyp / 2;
-    P.nxp = nxp; P.nyp = nyp; P.cY = 4 * bx; P.cZ = 4 * bx * by;
-    P.paddedCells = (long long)nxp * nyp * nzp;
-    P.ghostOrigin = (int)mcb_brick_address(MCB_GHOST, MCB_GHOST, MCB_GHOST, bx, by);
-    magic_divisor((uint32_t)bx * (uint32_t)by, &P.divSliceM, &P.divSliceS);      // brick index -> (qx, qy, qz)
-    magic_divisor((uint32_t)bx, &P.divRowM, &P.divRowS);
+    F.nxp = nxp; F.nyp = nyp; F.cY = 4 * bx; F.cZ = 4 * bx * by;
+    F.padded = (long long)nxp * nyp * nzp;
+    F.origin = (int)mcb_brick_address(MCB_GHOST, MCB_GHOST, MCB_GHOST, bx, by);
+    magic_divisor((uint32_t)bx * (uint32_t)by, &F.divSliceM, &F.divSliceS);      // brick index -> (bx, by, bz)
+    magic_divisor((uint32_t)bx, &F.divRowM, &F.divRowS);
   }
-#else
-  P.nxp = nx + 2 * MCB_GHOST; P.nyp = ny + 2 * MCB_GHOST;
-  if ((long long)P.nxp * P.nyp * (nz + 2 * MCB_GHOST) >= (1LL << 31)) FAIL(h, "mcb_set_grid: more than 2^31 cells");
-  P.ghostOrigin = MCB_GHOST + P.nxp * (MCB_GHOST + P.nyp * MCB_GHOST);
-  P.paddedCells = (long long)P.nxp * P.nyp * (nz + 2 * MCB_GHOST);
-  magic_divisor((uint32_t)P.nxp * (uint32_t)P.nyp, &P.divSliceM, &P.divSliceS);
-  magic_divisor((uint32_t)P.nxp, &P.divRowM, &P.divRowS);
-#endif
   h->haveGrid = true; h->haveOptics = false; h->haveSource = false; h->havePhysical = false;
   return 0;
 }
@@ -293,15 +295,17 @@ int mcb_set_optics(mcb_handle *h, int nc, const double *totalExt, const double *
 static int finish_optics(mcb_handle *h, int nc, double albedo, bool zeroFlags) {
   DevDomain &P = h->P;
   const size_t cells = (size_t)P.nx * P.ny * P.nz;
-  const size_t padded = (size_t)P.paddedCells;
-  if (reserve(h, &h->dExt32, sizeof(float) * padded)) return 1;
+  const size_t padded = (size_t)P.brk.padded;          // the larger of the two layouts
+  if (reserve(h, &h->dExt32, sizeof(float) * (size_t)P.lin.padded)) return 1;
+  if (reserve(h, &h->dExtBrick, sizeof(float) * (size_t)P.brk.padded)) return 1;
   int recShift = 0;                                   // event record: (nc-1) + nc + ceil(nc/2) words, padded to 2^recShift
   while ((1 << recShift) < 2 * nc - 1 + (nc + 1) / 2) ++recShift;
   if (reserve(h, &h->dRec, sizeof(uint32_t) * (cells << recShift))) return 1;
   P.nc = nc; P.albedo = albedo;
   P.totalExt = (const double *)h->dTotalExt; P.cumExt = (const double *)h->dCumExt;
   P.ssa = (const double *)h->dSsa; P.phaseIdx = (const int32_t *)h->dPhaseIdx;
-  P.extp = (const float *)h->dExt32 + P.ghostOrigin;
+  P.lin.ext = (const float *)h->dExt32 + P.lin.origin;
+  P.brk.ext = (const float *)h->dExtBrick + P.brk.origin;
   P.rec = (const uint32_t *)h->dRec; P.recShift = recShift;
   // Occupancy bitmap: only for fields that do not stay L2-resident (default: padded field > 48 MB; the C3 field,
   // 15.5 MB, is served by L2 and gains nothing).  MCB_EXT_MASK=0/1 forces it off/on (measurements, tests).
@@ -309,16 +313,18 @@ static int finish_optics(mcb_handle *h, int nc, double albedo, bool zeroFlags) {
     const char *e = getenv("MCB_EXT_MASK");              // read at every staging, so one process can compare both
     const int maskEnv = e ? atoi(e) : -1;
     const bool useMask = maskEnv >= 0 ? maskEnv > 0 : sizeof(float) * padded > ((size_t)48 << 20);
-    P.extMask = nullptr; P.layerExt = nullptr;
+    P.lin.mask = P.brk.mask = nullptr; P.layerExt = nullptr;
     if (useMask) {
       if (reserve(h, &h->dExtMask, sizeof(uint32_t) * ((padded + 31) / 32))) return 1;
+      if (reserve(h, &h->dExtMaskBrick, sizeof(uint32_t) * ((padded + 31) / 32))) return 1;
       if (reserve(h, &h->dLayerExt, sizeof(float) * (size_t)(P.nz + 2 * MCB_GHOST + 2))) return 1;
-      P.extMask = (const uint32_t *)h->dExtMask; P.layerExt = (const float *)h->dLayerExt;
+      P.lin.mask = (const uint32_t *)h->dExtMask; P.brk.mask = (const uint32_t *)h->dExtMaskBrick;
+      P.layerExt = (const float *)h->dLayerExt;
     }
   }
   if (zeroFlags) CK(h, cudaMemsetAsync(h->dFlags, 0, sizeof(int) * 4, h->stream));
-  mcb_launch_pack_optics(P, (float *)h->dExt32, (uint32_t *)h->dRec, h->dFlags,
-                         (uint32_t *)P.extMask, (float *)P.layerExt,
+  mcb_launch_pack_optics(P, (float *)h->dExt32, (float *)h->dExtBrick, (uint32_t *)h->dRec, h->dFlags,
+                         (uint32_t *)P.lin.mask, (uint32_t *)P.brk.mask, (float *)P.layerExt,
                          h->numSMs, h->stream);
   CK(h, cudaGetLastError());
   int flags4[4] = {0, 0, 0, 0};

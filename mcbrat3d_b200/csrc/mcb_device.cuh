@@ -28,23 +28,30 @@ struct DevDomain {
   double albedo;
   float maxExtinction;                        // real(maxval(totalExt)), INT:448 (maximum cross-section only)
   // ---- packed single-precision copies for the fast kernel ----
-  const float *extp;                          // padded (nx+2G, ny+2G, nz+2G) extinction field with its ghost shell
-                                              // (periodic replicas in x, y; zeros above and below), pointing AT the
-                                              // first real cell: cell (ix,iy,iz) is extp[ix + nxp*(iy + nyp*iz)]
-  int nxp, nyp, ghostOrigin;                  // padded row / slice lengths; linear offset of the first real cell
-#ifdef MCB_BRICK
-  // bricked layout: the padded field (dimensions rounded up to even) is stored as 2x2x2-cell bricks, one brick per
-  // 32-byte sector, bricks x-fastest: address(i,j,k) = 8*((k>>1)*by + (j>>1))*bx + (i>>1)) + 4*(k&1) + 2*(j&1) + (i&1).
-  // Whatever axis a ray steps along, the next cell is in the same sector half of the time.
-  int cY, cZ;                                 // 4*bx and 4*bx*by: address(i,j,k) = 4i - 3(i&1) + cY j - (cY-2)(j&1) + cZ k - (cZ-4)(k&1)
-#endif
-  long long paddedCells;                      // (nx+2G)(ny+2G)(nz+2G)
-  // Fields too large for L2 (C5: 93 MB) carry an occupancy bitmap: bit p of extMask (p = absolute padded cell) is set
-  // where the cell's extinction differs from its layer's clear-sky value layerExt[iz + G] (the layer minimum; 0 in the
-  // ghost layers).  The marcher reads the bitmap (1 bit per cell, L1/L2-resident) and gathers extp only where the bit
-  // is set, so clear-sky cells -- most of a cloud scene -- never go to HBM.  Exact: both branches give (float)totalExt.
-  const uint32_t *extMask;                    // ceil(paddedCells / 32) words, or nullptr
-  const float *layerExt;                      // nz + 2G values
+  // The padded extinction field (ghost shell of MCB_GHOST cells: periodic replicas in x, y; zeros above and below)
+  // is kept in two layouts, each described by an ExtField:
+  //   lin -- x fastest: cell (ix,iy,iz) at ix + nxp*(iy + nyp*iz).  Read by the local-estimation kernels and on narrow
+  //          or irregular grids.
+  //   brk -- 2x2x2-cell bricks, one brick per 32-byte sector, bricks x-fastest (padded dimensions rounded up to even):
+  //          address(i,j,k) = 8*(((k>>1)*by + (j>>1))*bx + (i>>1)) + 4*(k&1) + 2*(j&1) + (i&1)
+  //                         = 4i - 3(i&1) + cY j - (cY-2)(j&1) + cZ k - (cZ-4)(k&1),   cY = 4 bx, cZ = 4 bx by.
+  //          Whatever axis a ray steps along, the next cell is in the same sector half of the time (x-fastest rows:
+  //          7/8 of the x steps, none of the others), which is what bounds the flux kernels: L1TEX->XBAR requests.
+  // Fields too large for L2 (C5: 93 MB) also carry an occupancy bitmap per layout: bit p (p = absolute padded address)
+  // is set where the cell's extinction differs from its layer's clear-sky value layerExt[iz + G] (the layer minimum; 0
+  // in the ghost layers).  The marcher reads the bitmap (1 bit per cell, L1/L2-resident) and gathers the field only
+  // where the bit is set, so clear-sky cells -- most of a cloud scene -- never go to HBM.  Exact: both branches give
+  // (float)totalExt.
+  struct ExtField {
+    const float *ext;                         // points AT the first real cell
+    const uint32_t *mask;                     // ceil(padded / 32) words, or nullptr
+    int nxp, nyp, origin;                     // padded row / slice lengths; address of the first real cell
+    int cY, cZ;                               // bricked layout only
+    uint32_t divSliceM, divRowM;              // address -> (ix,iy,iz): q = (M * n) >> S, exact for n < 2^31
+    int divSliceS, divRowS;
+    long long padded;                         // number of padded cells
+  } lin, brk;
+  const float *layerExt;                      // nz + 2G (+1) clear-sky values
   // one record per cell with everything a scattering event reads, so an event costs ONE gather (a 32 B sector for
   // nc <= 3) instead of a dependent chain through three arrays: 2^recShift u32 words =
   // [f32 cumExt(c), c = 1..nc-1][f32 ssa(c), c = 1..nc][u16 phase index pairs], zero-padded
@@ -52,8 +59,6 @@ struct DevDomain {
   int recShift;
   float fx0, fy0, fz0, fLx, fLy, fLz;         // single-precision grid scalars (fast kernel, constant bank)
   float fhx, fhy, fhz, finvLx, finvLy, finvhx, finvhy, fzMax;
-  uint32_t divSliceM, divRowM;                // padded cell -> (ix,iy,iz): q = (M * n) >> S, exact for n < 2^31
-  int divSliceS, divRowS;
   // ---- tables ----
   const float *inv[MCB_MAX_COMP];  int invS[MCB_MAX_COMP];  int invE[MCB_MAX_COMP], fwdE[MCB_MAX_COMP];   // steps, entries
   const float *fwd[MCB_MAX_COMP];  const float *fwdOrig[MCB_MAX_COMP];  int fwdS[MCB_MAX_COMP];
@@ -84,11 +89,9 @@ __device__ __forceinline__ long long mcb_checked_index(const struct DevDomain &P
 #define MCB_CHECK_INDEX(P, i, n) (i)
 #endif
 
-#ifdef MCB_BRICK
 __host__ __device__ inline long long mcb_brick_address(int i, int j, int k, int bx, int by) {   // padded coordinates
   return ((((long long)(k >> 1) * by + (j >> 1)) * bx + (i >> 1)) << 3) | ((k & 1) << 2) | ((j & 1) << 1) | (i & 1);
 }
-#endif
 
 enum { CNT_PHOTONS = 0, CNT_CROSSINGS, CNT_SCATTERS, CNT_SURFACE, CNT_TOP, CNT_BAD,
        CNT_LE_RAYS, CNT_LE_CROSSINGS, CNT_RR_KILLS, CNT_SURFACE_KILLS, CNT_N };

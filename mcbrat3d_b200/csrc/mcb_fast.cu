@@ -31,9 +31,9 @@ namespace mcbfast {
 #define GH MCB_GHOST
 // gather of the padded extinction field (rel = index relative to the first real cell; may be negative in the shell)
 #ifdef MCB_BOUNDS_CHECK
-#define EXT_AT(P, extp, rel) __ldg((extp) + (mcb_checked_index((P), (long long)(rel) + (P).ghostOrigin, (P).paddedCells) - (P).ghostOrigin))
+#define EXT_AT(P, F, rel) __ldg((F).ext + (mcb_checked_index((P), (long long)(rel) + (F).origin, (F).padded) - (F).origin))
 #else
-#define EXT_AT(P, extp, rel) __ldg((extp) + (rel))
+#define EXT_AT(P, F, rel) __ldg((F).ext + (rel))
 #endif
 
 enum { ST_DEAD = 0, ST_MARCH = 1, ST_SCATTER = 2, ST_SURFACE = 3, ST_TOP = 4, ST_BORN = 5, ST_DONE = 6 };
@@ -140,32 +140,32 @@ __device__ __forceinline__ int wrap_index(int i, int n) {
 // padded linear cell (relative to the first real cell) -> (ix, iy, iz): two divisions by
 // launch-invariant divisors with the precomputed multipliers of the parameter block (exact for every
 // padded cell index < 2^31); x, y come back folded into the domain.
-template <bool WIDE>
+template <bool WIDE, bool BRICK>
 __device__ __forceinline__ void cell_decode(const DevDomain &P, int rel, int &ix, int &iy, int &iz) {
-  const uint32_t c = (uint32_t)(rel + P.ghostOrigin);
-#ifdef MCB_BRICK
-  const uint32_t b = c >> 3;                                                    // brick; the low three bits are (z, y, x) inside it
-  const uint32_t bz = (uint32_t)(((uint64_t)P.divSliceM * b) >> P.divSliceS);
-  const uint32_t rem = b - bz * (uint32_t)(P.cZ >> 2);
-  const uint32_t by = (uint32_t)(((uint64_t)P.divRowM * rem) >> P.divRowS);
-  const uint32_t bx = rem - by * (uint32_t)(P.cY >> 2);
-  ix = wrap_index<WIDE>((int)(2u * bx + (c & 1u)) - GH, P.nx);
-  iy = wrap_index<WIDE>((int)(2u * by + ((c >> 1) & 1u)) - GH, P.ny);
-  iz = (int)(2u * bz + ((c >> 2) & 1u)) - GH;
-#else
-  const uint32_t z = (uint32_t)(((uint64_t)P.divSliceM * c) >> P.divSliceS);
-  const uint32_t rem = c - z * (uint32_t)(P.nxp * P.nyp);
-  const uint32_t y = (uint32_t)(((uint64_t)P.divRowM * rem) >> P.divRowS);
-  ix = wrap_index<WIDE>((int)(rem - y * (uint32_t)P.nxp) - GH, P.nx);
-  iy = wrap_index<WIDE>((int)y - GH, P.ny);
-  iz = (int)z - GH;
-#endif
+  const DevDomain::ExtField &F = BRICK ? P.brk : P.lin;
+  const uint32_t c = (uint32_t)(rel + F.origin);
+  if (BRICK) {
+    const uint32_t b = c >> 3;                                                  // brick; the low three bits are (z, y, x) inside it
+    const uint32_t bz = (uint32_t)(((uint64_t)F.divSliceM * b) >> F.divSliceS);
+    const uint32_t rem = b - bz * (uint32_t)(F.cZ >> 2);
+    const uint32_t by = (uint32_t)(((uint64_t)F.divRowM * rem) >> F.divRowS);
+    const uint32_t bx = rem - by * (uint32_t)(F.cY >> 2);
+    ix = wrap_index<WIDE>((int)(2u * bx + (c & 1u)) - GH, P.nx);
+    iy = wrap_index<WIDE>((int)(2u * by + ((c >> 1) & 1u)) - GH, P.ny);
+    iz = (int)(2u * bz + ((c >> 2) & 1u)) - GH;
+  } else {
+    const uint32_t z = (uint32_t)(((uint64_t)F.divSliceM * c) >> F.divSliceS);
+    const uint32_t rem = c - z * (uint32_t)(F.nxp * F.nyp);
+    const uint32_t y = (uint32_t)(((uint64_t)F.divRowM * rem) >> F.divRowS);
+    ix = wrap_index<WIDE>((int)(rem - y * (uint32_t)F.nxp) - GH, P.nx);
+    iy = wrap_index<WIDE>((int)y - GH, P.ny);
+    iz = (int)z - GH;
+  }
 }
 
-#ifdef MCB_BRICK
-// address of cell (ix, iy, iz) relative to the first real cell (the ghost depth is even, so parities carry over)
-__device__ __forceinline__ int brick_rel(const DevDomain &P, int ix, int iy, int iz) {
-  return 4 * ix - 3 * (ix & 1) + P.cY * iy - (P.cY - 2) * (iy & 1) + P.cZ * iz - (P.cZ - 4) * (iz & 1);
+// bricked layout: address of cell (ix, iy, iz) relative to the first real cell (the ghost depth is even, so parities carry over)
+__device__ __forceinline__ int brick_rel(const DevDomain::ExtField &F, int ix, int iy, int iz) {
+  return 4 * ix - 3 * (ix & 1) + F.cY * iy - (F.cY - 2) * (iy & 1) + F.cZ * iz - (F.cZ - 4) * (iz & 1);
 }
 // address step of the next move along one axis: inside the brick (u) or on to the neighbouring brick (S - u);
 // after every move the two alternate: next = s*S - current
@@ -173,7 +173,6 @@ __device__ __forceinline__ int brick_step(int parity, int s, int u, int S) {
   const int m = (parity != 0) == (s > 0) ? S - u : u;
   return s > 0 ? m : -m;
 }
-#endif
 
 // what a burst ends with IS the lane's next state (no translation in the hot loop)
 enum { MARCH_ON = ST_MARCH, MARCH_HIT = ST_SCATTER, MARCH_BOTTOM = ST_SURFACE, MARCH_TOP = ST_TOP };
@@ -196,69 +195,66 @@ enum { MARCH_ON = ST_MARCH, MARCH_HIT = ST_SCATTER, MARCH_BOTTOM = ST_SURFACE, M
 //
 // MASK (fields too large for L2): the geometry loop also fetches, per cell, the occupancy-bitmap word and the layer's
 // clear-sky extinction (both L1/L2-resident); the gather of the big field is then issued only where the bit is set.
-template <bool REG, bool WIDE, int B, bool MASK>
-__device__ __forceinline__ int march_burst(Ray &r, const DevDomain &P, const Grid &G, const float *__restrict__ extp,
+//
+// BRICK: the field is read in its 2x2x2-brick layout (mcb_device.cuh).  The address is carried along incrementally: a
+// move along an axis adds that axis' current step, and the step then alternates between "inside the brick" and "on to
+// the next brick" -- two predicated integer instructions per axis instead of one, no multiplications.
+template <bool REG, bool WIDE, int B, bool MASK, bool BRICK>
+__device__ __forceinline__ int march_burst(Ray &r, const DevDomain &P, const Grid &G,
                                            float &ext, float target, unsigned &crossings) {
+  const DevDomain::ExtField &F = BRICK ? P.brk : P.lin;
   float tE[B], sg[B];
   int ck[B];
   uint32_t mw[MASK ? B : 1];
   const float t0 = r.t;
   const int sx = r.dx >= 0.0f ? 1 : -1, sy = r.dy >= 0.0f ? 1 : -1, sz = r.dz >= 0.0f ? 1 : -1;
-#ifdef MCB_BRICK
-  int a = brick_rel(P, r.ix, r.iy, r.iz);
-  const int SX = 8 * sx, SY = 2 * P.cY * sy, SZ = 2 * P.cZ * sz;
-  int dax = brick_step(r.ix & 1, sx, 1, 8), day = brick_step(r.iy & 1, sy, 2, 2 * P.cY), daz = brick_step(r.iz & 1, sz, 4, 2 * P.cZ);
-#endif
+  int a = 0, dax = 0, day = 0, daz = 0, SX = 0, SY = 0, SZ = 0;
+  if (BRICK) {
+    a = brick_rel(F, r.ix, r.iy, r.iz);
+    SX = 8 * sx; SY = 2 * F.cY * sy; SZ = 2 * F.cZ * sz;
+    dax = brick_step(r.ix & 1, sx, 1, 8); day = brick_step(r.iy & 1, sy, 2, 2 * F.cY); daz = brick_step(r.iz & 1, sz, 4, 2 * F.cZ);
+  }
 #pragma unroll
   for (int k = 0; k < B; ++k) {
     const float tmin = fminf(fminf(r.tx, r.ty), r.tz);
-#ifdef MCB_BRICK
-    ck[k] = a;
-#else
-    ck[k] = r.ix + P.nxp * (r.iy + P.nyp * r.iz);
-#endif
+    ck[k] = BRICK ? a : r.ix + F.nxp * (r.iy + F.nyp * r.iz);
     tE[k] = tmin;
     if (MASK) {
-      mw[k] = __ldg(P.extMask + MCB_CHECK_INDEX(P, (uint32_t)(ck[k] + P.ghostOrigin) >> 5, (P.paddedCells + 31) >> 5));
+      mw[k] = __ldg(F.mask + MCB_CHECK_INDEX(P, (uint32_t)(ck[k] + F.origin) >> 5, (F.padded + 31) >> 5));
       sg[k] = __ldg(P.layerExt + MCB_CHECK_INDEX(P, r.iz + GH, P.nz + 2 * GH));
     }
     if (REG) {
       // one compare and predicated updates per axis, spelled out so that the index step is not widened into a
       // select followed by an add
-#ifdef MCB_BRICK
+      if (BRICK) {
 #define MCB_STEP(T, I, S, H, RR, DA, SS) asm("{\n\t.reg .pred p;\n\t.reg .f32 q;\n\tsetp.le.f32 p, %0, %4;\n\tabs.f32 q, %7;\n\t" \
                                      "@p add.s32 %1, %1, %5;\n\t@p fma.rn.f32 %0, %6, q, %0;\n\t@p add.s32 %2, %2, %3;\n\t@p sub.s32 %3, %8, %3;\n\t}" \
                                      : "+f"(T), "+r"(I), "+r"(a), "+r"(DA) : "f"(tmin), "r"(S), "f"(H), "f"(RR), "r"(SS))
-      MCB_STEP(r.tx, r.ix, sx, P.fhx, r.rx, dax, SX);
-      MCB_STEP(r.ty, r.iy, sy, P.fhy, r.ry, day, SY);
-      MCB_STEP(r.tz, r.iz, sz, P.fhz, r.rz, daz, SZ);
-#else
+        MCB_STEP(r.tx, r.ix, sx, P.fhx, r.rx, dax, SX);
+        MCB_STEP(r.ty, r.iy, sy, P.fhy, r.ry, day, SY);
+        MCB_STEP(r.tz, r.iz, sz, P.fhz, r.rz, daz, SZ);
+#undef MCB_STEP
+      } else {
 #define MCB_STEP(T, I, S, H, RR) asm("{\n\t.reg .pred p;\n\t.reg .f32 q;\n\tsetp.le.f32 p, %0, %2;\n\tabs.f32 q, %5;\n\t" \
                                      "@p add.s32 %1, %1, %3;\n\t@p fma.rn.f32 %0, %4, q, %0;\n\t}" \
                                      : "+f"(T), "+r"(I) : "f"(tmin), "r"(S), "f"(H), "f"(RR))
-      MCB_STEP(r.tx, r.ix, sx, P.fhx, r.rx);
-      MCB_STEP(r.ty, r.iy, sy, P.fhy, r.ry);
-      MCB_STEP(r.tz, r.iz, sz, P.fhz, r.rz);
-#endif
+        MCB_STEP(r.tx, r.ix, sx, P.fhx, r.rx);
+        MCB_STEP(r.ty, r.iy, sy, P.fhy, r.ry);
+        MCB_STEP(r.tz, r.iz, sz, P.fhz, r.rz);
 #undef MCB_STEP
+      }
     } else {
-#ifdef MCB_BRICK
-      { const bool c = r.tx <= tmin; r.ix += c ? sx : 0; a += c ? dax : 0; dax = c ? SX - dax : dax; const float nt = (G.sx[r.ix + (sx > 0 ? 1 : 0)] - r.ox) * r.rx; r.tx = c ? nt : r.tx; }
-      { const bool c = r.ty <= tmin; r.iy += c ? sy : 0; a += c ? day : 0; day = c ? SY - day : day; const float nt = (G.sy[r.iy + (sy > 0 ? 1 : 0)] - r.oy) * r.ry; r.ty = c ? nt : r.ty; }
-      { const bool c = r.tz <= tmin; r.iz += c ? sz : 0; a += c ? daz : 0; daz = c ? SZ - daz : daz; const float nt = (G.sz[r.iz + (sz > 0 ? 1 : 0)] - r.oz) * r.rz; r.tz = c ? nt : r.tz; }
-#else
       { const bool c = r.tx <= tmin; r.ix += c ? sx : 0; const float nt = (G.sx[r.ix + (sx > 0 ? 1 : 0)] - r.ox) * r.rx; r.tx = c ? nt : r.tx; }
       { const bool c = r.ty <= tmin; r.iy += c ? sy : 0; const float nt = (G.sy[r.iy + (sy > 0 ? 1 : 0)] - r.oy) * r.ry; r.ty = c ? nt : r.ty; }
       { const bool c = r.tz <= tmin; r.iz += c ? sz : 0; const float nt = (G.sz[r.iz + (sz > 0 ? 1 : 0)] - r.oz) * r.rz; r.tz = c ? nt : r.tz; }
-#endif
     }
   }
 #pragma unroll
   for (int k = 0; k < B; ++k) {
     if (MASK) {                                        // bit p of the bitmap: the shift count wraps modulo 32
-      if (__funnelshift_r(mw[k], 0u, (uint32_t)(ck[k] + P.ghostOrigin)) & 1u) sg[k] = EXT_AT(P, extp, ck[k]);
+      if (__funnelshift_r(mw[k], 0u, (uint32_t)(ck[k] + F.origin)) & 1u) sg[k] = EXT_AT(P, F, ck[k]);
     } else {
-      sg[k] = EXT_AT(P, extp, ck[k]);
+      sg[k] = EXT_AT(P, F, ck[k]);
     }
   }
   // accumulate until the target is passed (OPT:1729-1738); from there on acc / tS stay frozen at the
@@ -278,7 +274,7 @@ __device__ __forceinline__ int march_burst(Ray &r, const DevDomain &P, const Gri
   if (found) {
     crossings += (unsigned)(hK + 1);               // cells entered up to and including the hit cell
     r.t = tS + __fdividef(target - acc, hS);           // where the target optical depth is met (OPT:1731)
-    cell_decode<WIDE>(P, hC, r.ix, r.iy, r.iz);
+    cell_decode<WIDE, BRICK>(P, hC, r.ix, r.iy, r.iz);
     return MARCH_HIT;
   }
   ext = acc;
@@ -364,6 +360,9 @@ struct Counts { unsigned crossings, scatters, leRays, leCrossings; };
 // the event phase anyway -- pull (request, direction) tasks from a warp-local counter until none is left.  Every
 // lane advances its current ray by one burst per iteration, so the marcher code stays convergent while rays of
 // very different lengths are in flight; a lane that finishes a ray tallies it and takes the next task.
+#ifndef MCB_LE_BURST
+#define MCB_LE_BURST 8          // cells per burst of a local-estimate ray (C3 + 5 views: 4 -> 5.9e7, 8 -> 6.4e7 photons/s)
+#endif
 #define LE_WORDS 13
 enum { LE_PX = 0, LE_PY, LE_PZ, LE_DX, LE_DY, LE_DZ, LE_W, LE_IXY, LE_IZO, LE_COMP, LE_C0, LE_C1, LE_BLK };
 enum { PH_IDLE = 0, PH_PLAIN, PH_E13, PH_E14A, PH_E14B };
@@ -457,7 +456,7 @@ __device__ void le_run(const DevDomain &P, const Grid &G, const Tally &T, uint32
     }
     if (__all_sync(FULL, done)) break;
     if (phase != PH_IDLE) {
-      const int ev = march_burst<REG, WIDE, 4, MASK>(r, P, G, P.extp, ext, tgt, cnt.leCrossings);
+      const int ev = march_burst<REG, WIDE, MCB_LE_BURST, MASK, false>(r, P, G, ext, tgt, cnt.leCrossings);
       if (ev != MARCH_ON) {
         float contribution = 0.0f;
         bool finished = true;
@@ -496,7 +495,7 @@ __device__ void le_run(const DevDomain &P, const Grid &G, const Tally &T, uint32
   __syncwarp();
 }
 
-template <int THREADS, bool REG, bool WIDE, int MINBLOCKS, int BURST, bool LE, bool MASK>
+template <int THREADS, bool REG, bool WIDE, int MINBLOCKS, int BURST, bool LE, bool MASK, bool BRICK>
 __global__ void __launch_bounds__(THREADS, MINBLOCKS)
 batch_kernel(const __grid_constant__ DevDomain P, long long nPhotons, uint64_t seed, uint64_t firstPhotonId,
              unsigned long long *workCounter, int parkThreshold, const SmemPlan plan) {
@@ -547,7 +546,6 @@ batch_kernel(const __grid_constant__ DevDomain P, long long nPhotons, uint64_t s
     sle = smem + plan.leOff + (threadIdx.x >> 5) * (LE_WORDS * 32 + 32);
     leQueue = (unsigned *)(sle + LE_WORDS * 32);
   }
-  const float *__restrict__ extp = P.extp;
   const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
 
   Counts cnt{0u, 0u, 0u, 0u};
@@ -761,7 +759,7 @@ batch_kernel(const __grid_constant__ DevDomain P, long long nPhotons, uint64_t s
       const unsigned live = __ballot_sync(FULL, state != ST_DONE);
       if (mk == 0u || __popc(live & ~mk) >= parkThreshold) break;
       if (state == ST_MARCH) {
-        state = march_burst<REG, WIDE, BURST, MASK>(r, P, G, extp, ext, tau, cnt.crossings);
+        state = march_burst<REG, WIDE, BURST, MASK, BRICK>(r, P, G, ext, tau, cnt.crossings);
       }
     }
   }
@@ -814,11 +812,11 @@ __global__ void philox_kat_kernel(uint64_t seed, uint64_t photon, int n, uint32_
 
 #include <cstdlib>
 
-template <bool REG, bool WIDE, int MINBLOCKS, int BURST, bool LE, bool MASK = false>
+template <bool REG, bool WIDE, int MINBLOCKS, int BURST, bool LE, bool MASK, bool BRICK>
 static void launch(const DevDomain &P, long long nPhotons, uint64_t seed, uint64_t firstPhotonId, int numSMs,
                    unsigned long long *workCounter, cudaStream_t stream) {
   constexpr int THREADS = 128;
-  auto kernel = mcbfast::batch_kernel<THREADS, REG, WIDE, MINBLOCKS, BURST, LE, MASK>;
+  auto kernel = mcbfast::batch_kernel<THREADS, REG, WIDE, MINBLOCKS, BURST, LE, MASK, BRICK>;
   // shared-memory plan: privatise the tallies when the column / cell grid is small enough to be an
   // atomic hot spot (homogeneous slabs, the 32-column step cloud); large grids spread their
   // atomics over many L2 lines and go straight to the f64 buffer.
@@ -852,27 +850,33 @@ static void launch(const DevDomain &P, long long nPhotons, uint64_t seed, uint64
 void mcb_launch_fast_batch(const DevDomain &P, long long nPhotons, uint64_t seed, uint64_t firstPhotonId,
                            int numSMs, unsigned long long *workCounter, cudaStream_t stream) {
   if (nPhotons <= 0) return;
-  // register budget / burst length variants (tuning knobs; defaults chosen from measurements): the flux-only kernel
-  // fits 64 registers (8 CTAs/SM); the local-estimation kernel keeps a second ray per lane and runs best at 6 CTAs/SM (80 registers)
-  static int occEnv = -2, burst = -1;
-  if (occEnv == -2) { const char *e = getenv("MCB_BLOCKS_PER_SM"); occEnv = e ? atoi(e) : -1; }
-  if (burst < 0) { const char *e = getenv("MCB_BURST"); burst = e ? atoi(e) : 8; }
-  const int occ = occEnv > 0 ? occEnv : (P.nDir > 0 ? 6 : 8);
-#define MCB_GO(REG, WIDE, OCC, BURST) do { \
-    if (P.nDir > 0) launch<REG, WIDE, OCC, BURST, true>(P, nPhotons, seed, firstPhotonId, numSMs, workCounter, stream); \
-    else launch<REG, WIDE, OCC, BURST, false>(P, nPhotons, seed, firstPhotonId, numSMs, workCounter, stream); } while (0)
+  // Kernel variants (defaults chosen from measurements on one B200):
+  //   * flux-only, regular grid at least a ghost shell wide: bricked field, 64 registers = 8 CTAs/SM
+  //     (C3: x-fastest 5.8e8 -> bricked 6.3e8 photons/s);
+  //   * local estimation: x-fastest field, 80 registers = 6 CTAs/SM (a second ray per lane; bricks cost it 10 %);
+  //   * fields too large for L2: the occupancy-bitmap variants (flux: 80 registers);
+  //   * narrow grids (a period shorter than the ghost shell) and irregular grids: x-fastest field.
+  // MCB_BLOCKS_PER_SM = 6 | 8 and MCB_LAYOUT = linear are measurement knobs for the flux-only kernel.
+  const char *eo = getenv("MCB_BLOCKS_PER_SM"), *el = getenv("MCB_LAYOUT");    // read per launch: tests compare both
+  const int occEnv = eo ? atoi(eo) : -1, linEnv = (el && el[0] == 'l') ? 1 : 0;
+#define MCB_GO(REG, WIDE, OCC, LE, MASK, BRICK) \
+    launch<REG, WIDE, OCC, 8, LE, MASK, BRICK>(P, nPhotons, seed, firstPhotonId, numSMs, workCounter, stream)
   const bool wide = P.nx >= MCB_GHOST && P.ny >= MCB_GHOST;      // no grid period shorter than the ghost shell
-  if (P.xyRegular && P.zRegular) {            // burst length <= MCB_GHOST (the ghost shell is that deep)
-    if (wide && P.extMask) {                  // field too large for L2: occupancy-bitmap variants (80 / 64 registers)
-      if (P.nDir > 0) launch<true, true, 6, 8, true, true>(P, nPhotons, seed, firstPhotonId, numSMs, workCounter, stream);
-      else if (occEnv >= 8) launch<true, true, 8, 8, false, true>(P, nPhotons, seed, firstPhotonId, numSMs, workCounter, stream);
-      else launch<true, true, 6, 8, false, true>(P, nPhotons, seed, firstPhotonId, numSMs, workCounter, stream);
-    } else
-    if (!wide) { if (P.nDir > 0) MCB_GO(true, false, 6, 8); else MCB_GO(true, false, 8, 8); }
-    else if (burst >= 8) { if (occ >= 8) MCB_GO(true, true, 8, 8); else if (occ >= 6) MCB_GO(true, true, 6, 8); else MCB_GO(true, true, 4, 8); }
-    else { if (occ >= 8) MCB_GO(true, true, 8, 4); else if (occ >= 6) MCB_GO(true, true, 6, 4); else MCB_GO(true, true, 4, 4); }
+  const bool le = P.nDir > 0, mask = P.lin.mask != nullptr;
+  if (P.xyRegular && P.zRegular) {
+    if (!wide) { if (le) MCB_GO(true, false, 6, true, false, false); else MCB_GO(true, false, 8, false, false, false); }
+    else if (le) { if (mask) MCB_GO(true, true, 6, true, true, false); else MCB_GO(true, true, 6, true, false, false); }
+    else if (mask) {
+      if (linEnv) MCB_GO(true, true, 6, false, true, false);
+      else if (occEnv >= 8) MCB_GO(true, true, 8, false, true, true);
+      else MCB_GO(true, true, 6, false, true, true);
+    } else {
+      if (linEnv) MCB_GO(true, true, 8, false, false, false);
+      else if (occEnv > 0 && occEnv < 8) MCB_GO(true, true, 6, false, false, true);
+      else MCB_GO(true, true, 8, false, false, true);
+    }
   } else {
-    if (burst >= 8) MCB_GO(false, false, 4, 8); else MCB_GO(false, false, 4, 4);
+    if (le) MCB_GO(false, false, 4, true, false, false); else MCB_GO(false, false, 4, false, false, false);
   }
 #undef MCB_GO
 }

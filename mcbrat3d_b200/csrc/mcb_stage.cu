@@ -21,19 +21,20 @@ enum { FLAG_EXT = 1, FLAG_SSA = 2, FLAG_IDX = 4, FLAG_TEMP = 8, FLAG_REFF = 16 }
 // flags[0]: argument-check bits; flags[2..3] (as one u64): bit pattern of maxval(totalExt) -- non-negative
 // doubles order like their bit patterns, so an integer atomicMax does the reduction (INT:448)
 __global__ void pack_extinction_kernel(const double *__restrict__ totalExt, float *__restrict__ e32,
-                                       int nx, int ny, int nz, int G, int *flags, int nxp, int nyp, long long total) {
+                                       int nx, int ny, int nz, int G, int *flags, int nxp, int nyp, long long total, int brick) {
   int bad = 0;
   double emax = 0.0;
   for (long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x; p < total; p += (long long)gridDim.x * blockDim.x) {
-#ifdef MCB_BRICK
-    const int bx = nxp >> 1, by = nyp >> 1, low = (int)(p & 7);                  // padded address -> (i, j, k)
-    const long long b = p >> 3, b2 = b / bx;
-    const int i = 2 * (int)(b % bx) + (low & 1), j = 2 * (int)(b2 % by) + ((low >> 1) & 1), k = 2 * (int)(b2 / by) + (low >> 2);
-#else
-    const int i = (int)(p % nxp);
-    const long long q = p / nxp;
-    const int j = (int)(q % nyp), k = (int)(q / nyp);
-#endif
+    int i, j, k;                                                                 // padded address -> (i, j, k)
+    if (brick) {
+      const int bx = nxp >> 1, by = nyp >> 1, low = (int)(p & 7);
+      const long long b = p >> 3, b2 = b / bx;
+      i = 2 * (int)(b % bx) + (low & 1); j = 2 * (int)(b2 % by) + ((low >> 1) & 1); k = 2 * (int)(b2 / by) + (low >> 2);
+    } else {
+      i = (int)(p % nxp);
+      const long long q = p / nxp;
+      j = (int)(q % nyp); k = (int)(q / nyp);
+    }
     float v = 0.0f;                                              // empty layers above the top and below the surface
     if (k >= G && k < nz + G) {
       int mx = (i - G) % nx; mx += mx < 0 ? nx : 0;                // periodic replicas in x and y (OPT:1782-1796)
@@ -52,16 +53,12 @@ __global__ void pack_extinction_kernel(const double *__restrict__ totalExt, floa
 }
 
 // clear-sky value of every padded layer: the layer minimum of the packed field (ghost layers: 0).  One block per layer.
+// (taken from the x-fastest copy)
 __global__ void layer_min_kernel(const float *__restrict__ e32, int nxp, int nyp, float *__restrict__ layerExt) {
   __shared__ float s[32];
   float m = FLT_MAX;
-#ifdef MCB_BRICK
-  for (int c = threadIdx.x; c < nxp * nyp; c += blockDim.x)
-    m = fminf(m, e32[mcb_brick_address(c % nxp, c / nxp, (int)blockIdx.x, nxp >> 1, nyp >> 1)]);
-#else
   const float *L = e32 + (long long)blockIdx.x * nxp * nyp;
   for (int i = threadIdx.x; i < nxp * nyp; i += blockDim.x) m = fminf(m, L[i]);
-#endif
   for (int o = 16; o > 0; o >>= 1) m = fminf(m, __shfl_down_sync(0xffffffffu, m, o));
   if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = m;
   __syncthreads();
@@ -75,7 +72,7 @@ __global__ void layer_min_kernel(const float *__restrict__ e32, int nxp, int nyp
 // occupancy bitmap of the padded field: bit p set where e32[p] differs from its layer's clear-sky value.
 // One warp builds one 32-bit word per iteration with a ballot (coalesced read, one store per warp).
 __global__ void occupancy_mask_kernel(const float *__restrict__ e32, const float *__restrict__ layerExt, long long total,
-                                      int slice, uint32_t *__restrict__ mask) {
+                                      int slice, uint32_t *__restrict__ mask, int brick) {
   const long long words = (total + 31) >> 5;
   const int lane = threadIdx.x & 31;
   const long long warp = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
@@ -83,11 +80,8 @@ __global__ void occupancy_mask_kernel(const float *__restrict__ e32, const float
   for (long long w = warp; w < words; w += nwarps) {
     const long long p = (w << 5) + lane;
     bool bit = false;
-#ifdef MCB_BRICK
-    if (p < total) bit = e32[p] != layerExt[2 * ((p >> 3) / (slice >> 2)) + ((p >> 2) & 1)];   // slice/4 bricks per brick layer
-#else
-    if (p < total) bit = e32[p] != layerExt[p / slice];
-#endif
+    // layer of address p: x-fastest p / slice; bricked: slice/4 bricks per brick layer, bit 2 of p = z inside the brick
+    if (p < total) bit = e32[p] != layerExt[brick ? 2 * ((p >> 3) / (slice >> 2)) + ((p >> 2) & 1) : p / slice];
     const unsigned m = __ballot_sync(0xffffffffu, bit);
     if (lane == 0) mask[w] = m;
   }
@@ -593,16 +587,22 @@ static int stream_grid(long long n, int threads, int numSMs) {
   return (int)(want < cap ? (want < 1 ? 1 : want) : cap);
 }
 
-void mcb_launch_pack_optics(const DevDomain &P, float *e32, uint32_t *rec, int *flags,
-                            uint32_t *mask, float *layerExt, int numSMs, cudaStream_t stream) {
-  const long long padded = P.paddedCells;
+void mcb_launch_pack_optics(const DevDomain &P, float *linExt, float *brkExt, uint32_t *rec, int *flags,
+                            uint32_t *linMask, uint32_t *brkMask, float *layerExt, int numSMs, cudaStream_t stream) {
   const long long n = (long long)P.nx * P.ny * P.nz;
-  mcbstage::pack_extinction_kernel<<<stream_grid(padded, 256, numSMs), 256, 0, stream>>>(P.totalExt, e32, P.nx, P.ny, P.nz,
-                                                                                         MCB_GHOST, flags, P.nxp, P.nyp, padded);
-  if (mask) {                                         // occupancy bitmap + clear-sky layer values (large fields only)
-    mcbstage::layer_min_kernel<<<(int)(padded / ((long long)P.nxp * P.nyp)), 256, 0, stream>>>(e32, P.nxp, P.nyp, layerExt);
-    mcbstage::occupancy_mask_kernel<<<stream_grid(padded, 256, numSMs), 256, 0, stream>>>(e32, layerExt, padded,
-                                                                                          P.nxp * P.nyp, mask);
+  const int layers = P.nz + 2 * MCB_GHOST;
+  // both layouts of the padded field (mcb_device.cuh); the argument flags / maxval are produced by the first pass only
+  mcbstage::pack_extinction_kernel<<<stream_grid(P.lin.padded, 256, numSMs), 256, 0, stream>>>(
+      P.totalExt, linExt, P.nx, P.ny, P.nz, MCB_GHOST, flags, P.lin.nxp, P.lin.nyp, P.lin.padded, 0);
+  mcbstage::pack_extinction_kernel<<<stream_grid(P.brk.padded, 256, numSMs), 256, 0, stream>>>(
+      P.totalExt, brkExt, P.nx, P.ny, P.nz, MCB_GHOST, flags, P.brk.nxp, P.brk.nyp, P.brk.padded, 1);
+  if (linMask) {                                      // occupancy bitmaps + clear-sky layer values (large fields only)
+    cudaMemsetAsync(layerExt, 0, sizeof(float) * (layers + 2), stream);
+    mcbstage::layer_min_kernel<<<layers, 256, 0, stream>>>(linExt, P.lin.nxp, P.lin.nyp, layerExt);
+    mcbstage::occupancy_mask_kernel<<<stream_grid(P.lin.padded, 256, numSMs), 256, 0, stream>>>(
+        linExt, layerExt, P.lin.padded, P.lin.nxp * P.lin.nyp, linMask, 0);
+    mcbstage::occupancy_mask_kernel<<<stream_grid(P.brk.padded, 256, numSMs), 256, 0, stream>>>(
+        brkExt, layerExt, P.brk.padded, P.brk.nxp * P.brk.nyp, brkMask, 1);
   }
   mcbstage::pack_components_kernel<<<stream_grid(n, 256, numSMs), 256, 0, stream>>>(P.cumExt, P.ssa, P.phaseIdx, rec,
                                                                                     P.recShift, n, P.nc, flags);

@@ -24,6 +24,8 @@ cases = {"C3_small_mie": (domains.landsat_cloud(ssa=0.99, nxy=24, mie=True), Fal
          "C2_views": (domains.step_cloud(ssa=0.99, solarMu=0.5), True, 60000),
          "T_irr_views": (domains.irregular_test_domain(), True, 60000),
          "C5_small": (domains.bench_domain(nxy=40, nz=48), False, 100000),
+         "C5_small_odd": (domains.bench_domain(nxy=41, nz=47), False, 100000),
+         "C5_small_odd_bitmap": (domains.bench_domain(nxy=41, nz=47), False, 100000),
          "single_column": ((_tiny_domain(1, 1, 6), dict(solarMu=0.5, solarAzimuth=0.0)), False, 60000),
          "narrow": ((_tiny_domain(2, 9, 3), dict(solarMu=0.3, solarAzimuth=315.0)), False, 60000)}
 cases["C5_small_bitmap"] = cases["C5_small"]

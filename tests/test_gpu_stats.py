@@ -422,6 +422,43 @@ def test_occupancy_bitmap_is_exact():
             np.testing.assert_allclose(np.asarray(b[0][k]), np.asarray(a[0][k]), rtol=1e-5, atol=1e-7, err_msg=k)
 
 
+def test_bricked_layout_is_exact():
+    """The flux kernels read the extinction field as 2x2x2 bricks (one brick per 32-byte sector), everything else
+    reads the x-fastest copy.  The layout changes addresses, not values: the same photons give the same
+    event counts exactly and the same tallies up to f64 summation order -- with even and odd grid sizes (odd padded
+    dimensions are rounded up), with and without the occupancy bitmap."""
+    import os
+    for make, mask, n in ((lambda: domains.landsat_cloud(ssa=0.99, nxy=32), None, 300000),
+                          (lambda: domains.bench_domain(nxy=41, nz=47), None, 200000),
+                          (lambda: domains.bench_domain(nxy=41, nz=47), "1", 200000),
+                          (lambda: domains.homogeneous_slab(ssa=0.99, n=9, delta=0.125), None, 200000)):
+        dom, case = make()
+        out = {}
+        for layout in ("linear", "bricks"):
+            os.environ["MCB_LAYOUT"] = layout
+            if mask:
+                os.environ["MCB_EXT_MASK"] = mask
+            try:
+                g = new_Integrator(dom)
+                try:
+                    specifyParameters(g, minInverseTableSize=10001)
+                    rs = new_RandomNumberSequence([10, 1, 0])
+                    ps = new_PhotonStream(case["solarMu"], case["solarAzimuth"], n, rs)
+                    computeRadiativeTransfer(g, dom, rs, ps, n)
+                    out[layout] = (reportResults(g, fluxUp=True, fluxDown=True, fluxAbsorbed=True, volumeAbsorption=True),
+                                   getCounters(g))
+                finally:
+                    finalize_Integrator(g)
+            finally:
+                os.environ.pop("MCB_LAYOUT", None); os.environ.pop("MCB_EXT_MASK", None)
+        a, b = out["linear"], out["bricks"]
+        for k in ("crossings", "scatters", "bad"):
+            assert a[1][k] == b[1][k], (k, a[1][k], b[1][k])
+        assert a[1]["crossings"] > n
+        for k in a[0]:
+            np.testing.assert_allclose(np.asarray(b[0][k]), np.asarray(a[0][k]), rtol=1e-5, atol=1e-7, err_msg=k)
+
+
 def test_hybrid_tables_and_contribution_limit_three_sigma(orc):
     """The throughput kernel with hybrid forward tables (orders > 1 use the Gaussian-peaked table) and limited
     contributions redistributed at the end of the batch (INT:294-322): mean radiances within 3 sigma of the oracle."""
