@@ -19,9 +19,10 @@ void mcb_launch_fast_batch(const DevDomain &P, long long nPhotons, uint64_t seed
                            int numSMs, unsigned long long *workCounter, cudaStream_t stream);
 void mcb_launch_philox_kat(uint64_t seed, uint64_t photon, int n, uint32_t *out, cudaStream_t stream);
 // mcb_stage.cu: device-side packing / validation, normalisation, emission CDF
-void mcb_launch_pack_optics(const DevDomain &P, float *linExt, float *brkExt, uint32_t *rec, int *flags,
-                            uint32_t *linMask, uint32_t *brkMask, float *layerExt,
-                            int numSMs, cudaStream_t stream);
+void mcb_launch_pack_field(const DevDomain &P, int brick, float *ext, uint32_t *mask, float *layerExt, int *flags,
+                           int numSMs, cudaStream_t stream);
+void mcb_launch_pack_records(const DevDomain &P, uint32_t *rec, int *flags, int numSMs, cudaStream_t stream);
+bool mcb_fast_reads_bricks(const DevDomain &P);
 void mcb_launch_normalise(const DevDomain &P, float numPhotons, float *out, int numSMs, cudaStream_t stream);
 long long mcb_emission_tiles(long long cells);
 void mcb_launch_emission_cdf(const DevDomain &P, const double *temps, double a, double b, double lambda5, void *scratch,
@@ -54,6 +55,7 @@ struct mcb_handle {
   std::string err;
   DevDomain P;
   bool haveGrid = false, haveOptics = false, haveSource = false;
+  bool packedLin = false, packedBrk = false;     // which layouts of the extinction field hold the current optics
   bool haveInv[MCB_MAX_COMP] = {false}, haveFwd[MCB_MAX_COMP] = {false};
   std::vector<double> xE, yE, zE;
   std::map<void **, size_t> slotBytes;    // capacity of every re-stageable slot (reused while large enough)
@@ -270,6 +272,16 @@ int mcb_set_grid(mcb_handle *h, int nx, int ny, int nz,
 
 static int finish_optics(mcb_handle *h, int nc, double albedo, bool zeroFlags = true);
 
+static int pack_field(mcb_handle *h, bool brick) {
+  DevDomain &P = h->P;
+  if (brick ? h->packedBrk : h->packedLin) return 0;
+  mcb_launch_pack_field(P, brick ? 1 : 0, (float *)(brick ? h->dExtBrick : h->dExt32),
+                        (uint32_t *)(brick ? P.brk.mask : P.lin.mask), (float *)P.layerExt, h->dFlags, h->numSMs, h->stream);
+  CK(h, cudaGetLastError());
+  (brick ? h->packedBrk : h->packedLin) = true;
+  return 0;
+}
+
 int mcb_set_optics(mcb_handle *h, int nc, const double *totalExt, const double *cumExt,
                    const double *ssa, const int32_t *phaseIdx, double albedo) {
   if (!h) return 1;
@@ -323,9 +335,10 @@ static int finish_optics(mcb_handle *h, int nc, double albedo, bool zeroFlags) {
     }
   }
   if (zeroFlags) CK(h, cudaMemsetAsync(h->dFlags, 0, sizeof(int) * 4, h->stream));
-  mcb_launch_pack_optics(P, (float *)h->dExt32, (float *)h->dExtBrick, (uint32_t *)h->dRec, h->dFlags,
-                         (uint32_t *)P.lin.mask, (uint32_t *)P.brk.mask, (float *)P.layerExt,
-                         h->numSMs, h->stream);
+  // the layout the next launch will read is packed now (with the argument checks); the other one on demand (run())
+  h->packedLin = h->packedBrk = false;
+  if (pack_field(h, mcb_fast_reads_bricks(P))) return 1;
+  mcb_launch_pack_records(P, (uint32_t *)h->dRec, h->dFlags, h->numSMs, h->stream);
   CK(h, cudaGetLastError());
   int flags4[4] = {0, 0, 0, 0};
   CK(h, cudaMemcpyAsync(flags4, h->dFlags, sizeof(flags4), cudaMemcpyDeviceToHost, h->stream));
@@ -712,6 +725,8 @@ static int run(mcb_handle *h, long long nPhotons, uint64_t seed, uint64_t firstP
   // refreshes the photon's cell indices after a move, which is reproduced verbatim and is not a throughput path
   if (P.opt.arithmetic == MCB_ARITH_REFERENCE || !P.opt.useRayTracing)
     mcb_launch_reference_batch(P, nPhotons, seed, firstPhotonId, h->numSMs, h->stream);
+  else if (pack_field(h, mcb_fast_reads_bricks(P)))            // no-op unless views were switched on/off since staging
+    return 1;
   else
     mcb_launch_fast_batch(P, nPhotons, seed, firstPhotonId, h->numSMs, h->dCounters + CNT_N, h->stream);
   CK(h, cudaGetLastError());

@@ -859,6 +859,13 @@ static void launch(const DevDomain &P, long long nPhotons, uint64_t seed, uint64
   kernel<<<blocks, THREADS, smem, stream>>>(P, nPhotons, seed, firstPhotonId, workCounter, park, plan);
 }
 
+// which layout of the extinction field the dispatcher below reads (the API packs that one)
+bool mcb_fast_reads_bricks(const DevDomain &P) {
+  const char *el = getenv("MCB_LAYOUT");
+  const bool wide = P.nx >= MCB_GHOST && P.ny >= MCB_GHOST;
+  return P.xyRegular && P.zRegular && wide && P.nDir == 0 && !(el && el[0] == 'l');
+}
+
 void mcb_launch_fast_batch(const DevDomain &P, long long nPhotons, uint64_t seed, uint64_t firstPhotonId,
                            int numSMs, unsigned long long *workCounter, cudaStream_t stream) {
   if (nPhotons <= 0) return;

@@ -52,20 +52,20 @@ __global__ void pack_extinction_kernel(const double *__restrict__ totalExt, floa
     atomicMax((unsigned long long *)(flags + 2), (unsigned long long)__double_as_longlong(emax));
 }
 
-// clear-sky value of every padded layer: the layer minimum of the packed field (ghost layers: 0).  One block per layer.
-// (taken from the x-fastest copy)
-__global__ void layer_min_kernel(const float *__restrict__ e32, int nxp, int nyp, float *__restrict__ layerExt) {
+// clear-sky value of every layer: the layer minimum of (float)totalExt (the ghost layers keep the 0 they were cleared
+// to).  One block per real layer.
+__global__ void layer_min_kernel(const double *__restrict__ totalExt, int cols, int G, float *__restrict__ layerExt) {
   __shared__ float s[32];
+  const double *L = totalExt + (long long)blockIdx.x * cols;
   float m = FLT_MAX;
-  const float *L = e32 + (long long)blockIdx.x * nxp * nyp;
-  for (int i = threadIdx.x; i < nxp * nyp; i += blockDim.x) m = fminf(m, L[i]);
+  for (int i = threadIdx.x; i < cols; i += blockDim.x) m = fminf(m, (float)L[i]);
   for (int o = 16; o > 0; o >>= 1) m = fminf(m, __shfl_down_sync(0xffffffffu, m, o));
   if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = m;
   __syncthreads();
   if (threadIdx.x < 32) {
     m = threadIdx.x < (blockDim.x >> 5) ? s[threadIdx.x] : FLT_MAX;
     for (int o = 16; o > 0; o >>= 1) m = fminf(m, __shfl_down_sync(0xffffffffu, m, o));
-    if (threadIdx.x == 0) layerExt[blockIdx.x] = m;
+    if (threadIdx.x == 0) layerExt[blockIdx.x + G] = m;
   }
 }
 
@@ -587,23 +587,24 @@ static int stream_grid(long long n, int threads, int numSMs) {
   return (int)(want < cap ? (want < 1 ? 1 : want) : cap);
 }
 
-void mcb_launch_pack_optics(const DevDomain &P, float *linExt, float *brkExt, uint32_t *rec, int *flags,
-                            uint32_t *linMask, uint32_t *brkMask, float *layerExt, int numSMs, cudaStream_t stream) {
-  const long long n = (long long)P.nx * P.ny * P.nz;
-  const int layers = P.nz + 2 * MCB_GHOST;
-  // both layouts of the padded field (mcb_device.cuh); the argument flags / maxval are produced by the first pass only
-  mcbstage::pack_extinction_kernel<<<stream_grid(P.lin.padded, 256, numSMs), 256, 0, stream>>>(
-      P.totalExt, linExt, P.nx, P.ny, P.nz, MCB_GHOST, flags, P.lin.nxp, P.lin.nyp, P.lin.padded, 0);
-  mcbstage::pack_extinction_kernel<<<stream_grid(P.brk.padded, 256, numSMs), 256, 0, stream>>>(
-      P.totalExt, brkExt, P.nx, P.ny, P.nz, MCB_GHOST, flags, P.brk.nxp, P.brk.nyp, P.brk.padded, 1);
-  if (linMask) {                                      // occupancy bitmaps + clear-sky layer values (large fields only)
-    cudaMemsetAsync(layerExt, 0, sizeof(float) * (layers + 2), stream);
-    mcbstage::layer_min_kernel<<<layers, 256, 0, stream>>>(linExt, P.lin.nxp, P.lin.nyp, layerExt);
-    mcbstage::occupancy_mask_kernel<<<stream_grid(P.lin.padded, 256, numSMs), 256, 0, stream>>>(
-        linExt, layerExt, P.lin.padded, P.lin.nxp * P.lin.nyp, linMask, 0);
-    mcbstage::occupancy_mask_kernel<<<stream_grid(P.brk.padded, 256, numSMs), 256, 0, stream>>>(
-        brkExt, layerExt, P.brk.padded, P.brk.nxp * P.brk.nyp, brkMask, 1);
+// One layout of the padded extinction field (mcb_device.cuh) and, for fields too large for L2, its occupancy bitmap.
+// Also runs the extinction argument check and the maxval reduction (flags).
+void mcb_launch_pack_field(const DevDomain &P, int brick, float *ext, uint32_t *mask, float *layerExt, int *flags,
+                           int numSMs, cudaStream_t stream) {
+  const DevDomain::ExtField &F = brick ? P.brk : P.lin;
+  mcbstage::pack_extinction_kernel<<<stream_grid(F.padded, 256, numSMs), 256, 0, stream>>>(
+      P.totalExt, ext, P.nx, P.ny, P.nz, MCB_GHOST, flags, F.nxp, F.nyp, F.padded, brick);
+  if (mask) {
+    cudaMemsetAsync(layerExt, 0, sizeof(float) * (P.nz + 2 * MCB_GHOST + 2), stream);
+    mcbstage::layer_min_kernel<<<P.nz, 256, 0, stream>>>(P.totalExt, P.nx * P.ny, MCB_GHOST, layerExt);
+    mcbstage::occupancy_mask_kernel<<<stream_grid(F.padded, 256, numSMs), 256, 0, stream>>>(ext, layerExt, F.padded,
+                                                                                            F.nxp * F.nyp, mask, brick);
   }
+}
+
+// per-cell event records + the argument checks of the per-component arrays
+void mcb_launch_pack_records(const DevDomain &P, uint32_t *rec, int *flags, int numSMs, cudaStream_t stream) {
+  const long long n = (long long)P.nx * P.ny * P.nz;
   mcbstage::pack_components_kernel<<<stream_grid(n, 256, numSMs), 256, 0, stream>>>(P.cumExt, P.ssa, P.phaseIdx, rec,
                                                                                     P.recShift, n, P.nc, flags);
 }
