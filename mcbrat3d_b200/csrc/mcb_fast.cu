@@ -44,7 +44,7 @@ struct SmemPlan {
   int fluxOff;             // float[3*cols]  privatised fluxUp|fluxDown|fluxAbs   (-1: global atomics)
   int volOff;              // float[cells]   privatised volumeAbsorption           (-1: global atomics)
   int intOff;              // float[cols*nDir] privatised intensity                (-1: global atomics)
-  int leOff;               // per warp: LE_WORDS x 32 request slots + 32 words of queue state (LE kernels only)
+  int leOff;               // per warp: LE_WORDS x 32 request slots + 64 words of queue state: task counter, rank -> lane map
   int totalFloats;
 };
 
@@ -130,9 +130,9 @@ __device__ __forceinline__ int wrap_index(int i, int n) {
   if (WIDE) {
     i += i < 0 ? n : 0;
     i -= i >= n ? n : 0;
-  } else {
-    while (i < 0) i += n;
-    while (i >= n) i -= n;
+  } else {                               // one remainder instead of a loop per period: the lanes of a warp stay together
+    i %= n;
+    i += i < 0 ? n : 0;
   }
   return i;
 }
@@ -391,7 +391,9 @@ __device__ void le_run(const DevDomain &P, const Grid &G, const Tally &T, uint32
                        float photonTau, int &photonState) {
   const int nDir = P.nDir;
   const int nTasks = __popc(posted) * nDir;
+  const float invDir = 1.0f / (float)nDir;
   if (lane == 0) *queue = 0u;
+  if ((posted >> lane) & 1u) queue[1 + __popc(posted & ((1u << lane) - 1u))] = (unsigned)lane;   // r-th request -> its lane
   __syncwarp();
   Ray r;
   r.ox = r.oy = r.oz = 0.0f; r.dx = r.dy = 0.0f; r.dz = 1.0f; r.rx = r.ry = r.rz = FLT_MAX;
@@ -406,9 +408,9 @@ __device__ void le_run(const DevDomain &P, const Grid &G, const Tally &T, uint32
         done = true;
         if (photonState == ST_MARCH) { r = photonRay; ext = photonExt; tgt = photonTau; phase = PH_PHOTON; mine = true; }
       } else {
-        const int req = t / nDir;
+        const int req = (int)(((float)t + 0.5f) * invDir);        // t / nDir (t < 32 * MCB_MAX_DIR: exact)
         dir = t - req * nDir;
-        const int s = (int)__fns(posted, 0u, req + 1);   // lane that posted the req-th request
+        const int s = (int)queue[1 + req];                         // lane that posted the req-th request
         const float vx = P.viewDir[3 * dir], vy = P.viewDir[3 * dir + 1], vz = P.viewDir[3 * dir + 2];
         const int ixy = __float_as_int(sle[LE_IXY * 32 + s]), izo = __float_as_int(sle[LE_IZO * 32 + s]);
         comps = __float_as_int(sle[LE_COMP * 32 + s]);
@@ -553,7 +555,7 @@ batch_kernel(const __grid_constant__ DevDomain P, long long nPhotons, uint64_t s
   float *sle = nullptr;
   unsigned *leQueue = nullptr;
   if (LE) {
-    sle = smem + plan.leOff + (threadIdx.x >> 5) * (LE_WORDS * 32 + 32);
+    sle = smem + plan.leOff + (threadIdx.x >> 5) * (LE_WORDS * 32 + 64);
     leQueue = (unsigned *)(sle + LE_WORDS * 32);
   }
   const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
@@ -840,7 +842,7 @@ static void launch(const DevDomain &P, long long nPhotons, uint64_t seed, uint64
   if (3 * cols <= 3 * 1024 && off + 3 * cols <= budgetFloats) { plan.fluxOff = off; off += 3 * cols; }
   if (cells <= 8192 && off + cells <= budgetFloats) { plan.volOff = off; off += cells; }
   if (P.nDir > 0 && cols * P.nDir <= 2048 && off + cols * P.nDir <= budgetFloats) { plan.intOff = off; off += cols * P.nDir; }
-  if (LE) { plan.leOff = off; off += (THREADS / 32) * (LE_WORDS * 32 + 32); }
+  if (LE) { plan.leOff = off; off += (THREADS / 32) * (LE_WORDS * 32 + 64); }
   plan.totalFloats = off;
   const size_t smem = sizeof(float) * (size_t)off;
   cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
