@@ -515,6 +515,7 @@ int mcb_build_forward_table(mcb_handle *h, int comp, int nS, int nE, const int32
   if (settle(h)) return 1;
   h->P.fwd[c] = (const float *)h->dFwd[c]; h->P.fwdOrig[c] = (const float *)h->dFwdOrig[c];
   h->P.fwdS[c] = nS; h->fwdE[c] = nE; h->P.fwdE[c] = nE; h->haveFwd[c] = true;
+  h->P.fwdInvDTheta[c] = (float)(nS - 1) / 3.14159265358979312f;
   return 0;
 }
 
@@ -549,6 +550,7 @@ int mcb_set_forward_table(mcb_handle *h, int comp, int nS, int nE, const float *
   if (stage(h, &h->dFwdOrig[c], Porig ? Porig : Pf, sizeof(float) * (size_t)nS * nE)) return 1;
   h->P.fwd[c] = (const float *)h->dFwd[c]; h->P.fwdOrig[c] = (const float *)h->dFwdOrig[c];
   h->P.fwdS[c] = nS; h->fwdE[c] = nE; h->P.fwdE[c] = nE; h->haveFwd[c] = true;
+  h->P.fwdInvDTheta[c] = (float)(nS - 1) / 3.14159265358979312f;
   return 0;
 }
 
@@ -561,6 +563,7 @@ int mcb_set_views(mcb_handle *h, int nDir, const float *dirCos) {
       FAIL(h, "specifyParameters: intensityMus can't be 0 (directly sideways)");
   h->P.nDir = nDir;
   for (int i = 0; i < 3 * nDir; ++i) h->P.viewDir[i] = dirCos[i];
+  for (int i = 0; i < nDir; ++i) h->P.viewNorm[i] = 1.0f / (4.0f * 3.14159265358979312f * std::fabs(dirCos[3 * i + 2]));
   return 0;
 }
 

@@ -62,9 +62,11 @@ struct DevDomain {
   // ---- tables ----
   const float *inv[MCB_MAX_COMP];  int invS[MCB_MAX_COMP];  int invE[MCB_MAX_COMP], fwdE[MCB_MAX_COMP];   // steps, entries
   const float *fwd[MCB_MAX_COMP];  const float *fwdOrig[MCB_MAX_COMP];  int fwdS[MCB_MAX_COMP];
+  float fwdInvDTheta[MCB_MAX_COMP];           // (nS - 1) / pi: the forward tables are on equal angle steps (OPT:1912-1913)
   // ---- views ----
   int nDir;
   float viewDir[3 * MCB_MAX_DIR];
+  float viewNorm[MCB_MAX_DIR];                // 1 / (4 pi |mu_view|), INT:1696, 1726
   // ---- options ----
   mcb_options opt;
   // ---- source ----

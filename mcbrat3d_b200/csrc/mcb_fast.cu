@@ -420,26 +420,25 @@ __device__ void le_run(const DevDomain &P, const Grid &G, const Tally &T, uint32
         if (component == 0) {
           npf = 1.0f / PI32;                                                       // INT:1694
         } else if (component < 0) {
-          npf = 1.0f / (4.0f * PI32 * fabsf(vz));                                  // INT:1696
+          npf = P.viewNorm[dir];                                                   // INT:1696
         } else {
           float proj = sle[LE_DX * 32 + s] * vx + sle[LE_DY * 32 + s] * vy + sle[LE_DZ * 32 + s] * vz;   // INT:1704-1706
           proj = fminf(fmaxf(proj, -1.0f), 1.0f);
-          const float ang = acosf(proj);
           const int c = component - 1;
           const int pidx = (int)((uint32_t)comps >> 16);                           // phase-function entry of the event's cell
           const float *tab = ((P.opt.useHybridPhaseFunsForIntenCalcs && order <= P.opt.numOrdersOrigPhaseFunIntenCalcs)
                                   ? P.fwdOrig[c] : P.fwd[c]) + (size_t)MCB_CHECK_INDEX(P, pidx - 1, P.fwdE[c]) * P.fwdS[c];
-          const int nS = P.fwdS[c];                                                // INT:1855-1870
-          const float dTheta = PI32 / (float)(nS - 1);
-          const int ai = (int)(ang / dTheta) + 1;
+          const int nS = P.fwdS[c];                                                // INT:1855-1870: linear in the angle
+          const float pos = acosf(proj) * P.fwdInvDTheta[c];                       // angle / dTheta
+          const int ai = (int)pos + 1;
           float val;
           if (ai < nS) {
-            const float wt = 1.0f - (ang - (float)(ai - 1) * dTheta) / dTheta;
+            const float wt = 1.0f - (pos - (float)(ai - 1));
             val = wt * __ldg(&tab[MCB_CHECK_INDEX(P, ai - 1, nS)]) + (1.0f - wt) * __ldg(&tab[MCB_CHECK_INDEX(P, ai, nS)]);
           } else {
             val = __ldg(&tab[nS - 1]);
           }
-          npf = val / (4.0f * PI32 * fabsf(vz));                                   // INT:1726
+          npf = val * P.viewNorm[dir];                                             // INT:1726
         }
         r.ox = sle[LE_PX * 32 + s]; r.oy = sle[LE_PY * 32 + s]; r.oz = sle[LE_PZ * 32 + s];
         r.dx = vx; r.dy = vy; r.dz = vz;
