@@ -23,6 +23,7 @@ void mcb_launch_pack_field(const DevDomain &P, int brick, float *ext, uint32_t *
                            int numSMs, cudaStream_t stream);
 void mcb_launch_pack_records(const DevDomain &P, uint32_t *rec, int *flags, int numSMs, cudaStream_t stream);
 bool mcb_fast_reads_bricks(const DevDomain &P);
+void mcb_launch_gather_column_cdf(const double *voxelCDF, int nx, int ny, int nz, double *colCDF, int numSMs, cudaStream_t stream);
 void mcb_launch_normalise(const DevDomain &P, float numPhotons, float *out, int numSMs, cudaStream_t stream);
 long long mcb_emission_tiles(long long cells);
 void mcb_launch_emission_cdf(const DevDomain &P, const double *temps, double a, double b, double lambda5, void *scratch,
@@ -66,7 +67,7 @@ struct mcb_handle {
   void *dExtMask = nullptr, *dExtMaskBrick = nullptr, *dLayerExt = nullptr;     // occupancy bitmap of fields too large for L2
   void *dInv[MCB_MAX_COMP] = {nullptr}, *dFwd[MCB_MAX_COMP] = {nullptr}, *dFwdOrig[MCB_MAX_COMP] = {nullptr};
   int invE[MCB_MAX_COMP] = {0}, fwdE[MCB_MAX_COMP] = {0};
-  void *dVoxelCDF = nullptr, *dTemps = nullptr, *dScratch = nullptr, *dResults = nullptr;
+  void *dColCDF = nullptr, *dVoxelCDF = nullptr, *dTemps = nullptr, *dScratch = nullptr, *dResults = nullptr;
   int *dFlags = nullptr;
   void *dMassConc = nullptr, *dReff = nullptr, *dNumConc = nullptr, *dAsmTables = nullptr;   // physical state (commonDomain)
   int nPhys = 0; bool havePhysical = false, haveNumConc = false;
@@ -168,7 +169,7 @@ int mcb_destroy(mcb_handle *h) {
                    h->dExt32, h->dRec, h->dVoxelCDF, h->dTally, h->dCounters,
                    h->dTemps, h->dScratch, h->dResults, (void *)h->dFlags, h->dStats, h->dStatsOut,
                    h->dMassConc, h->dReff, h->dNumConc, h->dAsmTables, h->dExtMask, h->dLayerExt,
-                   h->dExtBrick, h->dExtMaskBrick};
+                   h->dExtBrick, h->dExtMaskBrick, h->dColCDF};
   for (void *p : slots) if (p) cudaFree(p);
   for (int c = 0; c < MCB_MAX_COMP; ++c) {
     if (h->dInv[c]) cudaFree(h->dInv[c]);
@@ -271,6 +272,17 @@ int mcb_set_grid(mcb_handle *h, int nx, int ny, int nz,
 }
 
 static int finish_optics(mcb_handle *h, int nc, double albedo, bool zeroFlags = true);
+
+// the thermal source's CDF is in HBM: derive the compact column weights and publish the pointers
+static int finish_thermal_source(mcb_handle *h, double fracAtmsPower) {
+  DevDomain &P = h->P;
+  if (reserve(h, &h->dColCDF, sizeof(double) * (size_t)P.ny * P.nz)) return 1;
+  mcb_launch_gather_column_cdf((const double *)h->dVoxelCDF, P.nx, P.ny, P.nz, (double *)h->dColCDF, h->numSMs, h->stream);
+  CK(h, cudaGetLastError());
+  P.source = 1; P.fracAtmsPower = fracAtmsPower;
+  P.voxelCDF = (const double *)h->dVoxelCDF; P.colCDF = (const double *)h->dColCDF;
+  return 0;
+}
 
 static int pack_field(mcb_handle *h, bool brick) {
   DevDomain &P = h->P;
@@ -598,7 +610,7 @@ int mcb_set_thermal_source(mcb_handle *h, double fracAtmsPower, const double *vo
   if (!voxelCDF) FAIL(h, "mcb_set_thermal_source: null CDF");
   const size_t cells = (size_t)h->P.nx * h->P.ny * h->P.nz;
   if (stage(h, &h->dVoxelCDF, voxelCDF, sizeof(double) * cells)) return 1;
-  h->P.source = 1; h->P.fracAtmsPower = fracAtmsPower; h->P.voxelCDF = (const double *)h->dVoxelCDF;
+  if (finish_thermal_source(h, fracAtmsPower)) return 1;
   h->haveSource = true;
   return 0;
 }
@@ -656,7 +668,7 @@ int mcb_build_thermal_source(mcb_handle *h, const double *temps, double lambda_u
     FAIL(h, "emission_weightingNEW: Neither surface nor atmosphere will emitt photons since total power is 0. Not a valid solution");
   if (fracAtmsPowerOut) *fracAtmsPowerOut = frac;
   if (totalFluxOut) *totalFluxOut = (atmsPower + sfcPower) / (areaX * areaY * (1000.0 * 1000.0));
-  h->P.source = 1; h->P.fracAtmsPower = frac; h->P.voxelCDF = (const double *)h->dVoxelCDF;
+  if (finish_thermal_source(h, frac)) return 1;
   h->haveSource = true;
   return 0;
 }

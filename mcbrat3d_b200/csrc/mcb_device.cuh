@@ -75,6 +75,8 @@ struct DevDomain {
   float solarDir[3];                          // their direction cosines (INT:1876-1894)
   double fracAtmsPower;
   const double *voxelCDF;                     // (nx,ny,nz)
+  const double *colCDF;                       // (ny,nz): voxelCDF(nx,:,:), the column weights of EMI:56 gathered into one
+                                              // small array (the level weights are its rows' last entries)
   // ---- tallies: packed f64 buffer ----
   double *tally;
   long long offFluxUp, offFluxDown, offFluxAbs, offVolAbs, offInt, offIntByComp, offExcess, offPhotons;

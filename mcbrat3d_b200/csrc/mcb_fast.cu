@@ -11,6 +11,11 @@
 //     packed f32 extinction field carries a ghost shell (periodic replicas in x and y, empty cells
 //     above and below), so the per-cell step has no wrap or exit tests at all -- those run once per
 //     burst;
+//   * the field is stored twice (mcb_device.cuh): as 2x2x2-cell bricks, one brick per 32-byte sector, for the
+//     flux kernels (the measured limiter is the SM's L1TEX->XBAR request port, i.e. L1 misses: with bricks half
+//     of a ray's steps stay inside the sector, whatever the axis), and x-fastest for local estimation, narrow
+//     and irregular grids; fields too large for L2 add an occupancy bitmap so that clear-sky cells are never
+//     gathered from HBM; everything a scattering event reads sits in one per-cell record (one gather per event);
 //   * warp-level regrouping: lanes march in bursts and park when they reach an event (scatter /
 //     surface / exit); once enough lanes are parked ONE event phase runs for all of them: tallies,
 //     absorption, roulette, rebirth of finished lanes, one Philox block, the new direction, one
@@ -678,10 +683,9 @@ batch_kernel(const __grid_constant__ DevDomain P, long long nPhotons, uint64_t s
             z01 = 0.0f;
           } else {                                                             // atmospheric emission
             const float q = u.y;
-            const double *levelBase = P.voxelCDF + (size_t)(P.nx - 1) + (size_t)P.nx * (size_t)(P.ny - 1);
-            const int ik = cdf_search(levelBase, P.nz, (long long)cols, q);
-            const double *colBase = P.voxelCDF + (size_t)(P.nx - 1) + (size_t)cols * (size_t)(ik - 1);
-            const int ij = cdf_search(colBase, P.ny, P.nx, q);
+            // level and column from the compact column weights colCDF(ny,nz) = voxelCDF(nx,:,:) (EMI:56-57)
+            const int ik = cdf_search(P.colCDF + (P.ny - 1), P.nz, (long long)P.ny, q);
+            const int ij = cdf_search(P.colCDF + (size_t)P.ny * (size_t)(ik - 1), P.ny, 1, q);
             const double *voxBase = P.voxelCDF + (size_t)P.nx * ((size_t)(ij - 1) + (size_t)P.ny * (size_t)(ik - 1));
             const int ii = cdf_search(voxBase, P.nx, 1, q);
             // uniform inside the chosen cell, nudged off its faces (ILL:500-505)

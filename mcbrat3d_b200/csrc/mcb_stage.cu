@@ -112,6 +112,13 @@ __global__ void pack_components_kernel(const double *__restrict__ cumExt, const 
   if (bad) atomicOr(flags, bad);
 }
 
+// colWeights = voxelWeights(nx,:,:) (EMI:56-57) gathered into a compact (ny,nz) array: the level and column searches
+// of a thermal birth then probe a few hundred kilobytes instead of striding through the whole CDF
+__global__ void gather_column_cdf_kernel(const double *__restrict__ voxelCDF, int nx, long long rows, double *__restrict__ colCDF) {
+  for (long long r = blockIdx.x * (long long)blockDim.x + threadIdx.x; r < rows; r += (long long)gridDim.x * blockDim.x)
+    colCDF[r] = voxelCDF[(long long)(nx - 1) + (long long)nx * r];
+}
+
 // ---------------------------------------------------------------------------------------------
 // per-wavelength optical-property assembly: read_SSPTable's inner loops (OPT:204-299) followed by
 // getOpticalPropertiesByComponent (OPT:1022-1061), one thread per cell.  The physical state (mass
@@ -600,6 +607,11 @@ void mcb_launch_pack_field(const DevDomain &P, int brick, float *ext, uint32_t *
     mcbstage::occupancy_mask_kernel<<<stream_grid(F.padded, 256, numSMs), 256, 0, stream>>>(ext, layerExt, F.padded,
                                                                                             F.nxp * F.nyp, mask, brick);
   }
+}
+
+void mcb_launch_gather_column_cdf(const double *voxelCDF, int nx, int ny, int nz, double *colCDF, int numSMs, cudaStream_t stream) {
+  const long long rows = (long long)ny * nz;
+  mcbstage::gather_column_cdf_kernel<<<stream_grid(rows, 256, numSMs), 256, 0, stream>>>(voxelCDF, nx, rows, colCDF);
 }
 
 // per-cell event records + the argument checks of the per-component arrays
