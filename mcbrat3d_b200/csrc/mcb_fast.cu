@@ -27,6 +27,7 @@
 // Results agree with the reference arithmetic statistically (north-star criterion (b));
 // bit-level trace parity is the job of mcb_reference.cu.
 #include "mcb_device.cuh"
+#include <cstdio>
 
 namespace mcbfast {
 
@@ -366,12 +367,17 @@ struct Counts { unsigned crossings, scatters, leRays, leCrossings; };
 // lane advances its current ray by one burst per iteration, so the marcher code stays convergent while rays of
 // very different lengths are in flight; a lane that finishes a ray tallies it and takes the next task.  A lane that
 // finds the queue empty goes back to its OWN photon leg (if it has one under way) and keeps marching it while the
-// others finish their rays, so the tail of the queue does not idle the warp (ncu, C3 + 5 views: 12 of 32 lanes were
-// active in the marcher before); a photon that reaches an event in here simply parks until the next event phase.
+// others finish their rays; a photon that reaches an event in here simply parks until the next event phase.
+// Rays of very different lengths (a few cells inside the cloud, a hundred through clear sky to the top) leave a long
+// tail: measured on C3 + 5 views, 74 % of the loop's iterations ran with the queue already empty and 7 lanes busy.
+// So once the queue is empty and at most `carryThreshold` rays are still in flight, those rays are PARKED in shared
+// memory (16 words) and the round ends; their lanes resume them at the start of the next round, next to the new
+// requests, and a last round at the end of the kernel drains what is left.
 #ifndef MCB_LE_BURST
 #define MCB_LE_BURST 8          // cells per burst of a local-estimate ray (C3 + 5 views: 4 -> 5.9e7, 8 -> 6.4e7 photons/s)
 #endif
 #define LE_WORDS 13
+#define LE_CARRY_WORDS 16      // a view ray parked between two rounds of the queue (see le_run)
 enum { LE_PX = 0, LE_PY, LE_PZ, LE_DX, LE_DY, LE_DZ, LE_W, LE_IXY, LE_IZO, LE_COMP, LE_C0, LE_C1, LE_BLK };
 enum { PH_IDLE = 0, PH_PLAIN, PH_E13, PH_E14A, PH_E14B, PH_PHOTON };
 
@@ -393,9 +399,10 @@ __device__ __forceinline__ void le_post(float *sle, int lane, const DevDomain &P
 template <bool REG, bool WIDE, bool MASK>
 __device__ void le_run(const DevDomain &P, const Grid &G, const Tally &T, uint32_t k0, uint32_t k1, unsigned posted,
                        float *sle, unsigned *queue, int lane, Counts &cnt, Ray &photonRay, float &photonExt,
-                       float photonTau, int &photonState) {
+                       float photonTau, int &photonState, int carryThreshold) {
   const int nDir = P.nDir;
   const int nTasks = __popc(posted) * nDir;
+  float *carry = sle + LE_WORDS * 32 + 64;               // LE_CARRY_WORDS x 32, word-major like the request slots
   const float invDir = 1.0f / (float)nDir;
   if (lane == 0) *queue = 0u;
   if ((posted >> lane) & 1u) queue[1 + __popc(posted & ((1u << lane) - 1u))] = (unsigned)lane;   // r-th request -> its lane
@@ -406,6 +413,22 @@ __device__ void le_run(const DevDomain &P, const Grid &G, const Tally &T, uint32
   float ext = 0.0f, tgt = FLT_MAX, w = 0.0f, npf = 0.0f, tauFree = 0.0f, uTest = 0.0f;
   int phase = PH_IDLE, dir = 0, comps = 0;
   bool done = false, mine = false;                       // mine: r holds this lane's own photon leg
+  {                                                      // resume the ray this lane parked in the previous round
+    const int packed = __float_as_int(carry[15 * 32 + lane]);
+    if (packed != 0) {
+      carry[15 * 32 + lane] = 0.0f;
+      phase = (packed >> 16) & 0xf; dir = (packed >> 20) & 0xff; r.iz = packed & 0xffff;
+      r.ox = carry[0 * 32 + lane]; r.oy = carry[1 * 32 + lane]; r.oz = carry[2 * 32 + lane];
+      r.t = carry[3 * 32 + lane]; r.tx = carry[4 * 32 + lane]; r.ty = carry[5 * 32 + lane]; r.tz = carry[6 * 32 + lane];
+      ext = carry[7 * 32 + lane]; tgt = carry[8 * 32 + lane]; w = carry[9 * 32 + lane]; npf = carry[10 * 32 + lane];
+      tauFree = carry[11 * 32 + lane]; uTest = carry[12 * 32 + lane];
+      const int ixy = __float_as_int(carry[13 * 32 + lane]);
+      r.ix = ixy & 0xffff; r.iy = ixy >> 16;
+      comps = __float_as_int(carry[14 * 32 + lane]);
+      r.dx = P.viewDir[3 * dir]; r.dy = P.viewDir[3 * dir + 1]; r.dz = P.viewDir[3 * dir + 2];
+      r.rx = safe_rcp(r.dx); r.ry = safe_rcp(r.dy); r.rz = safe_rcp(r.dz);
+    }
+  }
   for (;;) {
     if (phase == PH_IDLE && !done) {                     // take the next (request, direction) task
       const int t = (int)atomicAdd(queue, 1u);
@@ -465,7 +488,20 @@ __device__ void le_run(const DevDomain &P, const Grid &G, const Tally &T, uint32
         }
       }
     }
-    if (__all_sync(FULL, done)) break;
+    {                                                    // queue empty and few rays left: park them, end the round
+      const unsigned flying = __ballot_sync(FULL, phase != PH_IDLE && phase != PH_PHOTON);
+      if ((nTasks == 0 || __any_sync(FULL, done)) && __popc(flying) <= carryThreshold) break;
+    }
+#ifdef MCB_LE_STATS
+    {
+      const unsigned act = __ballot_sync(FULL, phase != PH_IDLE && phase != PH_PHOTON), ph = __ballot_sync(FULL, phase == PH_PHOTON);
+      if (lane == 0) {
+        atomicAdd(&P.counters[16], 1ull); atomicAdd(&P.counters[17], (unsigned long long)__popc(act));
+        atomicAdd(&P.counters[18], (unsigned long long)__popc(ph));
+        if (*queue >= (unsigned)nTasks) { atomicAdd(&P.counters[19], 1ull); atomicAdd(&P.counters[20], (unsigned long long)__popc(act)); }
+      }
+    }
+#endif
     if (phase != PH_IDLE) {
       unsigned crossed = 0u;
       const int ev = march_burst<REG, WIDE, MCB_LE_BURST, MASK, false>(r, P, G, ext, tgt, crossed);
@@ -508,13 +544,22 @@ __device__ void le_run(const DevDomain &P, const Grid &G, const Tally &T, uint32
     }
   }
   if (mine) { photonRay = r; photonExt = ext; }
+  else if (phase != PH_IDLE) {                           // park the unfinished view ray
+    carry[0 * 32 + lane] = r.ox; carry[1 * 32 + lane] = r.oy; carry[2 * 32 + lane] = r.oz;
+    carry[3 * 32 + lane] = r.t; carry[4 * 32 + lane] = r.tx; carry[5 * 32 + lane] = r.ty; carry[6 * 32 + lane] = r.tz;
+    carry[7 * 32 + lane] = ext; carry[8 * 32 + lane] = tgt; carry[9 * 32 + lane] = w; carry[10 * 32 + lane] = npf;
+    carry[11 * 32 + lane] = tauFree; carry[12 * 32 + lane] = uTest;
+    carry[13 * 32 + lane] = __int_as_float(r.ix | (r.iy << 16));
+    carry[14 * 32 + lane] = __int_as_float(comps);
+    carry[15 * 32 + lane] = __int_as_float(r.iz | (phase << 16) | (dir << 20));
+  }
   __syncwarp();
 }
 
 template <int THREADS, bool REG, bool WIDE, int MINBLOCKS, int BURST, bool LE, bool MASK, bool BRICK>
 __global__ void __launch_bounds__(THREADS, MINBLOCKS)
 batch_kernel(const __grid_constant__ DevDomain P, long long nPhotons, uint64_t seed, uint64_t firstPhotonId,
-             unsigned long long *workCounter, int parkThreshold, const SmemPlan plan) {
+             unsigned long long *workCounter, int parkThreshold, int leCarry, const SmemPlan plan) {
   extern __shared__ float smem[];
   __shared__ unsigned sCnt[4];            // rare events: surface hits, surface kills, roulette kills
   const int cols = P.nx * P.ny, cells = cols * P.nz;
@@ -559,8 +604,10 @@ batch_kernel(const __grid_constant__ DevDomain P, long long nPhotons, uint64_t s
   float *sle = nullptr;
   unsigned *leQueue = nullptr;
   if (LE) {
-    sle = smem + plan.leOff + (threadIdx.x >> 5) * (LE_WORDS * 32 + 64);
+    sle = smem + plan.leOff + (threadIdx.x >> 5) * (LE_WORDS * 32 + 64 + LE_CARRY_WORDS * 32);
     leQueue = (unsigned *)(sle + LE_WORDS * 32);
+    sle[LE_WORDS * 32 + 64 + 15 * 32 + lane] = 0.0f;      // no parked view ray
+    __syncwarp();
   }
   const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
 
@@ -640,7 +687,7 @@ batch_kernel(const __grid_constant__ DevDomain P, long long nPhotons, uint64_t s
     }
     if (LE && P.nDir > 0 && P.opt.LW_flag > 0.0f) {      // thermal runs: births post too (below), one slot per lane
       const unsigned pm = __ballot_sync(FULL, posted);
-      if (pm) le_run<REG, WIDE, MASK>(P, G, T, k0, k1, pm, sle, leQueue, lane, cnt, r, ext, tau, state);
+      if (pm) le_run<REG, WIDE, MASK>(P, G, T, k0, k1, pm, sle, leQueue, lane, cnt, r, ext, tau, state, leCarry);
       posted = false;
     }
     // ---- finished lanes take the next photons: one atomic per warp (getNextPhoton, ILL:561-590) ----
@@ -662,7 +709,12 @@ batch_kernel(const __grid_constant__ DevDomain P, long long nPhotons, uint64_t s
         }
       }
     }
-    if (__all_sync(FULL, state == ST_DONE)) break;
+    if (__all_sync(FULL, state == ST_DONE)) {
+      // last round of the view-ray queue: the requests of the final events and every parked ray, to the end
+      if (LE && P.nDir > 0)
+        le_run<REG, WIDE, MASK>(P, G, T, k0, k1, __ballot_sync(FULL, posted), sle, leQueue, lane, cnt, r, ext, tau, state, 0);
+      break;
+    }
     // ---- one Philox block for every parked lane: (angle | position, azimuth | position, next optical depth, next pick) ----
     if (state != ST_MARCH && state != ST_DONE) {
       const float4 u = rng.block(k0, k1);
@@ -767,7 +819,7 @@ batch_kernel(const __grid_constant__ DevDomain P, long long nPhotons, uint64_t s
     // next leg by now, so lanes that run out of requests march their own photon meanwhile
     if (LE && P.nDir > 0) {
       const unsigned pm = __ballot_sync(FULL, posted);
-      if (pm) le_run<REG, WIDE, MASK>(P, G, T, k0, k1, pm, sle, leQueue, lane, cnt, r, ext, tau, state);
+      if (pm) le_run<REG, WIDE, MASK>(P, G, T, k0, k1, pm, sle, leQueue, lane, cnt, r, ext, tau, state, leCarry);
     }
 
     // =========================== march phase: bursts until enough lanes are parked ===========================
@@ -813,6 +865,11 @@ batch_kernel(const __grid_constant__ DevDomain P, long long nPhotons, uint64_t s
       const float v = T.sInt[i];
       if (v != 0.0f) atomicAdd(&P.tally[P.offInt + i], (double)v);
     }
+#ifdef MCB_LE_STATS
+  if (blockIdx.x == 0 && threadIdx.x == 0)
+    printf("LE_STATS (previous launches) iterations %llu le-lanes %llu photon-lanes %llu tail-iterations %llu tail-le-lanes %llu\n",
+           P.counters[16], P.counters[17], P.counters[18], P.counters[19], P.counters[20]);
+#endif
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     atomicAdd(&P.tally[P.offPhotons], (double)nPhotons);
     atomicAdd(&P.counters[CNT_PHOTONS], (unsigned long long)nPhotons);
@@ -845,7 +902,7 @@ static void launch(const DevDomain &P, long long nPhotons, uint64_t seed, uint64
   if (3 * cols <= 3 * 1024 && off + 3 * cols <= budgetFloats) { plan.fluxOff = off; off += 3 * cols; }
   if (cells <= 8192 && off + cells <= budgetFloats) { plan.volOff = off; off += cells; }
   if (P.nDir > 0 && cols * P.nDir <= 2048 && off + cols * P.nDir <= budgetFloats) { plan.intOff = off; off += cols * P.nDir; }
-  if (LE) { plan.leOff = off; off += (THREADS / 32) * (LE_WORDS * 32 + 64); }
+  if (LE) { plan.leOff = off; off += (THREADS / 32) * (LE_WORDS * 32 + 64 + LE_CARRY_WORDS * 32); }
   plan.totalFloats = off;
   const size_t smem = sizeof(float) * (size_t)off;
   cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
@@ -861,7 +918,11 @@ static void launch(const DevDomain &P, long long nPhotons, uint64_t seed, uint64
   if (parkEnv == -2) { const char *e = getenv("MCB_PARK_THRESHOLD"); parkEnv = e ? atoi(e) : -1; }
   int park = parkEnv > 0 ? parkEnv : (LE ? 24 : 16);
   if (park > 32) park = 32;
-  kernel<<<blocks, THREADS, smem, stream>>>(P, nPhotons, seed, firstPhotonId, workCounter, park, plan);
+  // view rays still in flight when a round of the queue ends with no tasks left: at most this many are parked
+  static int carryEnv = -2;
+  if (carryEnv == -2) { const char *e = getenv("MCB_LE_CARRY"); carryEnv = e ? atoi(e) : -1; }
+  const int carry = carryEnv >= 0 ? carryEnv : 12;
+  kernel<<<blocks, THREADS, smem, stream>>>(P, nPhotons, seed, firstPhotonId, workCounter, park, carry, plan);
 }
 
 // which layout of the extinction field the dispatcher below reads (the API packs that one)

@@ -255,29 +255,41 @@ def test_plane_parallel_fluxes_match_adding_doubling(tau, omega, g, mu0, albedo,
     assert (np.abs(m - want) < 4.0 * e + 2e-4).all(), (m, want, e)
 
 
-def test_result_independent_of_batch_split():
+@pytest.mark.parametrize("views", [False, True], ids=["flux", "le"])
+def test_result_independent_of_batch_split(views):
     """Counter-based RNG keyed by the global photon id: one batch of N equals two accumulated
     batches of N/2 (same photons, same histories) -- the property that makes multi-GPU sharding
-    decomposition-independent (the reference's results depend on batch size and rank count)."""
-    dom, case = domains.step_cloud(ssa=0.99, solarMu=0.5)
+    decomposition-independent (the reference's results depend on batch size and rank count).
+    With views it also proves that every local-estimate request is served exactly once however the
+    photons are spread over warps and launches: the view rays (counted) and the radiances must be the
+    same -- requests of a warp's last events and rays parked between two rounds of the queue included."""
+    dom, case = domains.step_cloud(ssa=0.99, solarMu=0.5) if not views else domains.landsat_cloud(ssa=0.99, nxy=32)
     g = new_Integrator(dom)
     try:
+        if views:
+            specifyParameters(g, intensityMus=[1.0, 0.5, 0.5], intensityPhis=[0.0, 0.0, 180.0], computeIntensity=True,
+                              useRussianRouletteForIntensity=True, zetaMin=0.3, minForwardTableSize=10001)
         specifyParameters(g, minInverseTableSize=10001)
         rs = new_RandomNumberSequence([10, 1, 0])
         n = 200000
+        want = dict(fluxUp=True, fluxDown=True, volumeAbsorption=True, **(dict(intensity=True, intensityByComponent=True) if views else {}))
         ps = new_PhotonStream(0.5, 0.0, n, rs)
         computeRadiativeTransfer(g, dom, rs, ps, n)
-        whole = reportResults(g, fluxUp=True, fluxDown=True, volumeAbsorption=True)
+        whole = reportResults(g, **want)
         cw = getCounters(g)
         done = C.c_int64(0)
         lib, h = g._lib, g.handle
-        assert lib.mcb_run_batch(h, n // 2, C.c_uint64(rs.seed), C.c_uint64(0), C.byref(done)) == 0
-        assert lib.mcb_accumulate_batch(h, n - n // 2, C.c_uint64(rs.seed), C.c_uint64(n // 2), C.byref(done)) == 0
-        split = reportResults(g, fluxUp=True, fluxDown=True, volumeAbsorption=True)
+        parts = [0, n // 2, n] if not views else [0, 1000, 1037, n // 3, n - 5, n]     # ragged launches, tiny ones included
+        for i in range(len(parts) - 1):
+            run = lib.mcb_run_batch if i == 0 else lib.mcb_accumulate_batch
+            assert run(h, parts[i + 1] - parts[i], C.c_uint64(rs.seed), C.c_uint64(parts[i]), C.byref(done)) == 0
+        split = reportResults(g, **want)
         cs = getCounters(g)
         assert cs == cw
+        if views:
+            assert cw["leRays"] == 3 * cw["scatters"], cw          # one ray per (scattering event, direction); albedo 0: no surface requests
         for k in whole:
-            np.testing.assert_allclose(split[k], whole[k], rtol=1e-5, atol=1e-7)
+            np.testing.assert_allclose(split[k], whole[k], rtol=2e-5, atol=1e-7, err_msg=k)
     finally:
         finalize_Integrator(g)
 
