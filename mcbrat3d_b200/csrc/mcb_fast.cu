@@ -51,6 +51,7 @@ struct SmemPlan {
   int volOff;              // float[cells]   privatised volumeAbsorption           (-1: global atomics)
   int intOff;              // float[cols*nDir] privatised intensity                (-1: global atomics)
   int leOff;               // per warp: LE_WORDS x 32 request slots + 64 words of queue state: task counter, rank -> lane map
+  int leStride;            // words per warp: the above (+ LE_CARRY_WORDS x 32 for parked view rays when leCarry >= 0)
   int totalFloats;
 };
 
@@ -376,6 +377,9 @@ struct Counts { unsigned crossings, scatters, leRays, leCrossings; };
 #ifndef MCB_LE_BURST
 #define MCB_LE_BURST 8          // cells per burst of a local-estimate ray (C3 + 5 views: 4 -> 5.9e7, 8 -> 6.4e7 photons/s)
 #endif
+#ifndef MCB_LE_OCC
+#define MCB_LE_OCC 5             // CTAs per SM of the local-estimation kernels: 96 registers, no spills (6: 80 registers, 314 B of spills, 8 % slower)
+#endif
 #define LE_WORDS 13
 #define LE_CARRY_WORDS 16      // a view ray parked between two rounds of the queue (see le_run)
 enum { LE_PX = 0, LE_PY, LE_PZ, LE_DX, LE_DY, LE_DZ, LE_W, LE_IXY, LE_IZO, LE_COMP, LE_C0, LE_C1, LE_BLK };
@@ -402,7 +406,7 @@ __device__ void le_run(const DevDomain &P, const Grid &G, const Tally &T, uint32
                        float photonTau, int &photonState, int carryThreshold) {
   const int nDir = P.nDir;
   const int nTasks = __popc(posted) * nDir;
-  float *carry = sle + LE_WORDS * 32 + 64;               // LE_CARRY_WORDS x 32, word-major like the request slots
+  float *carry = carryThreshold >= 0 ? sle + LE_WORDS * 32 + 64 : nullptr;   // LE_CARRY_WORDS x 32, word-major like the slots
   const float invDir = 1.0f / (float)nDir;
   if (lane == 0) *queue = 0u;
   if ((posted >> lane) & 1u) queue[1 + __popc(posted & ((1u << lane) - 1u))] = (unsigned)lane;   // r-th request -> its lane
@@ -413,7 +417,7 @@ __device__ void le_run(const DevDomain &P, const Grid &G, const Tally &T, uint32
   float ext = 0.0f, tgt = FLT_MAX, w = 0.0f, npf = 0.0f, tauFree = 0.0f, uTest = 0.0f;
   int phase = PH_IDLE, dir = 0, comps = 0;
   bool done = false, mine = false;                       // mine: r holds this lane's own photon leg
-  {                                                      // resume the ray this lane parked in the previous round
+  if (carry) {                                           // resume the ray this lane parked in the previous round
     const int packed = __float_as_int(carry[15 * 32 + lane]);
     if (packed != 0) {
       carry[15 * 32 + lane] = 0.0f;
@@ -490,7 +494,7 @@ __device__ void le_run(const DevDomain &P, const Grid &G, const Tally &T, uint32
     }
     {                                                    // queue empty and few rays left: park them, end the round
       const unsigned flying = __ballot_sync(FULL, phase != PH_IDLE && phase != PH_PHOTON);
-      if ((nTasks == 0 || __any_sync(FULL, done)) && __popc(flying) <= carryThreshold) break;
+      if ((nTasks == 0 || __any_sync(FULL, done)) && __popc(flying) <= max(carryThreshold, 0)) break;
     }
 #ifdef MCB_LE_STATS
     {
@@ -544,7 +548,7 @@ __device__ void le_run(const DevDomain &P, const Grid &G, const Tally &T, uint32
     }
   }
   if (mine) { photonRay = r; photonExt = ext; }
-  else if (phase != PH_IDLE) {                           // park the unfinished view ray
+  else if (carry && phase != PH_IDLE) {                  // park the unfinished view ray
     carry[0 * 32 + lane] = r.ox; carry[1 * 32 + lane] = r.oy; carry[2 * 32 + lane] = r.oz;
     carry[3 * 32 + lane] = r.t; carry[4 * 32 + lane] = r.tx; carry[5 * 32 + lane] = r.ty; carry[6 * 32 + lane] = r.tz;
     carry[7 * 32 + lane] = ext; carry[8 * 32 + lane] = tgt; carry[9 * 32 + lane] = w; carry[10 * 32 + lane] = npf;
@@ -604,9 +608,9 @@ batch_kernel(const __grid_constant__ DevDomain P, long long nPhotons, uint64_t s
   float *sle = nullptr;
   unsigned *leQueue = nullptr;
   if (LE) {
-    sle = smem + plan.leOff + (threadIdx.x >> 5) * (LE_WORDS * 32 + 64 + LE_CARRY_WORDS * 32);
+    sle = smem + plan.leOff + (threadIdx.x >> 5) * plan.leStride;
     leQueue = (unsigned *)(sle + LE_WORDS * 32);
-    sle[LE_WORDS * 32 + 64 + 15 * 32 + lane] = 0.0f;      // no parked view ray
+    if (leCarry >= 0) sle[LE_WORDS * 32 + 64 + 15 * 32 + lane] = 0.0f;      // no parked view ray
     __syncwarp();
   }
   const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
@@ -712,7 +716,7 @@ batch_kernel(const __grid_constant__ DevDomain P, long long nPhotons, uint64_t s
     if (__all_sync(FULL, state == ST_DONE)) {
       // last round of the view-ray queue: the requests of the final events and every parked ray, to the end
       if (LE && P.nDir > 0)
-        le_run<REG, WIDE, MASK>(P, G, T, k0, k1, __ballot_sync(FULL, posted), sle, leQueue, lane, cnt, r, ext, tau, state, 0);
+        le_run<REG, WIDE, MASK>(P, G, T, k0, k1, __ballot_sync(FULL, posted), sle, leQueue, lane, cnt, r, ext, tau, state, min(leCarry, 0));
       break;
     }
     // ---- one Philox block for every parked lane: (angle | position, azimuth | position, next optical depth, next pick) ----
@@ -895,14 +899,22 @@ static void launch(const DevDomain &P, long long nPhotons, uint64_t seed, uint64
   // atomic hot spot (homogeneous slabs, the 32-column step cloud); large grids spread their
   // atomics over many L2 lines and go straight to the f64 buffer.
   const int cols = P.nx * P.ny, cells = cols * P.nz;
-  mcbfast::SmemPlan plan{-1, -1, -1, -1, -1, 0};
+  mcbfast::SmemPlan plan{-1, -1, -1, -1, -1, 0, 0};
   int off = 0;
   if (!REG) { plan.edgesOff = off; off += P.nx + P.ny + P.nz + 3 + 6 * MCB_GHOST; }
   const int budgetFloats = 9 * 1024;            // 36 KB per block keeps >= 6 blocks/SM resident
   if (3 * cols <= 3 * 1024 && off + 3 * cols <= budgetFloats) { plan.fluxOff = off; off += 3 * cols; }
   if (cells <= 8192 && off + cells <= budgetFloats) { plan.volOff = off; off += cells; }
   if (P.nDir > 0 && cols * P.nDir <= 2048 && off + cols * P.nDir <= budgetFloats) { plan.intOff = off; off += cols * P.nDir; }
-  if (LE) { plan.leOff = off; off += (THREADS / 32) * (LE_WORDS * 32 + 64 + LE_CARRY_WORDS * 32); }
+  // view rays still in flight when a round of the queue ends with no tasks left: at most `carry` of them are parked
+  // (le_run).  That pays when a ray can be much longer than a burst -- grids deeper than 64 layers; on shallow grids
+  // (the step cloud: 32 layers, 3.6 cells per ray) the 8 KB per block it takes away from L1 cost 10 %, so it is off (-1)
+  const char *ec = getenv("MCB_LE_CARRY");               // measurement knob: -1 off, n >= 0 threshold
+  const int carry = ec ? atoi(ec) : (P.nz > 64 ? 12 : -1);
+  if (LE) {
+    plan.leOff = off; plan.leStride = LE_WORDS * 32 + 64 + (carry >= 0 ? LE_CARRY_WORDS * 32 : 0);
+    off += (THREADS / 32) * plan.leStride;
+  }
   plan.totalFloats = off;
   const size_t smem = sizeof(float) * (size_t)off;
   cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
@@ -918,10 +930,6 @@ static void launch(const DevDomain &P, long long nPhotons, uint64_t seed, uint64
   if (parkEnv == -2) { const char *e = getenv("MCB_PARK_THRESHOLD"); parkEnv = e ? atoi(e) : -1; }
   int park = parkEnv > 0 ? parkEnv : (LE ? 24 : 16);
   if (park > 32) park = 32;
-  // view rays still in flight when a round of the queue ends with no tasks left: at most this many are parked
-  static int carryEnv = -2;
-  if (carryEnv == -2) { const char *e = getenv("MCB_LE_CARRY"); carryEnv = e ? atoi(e) : -1; }
-  const int carry = carryEnv >= 0 ? carryEnv : 12;
   kernel<<<blocks, THREADS, smem, stream>>>(P, nPhotons, seed, firstPhotonId, workCounter, park, carry, plan);
 }
 
@@ -949,8 +957,8 @@ void mcb_launch_fast_batch(const DevDomain &P, long long nPhotons, uint64_t seed
   const bool wide = P.nx >= MCB_GHOST && P.ny >= MCB_GHOST;      // no grid period shorter than the ghost shell
   const bool le = P.nDir > 0, mask = P.lin.mask != nullptr;
   if (P.xyRegular && P.zRegular) {
-    if (!wide) { if (le) MCB_GO(true, false, 6, true, false, false); else MCB_GO(true, false, 8, false, false, false); }
-    else if (le) { if (mask) MCB_GO(true, true, 6, true, true, false); else MCB_GO(true, true, 6, true, false, false); }
+    if (!wide) { if (le) MCB_GO(true, false, MCB_LE_OCC, true, false, false); else MCB_GO(true, false, 8, false, false, false); }
+    else if (le) { if (mask) MCB_GO(true, true, MCB_LE_OCC, true, true, false); else MCB_GO(true, true, MCB_LE_OCC, true, false, false); }
     else if (mask) {
       if (linEnv) MCB_GO(true, true, 6, false, true, false);
       else if (occEnv >= 8) MCB_GO(true, true, 8, false, true, true);
