@@ -99,7 +99,26 @@ def cpu_rate(dom, case, seconds, views=False):
     total, batches, _ = orc.run_workers(make, workers, nb * workers, batch,
                                         solarMu=case["solarMu"], solarAzimuth=case["solarAzimuth"])
     dt = time.perf_counter() - t0
+    # What the reference pays on top of the loop, per batch and per worker: computeRT copies totalExt, cumulativeExt,
+    # ssa and phaseFunctionIndex out of the domain (INT:434-443).  Timed here as W concurrent memcpys of the same
+    # arrays (NumPy releases the GIL in copy); the per-batch table rebuild (INT:280-285) is NOT charged.
+    import concurrent.futures as cf
+    arrays = [dom.totalExt, dom.cumulativeExt, dom.ssa, dom.phaseFunctionIndex]
+
+    def copies(_):
+        t = time.perf_counter()
+        for _ in range(3):
+            for a in arrays:
+                a.copy()
+        return (time.perf_counter() - t) / 3.0
+    with cf.ThreadPoolExecutor(workers) as ex:
+        copy_s = max(ex.map(copies, range(workers)))
+    as_shipped = total / (dt + nb * copy_s)
     return dict(value=total / dt, unit=UNIT, cores=workers, kind="port",
+                as_shipped=dict(value=as_shipped, per_batch_copy_ms=1e3 * copy_s,
+                                note="loop + the per-batch O(cells) array copies of INT:434-443 (%d MB per batch per "
+                                     "worker, all workers copying at once); table rebuild not charged"
+                                     % (sum(a.nbytes for a in arrays) >> 20)),
                 sample="%d photons = %d workers x %d batches x %d photons of the same workload, %.1f s wall; "
                        "photon loop only (the reference's per-batch table rebuild and O(cells) copies are not charged)"
                        % (total, workers, nb, batch, dt)), total, dt
