@@ -28,13 +28,18 @@ def _legendre_matrix(lmax, x):
     return P
 
 
-def slab_fluxes(tau, omega, chi, mu0, albedo=0.0, nStreams=64, thin=1.0e-5):
+def slab_fluxes(tau, omega, chi, mu0, albedo=0.0, nStreams=64, thin=1.0e-5, muOut=()):
     """(Fup at the top, Fdown at the surface incl. the direct beam, absorbed in the slab), per unit incident flux.
-    ``chi``: Legendre coefficients chi_l of the phase function, chi_0 = 1 (Henyey-Greenstein: g**l)."""
+    ``chi``: Legendre coefficients chi_l of the phase function, chi_0 = 1 (Henyey-Greenstein: g**l).
+    With ``muOut`` a fourth value is returned: the azimuthally averaged upward radiance at the top, per unit incident
+    flux and per steradian, at those zenith cosines (extra nodes of negligible weight: their flux share divided by
+    weight, cosine and 2 pi)."""
     chi = np.asarray(chi, dtype=np.float64)
     x, w = np.polynomial.legendre.leggauss(nStreams)
-    mu = np.concatenate([0.5 * (x + 1.0), [mu0]])
-    wt = np.concatenate([0.5 * w, [0.0]])
+    eps = 1.0e-9
+    muOut = np.asarray(muOut, dtype=np.float64).reshape(-1)
+    mu = np.concatenate([0.5 * (x + 1.0), muOut, [mu0]])
+    wt = np.concatenate([0.5 * w, np.full(muOut.size, eps), [0.0]])
     L = chi.size - 1
     Pl = _legendre_matrix(L, mu)
     fac = (2 * np.arange(L + 1) + 1) * chi
@@ -60,6 +65,9 @@ def slab_fluxes(tau, omega, chi, mu0, albedo=0.0, nStreams=64, thin=1.0e-5):
     down = np.linalg.solve(I - R @ Rs, T @ y0)                                 # flux reaching the surface, all orders
     up = R @ y0 + T @ (Rs @ down)
     fup, fdn = up.sum(), down.sum()
+    if muOut.size:
+        sl = slice(nStreams, nStreams + muOut.size)
+        return fup, fdn, 1.0 - fup - (1.0 - albedo) * fdn, up[sl] / (wt[sl] * mu[sl] * 2.0 * np.pi)
     return fup, fdn, 1.0 - fup - (1.0 - albedo) * fdn
 
 

@@ -255,6 +255,38 @@ def test_plane_parallel_fluxes_match_adding_doubling(tau, omega, g, mu0, albedo,
     assert (np.abs(m - want) < 4.0 * e + 2e-4).all(), (m, want, e)
 
 
+@pytest.mark.parametrize("rr", [False, True], ids=["plain", "rr"])
+@pytest.mark.parametrize("arithmetic", [MCB_ARITH_FAST, MCB_ARITH_REFERENCE], ids=["fast", "reference"])
+@pytest.mark.parametrize("tau,omega,mu0,albedo", [(2.0, 0.9, 0.5, 0.3), (0.5, 1.0, 0.8, 0.0)])
+def test_local_estimate_radiances_match_adding_doubling(tau, omega, mu0, albedo, arithmetic, rr):
+    """Both CUDA kernels' local estimate against the adding-doubling radiances (tests/adding_doubling.py): for isotropic
+    scattering the radiance leaving a plane-parallel slab is azimuth-independent, so the solver's azimuthally averaged
+    radiance at the top is the answer for every view direction -- the 1/(4 pi |mu_view|) normalisation, the Lambertian
+    surface term, the extinction along the view rays and both Russian-roulette variants included.  8e6 (fast) / 2e6
+    (reference) photons; 4 sigma of the batch standard error + 0.1 %."""
+    from adding_doubling import slab_fluxes
+    dom, case = domains.homogeneous_slab(ssa=omega, tau=tau, albedo=albedo, g=0.0, n=8, delta=0.125)
+    mus, phis = [1.0, 0.866, 0.5], [0.0, 0.0, 180.0]
+    n, nb = (500000, 16) if arithmetic == MCB_ARITH_FAST else (125000, 16)
+    g_ = new_Integrator(dom)
+    try:
+        specifyParameters(g_, intensityMus=mus, intensityPhis=phis, computeIntensity=True, useRussianRouletteForIntensity=rr,
+                          zetaMin=0.3, minInverseTableSize=10001, minForwardTableSize=10001, arithmetic=arithmetic)
+        rs = new_RandomNumberSequence([10, 1, 0])
+        rows = []
+        for b in range(nb):
+            ps = new_PhotonStream(mu0, 0.0, n, rs)
+            computeRadiativeTransfer(g_, dom, rs, ps, n)
+            rows.append(np.asarray(reportResults(g_, meanIntensity=True)["meanIntensity"], np.float64))
+        assert getCounters(g_)["bad"] == 0
+    finally:
+        finalize_Integrator(g_)
+    rows = np.array(rows)
+    m, e = rows.mean(axis=0), rows.std(axis=0, ddof=1) / np.sqrt(nb)
+    want = slab_fluxes(tau, omega, [1.0], mu0, albedo, muOut=mus)[3]
+    assert (np.abs(m - want) < 4.0 * e + 1e-3 * want).all(), (m, want, e)
+
+
 @pytest.mark.parametrize("views", [False, True], ids=["flux", "le"])
 def test_result_independent_of_batch_split(views):
     """Counter-based RNG keyed by the global photon id: one batch of N equals two accumulated

@@ -197,3 +197,25 @@ def test_plane_parallel_fluxes_match_adding_doubling(orc, tau, omega, g, mu0, al
     for name, w in zip(("meanFluxUpStats", "meanFluxDownStats", "meanFluxAbsorbedStats"), want):
         m, e = _fin(orc, st, name, tot, nb)
         assert abs(m[0] - w) < 4.0 * e[0] + 2e-4, (name, m[0], w, e[0])
+
+
+@pytest.mark.parametrize("rr", [False, True], ids=["plain", "rr"])
+@pytest.mark.parametrize("tau,omega,mu0,albedo", [(2.0, 0.9, 0.5, 0.3), (0.5, 1.0, 0.8, 0.0)])
+def test_local_estimate_radiances_match_adding_doubling(orc, tau, omega, mu0, albedo, rr):
+    """Independent pin of the local estimate (computeIntensityContribution INT:1623-1832, with and without the
+    Russian-roulette variants): for ISOTROPIC scattering the radiance leaving a plane-parallel slab does not depend on
+    azimuth, so the adding-doubling solver's azimuthally averaged radiance at the top is the answer for every view
+    direction -- normalisation 1/(4 pi |mu_view|), the Lambertian surface term 1/pi and the extinction along the view
+    rays included.  4 sigma of the batch standard error + 0.2 %."""
+    from adding_doubling import slab_fluxes
+    d, case = domains.homogeneous_slab(ssa=omega, tau=tau, albedo=albedo, g=0.0, n=8, delta=0.125)
+    mus, phis = [1.0, 0.866, 0.5], [0.0, 0.0, 180.0]
+    og = orc.OracleIntegrator(orc.OracleDomain(d, tableSize=10001, forward=True), useRussianRouletteForIntensity=int(rr), zetaMin=0.3)
+    og.set_views(mus, phis)
+    nb = 30
+    tot, st = og.run_batches(nb, 4000, solarMu=mu0, solarAzimuth=0.0, iseed=10, rank=1, thread=0)
+    cols = d.numX * d.numY
+    m, e = orc.finalise(st["radianceStats"], 1.0, tot, nb)
+    got = m.reshape(-1, cols).mean(axis=1); err = np.sqrt((e.reshape(-1, cols) ** 2).sum(axis=1)) / cols
+    want = slab_fluxes(tau, omega, [1.0], mu0, albedo, muOut=mus)[3]
+    assert (np.abs(got - want) < 4.0 * err + 2e-3 * want).all(), (got, want, err)
