@@ -23,7 +23,10 @@
 //   * Philox4x32-10 per-photon streams (mcb_device.cuh) instead of a sequential MT19937;
 //   * tallies: shared-memory-privatised f32 atomics flushed once per block when the column /
 //     cell grid is small enough to be an atomic hot spot, f64 RED.ADD to the packed tally
-//     buffer otherwise.
+//     buffer otherwise.  fluxAbsorbed is not tallied per event: the reference adds the same amount
+//     to fluxAbsorbed(ix,iy) and volumeAbsorption(ix,iy,iz) (INT:765-771, 505-508), so the column
+//     tally IS the column sum of the volume tally and a streaming kernel forms it after the launch
+//     (one atomic per scattering event less on the request-bound path).
 // Results agree with the reference arithmetic statistically (north-star criterion (b));
 // bit-level trace parity is the job of mcb_reference.cu.
 #include "mcb_device.cuh"
@@ -47,7 +50,7 @@ enum { ST_DEAD = 0, ST_MARCH = 1, ST_SCATTER = 2, ST_SURFACE = 3, ST_TOP = 4, ST
 // launch-time layout of the dynamic shared memory
 struct SmemPlan {
   int edgesOff;            // float[(nx+1+2G) + (ny+1+2G) + (nz+1+2G)] ghost-extended edges (irregular grids; -1 otherwise)
-  int fluxOff;             // float[3*cols]  privatised fluxUp|fluxDown|fluxAbs   (-1: global atomics)
+  int fluxOff;             // float[2*cols]  privatised fluxUp|fluxDown           (-1: global atomics)
   int volOff;              // float[cells]   privatised volumeAbsorption           (-1: global atomics)
   int intOff;              // float[cols*nDir] privatised intensity                (-1: global atomics)
   int leOff;               // per warp: LE_WORDS x 32 request slots + 64 words of queue state: task counter, rank -> lane map
@@ -598,7 +601,7 @@ batch_kernel(const __grid_constant__ DevDomain P, long long nPhotons, uint64_t s
   T.sFlux = plan.fluxOff >= 0 ? smem + plan.fluxOff : nullptr;
   T.sVol = plan.volOff >= 0 ? smem + plan.volOff : nullptr;
   T.sInt = plan.intOff >= 0 ? smem + plan.intOff : nullptr;
-  if (T.sFlux) for (int i = threadIdx.x; i < 3 * cols; i += THREADS) T.sFlux[i] = 0.0f;
+  if (T.sFlux) for (int i = threadIdx.x; i < 2 * cols; i += THREADS) T.sFlux[i] = 0.0f;
   if (T.sVol) for (int i = threadIdx.x; i < cells; i += THREADS) T.sVol[i] = 0.0f;
   if (T.sInt) for (int i = threadIdx.x; i < cols * P.nDir; i += THREADS) T.sInt[i] = 0.0f;
   if (threadIdx.x < 4) sCnt[threadIdx.x] = 0u;
@@ -674,8 +677,7 @@ batch_kernel(const __grid_constant__ DevDomain P, long long nPhotons, uint64_t s
       }
       if (ssa < 1.0f) {                                                        // INT:765-771
         const float absorbed = w * (1.0f - ssa);
-        add_flux(P, T, 2, r.ix + P.nx * r.iy, absorbed);
-        add_vol(P, T, cell, absorbed);
+        add_vol(P, T, cell, absorbed);                     // fluxAbsorbed = column sum of this tally (column_absorption_kernel)
         w *= ssa;
       }
       ray_position(r, P, px, py, pz);
@@ -776,7 +778,6 @@ batch_kernel(const __grid_constant__ DevDomain P, long long nPhotons, uint64_t s
         }
         if (P.opt.LW_flag > 0.0f) {                                            // INT:504-542
           if (pz > 0.0f) {
-            add_flux(P, T, 2, r.ix + P.nx * r.iy, -1.0f);
             add_vol(P, T, r.ix + P.nx * (r.iy + P.ny * r.iz), -1.0f);
           }
           if (LE && P.nDir > 0) { le_post(sle, lane, P, rng, r, px, py, pz, w, pz == 0.0f ? 0 : -1, 0, order, 0); posted = true; }
@@ -855,9 +856,9 @@ batch_kernel(const __grid_constant__ DevDomain P, long long nPhotons, uint64_t s
   }
   // ---- flush: privatised tallies, once per block, into the f64 tally buffer ----
   if (T.sFlux)
-    for (int i = threadIdx.x; i < 3 * cols; i += THREADS) {
+    for (int i = threadIdx.x; i < 2 * cols; i += THREADS) {
       const float v = T.sFlux[i];
-      if (v != 0.0f) atomicAdd(&P.tally[P.offFluxUp + i], (double)v);       // fluxUp|fluxDown|fluxAbs are contiguous
+      if (v != 0.0f) atomicAdd(&P.tally[P.offFluxUp + i], (double)v);       // fluxUp|fluxDown are contiguous
     }
   if (T.sVol)
     for (int i = threadIdx.x; i < cells; i += THREADS) {
@@ -877,6 +878,17 @@ batch_kernel(const __grid_constant__ DevDomain P, long long nPhotons, uint64_t s
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     atomicAdd(&P.tally[P.offPhotons], (double)nPhotons);
     atomicAdd(&P.counters[CNT_PHOTONS], (unsigned long long)nPhotons);
+  }
+}
+
+// fluxAbsorbed(ix,iy) = sum over iz of volumeAbsorption(ix,iy,iz) for everything accumulated so far (both kernels
+// keep the two tallies equal by construction; the reference-arithmetic kernel still adds to both as the reference does)
+__global__ void column_absorption_kernel(const DevDomain P) {
+  const long long cols = (long long)P.nx * P.ny;
+  for (long long c = blockIdx.x * (long long)blockDim.x + threadIdx.x; c < cols; c += (long long)gridDim.x * blockDim.x) {
+    double s = 0.0;
+    for (int k = 0; k < P.nz; ++k) s += P.tally[P.offVolAbs + c + cols * k];
+    P.tally[P.offFluxAbs + c] = s;
   }
 }
 
@@ -903,7 +915,7 @@ static void launch(const DevDomain &P, long long nPhotons, uint64_t seed, uint64
   int off = 0;
   if (!REG) { plan.edgesOff = off; off += P.nx + P.ny + P.nz + 3 + 6 * MCB_GHOST; }
   const int budgetFloats = 9 * 1024;            // 36 KB per block keeps >= 6 blocks/SM resident
-  if (3 * cols <= 3 * 1024 && off + 3 * cols <= budgetFloats) { plan.fluxOff = off; off += 3 * cols; }
+  if (cols <= 1024 && off + 2 * cols <= budgetFloats) { plan.fluxOff = off; off += 2 * cols; }
   if (cells <= 8192 && off + cells <= budgetFloats) { plan.volOff = off; off += cells; }
   if (P.nDir > 0 && cols * P.nDir <= 2048 && off + cols * P.nDir <= budgetFloats) { plan.intOff = off; off += cols * P.nDir; }
   // view rays still in flight when a round of the queue ends with no tasks left: at most `carry` of them are parked
@@ -972,6 +984,11 @@ void mcb_launch_fast_batch(const DevDomain &P, long long nPhotons, uint64_t seed
     if (le) MCB_GO(false, false, 4, true, false, false); else MCB_GO(false, false, 4, false, false, false);
   }
 #undef MCB_GO
+  {
+    const long long cols = (long long)P.nx * P.ny;
+    const int blocks = (int)((cols + 127) / 128 < (long long)numSMs * 8 ? (cols + 127) / 128 : (long long)numSMs * 8);
+    mcbfast::column_absorption_kernel<<<blocks, 128, 0, stream>>>(P);
+  }
 }
 
 void mcb_launch_philox_kat(uint64_t seed, uint64_t photon, int n, uint32_t *out, cudaStream_t stream) {
