@@ -46,7 +46,8 @@ def parse():
     ap.add_argument("--steps", type=int, default=4)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--photons", type=int, default=50_000_000, help="photons per GPU per step")
+    ap.add_argument("--photons", type=int, default=125_000_000,
+                    help="photons per GPU per step (default: the metric's configuration, 1e9 photons over 8 GPUs)")
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target CPU time of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--views", action="store_true", help="add the 5 I3RC radiance directions (local estimation)")
