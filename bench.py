@@ -312,7 +312,11 @@ def run_ours(args):
     kernel_ms = float(ms.value)
     counters = getCounters(g)                          # of the last step
     t = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
+    by_rank = [total_ms / args.steps]
     if world > 1:
+        every = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(every, t)                                    # per-rank step time: static photon shares, so the
+        by_rank = [float(x.item()) / args.steps for x in every]      # slowest GPU sets the step
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     total_ms = float(t.item())
     value = world * P * args.steps / (total_ms * 1e-3)
@@ -375,7 +379,7 @@ def run_ours(args):
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic",
+            "dtype": "f32", "data": "synthetic", "ms_per_step_by_rank": by_rank,
             "config": {"workload": WORKLOAD + (" + 5 radiance views (local estimation, RR zeta_min 0.3)" if args.views else ""),
                        "photons_per_gpu_per_step": P, "rng": "Philox4x32-10 per photon id",
                        "l2": ("optical-property arrays are L2-resident by construction (<= 126 MB); " if args.workload == "c3" else
