@@ -88,8 +88,21 @@ def computeLegendrePolynomials(maxL: int, mus) -> np.ndarray:
     return P[: maxL + 1]
 
 
+_LOBATTO_CACHE = {}
+
+
 def computeLobattoTerms(n: int):
-    """Lobatto abscissas and weights on [-1, 1] by Newton iteration (NUM:27-114)."""
+    """Lobatto abscissas and weights on [-1, 1] by Newton iteration (NUM:27-114).  The result depends on ``n`` only, so
+    it is kept: a many-wavelength run asks for the same few node counts at every wavelength and phase function."""
+    n = int(n)
+    if n not in _LOBATTO_CACHE:
+        mus, weights = _computeLobattoTerms(n)
+        mus.setflags(write=False); weights.setflags(write=False)
+        _LOBATTO_CACHE[n] = (mus, weights)
+    return _LOBATTO_CACHE[n]
+
+
+def _computeLobattoTerms(n: int):
     relativeAccuracy = f32(3.0)
     maxIterations = 25
     pi = f32(np.arccos(np.float64(-1.0)))
