@@ -136,7 +136,8 @@ int mcb_set_options(mcb_handle *h, const mcb_options *o);
 int mcb_set_solar_source(mcb_handle *h, float solarMu, float solarAzimuthDeg);
 /* Weights from emission_weighting (EMI:424-550): voxelCDF(nx,ny,nz), fracAtmsPower          */
 int mcb_set_thermal_source(mcb_handle *h, double fracAtmsPower, const double *voxelCDF);
-/* device build of the same CDF from the staged optics (EMI:498-522); temps(nx,ny,nz) in K   */
+/* device build of the same CDF from the staged optics (EMI:498-522); temps(nx,ny,nz) in K;
+ * temps == NULL reuses the temperatures of the previous call on this grid (many-wavelength runs) */
 int mcb_build_thermal_source(mcb_handle *h, const double *temps, double lambda_um,
                              double surfaceTemp, double *fracAtmsPower, double *totalFlux);
 /* read the staged Weights back (voxelWeights EMI:56-57, fracAtmsPower); either pointer may be NULL */

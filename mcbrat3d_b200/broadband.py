@@ -88,6 +88,7 @@ def runBroadband(thisIntegrator, tables: List[SSPTable], commonD: commonDomain, 
     Returns a dict with ``mean`` / ``err`` (the driver's finalised statistics, W m^-2 when the source function is in
     W m^-2 um^-1), ``freqDistr``, ``solarFlux``, ``totalNumPhotons``, ``batchesCompleted``."""
     g = thisIntegrator
+    commonD.temps.setflags(write=False)                    # the physical state is frozen for the run (uploaded once)
     nLambda = tables[0].f_grid.size
     lambdas = light_spd * 1e6 / np.asarray(tables[0].f_grid, dtype=np.float64)
     # ---- set-up: flux per bin -> CDF -> photons per bin (DRV:307-445 LW, 447-503 SW) ----

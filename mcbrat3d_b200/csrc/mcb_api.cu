@@ -56,6 +56,7 @@ struct mcb_handle {
   std::string err;
   DevDomain P;
   bool haveGrid = false, haveOptics = false, haveSource = false;
+  bool haveTemps = false;                        // dTemps holds the temperatures of the current grid
   bool packedLin = false, packedBrk = false;     // which layouts of the extinction field hold the current optics
   bool haveInv[MCB_MAX_COMP] = {false}, haveFwd[MCB_MAX_COMP] = {false};
   std::vector<double> xE, yE, zE;
@@ -267,7 +268,7 @@ int mcb_set_grid(mcb_handle *h, int nx, int ny, int nz,
     magic_divisor((uint32_t)bx * (uint32_t)by, &F.divSliceM, &F.divSliceS);      // brick index -> (bx, by, bz)
     magic_divisor((uint32_t)bx, &F.divRowM, &F.divRowS);
   }
-  h->haveGrid = true; h->haveOptics = false; h->haveSource = false; h->havePhysical = false;
+  h->haveGrid = true; h->haveOptics = false; h->haveSource = false; h->havePhysical = false; h->haveTemps = false;
   return 0;
 }
 
@@ -621,7 +622,7 @@ int mcb_build_thermal_source(mcb_handle *h, const double *temps, double lambda_u
                              double surfaceTemp, double *fracAtmsPowerOut, double *totalFluxOut) {
   if (!h) return 1;
   if (!h->haveOptics) FAIL(h, "emission_weighting: domain hasn't been initialized.");
-  if (!temps) FAIL(h, "emission_weighting: null temperature array");
+  if (!temps && !h->haveTemps) FAIL(h, "emission_weighting: null temperature array");
   const DevDomain &P = h->P;
   const int nx = P.nx, ny = P.ny;
   const long long cells = (long long)nx * ny * P.nz;
@@ -639,7 +640,8 @@ int mcb_build_thermal_source(mcb_handle *h, const double *temps, double lambda_u
     sfcPower = Pi * emiss * sfcPlanckRad * areaX * areaY * (1000.0 * 1000.0);
   }
   const long long tiles = mcb_emission_tiles(cells);
-  if (stage_async(h, &h->dTemps, temps, sizeof(double) * cells)) return 1;
+  // temps == NULL: the temperatures staged by the previous call (they do not depend on the wavelength, DRV:326-345)
+  if (temps) { if (stage_async(h, &h->dTemps, temps, sizeof(double) * cells)) return 1; h->haveTemps = true; }
   if (reserve(h, &h->dScratch, sizeof(double) * 2 * (size_t)(tiles + 1))) return 1;
   if (reserve(h, &h->dVoxelCDF, sizeof(double) * cells)) return 1;
   CK(h, cudaMemsetAsync(h->dFlags, 0, sizeof(int) * 4, h->stream));

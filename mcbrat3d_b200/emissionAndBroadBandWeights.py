@@ -49,9 +49,16 @@ def emission_weighting_device(thisDomain, theseWeights: Weights, sfcTemp: float,
         raise ValueError("emission_weighting: domain hasn't been initialized.")
     _stage_domain(g, thisDomain)
     temps = np.ascontiguousarray(thisDomain.temps, dtype=np.float64)
+    # The temperatures do not depend on the wavelength: a read-only array (runBroadband freezes the physical state of
+    # a run) is uploaded once and NULL ("as before") is passed afterwards; the integrator keeps the array alive so
+    # that its address cannot be recycled.
+    tkey = (temps.ctypes.data, temps.shape)
+    reuse = getattr(g, "_stagedTemps", None) == tkey and not temps.flags.writeable
     frac = C.c_double(0.0); flux = C.c_double(0.0)
-    g._check(g._lib.mcb_build_thermal_source(g.handle, _lib.ptr(temps, C.c_double), float(thisDomain.lambda_um),
+    g._check(g._lib.mcb_build_thermal_source(g.handle, None if reuse else _lib.ptr(temps, C.c_double), float(thisDomain.lambda_um),
                                              float(sfcTemp), C.byref(frac), C.byref(flux)), "emission_weighting")
+    g._stagedTemps = tkey if not temps.flags.writeable else None
+    g._stagedTempsRef = temps
     theseWeights.voxelWeights = None
     theseWeights.fracAtmsPower = float(frac.value)
     theseWeights.spectrIntgrFlux = float(flux.value)
