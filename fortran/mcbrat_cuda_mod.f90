@@ -169,7 +169,7 @@ module mcbrat_cuda
         bind(C, name="mcb_build_thermal_source")
       import :: c_int, c_ptr, c_double
       type(c_ptr), value :: handle
-      real(c_double), intent(in) :: temps(*)
+      type(c_ptr), value :: temps            ! c_loc(temps(1,1,1)), or c_null_ptr: the temperatures staged before
       real(c_double), value :: lambda_um, surfaceTemp
       real(c_double), intent(out) :: fracAtmsPower, totalFlux
     end function

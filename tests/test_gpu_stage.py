@@ -160,6 +160,36 @@ def test_emission_cdf_built_on_device_matches_oracle(orc, name):
             assert w2.fracAtmsPower == 0.0 and not fetchVoxelWeights(w2).any()
         finally:
             d2.temps = keep
+        # a read-only temperature array is uploaded once: the next build passes NULL ("the temperatures staged
+        # before") and must give the same CDF; a different array of the same shape is uploaded again
+        d.temps.setflags(write=False)
+        try:
+            wa, wb = Weights(), Weights()
+            emission_weighting(d, wa, sfcTemp, thisIntegrator=g)
+            assert g._stagedTemps is not None
+            fa = emission_weighting(d, wb, sfcTemp, thisIntegrator=g)                 # NULL path
+            assert np.array_equal(fetchVoxelWeights(wb), got) and fa == got_flux
+            warm = d.temps + 5.0; warm.setflags(write=False)
+            keep = d.temps; d.temps = warm
+            try:
+                wc = Weights()
+                assert emission_weighting(d, wc, sfcTemp, thisIntegrator=g) > got_flux
+            finally:
+                d.temps = keep
+        finally:
+            d.temps.setflags(write=True)
+    finally:
+        finalize_Integrator(g)
+
+
+def test_thermal_source_without_temperatures_is_an_error():
+    d, case = domains.homogeneous_lw()
+    g = new_Integrator(d)
+    try:
+        from mcbrat3d_b200.monteCarloRadiativeTransfer import _stage_domain
+        _stage_domain(g, d)
+        frac = C.c_double(0.0); flux = C.c_double(0.0)
+        assert g._lib.mcb_build_thermal_source(g.handle, None, 10.0, 300.0, C.byref(frac), C.byref(flux)) != 0
     finally:
         finalize_Integrator(g)
 
