@@ -245,9 +245,18 @@ int mcb_set_grid(mcb_handle *h, int nx, int ny, int nz,
   P.deltaZ = zReg ? (double)deltaZ : 0.0;
   P.fx0 = (float)P.x0; P.fy0 = (float)P.y0; P.fz0 = (float)P.z0;
   P.fLx = (float)(P.xMax - P.x0); P.fLy = (float)(P.yMax - P.y0); P.fLz = (float)(P.zMax - P.z0);
-  P.fhx = (float)P.deltaX; P.fhy = (float)P.deltaY; P.fhz = (float)P.deltaZ;
+  // The throughput kernel is statistical, not bit-faithful: a grid whose spacings are uniform to 1e-6 is stepped
+  // incrementally with its mean spacing whether or not quirk q1 calls it regular (the reference-arithmetic kernel and
+  // the normalisation keep the reference's own flags).
+  auto uniformAxis = [](const double *e, int n) {
+    const double mean = (e[n] - e[0]) / n;
+    for (int i = 0; i < n; ++i) if (!(std::fabs((e[i + 1] - e[i]) - mean) <= 1.0e-6 * mean)) return false;
+    return true;
+  };
+  P.uniform = (uniformAxis(xEdges, nx) && uniformAxis(yEdges, ny) && uniformAxis(zEdges, nz)) ? 1 : 0;
+  P.fhx = (float)((P.xMax - P.x0) / nx); P.fhy = (float)((P.yMax - P.y0) / ny); P.fhz = (float)((P.zMax - P.z0) / nz);
   P.finvLx = 1.0f / P.fLx; P.finvLy = 1.0f / P.fLy; P.fzMax = (float)P.zMax;
-  P.finvhx = xyReg ? 1.0f / P.fhx : 0.0f; P.finvhy = xyReg ? 1.0f / P.fhy : 0.0f;
+  P.finvhx = 1.0f / P.fhx; P.finvhy = 1.0f / P.fhy;
   // padded extinction field: MCB_GHOST cells on every side (see mcb_set_optics)
   {                                                  // x-fastest layout
     DevDomain::ExtField &F = P.lin;

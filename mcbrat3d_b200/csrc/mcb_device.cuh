@@ -19,6 +19,9 @@ struct DevDomain {
   int nx, ny, nz, nc;
   const double *xE, *yE, *zE;                 // edges, n+1 each
   int xyRegular, zRegular;                    // INT:163-181 (f32-rounded spacing test, quirk q1)
+  int uniform;                                // all three spacings uniform to 1e-6 relative: the throughput kernel steps
+                                              // such grids incrementally even when q1 sends the reference down its
+                                              // irregular-grid path (0.05 km is not exactly representable in f32)
   double deltaX, deltaY, deltaZ;
   double x0, y0, z0, xMax, yMax, zMax;
   // ---- optical properties, reference layout and precision ----

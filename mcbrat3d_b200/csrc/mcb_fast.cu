@@ -949,7 +949,7 @@ static void launch(const DevDomain &P, long long nPhotons, uint64_t seed, uint64
 bool mcb_fast_reads_bricks(const DevDomain &P) {
   const char *el = getenv("MCB_LAYOUT");
   const bool wide = P.nx >= MCB_GHOST && P.ny >= MCB_GHOST;
-  return P.xyRegular && P.zRegular && wide && P.nDir == 0 && !(el && el[0] == 'l');
+  return P.uniform && wide && P.nDir == 0 && !(el && el[0] == 'l');
 }
 
 void mcb_launch_fast_batch(const DevDomain &P, long long nPhotons, uint64_t seed, uint64_t firstPhotonId,
@@ -968,7 +968,7 @@ void mcb_launch_fast_batch(const DevDomain &P, long long nPhotons, uint64_t seed
     launch<REG, WIDE, OCC, 8, LE, MASK, BRICK>(P, nPhotons, seed, firstPhotonId, numSMs, workCounter, stream)
   const bool wide = P.nx >= MCB_GHOST && P.ny >= MCB_GHOST;      // no grid period shorter than the ghost shell
   const bool le = P.nDir > 0, mask = P.lin.mask != nullptr;
-  if (P.xyRegular && P.zRegular) {
+  if (P.uniform) {
     if (!wide) { if (le) MCB_GO(true, false, MCB_LE_OCC, true, false, false); else MCB_GO(true, false, 8, false, false, false); }
     else if (le) { if (mask) MCB_GO(true, true, MCB_LE_OCC, true, true, false); else MCB_GO(true, true, MCB_LE_OCC, true, false, false); }
     else if (mask) {

@@ -141,13 +141,17 @@ def landsat_cloud(ssa=1.0, nxy=128, mie=False, seed=43, nLegendre=299) -> Tuple[
                    meanOpticalDepth=float(tau.mean()))
 
 
-def irregular_test_domain(albedo=0.3) -> Tuple[Domain, Dict]:
+def irregular_test_domain(albedo=0.3, stretched=False) -> Tuple[Domain, Dict]:
     """T-irr (trace harness): 12 x 10 x 8 cells with spacings 0.05 / 0.03 / 0.02 km that are NOT
     exactly representable in single precision, so new_Integrator takes the irregular path
     (quirks q1-q3); two components (one horizontally uniform, partial height), a layer with no
     extinction, absorbing cloud, reflecting surface."""
     nx, ny, nz = 12, 10, 8
     x = 0.05 * np.arange(nx + 1); y = 0.03 * np.arange(ny + 1); z = 0.02 * np.arange(nz + 1)
+    if stretched:                       # genuinely non-uniform spacings (the throughput kernel's edge-table variant)
+        x = np.concatenate([[0.0], np.cumsum(0.05 * (1.0 + 0.3 * np.sin(1.0 + np.arange(nx))))])
+        y = np.concatenate([[0.0], np.cumsum(0.03 * (1.0 + 0.25 * np.cos(0.5 + np.arange(ny))))])
+        z = np.concatenate([[0.0], np.cumsum(0.012 * 1.15 ** np.arange(nz))])
     d = Domain(x, y, z, temps=np.full((nz, ny, nx), 280.0), surfaceAlbedo=albedo, lambda_um=10.0)
     rng = np.random.default_rng(7)
     ext = rng.uniform(5.0, 60.0, size=(nz, ny, nx))
@@ -163,7 +167,7 @@ def irregular_test_domain(albedo=0.3) -> Tuple[Domain, Dict]:
     d.addOpticalComponent("gas", np.array([3.0, 2.0, 1.0]), np.array([0.3, 0.3, 0.3]), np.ones(3, np.int32),
                           new_PhaseFunctionTable([rayleigh()], key=[0.0]), zLevelBase=2)
     d.getOpticalPropertiesByComponent()
-    return d, dict(name="T_irr", solarMu=0.6, solarAzimuth=30.0, LW_flag=-1.0,
+    return d, dict(name="T_irr_stretched" if stretched else "T_irr", solarMu=0.6, solarAzimuth=30.0, LW_flag=-1.0,
                    intensityMus=[1.0, 0.7, -0.5], intensityPhis=[0.0, 45.0, 200.0])
 
 

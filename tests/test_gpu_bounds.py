@@ -23,6 +23,7 @@ from test_gpu_stats import _tiny_domain
 cases = {"C3_small_mie": (domains.landsat_cloud(ssa=0.99, nxy=24, mie=True), False, 150000),
          "C2_views": (domains.step_cloud(ssa=0.99, solarMu=0.5), True, 60000),
          "T_irr_views": (domains.irregular_test_domain(), True, 60000),
+         "T_irr_stretched_views": (domains.irregular_test_domain(stretched=True), True, 60000),
          "C5_small": (domains.bench_domain(nxy=40, nz=48), False, 100000),
          "C5_small_odd": (domains.bench_domain(nxy=41, nz=47), False, 100000),
          "C5_small_odd_bitmap": (domains.bench_domain(nxy=41, nz=47), False, 100000),

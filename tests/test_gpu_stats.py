@@ -85,6 +85,8 @@ CASES = [
     ("C2_views", lambda: domains.step_cloud(ssa=0.99, solarMu=0.5), 0, True, 1500),
     ("C4_LW", lambda: domains.homogeneous_lw(), 1, False, 6000),
     ("T_irr", lambda: domains.irregular_test_domain(), 0, False, 8000),
+    ("T_irr_stretched", lambda: domains.irregular_test_domain(stretched=True), 0, False, 8000),
+    ("T_irr_stretched_views", lambda: domains.irregular_test_domain(stretched=True), 0, True, 1500),
     ("C3_small_mie", lambda: domains.landsat_cloud(ssa=0.99, nxy=16, mie=True), 0, False, 3000),
 ]
 
