@@ -380,6 +380,9 @@ struct Counts { unsigned crossings, scatters, leRays, leCrossings; };
 #ifndef MCB_LE_BURST
 #define MCB_LE_BURST 8          // cells per burst of a local-estimate ray (C3 + 5 views: 4 -> 5.9e7, 8 -> 6.4e7 photons/s)
 #endif
+#ifndef MCB_IRR_OCC
+#define MCB_IRR_OCC 6            // CTAs per SM of the edge-table (stretched grid) flux kernel: 80 registers (4: 3.95e8, 6: 4.55e8, 8: 2.9e8 photons/s)
+#endif
 #ifndef MCB_LE_OCC
 #define MCB_LE_OCC 5             // CTAs per SM of the local-estimation kernels: 96 registers, no spills (6: 80 registers, 314 B of spills, 8 % slower)
 #endif
@@ -981,7 +984,7 @@ void mcb_launch_fast_batch(const DevDomain &P, long long nPhotons, uint64_t seed
       else MCB_GO(true, true, 8, false, false, true);
     }
   } else {
-    if (le) MCB_GO(false, false, 4, true, false, false); else MCB_GO(false, false, 4, false, false, false);
+    if (le) MCB_GO(false, false, 4, true, false, false); else MCB_GO(false, false, MCB_IRR_OCC, false, false, false);
   }
 #undef MCB_GO
   {

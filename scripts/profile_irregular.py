@@ -12,6 +12,9 @@ from mcbrat3d_b200.RandomNumbersForMC import new_RandomNumberSequence
 dom, case = domains.landsat_cloud(ssa=0.99)
 dom.xPosition = dom.xPosition * 1.0001; dom.yPosition = dom.yPosition * 1.0001
 dom.zPosition = 200.0 + (dom.zPosition - 200.0) * 1.0001
+if len(sys.argv) > 1 and sys.argv[1] == "stretched":        # genuinely stretched layers: the edge-table kernel variant
+    dz = 20.0 * (0.6 + 0.8 * np.arange(dom.numZ) / (dom.numZ - 1))
+    dom.zPosition = np.concatenate([[200.0], 200.0 + np.cumsum(dz)])
 g = new_Integrator(dom)
 specifyParameters(g, minInverseTableSize=10001)
 
