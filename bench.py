@@ -399,6 +399,11 @@ def run_ours(args):
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": peak_src, "kernel_ms": kernel_ms,
                          "algorithmic_bytes_per_launch": abytes,
+                         # the sector-granular figure -- every independent gather moves one 32-byte sector,
+                         # so HBM could serve peak/32 gathers per second; a ratio above 1 means the gathers are served by L2
+                         "sector_gather": {"gathers_per_s": (counters["crossings"] + counters["leCrossings"] + counters["scatters"]) / (kernel_ms * 1e-3),
+                                           "hbm_sector_roofline_per_s": peak * 1e9 / 32.0,
+                                           "frac": (counters["crossings"] + counters["leCrossings"] + counters["scatters"]) / (kernel_ms * 1e-3) / (peak * 1e9 / 32.0)},
                          "limiter_ncu": limiter,
                          "note": ("memory-gather roofline; the extinction field is L2-resident on this domain, so HBM "
                                   "traffic is far below the algorithmic bytes and the kernel is bounded by the SMs' "

@@ -38,6 +38,7 @@ def test_gpu_arm_prints_the_contract_line():
     assert line["n_gpus"] == 1 and line["gpu_launches"] == 1 and line["value"] > 1e8
     r = line["roofline"]
     assert r["bound"] == "hbm" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9 and r["unit"] == "GB/s"
+    assert r["sector_gather"]["gathers_per_s"] > 1e10 and r["sector_gather"]["frac"] > 0
     assert line["e2e"]["h2d_bytes_per_step"] > 0 and line["e2e"]["d2h_bytes_per_step"] > 0
     assert line["e2e"]["value"] != line["value"]
     assert line["config"]["bad_photons"] == 0
