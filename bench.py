@@ -279,9 +279,16 @@ def run_ours(args):
     # step starts from a cold L2, as the recipe asks.
     flush = torch.empty(64 * 1024 * 1024, dtype=torch.float32, device="cuda")
 
+    # Photon shares: a step traces world * P photons (weak scaling); rank r takes shares[r] of them, contiguous in the
+    # global photon id.  The warm-up steps use equal shares and time each rank's kernel; the timed steps use shares
+    # proportional to those rates, so that a GPU running a few per cent slower (power / thermal state) does not set the
+    # step -- the static analogue of the reference's master handing out batches to workers as they finish
+    # (DRV:665-1095).  Tallies do not depend on the split: photons are identified by their global id.
+    shares = [P] * world
+
     def step(i):
-        first = (i * world + rank) * P                 # disjoint global photon ids per (step, rank)
-        g._check(lib.mcb_run_batch(h, P, C.c_uint64(rs.seed), C.c_uint64(first), C.byref(done)), "mcb_run_batch")
+        first = i * world * P + sum(shares[:rank])     # disjoint global photon ids per (step, rank)
+        g._check(lib.mcb_run_batch(h, shares[rank], C.c_uint64(rs.seed), C.c_uint64(first), C.byref(done)), "mcb_run_batch")
         if world > 1:
             dist.reduce(tally, dst=0, op=dist.ReduceOp.SUM)          # the run's one exchange: NCCL over NVLink
 
@@ -290,9 +297,22 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    warm_ms = []
     for i in range(args.warmup):
         step(i); flush.zero_()
+        if world > 1:
+            torch.cuda.synchronize()
+            kms = C.c_float(0)
+            lib.mcb_last_batch_ms(h, C.byref(kms))         # this rank's kernel alone (CUDA events inside the library)
+            warm_ms.append(float(kms.value))
     sync()
+    if world > 1 and len(warm_ms) >= 2:
+        mine = torch.tensor([sorted(warm_ms[1:])[len(warm_ms[1:]) // 2]], dtype=torch.float64, device="cuda")   # median, first step dropped
+        every = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(every, mine)
+        rates = [1.0 / max(float(x.item()), 1e-6) for x in every]
+        shares = [int(world * P * r / sum(rates)) for r in rates]
+        shares[-1] = world * P - sum(shares[:-1])
     ev0 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     ev1 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     kernel_ms = []
@@ -381,7 +401,9 @@ def run_ours(args):
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic", "ms_per_step_by_rank": by_rank,
             "config": {"workload": WORKLOAD + (" + 5 radiance views (local estimation, RR zeta_min 0.3)" if args.views else ""),
-                       "photons_per_gpu_per_step": P, "rng": "Philox4x32-10 per photon id",
+                       "photons_per_gpu_per_step": P, "photon_shares": shares,
+                       "shares": "equal in the warm-up steps, proportional to each rank's measured kernel rate in the timed steps",
+                       "rng": "Philox4x32-10 per photon id",
                        "l2": ("optical-property arrays are L2-resident by construction (<= 126 MB); " if args.workload == "c3" else
                               "inputs (93 MB extinction field + 253 MB event records) are larger than L2; ") +
                              "a 256 MB buffer is rewritten between timed steps (L2 flush), outside the per-step event pairs",
