@@ -310,9 +310,7 @@ def run_ours(args):
         mine = torch.tensor([min(warm_ms[1:])], dtype=torch.float64, device="cuda")   # best step, the first one dropped
         every = [torch.zeros_like(mine) for _ in range(world)]
         dist.all_gather(every, mine)
-        rates = [1.0 / max(float(x.item()), 1e-6) for x in every]
-        shares = [int(world * P * r / sum(rates)) for r in rates]
-        shares[-1] = world * P - sum(shares[:-1])
+        shares = mpx.photonShares(world * P, [1.0 / max(float(x.item()), 1e-6) for x in every])
     ev0 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     ev1 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     kernel_ms = []

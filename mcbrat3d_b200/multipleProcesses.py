@@ -95,6 +95,21 @@ def photonRange(totalPhotons: int, numProcs_: int, thisProc_: int) -> Tuple[int,
     return first, base + (1 if thisProc_ < extra else 0)
 
 
+def photonShares(totalPhotons: int, rates) -> list:
+    """Shares of ``totalPhotons`` proportional to the ranks' measured photon rates (any positive unit), contiguous in
+    the global photon id: rank r traces ids [sum(shares[:r]), sum(shares[:r+1])).  The static analogue of the
+    master handing batches to workers as they finish (DRV:665-1095): a GPU that runs a few per cent slower gets
+    proportionally fewer photons instead of setting the step.  Non-finite or non-positive rates fall back to the mean."""
+    r = [float(x) for x in rates]
+    good = [x for x in r if x > 0.0 and x == x and x != float("inf")]
+    mean = sum(good) / len(good) if good else 1.0
+    r = [x if (x > 0.0 and x == x and x != float("inf")) else mean for x in r]
+    total = int(totalPhotons)
+    shares = [int(total * x / sum(r)) for x in r]
+    shares[-1] = total - sum(shares[:-1])
+    return shares
+
+
 class _DeviceBuffer:
     """Exposes a raw device pointer to torch through ``__cuda_array_interface__``."""
 

@@ -102,6 +102,23 @@ def test_photon_range_partition():
             assert max(c for _, c in ranges) - min(c for _, c in ranges) <= 1
 
 
+def test_rate_proportional_photon_shares():
+    from mcbrat3d_b200.multipleProcesses import photonShares
+    n = 8 * 125_000_000
+    eq = photonShares(n, [1.0] * 8)
+    assert sum(eq) == n and max(eq) - min(eq) <= 8
+    rates = [1.0, 1.0, 0.95, 1.0, 1.02, 1.0, 1.0, 0.99]
+    sh = photonShares(n, rates)
+    assert sum(sh) == n and all(s > 0 for s in sh)
+    for s_, r in zip(sh, rates):
+        assert abs(s_ - n * r / sum(rates)) <= 8
+    # every rank finishes at the same time: share / rate is constant
+    t = [s_ / r for s_, r in zip(sh, rates)]
+    assert max(t) / min(t) - 1.0 < 1e-6
+    assert sum(photonShares(10, [0.0, float("nan"), 1.0])) == 10 and min(photonShares(10, [0.0, float("nan"), 1.0])) >= 3
+    assert photonShares(7, [3.0]) == [7]
+
+
 def test_synthetic_domains_shapes():
     d, c = domains.step_cloud()
     assert (d.numX, d.numY, d.numZ) == (32, 1, 32) and d.xPosition[1] == 15.625
