@@ -79,3 +79,46 @@ def table_moments(inverseTable, lmax=127):
     deterministic solver must be given the same scattering law to be a test of the transport."""
     theta = np.asarray(inverseTable, dtype=np.float64).reshape(-1)
     return _legendre_matrix(lmax, np.cos(theta[:-1])).mean(axis=1)
+
+
+def layered_fluxes(layers, chi, mu0, albedo=0.0, nStreams=64, thin=1.0e-5):
+    """Fluxes of a stack of homogeneous layers, TOP FIRST, each (tau, omega), all with the phase function ``chi``:
+    every layer by doubling, the stack by adding (R12 = R1 + T1 (1 - R2 R1)^-1 R2 T1, T12 = T2 (1 - R1 R2)^-1 T1; a
+    homogeneous layer reflects alike from both sides).  Returns (Fup at the top, Fdown at the surface, absorbed)."""
+    chi = np.asarray(chi, dtype=np.float64)
+    x, w = np.polynomial.legendre.leggauss(nStreams)
+    mu = np.concatenate([0.5 * (x + 1.0), [mu0]])
+    wt = np.concatenate([0.5 * w, [0.0]])
+    L = chi.size - 1
+    Pl = _legendre_matrix(L, mu)
+    fac = (2 * np.arange(L + 1) + 1) * chi
+    Pf = (Pl * fac[:, None]).T @ Pl
+    Pb = (Pl * (fac * (-1.0) ** np.arange(L + 1))[:, None]).T @ Pl
+    norm = 0.5 * (wt[:, None] * (Pf + Pb)).sum(axis=0)
+    Pf, Pb = Pf / norm[None, :], Pb / norm[None, :]
+    I = np.eye(mu.size)
+
+    def layer(tau, omega):
+        n = max(int(np.ceil(np.log2(max(tau, 1e-300) / (thin * mu.min())))), 0)
+        d = tau / 2.0 ** n
+        T = np.diag(np.exp(-d / mu)) + wt[:, None] * omega * d * Pf / (2.0 * mu[None, :])
+        R = wt[:, None] * omega * d * Pb / (2.0 * mu[None, :])
+        for _ in range(n):
+            G = np.linalg.solve(I - R @ R, np.concatenate([T, R @ T], axis=1))
+            R, T = R + T @ G[:, mu.size:], T @ G[:, :mu.size]
+        return R, T
+    # R: reflection of the stack seen from above, Rb: seen from below, T: transmission downwards, Tb: upwards
+    R, T = layer(*layers[0]); Rb, Tb = R.copy(), T.copy()
+    for tau, omega in layers[1:]:
+        R2, T2 = layer(tau, omega)
+        A = np.linalg.inv(I - Rb @ R2)              # bounces between the stack's underside and the new layer
+        B = np.linalg.inv(I - R2 @ Rb)
+        R, T, Rb, Tb = (R + Tb @ np.linalg.solve(I - R2 @ Rb, R2 @ T), T2 @ A @ T,
+                        R2 + T2 @ A @ Rb @ T2, Tb @ B @ T2)
+    lam = wt * mu / (wt * mu).sum()
+    Rs = albedo * np.outer(lam, np.ones(mu.size))
+    y0 = np.zeros(mu.size); y0[-1] = 1.0
+    down = np.linalg.solve(I - Rb @ Rs, T @ y0)
+    up = R @ y0 + Tb @ (Rs @ down)
+    fup, fdn = up.sum(), down.sum()
+    return fup, fdn, 1.0 - fup - (1.0 - albedo) * fdn

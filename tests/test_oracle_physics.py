@@ -219,3 +219,34 @@ def test_local_estimate_radiances_match_adding_doubling(orc, tau, omega, mu0, al
     got = m.reshape(-1, cols).mean(axis=1); err = np.sqrt((e.reshape(-1, cols) ** 2).sum(axis=1)) / cols
     want = slab_fluxes(tau, omega, [1.0], mu0, albedo, muOut=mus)[3]
     assert (np.abs(got - want) < 4.0 * err + 2e-3 * want).all(), (got, want, err)
+
+
+@pytest.mark.parametrize("name,layers", [("two_layers", [(1.0, 1.0, 4), (3.0, 0.8, 4)]),
+                                         ("gap", [(2.0, 0.9, 3), (0.0, 0.0, 2), (4.0, 0.99, 3)])])
+def test_layered_slab_fluxes_match_adding(orc, name, layers):
+    """Vertical structure against the independent solver: a stack of different homogeneous layers (one case with an
+    EMPTY layer in the middle: extinction 0, phase-function index 0) is marched cell by cell by the Monte Carlo and
+    solved layer by layer with doubling + adding (tests/adding_doubling.py::layered_fluxes; the adding step reproduces
+    the single-slab solution exactly when the layers are identical).  layers: (tau, omega, cells), TOP FIRST."""
+    from adding_doubling import layered_fluxes, table_moments
+    from mcbrat3d_b200.opticalProperties import Domain
+    from mcbrat3d_b200.scatteringPhaseFunctions import henyeyGreenstein, new_PhaseFunctionTable
+    n, delta, mu0, albedo = 8, 0.125, 0.5, 0.2
+    edges = delta * np.arange(n + 1, dtype=np.float64)
+    d = Domain(edges, edges, edges, surfaceAlbedo=albedo)
+    ext = np.zeros((n, n, n)); ssa = np.zeros((n, n, n)); idx = np.zeros((n, n, n), np.int32)
+    k = n
+    for tau, omega, cells in layers:                                  # z index 0 is the bottom layer
+        k -= cells
+        ext[k:k + cells] = tau / (cells * delta); ssa[k:k + cells] = omega; idx[k:k + cells] = 1 if tau > 0 else 0
+    assert k == 0
+    d.addOpticalComponent("cloud", ext, ssa, idx, new_PhaseFunctionTable([henyeyGreenstein(0.85, 64)], key=[1.0]))
+    d.getOpticalPropertiesByComponent()
+    og = orc.OracleIntegrator(orc.OracleDomain(d, tableSize=10001))
+    nb = 40
+    tot, st = og.run_batches(nb, 5000, solarMu=mu0, solarAzimuth=0.0, iseed=10, rank=1, thread=0)
+    d.tabulateInversePhaseFunctions(10001)
+    want = layered_fluxes([(t, w) for t, w, _ in layers], table_moments(d.inversePhaseFunctions[0]), mu0, albedo, nStreams=96)
+    for key, w in zip(("meanFluxUpStats", "meanFluxDownStats", "meanFluxAbsorbedStats"), want):
+        m, e = _fin(orc, st, key, tot, nb)
+        assert abs(m[0] - w) < 4.0 * e[0] + 2e-4, (key, m[0], w, e[0])
