@@ -122,3 +122,62 @@ def layered_fluxes(layers, chi, mu0, albedo=0.0, nStreams=64, thin=1.0e-5):
     up = R @ y0 + Tb @ (Rs @ down)
     fup, fdn = up.sum(), down.sum()
     return fup, fdn, 1.0 - fup - (1.0 - albedo) * fdn
+
+
+def planck(lambda_um, T):
+    """Spectral radiance up to the constant factors the Monte Carlo's weights share (EMI:503): only ratios matter."""
+    hP, cL, kB = 6.62606957e-34, 2.99792458e+8, 1.3806488e-23
+    lam = lambda_um / 1.0e6
+    return (2.0 * hP * cL * cL) / (lam ** 5 * (np.exp(hP * cL / (kB * lam * T)) - 1.0))
+
+
+def thermal_fluxes(layers, chi, lambda_um, surfaceTemp, albedo=0.0, nStreams=64, thin=1.0e-5):
+    """Thermal emission of a stack of homogeneous layers, TOP FIRST, each (tau, omega, temperature), over a Lambertian
+    surface of emissivity 1 - albedo: doubling and adding WITH SOURCES.  A thin layer d emits 2 pi B (1 - omega) d into
+    each hemisphere, isotropically (node shares w_i); two identical layers combine to S2 = S + T (1 - R)^-1 S; a layer
+    2 added under a stack 1 gives D = (1 - Rb1 R2)^-1 (Sd1 + Rb1 Su2), U = Su2 + R2 D, Su = Su1 + Tb1 U, Sd = Sd2 + T2 D.
+    Returns the Monte Carlo's normalised quantities (per emitted photon): (fracAtmsPower, Fup at the top, Fdown at
+    the surface, absorbed minus emitted in the atmosphere)."""
+    chi = np.asarray(chi, dtype=np.float64)
+    x, w = np.polynomial.legendre.leggauss(nStreams)
+    mu, wt = 0.5 * (x + 1.0), 0.5 * w
+    L = chi.size - 1
+    Pl = _legendre_matrix(L, mu)
+    fac = (2 * np.arange(L + 1) + 1) * chi
+    Pf = (Pl * fac[:, None]).T @ Pl
+    Pb = (Pl * (fac * (-1.0) ** np.arange(L + 1))[:, None]).T @ Pl
+    norm = 0.5 * (wt[:, None] * (Pf + Pb)).sum(axis=0)
+    Pf, Pb = Pf / norm[None, :], Pb / norm[None, :]
+    I = np.eye(mu.size)
+
+    def layer(tau, omega, T):
+        n = max(int(np.ceil(np.log2(max(tau, 1e-300) / (thin * mu.min())))), 0)
+        d = tau / 2.0 ** n
+        Tm = np.diag(np.exp(-d / mu)) + wt[:, None] * omega * d * Pf / (2.0 * mu[None, :])
+        R = wt[:, None] * omega * d * Pb / (2.0 * mu[None, :])
+        S = 2.0 * np.pi * wt * planck(lambda_um, T) * (1.0 - omega) * d
+        for _ in range(n):
+            S = S + Tm @ np.linalg.solve(I - R, S)
+            G = np.linalg.solve(I - R @ R, np.concatenate([Tm, R @ Tm], axis=1))
+            R, Tm = R + Tm @ G[:, mu.size:], Tm @ G[:, :mu.size]
+        return R, Tm, S
+    R, T, S = layer(*layers[0])
+    Rb, Tb, Su, Sd = R.copy(), T.copy(), S.copy(), S.copy()
+    for tau, omega, temp in layers[1:]:
+        R2, T2, S2 = layer(tau, omega, temp)
+        D = np.linalg.solve(I - Rb @ R2, Sd + Rb @ S2)
+        U = S2 + R2 @ D
+        Su, Sd = Su + Tb @ U, S2 + T2 @ D
+        A = np.linalg.inv(I - Rb @ R2); B = np.linalg.inv(I - R2 @ Rb)
+        R, T, Rb, Tb = (R + Tb @ np.linalg.solve(I - R2 @ Rb, R2 @ T), T2 @ A @ T, R2 + T2 @ A @ Rb @ T2, Tb @ B @ T2)
+    lam = wt * mu / (wt * mu).sum()
+    eps = 1.0 - albedo
+    ys = np.pi * eps * planck(lambda_um, surfaceTemp) * lam
+    Rs = albedo * np.outer(lam, np.ones(mu.size))
+    Ds = np.linalg.solve(I - Rb @ Rs, Sd + Rb @ ys)
+    Us = ys + Rs @ Ds
+    fup, fdn = (Su + Tb @ Us).sum(), Ds.sum()
+    eAtm = sum(4.0 * np.pi * planck(lambda_um, t) * (1.0 - o) * tau for tau, o, t in layers)
+    eSfc = ys.sum()
+    tot = eAtm + eSfc
+    return eAtm / tot, fup / tot, fdn / tot, (eSfc - fup - eps * fdn) / tot

@@ -289,6 +289,55 @@ def test_local_estimate_radiances_match_adding_doubling(tau, omega, mu0, albedo,
     assert (np.abs(m - want) < 4.0 * e + 1e-3 * want).all(), (m, want, e)
 
 
+@pytest.mark.parametrize("arithmetic", [MCB_ARITH_FAST, MCB_ARITH_REFERENCE], ids=["fast", "reference"])
+@pytest.mark.parametrize("name,layers,sfcTemp,albedo", [
+    ("lapse", [(1.0, 0.3, 230.0, 2), (2.0, 0.6, 260.0, 3), (1.5, 0.2, 285.0, 3)], 300.0, 0.1),
+    ("warm_layer_aloft", [(0.5, 0.0, 300.0, 2), (0.0, 0.0, 250.0, 2), (3.0, 0.9, 250.0, 4)], 270.0, 0.3)])
+def test_thermal_fluxes_match_adding_doubling_with_sources(name, layers, sfcTemp, albedo, arithmetic):
+    """Both CUDA kernels' thermal source against doubling + adding WITH SOURCES (tests/adding_doubling.py::
+    thermal_fluxes): layers of different temperature, optical depth and albedo (one empty) over an emitting, partly
+    reflecting surface; the emission CDF is built on the device.  Share of the atmosphere in the emitted power to 1e-9,
+    flux leaving the top / reaching the surface / absorbed minus emitted within 4 sigma + 2e-4 at 4e6 (1e6) photons."""
+    from adding_doubling import table_moments, thermal_fluxes
+    from mcbrat3d_b200.emissionAndBroadBandWeights import Weights, emission_weighting
+    from mcbrat3d_b200.opticalProperties import Domain
+    from mcbrat3d_b200.scatteringPhaseFunctions import henyeyGreenstein, new_PhaseFunctionTable
+    n_, delta, lam = 8, 0.125, 10.0
+    edges = delta * np.arange(n_ + 1, dtype=np.float64)
+    temps = np.zeros((n_, n_, n_)); ext = np.zeros((n_, n_, n_)); ssa = np.zeros((n_, n_, n_)); idx = np.zeros((n_, n_, n_), np.int32)
+    k = n_
+    for tau, omega, T, cells in layers:
+        k -= cells
+        temps[k:k + cells] = T; ext[k:k + cells] = tau / (cells * delta); ssa[k:k + cells] = omega
+        idx[k:k + cells] = 1 if tau > 0 else 0
+    dom = Domain(edges, edges, edges, temps=temps, surfaceAlbedo=albedo, lambda_um=lam)
+    dom.addOpticalComponent("cloud", ext, ssa, idx, new_PhaseFunctionTable([henyeyGreenstein(0.6, 32)], key=[1.0]))
+    dom.getOpticalPropertiesByComponent()
+    dom.tabulateInversePhaseFunctions(10001)
+    want = np.array(thermal_fluxes([(t, w, T) for t, w, T, _ in layers], table_moments(dom.inversePhaseFunctions[0]), lam,
+                                   sfcTemp, albedo, nStreams=96))
+    n, nb = (250000, 16) if arithmetic == MCB_ARITH_FAST else (62500, 16)
+    g_ = new_Integrator(dom)
+    try:
+        specifyParameters(g_, minInverseTableSize=10001, arithmetic=arithmetic, LW_flag=1.0)
+        w = Weights()
+        emission_weighting(dom, w, sfcTemp, thisIntegrator=g_)
+        assert abs(w.fracAtmsPower - want[0]) < 1e-9
+        rs = new_RandomNumberSequence([10, 1, 0])
+        rows = []
+        for b in range(nb):
+            ps = new_PhotonStream(theseWeights=w, numberOfPhotons=n, randomNumbers=rs)
+            computeRadiativeTransfer(g_, dom, rs, ps, n)
+            r = reportResults(g_, meanFluxUp=True, meanFluxDown=True, meanFluxAbsorbed=True)
+            rows.append([float(r["meanFluxUp"]), float(r["meanFluxDown"]), float(r["meanFluxAbsorbed"])])
+        assert getCounters(g_)["bad"] == 0
+    finally:
+        finalize_Integrator(g_)
+    rows = np.array(rows)
+    m, e = rows.mean(axis=0), rows.std(axis=0, ddof=1) / np.sqrt(nb)
+    assert (np.abs(m - want[1:]) < 4.0 * e + 2e-4).all(), (m, want[1:], e)
+
+
 @pytest.mark.parametrize("views", [False, True], ids=["flux", "le"])
 def test_result_independent_of_batch_split(views):
     """Counter-based RNG keyed by the global photon id: one batch of N equals two accumulated

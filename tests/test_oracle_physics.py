@@ -250,3 +250,42 @@ def test_layered_slab_fluxes_match_adding(orc, name, layers):
     for key, w in zip(("meanFluxUpStats", "meanFluxDownStats", "meanFluxAbsorbedStats"), want):
         m, e = _fin(orc, st, key, tot, nb)
         assert abs(m[0] - w) < 4.0 * e[0] + 2e-4, (key, m[0], w, e[0])
+
+
+@pytest.mark.parametrize("name,layers,sfcTemp,albedo", [
+    ("isothermal", [(5.0, 0.5, 290.0, 8)], 290.0, 0.0),
+    ("lapse", [(1.0, 0.3, 230.0, 2), (2.0, 0.6, 260.0, 3), (1.5, 0.2, 285.0, 3)], 300.0, 0.1),
+    ("warm_layer_aloft", [(0.5, 0.0, 300.0, 2), (0.0, 0.0, 250.0, 2), (3.0, 0.9, 250.0, 4)], 270.0, 0.3)])
+def test_thermal_fluxes_match_adding_doubling_with_sources(orc, name, layers, sfcTemp, albedo):
+    """The thermal source (emission_weighting EMI:424-550, new_PhotonStream_BBEmission ILL:431-522, the -1 emission
+    bookkeeping INT:505-508) against doubling + adding WITH SOURCES (tests/adding_doubling.py::thermal_fluxes): layers of
+    different temperature, optical depth and albedo (one of them empty) over an emitting, partly reflecting surface.
+    Checked: the share of the atmosphere in the emitted power, the flux leaving the top, the flux reaching the surface
+    and absorbed-minus-emitted in the atmosphere, all per emitted photon.  layers: (tau, omega, T, cells), TOP FIRST."""
+    from adding_doubling import table_moments, thermal_fluxes
+    from mcbrat3d_b200.opticalProperties import Domain
+    from mcbrat3d_b200.scatteringPhaseFunctions import henyeyGreenstein, new_PhaseFunctionTable
+    n, delta, lam = 8, 0.125, 10.0
+    edges = delta * np.arange(n + 1, dtype=np.float64)
+    temps = np.zeros((n, n, n)); ext = np.zeros((n, n, n)); ssa = np.zeros((n, n, n)); idx = np.zeros((n, n, n), np.int32)
+    k = n
+    for tau, omega, T, cells in layers:                                # z index 0 is the bottom layer
+        k -= cells
+        temps[k:k + cells] = T; ext[k:k + cells] = tau / (cells * delta); ssa[k:k + cells] = omega
+        idx[k:k + cells] = 1 if tau > 0 else 0
+    assert k == 0
+    d = Domain(edges, edges, edges, temps=temps, surfaceAlbedo=albedo, lambda_um=lam)
+    d.addOpticalComponent("cloud", ext, ssa, idx, new_PhaseFunctionTable([henyeyGreenstein(0.6, 32)], key=[1.0]))
+    d.getOpticalPropertiesByComponent()
+    od = orc.OracleDomain(d, tableSize=10001)
+    frac, cdf, flux = od.emission_weighting(d.temps, d.lambda_um, sfcTemp)
+    d.tabulateInversePhaseFunctions(10001)
+    want = thermal_fluxes([(t, w, T) for t, w, T, _ in layers], table_moments(d.inversePhaseFunctions[0]), lam, sfcTemp,
+                          albedo, nStreams=96)
+    assert abs(frac - want[0]) < 1e-9
+    og = orc.OracleIntegrator(od, LW_flag=1.0)
+    nb = 40
+    tot, st = og.run_batches(nb, 5000, source=1, fracAtmsPower=frac, voxelCDF=cdf)
+    for key, w in zip(("meanFluxUpStats", "meanFluxDownStats", "meanFluxAbsorbedStats"), want[1:]):
+        m, e = _fin(orc, st, key, tot, nb)
+        assert abs(m[0] - w) < 4.0 * e[0] + 3e-4, (key, m[0], w, e[0])
