@@ -289,3 +289,24 @@ def test_thermal_fluxes_match_adding_doubling_with_sources(orc, name, layers, sf
     for key, w in zip(("meanFluxUpStats", "meanFluxDownStats", "meanFluxAbsorbedStats"), want[1:]):
         m, e = _fin(orc, st, key, tot, nb)
         assert abs(m[0] - w) < 4.0 * e[0] + 3e-4, (key, m[0], w, e[0])
+
+
+@pytest.mark.parametrize("rr", [False, True], ids=["plain", "rr"])
+@pytest.mark.parametrize("tau,omega,g,mu0,albedo", [(2.0, 0.9, 0.6, 0.5, 0.3), (5.0, 0.99, 0.85, 0.7, 0.0)])
+def test_nadir_radiance_with_anisotropic_scattering_matches_adding_doubling(orc, tau, omega, g, mu0, albedo, rr):
+    """The view along the vertical needs only the azimuthally averaged field, so the solver also pins the local estimate
+    for a forward-peaked phase function (forward-table look-up by scattering angle, INT:1834-1873).  The photon loop
+    scatters by the law the inverse table encodes while the local estimate evaluates the analytic function, so the
+    solver is run with both sets of Legendre moments and their difference is added to the tolerance."""
+    from adding_doubling import slab_fluxes, table_moments
+    d, case = domains.homogeneous_slab(ssa=omega, tau=tau, albedo=albedo, g=g, n=8, delta=0.125)
+    og = orc.OracleIntegrator(orc.OracleDomain(d, tableSize=10001, forward=True), useRussianRouletteForIntensity=int(rr), zetaMin=0.3)
+    og.set_views([1.0], [0.0])
+    nb = 30
+    tot, st = og.run_batches(nb, 4000, solarMu=mu0, solarAzimuth=0.0, iseed=10, rank=1, thread=0)
+    m, e = orc.finalise(st["radianceStats"], 1.0, tot, nb)
+    got, err = m.mean(), np.sqrt((e ** 2).sum()) / e.size
+    d.tabulateInversePhaseFunctions(10001)
+    a = slab_fluxes(tau, omega, table_moments(d.inversePhaseFunctions[0]), mu0, albedo, nStreams=96, muOut=[1.0])[3][0]
+    b = slab_fluxes(tau, omega, g ** np.arange(64), mu0, albedo, nStreams=96, muOut=[1.0])[3][0]
+    assert abs(got - 0.5 * (a + b)) < 4.0 * err + abs(a - b) + 1e-3 * a, (got, a, b, err)
