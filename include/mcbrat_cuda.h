@@ -47,8 +47,20 @@ typedef struct {
   float   maxIntensityContribution;         /* INT:95                                          */
   float   LW_flag;                          /* INT:68; > 0 switches on emission bookkeeping    */
   int32_t arithmetic;                       /* MCB_ARITH_FAST (default) | MCB_ARITH_REFERENCE  */
-  int32_t reserved[5];
+  /* Measurement knobs of the throughput kernels -- not part of the reference's interface.  0 = the
+   * library's own choice (what every production call uses); tests and profiling scripts set them to
+   * compare variants inside one process.  They never change results beyond f64 summation order.      */
+  int32_t tuneKernel;                       /* MCB_KERNEL_PARK | MCB_KERNEL_POOL (flux-only, uniform grids)   */
+  int32_t tuneLayout;                       /* MCB_LAYOUT_LINEAR | MCB_LAYOUT_BRICKS extinction field         */
+  int32_t tuneBlocksPerSM;                  /* resident CTAs per SM of the flux kernels                       */
+  int32_t tuneParkThreshold;                /* parked lanes that trigger an event phase (park kernel)         */
+  int32_t tuneLeCarry;                      /* view rays parked between queue rounds: < 0 off, > 0 threshold  */
+  int32_t tuneExtMask;                      /* occupancy bitmap of the extinction field: < 0 off, > 0 on      */
+  int32_t tuneBurst;                        /* cells per marching burst of the pool kernel (4 or 8)           */
+  int32_t reserved[3];
 } mcb_options;
+enum { MCB_KERNEL_PARK = 1, MCB_KERNEL_POOL = 2 };
+enum { MCB_LAYOUT_LINEAR = 1, MCB_LAYOUT_BRICKS = 2 };
 
 /* Event counters of the last batch (algorithmic-bytes accounting). */
 typedef struct {

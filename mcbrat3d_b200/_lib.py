@@ -29,7 +29,15 @@ class mcb_options(C.Structure):
                 ("zetaMin", C.c_float), ("useHybridPhaseFunsForIntenCalcs", C.c_int32),
                 ("numOrdersOrigPhaseFunIntenCalcs", C.c_int32), ("limitIntensityContributions", C.c_int32),
                 ("maxIntensityContribution", C.c_float), ("LW_flag", C.c_float),
-                ("arithmetic", C.c_int32), ("reserved", C.c_int32 * 5)]
+                ("arithmetic", C.c_int32),
+                # measurement knobs (0 = the library's own choice): see include/mcbrat_cuda.h
+                ("tuneKernel", C.c_int32), ("tuneLayout", C.c_int32), ("tuneBlocksPerSM", C.c_int32),
+                ("tuneParkThreshold", C.c_int32), ("tuneLeCarry", C.c_int32), ("tuneExtMask", C.c_int32),
+                ("tuneBurst", C.c_int32), ("reserved", C.c_int32 * 3)]
+
+
+MCB_KERNEL_PARK, MCB_KERNEL_POOL = 1, 2
+MCB_LAYOUT_LINEAR, MCB_LAYOUT_BRICKS = 1, 2
 
 
 class mcb_component(C.Structure):

@@ -58,6 +58,7 @@ struct mcb_handle {
   bool haveGrid = false, haveOptics = false, haveSource = false;
   bool haveTemps = false;                        // dTemps holds the temperatures of the current grid
   bool packedLin = false, packedBrk = false;     // which layouts of the extinction field hold the current optics
+  int maskKnob = 0;                              // mcb_options.tuneExtMask the packed field was set up with
   bool haveInv[MCB_MAX_COMP] = {false}, haveFwd[MCB_MAX_COMP] = {false};
   std::vector<double> xE, yE, zE;
   std::map<void **, size_t> slotBytes;    // capacity of every re-stageable slot (reused while large enough)
@@ -282,6 +283,7 @@ int mcb_set_grid(mcb_handle *h, int nx, int ny, int nz,
 }
 
 static int finish_optics(mcb_handle *h, int nc, double albedo, bool zeroFlags = true);
+static int setup_packed_field(mcb_handle *h);
 
 // the thermal source's CDF is in HBM: derive the compact column weights and publish the pointers
 static int finish_thermal_source(mcb_handle *h, double fracAtmsPower) {
@@ -302,6 +304,32 @@ static int pack_field(mcb_handle *h, bool brick) {
   CK(h, cudaGetLastError());
   (brick ? h->packedBrk : h->packedLin) = true;
   return 0;
+}
+
+// Buffers of the packed single-precision extinction field (both layouts), the decision whether it is marched through
+// an occupancy bitmap, and the packing of the layout the next launch reads (the other one on demand, run()).
+// Occupancy bitmap: only for fields that do not stay L2-resident (default: padded field > 48 MB; the C3 field,
+// 15.5 MB, is served by L2 and gains nothing); mcb_options.tuneExtMask forces it off / on (measurements, tests).
+static int setup_packed_field(mcb_handle *h) {
+  DevDomain &P = h->P;
+  const size_t padded = (size_t)P.brk.padded;          // the larger of the two layouts
+  if (reserve(h, &h->dExt32, sizeof(float) * (size_t)P.lin.padded)) return 1;
+  if (reserve(h, &h->dExtBrick, sizeof(float) * (size_t)P.brk.padded)) return 1;
+  P.lin.ext = (const float *)h->dExt32 + P.lin.origin;
+  P.brk.ext = (const float *)h->dExtBrick + P.brk.origin;
+  const int knob = P.opt.tuneExtMask;
+  const bool useMask = knob != 0 ? knob > 0 : sizeof(float) * padded > ((size_t)48 << 20);
+  P.lin.mask = P.brk.mask = nullptr; P.layerExt = nullptr;
+  if (useMask) {
+    if (reserve(h, &h->dExtMask, sizeof(uint32_t) * ((padded + 31) / 32))) return 1;
+    if (reserve(h, &h->dExtMaskBrick, sizeof(uint32_t) * ((padded + 31) / 32))) return 1;
+    if (reserve(h, &h->dLayerExt, sizeof(float) * (size_t)(P.nz + 2 * MCB_GHOST + 2))) return 1;
+    P.lin.mask = (const uint32_t *)h->dExtMask; P.brk.mask = (const uint32_t *)h->dExtMaskBrick;
+    P.layerExt = (const float *)h->dLayerExt;
+  }
+  h->maskKnob = knob;
+  h->packedLin = h->packedBrk = false;
+  return pack_field(h, mcb_fast_reads_bricks(P));
 }
 
 int mcb_set_optics(mcb_handle *h, int nc, const double *totalExt, const double *cumExt,
@@ -329,37 +357,15 @@ int mcb_set_optics(mcb_handle *h, int nc, const double *totalExt, const double *
 static int finish_optics(mcb_handle *h, int nc, double albedo, bool zeroFlags) {
   DevDomain &P = h->P;
   const size_t cells = (size_t)P.nx * P.ny * P.nz;
-  const size_t padded = (size_t)P.brk.padded;          // the larger of the two layouts
-  if (reserve(h, &h->dExt32, sizeof(float) * (size_t)P.lin.padded)) return 1;
-  if (reserve(h, &h->dExtBrick, sizeof(float) * (size_t)P.brk.padded)) return 1;
   int recShift = 0;                                   // event record: (nc-1) + nc + ceil(nc/2) words, padded to 2^recShift
   while ((1 << recShift) < 2 * nc - 1 + (nc + 1) / 2) ++recShift;
   if (reserve(h, &h->dRec, sizeof(uint32_t) * (cells << recShift))) return 1;
   P.nc = nc; P.albedo = albedo;
   P.totalExt = (const double *)h->dTotalExt; P.cumExt = (const double *)h->dCumExt;
   P.ssa = (const double *)h->dSsa; P.phaseIdx = (const int32_t *)h->dPhaseIdx;
-  P.lin.ext = (const float *)h->dExt32 + P.lin.origin;
-  P.brk.ext = (const float *)h->dExtBrick + P.brk.origin;
   P.rec = (const uint32_t *)h->dRec; P.recShift = recShift;
-  // Occupancy bitmap: only for fields that do not stay L2-resident (default: padded field > 48 MB; the C3 field,
-  // 15.5 MB, is served by L2 and gains nothing).  MCB_EXT_MASK=0/1 forces it off/on (measurements, tests).
-  {
-    const char *e = getenv("MCB_EXT_MASK");              // read at every staging, so one process can compare both
-    const int maskEnv = e ? atoi(e) : -1;
-    const bool useMask = maskEnv >= 0 ? maskEnv > 0 : sizeof(float) * padded > ((size_t)48 << 20);
-    P.lin.mask = P.brk.mask = nullptr; P.layerExt = nullptr;
-    if (useMask) {
-      if (reserve(h, &h->dExtMask, sizeof(uint32_t) * ((padded + 31) / 32))) return 1;
-      if (reserve(h, &h->dExtMaskBrick, sizeof(uint32_t) * ((padded + 31) / 32))) return 1;
-      if (reserve(h, &h->dLayerExt, sizeof(float) * (size_t)(P.nz + 2 * MCB_GHOST + 2))) return 1;
-      P.lin.mask = (const uint32_t *)h->dExtMask; P.brk.mask = (const uint32_t *)h->dExtMaskBrick;
-      P.layerExt = (const float *)h->dLayerExt;
-    }
-  }
   if (zeroFlags) CK(h, cudaMemsetAsync(h->dFlags, 0, sizeof(int) * 4, h->stream));
-  // the layout the next launch will read is packed now (with the argument checks); the other one on demand (run())
-  h->packedLin = h->packedBrk = false;
-  if (pack_field(h, mcb_fast_reads_bricks(P))) return 1;
+  if (setup_packed_field(h)) return 1;
   mcb_launch_pack_records(P, (uint32_t *)h->dRec, h->dFlags, h->numSMs, h->stream);
   CK(h, cudaGetLastError());
   int flags4[4] = {0, 0, 0, 0};
@@ -594,6 +600,10 @@ int mcb_set_options(mcb_handle *h, const mcb_options *o) {
   if (o->zetaMin < 0.0f) FAIL(h, "specifyParameters: zetaMin must be >= 0.");
   if (o->arithmetic != MCB_ARITH_FAST && o->arithmetic != MCB_ARITH_REFERENCE) FAIL(h, "mcb_set_options: unknown arithmetic mode");
   h->P.opt = *o;
+  if (h->haveOptics && o->tuneExtMask != h->maskKnob) {          // the knob changed after staging: pack again
+    CK(h, cudaSetDevice(h->device));
+    if (setup_packed_field(h) || settle(h)) return 1;
+  }
   return 0;
 }
 
@@ -709,9 +719,9 @@ static int ensure_tallies(mcb_handle *h) {
   P.offPhotons = P.offExcess + (long long)P.nDir * (P.nc + 1);
   const long long need = P.offPhotons + 1;
   if (need != h->nTally || !h->dTally) {
-    if (h->dTally) cudaFree(h->dTally);
-    h->dTally = nullptr;
-    CK(h, cudaMalloc((void **)&h->dTally, sizeof(double) * need));
+    // grow-only (reserve keeps the allocation while it is large enough): callers alias this buffer for the
+    // cross-rank reduce (mcb_tally_buffer), so it must not move when views or components are switched off and on
+    if (reserve(h, (void **)&h->dTally, sizeof(double) * (size_t)need)) return 1;
     CK(h, cudaMemsetAsync(h->dTally, 0, sizeof(double) * need, h->stream));
     h->nTally = need;
   }
@@ -726,6 +736,9 @@ static int check_ready(mcb_handle *h) {
     if (!h->haveInv[c]) FAIL(h, "computeRadiativeTransfer: no inverse phase function table for component %d", c + 1);
     if (h->P.nDir > 0 && !h->haveFwd[c]) FAIL(h, "computeRadiativeTransfer: no forward phase function table for component %d", c + 1);
   }
+  // the local-estimation queue of the throughput kernel packs cell indices into 16-bit fields (mcb_fast.cu)
+  if (h->P.nDir > 0 && (h->P.nx > 65535 || h->P.ny > 65535 || h->P.nz > 65535))
+    FAIL(h, "computeRadiativeTransfer: intensity calculations support at most 65535 cells per axis");
   return 0;
 }
 
@@ -983,11 +996,15 @@ int mcb_run_trace(mcb_handle *h, int64_t nPhotons, const float *rn, int64_t rnSt
   if (ensure_tallies(h)) return 1;
   CK(h, cudaMemsetAsync(h->dTally, 0, sizeof(double) * h->nTally, h->stream));
   CK(h, cudaMemsetAsync(h->dCounters, 0, sizeof(unsigned long long) * 32, h->stream));
-  float *dRn = nullptr; mcb_event *dEv = nullptr; int *dCount = nullptr;
+  struct DeviceScratch {                               // freed on every return path
+    void *p = nullptr;
+    ~DeviceScratch() { if (p) cudaFree(p); }
+  } sRn, sEv, sCount;
   const size_t nRn = (size_t)nPhotons * rnStride, nEv = (size_t)nPhotons * maxEventsPerPhoton;
-  CK(h, cudaMalloc((void **)&dRn, sizeof(float) * nRn));
-  CK(h, cudaMalloc((void **)&dEv, sizeof(mcb_event) * nEv));
-  CK(h, cudaMalloc((void **)&dCount, sizeof(int) * nPhotons));
+  CK(h, cudaMalloc(&sRn.p, sizeof(float) * nRn));
+  CK(h, cudaMalloc(&sEv.p, sizeof(mcb_event) * nEv));
+  CK(h, cudaMalloc(&sCount.p, sizeof(int) * nPhotons));
+  float *dRn = (float *)sRn.p; mcb_event *dEv = (mcb_event *)sEv.p; int *dCount = (int *)sCount.p;
   CK(h, cudaMemcpyAsync(dRn, rn, sizeof(float) * nRn, cudaMemcpyHostToDevice, h->stream));
   CK(h, cudaMemsetAsync(dCount, 0, sizeof(int) * nPhotons, h->stream));
   mcb_launch_trace(h->P, nPhotons, dRn, rnStride, dEv, maxEventsPerPhoton, dCount, h->stream);
@@ -997,7 +1014,6 @@ int mcb_run_trace(mcb_handle *h, int64_t nPhotons, const float *rn, int64_t rnSt
   CK(h, cudaMemcpyAsync(count.data(), dCount, sizeof(int) * nPhotons, cudaMemcpyDeviceToHost, h->stream));
   CK(h, cudaMemcpyAsync(ev.data(), dEv, sizeof(mcb_event) * nEv, cudaMemcpyDeviceToHost, h->stream));
   CK(h, cudaStreamSynchronize(h->stream));
-  cudaFree(dRn); cudaFree(dEv); cudaFree(dCount);
   int64_t total = 0;
   for (int64_t p = 0; p < nPhotons; ++p) {
     const int n = count[p] < maxEventsPerPhoton ? count[p] : maxEventsPerPhoton;
@@ -1018,13 +1034,12 @@ int mcb_run_trace(mcb_handle *h, int64_t nPhotons, const float *rn, int64_t rnSt
 int mcb_debug_philox(mcb_handle *h, uint64_t seed, uint64_t photon, int n, uint32_t *out) {
   if (!h || !out || n <= 0) return 1;
   CK(h, cudaSetDevice(h->device));
-  uint32_t *d = nullptr;
-  CK(h, cudaMalloc((void **)&d, sizeof(uint32_t) * n));
+  if (reserve(h, &h->dScratch, sizeof(uint32_t) * (size_t)n)) return 1;
+  uint32_t *d = (uint32_t *)h->dScratch;
   mcb_launch_philox_kat(seed, photon, n, d, h->stream);
   CK(h, cudaGetLastError());
   CK(h, cudaMemcpyAsync(out, d, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost, h->stream));
   CK(h, cudaStreamSynchronize(h->stream));
-  cudaFree(d);
   return 0;
 }
 

@@ -74,9 +74,12 @@ struct Rng {
       a += 0x9E3779B9u; b += 0xBB67AE85u;
     }
     blk++;
-    // f32 in [0,1] built from 32 bits (RNG:286-300)
-    return make_float4(__uint2float_rn(x0) * 2.3283064365386963e-10f, __uint2float_rn(x1) * 2.3283064365386963e-10f,
-                       __uint2float_rn(x2) * 2.3283064365386963e-10f, __uint2float_rn(x3) * 2.3283064365386963e-10f);
+    // f32 built from 32 bits like RNG:286-300, but on [0,1): the scale is the float just below 2^-32, so the 128
+    // largest integers (which round to 2^32) give 1 - 2^-24 instead of 1.  The closed upper end of the reference's
+    // generator only matters to its bit-exact traces (mcb_reference.cu); here a draw of exactly 1 could pick a trailing
+    // component of zero extinction (cumExt = 1) whose phase-function entry is 0.
+    const float S = __uint_as_float(0x2f7fffffu);
+    return make_float4(__uint2float_rn(x0) * S, __uint2float_rn(x1) * S, __uint2float_rn(x2) * S, __uint2float_rn(x3) * S);
   }
 };
 
@@ -386,6 +389,8 @@ struct Counts { unsigned crossings, scatters, leRays, leCrossings; };
 #ifndef MCB_LE_OCC
 #define MCB_LE_OCC 5             // CTAs per SM of the local-estimation kernels: 96 registers, no spills (6: 80 registers, 314 B of spills, 8 % slower)
 #endif
+// cell indices travel as 16-bit fields of the request / parked-ray words (decoded unsigned): grids with views are
+// limited to 65535 cells per axis, which mcb_api.cu enforces before the launch
 #define LE_WORDS 13
 #define LE_CARRY_WORDS 16      // a view ray parked between two rounds of the queue (see le_run)
 enum { LE_PX = 0, LE_PY, LE_PZ, LE_DX, LE_DY, LE_DZ, LE_W, LE_IXY, LE_IZO, LE_COMP, LE_C0, LE_C1, LE_BLK };
@@ -433,7 +438,7 @@ __device__ void le_run(const DevDomain &P, const Grid &G, const Tally &T, uint32
       ext = carry[7 * 32 + lane]; tgt = carry[8 * 32 + lane]; w = carry[9 * 32 + lane]; npf = carry[10 * 32 + lane];
       tauFree = carry[11 * 32 + lane]; uTest = carry[12 * 32 + lane];
       const int ixy = __float_as_int(carry[13 * 32 + lane]);
-      r.ix = ixy & 0xffff; r.iy = ixy >> 16;
+      r.ix = ixy & 0xffff; r.iy = (int)((uint32_t)ixy >> 16);
       comps = __float_as_int(carry[14 * 32 + lane]);
       r.dx = P.viewDir[3 * dir]; r.dy = P.viewDir[3 * dir + 1]; r.dz = P.viewDir[3 * dir + 2];
       r.rx = safe_rcp(r.dx); r.ry = safe_rcp(r.dy); r.rz = safe_rcp(r.dz);
@@ -452,8 +457,8 @@ __device__ void le_run(const DevDomain &P, const Grid &G, const Tally &T, uint32
         const float vx = P.viewDir[3 * dir], vy = P.viewDir[3 * dir + 1], vz = P.viewDir[3 * dir + 2];
         const int ixy = __float_as_int(sle[LE_IXY * 32 + s]), izo = __float_as_int(sle[LE_IZO * 32 + s]);
         comps = __float_as_int(sle[LE_COMP * 32 + s]);
-        const int component = (comps & 0xff) - 1, order = izo >> 16;
-        r.ix = ixy & 0xffff; r.iy = ixy >> 16; r.iz = izo & 0xffff;
+        const int component = (comps & 0xff) - 1, order = (int)((uint32_t)izo >> 16);
+        r.ix = ixy & 0xffff; r.iy = (int)((uint32_t)ixy >> 16); r.iz = izo & 0xffff;
         w = sle[LE_W * 32 + s];
         if (component == 0) {
           npf = 1.0f / PI32;                                                       // INT:1694
@@ -678,6 +683,7 @@ batch_kernel(const __grid_constant__ DevDomain P, long long nPhotons, uint64_t s
           pidx = (int)(((comp - 1) & 1) ? (pw >> 16) : (pw & 0xffffu));
         }
       }
+      pidx = max(pidx, 1);                   // entry 0 marks a cell the component is absent from: never index before the table
       if (ssa < 1.0f) {                                                        // INT:765-771
         const float absorbed = w * (1.0f - ssa);
         add_vol(P, T, cell, absorbed);                     // fluxAbsorbed = column sum of this tally (column_absorption_kernel)
@@ -696,7 +702,11 @@ batch_kernel(const __grid_constant__ DevDomain P, long long nPhotons, uint64_t s
     }
     if (LE && P.nDir > 0 && P.opt.LW_flag > 0.0f) {      // thermal runs: births post too (below), one slot per lane
       const unsigned pm = __ballot_sync(FULL, posted);
-      if (pm) le_run<REG, WIDE, MASK>(P, G, T, k0, k1, pm, sle, leQueue, lane, cnt, r, ext, tau, state, leCarry);
+      // This round runs in the MIDDLE of the event phase: a marching lane must not take its own photon along (it could
+      // come back at an event whose tallies, roulette and new leg this phase has already passed), so the queue sees
+      // every lane as parked.
+      int parked = ST_DEAD;
+      if (pm) le_run<REG, WIDE, MASK>(P, G, T, k0, k1, pm, sle, leQueue, lane, cnt, r, ext, tau, parked, leCarry);
       posted = false;
     }
     // ---- finished lanes take the next photons: one atomic per warp (getNextPhoton, ILL:561-590) ----
@@ -730,6 +740,7 @@ batch_kernel(const __grid_constant__ DevDomain P, long long nPhotons, uint64_t s
       float uTau = u.z;
       if (state == ST_BORN) {
         float x01, y01, z01;
+        int bi = -1, bj = 0, bk = 0;                                           // birth cell of an atmospheric emission
         w = 1.0f; order = 0;
         if (P.source == 0) {                                                   // ILL:88-96
           x01 = u.x; y01 = u.y; z01 = 1.0f - FLT_EPSILON;
@@ -754,6 +765,7 @@ batch_kernel(const __grid_constant__ DevDomain P, long long nPhotons, uint64_t s
             z01 = ((float)(ik - 1) + fminf(fmaxf(v2.x, 1e-6f), 1.0f - 1e-6f)) / (float)P.nz;
             x01 = ((float)(ii - 1) + fminf(v2.y, 1.0f - 1e-6f)) / (float)P.nx;
             y01 = ((float)(ij - 1) + fminf(v2.z, 1.0f - 1e-6f)) / (float)P.ny;
+            bi = ii - 1; bj = ij - 1; bk = ik - 1;           // the sampled cell itself: (cell + offset) / n may round across a face
             mu = 1.0f - 2.0f * v.x;                                            // ILL:507-509 retries on mu ~ 0
             if (!(fabsf(mu) > 2.0f * TINY32)) mu = 1.0e-30f;
             phi = v.y * 2.0f * PI32;
@@ -779,6 +791,9 @@ batch_kernel(const __grid_constant__ DevDomain P, long long nPhotons, uint64_t s
             pz = G.sz[r.iz] + (zs - (float)r.iz) * (G.sz[r.iz + 1] - G.sz[r.iz]);
           }
         }
+        // uniform grids: unit-square fraction and cell coincide.  On stretched grids the reference maps the fraction
+        // linearly into the domain and looks the cell up from the position (INT:478-494), which is kept above.
+        if (REG && bi >= 0) { r.ix = bi; r.iy = bj; r.iz = bk; }
         if (P.opt.LW_flag > 0.0f) {                                            // INT:504-542
           if (pz > 0.0f) {
             add_vol(P, T, r.ix + P.nx * (r.iy + P.ny * r.iz), -1.0f);
@@ -903,8 +918,6 @@ __global__ void philox_kat_kernel(uint64_t seed, uint64_t photon, int n, uint32_
 
 }  // namespace mcbfast
 
-#include <cstdlib>
-
 template <bool REG, bool WIDE, int MINBLOCKS, int BURST, bool LE, bool MASK, bool BRICK>
 static void launch(const DevDomain &P, long long nPhotons, uint64_t seed, uint64_t firstPhotonId, int numSMs,
                    unsigned long long *workCounter, cudaStream_t stream) {
@@ -924,8 +937,7 @@ static void launch(const DevDomain &P, long long nPhotons, uint64_t seed, uint64
   // view rays still in flight when a round of the queue ends with no tasks left: at most `carry` of them are parked
   // (le_run).  That pays when a ray can be much longer than a burst -- grids deeper than 64 layers; on shallow grids
   // (the step cloud: 32 layers, 3.6 cells per ray) the 8 KB per block it takes away from L1 cost 10 %, so it is off (-1)
-  const char *ec = getenv("MCB_LE_CARRY");               // measurement knob: -1 off, n >= 0 threshold
-  const int carry = ec ? atoi(ec) : (P.nz > 64 ? 12 : -1);
+  const int carry = P.opt.tuneLeCarry < 0 ? -1 : P.opt.tuneLeCarry > 0 ? P.opt.tuneLeCarry : (P.nz > 64 ? 12 : -1);
   if (LE) {
     plan.leOff = off; plan.leStride = LE_WORDS * 32 + 64 + (carry >= 0 ? LE_CARRY_WORDS * 32 : 0);
     off += (THREADS / 32) * plan.leStride;
@@ -941,18 +953,15 @@ static void launch(const DevDomain &P, long long nPhotons, uint64_t seed, uint64
   const int blocks = (int)(want < cap ? want : cap);
   // lanes parked before an event phase runs: 16 for flux runs; with local estimation the event phase is long and
   // shared by all 32 lanes, so waiting for 24 pays (C3 + 5 views: 16 -> 4.0e7, 24 -> 4.3e7 photons/s)
-  static int parkEnv = -2;
-  if (parkEnv == -2) { const char *e = getenv("MCB_PARK_THRESHOLD"); parkEnv = e ? atoi(e) : -1; }
-  int park = parkEnv > 0 ? parkEnv : (LE ? 24 : 16);
+  int park = P.opt.tuneParkThreshold > 0 ? P.opt.tuneParkThreshold : (LE ? 24 : 16);
   if (park > 32) park = 32;
   kernel<<<blocks, THREADS, smem, stream>>>(P, nPhotons, seed, firstPhotonId, workCounter, park, carry, plan);
 }
 
 // which layout of the extinction field the dispatcher below reads (the API packs that one)
 bool mcb_fast_reads_bricks(const DevDomain &P) {
-  const char *el = getenv("MCB_LAYOUT");
   const bool wide = P.nx >= MCB_GHOST && P.ny >= MCB_GHOST;
-  return P.uniform && wide && P.nDir == 0 && !(el && el[0] == 'l');
+  return P.uniform && wide && P.nDir == 0 && P.opt.tuneLayout != MCB_LAYOUT_LINEAR;
 }
 
 void mcb_launch_fast_batch(const DevDomain &P, long long nPhotons, uint64_t seed, uint64_t firstPhotonId,
@@ -964,9 +973,8 @@ void mcb_launch_fast_batch(const DevDomain &P, long long nPhotons, uint64_t seed
   //   * local estimation: x-fastest field, 80 registers = 6 CTAs/SM (a second ray per lane; bricks cost it 10 %);
   //   * fields too large for L2: the occupancy-bitmap variants (flux: 80 registers);
   //   * narrow grids (a period shorter than the ghost shell) and irregular grids: x-fastest field.
-  // MCB_BLOCKS_PER_SM = 6 | 8 and MCB_LAYOUT = linear are measurement knobs for the flux-only kernel.
-  const char *eo = getenv("MCB_BLOCKS_PER_SM"), *el = getenv("MCB_LAYOUT");    // read per launch: tests compare both
-  const int occEnv = eo ? atoi(eo) : -1, linEnv = (el && el[0] == 'l') ? 1 : 0;
+  // mcb_options.tuneBlocksPerSM = 6 | 8 and tuneLayout = MCB_LAYOUT_LINEAR are measurement knobs of the flux-only kernel.
+  const int occEnv = P.opt.tuneBlocksPerSM > 0 ? P.opt.tuneBlocksPerSM : -1, linEnv = P.opt.tuneLayout == MCB_LAYOUT_LINEAR ? 1 : 0;
 #define MCB_GO(REG, WIDE, OCC, LE, MASK, BRICK) \
     launch<REG, WIDE, OCC, 8, LE, MASK, BRICK>(P, nPhotons, seed, firstPhotonId, numSMs, workCounter, stream)
   const bool wide = P.nx >= MCB_GHOST && P.ny >= MCB_GHOST;      // no grid period shorter than the ghost shell

@@ -208,6 +208,9 @@ __global__ void redistribute_excess_kernel(DevDomain P) {
     __syncthreads();
   }
   const double total = part[0];
+  // nothing of this component reached this direction below the cap: the reference divides by the zero sum here
+  // (INT:316-318) and fills the radiance with NaN; the excess stays in intensityExcess instead
+  if (!(total > 0.0)) return;
   for (long long i = threadIdx.x; i < cols; i += blockDim.x) {
     const double add = (byc[i] / total) * excess;
     atomicAdd(&P.tally[P.offInt + i + cols * d], add);   // several components feed one direction

@@ -11,6 +11,8 @@ from typing import Optional
 
 import numpy as np
 
+from .opticalProperties import new_token
+
 
 @dataclass
 class Weights:
@@ -18,6 +20,10 @@ class Weights:
     fracAtmsPower: float = 0.0
     spectrIntgrFlux: float = 0.0                   # W m^-2 (monochromatic, EMI:536-538)
     deviceOwner: Optional[object] = None           # the integrator whose HBM holds the CDF (device-built weights)
+    token: int = 0                                 # staging-cache key: replaced by every emission_weighting call
+
+    def __post_init__(self):
+        self.token = new_token()
 
     @property
     def levelWeights(self):                        # voxelWeights(nx, ny, :)
@@ -63,7 +69,8 @@ def emission_weighting_device(thisDomain, theseWeights: Weights, sfcTemp: float,
     theseWeights.fracAtmsPower = float(frac.value)
     theseWeights.spectrIntgrFlux = float(flux.value)
     theseWeights.deviceOwner = g
-    g._stagedSource = ("bbemission-device", id(theseWeights))
+    theseWeights.token = new_token()
+    g._stagedSource = ("bbemission-device", theseWeights.token)
     return theseWeights.spectrIntgrFlux
 
 
@@ -132,6 +139,7 @@ def emission_weighting(thisDomain, theseWeights: Weights, sfcTemp: float, thisIn
         raise ValueError("emission_weightingNEW: Neither surface nor atmosphere will emitt photons "
                          "since total power is 0. Not a valid solution")
     theseWeights.voxelWeights = np.ascontiguousarray(cdf)
+    theseWeights.token = new_token()
     theseWeights.deviceOwner = None
     theseWeights.spectrIntgrFlux = (atmsPower + sfcPower) / (areaX * areaY * (1000.0 ** 2.0))
     return theseWeights.spectrIntgrFlux

@@ -15,7 +15,8 @@ from typing import Dict, Optional, Sequence
 import numpy as np
 
 from . import _lib
-from ._lib import MCB_ARITH_FAST, MCB_ARITH_REFERENCE, McbError, mcb_counters, mcb_options
+from ._lib import (MCB_ARITH_FAST, MCB_ARITH_REFERENCE, MCB_KERNEL_PARK, MCB_KERNEL_POOL, MCB_LAYOUT_BRICKS,
+                   MCB_LAYOUT_LINEAR, McbError, mcb_counters, mcb_options)
 from .monteCarloIllumination import morePhotonsExist, photonStream
 from .opticalProperties import Domain
 from .RandomNumbersForMC import randomNumberSequence
@@ -110,12 +111,18 @@ def specifyParameters(thisIntegrator: integrator, minForwardTableSize=None, minI
                       hybridPhaseFunWidth: Optional[float] = None, numOrdersOrigPhaseFunIntenCalcs: Optional[int] = None,
                       limitIntensityContributions: Optional[bool] = None, maxIntensityContribution: Optional[float] = None,
                       LW_flag: Optional[float] = None, numComps: Optional[int] = None,
-                      arithmetic: Optional[int] = None, buildTablesOnDevice: Optional[bool] = None) -> None:
+                      arithmetic: Optional[int] = None, buildTablesOnDevice: Optional[bool] = None,
+                      tuneKernel: Optional[int] = None, tuneLayout: Optional[int] = None,
+                      tuneBlocksPerSM: Optional[int] = None, tuneParkThreshold: Optional[int] = None,
+                      tuneLeCarry: Optional[int] = None, tuneExtMask: Optional[int] = None,
+                      tuneBurst: Optional[int] = None) -> None:
     """``specifyParameters`` (INT:1046-1337): same optional arguments, same checks.
 
     ``arithmetic`` is one addition: ``MCB_ARITH_FAST`` (default) or ``MCB_ARITH_REFERENCE``;
     ``buildTablesOnDevice`` the other: the inverse phase-function tables of INV:66-174 are then built by
     ``mcb_build_inverse_table`` in HBM instead of by the NumPy mirror (the default).
+    The ``tune*`` arguments are the measurement knobs of ``mcb_options`` (kernel variant, field layout, occupancy,
+    ...; 0 = the library's own choice): tests and profiling scripts compare variants with them.
     ``surfaceBDRF`` and ``recScatOrd``/``numRecScatOrd`` are not supported (the driver never
     installs a BDRF, INT:667-674; the by-order tallies are commented out in the reference).
     """
@@ -158,6 +165,11 @@ def specifyParameters(thisIntegrator: integrator, minForwardTableSize=None, minI
         o.maxIntensityContribution = float(maxIntensityContribution)
     if LW_flag is not None: o.LW_flag = float(LW_flag)
     if arithmetic is not None: o.arithmetic = int(arithmetic)
+    for name, val in (("tuneKernel", tuneKernel), ("tuneLayout", tuneLayout), ("tuneBlocksPerSM", tuneBlocksPerSM),
+                      ("tuneParkThreshold", tuneParkThreshold), ("tuneLeCarry", tuneLeCarry), ("tuneExtMask", tuneExtMask),
+                      ("tuneBurst", tuneBurst)):
+        if val is not None:
+            setattr(o, name, int(val))
     if buildTablesOnDevice is not None:
         g.buildTablesOnDevice = bool(buildTablesOnDevice)
         g._stagedTables = None
@@ -177,13 +189,13 @@ def specifyParameters(thisIntegrator: integrator, minForwardTableSize=None, minI
 def _stage_domain(g: integrator, d: Domain) -> None:
     """What ``computeRT`` copies out of the domain every batch (INT:434-443) -- staged once."""
     if getattr(d, "deviceOwner", None) is not None:          # assembled in this integrator's HBM (read_SSPTable)
-        key = ("device", id(d))
+        key = ("device", d.token)
         if d.deviceOwner is not g or g._stagedDomain != key:
             raise McbError("computeRadiativeTransfer: the domain was assembled on another integrator or has been replaced")
     elif d.totalExt is None:
         d.getOpticalPropertiesByComponent()
     if getattr(d, "deviceOwner", None) is None:
-        key = (id(d), id(d.totalExt))
+        key = ("host", d.token, float(d.surfaceAlbedo))
     if g._stagedDomain != key:
         if (d.numX, d.numY, d.numZ) != (g.numX, g.numY, g.numZ):
             raise McbError("computeRadiativeTransfer: domain and integrator grids differ")
@@ -204,9 +216,9 @@ def _stage_domain(g: integrator, d: Domain) -> None:
                    for tab in d.forwardTables] if g.computeIntensity else []
     if g.computeIntensity and not all(fwdOnDevice):
         d.tabulateForwardPhaseFunctions(g.minForwardTableSize, hybrid, g.hybridPhaseFunWidth)
-    tkey = (key, onDevice, g.minInverseTableSize if onDevice else tuple(id(t) for t in d.inversePhaseFunctions),
-            (tuple(fwdOnDevice), g.minForwardTableSize, hybrid, g.hybridPhaseFunWidth,
-             tuple(id(t) for t in d.tabulatedPhaseFunctions)) if g.computeIntensity else None)
+    tkey = (key, onDevice, g.minInverseTableSize if onDevice else d.tableToken,
+            (tuple(fwdOnDevice), g.minForwardTableSize, hybrid, g.hybridPhaseFunWidth, d.tableToken)
+            if g.computeIntensity else None)
     if g._stagedTables != tkey:
         if onDevice:
             from .inversePhaseFunctions import inversion_inputs
@@ -246,11 +258,11 @@ def _stage_source(g: integrator, photons: photonStream) -> None:
     else:
         w = photons.weights
         if w.deviceOwner is not None:                      # built in this integrator's HBM (emission_weighting_device)
-            key = ("bbemission-device", id(w))
+            key = ("bbemission-device", w.token)
             if w.deviceOwner is not g or g._stagedSource != key:
                 raise McbError("new_PhotonStream: device-built weights belong to another integrator or were replaced")
             return
-        key = ("bbemission", id(w.voxelWeights), w.fracAtmsPower)
+        key = ("bbemission", w.token, w.fracAtmsPower)
         if g._stagedSource != key:
             g._check(g._lib.mcb_set_thermal_source(g._h, float(w.fracAtmsPower), _lib.ptr(w.voxelWeights, C.c_double)),
                      "new_PhotonStream")

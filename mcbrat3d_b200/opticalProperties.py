@@ -12,7 +12,8 @@ of the buffer IS the Fortran order.  File I/O (netCDF readers/writers) is out of
 """
 from __future__ import annotations
 
-from dataclasses import dataclass
+import itertools
+from dataclasses import dataclass, field
 from typing import List, Optional
 
 import numpy as np
@@ -23,6 +24,14 @@ from .scatteringPhaseFunctions import getPhaseFunctionValues, phaseFunctionTable
 
 f32 = np.float32
 Pi = f32(3.14159265358979312)          # OPT:26
+
+# Staging caches (what is already in HBM) are keyed on these tokens, never on id(): a token is unique for the life of
+# the process and is replaced whenever the object's staged content changes.
+_tokens = itertools.count(1)
+
+
+def new_token() -> int:
+    return next(_tokens)
 
 
 @dataclass
@@ -53,6 +62,8 @@ class Domain:
                       else np.ascontiguousarray(temps, dtype=np.float64).reshape(nz, ny, nx))
         self.surfaceAlbedo = float(surfaceAlbedo)
         self.lambda_um = float(lambda_um)
+        self.token = new_token()           # identifies the dense optical arrays (replaced when they change)
+        self.tableToken = new_token()      # identifies the tabulated phase functions
 
         def regular(p, tol):
             return bool(np.all(np.abs(np.diff(p) - (p[1] - p[0])) <= tol * spacing64(p[1:])))
@@ -113,6 +124,7 @@ class Domain:
         self.components.append(opticalComponent(componentName, int(zLevelBase), uniform, ext, ssa, idx,
                                                 phaseFunctions))
         self.totalExt = None               # must be re-assembled
+        self.token = new_token()
 
     # -- getOpticalPropertiesByComponent (OPT:966-1072) ---------------------------------
     def getOpticalPropertiesByComponent(self):
@@ -142,6 +154,7 @@ class Domain:
         for i in range(nc):
             np.divide(cum[i], total, out=cum[i], where=mask)
         self.totalExt, self.cumulativeExt, self.ssa, self.phaseFunctionIndex = total, cum, ssa, idx
+        self.token = new_token(); self.tableToken = new_token()
         self.inversePhaseFunctions = [None] * nc
         self.tabulatedPhaseFunctions = [None] * nc
         self.tabulatedOrigPhaseFunctions = [None] * nc
@@ -154,6 +167,12 @@ class Domain:
             if cur is not None and cur.shape[1] >= tableSize:
                 continue
             self.inversePhaseFunctions[i] = computeInversePhaseFuncTable(tab, tableSize)
+            self.tableToken = new_token()
+
+    def touch(self):
+        """Call after editing ``totalExt`` / ``cumulativeExt`` / ``ssa`` / ``phaseFunctionIndex`` or ``surfaceAlbedo`` in
+        place: the next ``computeRadiativeTransfer`` stages the arrays again."""
+        self.token = new_token()
 
     # -- tabulateForwardPhaseFunctions (OPT:1872-1934) -----------------------------------
     def tabulateForwardPhaseFunctions(self, tableSize: int, hybrid: bool = False, hybridWidth: float = 7.0):
@@ -166,6 +185,7 @@ class Domain:
             values = getPhaseFunctionValues(tab, angles)                 # (nSteps, nEntries)
             orig = np.ascontiguousarray(values.T, dtype=f32)             # (nEntries, nSteps)
             self.tabulatedOrigPhaseFunctions[i] = orig
+            self.tableToken = new_token()
             if hybrid and hybridWidth > 0:
                 self.tabulatedPhaseFunctions[i] = computeHybridPhaseFunctions(angles, orig, f32(hybridWidth))
             else:
@@ -258,6 +278,7 @@ class commonDomain:
     Reff: np.ndarray
     numConc: Optional[np.ndarray] = None
     rho: Optional[np.ndarray] = None
+    token: int = field(default_factory=new_token)      # staging-cache key (replace after editing the arrays in place)
 
 
 @dataclass
@@ -367,14 +388,14 @@ def _assemble_on_device(g, d: "Domain", commonD: commonDomain, descr, setup: boo
     from . import _lib
     if (d.numX, d.numY, d.numZ) != (g.numX, g.numY, g.numZ):
         raise ValueError("read_SSPTable: domain and integrator grids differ")
-    if getattr(g, "_stagedPhysical", None) != id(commonD):                        # once per run
+    if getattr(g, "_stagedPhysical", None) != commonD.token:                      # once per run
         mc = np.ascontiguousarray(commonD.massConc, dtype=np.float64)
         re = np.ascontiguousarray(commonD.Reff, dtype=np.float64)
         nPhys = mc.shape[-1] if mc.ndim == 4 else 0
         nconc = None if commonD.numConc is None else np.ascontiguousarray(commonD.numConc[:, 0, 0], dtype=np.float64)
         g._check(g._lib.mcb_set_physical(g.handle, nPhys, _lib.ptr(mc, C.c_double), _lib.ptr(re, C.c_double),
                                          _lib.ptr(nconc, C.c_double)), "read_SSPTable")
-        g._stagedPhysical = id(commonD)
+        g._stagedPhysical = commonD.token
     arr = (_lib.mcb_component * len(descr))()
     keep = []
     for i, q in enumerate(descr):
@@ -392,8 +413,9 @@ def _assemble_on_device(g, d: "Domain", commonD: commonDomain, descr, setup: boo
     d.tabulatedPhaseFunctions = [None] * nc
     d.tabulatedOrigPhaseFunctions = [None] * nc
     d.deviceOwner = g
+    d.token = new_token(); d.tableToken = new_token()
     g.numComps = nc
-    g._stagedDomain = ("device", id(d))
+    g._stagedDomain = ("device", d.token)
     g._stagedTables = None
 
 

@@ -43,7 +43,7 @@ def test_only_sm_100a_code_is_embedded():
 
 
 def test_struct_layouts_match_header():
-    assert C.sizeof(_lib.mcb_options) == 64
+    assert C.sizeof(_lib.mcb_options) == 84          # 11 reference-facing words + 7 tune knobs + 3 reserved
     assert C.sizeof(_lib.mcb_counters) == 128
     assert _lib.EVENT_DTYPE.itemsize == 96
     assert _lib.EVENT_DTYPE.fields["path"][1] == 48 and _lib.EVENT_DTYPE.fields["dir"][1] == 80
@@ -73,3 +73,11 @@ def test_product_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
                 text = open(os.path.join(dirpath, f)).read()
                 assert "oracle" not in text.lower(), os.path.join(dirpath, f)
+
+
+def test_no_environment_variables_on_the_launch_path():
+    """Measurement knobs live in mcb_options.tune*; the CUDA sources read no environment variable."""
+    csrc = os.path.join(ROOT, "mcbrat3d_b200", "csrc")
+    for f in os.listdir(csrc):
+        if f.endswith((".cu", ".cuh")):
+            assert "getenv" not in open(os.path.join(csrc, f)).read(), f

@@ -31,18 +31,30 @@ cases = {"C3_small_mie": (domains.landsat_cloud(ssa=0.99, nxy=24, mie=True), Fal
          "narrow": ((_tiny_domain(2, 9, 3), dict(solarMu=0.3, solarAzimuth=315.0)), False, 60000)}
 cases["C5_small_bitmap"] = cases["C5_small"]
 cases["C5_small_bitmap_views"] = (domains.bench_domain(nxy=24, nz=32), True, 30000)
+# thermal source + views: births post local-estimate requests inside the event phase (ADVICE r1: high)
+cases["C4_LW_views"] = ((domains.homogeneous_lw()[0], dict(lw=True, surfaceTemp=300.0, intensityMus=[1.0, 0.5, -0.5],
+                                                          intensityPhis=[0.0, 0.0, 90.0])), True, 60000)
+cases["T_irr_LW_views"] = ((domains.irregular_test_domain()[0], dict(lw=True, surfaceTemp=290.0, intensityMus=[1.0, 0.7, -0.5],
+                                                                    intensityPhis=[0.0, 45.0, 200.0])), True, 60000)
+for name in ("C3_small_mie", "C5_small", "C5_small_odd", "C5_small_odd_bitmap"):      # the photon-pool kernel as well
+    cases[name + "_pool"] = cases[name]
 out = {}
-import os
+from mcbrat3d_b200.emissionAndBroadBandWeights import Weights, emission_weighting
 for name, ((dom, case), views, n) in cases.items():
-    os.environ.pop("MCB_EXT_MASK", None)
-    if "bitmap" in name: os.environ["MCB_EXT_MASK"] = "1"      # occupancy-bitmap variants of the marcher
     g = new_Integrator(dom)
     if views:
         specifyParameters(g, intensityMus=case.get("intensityMus", [1.0, 0.5]), intensityPhis=case.get("intensityPhis", [0.0, 0.0]),
                           computeIntensity=True, useRussianRouletteForIntensity=True, zetaMin=0.3)
-    specifyParameters(g, minInverseTableSize=9001, minForwardTableSize=9001)
+    specifyParameters(g, minInverseTableSize=9001, minForwardTableSize=9001, LW_flag=1.0 if case.get("lw") else -1.0,
+                      tuneExtMask=1 if "bitmap" in name else 0,       # occupancy-bitmap variants of the marcher
+                      tuneKernel=MCB_KERNEL_POOL if name.endswith("_pool") else MCB_KERNEL_PARK)
     rs = new_RandomNumberSequence([3, 1, 0])
-    ps = new_PhotonStream(case["solarMu"], case["solarAzimuth"], n, rs)
+    if case.get("lw"):
+        w = Weights()
+        emission_weighting(dom, w, case["surfaceTemp"], thisIntegrator=g)
+        ps = new_PhotonStream(theseWeights=w, numberOfPhotons=n, randomNumbers=rs)
+    else:
+        ps = new_PhotonStream(case["solarMu"], case["solarAzimuth"], n, rs)
     computeRadiativeTransfer(g, dom, rs, ps, n)
     c = getCounters(g)
     out[name] = dict(bad=c["bad"], photons=c["photons"], crossings=c["crossings"], leCrossings=c["leCrossings"])
@@ -62,3 +74,4 @@ def test_no_out_of_bounds_access_in_the_fast_kernel():
         assert c["bad"] == 0, (name, c)
         assert c["crossings"] > c["photons"]
     assert res["C2_views"]["leCrossings"] > 0 and res["T_irr_views"]["leCrossings"] > 0
+    assert res["C4_LW_views"]["leCrossings"] > 0 and res["T_irr_LW_views"]["leCrossings"] > 0

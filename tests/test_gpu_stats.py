@@ -11,7 +11,8 @@ from common import oracle_weights
 from mcbrat3d_b200 import domains
 from mcbrat3d_b200.batchStatistics import BatchStatistics
 from mcbrat3d_b200.monteCarloIllumination import new_PhotonStream
-from mcbrat3d_b200.monteCarloRadiativeTransfer import (MCB_ARITH_FAST, MCB_ARITH_REFERENCE, computeRadiativeTransfer,
+from mcbrat3d_b200.monteCarloRadiativeTransfer import (MCB_ARITH_FAST, MCB_ARITH_REFERENCE, MCB_KERNEL_PARK, MCB_KERNEL_POOL,
+                                                       MCB_LAYOUT_BRICKS, MCB_LAYOUT_LINEAR, computeRadiativeTransfer,
                                                        finalize_Integrator, getCounters, new_Integrator,
                                                        reportResults, specifyParameters)
 from mcbrat3d_b200.RandomNumbersForMC import new_RandomNumberSequence
@@ -485,32 +486,27 @@ def test_occupancy_bitmap_is_exact():
     layer's clear-sky extinction).  Both branches deliver (float)totalExt, so the same photons must give
     the same event counts exactly and the same tallies up to f64 summation order -- with and without views, on a
     scene with a molecular background in every cell (C5) and on one with truly empty cells (C3)."""
-    import os
     for make, views, n in ((lambda: domains.bench_domain(nxy=40, nz=48), False, 300000),
                            (lambda: domains.landsat_cloud(ssa=0.99, nxy=32), False, 300000),
                            (lambda: domains.bench_domain(nxy=24, nz=32), True, 40000)):
         dom, case = make()
         out = {}
-        for mask in ("0", "1"):
-            os.environ["MCB_EXT_MASK"] = mask
+        for mask in (-1, 1):
+            g = new_Integrator(dom)
             try:
-                g = new_Integrator(dom)
-                try:
-                    if views:
-                        specifyParameters(g, intensityMus=[1.0, 0.5, 0.5], intensityPhis=[0.0, 0.0, 180.0], computeIntensity=True,
-                                          useRussianRouletteForIntensity=True, zetaMin=0.3, minForwardTableSize=10001)
-                    specifyParameters(g, minInverseTableSize=10001)
-                    rs = new_RandomNumberSequence([10, 1, 0])
-                    ps = new_PhotonStream(case["solarMu"], case["solarAzimuth"], n, rs)
-                    computeRadiativeTransfer(g, dom, rs, ps, n)
-                    res = reportResults(g, fluxUp=True, fluxDown=True, fluxAbsorbed=True, volumeAbsorption=True,
-                                        **(dict(intensity=True) if views else {}))
-                    out[mask] = (res, getCounters(g))
-                finally:
-                    finalize_Integrator(g)
+                if views:
+                    specifyParameters(g, intensityMus=[1.0, 0.5, 0.5], intensityPhis=[0.0, 0.0, 180.0], computeIntensity=True,
+                                      useRussianRouletteForIntensity=True, zetaMin=0.3, minForwardTableSize=10001)
+                specifyParameters(g, minInverseTableSize=10001, tuneExtMask=mask, tuneKernel=MCB_KERNEL_PARK)
+                rs = new_RandomNumberSequence([10, 1, 0])
+                ps = new_PhotonStream(case["solarMu"], case["solarAzimuth"], n, rs)
+                computeRadiativeTransfer(g, dom, rs, ps, n)
+                res = reportResults(g, fluxUp=True, fluxDown=True, fluxAbsorbed=True, volumeAbsorption=True,
+                                    **(dict(intensity=True) if views else {}))
+                out[mask] = (res, getCounters(g))
             finally:
-                os.environ.pop("MCB_EXT_MASK", None)
-        a, b = out["0"], out["1"]
+                finalize_Integrator(g)
+        a, b = out[-1], out[1]
         for k in ("crossings", "scatters", "leRays", "leCrossings", "bad"):
             assert a[1][k] == b[1][k], (k, a[1][k], b[1][k])
         for k in a[0]:
@@ -522,31 +518,24 @@ def test_bricked_layout_is_exact():
     reads the x-fastest copy.  The layout changes addresses, not values: the same photons give the same
     event counts exactly and the same tallies up to f64 summation order -- with even and odd grid sizes (odd padded
     dimensions are rounded up), with and without the occupancy bitmap."""
-    import os
-    for make, mask, n in ((lambda: domains.landsat_cloud(ssa=0.99, nxy=32), None, 300000),
-                          (lambda: domains.bench_domain(nxy=41, nz=47), None, 200000),
-                          (lambda: domains.bench_domain(nxy=41, nz=47), "1", 200000),
-                          (lambda: domains.homogeneous_slab(ssa=0.99, n=9, delta=0.125), None, 200000)):
+    for make, mask, n in ((lambda: domains.landsat_cloud(ssa=0.99, nxy=32), 0, 300000),
+                          (lambda: domains.bench_domain(nxy=41, nz=47), 0, 200000),
+                          (lambda: domains.bench_domain(nxy=41, nz=47), 1, 200000),
+                          (lambda: domains.homogeneous_slab(ssa=0.99, n=9, delta=0.125), 0, 200000)):
         dom, case = make()
         out = {}
-        for layout in ("linear", "bricks"):
-            os.environ["MCB_LAYOUT"] = layout
-            if mask:
-                os.environ["MCB_EXT_MASK"] = mask
+        for layout in (MCB_LAYOUT_LINEAR, MCB_LAYOUT_BRICKS):
+            g = new_Integrator(dom)
             try:
-                g = new_Integrator(dom)
-                try:
-                    specifyParameters(g, minInverseTableSize=10001)
-                    rs = new_RandomNumberSequence([10, 1, 0])
-                    ps = new_PhotonStream(case["solarMu"], case["solarAzimuth"], n, rs)
-                    computeRadiativeTransfer(g, dom, rs, ps, n)
-                    out[layout] = (reportResults(g, fluxUp=True, fluxDown=True, fluxAbsorbed=True, volumeAbsorption=True),
-                                   getCounters(g))
-                finally:
-                    finalize_Integrator(g)
+                specifyParameters(g, minInverseTableSize=10001, tuneLayout=layout, tuneExtMask=mask, tuneKernel=MCB_KERNEL_PARK)
+                rs = new_RandomNumberSequence([10, 1, 0])
+                ps = new_PhotonStream(case["solarMu"], case["solarAzimuth"], n, rs)
+                computeRadiativeTransfer(g, dom, rs, ps, n)
+                out[layout] = (reportResults(g, fluxUp=True, fluxDown=True, fluxAbsorbed=True, volumeAbsorption=True),
+                               getCounters(g))
             finally:
-                os.environ.pop("MCB_LAYOUT", None); os.environ.pop("MCB_EXT_MASK", None)
-        a, b = out["linear"], out["bricks"]
+                finalize_Integrator(g)
+        a, b = out[MCB_LAYOUT_LINEAR], out[MCB_LAYOUT_BRICKS]
         for k in ("crossings", "scatters", "bad"):
             assert a[1][k] == b[1][k], (k, a[1][k], b[1][k])
         assert a[1]["crossings"] > n
