@@ -221,6 +221,12 @@ int mcb_run_trace(mcb_handle *h, int64_t nPhotons, const float *rn, int64_t rnSt
 /* ---- testing aid ------------------------------------------------------------------- */
 /* The first n 32-bit outputs of the Philox4x32-10 stream of (seed, photon id).          */
 int mcb_debug_philox(mcb_handle *h, uint64_t seed, uint64_t photon, int n, uint32_t *out);
+/* Measured ceiling of the operation that bounds the photon kernels: fully divergent 4-byte gathers (one 32-byte
+ * sector per lane per load, loadsInFlight independent loads per lane: 1, 2, 4, 8 or 16) inside a buffer of `bytes`
+ * bytes, launched like the flux kernels (persistent, 128 threads, blocksPerSM CTAs per SM).  Returns gathers per
+ * second -- the denominator of bench.py's roofline.l2_gather.                                                    */
+int mcb_debug_gather_probe(mcb_handle *h, int64_t bytes, int loadsInFlight, int blocksPerSM, int iterations,
+                           double *gathersPerSecond);
 
 #ifdef __cplusplus
 }

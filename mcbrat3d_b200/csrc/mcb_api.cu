@@ -18,6 +18,7 @@ void mcb_launch_trace(const DevDomain &P, long long nPhotons, const float *rn, l
 void mcb_launch_fast_batch(const DevDomain &P, long long nPhotons, uint64_t seed, uint64_t firstPhotonId,
                            int numSMs, unsigned long long *workCounter, cudaStream_t stream);
 void mcb_launch_philox_kat(uint64_t seed, uint64_t photon, int n, uint32_t *out, cudaStream_t stream);
+double mcb_run_gather_probe(size_t bytes, int inFlight, int blocksPerSM, int iterations, int numSMs, cudaStream_t stream);
 // mcb_stage.cu: device-side packing / validation, normalisation, emission CDF
 void mcb_launch_pack_field(const DevDomain &P, int brick, float *ext, uint32_t *mask, float *layerExt, int *flags,
                            int numSMs, cudaStream_t stream);
@@ -1040,6 +1041,19 @@ int mcb_debug_philox(mcb_handle *h, uint64_t seed, uint64_t photon, int n, uint3
   CK(h, cudaGetLastError());
   CK(h, cudaMemcpyAsync(out, d, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost, h->stream));
   CK(h, cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+// measured ceiling of divergent sector gathers (mcb_probe.cu): what the roofline of the L2-resident configurations
+// is reported against
+int mcb_debug_gather_probe(mcb_handle *h, int64_t bytes, int loadsInFlight, int blocksPerSM, int iterations,
+                           double *gathersPerSecond) {
+  if (!h || !gathersPerSecond) return 1;
+  if (bytes < 4096 || blocksPerSM < 1 || blocksPerSM > 16 || iterations < 1) FAIL(h, "mcb_debug_gather_probe: bad arguments");
+  CK(h, cudaSetDevice(h->device));
+  const double r = mcb_run_gather_probe((size_t)bytes, loadsInFlight, blocksPerSM, iterations, h->numSMs, h->stream);
+  if (r < 0.0) FAIL(h, "mcb_debug_gather_probe: failed (%g)", r);
+  *gathersPerSecond = r;
   return 0;
 }
 

@@ -349,6 +349,17 @@ def getCounters(thisIntegrator: integrator) -> Dict[str, int]:
     return c.as_dict()
 
 
+def gatherProbe(thisIntegrator: integrator, nbytes: int, loadsInFlight: int = 8, blocksPerSM: int = 8,
+                iterations: int = 2000) -> float:
+    """Measured ceiling of fully divergent sector gathers on this GPU (``csrc/mcb_probe.cu``): gathers per second
+    inside a buffer of ``nbytes`` bytes, launched like the flux kernels.  The denominator of the gather roofline."""
+    out = C.c_double(0.0)
+    thisIntegrator._check(thisIntegrator._lib.mcb_debug_gather_probe(thisIntegrator.handle, int(nbytes), int(loadsInFlight),
+                                                                     int(blocksPerSM), int(iterations), C.byref(out)),
+                          "gatherProbe")
+    return float(out.value)
+
+
 def lastBatchMilliseconds(thisIntegrator: integrator) -> float:
     ms = C.c_float(0)
     thisIntegrator._check(thisIntegrator._lib.mcb_last_batch_ms(thisIntegrator._h, C.byref(ms)), "lastBatchMilliseconds")

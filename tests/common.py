@@ -9,12 +9,36 @@ FLT_FIELDS = ("weight", "tau", "path", "x", "y", "z")
 REL_TOL = 1e-6          # north-star criterion (a): path lengths and weights within 1e-6 relative
 
 
+class _Lazy:
+    """A (domain, case) pair built on first use: the full-size scenes are not constructed at collection time."""
+
+    def __init__(self, make):
+        self._make, self._value = make, None
+
+    def get(self):
+        if self._value is None:
+            self._value = self._make()
+        return self._value
+
+
 def trace_cases():
-    """(name, domain, case, source) for the fixed-random-number harness."""
-    return [("C1", *domains.homogeneous_slab(ssa=0.99), 0),
-            ("T_irr", *domains.irregular_test_domain(), 0),
-            ("C2", *domains.step_cloud(ssa=0.99, solarMu=0.5), 0),
-            ("T_irr_LW", *domains.irregular_test_domain(), 1)]
+    """(name, lazy (domain, case), source) for the fixed-random-number harness.  The headline configurations are in:
+    C3 at full size (z0 = 200, empty cells with phase index 0, 299-term HG), C3 with the 16-entry Mie-like table and a
+    Rayleigh component (nc = 2), a small C5 (nc = 2, molecular background in every cell, albedo 0.05)."""
+    return [("C1", _Lazy(lambda: domains.homogeneous_slab(ssa=0.99)), 0),
+            ("T_irr", _Lazy(lambda: domains.irregular_test_domain()), 0),
+            ("C2", _Lazy(lambda: domains.step_cloud(ssa=0.99, solarMu=0.5)), 0),
+            ("T_irr_LW", _Lazy(lambda: domains.irregular_test_domain()), 1),
+            ("C3", _Lazy(lambda: domains.landsat_cloud(ssa=0.99)), 0),
+            ("C3_mie", _Lazy(lambda: domains.landsat_cloud(ssa=0.99, mie=True)), 0),
+            ("C5_small", _Lazy(lambda: domains.bench_domain(nxy=40, nz=48)), 0),
+            ("C4_LW", _Lazy(lambda: domains.homogeneous_lw()), 1)]
+
+
+def stable_seed(name, salt=0):
+    """A seed that does not change from run to run (str hashes are salted per process)."""
+    import zlib
+    return (zlib.crc32(name.encode()) + salt) % 1000
 
 
 def injected_randoms(nPhotons, stride, seed):

@@ -6,7 +6,7 @@ import ctypes as C
 import numpy as np
 import pytest
 
-from common import assert_events_equal, injected_randoms, oracle_weights, trace_cases
+from common import assert_events_equal, injected_randoms, oracle_weights, stable_seed, trace_cases
 from mcbrat3d_b200 import _lib
 from mcbrat3d_b200.monteCarloIllumination import new_PhotonStream
 from mcbrat3d_b200.monteCarloRadiativeTransfer import (finalize_Integrator, new_Integrator, specifyParameters,
@@ -18,9 +18,10 @@ pytestmark = pytest.mark.gpu
 CASES = trace_cases()
 
 
-@pytest.mark.parametrize("name,dom,case,source", CASES, ids=[c[0] for c in CASES])
+@pytest.mark.parametrize("name,lazy,source", CASES, ids=[c[0] for c in CASES])
 @pytest.mark.parametrize("views,rr", [(False, False), (True, False), (True, True)], ids=["flux", "le", "le_rr"])
-def test_trace_parity(orc, name, dom, case, source, views, rr):
+def test_trace_parity(orc, name, lazy, source, views, rr):
+    dom, case = lazy.get()
     g = new_Integrator(dom)
     try:
         if views:
@@ -35,13 +36,13 @@ def test_trace_parity(orc, name, dom, case, source, views, rr):
         if views:
             og.set_view_cosines(g.intensityDirections)
         n, stride = 1500, 400
-        rn = injected_randoms(n, stride, seed=hash(name) % 1000)
+        rn = injected_randoms(n, stride, seed=stable_seed(name))
         rs = new_RandomNumberSequence([10, 1, 0])
         if source == 0:
             ps = new_PhotonStream(case["solarMu"], case["solarAzimuth"], n, rs)
             want = og.trace(rn, 0, case["solarMu"], case["solarAzimuth"], maxEvents=n * 1024)
         else:
-            w = oracle_weights(orc, od, dom)
+            w = oracle_weights(orc, od, dom, case.get("surfaceTemp", 300.0))
             ps = new_PhotonStream(theseWeights=w, numberOfPhotons=n, randomNumbers=rs)
             want = og.trace(rn, 1, fracAtmsPower=w.fracAtmsPower, voxelCDF=w.voxelWeights, maxEvents=n * 1024)
         got, raw = tracePhotons(g, dom, ps, rn, maxEventsPerPhoton=1024)
@@ -55,12 +56,13 @@ def test_trace_parity(orc, name, dom, case, source, views, rr):
         finalize_Integrator(g)
 
 
-@pytest.mark.parametrize("name,dom,case,source", [c for c in CASES if c[0] in ("C1", "T_irr", "C2")],
+@pytest.mark.parametrize("name,lazy,source", [c for c in CASES if c[0] in ("C1", "T_irr", "C2")],
                          ids=[c[0] for c in CASES if c[0] in ("C1", "T_irr", "C2")])
 @pytest.mark.parametrize("views", [False, True], ids=["flux", "le"])
-def test_trace_parity_max_cross_section(orc, name, dom, case, source, views):
+def test_trace_parity_max_cross_section(orc, name, lazy, source, views):
     """useRayTracing=.false. (INT:564-571, 578-585, 624-631, 709-710; makePeriodic returns default real,
     quirk q15): same bit-exact criterion, including the mathematical (null) collisions."""
+    dom, case = lazy.get()
     g = new_Integrator(dom)
     try:
         if views:
@@ -72,7 +74,7 @@ def test_trace_parity_max_cross_section(orc, name, dom, case, source, views):
         if views:
             og.set_view_cosines(g.intensityDirections)
         n, stride = 800, 600
-        rn = injected_randoms(n, stride, seed=7 + hash(name) % 1000)
+        rn = injected_randoms(n, stride, seed=stable_seed(name, 7))
         rs = new_RandomNumberSequence([10, 1, 0])
         ps = new_PhotonStream(case["solarMu"], case["solarAzimuth"], n, rs)
         want = og.trace(rn, 0, case["solarMu"], case["solarAzimuth"], maxEvents=n * 2048)
@@ -122,12 +124,13 @@ def test_philox_known_answer():
         finalize_Integrator(g)
 
 
-@pytest.mark.parametrize("name,dom,case,source", [c for c in CASES if c[0] in ("C2", "T_irr")],
-                         ids=[c[0] for c in CASES if c[0] in ("C2", "T_irr")])
-def test_trace_parity_hybrid_tables_and_contribution_limit(orc, name, dom, case, source):
+@pytest.mark.parametrize("name,lazy,source", [c for c in CASES if c[0] in ("C2", "T_irr", "C3_mie")],
+                         ids=[c[0] for c in CASES if c[0] in ("C2", "T_irr", "C3_mie")])
+def test_trace_parity_hybrid_tables_and_contribution_limit(orc, name, lazy, source):
     """Local estimation with the hybrid (Gaussian forward peak) tables for scattering orders above
     numOrdersOrigPhaseFunIntenCalcs (INT:1715-1724, OPT:1936-2050) and with limited contributions
     (INT:1815-1826): bit-exact events, and the raw tallies including intensityExcess."""
+    dom, case = lazy.get()
     g = new_Integrator(dom)
     try:
         mus = case.get("intensityMus", [1.0, 0.5]); phis = case.get("intensityPhis", [0.0, 0.0])
@@ -140,7 +143,7 @@ def test_trace_parity_hybrid_tables_and_contribution_limit(orc, name, dom, case,
                                   limitIntensityContributions=1, maxIntensityContribution=0.05)
         og.set_view_cosines(g.intensityDirections)
         n, stride = 1000, 400
-        rn = injected_randoms(n, stride, seed=11 + hash(name) % 1000)
+        rn = injected_randoms(n, stride, seed=stable_seed(name, 11))
         rs = new_RandomNumberSequence([10, 1, 0])
         ps = new_PhotonStream(case["solarMu"], case["solarAzimuth"], n, rs)
         want = og.trace(rn, 0, case["solarMu"], case["solarAzimuth"], maxEvents=n * 1024)
