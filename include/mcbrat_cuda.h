@@ -209,6 +209,26 @@ int mcb_get_results(mcb_handle *h, int64_t nPhotonsNormalise,
 int mcb_tally_buffer(mcb_handle *h, void **devicePtr, int64_t *nDoubles);
 int mcb_get_raw_tallies(mcb_handle *h, double *out, int64_t nDoubles);
 
+/* ---- multi-GPU: multipleProcesses_mpi (MPIW:29-251) over NCCL ------------------------------
+ * One process per GPU, the domain replicated in every GPU's HBM, photons split by global photon id
+ * (firstPhotonId of mcb_run_batch / mcb_run_batches), and ONE sum-reduce of the packed buffer at the
+ * end -- it replaces the nine sumAcrossProcesses calls at DRV:1151-1166 (MPI_REDUCE, MPIW:70-251).
+ * libnccl is bound at run time (dlopen), so single-GPU hosts need no NCCL.
+ *   mcb_comm_unique_id : rank 0 creates the 128-byte NCCL id; the HOST distributes it (the Fortran host
+ *                        with one MPI_BCAST next to its MPI_INIT, MPIW:29-52; torchrun hosts with
+ *                        torch.distributed; the C++ example through a file).
+ *   mcb_comm_init      : initializeProcesses -- collective over all ranks.
+ *   mcb_reduce_tallies / mcb_reduce_statistics : in place, asynchronous on the handle's stream;
+ *                        root >= 0 reduces to that rank (MPI_REDUCE), root < 0 all-reduces.  No-ops on a
+ *                        handle without a communicator (multipleProcesses_nompi.f95).
+ *   mcb_comm_destroy   : finalizeProcesses (MPIW:62-68).                                               */
+int mcb_comm_unique_id(void *id128);
+int mcb_comm_init(mcb_handle *h, int nranks, int rank, const void *id128);
+int mcb_comm_info(mcb_handle *h, int *nranks, int *rank, int *ncclVersion);
+int mcb_reduce_tallies(mcb_handle *h, int root);
+int mcb_reduce_statistics(mcb_handle *h, int root);
+int mcb_comm_destroy(mcb_handle *h);
+
 /* ---- trace harness ------------------------------------------------------------------ */
 /* Photon p is born from and transported with rn[p*rnStride ...] (source draws first, then the
  * computeRT order).  Always reference arithmetic.  Events of photon 0 come first,
@@ -222,7 +242,8 @@ int mcb_run_trace(mcb_handle *h, int64_t nPhotons, const float *rn, int64_t rnSt
 /* The first n 32-bit outputs of the Philox4x32-10 stream of (seed, photon id).          */
 int mcb_debug_philox(mcb_handle *h, uint64_t seed, uint64_t photon, int n, uint32_t *out);
 /* Measured ceiling of the operation that bounds the photon kernels: fully divergent 4-byte gathers (one 32-byte
- * sector per lane per load, loadsInFlight independent loads per lane: 1, 2, 4, 8 or 16) inside a buffer of `bytes`
+ * sector per lane per load, loadsInFlight independent loads per lane: 1, 2, 4, 8 or 16; negative: 16-byte loads,
+ * -1, -4 or -8 of them) inside a buffer of `bytes`
  * bytes, launched like the flux kernels (persistent, 128 threads, blocksPerSM CTAs per SM).  Returns gathers per
  * second -- the denominator of bench.py's roofline.l2_gather.                                                    */
 int mcb_debug_gather_probe(mcb_handle *h, int64_t bytes, int loadsInFlight, int blocksPerSM, int iterations,

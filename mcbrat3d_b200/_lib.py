@@ -71,7 +71,8 @@ EXPORTS = ["mcb_create", "mcb_destroy", "mcb_last_error", "mcb_version", "mcb_se
            "mcb_build_thermal_source", "mcb_get_thermal_source", "mcb_frequency_distribution", "mcb_run_batch", "mcb_accumulate_batch", "mcb_stats_reset", "mcb_run_batches",
            "mcb_stats_buffer", "mcb_get_statistics", "mcb_last_batch_ms",
            "mcb_get_counters", "mcb_get_results", "mcb_tally_buffer", "mcb_get_raw_tallies", "mcb_run_trace",
-           "mcb_debug_philox", "mcb_debug_gather_probe"]
+           "mcb_debug_philox", "mcb_debug_gather_probe", "mcb_comm_unique_id", "mcb_comm_init", "mcb_comm_info",
+           "mcb_reduce_tallies", "mcb_reduce_statistics", "mcb_comm_destroy"]
 
 _lib: Optional[C.CDLL] = None
 
@@ -130,6 +131,12 @@ def load() -> C.CDLL:
     lib.mcb_run_trace.argtypes = [_vp, C.c_int64, _fp, C.c_int64, C.c_int32, _vp, C.c_int64, C.POINTER(C.c_int64)]
     lib.mcb_debug_philox.argtypes = [_vp, C.c_uint64, C.c_uint64, C.c_int, C.POINTER(C.c_uint32)]
     lib.mcb_debug_gather_probe.argtypes = [_vp, C.c_int64, C.c_int, C.c_int, C.c_int, _dp]
+    lib.mcb_comm_unique_id.argtypes = [_vp]
+    lib.mcb_comm_init.argtypes = [_vp, C.c_int, C.c_int, _vp]
+    lib.mcb_comm_info.argtypes = [_vp, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    lib.mcb_reduce_tallies.argtypes = [_vp, C.c_int]
+    lib.mcb_reduce_statistics.argtypes = [_vp, C.c_int]
+    lib.mcb_comm_destroy.argtypes = [_vp]
     for name in EXPORTS:
         if name != "mcb_default_options":
             getattr(lib, name).restype = C.c_int

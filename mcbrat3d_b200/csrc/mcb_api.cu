@@ -1,5 +1,8 @@
 // mcb_api.cu -- the C ABI (include/mcbrat_cuda.h): handle, staging into HBM, launches,
 // normalisation and read-back.  No photon arithmetic happens on the host.
+#include <dlfcn.h>
+#include <nccl.h>                      // types and prototypes only: libnccl is bound at run time (mcb_comm_init)
+
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -78,7 +81,40 @@ struct mcb_handle {
   double *dTally = nullptr; long long nTally = 0;
   unsigned long long *dCounters = nullptr;     // CNT_N counters + 1 work counter
   double *hTally = nullptr; long long hTallyCap = 0;   // pinned
+  ncclComm_t comm = nullptr; int commRanks = 1, commRank = 0;   // mcb_comm_init
 };
+
+// ---- NCCL, bound at run time ---------------------------------------------------------------------------------
+// The library has no link-time dependency on libnccl: a single-GPU run needs none, and inside a process that already
+// carries an NCCL (PyTorch bundles its own) dlopen by SONAME returns THAT copy instead of loading a second one.
+struct NcclApi {
+  void *lib = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*Reduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  const char *(*GetErrorString)(ncclResult_t) = nullptr;
+  ncclResult_t (*GetVersion)(int *) = nullptr;
+  std::string err;
+};
+static NcclApi *nccl_api() {
+  static NcclApi api;
+  if (api.lib || !api.err.empty()) return &api;
+  const char *names[] = {"libnccl.so.2", "libnccl.so"};
+  for (const char *n : names) { api.lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL); if (api.lib) break; }
+  if (!api.lib) { api.err = std::string("libnccl.so.2 not found: ") + dlerror(); return &api; }
+  auto sym = [&](const char *n) { void *p = dlsym(api.lib, n); if (!p && api.err.empty()) api.err = std::string("missing NCCL symbol ") + n; return p; };
+  api.GetUniqueId = (decltype(api.GetUniqueId))sym("ncclGetUniqueId");
+  api.CommInitRank = (decltype(api.CommInitRank))sym("ncclCommInitRank");
+  api.CommDestroy = (decltype(api.CommDestroy))sym("ncclCommDestroy");
+  api.Reduce = (decltype(api.Reduce))sym("ncclReduce");
+  api.AllReduce = (decltype(api.AllReduce))sym("ncclAllReduce");
+  api.GetErrorString = (decltype(api.GetErrorString))sym("ncclGetErrorString");
+  api.GetVersion = (decltype(api.GetVersion))sym("ncclGetVersion");
+  if (!api.err.empty()) { dlclose(api.lib); api.lib = nullptr; }
+  return &api;
+}
 
 #define FAIL(h, ...)                                                     \
   do {                                                                   \
@@ -180,6 +216,7 @@ int mcb_destroy(mcb_handle *h) {
     if (h->dFwdOrig[c]) cudaFree(h->dFwdOrig[c]);
   }
   if (h->hTally) cudaFreeHost(h->hTally);
+  if (h->comm && nccl_api()->lib) nccl_api()->CommDestroy(h->comm);
   cudaEventDestroy(h->evStart); cudaEventDestroy(h->evStop);
   cudaStreamDestroy(h->ownStream);
   delete h;
@@ -1042,6 +1079,83 @@ int mcb_debug_philox(mcb_handle *h, uint64_t seed, uint64_t photon, int n, uint3
   CK(h, cudaMemcpyAsync(out, d, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost, h->stream));
   CK(h, cudaStreamSynchronize(h->stream));
   return 0;
+}
+
+// ---- multi-GPU: one process per GPU, the domain replicated, photons split by global id, ONE sum-reduce ----------
+#define NCK(h, call)                                                                 \
+  do {                                                                               \
+    ncclResult_t _r = (call);                                                        \
+    if (_r != ncclSuccess) FAIL(h, "%s: %s", #call, nccl_api()->GetErrorString(_r)); \
+  } while (0)
+
+int mcb_comm_unique_id(void *id128) {
+  if (!id128) return 1;
+  NcclApi *n = nccl_api();
+  if (!n->lib) return 2;
+  ncclUniqueId id;
+  if (n->GetUniqueId(&id) != ncclSuccess) return 3;
+  memcpy(id128, &id, sizeof(id));
+  return 0;
+}
+
+int mcb_comm_init(mcb_handle *h, int nranks, int rank, const void *id128) {
+  if (!h) return 1;
+  if (nranks < 1 || rank < 0 || rank >= nranks || !id128) FAIL(h, "initializeProcesses: bad rank / number of processes");
+  NcclApi *n = nccl_api();
+  if (!n->lib) FAIL(h, "initializeProcesses: %s", n->err.c_str());
+  CK(h, cudaSetDevice(h->device));
+  if (h->comm) { n->CommDestroy(h->comm); h->comm = nullptr; }
+  ncclUniqueId id;
+  memcpy(&id, id128, sizeof(id));
+  NCK(h, n->CommInitRank(&h->comm, nranks, id, rank));
+  h->commRanks = nranks; h->commRank = rank;
+  return 0;
+}
+
+int mcb_comm_info(mcb_handle *h, int *nranks, int *rank, int *ncclVersion) {
+  if (!h) return 1;
+  if (nranks) *nranks = h->comm ? h->commRanks : 1;
+  if (rank) *rank = h->comm ? h->commRank : 0;
+  if (ncclVersion) { *ncclVersion = 0; NcclApi *n = nccl_api(); if (n->lib) n->GetVersion(ncclVersion); }
+  return 0;
+}
+
+int mcb_comm_destroy(mcb_handle *h) {
+  if (!h) return 1;
+  if (h->comm) {
+    CK(h, cudaSetDevice(h->device));
+    CK(h, cudaStreamSynchronize(h->stream));
+    nccl_api()->CommDestroy(h->comm);
+    h->comm = nullptr; h->commRanks = 1; h->commRank = 0;
+  }
+  return 0;
+}
+
+// sum-reduce (root >= 0) or all-reduce (root < 0) of a device buffer of doubles, in place, on the handle's stream
+static int reduce_doubles(mcb_handle *h, double *buf, long long n, int root, const char *what) {
+  if (!h->comm) return 0;                              // a single process: nothing to sum (multipleProcesses_nompi)
+  if (root >= h->commRanks) FAIL(h, "%s: root %d is not a rank of this communicator", what, root);
+  NcclApi *a = nccl_api();
+  CK(h, cudaSetDevice(h->device));
+  if (root >= 0) NCK(h, a->Reduce(buf, buf, (size_t)n, ncclFloat64, ncclSum, root, h->comm, h->stream));
+  else NCK(h, a->AllReduce(buf, buf, (size_t)n, ncclFloat64, ncclSum, h->comm, h->stream));
+  return 0;
+}
+
+int mcb_reduce_tallies(mcb_handle *h, int root) {
+  if (!h) return 1;
+  if (!h->haveGrid || !h->haveOptics) FAIL(h, "sumAcrossProcesses: problem not completely specified.");
+  CK(h, cudaSetDevice(h->device));
+  if (ensure_tallies(h)) return 1;
+  return reduce_doubles(h, h->dTally, h->nTally, root, "sumAcrossProcesses");
+}
+
+int mcb_reduce_statistics(mcb_handle *h, int root) {
+  if (!h) return 1;
+  if (!h->haveGrid || !h->haveOptics) FAIL(h, "sumAcrossProcesses: problem not completely specified.");
+  CK(h, cudaSetDevice(h->device));
+  if (ensure_stats(h)) return 1;
+  return reduce_doubles(h, (double *)h->dStats, 2 * h->nStats + 2, root, "sumAcrossProcesses");
 }
 
 // measured ceiling of divergent sector gathers (mcb_probe.cu): what the roofline of the L2-resident configurations

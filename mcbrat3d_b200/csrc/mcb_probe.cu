@@ -8,7 +8,7 @@
 // bench.py is a fraction of a MEASURED peak: same launch shape as the flux kernels (persistent, 128 threads, a given
 // number of CTAs per SM), `inFlight` independent loads per lane per iteration at pseudo-random addresses inside a
 // buffer of `bytes` bytes (16 MB: L2-resident like the C3 field; 93 MB: the C5 field; >= 512 MB: HBM-bound), next
-// to nothing else (3 integer instructions per address).
+// to nothing else (3 integer instructions per address).  A negative `inFlight` issues 16-byte loads (float4) instead.
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -31,6 +31,24 @@ __global__ void __launch_bounds__(128) gather_kernel(const float *__restrict__ b
   if (acc == 1.2345e-30f) *sink = acc;                      // keeps the loads alive
 }
 
+// the same with 16-byte loads (one aligned float4 per lane per load): does a wider gather cost more than a 4-byte one?
+template <int INFLIGHT>
+__global__ void __launch_bounds__(128) gather4_kernel(const float4 *__restrict__ buf, uint32_t nQuads, int iterations, float *sink) {
+  uint32_t s = (blockIdx.x * 128u + threadIdx.x) * 2654435761u + 12345u;
+  float acc = 0.0f;
+  for (int it = 0; it < iterations; ++it) {
+    float4 v[INFLIGHT];
+#pragma unroll
+    for (int k = 0; k < INFLIGHT; ++k) {
+      s = s * 1664525u + 1013904223u;
+      v[k] = __ldg(buf + __umulhi(s, nQuads));
+    }
+#pragma unroll
+    for (int k = 0; k < INFLIGHT; ++k) acc += v[k].x + v[k].y + v[k].z + v[k].w;
+  }
+  if (acc == 1.2345e-30f) *sink = acc;
+}
+
 __global__ void fill_kernel(float *buf, size_t n) {
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) buf[i] = 1.0f;
 }
@@ -49,6 +67,12 @@ double mcb_run_gather_probe(size_t bytes, int inFlight, int blocksPerSM, int ite
   cudaEventCreate(&e0); cudaEventCreate(&e1);
   const int blocks = numSMs * blocksPerSM;
   auto go = [&](int iters) {
+    if (inFlight < 0) {                                     // 16-byte loads
+      if (inFlight == -1) mcbprobe::gather4_kernel<1><<<blocks, 128, 0, stream>>>((const float4 *)buf, (uint32_t)(n / 4), iters, sink);
+      else if (inFlight == -4) mcbprobe::gather4_kernel<4><<<blocks, 128, 0, stream>>>((const float4 *)buf, (uint32_t)(n / 4), iters, sink);
+      else { mcbprobe::gather4_kernel<8><<<blocks, 128, 0, stream>>>((const float4 *)buf, (uint32_t)(n / 4), iters, sink); inFlight = -8; }
+      return;
+    }
     switch (inFlight) {
       case 1: mcbprobe::gather_kernel<1><<<blocks, 128, 0, stream>>>(buf, (uint32_t)n, iters, sink); break;
       case 2: mcbprobe::gather_kernel<2><<<blocks, 128, 0, stream>>>(buf, (uint32_t)n, iters, sink); break;
@@ -66,7 +90,7 @@ double mcb_run_gather_probe(size_t bytes, int inFlight, int blocksPerSM, int ite
     if (cudaEventSynchronize(e1) != cudaSuccess) { best = -3.0; break; }
     float ms = 0.0f;
     cudaEventElapsedTime(&ms, e0, e1);
-    const double rate = (double)blocks * 128.0 * (double)iterations * (double)inFlight / (ms * 1e-3);
+    const double rate = (double)blocks * 128.0 * (double)iterations * (double)(inFlight < 0 ? -inFlight : inFlight) / (ms * 1e-3);
     if (rate > best) best = rate;
   }
   cudaEventDestroy(e0); cudaEventDestroy(e1);

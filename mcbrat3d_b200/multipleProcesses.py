@@ -110,6 +110,31 @@ def photonShares(totalPhotons: int, rates) -> list:
     return shares
 
 
+def initializeIntegratorProcesses(thisIntegrator) -> bool:
+    """Give the integrator its own NCCL communicator through the C ABI (``mcb_comm_init``): the same entry points a
+    compiled host uses (``fortran/mcbrat_cuda_mod.f90``, ``examples/i3rc_driver --ranks N``).  Rank 0 creates the
+    128-byte id with ``mcb_comm_unique_id``; ``torch.distributed`` only carries it to the other ranks -- the job
+    ``MPI_BCAST`` has in the Fortran host.  Returns False (and changes nothing) in a single-process run."""
+    if not dist.is_initialized() or dist.get_world_size() < 2:
+        return False
+    g = thisIntegrator
+    ident = (C.c_ubyte * 128)()
+    if dist.get_rank() == 0:
+        rc = g._lib.mcb_comm_unique_id(C.cast(ident, C.c_void_p))
+        if rc != 0:
+            raise RuntimeError("initializeProcesses: mcb_comm_unique_id failed (%d): is libnccl.so.2 loadable?" % rc)
+    t = torch.tensor(list(ident), dtype=torch.uint8)
+    if dist.get_backend() == "nccl":
+        t = t.cuda(g.device)
+    dist.broadcast(t, src=0)
+    raw = bytes(t.cpu().tolist())
+    buf = (C.c_ubyte * 128).from_buffer_copy(raw)
+    g._check(g._lib.mcb_comm_init(g.handle, dist.get_world_size(), dist.get_rank(), C.cast(buf, C.c_void_p)),
+             "initializeProcesses")
+    g._hasComm = True
+    return True
+
+
 class _DeviceBuffer:
     """Exposes a raw device pointer to torch through ``__cuda_array_interface__``."""
 
@@ -129,6 +154,10 @@ def tallyTensor(thisIntegrator) -> torch.Tensor:
 
 def sumTalliesAcrossProcesses(thisIntegrator, root: int = 0) -> None:
     """One NCCL sum-reduce of all tallies (replaces the nine reduces at DRV:1151-1166)."""
+    if getattr(thisIntegrator, "_hasComm", False):               # the library's own communicator: ncclReduce on its stream
+        thisIntegrator._check(thisIntegrator._lib.mcb_reduce_tallies(thisIntegrator.handle, int(root)), "sumTalliesAcrossProcesses")
+        thisIntegrator._check(thisIntegrator._lib.mcb_synchronize(thisIntegrator.handle), "sumTalliesAcrossProcesses")
+        return
     if not dist.is_initialized():
         return
     thisIntegrator._check(thisIntegrator._lib.mcb_synchronize(thisIntegrator.handle), "sumTalliesAcrossProcesses")
@@ -150,6 +179,10 @@ def statisticsTensor(thisIntegrator) -> torch.Tensor:
 def sumStatisticsAcrossProcesses(thisIntegrator, root: int = 0) -> None:
     """Moments, photon counts and batch counts add across ranks exactly as the driver's
     ``sumAcrossProcesses`` calls do (DRV:1151-1166): one reduce of the moment buffer."""
+    if getattr(thisIntegrator, "_hasComm", False):
+        thisIntegrator._check(thisIntegrator._lib.mcb_reduce_statistics(thisIntegrator.handle, int(root)), "sumStatisticsAcrossProcesses")
+        thisIntegrator._check(thisIntegrator._lib.mcb_synchronize(thisIntegrator.handle), "sumStatisticsAcrossProcesses")
+        return
     if not dist.is_initialized():
         return
     thisIntegrator._check(thisIntegrator._lib.mcb_synchronize(thisIntegrator.handle), "sumStatisticsAcrossProcesses")

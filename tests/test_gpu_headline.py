@@ -41,7 +41,10 @@ def _gpu_rows(dom, case, nb, n, seed, views=False, want=(), **params):
             res = reportResults(g, **{k: True for k in want})
             for k in want:
                 rows[k].append(np.asarray(res[k], np.float64).copy())
-        assert getCounters(g)["bad"] == 0
+        # The reference drops a photon whose march reports a non-positive step (OPT:1719-1722, INT:562-563): the
+        # reference-arithmetic kernel reproduces that (a few per 1e6 photons on C3); the throughput kernels never do.
+        bad = getCounters(g)["bad"]
+        assert bad == 0 if params.get("arithmetic", MCB_ARITH_FAST) == MCB_ARITH_FAST else bad <= 2e-5 * n, bad
         return {k: np.array(v) for k, v in rows.items()}
     finally:
         finalize_Integrator(g)
