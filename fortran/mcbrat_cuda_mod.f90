@@ -24,8 +24,27 @@ module mcbrat_cuda
     real(c_float)      :: maxIntensityContribution
     real(c_float)      :: LW_flag
     integer(c_int32_t) :: arithmetic
-    integer(c_int32_t) :: reserved(5)
+    ! measurement knobs (0 = the library's own choice), see include/mcbrat_cuda.h
+    integer(c_int32_t) :: tuneKernel, tuneLayout, tuneBlocksPerSM, tuneParkThreshold, tuneLeCarry, tuneExtMask, tuneBurst
+    integer(c_int32_t) :: reserved(3)
   end type mcb_options
+  integer(c_int32_t), parameter, public :: MCB_KERNEL_PARK = 1, MCB_KERNEL_POOL = 2
+  integer(c_int32_t), parameter, public :: MCB_LAYOUT_LINEAR = 1, MCB_LAYOUT_BRICKS = 2
+
+  ! event counters of the last batch (mcb_get_counters)
+  type, bind(C), public :: mcb_counters
+    integer(c_int64_t) :: photons, crossings, scatters, surfaceHits, topExits, bad, leRays, leCrossings, rouletteKills
+    integer(c_int64_t) :: reserved(7)
+  end type mcb_counters
+
+  ! trace record of the fixed-random-number harness (mcb_run_trace)
+  type, bind(C), public :: mcb_event
+    integer(c_int32_t) :: photon, kind, ix, iy, iz, component, phaseIndex, angleIndex, order, nrn
+    real(c_float)      :: weight, tau
+    real(c_double)     :: path, x, y, z
+    real(c_float)      :: dir(3)
+    integer(c_int32_t) :: pad
+  end type mcb_event
 
   ! one wavelength's description of an optical component for mcb_assemble_optics (read_SSPTable OPT:200-246)
   integer(c_int32_t), parameter, public :: MCB_COMP_VOLEXT = 0, MCB_COMP_ABSXSEC = 1, MCB_COMP_PROFILE = 2
@@ -43,7 +62,11 @@ module mcbrat_cuda
             mcb_tally_buffer, mcb_synchronize, mcb_status_to_message,                                    &
             mcb_set_physical, mcb_assemble_optics, mcb_get_optics, mcb_build_inverse_table,              &
             mcb_build_thermal_source, mcb_frequency_distribution, mcb_accumulate_batch,                  &
-            mcb_stats_reset, mcb_run_batches, mcb_stats_buffer, mcb_get_statistics
+            mcb_stats_reset, mcb_run_batches, mcb_stats_buffer, mcb_get_statistics,                       &
+            mcb_version, mcb_set_stream, mcb_build_forward_table, mcb_get_inverse_table, mcb_get_forward_table,  &
+            mcb_get_thermal_source, mcb_last_batch_ms, mcb_get_counters, mcb_get_raw_tallies, mcb_run_trace, &
+            mcb_debug_philox, mcb_debug_gather_probe,                                                    &
+            mcb_comm_unique_id, mcb_comm_init, mcb_comm_info, mcb_reduce_tallies, mcb_reduce_statistics, mcb_comm_destroy
 
   interface
     integer(c_int) function mcb_create(device, handle) bind(C, name="mcb_create")
@@ -217,6 +240,112 @@ module mcbrat_cuda
                             absorbedVolumeStats, radianceStats        ! c_loc(stats array) or c_null_ptr
       integer(c_int64_t), intent(out) :: totalNumPhotons, batchesCompleted
     end function
+    ! ---- the rest of the header: version, stream, table builders / read-back, timing, counters, trace, aids ----
+    integer(c_int) function mcb_version() bind(C, name="mcb_version")
+      import :: c_int
+    end function
+    integer(c_int) function mcb_set_stream(handle, cudaStream) bind(C, name="mcb_set_stream")
+      import :: c_int, c_ptr
+      type(c_ptr), value :: handle, cudaStream                 ! a cudaStream_t, or c_null_ptr for the handle's own
+    end function
+    integer(c_int) function mcb_build_forward_table(handle, comp, nS, nE, nCoef, coefs) bind(C, name="mcb_build_forward_table")
+      import :: c_int, c_ptr, c_float, c_int32_t
+      type(c_ptr), value :: handle
+      integer(c_int), value :: comp, nS, nE
+      integer(c_int32_t), intent(in) :: nCoef(*)
+      real(c_float), intent(in) :: coefs(*)
+    end function
+    integer(c_int) function mcb_get_inverse_table(handle, comp, T, nFloats) bind(C, name="mcb_get_inverse_table")
+      import :: c_int, c_ptr, c_float, c_int64_t
+      type(c_ptr), value :: handle
+      integer(c_int), value :: comp
+      real(c_float), intent(out) :: T(*)
+      integer(c_int64_t), value :: nFloats
+    end function
+    integer(c_int) function mcb_get_forward_table(handle, comp, T, nFloats) bind(C, name="mcb_get_forward_table")
+      import :: c_int, c_ptr, c_float, c_int64_t
+      type(c_ptr), value :: handle
+      integer(c_int), value :: comp
+      real(c_float), intent(out) :: T(*)
+      integer(c_int64_t), value :: nFloats
+    end function
+    integer(c_int) function mcb_get_thermal_source(handle, fracAtmsPower, voxelCDF, nDoubles) bind(C, name="mcb_get_thermal_source")
+      import :: c_int, c_ptr, c_int64_t
+      type(c_ptr), value :: handle
+      type(c_ptr), value :: fracAtmsPower, voxelCDF            ! c_loc(real(c_double)) or c_null_ptr
+      integer(c_int64_t), value :: nDoubles
+    end function
+    integer(c_int) function mcb_last_batch_ms(handle, ms) bind(C, name="mcb_last_batch_ms")
+      import :: c_int, c_ptr, c_float
+      type(c_ptr), value :: handle
+      real(c_float), intent(out) :: ms
+    end function
+    integer(c_int) function mcb_get_counters(handle, c) bind(C, name="mcb_get_counters")
+      import :: c_int, c_ptr, mcb_counters
+      type(c_ptr), value :: handle
+      type(mcb_counters), intent(out) :: c
+    end function
+    integer(c_int) function mcb_get_raw_tallies(handle, out, nDoubles) bind(C, name="mcb_get_raw_tallies")
+      import :: c_int, c_ptr, c_double, c_int64_t
+      type(c_ptr), value :: handle
+      real(c_double), intent(out) :: out(*)
+      integer(c_int64_t), value :: nDoubles
+    end function
+    integer(c_int) function mcb_run_trace(handle, nPhotons, rn, rnStride, maxEventsPerPhoton, events, eventCap, nEvents) &
+        bind(C, name="mcb_run_trace")
+      import :: c_int, c_ptr, c_float, c_int32_t, c_int64_t, mcb_event
+      type(c_ptr), value :: handle
+      integer(c_int64_t), value :: nPhotons, rnStride, eventCap
+      real(c_float), intent(in) :: rn(*)
+      integer(c_int32_t), value :: maxEventsPerPhoton
+      type(mcb_event), intent(out) :: events(*)
+      integer(c_int64_t), intent(out) :: nEvents
+    end function
+    integer(c_int) function mcb_debug_philox(handle, seed, photon, n, out) bind(C, name="mcb_debug_philox")
+      import :: c_int, c_ptr, c_int32_t, c_int64_t
+      type(c_ptr), value :: handle
+      integer(c_int64_t), value :: seed, photon
+      integer(c_int), value :: n
+      integer(c_int32_t), intent(out) :: out(*)
+    end function
+    integer(c_int) function mcb_debug_gather_probe(handle, bytes, loadsInFlight, blocksPerSM, iterations, gathersPerSecond) &
+        bind(C, name="mcb_debug_gather_probe")
+      import :: c_int, c_ptr, c_int64_t, c_double
+      type(c_ptr), value :: handle
+      integer(c_int64_t), value :: bytes
+      integer(c_int), value :: loadsInFlight, blocksPerSM, iterations
+      real(c_double), intent(out) :: gathersPerSecond
+    end function
+    ! ---- multipleProcesses (MPIW:29-251) over NCCL: one process per GPU, one reduce at the end (DRV:1151-1166) ----
+    integer(c_int) function mcb_comm_unique_id(id128) bind(C, name="mcb_comm_unique_id")
+      import :: c_int, c_char
+      character(kind=c_char), intent(out) :: id128(128)        ! rank 0 creates it; MPI_BCAST carries it to the others
+    end function
+    integer(c_int) function mcb_comm_init(handle, nranks, rank, id128) bind(C, name="mcb_comm_init")
+      import :: c_int, c_ptr, c_char
+      type(c_ptr), value :: handle
+      integer(c_int), value :: nranks, rank
+      character(kind=c_char), intent(in) :: id128(128)
+    end function
+    integer(c_int) function mcb_comm_info(handle, nranks, rank, ncclVersion) bind(C, name="mcb_comm_info")
+      import :: c_int, c_ptr
+      type(c_ptr), value :: handle
+      integer(c_int), intent(out) :: nranks, rank, ncclVersion
+    end function
+    integer(c_int) function mcb_reduce_tallies(handle, root) bind(C, name="mcb_reduce_tallies")
+      import :: c_int, c_ptr
+      type(c_ptr), value :: handle
+      integer(c_int), value :: root                            ! >= 0: MPI_REDUCE to that rank; < 0: all-reduce
+    end function
+    integer(c_int) function mcb_reduce_statistics(handle, root) bind(C, name="mcb_reduce_statistics")
+      import :: c_int, c_ptr
+      type(c_ptr), value :: handle
+      integer(c_int), value :: root
+    end function
+    integer(c_int) function mcb_comm_destroy(handle) bind(C, name="mcb_comm_destroy")
+      import :: c_int, c_ptr
+      type(c_ptr), value :: handle
+    end function
   end interface
 
 contains
@@ -273,3 +402,20 @@ end module mcbrat_cuda
 !                          c_loc(thisIntegrator%intensity), c_loc(thisIntegrator%intensityByComponent))
 !     ! reportResults (INT:845-1042) is unchanged: it copies out of thisIntegrator%fluxUp etc.
 !   end subroutine
+!
+!   ! ---- multi-GPU (one MPI rank per GPU; the domain replicated; photons split by global photon id) ----
+!   ! src/multipleProcesses_mpi.f95 keeps MPI for process start-up; the tallies no longer travel through
+!   ! sumAcrossProcesses (MPIW:70-251) but through ONE NCCL reduce on the device:
+!   !
+!   !   call initializeProcesses(numProcs, thisProc)                              ! MPIW:29-52, unchanged (MPI_INIT ...)
+!   !   rc = mcb_create(int(mod(thisProc, gpusPerNode), c_int), mcIntegrator%gpu) ! in new_Integrator
+!   !   if (MasterProc) rc = mcb_comm_unique_id(ncclId)
+!   !   call MPI_BCAST(ncclId, 128, MPI_CHARACTER, 0, MPI_COMM_WORLD, ierr)
+!   !   rc = mcb_comm_init(mcIntegrator%gpu, int(numProcs, c_int), int(thisProc, c_int), ncclId)
+!   !   ... every rank, the master included, runs its block of batches:
+!   !   rc = mcb_run_batches(mcIntegrator%gpu, batchesPerProc, numPhotonsPerBatch, seed, &
+!   !                        thisProc * batchesPerProc * numPhotonsPerBatch, nDone)
+!   !   ... DRV:1151-1166, nine sumAcrossProcesses calls on host arrays, become
+!   !   rc = mcb_reduce_statistics(mcIntegrator%gpu, 0_c_int)
+!   !   if (MasterProc) rc = mcb_get_statistics(mcIntegrator%gpu, solarFlux, c_loc(meanFluxStats), c_loc(fluxUpStats), ...)
+!   !   rc = mcb_comm_destroy(mcIntegrator%gpu); call finalizeProcesses()         ! MPIW:62-68

@@ -13,6 +13,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdint>
+#include <cstdio>
 #include <cstring>
 #include <stdexcept>
 #include <string>
@@ -330,7 +331,13 @@ inline void reportResults(integrator &g, Results &r, Status &status, bool volume
 }
 
 // ---- the driver's batch loop and statistics on the device (DRV:949-1052, 1188-1228) ----
-struct Statistics { double meanFlux[6] = {0, 0, 0, 0, 0, 0}; std::vector<double> absorbedProfile, radiance; int64_t totalNumPhotons = 0, batchesCompleted = 0; };
+// every array is stats(..., 1:2) in the Fortran layout: the block of means, then the block of standard errors;
+// meanFlux = (up, down, absorbed | their standard errors)
+struct Statistics {
+  double meanFlux[6] = {0, 0, 0, 0, 0, 0};
+  std::vector<double> fluxUp, fluxDown, fluxAbsorbed, absorbedProfile, absorbedVolume, radiance;
+  int64_t totalNumPhotons = 0, batchesCompleted = 0;
+};
 inline void runBatches(integrator &g, Domain &d, randomNumberSequence &randoms, float solarMu, float solarAzimuth, int64_t numBatches,
                        int64_t numPhotonsPerBatch, Status &status) {
   stageDomain(g, d, status);
@@ -341,12 +348,179 @@ inline void runBatches(integrator &g, Domain &d, randomNumberSequence &randoms, 
     return status.setStateToFailure(g.lastMessage("computeRadiativeTransfer"));
   randoms.nextPhotonId += (uint64_t)done;
 }
-inline void reportStatistics(integrator &g, double solarFlux, Statistics &s, Status &status) {
+inline void reportStatistics(integrator &g, double solarFlux, Statistics &s, Status &status, bool pixels = false, bool volume = false) {
+  const size_t cols = (size_t)g.numX * g.numY;
   s.absorbedProfile.assign(2 * (size_t)g.numZ, 0.0);
-  s.radiance.assign(2 * (size_t)g.numX * g.numY * g.numDirections, 0.0);
-  if (mcb_get_statistics(g.gpu, solarFlux, s.meanFlux, nullptr, nullptr, nullptr, s.absorbedProfile.data(), nullptr,
+  s.radiance.assign(2 * cols * g.numDirections, 0.0);
+  if (pixels) { s.fluxUp.assign(2 * cols, 0.0); s.fluxDown.assign(2 * cols, 0.0); s.fluxAbsorbed.assign(2 * cols, 0.0); }
+  if (volume) s.absorbedVolume.assign(2 * cols * g.numZ, 0.0);
+  if (mcb_get_statistics(g.gpu, solarFlux, s.meanFlux, pixels ? s.fluxUp.data() : nullptr, pixels ? s.fluxDown.data() : nullptr,
+                         pixels ? s.fluxAbsorbed.data() : nullptr, s.absorbedProfile.data(), volume ? s.absorbedVolume.data() : nullptr,
                          g.numDirections ? s.radiance.data() : nullptr, &s.totalNumPhotons, &s.batchesCompleted))
     status.setStateToFailure(g.lastMessage("reportStatistics"));
+}
+
+// ---- multipleProcesses_mpi.f95 over NCCL (MPIW:29-251): one process per GPU ----
+// The 128-byte id is created by rank 0 (mcb_comm_unique_id) and carried to the other ranks by the host's own means --
+// MPI_BCAST in the Fortran host; the example driver uses a file.
+inline void initializeProcesses(integrator &g, int numProcs, int thisProc, const void *id128, Status &status) {   // MPIW:29-52
+  if (mcb_comm_init(g.gpu, numProcs, thisProc, id128)) status.setStateToFailure(g.lastMessage("initializeProcesses"));
+}
+inline void sumAcrossProcesses_tallies(integrator &g, Status &status, int root = 0) {                           // DRV:1151-1166
+  if (mcb_reduce_tallies(g.gpu, root) || mcb_synchronize(g.gpu)) status.setStateToFailure(g.lastMessage("sumAcrossProcesses"));
+}
+inline void sumAcrossProcesses_statistics(integrator &g, Status &status, int root = 0) {
+  if (mcb_reduce_statistics(g.gpu, root) || mcb_synchronize(g.gpu)) status.setStateToFailure(g.lastMessage("sumAcrossProcesses"));
+}
+inline void finalizeProcesses(integrator &g) { mcb_comm_destroy(g.gpu); }                                       // MPIW:62-68
+
+// ---- writeResults_ASCII (DRV:1324-1495): the driver's four ASCII tables, format-exact ----
+namespace fmt {
+// Fw.d: right-justified, the optional leading zero dropped when the field is one character short, w asterisks on overflow
+inline std::string F(double v, int w, int d) {
+  char buf[512];
+  std::snprintf(buf, sizeof(buf), "%.*f", d, v);           // glibc rounds the exact binary value, ties to even, like gfortran
+  std::string t(buf);
+  if ((int)t.size() > w) {
+    if (t.compare(0, 2, "0.") == 0) t.erase(0, 1);
+    else if (t.compare(0, 3, "-0.") == 0) t.erase(1, 1);
+  }
+  if ((int)t.size() > w) return std::string((size_t)w, '*');
+  return std::string((size_t)w - t.size(), ' ') + t;
+}
+// Ew.d: 0.ddddddE+ee
+inline std::string E(double v, int w, int d) {
+  char buf[64];
+  std::snprintf(buf, sizeof(buf), "%.*e", d - 1, std::fabs(v));        // D.ddddde+XX with d significant digits
+  std::string t(buf);
+  const size_t e = t.find('e');
+  std::string digits = t.substr(0, 1) + t.substr(2, e - 2);
+  int ex = std::atoi(t.c_str() + e + 1) + 1;
+  if (v == 0.0) ex = 0;
+  char es[16];
+  if (std::abs(ex) < 100) std::snprintf(es, sizeof(es), "E%+03d", ex); else std::snprintf(es, sizeof(es), "%+04d", ex);
+  std::string r = std::string(v < 0 ? "-" : "") + "0." + digits + es;
+  if ((int)r.size() > w) {
+    if (r.compare(0, 2, "0.") == 0) r.erase(0, 1);
+    else if (r.compare(0, 3, "-0.") == 0) r.erase(1, 1);
+  }
+  if ((int)r.size() > w) return std::string((size_t)w, '*');
+  return std::string((size_t)w - r.size(), ' ') + r;
+}
+inline std::string I(long long v, int w) {
+  const std::string t = std::to_string(v);
+  return (int)t.size() > w ? std::string((size_t)w, '*') : std::string((size_t)w - t.size(), ' ') + t;
+}
+// A60 of the driver's character(len=256) variable: the leftmost 60 characters of the blank-padded name
+inline std::string A60(const std::string &name) { std::string t = name; t.resize(256, ' '); return t.substr(0, 60); }
+inline const char *L(bool b) { return b ? "T" : "F"; }
+inline std::string pair(const std::vector<double> &stats, size_t i, size_t n) {      // 2(1X,F9.4) of stats(i, 1:2)
+  return " " + F(stats[i], 9, 4) + " " + F(stats[n + i], 9, 4);
+}
+}  // namespace fmt
+
+struct RadianceOptions {                  // module variables of the driver the radiance header prints (DRV:78-82)
+  bool useRussianRouletteForIntensity = true; float zetaMin = 0.3f;
+  bool limitIntensityContributions = false; float maxIntensityContribution = 77.0f;
+};
+
+inline void writeResults_ASCII(const std::string &domainFileName, int64_t totalNumPhotons, int /*numBatches*/, bool useRayTracing,
+                               bool useRussianRoulette, bool useHybridPhaseFunsForIntenCalcs, float hybridPhaseFunWidth,
+                               double solarFlux, float solarMu, float solarAzimuth, double surfaceAlbedo,
+                               const std::vector<double> &xPosition, const std::vector<double> &yPosition,
+                               const std::vector<double> &zPosition, const std::string &outputFluxFile, const Statistics &s,
+                               const std::string &outputAbsProfFile, const std::string &outputAbsVolumeFile,
+                               const std::string &outputRadFile, const std::vector<float> &intensityMus,
+                               const std::vector<float> &intensityPhis, const RadianceOptions &ro, Status &status) {
+  using namespace fmt;
+  const int nx = (int)xPosition.size() - 1, ny = (int)yPosition.size() - 1, nz = (int)zPosition.size() - 1;
+  const size_t cols = (size_t)nx * ny;
+  auto trimmed = [](const std::string &f) { return f.find_first_not_of(' ') != std::string::npos; };    // len_trim(f) > 0
+  auto xc = [&](int i) { return (xPosition[i] + xPosition[i + 1]) / 2.0; };
+  auto yc = [&](int j) { return (yPosition[j] + yPosition[j + 1]) / 2.0; };
+  auto header = [&](FILE *f, const char *kind, bool radiance) {
+    std::fprintf(f, "!   I3RC Monte Carlo 3D Solar Radiative Transfer: %s\n", kind);
+    std::fprintf(f, "!  Property_File=%s\n", A60(domainFileName).c_str());
+    std::fprintf(f, "!  Num_Photons=%s\n", I(totalNumPhotons, 10).c_str());
+    std::fprintf(f, "!  PhotonTracing=%s    Russian_Roulette=%s\n", L(useRayTracing), L(useRussianRoulette));
+    std::fprintf(f, "!  Hybrid_Phase_Func_for_Radiance=%s   Gaussian_Phase_Func_Width_deg=%s\n", L(useHybridPhaseFunsForIntenCalcs),
+                 F((double)hybridPhaseFunWidth, 5, 2).c_str());
+    if (radiance) {
+      std::fprintf(f, "!  Intensity_uses_Russian_Roulette=%s   Intensity_Russian_Roulette_zeta_min=%s\n",
+                   L(ro.useRussianRouletteForIntensity), F((double)ro.zetaMin, 5, 2).c_str());
+      std::fprintf(f, "!  limited_intensity_contributions=%s   max_intensity_contribution=%s\n",
+                   L(ro.limitIntensityContributions), F((double)ro.maxIntensityContribution, 5, 2).c_str());
+    }
+    std::fprintf(f, "!  Solar_Flux=%s   Solar_Mu=%s   Solar_Phi=%s\n", E(solarFlux, 13, 6).c_str(), F((double)solarMu, 10, 7).c_str(),
+                 F((double)solarAzimuth, 7, 3).c_str());
+    std::fprintf(f, "!  Lambertian_Surface_Albedo=%s\n", F(surfaceAlbedo, 7, 4).c_str());
+  };
+  auto open = [&](const std::string &name) -> FILE * {
+    const size_t a = name.find_first_not_of(' '), b = name.find_last_not_of(' ');
+    FILE *f = std::fopen(name.substr(a, b - a + 1).c_str(), "w");
+    if (!f) status.setStateToFailure("writeResults_ASCII: cannot open " + name);
+    return f;
+  };
+  if (trimmed(outputFluxFile) && s.fluxUp.size() == 2 * cols) {                                      // DRV:1375-1403
+    FILE *f = open(outputFluxFile); if (!f) return;
+    header(f, "Flux", false);
+    std::fprintf(f, "!  Output_Type= Pixel Flux\n");
+    std::fprintf(f, "!  Upwelling_Level=%s   Downwelling_level=%s\n", F(zPosition[nz], 7, 3).c_str(), F(zPosition[0], 7, 3).c_str());
+    std::fprintf(f, "!   X      Y           Flux_Up             Flux_Down            Flux_Absorbed \n");
+    std::fprintf(f, "!                  Mean     StdErr       Mean     StdErr       Mean     StdErr\n");
+    std::fprintf(f, "!  Average:   ");
+    for (int q = 0; q < 3; ++q) std::fprintf(f, "  %s %s", F(s.meanFlux[q], 9, 4).c_str(), F(s.meanFlux[3 + q], 9, 4).c_str());
+    std::fprintf(f, "\n");
+    for (int j = 0; j < ny; ++j)
+      for (int i = 0; i < nx; ++i) {
+        const size_t c = (size_t)i + (size_t)nx * j;
+        std::fprintf(f, "%s%s %s %s %s\n", F(xc(i), 7, 3).c_str(), F(yc(j), 7, 3).c_str(), pair(s.fluxUp, c, cols).c_str(),
+                     pair(s.fluxDown, c, cols).c_str(), pair(s.fluxAbsorbed, c, cols).c_str());
+      }
+    std::fclose(f);
+  }
+  if (trimmed(outputAbsProfFile) && s.absorbedProfile.size() == 2 * (size_t)nz) {                    // DRV:1410-1431
+    FILE *f = open(outputAbsProfFile); if (!f) return;
+    header(f, "Absorption Profile", false);
+    std::fprintf(f, "!  Output_Type= Absorption Profile\n!   Z    Absorbed_Flux (flux/km) \n!          Mean     StdErr \n");
+    for (int k = 0; k < nz; ++k)
+      std::fprintf(f, "%s %s\n", F(0.5 * (zPosition[k] + zPosition[k + 1]), 7, 3).c_str(), pair(s.absorbedProfile, (size_t)k, (size_t)nz).c_str());
+    std::fclose(f);
+  }
+  if (trimmed(outputAbsVolumeFile) && s.absorbedVolume.size() == 2 * cols * nz) {                    // DRV:1437-1463
+    FILE *f = open(outputAbsVolumeFile); if (!f) return;
+    header(f, "3D Absorption Field", false);
+    std::fprintf(f, "!  Output_Type= Volume Absorption \n!    X       Y        Z       Absorbed_Flux (flux/km)\n"
+                    "!                               Mean     StdErr \n");
+    for (int i = 0; i < nx; ++i)
+      for (int j = 0; j < ny; ++j)
+        for (int k = 0; k < nz; ++k)
+          std::fprintf(f, "%s %s %s %s\n", F(xc(i), 7, 3).c_str(), F(yc(j), 7, 3).c_str(),
+                       F((zPosition[k] + zPosition[k + 1]) / 2.0, 7, 3).c_str(),
+                       pair(s.absorbedVolume, (size_t)i + (size_t)nx * ((size_t)j + (size_t)ny * k), cols * nz).c_str());
+    std::fclose(f);
+  }
+  if (trimmed(outputRadFile) && !s.radiance.empty()) {                                               // DRV:1468-1493
+    FILE *f = open(outputRadFile); if (!f) return;
+    int numRadDir = 0;
+    for (float m : intensityMus) numRadDir += std::fabs(m) > 0.0f ? 1 : 0;
+    const size_t n = s.radiance.size() / 2;
+    header(f, "Radiance", true);
+    std::fprintf(f, "!  Output_Type= Pixel Radiance\n");
+    std::fprintf(f, "!  RADIANCE AT Z=%s   NXO=%s   NYO=%s   NDIR=%s\n", F(zPosition[nz], 7, 3).c_str(), I(nx, 4).c_str(), I(ny, 4).c_str(),
+                 I(numRadDir, 4).c_str());
+    std::fprintf(f, "!   X      Y         Radiance (Mean, StdErr)\n");
+    for (int k = 0; k < numRadDir; ++k) {
+      std::fprintf(f, "!  %s %s  <- (mu,phi)\n", F((double)intensityMus[k], 8, 5).c_str(), F((double)intensityPhis[k], 6, 2).c_str());
+      for (int j = 0; j < ny; ++j)
+        for (int i = 0; i < nx; ++i) {
+          const size_t c = (size_t)i + (size_t)nx * ((size_t)j + (size_t)ny * k);
+          std::fprintf(f, "%s%s %s %s\n", F(xc(i), 7, 3).c_str(), F(yc(j), 7, 3).c_str(), F(s.radiance[c], 9, 4).c_str(),
+                       F(s.radiance[n + c], 9, 4).c_str());
+        }
+    }
+    std::fclose(f);
+  }
 }
 
 }  // namespace mcbrat

@@ -186,7 +186,13 @@ enum { MARCH_ON = ST_MARCH, MARCH_HIT = ST_SCATTER, MARCH_BOTTOM = ST_SURFACE, M
 // BRICK: the field is read in its 2x2x2-brick layout (mcb_device.cuh).  The address is carried along incrementally: a
 // move along an axis adds that axis' current step, and the step then alternates between "inside the brick" and "on to
 // the next brick" -- two predicated integer instructions per axis instead of one, no multiplications.
-template <bool REG, bool WIDE, int B, bool MASK, bool BRICK>
+//
+// RAW (photon-pool kernel): a burst that ends at an event leaves the ray in its raw state -- r.t at the event, r.ix =
+// the hit cell's padded address (hits), indices untouched (exits) -- and the caller decodes cell and position later,
+// where all 32 lanes have an event to decode (mcb_pool.cu's event phase), instead of here with a third of the lanes.
+// SPLIT: the gathers of the second half of the burst are issued only by lanes whose target was not met in the first
+// half (one more dependent round trip per burst, fewer requests on the L1TEX -> L2 path that bounds the kernel).
+template <bool REG, bool WIDE, int B, bool MASK, bool BRICK, bool RAW = false, bool SPLIT = false>
 __device__ __forceinline__ int march_burst(Ray &r, const DevDomain &P, const Grid &G,
                                            float &ext, float target, unsigned &crossings) {
   const DevDomain::ExtField &F = BRICK ? P.brk : P.lin;
@@ -236,22 +242,34 @@ __device__ __forceinline__ int march_burst(Ray &r, const DevDomain &P, const Gri
       { const bool c = r.tz <= tmin; r.iz += c ? sz : 0; const float nt = (G.sz[r.iz + (sz > 0 ? 1 : 0)] - r.oz) * r.rz; r.tz = c ? nt : r.tz; }
     }
   }
-#pragma unroll
-  for (int k = 0; k < B; ++k) {
-    if (MASK) {                                        // bit p of the bitmap: the shift count wraps modulo 32
-      if (__funnelshift_r(mw[k], 0u, (uint32_t)(ck[k] + F.origin)) & 1u) sg[k] = EXT_AT(P, F, ck[k]);
-    } else {
-      sg[k] = EXT_AT(P, F, ck[k]);
-    }
-  }
   // accumulate until the target is passed (OPT:1729-1738); from there on acc / tS stay frozen at the
   // ENTRY of the hit cell, so only its extinction and index have to be carried along
   float acc = ext, tS = t0, hS = 1.0f;
   int hC = 0;
   int hK = B - 1;                                      // burst position of the hit cell
   bool found = false;
+  constexpr int H = SPLIT ? B / 2 : B;                 // gathers issued up front
+#pragma unroll
+  for (int k = 0; k < H; ++k) {
+    if (MASK) {                                        // bit p of the bitmap: the shift count wraps modulo 32
+      if (__funnelshift_r(mw[k], 0u, (uint32_t)(ck[k] + F.origin)) & 1u) sg[k] = EXT_AT(P, F, ck[k]);
+    } else {
+      sg[k] = EXT_AT(P, F, ck[k]);
+    }
+  }
 #pragma unroll
   for (int k = 0; k < B; ++k) {
+    if (SPLIT && k == H) {                             // second half: only where the first half did not reach the target
+#pragma unroll
+      for (int j = H; j < B; ++j) {
+        if (MASK) {
+          if (!found && (__funnelshift_r(mw[j], 0u, (uint32_t)(ck[j] + F.origin)) & 1u)) sg[j] = EXT_AT(P, F, ck[j]);
+        } else {
+          sg[j] = 0.0f;
+          if (!found) sg[j] = EXT_AT(P, F, ck[j]);
+        }
+      }
+    }
     const float en = fmaf(tE[k] - tS, sg[k], acc);
     const bool h = !found && en > target;
     hS = h ? sg[k] : hS; hC = h ? ck[k] : hC; hK = h ? k : hK;
@@ -261,7 +279,7 @@ __device__ __forceinline__ int march_burst(Ray &r, const DevDomain &P, const Gri
   if (found) {
     crossings += (unsigned)(hK + 1);               // cells entered up to and including the hit cell
     r.t = tS + __fdividef(target - acc, hS);           // where the target optical depth is met (OPT:1731)
-    cell_decode<WIDE, BRICK>(P, hC, r.ix, r.iy, r.iz);
+    if (RAW) r.ix = hC; else cell_decode<WIDE, BRICK>(P, hC, r.ix, r.iy, r.iz);
     return MARCH_HIT;
   }
   ext = acc;
@@ -273,6 +291,7 @@ __device__ __forceinline__ int march_burst(Ray &r, const DevDomain &P, const Gri
     for (int k = 1; k < B; ++k) nv += tE[k - 1] < tX ? 1u : 0u;
     crossings += nv;
     r.t = tX;
+    if (RAW) return top ? MARCH_TOP : MARCH_BOTTOM;
     float px, py, pz;
     ray_position(r, P, px, py, pz);
     if (REG) {

@@ -4,7 +4,7 @@
 // The park/regroup kernel keeps one photon per lane: a lane that reaches an event idles until half the warp has
 // arrived, and the event phase then runs with the other half idle (ncu, round 1: 20 of 32 lanes active per
 // instruction -- march code 26, event code 16).  Here every warp owns a POOL of 64 photons: 32 are in the lanes'
-// registers, marching; the others wait in shared memory as 14-word records in one of two stacks that grow towards
+// registers, marching; the others wait in shared memory as 17-word records in one of two stacks that grow towards
 // each other inside one array of 64 slots,
 //     READY  [0, nR)        legs that have been set up (origin, direction, cell, target optical depth) and wait for a lane
 //     EVENT  [64 - nE, 64)  photons that reached an event (scattering, surface, top) and wait for the event phase
@@ -19,9 +19,12 @@
 // so the stacks cannot collide.
 //
 // A record is the universal hand-over format: position, direction, weight, target optical depth, the uniform that
-// picks the component at the next scattering, the photon's Philox counter, its cell and the kind of event.  The
-// marcher's derived state (reciprocal directions, face distances) is rebuilt by ray_start when a lane pops a leg --
-// work the park/regroup kernel does at the end of its event phase anyway.
+// picks the component at the next scattering, the photon's Philox counter, its cell and the kind of event.
+// Everything that is work per EVENT rather than per cell runs in the event phase, where all 32 lanes have an event:
+// a marching lane pushes its ray RAW (leg origin, distance along the leg, padded address of the hit cell) and the
+// event phase decodes cell and position; the event phase also sets the next leg up completely (first face
+// distances), so a lane that pops a READY leg only loads it.  (First version: decode and leg set-up ran in the march
+// loop with the ~12 lanes that had just arrived -- 200 warp-instructions per burst at 12 of 32 lanes, ncu r02.)
 //
 // Scope: flux / absorption runs (no view directions) on uniform grids at least a ghost shell wide -- C1, C3, C4, C5.
 // Everything else stays on mcb_fast.cu.  Statistical parity with the reference arithmetic (criterion (b)) is tested
@@ -33,11 +36,14 @@ namespace mcbpool {
 
 using namespace mcbfast;
 
-#define POOL_WORDS 14
+#define POOL_WORDS 17
 #define POOL_SLOTS 64
-enum { PW_PX = 0, PW_PY, PW_PZ, PW_DX, PW_DY, PW_DZ, PW_W, PW_TAU, PW_UNEXT, PW_C0, PW_C1, PW_BLK, PW_IXY, PW_IZK };
+// EVENT records: PX.. = leg origin, TAU = distance along the leg, IXY = padded address of the hit cell, IZK = kind << 28
+// READY records: PX.. = leg origin, TAU = target optical depth, IXY / IZK = cell, TX.. = first face distances
+enum { PW_PX = 0, PW_PY, PW_PZ, PW_DX, PW_DY, PW_DZ, PW_W, PW_TAU, PW_UNEXT, PW_C0, PW_C1, PW_BLK, PW_IXY, PW_IZK,
+       PW_TX, PW_TY, PW_TZ };
 
-template <int THREADS, int MINBLOCKS, int BURST, bool MASK, bool BRICK>
+template <int THREADS, int MINBLOCKS, int BURST, bool SPLIT, bool MASK, bool BRICK>
 __global__ void __launch_bounds__(THREADS, MINBLOCKS)
 pool_kernel(const __grid_constant__ DevDomain P, long long nPhotons, uint64_t seed, uint64_t firstPhotonId,
             unsigned long long *workCounter, const SmemPlan plan) {
@@ -92,13 +98,24 @@ pool_kernel(const __grid_constant__ DevDomain P, long long nPhotons, uint64_t se
         const int izk = __float_as_int(pool[PW_IZK * POOL_SLOTS + slot]);
         state = (int)((uint32_t)izk >> 28);
         if (state != ST_DEAD) {
-          const int ixy = __float_as_int(pool[PW_IXY * POOL_SLOTS + slot]);
-          ix = ixy & 0xffff; iy = (int)((uint32_t)ixy >> 16); iz = izk & 0xffff;
+          const int raw = __float_as_int(pool[PW_IXY * POOL_SLOTS + slot]);
+          const float t = pool[PW_TAU * POOL_SLOTS + slot];
           px = pool[PW_PX * POOL_SLOTS + slot]; py = pool[PW_PY * POOL_SLOTS + slot]; pz = pool[PW_PZ * POOL_SLOTS + slot];
           dx = pool[PW_DX * POOL_SLOTS + slot]; dy = pool[PW_DY * POOL_SLOTS + slot]; dz = pool[PW_DZ * POOL_SLOTS + slot];
           ew = pool[PW_W * POOL_SLOTS + slot]; eNext = pool[PW_UNEXT * POOL_SLOTS + slot];
           rng.c0 = __float_as_uint(pool[PW_C0 * POOL_SLOTS + slot]); rng.c1 = __float_as_uint(pool[PW_C1 * POOL_SLOTS + slot]);
           rng.blk = __float_as_uint(pool[PW_BLK * POOL_SLOTS + slot]);
+          // where the leg ended, folded back into the periodic domain (ray_position), and in which cell
+          px = fmaf(t, dx, px); py = fmaf(t, dy, py); pz = fmaf(t, dz, pz);
+          px -= P.fLx * floorf((px - P.fx0) * P.finvLx);
+          py -= P.fLy * floorf((py - P.fy0) * P.finvLy);
+          if (state == ST_SCATTER) {
+            cell_decode<true, BRICK>(P, raw, ix, iy, iz);
+          } else {                                         // left through the top / reached the surface: column of the exit point
+            ix = min(max((int)((px - P.fx0) * P.finvhx), 0), P.nx - 1);
+            iy = min(max((int)((py - P.fy0) * P.finvhy), 0), P.ny - 1);
+            iz = state == ST_TOP ? P.nz - 1 : 0;
+          }
         }
       }
       int comp = 1, pidx = 1;
@@ -245,10 +262,16 @@ pool_kernel(const __grid_constant__ DevDomain P, long long nPhotons, uint64_t se
         eTau = -__logf(fmaxf(TINY32, u.z));                                      // INT:554
         eNext = u.w;
       }
-      // ---- push the new legs onto READY ----
+      // ---- push the new legs, completely set up, onto READY ----
       const unsigned m = __ballot_sync(FULL, alive);
       if (alive) {
         const int s = nR + __popc(m & below);
+        {
+          Ray q;
+          q.ox = px; q.oy = py; q.oz = pz; q.dx = dx; q.dy = dy; q.dz = dz; q.ix = ix; q.iy = iy; q.iz = iz;
+          ray_start<true>(q, P, G);
+          pool[PW_TX * POOL_SLOTS + s] = q.tx; pool[PW_TY * POOL_SLOTS + s] = q.ty; pool[PW_TZ * POOL_SLOTS + s] = q.tz;
+        }
         pool[PW_PX * POOL_SLOTS + s] = px; pool[PW_PY * POOL_SLOTS + s] = py; pool[PW_PZ * POOL_SLOTS + s] = pz;
         pool[PW_DX * POOL_SLOTS + s] = dx; pool[PW_DY * POOL_SLOTS + s] = dy; pool[PW_DZ * POOL_SLOTS + s] = dz;
         pool[PW_W * POOL_SLOTS + s] = ew; pool[PW_TAU * POOL_SLOTS + s] = eTau; pool[PW_UNEXT * POOL_SLOTS + s] = eNext;
@@ -276,8 +299,9 @@ pool_kernel(const __grid_constant__ DevDomain P, long long nPhotons, uint64_t se
           const int ixy = __float_as_int(pool[PW_IXY * POOL_SLOTS + s]);
           r.ix = ixy & 0xffff; r.iy = (int)((uint32_t)ixy >> 16);
           r.iz = __float_as_int(pool[PW_IZK * POOL_SLOTS + s]);
-          ext = 0.0f;
-          ray_start<true>(r, P, G);
+          r.tx = pool[PW_TX * POOL_SLOTS + s]; r.ty = pool[PW_TY * POOL_SLOTS + s]; r.tz = pool[PW_TZ * POOL_SLOTS + s];
+          r.rx = safe_rcp(r.dx); r.ry = safe_rcp(r.dy); r.rz = safe_rcp(r.dz);
+          r.t = 0.0f; ext = 0.0f;
           have = true;
         }
         nR -= min(__popc(idle), nR);
@@ -288,7 +312,7 @@ pool_kernel(const __grid_constant__ DevDomain P, long long nPhotons, uint64_t se
 
     // =========================== march: one burst for every lane ===========================
     int ev = MARCH_ON;
-    if (have) ev = march_burst<true, true, BURST, MASK, BRICK>(r, P, G, ext, tau, crossings);
+    if (have) ev = march_burst<true, true, BURST, MASK, BRICK, true, SPLIT>(r, P, G, ext, tau, crossings);
 
     // =========================== photons that reached an event go onto EVENT ===========================
     {
@@ -296,16 +320,14 @@ pool_kernel(const __grid_constant__ DevDomain P, long long nPhotons, uint64_t se
       const unsigned hit = __ballot_sync(FULL, arrived);
       if (hit) {
         if (arrived) {
-          const int s = POOL_SLOTS - nE - 1 - __popc(hit & below);
-          float px, py, pz;
-          ray_position(r, P, px, py, pz);
-          pool[PW_PX * POOL_SLOTS + s] = px; pool[PW_PY * POOL_SLOTS + s] = py; pool[PW_PZ * POOL_SLOTS + s] = pz;
+          const int s = POOL_SLOTS - nE - 1 - __popc(hit & below);       // the ray as the burst left it (RAW)
+          pool[PW_PX * POOL_SLOTS + s] = r.ox; pool[PW_PY * POOL_SLOTS + s] = r.oy; pool[PW_PZ * POOL_SLOTS + s] = r.oz;
           pool[PW_DX * POOL_SLOTS + s] = r.dx; pool[PW_DY * POOL_SLOTS + s] = r.dy; pool[PW_DZ * POOL_SLOTS + s] = r.dz;
-          pool[PW_W * POOL_SLOTS + s] = w; pool[PW_UNEXT * POOL_SLOTS + s] = uNext;
+          pool[PW_W * POOL_SLOTS + s] = w; pool[PW_TAU * POOL_SLOTS + s] = r.t; pool[PW_UNEXT * POOL_SLOTS + s] = uNext;
           pool[PW_C0 * POOL_SLOTS + s] = __uint_as_float(c0); pool[PW_C1 * POOL_SLOTS + s] = __uint_as_float(c1);
           pool[PW_BLK * POOL_SLOTS + s] = __uint_as_float(blk);
-          pool[PW_IXY * POOL_SLOTS + s] = __int_as_float(r.ix | (r.iy << 16));
-          pool[PW_IZK * POOL_SLOTS + s] = __int_as_float(r.iz | (ev << 28));
+          pool[PW_IXY * POOL_SLOTS + s] = __int_as_float(r.ix);
+          pool[PW_IZK * POOL_SLOTS + s] = __int_as_float(ev << 28);
           have = false;
         }
         nE += __popc(hit);
@@ -349,11 +371,11 @@ pool_kernel(const __grid_constant__ DevDomain P, long long nPhotons, uint64_t se
 
 }  // namespace mcbpool
 
-template <int MINBLOCKS, int BURST, bool MASK, bool BRICK>
+template <int MINBLOCKS, int BURST, bool SPLIT, bool MASK, bool BRICK>
 static void launch_pool(const DevDomain &P, long long nPhotons, uint64_t seed, uint64_t firstPhotonId, int numSMs,
                         unsigned long long *workCounter, cudaStream_t stream) {
   constexpr int THREADS = 128;
-  auto kernel = mcbpool::pool_kernel<THREADS, MINBLOCKS, BURST, MASK, BRICK>;
+  auto kernel = mcbpool::pool_kernel<THREADS, MINBLOCKS, BURST, SPLIT, MASK, BRICK>;
   const int cols = P.nx * P.ny, cells = cols * P.nz;
   mcbfast::SmemPlan plan{-1, -1, -1, -1, -1, 0, 0, 0};
   int off = 0;
@@ -375,6 +397,13 @@ static void launch_pool(const DevDomain &P, long long nPhotons, uint64_t seed, u
   kernel<<<blocks, THREADS, smem, stream>>>(P, nPhotons, seed, firstPhotonId, workCounter, plan);
 }
 
+#ifndef MCB_POOL_DEFAULT_BURST
+#define MCB_POOL_DEFAULT_BURST 8
+#endif
+#ifndef MCB_POOL_DEFAULT_OCC
+#define MCB_POOL_DEFAULT_OCC 6
+#endif
+
 // the pool kernel covers flux-only runs on uniform grids at least a ghost shell wide
 bool mcb_pool_covers(const DevDomain &P) {
   return P.uniform && P.nx >= MCB_GHOST && P.ny >= MCB_GHOST && P.nDir == 0 && P.nx <= 65535 && P.ny <= 65535 && P.nz <= 65535;
@@ -384,14 +413,15 @@ void mcb_launch_pool_batch(const DevDomain &P, long long nPhotons, uint64_t seed
                            int numSMs, unsigned long long *workCounter, cudaStream_t stream) {
   if (nPhotons <= 0) return;
   const bool mask = P.lin.mask != nullptr, brick = P.opt.tuneLayout != MCB_LAYOUT_LINEAR;
-  const int burst = P.opt.tuneBurst == 4 ? 4 : 8;
-  const int occ = P.opt.tuneBlocksPerSM;             // register budget: 8 CTAs/SM = 64 registers, 6 = 80
-#define MCB_POOL_GO(OCC, B, MASK, BRICK) launch_pool<OCC, B, MASK, BRICK>(P, nPhotons, seed, firstPhotonId, numSMs, workCounter, stream)
-#define MCB_POOL_LAYOUT(OCC, B) \
-  do { if (mask) { if (brick) MCB_POOL_GO(OCC, B, true, true); else MCB_POOL_GO(OCC, B, true, false); } \
-       else { if (brick) MCB_POOL_GO(OCC, B, false, true); else MCB_POOL_GO(OCC, B, false, false); } } while (0)
-  if (occ >= 8) { if (burst == 4) MCB_POOL_LAYOUT(8, 4); else MCB_POOL_LAYOUT(8, 8); }
-  else { if (burst == 4) MCB_POOL_LAYOUT(6, 4); else MCB_POOL_LAYOUT(6, 8); }
+  // tuneBurst: 8 = eight cells per burst, all gathers up front; 4 = four; 44 = eight cells, gathers in two halves (SPLIT)
+  const int burst = P.opt.tuneBurst ? P.opt.tuneBurst : MCB_POOL_DEFAULT_BURST;
+  const int occ = P.opt.tuneBlocksPerSM ? P.opt.tuneBlocksPerSM : MCB_POOL_DEFAULT_OCC;   // register budget: 8 CTAs/SM = 64 registers, 6 = 80
+#define MCB_POOL_GO(OCC, B, SPLIT, MASK, BRICK) launch_pool<OCC, B, SPLIT, MASK, BRICK>(P, nPhotons, seed, firstPhotonId, numSMs, workCounter, stream)
+#define MCB_POOL_LAYOUT(OCC, B, SPLIT) \
+  do { if (mask) { if (brick) MCB_POOL_GO(OCC, B, SPLIT, true, true); else MCB_POOL_GO(OCC, B, SPLIT, true, false); } \
+       else { if (brick) MCB_POOL_GO(OCC, B, SPLIT, false, true); else MCB_POOL_GO(OCC, B, SPLIT, false, false); } } while (0)
+  if (occ >= 8) { if (burst == 4) MCB_POOL_LAYOUT(8, 4, false); else if (burst == 44) MCB_POOL_LAYOUT(8, 8, true); else MCB_POOL_LAYOUT(8, 8, false); }
+  else { if (burst == 4) MCB_POOL_LAYOUT(6, 4, false); else if (burst == 44) MCB_POOL_LAYOUT(6, 8, true); else MCB_POOL_LAYOUT(6, 8, false); }
 #undef MCB_POOL_LAYOUT
 #undef MCB_POOL_GO
 }

@@ -81,3 +81,25 @@ def test_no_environment_variables_on_the_launch_path():
     for f in os.listdir(csrc):
         if f.endswith((".cu", ".cuh")):
             assert "getenv" not in open(os.path.join(csrc, f)).read(), f
+
+
+def test_fortran_module_binds_every_declared_symbol():
+    """fortran/mcbrat_cuda_mod.f90 (the ISO_C_BINDING layer of the reference-side integration) has a bind(C) interface
+    for every entry point of the header, lists it as public, and mirrors the option struct field by field."""
+    text = open(os.path.join(ROOT, "fortran", "mcbrat_cuda_mod.f90")).read()
+    bound = set(re.findall(r'bind\(C,\s*name="(mcb_\w+)"\)', text))
+    assert bound == set(_declared()), (sorted(set(_declared()) - bound), sorted(bound - set(_declared())))
+    public = re.search(r"public :: mcb_create.*?\n\n", text, re.S).group(0)
+    for name in _declared():
+        assert re.search(r"\b%s\b" % name, public), "not public: " + name
+    block = re.search(r"type, bind\(C\), public :: mcb_options(.*?)end type mcb_options", text, re.S).group(1)
+    block = re.sub(r"!.*", "", block)
+    fields = []
+    for decl in re.findall(r"::\s*(.+)", block):
+        for f in decl.split(","):
+            m = re.match(r"\s*(\w+)(?:\((\d+)\))?", f)
+            fields += [m.group(1)] * int(m.group(2) or 1)
+    want = []
+    for n, t in _lib.mcb_options._fields_:
+        want += [n] * (C.sizeof(t) // 4)
+    assert fields == want, (fields, want)

@@ -52,8 +52,7 @@ def test_compiled_host_matches_python_host(deck, views):
             specifyParameters(g, intensityMus=case["intensityMus"], intensityPhis=case["intensityPhis"], computeIntensity=True,
                               useRussianRouletteForIntensity=True, zetaMin=0.3)
         specifyParameters(g, minInverseTableSize=10001)
-        rs = new_RandomNumberSequence([10, 1, 0])
-        rs.nextPhotonId = n                                   # the driver spends its first n photon ids on the single batch
+        rs = new_RandomNumberSequence([10, 1, 0])           # the driver's batch loop starts at photon id 0 as well
         ps = new_PhotonStream(0.5, 0.0, nb * n, rs)
         resetDeviceStatistics(g, dom)
         computeRadiativeTransferBatches(g, dom, rs, ps, n, nb)
@@ -69,3 +68,46 @@ def test_compiled_host_matches_python_host(deck, views):
         rad = [float(v) for v in re.findall(r"Radiance view \d+\s+(\S+)", out)]
         want = mean["intensity"].reshape(5, -1).mean(axis=1)
         assert len(rad) == 5 and np.allclose(rad, want, rtol=0.05)
+
+
+@pytest.mark.gpu
+def test_compiled_host_writes_the_ascii_tables(tmp_path):
+    """--out PREFIX: the driver's four ASCII tables (writeResults_ASCII, DRV:1324-1495) from device-side statistics."""
+    _build()
+    prefix = str(tmp_path / "step")
+    subprocess.run([EXE, "stepcloud", "8", "20000", "10", "1", "--out", prefix], capture_output=True, text=True, check=True)
+    flux = open(prefix + "_flux.out").read().split("\n")
+    assert flux[0] == "!   I3RC Monte Carlo 3D Solar Radiative Transfer: Flux"
+    assert flux[2] == "!  Num_Photons=    160000"
+    rows = [l for l in flux if l and not l.startswith("!")]
+    assert len(rows) == 32 and all(len(l) == 14 + 3 * 21 for l in rows)
+    up = np.array([float(l[14:25]) for l in rows])
+    avg = float(flux[12][14:25])
+    assert abs(up.mean() - avg) < 2e-4                      # the average line is the mean of the pixel column
+    rad = open(prefix + "_rad.out").read().split("\n")
+    assert sum(1 for l in rad if l.endswith("<- (mu,phi)")) == 5
+    assert "NXO=  32   NYO=   1   NDIR=   5" in rad[11]
+    prof = [l for l in open(prefix + "_absprof.out").read().split("\n") if l and not l.startswith("!")]
+    assert len(prof) == 32
+    vol = [l for l in open(prefix + "_absvol.out").read().split("\n") if l and not l.startswith("!")]
+    assert len(vol) == 32 * 32
+
+
+@pytest.mark.gpu
+def test_compiled_host_ranks_reduce_through_the_c_abi():
+    """--ranks 2: one process per GPU, mcb_comm_init + ONE mcb_reduce_statistics (ncclReduce) -- the same batches as
+    the single-process run (same global photon ids), so the means agree to f64 summation order."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    _build()
+    args = ["stepcloud", "16", "50000", "10", "0"]
+    one = subprocess.run([EXE] + args, capture_output=True, text=True, check=True).stdout
+    two = subprocess.run([EXE] + args + ["--ranks", "2"], capture_output=True, text=True, check=True, timeout=300).stdout
+    assert "ranks 2 batches 16 photons 800000" in two and "ranks 1 batches 16 photons 800000" in one
+
+    def means(text):
+        m = re.search(r"means (\S+) (\S+) (\S+)  errors (\S+) (\S+) (\S+)", text)
+        return np.array([float(v) for v in m.groups()])
+    np.testing.assert_allclose(means(two)[:3], means(one)[:3], rtol=1e-10, atol=1e-14)
+    np.testing.assert_allclose(means(two)[3:], means(one)[3:], rtol=1e-5, atol=1e-12)     # sqrt(m2 - m1^2): cancellation
