@@ -32,12 +32,32 @@ import numpy as np  # noqa: E402
 METRIC = "photons/sec, I3RC Landsat SW cloud"
 UNIT = "photons/s"
 # --workload c5: the BASELINE configs[4] domain at one wavelength (a parity / HBM-roofline case, not the headline line)
+# --workload broadband: configs[4] proper -- 32 wavelength bins on the 325x325x160 domain, a step = one whole spectral run
 METRIC_C5 = "photons/sec, I3RC bench SW cloud (C5, one wavelength bin)"
+METRIC_BB = "photons/sec, I3RC bench SW broadband (C5, 32 wavelength bins)"
 WORKLOAD_C5 = ("C5 I3RC bench cloud (synthetic scene, seed 5) 325x325x150 cells 0.0625x0.0625x0.03125 km, HG g=0.85 cloud "
-               "(ssa 0.999) + Rayleigh background (nc=2), mu0=0.5, albedo 0.05; fluxes + column/volume absorption; "
+               "(ssa 0.999) + Rayleigh background at 0.55 um (nc=2), mu0=0.5, albedo 0.05; fluxes + column/volume absorption; "
                "93 MB padded f32 extinction field (> L2) marched through the occupancy bitmap")
+WORKLOAD_BB = ("C5 I3RC_bench_SW broadband: 325x325x160 cells, 32 wavelength bins 0.45-2.1 um, per-bin cloud optics interpolated "
+               "in effective radius + gas absorption + Rayleigh (nc=3), photons allocated to bins by the flux CDF, mu0=0.5; "
+               "a step = one whole spectral run (per-bin assembly, tables, photon allocation, tracing, batch statistics)")
 WORKLOAD = ("C3 I3RC Landsat cloud (synthetic scene, seed 43) 128x128x119 cells 30x30x20, HG g=0.85 (299 Legendre terms), "
             "ssa=0.99, mu0=0.5, albedo 0; fluxes + column/volume absorption; nPhaseIntervals=10001")
+L2_NOTE = {"c3": "optical-property arrays are L2-resident by construction (<= 126 MB); a 256 MB buffer is rewritten between "
+                 "timed steps (L2 flush), outside the per-step event pairs",
+           "c5": "inputs (93 MB extinction field + 253 MB event records) are larger than L2; a 256 MB buffer is rewritten "
+                 "between timed steps (L2 flush), outside the per-step event pairs",
+           "broadband": "inputs are larger than L2 and every wavelength bin rebuilds them; a 256 MB buffer is rewritten "
+                        "between timed steps (L2 flush), outside the per-step event pairs"}
+
+
+POOL_IS_DEFAULT = True          # csrc/mcb_fast.cu: MCB_DEFAULT_KERNEL (flux-only runs on uniform grids)
+
+
+def config_of(args):
+    """The `config` object of the JSON line -- the SAME in both arms (the driver compares them)."""
+    return {"workload": WORKLOAD + (" + 5 radiance views (local estimation, RR zeta_min 0.3)" if args.views else ""),
+            "l2": L2_NOTE[args.workload]}
 
 
 def parse():
@@ -51,22 +71,33 @@ def parse():
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target CPU time of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--views", action="store_true", help="add the 5 I3RC radiance directions (local estimation)")
-    ap.add_argument("--workload", default="c3", choices=["c3", "c5"],
-                    help="c3 = the metric's configuration (default); c5 = the 325x325x150 bench domain (HBM-sized field)")
+    ap.add_argument("--workload", default="c3", choices=["c3", "c5", "broadband"],
+                    help="c3 = the metric's configuration (default); c5 = the 325x325x150 bench domain (HBM-sized field), one "
+                         "wavelength; broadband = the 32-bin spectral run on that domain")
+    ap.add_argument("--kernel", type=int, default=0, help="mcb_options.tuneKernel (0 = the library's choice)")
     a = ap.parse_args()
+    global METRIC, WORKLOAD
     if a.workload == "c5":
-        global METRIC, WORKLOAD
         METRIC, WORKLOAD = METRIC_C5, WORKLOAD_C5
-        if a.views:
-            ap.error("--views is defined for the c3 workload")
+    elif a.workload == "broadband":
+        METRIC, WORKLOAD = METRIC_BB, WORKLOAD_BB
+        if a.photons == 125_000_000:
+            a.photons = 320_000_000                     # photons per GPU per spectral run
+    if a.workload != "c3" and a.views:
+        ap.error("--views is defined for the c3 workload")
     return a
 
 
 def make_case(views=False, workload="c3"):
     from mcbrat3d_b200 import domains
-    if workload == "c5":
-        dom, case = domains.bench_domain()
+    if workload in ("c5", "broadband"):
+        # the scene as the driver holds it: the physical state + a single-scattering-property table; the dense arrays of
+        # one wavelength come out of read_SSPTable (host mirror here; in HBM for the e2e leg)
+        from mcbrat3d_b200.opticalProperties import read_SSPTable
+        common, tables, case = domains.bench_problem()
+        dom = read_SSPTable(tables, 1, common, calcRayl=True)
         dom.tabulateInversePhaseFunctions(10001)
+        case = dict(case, physical=(common, tables))
         return dom, case
     dom, case = domains.landsat_cloud(ssa=0.99)
     dom.tabulateInversePhaseFunctions(10001)
@@ -100,11 +131,15 @@ def cpu_rate(dom, case, seconds, views=False):
     total, batches, _ = orc.run_workers(make, workers, nb * workers, batch,
                                         solarMu=case["solarMu"], solarAzimuth=case["solarAzimuth"])
     dt = time.perf_counter() - t0
-    # What the reference pays on top of the loop, per batch and per worker: computeRT copies totalExt, cumulativeExt,
-    # ssa and phaseFunctionIndex out of the domain (INT:434-443).  Timed here as W concurrent memcpys of the same
-    # arrays (NumPy releases the GIL in copy); the per-batch table rebuild (INT:280-285) is NOT charged.
+    # What the reference pays on top of the loop, per batch and per worker: computeRT copies totalExt,
+    # cumulativeExt, ssa and phaseFunctionIndex out of the domain (INT:434-443) -- timed as W concurrent memcpys of the
+    # same arrays (NumPy releases the GIL in copy) -- and the worker's fresh domain has its inverse phase-function
+    # tables re-tabulated (INT:280-285 -> INV:113-168) -- timed as W concurrent runs of the oracle's C restatement
+    # of that routine over every table entry (the Lobatto / Legendre evaluation feeding it is not charged).
     import concurrent.futures as cf
+    from mcbrat3d_b200.inversePhaseFunctions import inversion_inputs
     arrays = [dom.totalExt, dom.cumulativeExt, dom.ssa, dom.phaseFunctionIndex]
+    entries = [inversion_inputs(pf) for tab in dom.forwardTables for pf in tab.phaseFunctions]
 
     def copies(_):
         t = time.perf_counter()
@@ -112,14 +147,22 @@ def cpu_rate(dom, case, seconds, views=False):
             for a in arrays:
                 a.copy()
         return (time.perf_counter() - t) / 3.0
+
+    def tables(_):
+        t = time.perf_counter()
+        for mus, values in entries:
+            orc.inverse_phase_function(mus, values, 10001)
+        return time.perf_counter() - t
     with cf.ThreadPoolExecutor(workers) as ex:
         copy_s = max(ex.map(copies, range(workers)))
-    as_shipped = total / (dt + nb * copy_s)
+        table_s = max(ex.map(tables, range(workers)))
+    as_shipped = total / (dt + nb * (copy_s + table_s))
     return dict(value=total / dt, unit=UNIT, cores=workers, kind="port",
-                as_shipped=dict(value=as_shipped, per_batch_copy_ms=1e3 * copy_s,
+                as_shipped=dict(value=as_shipped, per_batch_copy_ms=1e3 * copy_s, per_batch_table_ms=1e3 * table_s,
                                 note="loop + the per-batch O(cells) array copies of INT:434-443 (%d MB per batch per "
-                                     "worker, all workers copying at once); table rebuild not charged"
-                                     % (sum(a.nbytes for a in arrays) >> 20)),
+                                     "worker, all workers copying at once) + the per-batch inverse-table rebuild of "
+                                     "INT:280-285 (%d table entries of 10001 steps)"
+                                     % (sum(a.nbytes for a in arrays) >> 20, len(entries))),
                 sample="%d photons = %d workers x %d batches x %d photons of the same workload, %.1f s wall; "
                        "photon loop only (the reference's per-batch table rebuild and O(cells) copies are not charged)"
                        % (total, workers, nb, batch, dt)), total, dt
@@ -145,10 +188,11 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dts / max(1, args.steps),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64/f32 mixed (reference arithmetic)",
-        "data": "synthetic", "config": {"workload": WORKLOAD + (" + 5 radiance views" if args.views else ""),
-                                        "note": "CPU restatement (oracle port) of the reference algorithm; the Fortran "
-                                                "reference cannot be built in this image (no Fortran compiler/MPI/netCDF)",
-                                        "wall_s": time.perf_counter() - t_all},
+        "data": "synthetic", "config": config_of(args),
+        "details": {"note": "CPU restatement (oracle port) of the reference algorithm; the Fortran reference cannot be built "
+                            "in this image or on the GPU box (no Fortran compiler/MPI/netCDF: profiles/r02_compiler_probe_gpu_box.log)"
+                            + ("; one wavelength bin of the broadband domain is sampled" if args.workload == "broadband" else ""),
+                    "wall_s": time.perf_counter() - t_all},
         "cpu_baseline": base,
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
@@ -247,8 +291,8 @@ def run_ours(args):
     from mcbrat3d_b200 import multipleProcesses as mpx
     from mcbrat3d_b200.monteCarloIllumination import new_PhotonStream
     from mcbrat3d_b200.monteCarloRadiativeTransfer import (MCB_ARITH_FAST, _stage_domain, _stage_source,
-                                                           computeRadiativeTransfer, getCounters, new_Integrator,
-                                                           reportResults, specifyParameters)
+                                                           computeRadiativeTransfer, gatherProbe, getCounters,
+                                                           new_Integrator, reportResults, specifyParameters)
     from mcbrat3d_b200.RandomNumbersForMC import new_RandomNumberSequence
 
     if not torch.cuda.is_available():
@@ -256,16 +300,22 @@ def run_ours(args):
     world, rank = mpx.initializeProcesses()
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
+    if args.workload == "broadband":
+        return run_broadband(args, world, rank, local)
     dom, case = make_case(args.views, args.workload)
     g = new_Integrator(dom, device=local)
     # a real (non-NULL) stream: the kernels, the torch events and the NCCL reduce all order on it
     stream = torch.cuda.Stream(device=local)
     torch.cuda.set_stream(stream)
     g._check(g._lib.mcb_set_stream(g.handle, C.c_void_p(stream.cuda_stream)), "mcb_set_stream")
+    # the cross-rank exchange runs through the C ABI (mcb_comm_init / mcb_reduce_tallies: ncclReduce on the handle's
+    # stream), the entry points a compiled host uses; torch.distributed only carries the NCCL id and the timings
+    own_comm = mpx.initializeIntegratorProcesses(g)
+    used_pool = (not args.views) and args.kernel != 1 and POOL_IS_DEFAULT or args.kernel == 2
     if args.views:
         specifyParameters(g, intensityMus=case["intensityMus"], intensityPhis=case["intensityPhis"],
                           computeIntensity=True, useRussianRouletteForIntensity=True, zetaMin=0.3)
-    specifyParameters(g, minInverseTableSize=10001, minForwardTableSize=10001, arithmetic=MCB_ARITH_FAST)
+    specifyParameters(g, minInverseTableSize=10001, minForwardTableSize=10001, arithmetic=MCB_ARITH_FAST, tuneKernel=args.kernel)
     rs = new_RandomNumberSequence([10, 0, 0])
     P = int(args.photons)
     ps = new_PhotonStream(case["solarMu"], case["solarAzimuth"], 1, rs)
@@ -289,14 +339,22 @@ def run_ours(args):
     def step(i):
         first = i * world * P + sum(shares[:rank])     # disjoint global photon ids per (step, rank)
         g._check(lib.mcb_run_batch(h, shares[rank], C.c_uint64(rs.seed), C.c_uint64(first), C.byref(done)), "mcb_run_batch")
-        if world > 1:
-            dist.reduce(tally, dst=0, op=dist.ReduceOp.SUM)          # the run's one exchange: NCCL over NVLink
+        if own_comm:
+            g._check(lib.mcb_reduce_tallies(h, 0), "mcb_reduce_tallies")     # the run's one exchange: ncclReduce over NVLink
+        elif world > 1:
+            dist.reduce(tally, dst=0, op=dist.ReduceOp.SUM)
 
     def sync():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
+    # measured ceiling of the operation that bounds the kernel: divergent sector gathers inside a buffer the size of the
+    # packed extinction field (csrc/mcb_probe.cu), launched like the flux kernels -- measured here, in this run
+    G = 8
+    field_bytes = 4 * (dom.numX + 2 * G) * (dom.numY + 2 * G) * (dom.numZ + 2 * G)
+    probe = {"l2_16MB": gatherProbe(g, 16 << 20, 8, 8), "field": gatherProbe(g, max(field_bytes, 1 << 20), 8, 8),
+             "hbm_1GB": gatherProbe(g, 1 << 30, 8, 8, 600)} if rank == 0 else None
     warm_ms = []
     for i in range(args.warmup):
         step(i); flush.zero_()
@@ -340,16 +398,30 @@ def run_ours(args):
     value = world * P * args.steps / (total_ms * 1e-3)
 
     # ---- e2e: host buffers in, results out, through the public API, every step ----
-    pinned = {}
-    for name in ("totalExt", "cumulativeExt", "ssa", "phaseFunctionIndex"):
-        a = getattr(dom, name)
-        tbuf = torch.empty(a.size, dtype=torch.from_numpy(a.ravel()[:1]).dtype).pin_memory()
-        tbuf.numpy()[:] = a.ravel()
-        pinned[name] = tbuf
-        setattr(dom, name, tbuf.numpy().reshape(a.shape))
-    h2d = sum(p.numel() * p.element_size() for p in pinned.values()) + sum(T.nbytes for T in dom.inversePhaseFunctions)
     cells = dom.numX * dom.numY * dom.numZ
     cols = dom.numX * dom.numY
+    staged_once = 0
+    if args.workload == "c5":
+        # The driver's own flow for this domain (DRV:903-947): the physical state of type(commonDomain) is staged ONCE
+        # per run (mcb_set_physical: mass concentration, effective radius, number concentration), and every step
+        # hands over only what read_SSPTable reads for its wavelength -- a few hundred bytes of tables -- from which
+        # mcb_assemble_optics builds the dense arrays in HBM.  (Round 1 pushed the 760 MB of dense f64 arrays
+        # through PCIe every step.)
+        from mcbrat3d_b200.opticalProperties import read_SSPTable
+        common, sspTables = case["physical"]
+        staged_once = int(common.massConc.nbytes + common.Reff.nbytes + 8 * dom.numZ)
+        h2d = int(sum(c.extinctionT[0].nbytes + c.singleScatteringAlbedoT[0].nbytes + np.asarray(c.key).nbytes
+                      for t in sspTables for c in t.components if c.extType == "volExt") + 3 * 8 * dom.numZ
+                  + sum(T.nbytes for T in dom.inversePhaseFunctions))
+    else:
+        pinned = {}
+        for name in ("totalExt", "cumulativeExt", "ssa", "phaseFunctionIndex"):
+            a = getattr(dom, name)
+            tbuf = torch.empty(a.size, dtype=torch.from_numpy(a.ravel()[:1]).dtype).pin_memory()
+            tbuf.numpy()[:] = a.ravel()
+            pinned[name] = tbuf
+            setattr(dom, name, tbuf.numpy().reshape(a.shape))
+        h2d = sum(p.numel() * p.element_size() for p in pinned.values()) + sum(T.nbytes for T in dom.inversePhaseFunctions)
     # the packed single-precision copies are produced in HBM (csrc/mcb_stage.cu), they do not cross PCIe;
     # reportResults brings back the normalised f32 arrays asked for below, not the f64 tally buffer
     d2h = 4 * (3 * cols + cells + (cols * len(case["intensityMus"]) if args.views else 0))
@@ -360,8 +432,14 @@ def run_ours(args):
         rs2 = new_RandomNumberSequence([10, 0, 0])
         rs2.nextPhotonId = ((args.warmup + args.steps + i) * world + rank) * P
         ps2 = new_PhotonStream(case["solarMu"], case["solarAzimuth"], P, rs2)
-        n = computeRadiativeTransfer(g, dom, rs2, ps2, P, synchronize=False)
-        if world > 1:
+        d2 = dom
+        if args.workload == "c5":                                     # this step's wavelength: tables in, optics built in HBM
+            d2 = read_SSPTable(sspTables, 1, common, calcRayl=True, thisIntegrator=g)
+            d2.inversePhaseFunctions = dom.inversePhaseFunctions      # tabulated on the host once (cached per domain)
+        n = computeRadiativeTransfer(g, d2, rs2, ps2, P, synchronize=False)
+        if own_comm:
+            g._check(lib.mcb_reduce_tallies(h, 0), "mcb_reduce_tallies")
+        elif world > 1:
             dist.reduce(tally, dst=0, op=dist.ReduceOp.SUM)
         return reportResults(g, meanFluxUp=True, meanFluxDown=True, meanFluxAbsorbed=True, fluxUp=True, fluxDown=True,
                              fluxAbsorbed=True, volumeAbsorption=True, meanIntensity=args.views,
@@ -386,56 +464,169 @@ def run_ours(args):
             peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
         abytes = algorithmic_bytes(counters, g.numComps)
         achieved = abytes / (kernel_ms * 1e-3) / 1e9
-        traffic = limiter = None
-        try:                                       # per-launch DRAM bytes and limiter metrics of the same command under ncu
-            tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))[args.workload]
-            if not args.views and int(tj.get("photons_per_launch", P)) == P:
-                traffic = tj.get("dram_bytes_per_launch")
-            limiter = tj.get("limiter")
+        kernel_name = ("mcbfast::batch_kernel (park/regroup megakernel + local estimation)" if args.views else
+                       "mcbpool::pool_kernel (photon pool)" if used_pool else "mcbfast::batch_kernel (park/regroup megakernel)")
+        traffic = None
+        try:        # DRAM bytes per launch of the same command under `ncu --set full`, keyed by workload, kernel and photons per launch
+            for e in json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("entries", []):
+                if (e["workload"], bool(e.get("views", False)), e["kernel"], int(e["photons_per_launch"])) == \
+                        (args.workload, bool(args.views), kernel_name.split(" ")[0], P):
+                    traffic = e["dram_bytes_per_launch"]
         except Exception:
             pass
+        gathers = counters["crossings"] + counters["leCrossings"] + counters["scatters"]
+        gps = gathers / (kernel_ms * 1e-3)
+        # which measured gather ceiling applies: the L2-resident one when the packed field fits L2 (C1-C3), else the
+        # ceiling measured on a buffer of the field's own size (C5: 93 MB, partly L2, partly HBM)
+        ceiling = probe["l2_16MB"] if field_bytes <= (48 << 20) else probe["field"]
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic", "ms_per_step_by_rank": by_rank,
-            "config": {"workload": WORKLOAD + (" + 5 radiance views (local estimation, RR zeta_min 0.3)" if args.views else ""),
-                       "photons_per_gpu_per_step": P, "photon_shares": shares,
-                       "shares": "equal in the warm-up steps, proportional to each rank's measured kernel rate in the timed steps",
-                       "rng": "Philox4x32-10 per photon id",
-                       "l2": ("optical-property arrays are L2-resident by construction (<= 126 MB); " if args.workload == "c3" else
-                              "inputs (93 MB extinction field + 253 MB event records) are larger than L2; ") +
-                             "a 256 MB buffer is rewritten between timed steps (L2 flush), outside the per-step event pairs",
-                       "kernel": "mcbfast::batch_kernel (persistent, 1 launch per step)",
-                       "events_per_photon": {"crossings": counters["crossings"] / max(1, counters["photons"]),
-                                             "scatters": counters["scatters"] / max(1, counters["photons"])},
-                       "crossings_per_s": counters["crossings"] / (kernel_ms * 1e-3),
-                       "scatters_per_s": counters["scatters"] / (kernel_ms * 1e-3),
-                       "bad_photons": counters["bad"], "wall_s_timed_region": t_wall,
-                       "e2e_steps": e2e_steps,
-                       "fluxes": {k: float(res[k]) for k in ("meanFluxUp", "meanFluxDown", "meanFluxAbsorbed")}},
+            "config": config_of(args),
+            "details": {"photons_per_gpu_per_step": P, "photon_shares": shares,
+                        "shares": "equal in the warm-up steps, proportional to each rank's measured kernel rate in the timed steps",
+                        "rng": "Philox4x32-10 per photon id",
+                        "kernel": kernel_name + ", persistent, 1 launch per step",
+                        "exchange": ("mcb_reduce_tallies (ncclReduce through the C ABI)" if own_comm else
+                                     "torch.distributed reduce" if world > 1 else "none (one GPU)"),
+                        "events_per_photon": {"crossings": counters["crossings"] / max(1, counters["photons"]),
+                                              "scatters": counters["scatters"] / max(1, counters["photons"]),
+                                              "view_ray_crossings": counters["leCrossings"] / max(1, counters["photons"])},
+                        "crossings_per_s": counters["crossings"] / (kernel_ms * 1e-3),
+                        "scatters_per_s": counters["scatters"] / (kernel_ms * 1e-3),
+                        "bad_photons": counters["bad"], "wall_s_timed_region": t_wall,
+                        "e2e_steps": e2e_steps, "e2e_staged_once_bytes": staged_once,
+                        "fluxes": {k: float(res[k]) for k in ("meanFluxUp", "meanFluxDown", "meanFluxAbsorbed")}},
             "clocks": clocks.summary(),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
             "gpu_launches": args.steps * world,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": peak_src, "kernel_ms": kernel_ms,
                          "algorithmic_bytes_per_launch": abytes,
-                         # the sector-granular figure -- every independent gather moves one 32-byte sector,
-                         # so HBM could serve peak/32 gathers per second; a ratio above 1 means the gathers are served by L2
-                         "sector_gather": {"gathers_per_s": (counters["crossings"] + counters["leCrossings"] + counters["scatters"]) / (kernel_ms * 1e-3),
-                                           "hbm_sector_roofline_per_s": peak * 1e9 / 32.0,
-                                           "frac": (counters["crossings"] + counters["leCrossings"] + counters["scatters"]) / (kernel_ms * 1e-3) / (peak * 1e9 / 32.0)},
-                         "limiter_ncu": limiter,
+                         # The limiter that applies here, against a peak MEASURED IN THIS RUN (csrc/mcb_probe.cu): every
+                         # cell crossing / scattering event is one fully divergent gather (one 32-byte sector per lane);
+                         # `peak` is the rate at which this GPU serves such gathers from a buffer of the field's residency
+                         # class, launched like the flux kernels.  achieved counts ALGORITHMIC gathers (counted crossings
+                         # + scatterings), not the extra ones a burst issues past an event.
+                         "l2_gather": {"achieved": gps, "peak": ceiling, "unit": "gathers/s", "frac": gps / ceiling,
+                                       "peak_source": "measured in this run: mcb_debug_gather_probe, 8 loads in flight, 8 CTAs/SM, "
+                                                      + ("16 MB buffer (L2-resident, like the %.1f MB field)" % (field_bytes / 2.0 ** 20)
+                                                         if field_bytes <= (48 << 20) else "%.0f MB buffer (the field's size)" % (field_bytes / 2.0 ** 20)),
+                                       "measured_ceilings_gathers_per_s": probe},
+                         "limiting": "l2_gather" if field_bytes <= (48 << 20) else "l2_gather (field-sized buffer: L2 + HBM)",
                          "note": ("memory-gather roofline; the extinction field is L2-resident on this domain, so HBM "
-                                  "traffic is far below the algorithmic bytes and the kernel is bounded by the SMs' "
-                                  "L1TEX->XBAR gather-request rate and issue slots (limiter_ncu, DESIGN.md section 5.4)")
+                                  "traffic is far below the algorithmic bytes: the binding ceiling is the L1TEX->L2 sector "
+                                  "rate (1 sector per clock per SM, measured), reported as l2_gather (DESIGN.md section 5.4)")
                          if args.workload == "c3" else
                          ("memory-gather roofline; the 93 MB field exceeds L2: clear-sky cells are resolved from the "
-                          "occupancy bitmap, only cloudy cells are gathered from HBM (DESIGN.md section 5.2)")},
+                          "occupancy bitmap, only cloudy cells are gathered from L2 / HBM (DESIGN.md section 5.2)")},
         }
         if not args.no_cpu_baseline and world == 1:
             base, _, _ = cpu_rate(dom, case, args.cpu_seconds, args.views)
             line["cpu_baseline"] = base
         print(json.dumps(line))
+    mpx.finalizeProcesses()
+
+
+def run_broadband(args, world, rank, local):
+    """--workload broadband: BASELINE configs[4] proper.  A step is one whole spectral run of world x P photons over 32
+    wavelength bins through the public API (runBroadband): per bin the optics are assembled in HBM from the resident
+    physical state, the tables are built, the photons allocated by the flux CDF are traced in batches, and the batch
+    statistics stay on the device; one reduce across ranks at the end.  Host buffers in (physical state once per run,
+    per-bin tables every bin), statistics out -- so `value` and `e2e` are the same measurement here."""
+    import torch
+    import torch.distributed as dist
+
+    from mcbrat3d_b200 import domains
+    from mcbrat3d_b200 import multipleProcesses as mpx
+    from mcbrat3d_b200.broadband import runBroadband
+    from mcbrat3d_b200.monteCarloRadiativeTransfer import gatherProbe, new_Integrator, specifyParameters
+    from mcbrat3d_b200.opticalProperties import read_SSPTable
+    from mcbrat3d_b200.RandomNumbersForMC import new_RandomNumberSequence
+    nLambda, P = 32, int(args.photons)
+    common, tables, case = domains.broadband_problem(nxy=325, nz=160, nLambda=nLambda)
+    d0 = read_SSPTable(tables, 1, common, setup=True)
+    g = new_Integrator(d0, device=local)
+    stream = torch.cuda.Stream(device=local)
+    torch.cuda.set_stream(stream)
+    g._check(g._lib.mcb_set_stream(g.handle, C.c_void_p(stream.cuda_stream)), "mcb_set_stream")
+    own_comm = mpx.initializeIntegratorProcesses(g)
+    specifyParameters(g, minInverseTableSize=9001, tuneKernel=args.kernel)
+    src = 2.0e3 * np.exp(-((np.linspace(0.45, 2.1, nLambda) - 0.5) / 0.6) ** 2)          # W m^-2 um^-1
+    flush = torch.empty(64 * 1024 * 1024, dtype=torch.float32, device="cuda")
+    G = 8
+    field_bytes = 4 * (d0.numX + 2 * G) * (d0.numY + 2 * G) * (d0.numZ + 2 * G)
+    probe = {"l2_16MB": gatherProbe(g, 16 << 20, 8, 8), "field": gatherProbe(g, field_bytes, 8, 8),
+             "hbm_1GB": gatherProbe(g, 1 << 30, 8, 8, 600)} if rank == 0 else None
+
+    def sync():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step(i, sink=None):
+        rs = new_RandomNumberSequence([10 + i, 0, 0])
+        return runBroadband(g, tables, common, rs, world * P, 5_000_000, solarMu=0.5, solarSourceFunction=src, LW=False,
+                            calcRayl=True, counterSink=sink)
+    for i in range(args.warmup):
+        step(i); flush.zero_()
+    sync()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    with ClockSampler(local) as clocks:
+        t_wall = time.perf_counter()
+        for i in range(args.steps):
+            ev[i][0].record(stream)
+            out = step(args.warmup + i)
+            ev[i][1].record(stream)
+            flush.zero_()
+        sync()
+        t_wall = time.perf_counter() - t_wall
+    total_ms = sum(a.elapsed_time(b) for a, b in ev)
+    t = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms = float(t.item())
+    counters = {}
+    step(args.warmup + args.steps, counters)                 # one more, untimed, pass to count events (one sync per bin)
+    if rank == 0:
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+            peak, peak_src = float(peaks["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+        photons = world * P * args.steps
+        value = photons / (total_ms * 1e-3)
+        scale = (P / max(1, counters.get("photons", 1)))      # this rank's counted batches -> its whole share
+        abytes = algorithmic_bytes(counters, 3) * scale
+        achieved = abytes / (total_ms / args.steps * 1e-3) / 1e9
+        gps = (counters["crossings"] + counters["scatters"]) * scale / (total_ms / args.steps * 1e-3)
+        m = out["mean"]
+        print(json.dumps({
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": config_of(args),
+            "details": {"photons_per_gpu_per_step": P, "wavelength_bins": nLambda, "bins_used": int((out["freqDistr"] > 0).sum()),
+                        "batches_per_step": int(out["batchesCompleted"]), "rng": "Philox4x32-10 per photon id",
+                        "exchange": "mcb_reduce_statistics (ncclReduce through the C ABI)" if own_comm else "none (one GPU)",
+                        "events_per_photon": {"crossings": counters["crossings"] / max(1, counters["photons"]),
+                                              "scatters": counters["scatters"] / max(1, counters["photons"])},
+                        "wall_s_timed_region": t_wall, "solarFlux_W_m2": float(out["solarFlux"]),
+                        "fluxes_W_m2": {k: float(m[k]) for k in ("meanFluxUp", "meanFluxDown", "meanFluxAbsorbed")}},
+            "clocks": clocks.summary(),
+            "e2e": {"value": world * P * args.steps / t_wall, "unit": UNIT,
+                    "h2d_bytes_per_step": int(nLambda * 4096), "d2h_bytes_per_step": int(out["mean"]["volumeAbsorption"].nbytes * 2
+                                                                                          + 8 * out["mean"]["fluxUp"].nbytes),
+                    "note": "the spectral run IS the public API call; per-bin tables (a few KB each) in, finalised statistics out; "
+                            "the physical state (%.0f MB) is staged once per run" % ((common.massConc.nbytes + common.Reff.nbytes) / 2.0 ** 20)},
+            "gpu_launches": int(out["batchesCompleted"]) * world * args.steps,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_step": abytes,
+                         "l2_gather": {"achieved": gps, "peak": probe["field"], "unit": "gathers/s", "frac": gps / probe["field"],
+                                       "peak_source": "measured in this run on a %.0f MB buffer" % (field_bytes / 2.0 ** 20),
+                                       "measured_ceilings_gathers_per_s": probe},
+                         "note": "whole-step rate (assembly, table builds, allocation and statistics included), not the photon kernel alone"},
+        }))
     mpx.finalizeProcesses()
 
 

@@ -82,8 +82,11 @@ def getFrequencyDistr(thisIntegrator, CDF, totalPhotons: int, seed: int) -> np.n
 def runBroadband(thisIntegrator, tables: List[SSPTable], commonD: commonDomain, randomNumbers, totalPhotons: int,
                  numPhotonsPerBatch: int, solarMu: float = 0.5, solarAzimuth: float = 0.0,
                  solarSourceFunction=None, LW: bool = False, surfaceTemp: float = 290.0, calcRayl: bool = True,
-                 minBatchesPerBin: int = 1) -> Dict:
+                 minBatchesPerBin: int = 1, counterSink: Dict = None) -> Dict:
     """One broadband run on this rank's GPU (all ranks call it; rank r traces its share of every bin).
+
+    ``counterSink`` (a dict) receives the event counters summed over the bins (one extra synchronisation per bin:
+    for measurements, not for production runs).
 
     Returns a dict with ``mean`` / ``err`` (the driver's finalised statistics, W m^-2 when the source function is in
     W m^-2 um^-1), ``freqDistr``, ``solarFlux``, ``totalNumPhotons``, ``batchesCompleted``."""
@@ -132,6 +135,10 @@ def runBroadband(thisIntegrator, tables: List[SSPTable], commonD: commonDomain, 
         if per > 0:
             computeRadiativeTransferBatches(g, d, sub, mk(per * nb), per, nb, synchronize=False)
         rest = mine - per * nb
+        if counterSink is not None and per > 0:
+            from .monteCarloRadiativeTransfer import getCounters
+            for k, v in getCounters(g).items():
+                counterSink[k] = counterSink.get(k, 0) + v
         if rest > 0:
             computeRadiativeTransferBatches(g, d, sub, mk(rest), rest, 1, synchronize=False)
     sumStatisticsAcrossProcesses(g)

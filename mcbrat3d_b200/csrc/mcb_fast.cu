@@ -634,11 +634,9 @@ bool mcb_fast_reads_bricks(const DevDomain &P) {
 
 // mcb_pool.cu
 bool mcb_pool_covers(const DevDomain &P);
+bool mcb_pool_preferred(const DevDomain &P);
 void mcb_launch_pool_batch(const DevDomain &P, long long nPhotons, uint64_t seed, uint64_t firstPhotonId,
                            int numSMs, unsigned long long *workCounter, cudaStream_t stream);
-#ifndef MCB_DEFAULT_KERNEL
-#define MCB_DEFAULT_KERNEL MCB_KERNEL_PARK      // what mcb_options.tuneKernel = 0 selects where both kernels apply
-#endif
 
 static void column_absorption(const DevDomain &P, int numSMs, cudaStream_t stream) {
   const long long cols = (long long)P.nx * P.ny;
@@ -650,7 +648,8 @@ void mcb_launch_fast_batch(const DevDomain &P, long long nPhotons, uint64_t seed
                            int numSMs, unsigned long long *workCounter, cudaStream_t stream) {
   if (nPhotons <= 0) return;
   // flux-only runs on uniform grids: the photon-pool kernel (mcb_pool.cu) or the park/regroup kernel below
-  if (mcb_pool_covers(P) && (P.opt.tuneKernel ? P.opt.tuneKernel : MCB_DEFAULT_KERNEL) == MCB_KERNEL_POOL) {
+  // (mcb_options.tuneKernel = 0: the pool kernel where it measured faster -- grids too large for shared-memory tallies)
+  if (mcb_pool_covers(P) && (P.opt.tuneKernel ? P.opt.tuneKernel == MCB_KERNEL_POOL : mcb_pool_preferred(P))) {
     mcb_launch_pool_batch(P, nPhotons, seed, firstPhotonId, numSMs, workCounter, stream);
     column_absorption(P, numSMs, stream);
     return;

@@ -397,9 +397,6 @@ static void launch_pool(const DevDomain &P, long long nPhotons, uint64_t seed, u
   kernel<<<blocks, THREADS, smem, stream>>>(P, nPhotons, seed, firstPhotonId, workCounter, plan);
 }
 
-#ifndef MCB_POOL_DEFAULT_BURST
-#define MCB_POOL_DEFAULT_BURST 8
-#endif
 #ifndef MCB_POOL_DEFAULT_OCC
 #define MCB_POOL_DEFAULT_OCC 6
 #endif
@@ -409,18 +406,30 @@ bool mcb_pool_covers(const DevDomain &P) {
   return P.uniform && P.nx >= MCB_GHOST && P.ny >= MCB_GHOST && P.nDir == 0 && P.nx <= 65535 && P.ny <= 65535 && P.nz <= 65535;
 }
 
+// ... and is the default where it measured faster (one B200, r02: C3 6.56e8 -> 7.27e8 photons/s, C3 Mie 6.28e8 -> 7.00e8,
+// C5 3.76e8 -> 4.07e8): grids whose tallies go straight to the f64 buffer.  On grids small enough for shared-memory
+// tallies the park/regroup kernel stays ahead (C1 9.9e8 vs 9.3e8, C4 5.0e9 vs 4.2e9): its photons are short-lived and
+// the pool's 17 KB of shared memory per CTA come on top of the privatised tallies.
+bool mcb_pool_preferred(const DevDomain &P) {
+  const long long cols = (long long)P.nx * P.ny;
+  return mcb_pool_covers(P) && cols > 1024;
+}
+
 void mcb_launch_pool_batch(const DevDomain &P, long long nPhotons, uint64_t seed, uint64_t firstPhotonId,
                            int numSMs, unsigned long long *workCounter, cudaStream_t stream) {
   if (nPhotons <= 0) return;
   const bool mask = P.lin.mask != nullptr, brick = P.opt.tuneLayout != MCB_LAYOUT_LINEAR;
   // tuneBurst: 8 = eight cells per burst, all gathers up front; 4 = four; 44 = eight cells, gathers in two halves (SPLIT)
-  const int burst = P.opt.tuneBurst ? P.opt.tuneBurst : MCB_POOL_DEFAULT_BURST;
+  // default: split gathers on L2-resident fields (C3: 7.09e8 -> 7.27e8); with the occupancy bitmap (C5) the second
+  // round trip costs more than the saved gathers (4.07e8 vs 3.92e8)
+  const int burst = P.opt.tuneBurst ? P.opt.tuneBurst : (mask ? 8 : 44);
   const int occ = P.opt.tuneBlocksPerSM ? P.opt.tuneBlocksPerSM : MCB_POOL_DEFAULT_OCC;   // register budget: 8 CTAs/SM = 64 registers, 6 = 80
 #define MCB_POOL_GO(OCC, B, SPLIT, MASK, BRICK) launch_pool<OCC, B, SPLIT, MASK, BRICK>(P, nPhotons, seed, firstPhotonId, numSMs, workCounter, stream)
 #define MCB_POOL_LAYOUT(OCC, B, SPLIT) \
   do { if (mask) { if (brick) MCB_POOL_GO(OCC, B, SPLIT, true, true); else MCB_POOL_GO(OCC, B, SPLIT, true, false); } \
        else { if (brick) MCB_POOL_GO(OCC, B, SPLIT, false, true); else MCB_POOL_GO(OCC, B, SPLIT, false, false); } } while (0)
-  if (occ >= 8) { if (burst == 4) MCB_POOL_LAYOUT(8, 4, false); else if (burst == 44) MCB_POOL_LAYOUT(8, 8, true); else MCB_POOL_LAYOUT(8, 8, false); }
+  if (occ >= 8) { if (burst == 44) MCB_POOL_LAYOUT(8, 8, true); else MCB_POOL_LAYOUT(8, 8, false); }
+  else if (occ == 7) { if (burst == 44) MCB_POOL_LAYOUT(7, 8, true); else MCB_POOL_LAYOUT(7, 8, false); }
   else { if (burst == 4) MCB_POOL_LAYOUT(6, 4, false); else if (burst == 44) MCB_POOL_LAYOUT(6, 8, true); else MCB_POOL_LAYOUT(6, 8, false); }
 #undef MCB_POOL_LAYOUT
 #undef MCB_POOL_GO

@@ -200,6 +200,30 @@ def bench_domain(nxy=325, nz=150, seed=5, ssa=0.999) -> Tuple[Domain, Dict]:
     return d, dict(name="C5_bench", solarMu=0.5, solarAzimuth=0.0, LW_flag=-1.0, numPhotonsPerBatch=10000)
 
 
+def bench_problem(nxy=325, nz=150, seed=5, ssa=0.999):
+    """The C5 scene of ``bench_domain`` described the way the driver holds it (DRV:903-947): the wavelength-independent
+    physical state of ``type(commonDomain)`` -- here the cloud's mass concentration and effective radius, the molecular
+    number concentration and density profiles -- plus a one-wavelength SSP table (0.55 um).  ``read_SSPTable`` turns it
+    into the dense optical arrays, on the host (NumPy mirror) or in HBM (``mcb_set_physical`` once per run, then
+    ``mcb_assemble_optics`` with a few hundred bytes per wavelength).  Returns (commonDomain, [SSPTable], case)."""
+    from .opticalProperties import SSPComponent, SSPTable, commonDomain, light_spd
+    d, case = bench_domain(nxy=nxy, nz=nz, seed=seed, ssa=ssa)
+    cloud = d.components[0]
+    zc = 0.5 * (d.zPosition[1:] + d.zPosition[:-1])
+    mass = cloud.extinction[..., None].copy()                       # unit mass extinction coefficient: ext = massConc * 1
+    reff = np.where(cloud.extinction > 0, 10.0, 0.0)[..., None].copy()
+    numConc = np.broadcast_to((2.55e25 * np.exp(-zc / 8.0))[:, None, None], (nz, nxy, nxy)).copy()
+    rho = np.broadcast_to((1.225 * np.exp(-zc / 8.0))[:, None, None], (nz, nxy, nxy)).copy()
+    common = commonDomain(d.xPosition, d.yPosition, d.zPosition, d.temps, mass, reff, numConc, rho)
+    key = np.array([5.0, 15.0], dtype=f32)
+    table = SSPTable(np.array([light_spd * 1e6 / 0.55]), np.array([d.surfaceAlbedo]),
+                     [SSPComponent("cloud", "volExt", 1, key, np.ones((1, 2)), np.full((1, 2), ssa),
+                                   tables=[new_PhaseFunctionTable([henyeyGreenstein(0.85, 128), henyeyGreenstein(0.85, 128)],
+                                                                  key=key.astype(np.float64))])])
+    case = dict(case, name="C5_bench_physical", calcRayl=True)
+    return common, [table], case
+
+
 def broadband_problem(nxy=24, nz=20, nLambda=6, seed=11, lw=False):
     """C5-style multi-wavelength input (``run/I3RC_bench_SW.deck`` / ``_LW.deck``): the wavelength-independent physical
     state of ``type(commonDomain)`` (liquid-water mass concentration and effective radius of one cloud component,

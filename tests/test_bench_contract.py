@@ -29,6 +29,13 @@ def test_reference_arm_prints_the_contract_line():
     assert line["e2e"] == {"value": line["value"], "unit": line["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert line["cpu_baseline"]["as_shipped"]["value"] <= line["cpu_baseline"]["value"]
     assert "workload" in line["config"] and "model" not in line["config"]
+    # both arms emit the SAME config object (the driver compares them)
+    sys.path.insert(0, ROOT)
+    import bench
+
+    class A:
+        views = False; workload = "c3"
+    assert line["config"] == bench.config_of(A)
 
 
 @pytest.mark.gpu
@@ -38,9 +45,12 @@ def test_gpu_arm_prints_the_contract_line():
     assert line["n_gpus"] == 1 and line["gpu_launches"] == 1 and line["value"] > 1e8
     r = line["roofline"]
     assert r["bound"] == "hbm" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9 and r["unit"] == "GB/s"
-    assert r["sector_gather"]["gathers_per_s"] > 1e10 and r["sector_gather"]["frac"] > 0
+    g = r["l2_gather"]                                    # the binding ceiling, measured in the same run
+    assert g["peak"] > 1e11 and 0.2 < g["frac"] < 1.5 and abs(g["frac"] - g["achieved"] / g["peak"]) < 1e-9
+    assert g["measured_ceilings_gathers_per_s"]["hbm_1GB"] < g["measured_ceilings_gathers_per_s"]["l2_16MB"]
     assert line["e2e"]["h2d_bytes_per_step"] > 0 and line["e2e"]["d2h_bytes_per_step"] > 0
     assert line["e2e"]["value"] != line["value"]
-    assert line["config"]["bad_photons"] == 0
-    f = line["config"]["fluxes"]
+    assert set(line["config"]) == {"workload", "l2"}
+    assert line["details"]["bad_photons"] == 0
+    f = line["details"]["fluxes"]
     assert abs(f["meanFluxUp"] + f["meanFluxDown"] + f["meanFluxAbsorbed"] - 1.0) < 2e-3      # albedo 0: energy closure

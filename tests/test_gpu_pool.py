@@ -33,7 +33,7 @@ CASES = [
 ]
 # tuneBurst: 8 / 4 cells per burst with all gathers up front, 44 = eight cells with the gathers in two halves
 VARIANTS = [dict(tuneBlocksPerSM=6, tuneBurst=8), dict(tuneBlocksPerSM=8, tuneBurst=8), dict(tuneBlocksPerSM=6, tuneBurst=4),
-            dict(tuneBlocksPerSM=8, tuneBurst=44), dict(tuneBlocksPerSM=6, tuneBurst=44)]
+            dict(tuneBlocksPerSM=8, tuneBurst=44), dict(tuneBlocksPerSM=6, tuneBurst=44), dict(tuneBlocksPerSM=7, tuneBurst=44)]
 
 
 def run(dom, case, n, **knobs):
