@@ -168,6 +168,38 @@ def cpu_rate(dom, case, seconds, views=False):
                        % (total, workers, nb, batch, dt)), total, dt
 
 
+REF_DRIVER = os.path.join(ROOT, "oracle", "_ref", "ref_trace_driver")
+
+
+def ref_driver_rate(dom, case, seconds, views):
+    """photons/s of the UNMODIFIED reference (oracle/_ref/ref_trace_driver, built by oracle/ref_build when a Fortran
+    compiler exists): W = cores - 1 processes, each the reference's own batch loop on its own MT19937 stream."""
+    import concurrent.futures as cf
+    import tempfile
+    sys.path.insert(0, os.path.join(ROOT, "oracle", "ref_build"))
+    from make_ref_cases import write_case
+    workers = max(1, (os.cpu_count() or 1) - 1)
+    tmp = tempfile.mkdtemp(prefix="mcb_ref_")
+
+    def one(rank, batches):
+        cf_, of_ = os.path.join(tmp, "r%d.case" % rank), os.path.join(tmp, "r%d.out" % rank)
+        write_case(cf_, dom, case, views, batches, 10000, rank=rank, mode=1)
+        subprocess.check_call([REF_DRIVER, cf_, of_], stdout=subprocess.DEVNULL)
+        n, t = open(of_).read().split()
+        return int(n), float(t)
+    n0, t0 = one(1, 1)                                    # calibrate: one batch
+    nb = max(1, int(round(seconds / max(t0, 1e-3))))
+    t = time.perf_counter()
+    with cf.ThreadPoolExecutor(workers) as ex:
+        res = list(ex.map(lambda r: one(r, nb), range(1, workers + 1)))
+    dt = time.perf_counter() - t
+    total = sum(r[0] for r in res)
+    return dict(value=total / dt, unit=UNIT, cores=workers, kind="reference",
+                sample="%d photons = %d processes x %d batches x 10000 photons of the same workload through the unmodified "
+                       "Fortran (oracle/_ref/ref_trace_driver), %.1f s wall, table builds and per-batch copies included"
+                       % (total, workers, nb, dt)), total, dt
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -178,7 +210,7 @@ def run_reference(args):
     base = None
     t_all = time.perf_counter()
     for i in range(args.warmup + args.steps):
-        base, total, dt = cpu_rate(dom, case, per_step, args.views)
+        base, total, dt = (ref_driver_rate if os.path.exists(REF_DRIVER) else cpu_rate)(dom, case, per_step, args.views)
         if i >= args.warmup:
             rates.append((total, dt))
     tot = sum(r[0] for r in rates); dts = sum(r[1] for r in rates)

@@ -118,6 +118,13 @@ def load():
     lib.orc_trace_photons.restype = C.c_int64
     lib.orc_trace_photons.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_float, C.c_double, _dp,
                                       C.c_int64, _fp, C.c_int64]
+    lib.orc_photons_directional.restype = C.c_void_p
+    lib.orc_photons_directional.argtypes = [C.c_float, C.c_float, C.c_int64, C.POINTER(orc_rng)]
+    lib.orc_photons_free.argtypes = [C.c_void_p]
+    lib.orc_compute_radiative_transfer.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(orc_rng), C.c_void_p, C.c_int64, C.c_int,
+                                                   C.POINTER(C.c_int64)]
+    lib.orc_report_results.restype = None
+    lib.orc_report_results.argtypes = [C.c_void_p] + [_fp] * 10
     lib.orc_run_batches.restype = C.c_int64
     lib.orc_run_batches.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_float, C.c_double, _dp,
                                     C.c_int, C.c_int, C.c_int, C.c_int64, C.c_int64, C.POINTER(orc_stats)]
@@ -243,6 +250,38 @@ class OracleIntegrator:
         nEv = int(self.head().traceN)
         self.lib.orc_integrator_set_trace(self.ptr, None, 0)
         return ev[: min(nEv, cap)]
+
+    def photon_fingerprints(self, numBatches, photonsPerBatch, solarMu, solarAzimuth, iseed=10, rank=1):
+        """What oracle/ref_build/ref_trace_driver.f90 records for the Fortran reference: the reference's batch loop
+        (new_PhotonStream + computeRadiativeTransfer + reportResults, DRV:956-1011) on ONE MT19937 stream seeded
+        (iseed, rank, 0), and after every batch every non-zero entry of fluxUp / fluxDown / fluxAbsorbed /
+        volumeAbsorption / intensity as (batch, photons processed, array id 1..5, 1-based Fortran index, value)."""
+        nx, ny, nz = self.dom.nx, self.dom.ny, self.dom.nz
+        cols = nx * ny
+        r = orc_rng()
+        key = (C.c_uint32 * 3)(int(iseed), int(rank), 0)
+        self.lib.orc_rng_init_array(C.byref(r), key, 3)
+        arrs = [np.zeros(cols, np.float32), np.zeros(cols, np.float32), np.zeros(cols, np.float32),
+                np.zeros(cols * nz, np.float32), np.zeros(cols * max(self.nDir, 1), np.float32)]
+        out = [[], [], [], [], []]
+        for b in range(1, int(numBatches) + 1):
+            ph = self.lib.orc_photons_directional(float(solarMu), float(solarAzimuth), int(photonsPerBatch), C.byref(r))
+            done = C.c_int64(0)
+            self.lib.orc_compute_radiative_transfer(self.ptr, self.dom.ptr, C.byref(r), ph, int(photonsPerBatch), 1, C.byref(done))
+            self.lib.orc_photons_free(ph)
+            self.lib.orc_report_results(self.ptr, None, None, None, _p(arrs[0], C.c_float), _p(arrs[1], C.c_float),
+                                        _p(arrs[2], C.c_float), None, _p(arrs[3], C.c_float), None,
+                                        _p(arrs[4], C.c_float) if self.nDir else None)
+            n0 = len(out[0])
+            for a, arr in enumerate(arrs if self.nDir else arrs[:4]):
+                nzi = np.nonzero(arr)[0]
+                out[0] += [b] * nzi.size; out[1] += [int(done.value)] * nzi.size
+                out[2].append(np.full(nzi.size, a + 1, np.int32)); out[3].append((nzi + 1).astype(np.int32)); out[4].append(arr[nzi].copy())
+            if len(out[0]) == n0:                       # a photon that left no trace still shows up as a batch
+                out[0].append(b); out[1].append(int(done.value))
+                out[2].append(np.zeros(1, np.int32)); out[3].append(np.zeros(1, np.int32)); out[4].append(np.zeros(1, np.float32))
+        return (np.array(out[0], np.int32), np.array(out[1], np.int32), np.concatenate(out[2]), np.concatenate(out[3]),
+                np.concatenate(out[4]))
 
     def run_batches(self, numBatches, numPhotonsPerBatch, source=0, solarMu=1.0, solarAzimuth=0.0,
                     fracAtmsPower=0.0, voxelCDF=None, iseed=10, rank=1, thread=0, volume=False):
