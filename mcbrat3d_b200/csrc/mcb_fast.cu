@@ -626,17 +626,33 @@ static void launch(const DevDomain &P, long long nPhotons, uint64_t seed, uint64
   kernel<<<blocks, THREADS, smem, stream>>>(P, nPhotons, seed, firstPhotonId, workCounter, park, carry, plan);
 }
 
-// which layout of the extinction field the dispatcher below reads (the API packs that one)
-bool mcb_fast_reads_bricks(const DevDomain &P) {
-  const bool wide = P.nx >= MCB_GHOST && P.ny >= MCB_GHOST;
-  return P.uniform && wide && P.nDir == 0 && P.opt.tuneLayout != MCB_LAYOUT_LINEAR;
-}
-
-// mcb_pool.cu
+// mcb_pool.cu, mcb_pool_le.cu
 bool mcb_pool_covers(const DevDomain &P);
 bool mcb_pool_preferred(const DevDomain &P);
 void mcb_launch_pool_batch(const DevDomain &P, long long nPhotons, uint64_t seed, uint64_t firstPhotonId,
                            int numSMs, unsigned long long *workCounter, cudaStream_t stream);
+bool mcb_pool_le_covers(const DevDomain &P);
+bool mcb_pool_le_reads_bricks(const DevDomain &P);
+void mcb_launch_pool_le_batch(const DevDomain &P, long long nPhotons, uint64_t seed, uint64_t firstPhotonId,
+                              int numSMs, unsigned long long *workCounter, cudaStream_t stream);
+#ifndef MCB_POOL_LE_DEFAULT
+#define MCB_POOL_LE_DEFAULT 0                  // runs with view directions: 1 = the pool organisation is the default
+#endif
+
+// which of the two organisations traces this run: mcb_options.tuneKernel, or where none is asked for the one that
+// measured faster (flux-only: mcb_pool_preferred)
+static bool runs_on_pool(const DevDomain &P) {
+  if (P.nDir > 0) return mcb_pool_le_covers(P) && (P.opt.tuneKernel ? P.opt.tuneKernel == MCB_KERNEL_POOL : MCB_POOL_LE_DEFAULT != 0);
+  return mcb_pool_covers(P) && (P.opt.tuneKernel ? P.opt.tuneKernel == MCB_KERNEL_POOL : mcb_pool_preferred(P));
+}
+
+// which layout of the extinction field the dispatcher below reads (the API packs that one)
+bool mcb_fast_reads_bricks(const DevDomain &P) {
+  const bool wide = P.nx >= MCB_GHOST && P.ny >= MCB_GHOST;
+  if (P.nDir > 0) return runs_on_pool(P) && mcb_pool_le_reads_bricks(P);
+  return P.uniform && wide && P.opt.tuneLayout != MCB_LAYOUT_LINEAR;
+}
+
 
 static void column_absorption(const DevDomain &P, int numSMs, cudaStream_t stream) {
   const long long cols = (long long)P.nx * P.ny;
@@ -647,10 +663,10 @@ static void column_absorption(const DevDomain &P, int numSMs, cudaStream_t strea
 void mcb_launch_fast_batch(const DevDomain &P, long long nPhotons, uint64_t seed, uint64_t firstPhotonId,
                            int numSMs, unsigned long long *workCounter, cudaStream_t stream) {
   if (nPhotons <= 0) return;
-  // flux-only runs on uniform grids: the photon-pool kernel (mcb_pool.cu) or the park/regroup kernel below
-  // (mcb_options.tuneKernel = 0: the pool kernel where it measured faster -- grids too large for shared-memory tallies)
-  if (mcb_pool_covers(P) && (P.opt.tuneKernel ? P.opt.tuneKernel == MCB_KERNEL_POOL : mcb_pool_preferred(P))) {
-    mcb_launch_pool_batch(P, nPhotons, seed, firstPhotonId, numSMs, workCounter, stream);
+  // uniform grids: the photon-pool kernels (mcb_pool.cu, mcb_pool_le.cu) or the park/regroup kernel below
+  if (runs_on_pool(P)) {
+    if (P.nDir > 0) mcb_launch_pool_le_batch(P, nPhotons, seed, firstPhotonId, numSMs, workCounter, stream);
+    else mcb_launch_pool_batch(P, nPhotons, seed, firstPhotonId, numSMs, workCounter, stream);
     column_absorption(P, numSMs, stream);
     return;
   }

@@ -38,6 +38,9 @@ cases["T_irr_LW_views"] = ((domains.irregular_test_domain()[0], dict(lw=True, su
                                                                     intensityPhis=[0.0, 45.0, 200.0])), True, 60000)
 for name in ("C3_small_mie", "C5_small", "C5_small_odd", "C5_small_odd_bitmap"):      # the photon-pool kernel as well
     cases[name + "_pool"] = cases[name]
+cases["C3_small_views_pool"] = (domains.landsat_cloud(ssa=0.99, nxy=24, mie=True), True, 30000)        # ... and its view rays
+cases["C5_small_bitmap_views_pool"] = cases["C5_small_bitmap_views"]
+cases["C4_LW_views_pool"] = cases["C4_LW_views"]
 out = {}
 from mcbrat3d_b200.emissionAndBroadBandWeights import Weights, emission_weighting
 for name, ((dom, case), views, n) in cases.items():

@@ -127,3 +127,60 @@ def test_pool_three_sigma_against_oracle(orc):
     z = assert_within("pool absorbedProfile", gm["absorbedProfile"], ge["absorbedProfile"], ores["absorbedProfile"][0],
                       ores["absorbedProfile"][1], 4.0)
     assert np.sqrt(np.mean(z ** 2)) < 1.6
+
+
+# ---- local estimation on the pool organisation (csrc/mcb_pool_le.cu) against the task-queue kernel (mcb_fast.cu) ----
+LE_CASES = [
+    ("C3_small_rr", lambda: domains.landsat_cloud(ssa=0.99, nxy=32), 60000, dict(useRussianRouletteForIntensity=True, zetaMin=0.3), None),
+    ("C3_small_plain", lambda: domains.landsat_cloud(ssa=0.99, nxy=32), 40000, dict(useRussianRouletteForIntensity=False), None),
+    ("C3_small_mie_rr", lambda: domains.landsat_cloud(ssa=0.99, nxy=24, mie=True), 40000,
+     dict(useRussianRouletteForIntensity=True, zetaMin=0.3), None),
+    ("C5_small_bitmap_rr", lambda: domains.bench_domain(nxy=24, nz=32), 40000,
+     dict(useRussianRouletteForIntensity=True, zetaMin=0.3, tuneExtMask=1), None),
+    ("C3_small_hybrid_limit", lambda: domains.landsat_cloud(ssa=0.99, nxy=24, mie=True), 30000,
+     dict(useRussianRouletteForIntensity=True, zetaMin=0.3, useHybridPhaseFunsForIntenCalcs=True, hybridPhaseFunWidth=7.0,
+          numOrdersOrigPhaseFunIntenCalcs=2, limitIntensityContributions=True, maxIntensityContribution=0.05), None),
+    ("C3_small_three_views", lambda: domains.landsat_cloud(ssa=0.99, nxy=32), 40000,
+     dict(useRussianRouletteForIntensity=True, zetaMin=0.3), ([1.0, 0.5, -0.5], [0.0, 0.0, 180.0])),     # odd count, one looking down
+    ("C4_LW_views", lambda: domains.homogeneous_lw(), 60000, dict(useRussianRouletteForIntensity=True, zetaMin=0.3),
+     ([1.0, 0.5, -0.5], [0.0, 0.0, 90.0])),                                                               # births post requests too
+    ("reflecting_plain", lambda: domains.homogeneous_slab(ssa=0.9, tau=2.0, albedo=0.5, n=9, delta=0.125), 40000,
+     dict(useRussianRouletteForIntensity=False), ([1.0, 0.866], [0.0, 0.0])),                             # surface requests
+]
+
+
+def run_le(dom, case, n, views, **params):
+    g = new_Integrator(dom)
+    try:
+        lw = case.get("LW_flag", -1.0) > 0
+        mus, phis = views if views else (case["intensityMus"], case["intensityPhis"])
+        specifyParameters(g, intensityMus=mus, intensityPhis=phis, computeIntensity=True, minInverseTableSize=10001,
+                          minForwardTableSize=10001, LW_flag=1.0 if lw else -1.0, **params)
+        rs = new_RandomNumberSequence([10, 1, 0])
+        if lw:
+            w = Weights()
+            emission_weighting(dom, w, case.get("surfaceTemp", 300.0), thisIntegrator=g)
+            ps = new_PhotonStream(theseWeights=w, numberOfPhotons=n, randomNumbers=rs)
+        else:
+            ps = new_PhotonStream(case["solarMu"], case["solarAzimuth"], n, rs)
+        assert computeRadiativeTransfer(g, dom, rs, ps, n) == n
+        res = reportResults(g, fluxUp=True, fluxDown=True, volumeAbsorption=True, intensity=True, intensityByComponent=True,
+                            meanIntensity=True)
+        return res, getCounters(g)
+    finally:
+        finalize_Integrator(g)
+
+
+@pytest.mark.parametrize("name,make,n,params,views", LE_CASES, ids=[c[0] for c in LE_CASES])
+def test_pool_le_traces_the_same_rays_as_the_queue_kernel(name, make, n, params, views):
+    dom, case = make()
+    want, cw = run_le(dom, case, n, views, tuneKernel=MCB_KERNEL_PARK, **params)
+    assert cw["bad"] == 0 and cw["leRays"] > n and (np.asarray(want["meanIntensity"]) > 0).all()
+    private = dom.numX * dom.numY <= 1024
+    for variant in (dict(tuneBlocksPerSM=5), dict(tuneBlocksPerSM=4), dict(tuneBlocksPerSM=5, tuneLayout=2)):
+        got, cg = run_le(dom, case, n, views, tuneKernel=MCB_KERNEL_POOL, **params, **variant)
+        diff = {k: (cg[k], cw[k]) for k in cg if cg[k] != cw[k]}
+        assert not diff, (variant, diff)
+        for k in want:
+            np.testing.assert_allclose(np.asarray(got[k], np.float64), np.asarray(want[k], np.float64),
+                                       rtol=3e-4 if private else 3e-5, atol=3e-5 if private else 1e-7, err_msg="%s %s" % (k, variant))
