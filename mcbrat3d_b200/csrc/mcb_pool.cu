@@ -397,17 +397,13 @@ static void launch_pool(const DevDomain &P, long long nPhotons, uint64_t seed, u
   kernel<<<blocks, THREADS, smem, stream>>>(P, nPhotons, seed, firstPhotonId, workCounter, plan);
 }
 
-#ifndef MCB_POOL_DEFAULT_OCC
-#define MCB_POOL_DEFAULT_OCC 6
-#endif
-
 // the pool kernel covers flux-only runs on uniform grids at least a ghost shell wide
 bool mcb_pool_covers(const DevDomain &P) {
   return P.uniform && P.nx >= MCB_GHOST && P.ny >= MCB_GHOST && P.nDir == 0 && P.nx <= 65535 && P.ny <= 65535 && P.nz <= 65535;
 }
 
-// ... and is the default where it measured faster (one B200, r02: C3 6.56e8 -> 7.27e8 photons/s, C3 Mie 6.28e8 -> 7.00e8,
-// C5 3.76e8 -> 4.07e8): grids whose tallies go straight to the f64 buffer.  On grids small enough for shared-memory
+// ... and is the default where it measured faster (one B200, r02: C3 6.56e8 -> 7.48e8 photons/s, C3 Mie 6.28e8 -> 7.0e8,
+// C5 3.76e8 -> 4.41e8): grids whose tallies go straight to the f64 buffer.  On grids small enough for shared-memory
 // tallies the park/regroup kernel stays ahead (C1 9.9e8 vs 9.3e8, C4 5.0e9 vs 4.2e9): its photons are short-lived and
 // the pool's 17 KB of shared memory per CTA come on top of the privatised tallies.
 bool mcb_pool_preferred(const DevDomain &P) {
@@ -423,7 +419,9 @@ void mcb_launch_pool_batch(const DevDomain &P, long long nPhotons, uint64_t seed
   // default: split gathers on L2-resident fields (C3: 7.09e8 -> 7.27e8); with the occupancy bitmap (C5) the second
   // round trip costs more than the saved gathers (4.07e8 vs 3.92e8)
   const int burst = P.opt.tuneBurst ? P.opt.tuneBurst : (mask ? 8 : 44);
-  const int occ = P.opt.tuneBlocksPerSM ? P.opt.tuneBlocksPerSM : MCB_POOL_DEFAULT_OCC;   // register budget: 8 CTAs/SM = 64 registers, 6 = 80
+  // register budget: 8 CTAs/SM = 64 registers (spills), 7 = 72, 6 = 80.  Measured (one B200, r02, photons/s): C3 with split
+  // gathers 6: 7.27e8, 7: 7.48e8, 8: 6.0e8; C5 (bitmap, eight gathers up front) 6: 4.41e8, 7: 4.03e8
+  const int occ = P.opt.tuneBlocksPerSM ? P.opt.tuneBlocksPerSM : (mask ? 6 : 7);
 #define MCB_POOL_GO(OCC, B, SPLIT, MASK, BRICK) launch_pool<OCC, B, SPLIT, MASK, BRICK>(P, nPhotons, seed, firstPhotonId, numSMs, workCounter, stream)
 #define MCB_POOL_LAYOUT(OCC, B, SPLIT) \
   do { if (mask) { if (brick) MCB_POOL_GO(OCC, B, SPLIT, true, true); else MCB_POOL_GO(OCC, B, SPLIT, true, false); } \

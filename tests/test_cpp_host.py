@@ -78,11 +78,11 @@ def test_compiled_host_writes_the_ascii_tables(tmp_path):
     subprocess.run([EXE, "stepcloud", "8", "20000", "10", "1", "--out", prefix], capture_output=True, text=True, check=True)
     flux = open(prefix + "_flux.out").read().split("\n")
     assert flux[0] == "!   I3RC Monte Carlo 3D Solar Radiative Transfer: Flux"
-    assert flux[2] == "!  Num_Photons=    160000"
+    assert flux[2] == "!  Num_Photons=    160000" and flux[11].startswith("!  Average:   ")
     rows = [l for l in flux if l and not l.startswith("!")]
     assert len(rows) == 32 and all(len(l) == 14 + 3 * 21 for l in rows)
     up = np.array([float(l[14:25]) for l in rows])
-    avg = float(flux[12][14:25])
+    avg = float(flux[11][14:25])
     assert abs(up.mean() - avg) < 2e-4                      # the average line is the mean of the pixel column
     rad = open(prefix + "_rad.out").read().split("\n")
     assert sum(1 for l in rad if l.endswith("<- (mu,phi)")) == 5

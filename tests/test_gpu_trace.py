@@ -46,7 +46,7 @@ def test_trace_parity(orc, name, lazy, source, views, rr):
             ps = new_PhotonStream(theseWeights=w, numberOfPhotons=n, randomNumbers=rs)
             want = og.trace(rn, 1, fracAtmsPower=w.fracAtmsPower, voxelCDF=w.voxelWeights, maxEvents=n * 1024)
         got, raw = tracePhotons(g, dom, ps, rn, maxEventsPerPhoton=1024)
-        assert len(want) > 5 * n
+        assert len(want) > (5 if source == 0 else 2) * n      # thermal photons in an absorbing slab live a few events
         assert_events_equal(got, want, "%s views=%s rr=%s" % (name, views, rr))
         # the tallies of the traced photons agree too (f64 sums on the GPU, f32 in the oracle)
         ot = og.raw_tallies()
