@@ -343,7 +343,7 @@ def run_ours(args):
     # the cross-rank exchange runs through the C ABI (mcb_comm_init / mcb_reduce_tallies: ncclReduce on the handle's
     # stream), the entry points a compiled host uses; torch.distributed only carries the NCCL id and the timings
     own_comm = mpx.initializeIntegratorProcesses(g)
-    used_pool = (not args.views) and args.kernel != 1 and POOL_IS_DEFAULT or args.kernel == 2
+    used_pool = args.kernel != 1 and POOL_IS_DEFAULT or args.kernel == 2
     if args.views:
         specifyParameters(g, intensityMus=case["intensityMus"], intensityPhis=case["intensityPhis"],
                           computeIntensity=True, useRussianRouletteForIntensity=True, zetaMin=0.3)
@@ -496,7 +496,8 @@ def run_ours(args):
             peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
         abytes = algorithmic_bytes(counters, g.numComps)
         achieved = abytes / (kernel_ms * 1e-3) / 1e9
-        kernel_name = ("mcbfast::batch_kernel (park/regroup megakernel + local estimation)" if args.views else
+        kernel_name = (("mcbpoolle::pool_le_kernel (photon pool + view-ray jobs)" if used_pool else
+                        "mcbfast::batch_kernel (park/regroup megakernel + local estimation)") if args.views else
                        "mcbpool::pool_kernel (photon pool)" if used_pool else "mcbfast::batch_kernel (park/regroup megakernel)")
         traffic = None
         try:        # DRAM bytes per launch of the same command under `ncu --set full`, keyed by workload, kernel and photons per launch
@@ -525,6 +526,10 @@ def run_ours(args):
                         "events_per_photon": {"crossings": counters["crossings"] / max(1, counters["photons"]),
                                               "scatters": counters["scatters"] / max(1, counters["photons"]),
                                               "view_ray_crossings": counters["leCrossings"] / max(1, counters["photons"])},
+                        # cells crossed in vacuum / clear-sky leaps (csrc/mcb_march.cuh march_leap): part of the algorithmic
+                        # crossings above (the reference visits them one by one), never gathered
+                        "leaps_per_photon": counters["leaps"] / max(1, counters["photons"]),
+                        "leap_share_of_crossings": counters["leapCells"] / max(1, counters["crossings"] + counters["leCrossings"]),
                         "crossings_per_s": counters["crossings"] / (kernel_ms * 1e-3),
                         "scatters_per_s": counters["scatters"] / (kernel_ms * 1e-3),
                         "bad_photons": counters["bad"], "wall_s_timed_region": t_wall,
@@ -540,8 +545,10 @@ def run_ours(args):
                          # cell crossing / scattering event is one fully divergent gather (one 32-byte sector per lane);
                          # `peak` is the rate at which this GPU serves such gathers from a buffer of the field's residency
                          # class, launched like the flux kernels.  achieved counts ALGORITHMIC gathers (counted crossings
-                         # + scatterings), not the extra ones a burst issues past an event.
+                         # + scatterings, including the cells a leap crosses without a gather), not the extra ones a burst
+                         # issues past an event.  gathers_issued_per_s = the same without the leapt cells.
                          "l2_gather": {"achieved": gps, "peak": ceiling, "unit": "gathers/s", "frac": gps / ceiling,
+                                       "gathers_issued_per_s": (gathers - counters["leapCells"]) / (kernel_ms * 1e-3),
                                        "peak_source": "measured in this run: mcb_debug_gather_probe, 8 loads in flight, 8 CTAs/SM, "
                                                       + ("16 MB buffer (L2-resident, like the %.1f MB field)" % (field_bytes / 2.0 ** 20)
                                                          if field_bytes <= (48 << 20) else "%.0f MB buffer (the field's size)" % (field_bytes / 2.0 ** 20)),

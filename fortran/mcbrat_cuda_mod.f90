@@ -26,7 +26,8 @@ module mcbrat_cuda
     integer(c_int32_t) :: arithmetic
     ! measurement knobs (0 = the library's own choice), see include/mcbrat_cuda.h
     integer(c_int32_t) :: tuneKernel, tuneLayout, tuneBlocksPerSM, tuneParkThreshold, tuneLeCarry, tuneExtMask, tuneBurst
-    integer(c_int32_t) :: reserved(3)
+    integer(c_int32_t) :: tuneLeap, tuneLeapLanes
+    integer(c_int32_t) :: reserved(1)
   end type mcb_options
   integer(c_int32_t), parameter, public :: MCB_KERNEL_PARK = 1, MCB_KERNEL_POOL = 2
   integer(c_int32_t), parameter, public :: MCB_LAYOUT_LINEAR = 1, MCB_LAYOUT_BRICKS = 2
@@ -34,7 +35,8 @@ module mcbrat_cuda
   ! event counters of the last batch (mcb_get_counters)
   type, bind(C), public :: mcb_counters
     integer(c_int64_t) :: photons, crossings, scatters, surfaceHits, topExits, bad, leRays, leCrossings, rouletteKills
-    integer(c_int64_t) :: reserved(7)
+    integer(c_int64_t) :: surfaceKills, leaps, leapCells
+    integer(c_int64_t) :: reserved(4)
   end type mcb_counters
 
   ! trace record of the fixed-random-number harness (mcb_run_trace)
@@ -65,7 +67,7 @@ module mcbrat_cuda
             mcb_stats_reset, mcb_run_batches, mcb_stats_buffer, mcb_get_statistics,                       &
             mcb_version, mcb_set_stream, mcb_build_forward_table, mcb_get_inverse_table, mcb_get_forward_table,  &
             mcb_get_thermal_source, mcb_last_batch_ms, mcb_get_counters, mcb_get_raw_tallies, mcb_run_trace, &
-            mcb_debug_philox, mcb_debug_gather_probe,                                                    &
+            mcb_debug_philox, mcb_debug_gather_probe, mcb_debug_distance_map,                            &
             mcb_comm_unique_id, mcb_comm_init, mcb_comm_info, mcb_reduce_tallies, mcb_reduce_statistics, mcb_comm_destroy
 
   interface
@@ -315,6 +317,12 @@ module mcbrat_cuda
       integer(c_int64_t), value :: bytes
       integer(c_int), value :: loadsInFlight, blocksPerSM, iterations
       real(c_double), intent(out) :: gathersPerSecond
+    end function
+    integer(c_int) function mcb_debug_distance_map(handle, out, nBytes) bind(C, name="mcb_debug_distance_map")
+      import :: c_int, c_ptr, c_int64_t, c_int8_t
+      type(c_ptr), value :: handle
+      integer(c_int8_t), intent(out) :: out(*)
+      integer(c_int64_t), value :: nBytes
     end function
     ! ---- multipleProcesses (MPIW:29-251) over NCCL: one process per GPU, one reduce at the end (DRV:1151-1166) ----
     integer(c_int) function mcb_comm_unique_id(id128) bind(C, name="mcb_comm_unique_id")

@@ -57,7 +57,9 @@ typedef struct {
   int32_t tuneLeCarry;                      /* view rays parked between queue rounds: < 0 off, > 0 threshold  */
   int32_t tuneExtMask;                      /* occupancy bitmap of the extinction field: < 0 off, > 0 on      */
   int32_t tuneBurst;                        /* cells per marching burst of the pool kernel (4 or 8)           */
-  int32_t reserved[3];
+  int32_t tuneLeap;                         /* vacuum leaps of the pool kernels: < 0 off, > 0 smallest distance */
+  int32_t tuneLeapLanes;                    /* lanes of a warp that must want a leap for the warp to take one   */
+  int32_t reserved[1];
 } mcb_options;
 enum { MCB_KERNEL_PARK = 1, MCB_KERNEL_POOL = 2 };
 enum { MCB_LAYOUT_LINEAR = 1, MCB_LAYOUT_BRICKS = 2 };
@@ -65,7 +67,9 @@ enum { MCB_LAYOUT_LINEAR = 1, MCB_LAYOUT_BRICKS = 2 };
 /* Event counters of the last batch (algorithmic-bytes accounting). */
 typedef struct {
   int64_t photons, crossings, scatters, surfaceHits, topExits, bad,
-          leRays, leCrossings, rouletteKills, reserved[7];
+          leRays, leCrossings, rouletteKills, surfaceKills,
+          leaps, leapCells,        /* vacuum / clear-sky leaps taken by the pool kernels; cells they crossed (also in crossings) */
+          reserved[4];
 } mcb_counters;
 
 /* Trace record (fixed-random-number single-photon harness, north-star criterion (a)). */
@@ -248,6 +252,11 @@ int mcb_debug_philox(mcb_handle *h, uint64_t seed, uint64_t photon, int n, uint3
  * second -- the denominator of bench.py's roofline.l2_gather.                                                    */
 int mcb_debug_gather_probe(mcb_handle *h, int64_t bytes, int loadsInFlight, int blocksPerSM, int iterations,
                            double *gathersPerSecond);
+/* The vacuum-distance map the packed extinction field of the staged domain is encoded with (nx*ny*nz bytes, x
+ * fastest): per cell the Chebyshev distance, in cells, to the nearest cell with extinction, 0 for such a cell --
+ * periodic in x and y, nothing above the top or below the surface, limited by 64.  The photon-pool kernels cross
+ * that many cells of vacuum in one step (fewer when the boundary the ray is heading for is closer).  Fails if the staged grid is not marched that way.               */
+int mcb_debug_distance_map(mcb_handle *h, uint8_t *out, int64_t nBytes);
 
 #ifdef __cplusplus
 }

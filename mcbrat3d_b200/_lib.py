@@ -33,7 +33,7 @@ class mcb_options(C.Structure):
                 # measurement knobs (0 = the library's own choice): see include/mcbrat_cuda.h
                 ("tuneKernel", C.c_int32), ("tuneLayout", C.c_int32), ("tuneBlocksPerSM", C.c_int32),
                 ("tuneParkThreshold", C.c_int32), ("tuneLeCarry", C.c_int32), ("tuneExtMask", C.c_int32),
-                ("tuneBurst", C.c_int32), ("reserved", C.c_int32 * 3)]
+                ("tuneBurst", C.c_int32), ("tuneLeap", C.c_int32), ("tuneLeapLanes", C.c_int32), ("reserved", C.c_int32 * 1)]
 
 
 MCB_KERNEL_PARK, MCB_KERNEL_POOL = 1, 2
@@ -50,8 +50,9 @@ MCB_COMP_VOLEXT, MCB_COMP_ABSXSEC, MCB_COMP_PROFILE = 0, 1, 2
 
 
 class mcb_counters(C.Structure):
-    _fields_ = [(n, C.c_int64) for n in ("photons", "crossings", "scatters", "surfaceHits", "topExits", "bad",
-                                         "leRays", "leCrossings", "rouletteKills")] + [("reserved", C.c_int64 * 7)]
+    _fields_ = ([(n, C.c_int64) for n in ("photons", "crossings", "scatters", "surfaceHits", "topExits", "bad",
+                                          "leRays", "leCrossings", "rouletteKills", "surfaceKills", "leaps", "leapCells")]
+                + [("reserved", C.c_int64 * 4)])
 
     def as_dict(self):
         return {n: int(getattr(self, n)) for n, _ in self._fields_ if n != "reserved"}
@@ -71,7 +72,7 @@ EXPORTS = ["mcb_create", "mcb_destroy", "mcb_last_error", "mcb_version", "mcb_se
            "mcb_build_thermal_source", "mcb_get_thermal_source", "mcb_frequency_distribution", "mcb_run_batch", "mcb_accumulate_batch", "mcb_stats_reset", "mcb_run_batches",
            "mcb_stats_buffer", "mcb_get_statistics", "mcb_last_batch_ms",
            "mcb_get_counters", "mcb_get_results", "mcb_tally_buffer", "mcb_get_raw_tallies", "mcb_run_trace",
-           "mcb_debug_philox", "mcb_debug_gather_probe", "mcb_comm_unique_id", "mcb_comm_init", "mcb_comm_info",
+           "mcb_debug_philox", "mcb_debug_gather_probe", "mcb_debug_distance_map", "mcb_comm_unique_id", "mcb_comm_init", "mcb_comm_info",
            "mcb_reduce_tallies", "mcb_reduce_statistics", "mcb_comm_destroy"]
 
 _lib: Optional[C.CDLL] = None
@@ -131,6 +132,7 @@ def load() -> C.CDLL:
     lib.mcb_run_trace.argtypes = [_vp, C.c_int64, _fp, C.c_int64, C.c_int32, _vp, C.c_int64, C.POINTER(C.c_int64)]
     lib.mcb_debug_philox.argtypes = [_vp, C.c_uint64, C.c_uint64, C.c_int, C.POINTER(C.c_uint32)]
     lib.mcb_debug_gather_probe.argtypes = [_vp, C.c_int64, C.c_int, C.c_int, C.c_int, _dp]
+    lib.mcb_debug_distance_map.argtypes = [_vp, C.POINTER(C.c_uint8), C.c_int64]
     lib.mcb_comm_unique_id.argtypes = [_vp]
     lib.mcb_comm_init.argtypes = [_vp, C.c_int, C.c_int, _vp]
     lib.mcb_comm_info.argtypes = [_vp, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]

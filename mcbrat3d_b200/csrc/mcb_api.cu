@@ -23,7 +23,8 @@ void mcb_launch_fast_batch(const DevDomain &P, long long nPhotons, uint64_t seed
 void mcb_launch_philox_kat(uint64_t seed, uint64_t photon, int n, uint32_t *out, cudaStream_t stream);
 double mcb_run_gather_probe(size_t bytes, int inFlight, int blocksPerSM, int iterations, int numSMs, cudaStream_t stream);
 // mcb_stage.cu: device-side packing / validation, normalisation, emission CDF
-void mcb_launch_pack_field(const DevDomain &P, int brick, float *ext, uint32_t *mask, float *layerExt, int *flags,
+void mcb_launch_distance_map(const DevDomain &P, int cap, uint8_t *dist, uint8_t *scratch, int numSMs, cudaStream_t stream);
+void mcb_launch_pack_field(const DevDomain &P, int brick, float *ext, uint32_t *mask, float *layerExt, int *flags, const uint8_t *dist,
                            int numSMs, cudaStream_t stream);
 void mcb_launch_pack_records(const DevDomain &P, uint32_t *rec, int *flags, int numSMs, cudaStream_t stream);
 bool mcb_fast_reads_bricks(const DevDomain &P);
@@ -63,6 +64,7 @@ struct mcb_handle {
   bool haveTemps = false;                        // dTemps holds the temperatures of the current grid
   bool packedLin = false, packedBrk = false;     // which layouts of the extinction field hold the current optics
   int maskKnob = 0;                              // mcb_options.tuneExtMask the packed field was set up with
+  bool haveDist = false;                         // dDist holds the vacuum-distance map of the current optics
   bool haveInv[MCB_MAX_COMP] = {false}, haveFwd[MCB_MAX_COMP] = {false};
   std::vector<double> xE, yE, zE;
   std::map<void **, size_t> slotBytes;    // capacity of every re-stageable slot (reused while large enough)
@@ -71,6 +73,7 @@ struct mcb_handle {
   void *dTotalExt = nullptr, *dCumExt = nullptr, *dSsa = nullptr, *dPhaseIdx = nullptr;
   void *dExt32 = nullptr, *dExtBrick = nullptr, *dRec = nullptr;
   void *dExtMask = nullptr, *dExtMaskBrick = nullptr, *dLayerExt = nullptr;     // occupancy bitmap of fields too large for L2
+  void *dDist = nullptr, *dDistScratch = nullptr;   // vacuum-distance map (u8 per cell) the packed fields are encoded with
   void *dInv[MCB_MAX_COMP] = {nullptr}, *dFwd[MCB_MAX_COMP] = {nullptr}, *dFwdOrig[MCB_MAX_COMP] = {nullptr};
   int invE[MCB_MAX_COMP] = {0}, fwdE[MCB_MAX_COMP] = {0};
   void *dColCDF = nullptr, *dVoxelCDF = nullptr, *dTemps = nullptr, *dScratch = nullptr, *dResults = nullptr;
@@ -208,7 +211,7 @@ int mcb_destroy(mcb_handle *h) {
                    h->dExt32, h->dRec, h->dVoxelCDF, h->dTally, h->dCounters,
                    h->dTemps, h->dScratch, h->dResults, (void *)h->dFlags, h->dStats, h->dStatsOut,
                    h->dMassConc, h->dReff, h->dNumConc, h->dAsmTables, h->dExtMask, h->dLayerExt,
-                   h->dExtBrick, h->dExtMaskBrick, h->dColCDF};
+                   h->dExtBrick, h->dExtMaskBrick, h->dColCDF, h->dDist, h->dDistScratch};
   for (void *p : slots) if (p) cudaFree(p);
   for (int c = 0; c < MCB_MAX_COMP; ++c) {
     if (h->dInv[c]) cudaFree(h->dInv[c]);
@@ -295,7 +298,7 @@ int mcb_set_grid(mcb_handle *h, int nx, int ny, int nz,
   P.uniform = (uniformAxis(xEdges, nx) && uniformAxis(yEdges, ny) && uniformAxis(zEdges, nz)) ? 1 : 0;
   P.fhx = (float)((P.xMax - P.x0) / nx); P.fhy = (float)((P.yMax - P.y0) / ny); P.fhz = (float)((P.zMax - P.z0) / nz);
   P.finvLx = 1.0f / P.fLx; P.finvLy = 1.0f / P.fLy; P.fzMax = (float)P.zMax;
-  P.finvhx = 1.0f / P.fhx; P.finvhy = 1.0f / P.fhy;
+  P.finvhx = 1.0f / P.fhx; P.finvhy = 1.0f / P.fhy; P.finvhz = 1.0f / P.fhz;
   // padded extinction field: MCB_GHOST cells on every side (see mcb_set_optics)
   {                                                  // x-fastest layout
     DevDomain::ExtField &F = P.lin;
@@ -337,8 +340,22 @@ static int finish_thermal_source(mcb_handle *h, double fracAtmsPower) {
 static int pack_field(mcb_handle *h, bool brick) {
   DevDomain &P = h->P;
   if (brick ? h->packedBrk : h->packedLin) return 0;
+  // Vacuum-distance encoding (mcb_stage.cu): on grids the photon-pool kernels march (uniform, at least a ghost shell
+  // wide, field read without the occupancy bitmap) a cell without extinction holds -D, D = its Chebyshev distance to
+  // the nearest cell with extinction; every marcher clamps at 0, the pool kernels leap (march_leap, mcb_march.cuh).
+  const bool encode = P.uniform && P.nx >= MCB_GHOST && P.ny >= MCB_GHOST && !P.lin.mask;
+  if (encode && !h->haveDist) {
+    const size_t cells = (size_t)P.nx * P.ny * P.nz;
+    if (reserve(h, &h->dDist, cells) || reserve(h, &h->dDistScratch, cells)) return 1;
+    int cap = MCB_LEAP_CAP;
+    cap = cap < P.nx ? cap : P.nx; cap = cap < P.ny ? cap : P.ny;
+    mcb_launch_distance_map(P, cap, (uint8_t *)h->dDist, (uint8_t *)h->dDistScratch, h->numSMs, h->stream);
+    CK(h, cudaGetLastError());
+    h->haveDist = true;
+  }
   mcb_launch_pack_field(P, brick ? 1 : 0, (float *)(brick ? h->dExtBrick : h->dExt32),
-                        (uint32_t *)(brick ? P.brk.mask : P.lin.mask), (float *)P.layerExt, h->dFlags, h->numSMs, h->stream);
+                        (uint32_t *)(brick ? P.brk.mask : P.lin.mask), (float *)P.layerExt, h->dFlags,
+                        encode ? (const uint8_t *)h->dDist : nullptr, h->numSMs, h->stream);
   CK(h, cudaGetLastError());
   (brick ? h->packedBrk : h->packedLin) = true;
   return 0;
@@ -357,16 +374,17 @@ static int setup_packed_field(mcb_handle *h) {
   P.brk.ext = (const float *)h->dExtBrick + P.brk.origin;
   const int knob = P.opt.tuneExtMask;
   const bool useMask = knob != 0 ? knob > 0 : sizeof(float) * padded > ((size_t)48 << 20);
-  P.lin.mask = P.brk.mask = nullptr; P.layerExt = nullptr;
+  P.lin.mask = P.brk.mask = nullptr; P.layerExt = P.layerLeap = P.layerCum = nullptr;
   if (useMask) {
     if (reserve(h, &h->dExtMask, sizeof(uint32_t) * ((padded + 31) / 32))) return 1;
     if (reserve(h, &h->dExtMaskBrick, sizeof(uint32_t) * ((padded + 31) / 32))) return 1;
-    if (reserve(h, &h->dLayerExt, sizeof(float) * (size_t)(P.nz + 2 * MCB_GHOST + 2))) return 1;
+    const size_t nLayer = (size_t)(P.nz + 2 * MCB_GHOST + 2);             // layerExt | layerLeap | layerCum
+    if (reserve(h, &h->dLayerExt, sizeof(float) * 3 * nLayer)) return 1;
     P.lin.mask = (const uint32_t *)h->dExtMask; P.brk.mask = (const uint32_t *)h->dExtMaskBrick;
-    P.layerExt = (const float *)h->dLayerExt;
+    P.layerExt = (const float *)h->dLayerExt; P.layerLeap = P.layerExt + nLayer; P.layerCum = P.layerLeap + nLayer;
   }
   h->maskKnob = knob;
-  h->packedLin = h->packedBrk = false;
+  h->packedLin = h->packedBrk = false; h->haveDist = false;
   return pack_field(h, mcb_fast_reads_bricks(P));
 }
 
@@ -945,7 +963,7 @@ int mcb_get_counters(mcb_handle *h, mcb_counters *c) {
   if (!h || !c) return 1;
   CK(h, cudaSetDevice(h->device));
   CK(h, cudaStreamSynchronize(h->stream));
-  unsigned long long v[CNT_N];
+  unsigned long long v[CNT_END];
   CK(h, cudaMemcpy(v, h->dCounters, sizeof(v), cudaMemcpyDeviceToHost));
   memset(c, 0, sizeof(*c));
   c->photons = (int64_t)v[CNT_PHOTONS]; c->crossings = (int64_t)v[CNT_CROSSINGS];
@@ -953,11 +971,12 @@ int mcb_get_counters(mcb_handle *h, mcb_counters *c) {
   c->topExits = (int64_t)v[CNT_TOP]; c->bad = (int64_t)v[CNT_BAD];
   c->leRays = (int64_t)v[CNT_LE_RAYS]; c->leCrossings = (int64_t)v[CNT_LE_CROSSINGS];
   c->rouletteKills = (int64_t)v[CNT_RR_KILLS];
-  c->reserved[0] = (int64_t)v[CNT_SURFACE_KILLS];                      // photons absorbed by the surface (weight <= tiny)
+  c->surfaceKills = (int64_t)v[CNT_SURFACE_KILLS];                     // photons absorbed by the surface (weight <= tiny)
+  c->leaps = (int64_t)v[CNT_LEAPS]; c->leapCells = (int64_t)v[CNT_LEAP_CELLS];
   // the fast kernel does not count top exits while marching: every photon ends at the top, at the
   // surface (weight <= tiny), by roulette, or is dropped as bad
   if (h->P.opt.arithmetic == MCB_ARITH_FAST)
-    c->topExits = c->photons - c->rouletteKills - c->reserved[0] - c->bad;
+    c->topExits = c->photons - c->rouletteKills - c->surfaceKills - c->bad;
   return 0;
 }
 
@@ -1169,6 +1188,18 @@ int mcb_debug_gather_probe(mcb_handle *h, int64_t bytes, int loadsInFlight, int 
   if (r < 0.0) FAIL(h, "mcb_debug_gather_probe: failed (%g)", r);
   *gathersPerSecond = r;
   return 0;
+}
+
+// the vacuum-distance map of the staged domain (pack_field), for the tests of the leaping marcher
+int mcb_debug_distance_map(mcb_handle *h, uint8_t *out, int64_t nBytes) {
+  if (!h || !out) return 1;
+  if (!h->haveGrid || !h->haveOptics) FAIL(h, "mcb_debug_distance_map: problem not completely specified.");
+  if (!h->haveDist) FAIL(h, "mcb_debug_distance_map: this grid is not marched with vacuum leaps");
+  const int64_t cells = (int64_t)h->P.nx * h->P.ny * h->P.nz;
+  if (nBytes < cells) FAIL(h, "mcb_debug_distance_map: buffer too small (%lld needed)", (long long)cells);
+  CK(h, cudaSetDevice(h->device));
+  CK(h, cudaMemcpyAsync(out, h->dDist, (size_t)cells, cudaMemcpyDeviceToHost, h->stream));
+  return settle(h);
 }
 
 }  // extern "C"

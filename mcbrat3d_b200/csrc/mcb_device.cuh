@@ -13,6 +13,9 @@
 #define MCB_MAX_COMP 8          // optical components per domain (the reference's decks use <= 4)
 #define MCB_MAX_DIR 32          // view directions kept in the parameter block
 #define MCB_GHOST 8             // ghost cells on every side of the packed extinction field = longest marching burst
+#define MCB_LEAP_MIN 3          // smallest vacuum distance the pool kernels leap from (mcb_options.tuneLeap overrides)
+#define MCB_LEAP_LANES 8        // lanes of a warp that must want a leap for the warp to run the leap code (tuneLeapLanes)
+#define MCB_LEAP_CAP 64         // largest vacuum distance (cells) encoded in the packed field = longest leap of the pool kernels
 
 struct DevDomain {
   // ---- grid (OPT:77-83, INT:60-66) ----
@@ -54,14 +57,18 @@ struct DevDomain {
     int divSliceS, divRowS;
     long long padded;                         // number of padded cells
   } lin, brk;
-  const float *layerExt;                      // nz + 2G (+1) clear-sky values
+  const float *layerExt;                      // nz + 2G (+2) clear-sky values; sign bit set: the WHOLE layer has this value
+                                              // (no bitmap look-up needed there)
+  const float *layerLeap;                     // nz + 2G (+2): minus the distance, in layers, to the nearest layer that is not
+                                              // clear throughout (0 for such a layer): march_leap crosses that many at once
+  const float *layerCum;                      // nz + 1: clear-sky optical depth per unit |1/mu| from the surface to each edge
   // one record per cell with everything a scattering event reads, so an event costs ONE gather (a 32 B sector for
   // nc <= 3) instead of a dependent chain through three arrays: 2^recShift u32 words =
   // [f32 cumExt(c), c = 1..nc-1][f32 ssa(c), c = 1..nc][u16 phase index pairs], zero-padded
   const uint32_t *rec;
   int recShift;
   float fx0, fy0, fz0, fLx, fLy, fLz;         // single-precision grid scalars (fast kernel, constant bank)
-  float fhx, fhy, fhz, finvLx, finvLy, finvhx, finvhy, fzMax;
+  float fhx, fhy, fhz, finvLx, finvLy, finvhx, finvhy, finvhz, fzMax;
   // ---- tables ----
   const float *inv[MCB_MAX_COMP];  int invS[MCB_MAX_COMP];  int invE[MCB_MAX_COMP], fwdE[MCB_MAX_COMP];   // steps, entries
   const float *fwd[MCB_MAX_COMP];  const float *fwdOrig[MCB_MAX_COMP];  int fwdS[MCB_MAX_COMP];
@@ -101,7 +108,8 @@ __host__ __device__ inline long long mcb_brick_address(int i, int j, int k, int 
 }
 
 enum { CNT_PHOTONS = 0, CNT_CROSSINGS, CNT_SCATTERS, CNT_SURFACE, CNT_TOP, CNT_BAD,
-       CNT_LE_RAYS, CNT_LE_CROSSINGS, CNT_RR_KILLS, CNT_SURFACE_KILLS, CNT_N };
+       CNT_LE_RAYS, CNT_LE_CROSSINGS, CNT_RR_KILLS, CNT_SURFACE_KILLS, CNT_N,     // [CNT_N] is the photon work counter
+       CNT_LEAPS, CNT_LEAP_CELLS, CNT_END };
 
 #ifdef MCB_BOUNDS_CHECK
 __device__ __forceinline__ long long mcb_checked_index(const DevDomain &P, long long i, long long n) {

@@ -636,8 +636,8 @@ bool mcb_pool_le_reads_bricks(const DevDomain &P);
 void mcb_launch_pool_le_batch(const DevDomain &P, long long nPhotons, uint64_t seed, uint64_t firstPhotonId,
                               int numSMs, unsigned long long *workCounter, cudaStream_t stream);
 #ifndef MCB_POOL_LE_DEFAULT
-#define MCB_POOL_LE_DEFAULT 0                  // runs with view directions: 1 = the pool organisation is the default
-#endif
+#define MCB_POOL_LE_DEFAULT 1                  // runs with view directions: 1 = the pool organisation is the default
+#endif                                         // (one B200, r02, C3 + 5 views: 1.05e8 photons/s against the task queue's 8.5e7)
 
 // which of the two organisations traces this run: mcb_options.tuneKernel, or where none is asked for the one that
 // measured faster (flux-only: mcb_pool_preferred)

@@ -192,9 +192,14 @@ enum { MARCH_ON = ST_MARCH, MARCH_HIT = ST_SCATTER, MARCH_BOTTOM = ST_SURFACE, M
 // where all 32 lanes have an event to decode (mcb_pool.cu's event phase), instead of here with a third of the lanes.
 // SPLIT: the gathers of the second half of the burst are issued only by lanes whose target was not met in the first
 // half (one more dependent round trip per burst, fewer requests on the L1TEX -> L2 path that bounds the kernel).
+//
+// Vacuum-distance encoding (mcb_stage.cu, fields read without MASK): a cell without extinction holds -D, D = its
+// Chebyshev distance in cells to the nearest cell that has some, so every gathered value is clamped at 0 before it is
+// used.  vlast (photon-pool kernels): where the burst ends with MARCH_ON it receives a lower bound of -D for the cell
+// the ray is in now (the last gathered value + 1: D changes by at most 1 between neighbours) -- march_leap's input.
 template <bool REG, bool WIDE, int B, bool MASK, bool BRICK, bool RAW = false, bool SPLIT = false>
 __device__ __forceinline__ int march_burst(Ray &r, const DevDomain &P, const Grid &G,
-                                           float &ext, float target, unsigned &crossings) {
+                                           float &ext, float target, unsigned &crossings, float *vlast = nullptr) {
   const DevDomain::ExtField &F = BRICK ? P.brk : P.lin;
   float tE[B], sg[B];
   int ck[B];
@@ -213,8 +218,12 @@ __device__ __forceinline__ int march_burst(Ray &r, const DevDomain &P, const Gri
     ck[k] = BRICK ? a : r.ix + F.nxp * (r.iy + F.nyp * r.iz);
     tE[k] = tmin;
     if (MASK) {
-      mw[k] = __ldg(F.mask + MCB_CHECK_INDEX(P, (uint32_t)(ck[k] + F.origin) >> 5, (F.padded + 31) >> 5));
-      sg[k] = __ldg(P.layerExt + MCB_CHECK_INDEX(P, r.iz + GH, P.nz + 2 * GH));
+      // the layer's clear-sky extinction; its sign bit says that the whole layer has that value, so the bitmap word is
+      // fetched only in layers that hold cloud somewhere (C5: 64 of 150 layers)
+      const float lv = __ldg(P.layerExt + MCB_CHECK_INDEX(P, r.iz + GH, P.nz + 2 * GH));
+      sg[k] = fabsf(lv);
+      mw[k] = 0u;
+      if (!signbit(lv)) mw[k] = __ldg(F.mask + MCB_CHECK_INDEX(P, (uint32_t)(ck[k] + F.origin) >> 5, (F.padded + 31) >> 5));
     }
     if (REG) {
       // one compare and predicated updates per axis, spelled out so that the index step is not widened into a
@@ -270,9 +279,10 @@ __device__ __forceinline__ int march_burst(Ray &r, const DevDomain &P, const Gri
         }
       }
     }
-    const float en = fmaf(tE[k] - tS, sg[k], acc);
+    const float sk = MASK ? sg[k] : fmaxf(sg[k], 0.0f);       // vacuum cells hold -D
+    const float en = fmaf(tE[k] - tS, sk, acc);
     const bool h = !found && en > target;
-    hS = h ? sg[k] : hS; hC = h ? ck[k] : hC; hK = h ? k : hK;
+    hS = h ? sk : hS; hC = h ? ck[k] : hC; hK = h ? k : hK;
     found = found || h;
     acc = found ? acc : en; tS = found ? tS : tE[k];
   }
@@ -306,6 +316,7 @@ __device__ __forceinline__ int march_burst(Ray &r, const DevDomain &P, const Gri
   }
   crossings += (unsigned)B;
   r.t = tS;
+  if (vlast) *vlast = MASK ? __ldg(P.layerLeap + r.iz + GH) : sg[B - 1] + 1.0f;
   if (REG) {
     r.ix = wrap_index<WIDE>(r.ix, P.nx);
     r.iy = wrap_index<WIDE>(r.iy, P.ny);
@@ -315,6 +326,69 @@ __device__ __forceinline__ int march_burst(Ray &r, const DevDomain &P, const Gri
     while (r.iy < 0) { r.iy += P.ny; r.oy += P.fLy; }
     while (r.iy >= P.ny) { r.iy -= P.ny; r.oy -= P.fLy; }
   }
+  return MARCH_ON;
+}
+
+// One leap through vacuum (photon-pool kernels, uniform grids): the ray is in a cell whose vacuum distance is at least
+// D (mcb_stage.cu: every cell within D - 1 cells of it, Chebyshev, has no extinction; the caller has limited D by the
+// number of layers up to the boundary the ray is heading for -- leap_distance -- so the cube ends on that boundary at
+// the latest), so it can go straight to where it leaves that cube -- D faces away along one axis -- without looking at
+// a single cell: no optical depth accumulates on the way (OPT:1729-1738 adds 0 per cell).  The DDA state is advanced by
+// whole faces (face distances stay on the same lattice tx0 + n * step as the cell-by-cell walk) and the cells passed are
+// counted (one per face crossed: the cell the ray is in now up to the last one before the landing cell, exactly what
+// bursts over the same path would have counted).  Landing on the top / the surface ends the leg like a burst does
+// (RAW); otherwise the caller marches on from the landing cell with a burst IN THE SAME ITERATION, whose last gather
+// says whether the next iteration starts with a leap again.  (Measured, r02: a leap that took the place of the burst --
+// with one gather at the landing cell to chain leaps -- covered 42 % of the C3 crossings and gained nothing: its
+// divergent code and the extra dependent round trip per iteration cost what the saved bursts had bought.)
+// how far the ray may leap from its cell (0: march): v = what is known about the cell (march_burst's vlast)
+__device__ __forceinline__ int leap_distance(const Ray &r, const DevDomain &P, float v, float leapBelow) {
+  if (!(v <= leapBelow)) return 0;
+  const int D = min((int)(-v), r.dz >= 0.0f ? P.nz - r.iz : r.iz + 1);
+  return D >= 2 ? D : 0;
+}
+//
+// MASK (fields read through the occupancy bitmap, whose clear sky is not vacuum): D counts layers that are clear
+// throughout (layerLeap), the optical depth of the leap is that of the horizontally uniform clear sky (layerExt,
+// layerCum) -- and if the target falls inside it the leap is not taken (the burst that follows finds the event).
+template <bool MASK>
+__device__ __forceinline__ int march_leap(Ray &r, const DevDomain &P, const int D, unsigned &crossings,
+                                          float &ext, const float target) {
+  const float k = (float)(D - 1);
+  const float ax = fabsf(r.rx) * P.fhx, ay = fabsf(r.ry) * P.fhy, az = fabsf(r.rz) * P.fhz;   // path between two faces (inf: axis not moving)
+  const float ex = fmaf(k, ax, r.tx), ey = fmaf(k, ay, r.ty), ez = fmaf(k, az, r.tz);          // where the cube ends
+  const float te = fminf(fminf(ex, ey), ez);
+  // faces crossed on the way: all D along the axis the ray leaves through, fewer along the others
+  int nx = 0, ny = 0, nz = 0;
+  if (r.tx <= te) nx = ex == te ? D : min((int)((te - r.tx) * (fabsf(r.dx) * P.finvhx)) + 1, D);
+  if (r.ty <= te) ny = ey == te ? D : min((int)((te - r.ty) * (fabsf(r.dy) * P.finvhy)) + 1, D);
+  if (r.tz <= te) nz = ez == te ? D : min((int)((te - r.tz) * (fabsf(r.dz) * P.finvhz)) + 1, D);
+  if (MASK) {                                                // clear-sky optical depth from r.t to te
+    const float *L = P.layerExt + GH;
+    const bool up = r.dz >= 0.0f;
+    float tauL = fabsf(__ldg(L + r.iz));
+    if (nz == 0) {
+      tauL *= te - r.t;
+    } else {                                                 // rest of this layer + whole layers + the part of the landing layer
+      const int izN = r.iz + (up ? nz : -nz);                // (the ghost layer outside the domain has no extinction)
+      const float c0 = __ldg(P.layerCum + (up ? r.iz + 1 : r.iz)), c1 = __ldg(P.layerCum + (up ? izN : izN + 1));
+      tauL = tauL * (r.tz - r.t) + fabsf(c1 - c0) * fabsf(r.rz) + fabsf(__ldg(L + izN)) * (te - fmaf((float)(nz - 1), az, r.tz));
+    }
+    if (ext + tauL > target) return MARCH_ON;
+    ext += tauL;
+  }
+  if (nx) { r.tx = fmaf((float)nx, ax, r.tx); r.ix += r.dx >= 0.0f ? nx : -nx; }
+  if (ny) { r.ty = fmaf((float)ny, ay, r.ty); r.iy += r.dy >= 0.0f ? ny : -ny; }
+  if (nz) { r.tz = fmaf((float)nz, az, r.tz); r.iz += r.dz >= 0.0f ? nz : -nz; }
+  crossings += (unsigned)(nx + ny + nz);
+  if ((unsigned)r.iz >= (unsigned)P.nz) {                    // landed on the boundary: the leg ends there
+    const bool top = r.iz > 0;
+    r.t = ((top ? P.fzMax : P.fz0) - r.oz) * r.rz;
+    return top ? MARCH_TOP : MARCH_BOTTOM;
+  }
+  r.t = te;
+  r.ix = wrap_index<true>(r.ix, P.nx);
+  r.iy = wrap_index<true>(r.iy, P.ny);
   return MARCH_ON;
 }
 

@@ -46,9 +46,9 @@ enum { PW_PX = 0, PW_PY, PW_PZ, PW_DX, PW_DY, PW_DZ, PW_W, PW_TAU, PW_UNEXT, PW_
 template <int THREADS, int MINBLOCKS, int BURST, bool SPLIT, bool MASK, bool BRICK>
 __global__ void __launch_bounds__(THREADS, MINBLOCKS)
 pool_kernel(const __grid_constant__ DevDomain P, long long nPhotons, uint64_t seed, uint64_t firstPhotonId,
-            unsigned long long *workCounter, const SmemPlan plan) {
+            unsigned long long *workCounter, const SmemPlan plan, const float leapBelow, const int leapLanes) {
   extern __shared__ float smem[];
-  __shared__ unsigned sCnt[4];            // rare events: surface hits, surface kills, roulette kills
+  __shared__ unsigned sCnt[6];            // rare events: surface hits, surface kills, roulette kills
   const int cols = P.nx * P.ny, cells = cols * P.nz;
   Grid G;
   G.sx = G.sy = G.sz = nullptr;
@@ -59,7 +59,7 @@ pool_kernel(const __grid_constant__ DevDomain P, long long nPhotons, uint64_t se
   T.sInt = nullptr;
   if (T.sFlux) for (int i = threadIdx.x; i < 2 * cols; i += THREADS) T.sFlux[i] = 0.0f;
   if (T.sVol) for (int i = threadIdx.x; i < cells; i += THREADS) T.sVol[i] = 0.0f;
-  if (threadIdx.x < 4) sCnt[threadIdx.x] = 0u;
+  if (threadIdx.x < 6) sCnt[threadIdx.x] = 0u;
   __syncthreads();
 
   const int lane = threadIdx.x & 31;
@@ -73,6 +73,7 @@ pool_kernel(const __grid_constant__ DevDomain P, long long nPhotons, uint64_t se
   r.ox = r.oy = r.oz = 0.0f; r.dx = r.dy = 0.0f; r.dz = 1.0f; r.rx = r.ry = r.rz = FLT_MAX;
   r.t = 0.0f; r.tx = r.ty = r.tz = FLT_MAX; r.ix = r.iy = r.iz = 0;
   float ext = 0.0f, tau = 0.0f, w = 0.0f, uNext = 0.0f;
+  float vcur = 0.0f;                     // <= -1: the ray's cell is vacuum, and so is everything within -vcur - 1 cells of it
   uint32_t c0 = 0u, c1 = 0u, blk = 0u;
   bool have = false;
   bool more = true;                      // photons may remain in the global counter
@@ -301,7 +302,7 @@ pool_kernel(const __grid_constant__ DevDomain P, long long nPhotons, uint64_t se
           r.iz = __float_as_int(pool[PW_IZK * POOL_SLOTS + s]);
           r.tx = pool[PW_TX * POOL_SLOTS + s]; r.ty = pool[PW_TY * POOL_SLOTS + s]; r.tz = pool[PW_TZ * POOL_SLOTS + s];
           r.rx = safe_rcp(r.dx); r.ry = safe_rcp(r.dy); r.rz = safe_rcp(r.dz);
-          r.t = 0.0f; ext = 0.0f;
+          r.t = 0.0f; ext = 0.0f; vcur = 0.0f;
           have = true;
         }
         nR -= min(__popc(idle), nR);
@@ -311,8 +312,18 @@ pool_kernel(const __grid_constant__ DevDomain P, long long nPhotons, uint64_t se
     if (!__any_sync(FULL, have)) break;                    // nothing marching, nothing ready, no event waiting: done
 
     // =========================== march: one burst for every lane ===========================
+    // (a lane whose cell is known to lie deep enough in vacuum crosses that in one leap first: march_leap)
     int ev = MARCH_ON;
-    if (have) ev = march_burst<true, true, BURST, MASK, BRICK, true, SPLIT>(r, P, G, ext, tau, crossings);
+    int D = have ? leap_distance(r, P, vcur, leapBelow) : 0;
+    if (leapLanes > 1 && __popc(__ballot_sync(FULL, D > 0)) < leapLanes) D = 0;     // too few lanes to pay for the divergence
+    if (D) {                                                // (implies have)
+      const unsigned before = crossings, lanes = __activemask();
+      ev = march_leap<MASK>(r, P, D, crossings, ext, tau);
+      const unsigned cells = __reduce_add_sync(lanes, crossings - before);      // counters leaps / leapCells: one lane adds
+      const unsigned took = __ballot_sync(lanes, crossings != before);           // (a leap the target falls into is not taken)
+      if (lane == __ffs(lanes) - 1) { atomicAdd(&sCnt[4], (unsigned)__popc(took)); atomicAdd(&sCnt[5], cells); }
+    }
+    if (have && ev == MARCH_ON) ev = march_burst<true, true, BURST, MASK, BRICK, true, SPLIT>(r, P, G, ext, tau, crossings, &vcur);
 
     // =========================== photons that reached an event go onto EVENT ===========================
     {
@@ -351,6 +362,8 @@ pool_kernel(const __grid_constant__ DevDomain P, long long nPhotons, uint64_t se
     if (sCnt[0]) atomicAdd(&P.counters[CNT_SURFACE], (unsigned long long)sCnt[0]);
     if (sCnt[1]) atomicAdd(&P.counters[CNT_SURFACE_KILLS], (unsigned long long)sCnt[1]);
     if (sCnt[2]) atomicAdd(&P.counters[CNT_RR_KILLS], (unsigned long long)sCnt[2]);
+    if (sCnt[4]) atomicAdd(&P.counters[CNT_LEAPS], (unsigned long long)sCnt[4]);
+    if (sCnt[5]) atomicAdd(&P.counters[CNT_LEAP_CELLS], (unsigned long long)sCnt[5]);
   }
   // ---- flush: privatised tallies, once per block, into the f64 tally buffer ----
   if (T.sFlux)
@@ -394,7 +407,9 @@ static void launch_pool(const DevDomain &P, long long nPhotons, uint64_t seed, u
   const long long want = (nPhotons + perBlock - 1) / perBlock;
   const long long cap = (long long)numSMs * blocksPerSM;    // persistent: every CTA resident, whole waves only
   const int blocks = (int)(want < cap ? want : cap);
-  kernel<<<blocks, THREADS, smem, stream>>>(P, nPhotons, seed, firstPhotonId, workCounter, plan);
+  // vacuum leaps: from a distance of tuneLeap cells (default MCB_LEAP_MIN; < 0: never)
+  const float leapBelow = P.opt.tuneLeap < 0 ? -FLT_MAX : -(float)(P.opt.tuneLeap >= 2 ? P.opt.tuneLeap : MCB_LEAP_MIN);
+  kernel<<<blocks, THREADS, smem, stream>>>(P, nPhotons, seed, firstPhotonId, workCounter, plan, leapBelow, P.opt.tuneLeapLanes > 0 ? P.opt.tuneLeapLanes : MCB_LEAP_LANES);
 }
 
 // the pool kernel covers flux-only runs on uniform grids at least a ghost shell wide

@@ -69,9 +69,9 @@ __device__ __forceinline__ float view_phase_value(const DevDomain &P, int compon
 template <int THREADS, int MINBLOCKS, int BURST, bool MASK, bool BRICK>
 __global__ void __launch_bounds__(THREADS, MINBLOCKS)
 pool_le_kernel(const __grid_constant__ DevDomain P, long long nPhotons, uint64_t seed, uint64_t firstPhotonId,
-               unsigned long long *workCounter, const SmemPlan plan) {
+               unsigned long long *workCounter, const SmemPlan plan, const float leapBelow, const int leapLanes) {
   extern __shared__ float smem[];
-  __shared__ unsigned sCnt[4];
+  __shared__ unsigned sCnt[6];
   const int cols = P.nx * P.ny, cells = cols * P.nz;
   const int nDir = P.nDir;
   const bool useRR = P.opt.useRussianRouletteForIntensity != 0;
@@ -86,7 +86,7 @@ pool_le_kernel(const __grid_constant__ DevDomain P, long long nPhotons, uint64_t
   if (T.sFlux) for (int i = threadIdx.x; i < 2 * cols; i += THREADS) T.sFlux[i] = 0.0f;
   if (T.sVol) for (int i = threadIdx.x; i < cells; i += THREADS) T.sVol[i] = 0.0f;
   if (T.sInt) for (int i = threadIdx.x; i < cols * nDir; i += THREADS) T.sInt[i] = 0.0f;
-  if (threadIdx.x < 4) sCnt[threadIdx.x] = 0u;
+  if (threadIdx.x < 6) sCnt[threadIdx.x] = 0u;
   __syncthreads();
 
   const int lane = threadIdx.x & 31;
@@ -105,6 +105,7 @@ pool_le_kernel(const __grid_constant__ DevDomain P, long long nPhotons, uint64_t
   r.ox = r.oy = r.oz = 0.0f; r.dx = r.dy = 0.0f; r.dz = 1.0f; r.rx = r.ry = r.rz = FLT_MAX;
   r.t = 0.0f; r.tx = r.ty = r.tz = FLT_MAX; r.ix = r.iy = r.iz = 0;
   float ext = 0.0f, tgt = 0.0f, jw = 0.0f, ja = 0.0f;
+  float vcur = 0.0f;                                          // <= -1: the ray's cell lies -vcur cells deep in vacuum (march_leap)
   uint32_t jb = 0u, jc = 0u, jd = 0u;
   int order = 0;
   int job = JOB_NONE;
@@ -385,7 +386,7 @@ pool_le_kernel(const __grid_constant__ DevDomain P, long long nPhotons, uint64_t
           r.ox = ring[RQ_PX * PLE_REQS + s]; r.oy = ring[RQ_PY * PLE_REQS + s]; r.oz = ring[RQ_PZ * PLE_REQS + s];
           r.dx = P.viewDir[3 * dir]; r.dy = P.viewDir[3 * dir + 1]; r.dz = P.viewDir[3 * dir + 2];
           ray_start<true>(r, P, G);
-          ext = 0.0f;
+          ext = 0.0f; vcur = 0.0f;
           jw = ring[RQ_W * PLE_REQS + s];
           ja = ring[(RQ_T + 3 * dir) * PLE_REQS + s];                                   // npf
           jb = __float_as_uint(ring[(RQ_T + 3 * dir + 1) * PLE_REQS + s]);              // tauFree
@@ -414,7 +415,7 @@ pool_le_kernel(const __grid_constant__ DevDomain P, long long nPhotons, uint64_t
           r.ix = ixy & 0xffff; r.iy = (int)((uint32_t)ixy >> 16); r.iz = izo & 0xffff; order = (int)((uint32_t)izo >> 16);
           r.tx = pool[PW_TX * PLE_SLOTS + s]; r.ty = pool[PW_TY * PLE_SLOTS + s]; r.tz = pool[PW_TZ * PLE_SLOTS + s];
           r.rx = safe_rcp(r.dx); r.ry = safe_rcp(r.dy); r.rz = safe_rcp(r.dz);
-          r.t = 0.0f; ext = 0.0f;
+          r.t = 0.0f; ext = 0.0f; vcur = 0.0f;
           job = JOB_PHOTON;
         }
         nR -= legs;
@@ -426,7 +427,16 @@ pool_le_kernel(const __grid_constant__ DevDomain P, long long nPhotons, uint64_t
     // =========================== march: one burst for every lane ===========================
     int ev = MARCH_ON;
     unsigned crossed = 0u;
-    if (job != JOB_NONE) ev = march_burst<true, true, BURST, MASK, BRICK, true, false>(r, P, G, ext, tgt, crossed);
+    int D = job != JOB_NONE ? leap_distance(r, P, vcur, leapBelow) : 0;
+    if (leapLanes > 1 && __popc(__ballot_sync(FULL, D > 0)) < leapLanes) D = 0;     // too few lanes to pay for the divergence
+    if (D) {                                                   // first through vacuum in one leap where the cell is known to lie
+      const unsigned lanes = __activemask();
+      ev = march_leap<MASK>(r, P, D, crossed, ext, tgt);       // deep in it (implies a job)
+      const unsigned cells = __reduce_add_sync(lanes, crossed);                  // counters leaps / leapCells: one lane adds
+      const unsigned took = __ballot_sync(lanes, crossed != 0u);                 // (a leap the target falls into is not taken)
+      if (lane == __ffs(lanes) - 1) { atomicAdd(&sCnt[4], (unsigned)__popc(took)); atomicAdd(&sCnt[5], cells); }
+    }
+    if (job != JOB_NONE && ev == MARCH_ON) ev = march_burst<true, true, BURST, MASK, BRICK, true, false>(r, P, G, ext, tgt, crossed, &vcur);
     if (job == JOB_PHOTON) crossings += crossed; else leCrossings += crossed;
 
     // =========================== rays that ended ===========================
@@ -448,7 +458,7 @@ pool_le_kernel(const __grid_constant__ DevDomain P, long long nPhotons, uint64_t
           cell_decode<true, BRICK>(P, raw, r.ix, r.iy, r.iz);
           r.ox = qx; r.oy = qy; r.oz = qz;
           ray_start<true>(r, P, G);
-          ext = 0.0f; tgt = tauFree; job = JOB_E14B;
+          ext = 0.0f; vcur = 0.0f; tgt = tauFree; job = JOB_E14B;
           finished = false;
         }
       } else {                                                 // JOB_E14B
@@ -508,6 +518,8 @@ pool_le_kernel(const __grid_constant__ DevDomain P, long long nPhotons, uint64_t
     if (sCnt[0]) atomicAdd(&P.counters[CNT_SURFACE], (unsigned long long)sCnt[0]);
     if (sCnt[1]) atomicAdd(&P.counters[CNT_SURFACE_KILLS], (unsigned long long)sCnt[1]);
     if (sCnt[2]) atomicAdd(&P.counters[CNT_RR_KILLS], (unsigned long long)sCnt[2]);
+    if (sCnt[4]) atomicAdd(&P.counters[CNT_LEAPS], (unsigned long long)sCnt[4]);
+    if (sCnt[5]) atomicAdd(&P.counters[CNT_LEAP_CELLS], (unsigned long long)sCnt[5]);
   }
   if (T.sFlux)
     for (int i = threadIdx.x; i < 2 * cols; i += THREADS) {
@@ -557,7 +569,8 @@ static void launch_pool_le(const DevDomain &P, long long nPhotons, uint64_t seed
   const long long want = (nPhotons + perBlock - 1) / perBlock;
   const long long cap = (long long)numSMs * blocksPerSM;
   const int blocks = (int)(want < cap ? want : cap);
-  kernel<<<blocks, THREADS, smem, stream>>>(P, nPhotons, seed, firstPhotonId, workCounter, plan);
+  const float leapBelow = P.opt.tuneLeap < 0 ? -FLT_MAX : -(float)(P.opt.tuneLeap >= 2 ? P.opt.tuneLeap : MCB_LEAP_MIN);
+  kernel<<<blocks, THREADS, smem, stream>>>(P, nPhotons, seed, firstPhotonId, workCounter, plan, leapBelow, P.opt.tuneLeapLanes > 0 ? P.opt.tuneLeapLanes : MCB_LEAP_LANES);
 }
 
 // runs with view directions on uniform grids at least a ghost shell wide, up to MCB_POOL_LE_MAXDIR directions

@@ -20,8 +20,12 @@ enum { FLAG_EXT = 1, FLAG_SSA = 2, FLAG_IDX = 4, FLAG_TEMP = 8, FLAG_REFF = 16 }
 
 // flags[0]: argument-check bits; flags[2..3] (as one u64): bit pattern of maxval(totalExt) -- non-negative
 // doubles order like their bit patterns, so an integer atomicMax does the reduction (INT:448)
+// dist (or nullptr): the vacuum-distance map of the domain (below).  A cell without extinction then carries -D instead
+// of 0: D = Chebyshev distance (in cells) to the nearest cell that has extinction.  The marchers clamp what they gather
+// at 0, so the field reads exactly as before; the photon-pool kernels use D to cross vacuum in one step (march_leap).
 __global__ void pack_extinction_kernel(const double *__restrict__ totalExt, float *__restrict__ e32,
-                                       int nx, int ny, int nz, int G, int *flags, int nxp, int nyp, long long total, int brick) {
+                                       int nx, int ny, int nz, int G, int *flags, int nxp, int nyp, long long total, int brick,
+                                       const uint8_t *__restrict__ dist) {
   int bad = 0;
   double emax = 0.0;
   for (long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x; p < total; p += (long long)gridDim.x * blockDim.x) {
@@ -43,6 +47,7 @@ __global__ void pack_extinction_kernel(const double *__restrict__ totalExt, floa
       if (!(e >= 0.0)) bad = FLAG_EXT;
       emax = e > emax ? e : emax;
       v = (float)e;
+      if (dist && v == 0.0f) v = -(float)dist[mx + (long long)nx * (my + (long long)ny * (k - G))];
     }
     e32[p] = v;
   }
@@ -52,20 +57,51 @@ __global__ void pack_extinction_kernel(const double *__restrict__ totalExt, floa
     atomicMax((unsigned long long *)(flags + 2), (unsigned long long)__double_as_longlong(emax));
 }
 
-// clear-sky value of every layer: the layer minimum of (float)totalExt (the ghost layers keep the 0 they were cleared
-// to).  One block per real layer.
-__global__ void layer_min_kernel(const double *__restrict__ totalExt, int cols, int G, float *__restrict__ layerExt) {
-  __shared__ float s[32];
-  const double *L = totalExt + (long long)blockIdx.x * cols;
-  float m = FLT_MAX;
-  for (int i = threadIdx.x; i < cols; i += blockDim.x) m = fminf(m, (float)L[i]);
-  for (int o = 16; o > 0; o >>= 1) m = fminf(m, __shfl_down_sync(0xffffffffu, m, o));
-  if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = m;
+// clear-sky value of every layer: the layer minimum of (float)totalExt; 0 in the ghost layers.  A layer in which EVERY
+// cell has that value (above the highest cloud top, below the lowest base, the ghost layers) carries it with the sign
+// bit set: the marcher then knows without looking at the bitmap that no cell of the layer needs a gather.
+// One block per padded layer.
+__global__ void layer_min_kernel(const double *__restrict__ totalExt, int cols, int nz, int G, float *__restrict__ layerExt) {
+  __shared__ float s[32], t[32];
+  const int layer = (int)blockIdx.x - G;                       // real layer, or a ghost layer (outside [0, nz))
+  if (layer < 0 || layer >= nz) {
+    if (threadIdx.x == 0) layerExt[blockIdx.x] = -0.0f;
+    return;
+  }
+  const double *L = totalExt + (long long)layer * cols;
+  float m = FLT_MAX, M = 0.0f;
+  for (int i = threadIdx.x; i < cols; i += blockDim.x) { const float v = (float)L[i]; m = fminf(m, v); M = fmaxf(M, v); }
+  for (int o = 16; o > 0; o >>= 1) { m = fminf(m, __shfl_down_sync(0xffffffffu, m, o)); M = fmaxf(M, __shfl_down_sync(0xffffffffu, M, o)); }
+  if ((threadIdx.x & 31) == 0) { s[threadIdx.x >> 5] = m; t[threadIdx.x >> 5] = M; }
   __syncthreads();
   if (threadIdx.x < 32) {
     m = threadIdx.x < (blockDim.x >> 5) ? s[threadIdx.x] : FLT_MAX;
-    for (int o = 16; o > 0; o >>= 1) m = fminf(m, __shfl_down_sync(0xffffffffu, m, o));
-    if (threadIdx.x == 0) layerExt[blockIdx.x + G] = m;
+    M = threadIdx.x < (blockDim.x >> 5) ? t[threadIdx.x] : 0.0f;
+    for (int o = 16; o > 0; o >>= 1) { m = fminf(m, __shfl_down_sync(0xffffffffu, m, o)); M = fmaxf(M, __shfl_down_sync(0xffffffffu, M, o)); }
+    if (threadIdx.x == 0) layerExt[blockIdx.x] = (M == m) ? __uint_as_float(__float_as_uint(m) | 0x80000000u) : m;
+  }
+}
+
+// What the marcher needs to cross whole clear layers in one step (march_leap, MASK): per padded layer the distance, in
+// layers, to the nearest layer that is not clear throughout (0 for such a layer and in the ghost layers; cap if there
+// is none within cap), and the clear-sky optical depth per unit |1/mu| from the surface up to every layer edge.
+__global__ void layer_tables_kernel(const float *__restrict__ layerExt, int nz, int G, int cap, float hz,
+                                    float *__restrict__ layerLeap, float *__restrict__ layerCum) {
+  for (int l = threadIdx.x; l < nz + 2 * G + 2; l += blockDim.x) {
+    const int k = l - G;
+    int d = 0;
+    if (k >= 0 && k < nz && signbit(layerExt[l])) {
+      d = cap;
+      for (int s = 1; s < d; ++s) {
+        const bool up = k + s < nz && !signbit(layerExt[l + s]), dn = k - s >= 0 && !signbit(layerExt[l - s]);
+        if (up || dn) d = s;
+      }
+    }
+    layerLeap[l] = -(float)d;                                  // the form march_leap's callers keep it in
+  }
+  if (threadIdx.x == 0) {
+    double c = 0.0;
+    for (int k = 0; k <= nz; ++k) { layerCum[k] = (float)c; if (k < nz) c += (double)fabsf(layerExt[k + G]) * (double)hz; }
   }
 }
 
@@ -81,9 +117,53 @@ __global__ void occupancy_mask_kernel(const float *__restrict__ e32, const float
     const long long p = (w << 5) + lane;
     bool bit = false;
     // layer of address p: x-fastest p / slice; bricked: slice/4 bricks per brick layer, bit 2 of p = z inside the brick
-    if (p < total) bit = e32[p] != layerExt[brick ? 2 * ((p >> 3) / (slice >> 2)) + ((p >> 2) & 1) : p / slice];
+    if (p < total) bit = e32[p] != fabsf(layerExt[brick ? 2 * ((p >> 3) / (slice >> 2)) + ((p >> 2) & 1) : p / slice]);
     const unsigned m = __ballot_sync(0xffffffffu, bit);
     if (lane == 0) mask[w] = m;
+  }
+}
+
+// ---- vacuum-distance map: D(cell) = Chebyshev distance to the nearest cell with extinction (0 for such a cell), periodic
+// in x and y, limited by cap; nothing lies above the top or below the surface (the marcher limits a leap by the distance
+// to the boundary the ray is heading for).  max(a, min_i b_i) = min_i max(a, b_i) makes the transform separable: along
+// x, then y, then z.
+__global__ void dist_x_kernel(const double *__restrict__ totalExt, int nx, long long cells, int cap, uint8_t *__restrict__ d) {
+  for (long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x; p < cells; p += (long long)gridDim.x * blockDim.x) {
+    const int i = (int)(p % nx);
+    const double *row = totalExt + (p - i);
+    int best = cap;
+    if ((float)row[i] != 0.0f) best = 0;
+    for (int s = 1; s < best; ++s) {
+      int a = i + s; a -= a >= nx ? nx : 0;
+      int b = i - s; b += b < 0 ? nx : 0;
+      if ((float)row[a] != 0.0f || (float)row[b] != 0.0f) best = s;
+    }
+    d[p] = (uint8_t)best;
+  }
+}
+__global__ void dist_y_kernel(const uint8_t *__restrict__ in, int nx, int ny, long long cells, uint8_t *__restrict__ out) {
+  for (long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x; p < cells; p += (long long)gridDim.x * blockDim.x) {
+    const int j = (int)((p / nx) % ny);
+    const uint8_t *col = in + (p - (long long)j * nx);                 // same x, same layer, y = 0
+    int best = in[p];
+    for (int s = 1; s < best; ++s) {
+      int a = j + s; a -= a >= ny ? ny : 0;
+      int b = j - s; b += b < 0 ? ny : 0;
+      const int m = min((int)col[(long long)a * nx], (int)col[(long long)b * nx]);
+      best = min(best, max(s, m));
+    }
+    out[p] = (uint8_t)best;
+  }
+}
+__global__ void dist_z_kernel(const uint8_t *__restrict__ in, long long cols, int nz, long long cells, uint8_t *__restrict__ out) {
+  for (long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x; p < cells; p += (long long)gridDim.x * blockDim.x) {
+    const int k = (int)(p / cols);
+    int best = in[p];
+    for (int s = 1; s < best; ++s) {
+      const int m = min(k + s < nz ? (int)in[p + s * cols] : 255, k - s >= 0 ? (int)in[p - s * cols] : 255);
+      best = min(best, max(s, m));
+    }
+    out[p] = (uint8_t)best;
   }
 }
 
@@ -600,16 +680,27 @@ static int stream_grid(long long n, int threads, int numSMs) {
 // One layout of the padded extinction field (mcb_device.cuh) and, for fields too large for L2, its occupancy bitmap.
 // Also runs the extinction argument check and the maxval reduction (flags).
 void mcb_launch_pack_field(const DevDomain &P, int brick, float *ext, uint32_t *mask, float *layerExt, int *flags,
-                           int numSMs, cudaStream_t stream) {
+                           const uint8_t *dist, int numSMs, cudaStream_t stream) {
   const DevDomain::ExtField &F = brick ? P.brk : P.lin;
   mcbstage::pack_extinction_kernel<<<stream_grid(F.padded, 256, numSMs), 256, 0, stream>>>(
-      P.totalExt, ext, P.nx, P.ny, P.nz, MCB_GHOST, flags, F.nxp, F.nyp, F.padded, brick);
+      P.totalExt, ext, P.nx, P.ny, P.nz, MCB_GHOST, flags, F.nxp, F.nyp, F.padded, brick, dist);
   if (mask) {
-    cudaMemsetAsync(layerExt, 0, sizeof(float) * (P.nz + 2 * MCB_GHOST + 2), stream);
-    mcbstage::layer_min_kernel<<<P.nz, 256, 0, stream>>>(P.totalExt, P.nx * P.ny, MCB_GHOST, layerExt);
+    mcbstage::layer_min_kernel<<<P.nz + 2 * MCB_GHOST + 2, 256, 0, stream>>>(P.totalExt, P.nx * P.ny, P.nz, MCB_GHOST, layerExt);
+    int cap = MCB_LEAP_CAP;
+    cap = cap < P.nx ? cap : P.nx; cap = cap < P.ny ? cap : P.ny;
+    mcbstage::layer_tables_kernel<<<1, 256, 0, stream>>>(layerExt, P.nz, MCB_GHOST, cap, P.fhz, (float *)P.layerLeap, (float *)P.layerCum);
     mcbstage::occupancy_mask_kernel<<<stream_grid(F.padded, 256, numSMs), 256, 0, stream>>>(ext, layerExt, F.padded,
                                                                                             F.nxp * F.nyp, mask, brick);
   }
+}
+
+// the vacuum-distance map of the staged domain: dist[cells] (result) and scratch[cells]
+void mcb_launch_distance_map(const DevDomain &P, int cap, uint8_t *dist, uint8_t *scratch, int numSMs, cudaStream_t stream) {
+  const long long cols = (long long)P.nx * P.ny, cells = cols * P.nz;
+  const int grid = stream_grid(cells, 256, numSMs);
+  mcbstage::dist_x_kernel<<<grid, 256, 0, stream>>>(P.totalExt, P.nx, cells, cap, dist);
+  mcbstage::dist_y_kernel<<<grid, 256, 0, stream>>>(dist, P.nx, P.ny, cells, scratch);
+  mcbstage::dist_z_kernel<<<grid, 256, 0, stream>>>(scratch, cols, P.nz, cells, dist);
 }
 
 void mcb_launch_gather_column_cdf(const double *voxelCDF, int nx, int ny, int nz, double *colCDF, int numSMs, cudaStream_t stream) {

@@ -115,7 +115,8 @@ def specifyParameters(thisIntegrator: integrator, minForwardTableSize=None, minI
                       tuneKernel: Optional[int] = None, tuneLayout: Optional[int] = None,
                       tuneBlocksPerSM: Optional[int] = None, tuneParkThreshold: Optional[int] = None,
                       tuneLeCarry: Optional[int] = None, tuneExtMask: Optional[int] = None,
-                      tuneBurst: Optional[int] = None) -> None:
+                      tuneBurst: Optional[int] = None, tuneLeap: Optional[int] = None,
+                      tuneLeapLanes: Optional[int] = None) -> None:
     """``specifyParameters`` (INT:1046-1337): same optional arguments, same checks.
 
     ``arithmetic`` is one addition: ``MCB_ARITH_FAST`` (default) or ``MCB_ARITH_REFERENCE``;
@@ -167,7 +168,7 @@ def specifyParameters(thisIntegrator: integrator, minForwardTableSize=None, minI
     if arithmetic is not None: o.arithmetic = int(arithmetic)
     for name, val in (("tuneKernel", tuneKernel), ("tuneLayout", tuneLayout), ("tuneBlocksPerSM", tuneBlocksPerSM),
                       ("tuneParkThreshold", tuneParkThreshold), ("tuneLeCarry", tuneLeCarry), ("tuneExtMask", tuneExtMask),
-                      ("tuneBurst", tuneBurst)):
+                      ("tuneBurst", tuneBurst), ("tuneLeap", tuneLeap), ("tuneLeapLanes", tuneLeapLanes)):
         if val is not None:
             setattr(o, name, int(val))
     if buildTablesOnDevice is not None:
@@ -358,6 +359,16 @@ def gatherProbe(thisIntegrator: integrator, nbytes: int, loadsInFlight: int = 8,
                                                                      int(blocksPerSM), int(iterations), C.byref(out)),
                           "gatherProbe")
     return float(out.value)
+
+
+def vacuumDistanceMap(thisIntegrator: integrator, domain) -> np.ndarray:
+    """The (nz, ny, nx) map of Chebyshev distances to the nearest cell with extinction that the packed extinction
+    field of ``domain`` is encoded with (``csrc/mcb_stage.cu``; the photon-pool kernels leap that far through vacuum)."""
+    g = thisIntegrator
+    _stage_domain(g, domain)
+    out = np.zeros((domain.numZ, domain.numY, domain.numX), dtype=np.uint8)
+    g._check(g._lib.mcb_debug_distance_map(g.handle, out.ctypes.data_as(C.POINTER(C.c_uint8)), out.size), "vacuumDistanceMap")
+    return out
 
 
 def lastBatchMilliseconds(thisIntegrator: integrator) -> float:

@@ -12,7 +12,7 @@ ap.add_argument("--photons", type=int, default=4000000)
 ap.add_argument("--batches", type=int, default=3)
 ap.add_argument("--views", action="store_true")
 ap.add_argument("--arith", type=int, default=0)
-for knob in ("kernel", "layout", "blocks-per-sm", "park-threshold", "le-carry", "ext-mask", "burst"):   # mcb_options.tune*
+for knob in ("kernel", "layout", "blocks-per-sm", "park-threshold", "le-carry", "ext-mask", "burst", "leap", "leap-lanes"):   # mcb_options.tune*
     ap.add_argument("--" + knob, type=int, default=0)
 ap.add_argument("--tag", default="")
 a = ap.parse_args()
@@ -26,7 +26,7 @@ if a.views:
                       useRussianRouletteForIntensity=True, zetaMin=0.3)
 specifyParameters(g, minInverseTableSize=10001, minForwardTableSize=10001, arithmetic=a.arith,
                   LW_flag=case.get("LW_flag", -1.0), tuneKernel=a.kernel, tuneLayout=a.layout, tuneBlocksPerSM=a.blocks_per_sm,
-                  tuneParkThreshold=a.park_threshold, tuneLeCarry=a.le_carry, tuneExtMask=a.ext_mask, tuneBurst=a.burst)
+                  tuneParkThreshold=a.park_threshold, tuneLeCarry=a.le_carry, tuneExtMask=a.ext_mask, tuneBurst=a.burst, tuneLeap=a.leap, tuneLeapLanes=a.leap_lanes)
 rs = new_RandomNumberSequence([10, 1, 0])
 weights = None
 if case.get("LW_flag", -1.0) > 0:
@@ -40,10 +40,12 @@ for b in range(a.batches):
     computeRadiativeTransfer(g, dom, rs, ps, a.photons)
     ms = lastBatchMilliseconds(g)
     c = getCounters(g)
-    print("batch %d: %.3f ms  %.4g photons/s  %.4g crossings/s  crossings/photon %.1f scatters/photon %.2f bad %d" % (
-        b, ms, a.photons / ms * 1e3, c["crossings"] / ms * 1e3, c["crossings"] / a.photons, c["scatters"] / a.photons, c["bad"]))
+    print("batch %d: %.3f ms  %.4g photons/s  %.4g crossings/s  crossings/photon %.1f scatters/photon %.2f bad %d  leaps/photon %.2f cells/leap %.1f" % (
+        b, ms, a.photons / ms * 1e3, c["crossings"] / ms * 1e3, c["crossings"] / a.photons, c["scatters"] / a.photons, c["bad"],
+        c["leaps"] / a.photons, c["leapCells"] / max(1, c["leaps"])))
     best = max(best, a.photons / ms * 1e3)
-print("BEST %s case=%s views=%d kernel=%d layout=%d occ=%d burst=%d park=%d mask=%d photons=%d: %.4g photons/s" % (
-    a.tag, a.case, a.views, a.kernel, a.layout, a.blocks_per_sm, a.burst, a.park_threshold, a.ext_mask, a.photons, best))
+print("BEST %s case=%s views=%d kernel=%d layout=%d occ=%d burst=%d park=%d mask=%d leap=%d/%d photons=%d: %.4g photons/s  leaps/photon %.2f cells/leap %.1f" % (
+    a.tag, a.case, a.views, a.kernel, a.layout, a.blocks_per_sm, a.burst, a.park_threshold, a.ext_mask, a.leap, a.leap_lanes, a.photons, best,
+    c["leaps"] / a.photons, c["leapCells"] / max(1, c["leaps"])))
 r = reportResults(g, meanFluxUp=True, meanFluxDown=True, meanFluxAbsorbed=True)
 print({k: float(v) for k, v in r.items()})

@@ -43,7 +43,7 @@ def test_only_sm_100a_code_is_embedded():
 
 
 def test_struct_layouts_match_header():
-    assert C.sizeof(_lib.mcb_options) == 84          # 11 reference-facing words + 7 tune knobs + 3 reserved
+    assert C.sizeof(_lib.mcb_options) == 84          # 11 reference-facing words + 9 tune knobs + 1 reserved
     assert C.sizeof(_lib.mcb_counters) == 128
     assert _lib.EVENT_DTYPE.itemsize == 96
     assert _lib.EVENT_DTYPE.fields["path"][1] == 48 and _lib.EVENT_DTYPE.fields["dir"][1] == 80

@@ -86,7 +86,7 @@ def test_compiled_host_writes_the_ascii_tables(tmp_path):
     assert abs(up.mean() - avg) < 2e-4                      # the average line is the mean of the pixel column
     rad = open(prefix + "_rad.out").read().split("\n")
     assert sum(1 for l in rad if l.endswith("<- (mu,phi)")) == 5
-    assert "NXO=  32   NYO=   1   NDIR=   5" in rad[11]
+    assert "NXO=  32   NYO=   1   NDIR=   5" in rad[10] and rad[11].startswith("!   X      Y")
     prof = [l for l in open(prefix + "_absprof.out").read().split("\n") if l and not l.startswith("!")]
     assert len(prof) == 32
     vol = [l for l in open(prefix + "_absvol.out").read().split("\n") if l and not l.startswith("!")]

@@ -1,0 +1,141 @@
+"""Vacuum leaps of the photon-pool kernels (csrc/mcb_march.cuh march_leap, csrc/mcb_stage.cu dist_*_kernel).
+
+The packed extinction field carries, in every cell without extinction, the Chebyshev distance D to the nearest cell
+that has some; a ray whose cell lies D >= 4 cells deep in vacuum goes straight to the face where it leaves the cube of
+D - 1 cells around it.  No optical depth accumulates in vacuum (OPT:1729-1738 adds 0 per cell), so the physics is the
+cell-by-cell walk's: (1) the map is checked against a brute-force transform, (2) leaps on / off give the same photon
+histories up to rounding at the landing faces -- event counters (including the cells-crossed counter, which a leap
+advances by the faces it crosses) and tallies agree far inside the Monte Carlo noise, (3) the full-size 1e8-photon
+maps of tests/test_gpu_headline.py run with leaps on (the default)."""
+import numpy as np
+import pytest
+
+from mcbrat3d_b200 import domains
+from mcbrat3d_b200.monteCarloIllumination import new_PhotonStream
+from mcbrat3d_b200.monteCarloRadiativeTransfer import (MCB_KERNEL_POOL, computeRadiativeTransfer, finalize_Integrator,
+                                                       getCounters, new_Integrator, reportResults, specifyParameters,
+                                                       vacuumDistanceMap)
+from mcbrat3d_b200.RandomNumbersForMC import new_RandomNumberSequence
+
+pytestmark = pytest.mark.gpu
+
+
+def brute_force_distance(ext, cap):
+    """ext (nz, ny, nx).  Grow cubes around the occupied cells one shell at a time: periodic in x and y, nothing
+    above the top or below the surface."""
+    occ = np.asarray(ext, np.float32) != 0
+    nz = occ.shape[0]
+    D = np.where(occ, 0, cap).astype(np.int32)
+    reach = np.concatenate([np.zeros_like(occ[:1]), occ, np.zeros_like(occ[:1])], axis=0)
+    for s in range(1, cap):
+        grown = reach.copy()
+        for ax in (1, 2):                                   # periodic axes
+            grown = grown | np.roll(grown, 1, axis=ax) | np.roll(grown, -1, axis=ax)
+        up = np.zeros_like(grown); up[1:] = grown[:-1]
+        dn = np.zeros_like(grown); dn[:-1] = grown[1:]
+        grown = grown | up | dn
+        new = grown[1:nz + 1] & ~reach[1:nz + 1]
+        D[new] = s
+        reach = grown
+        reach[0] = reach[-1] = False
+    return D
+
+
+def sparse_domain(nx=19, ny=12, nz=23, seed=3):
+    from mcbrat3d_b200.opticalProperties import Domain
+    from mcbrat3d_b200.scatteringPhaseFunctions import henyeyGreenstein, new_PhaseFunctionTable
+    rng = np.random.default_rng(seed)
+    d = Domain(0.5 * np.arange(nx + 1), 0.25 * np.arange(ny + 1), 0.125 * np.arange(nz + 1), surfaceAlbedo=0.3)
+    ext = np.where(rng.random((nz, ny, nx)) < 0.004, rng.uniform(2.0, 40.0, (nz, ny, nx)), 0.0)
+    ext[14:] = 0.0                                         # vacuum above the highest cell
+    ext[3:6, 2:5, 4:9] = 12.0                              # one solid block, the rest isolated cells
+    ssa = np.where(ext > 0, 0.95, 0.0)
+    idx = np.where(ext > 0, 1, 0).astype(np.int32)
+    d.addOpticalComponent("cloud", ext, ssa, idx, new_PhaseFunctionTable([henyeyGreenstein(0.8, 32)], key=[1.0]))
+    d.getOpticalPropertiesByComponent()
+    return d, dict(name="sparse", solarMu=0.35, solarAzimuth=25.0)
+
+
+MAPS = [("C3_small", lambda: domains.landsat_cloud(ssa=0.99, nxy=32)),
+        ("sparse", sparse_domain),
+        ("slab", lambda: domains.homogeneous_slab(ssa=0.99, n=9, delta=0.125))]
+
+
+@pytest.mark.parametrize("name,make", MAPS, ids=[m[0] for m in MAPS])
+def test_vacuum_distance_map_matches_brute_force(name, make):
+    dom, case = make()
+    g = new_Integrator(dom)
+    try:
+        got = vacuumDistanceMap(g, dom).astype(np.int32)
+    finally:
+        finalize_Integrator(g)
+    cap = min(64, dom.numX, dom.numY)
+    want = brute_force_distance(dom.totalExt.reshape(dom.numZ, dom.numY, dom.numX), cap)
+    assert np.array_equal(got, want), (np.argwhere(got != want)[:5], got[got != want][:5], want[got != want][:5])
+    if name != "slab":
+        assert want.max() >= 4                              # there is something to leap through
+
+
+def _run(dom, case, n, views=None, **knobs):
+    g = new_Integrator(dom)
+    try:
+        if views:
+            specifyParameters(g, intensityMus=views[0], intensityPhis=views[1], computeIntensity=True,
+                              useRussianRouletteForIntensity=True, zetaMin=0.3)
+        specifyParameters(g, minInverseTableSize=10001, minForwardTableSize=10001, tuneKernel=MCB_KERNEL_POOL, **knobs)
+        rs = new_RandomNumberSequence([10, 1, 0])
+        ps = new_PhotonStream(case["solarMu"], case["solarAzimuth"], n, rs)
+        assert computeRadiativeTransfer(g, dom, rs, ps, n) == n
+        want = dict(fluxUp=True, fluxDown=True, volumeAbsorption=True, meanFluxUp=True, meanFluxDown=True, meanFluxAbsorbed=True)
+        if views:
+            want.update(intensity=True, meanIntensity=True)
+        return reportResults(g, **want), getCounters(g)
+    finally:
+        finalize_Integrator(g)
+
+
+LEAP_CASES = [("C3_small", lambda: domains.landsat_cloud(ssa=0.99, nxy=32), 400000, None),
+              ("C3_small_linear", lambda: domains.landsat_cloud(ssa=0.99, nxy=32), 300000, None),
+              ("sparse", sparse_domain, 400000, None),
+              ("C5_small_bitmap", lambda: domains.bench_domain(nxy=40, nz=96), 300000, None),   # whole clear layers, not vacuum
+              ("C5_small_bitmap_views", lambda: domains.bench_domain(nxy=24, nz=96), 40000, ([1.0, 0.5, -0.5], [0.0, 0.0, 180.0])),
+              ("C3_small_views", lambda: domains.landsat_cloud(ssa=0.99, nxy=32), 60000, (domains.I3RC_VIEWS_MU, domains.I3RC_VIEWS_PHI)),
+              ("sparse_views", sparse_domain, 60000, ([1.0, 0.5, -0.6], [0.0, 70.0, 200.0]))]
+
+
+@pytest.mark.parametrize("name,make,n,views", LEAP_CASES, ids=[c[0] for c in LEAP_CASES])
+def test_leaps_trace_the_same_histories_up_to_rounding(name, make, n, views):
+    dom, case = make()
+    extra = dict(tuneLayout=1) if name.endswith("linear") else dict(tuneExtMask=1) if "bitmap" in name else {}
+    want, cw = _run(dom, case, n, views, tuneLeap=-1, **extra)
+    assert cw["bad"] == 0
+    for leap in (0, 2, 7):                                  # default distance, the smallest, a larger one
+        got, cg = _run(dom, case, n, views, tuneLeap=leap, tuneLeapLanes=1 if leap else 0, **extra)   # every leap / the default gate
+        assert cg["bad"] == 0 and cg["photons"] == cw["photons"]
+        # Same random numbers, same directions; positions differ by an ulp of the coordinate once a leap has replaced
+        # repeated additions by one multiplication, and a photon that passes within that of a cell edge takes another
+        # cell there: a few photons per thousand end in another column, everything else is the same history.  The
+        # counters move by a few 1e-5, the per-column maps far less than their noise (5 % per column at this size).
+        # (crossings: where a burst runs through the top or the surface, rounding of the boundary distance can count the
+        # first ghost cell as entered -- tests/test_gpu_pool.py; a leap lands on the boundary exactly -- hence up to one
+        # cell per exit between the two counts)
+        for k in ("crossings", "scatters", "surfaceHits", "leRays", "leCrossings"):
+            slack = (cw["photons"] + cw["surfaceHits"] if k == "crossings" else cw["leRays"] if k == "leCrossings" else 0)
+            assert abs(cg[k] - cw[k]) <= 2e-4 * max(cw[k], 1) + 3 + slack, (leap, k, cg[k], cw[k])
+        assert (cg["leaps"] > 0 or leap > 4) and cg["leapCells"] >= 2 * cg["leaps"], (leap, cg["leaps"], cg["leapCells"])
+        for k in ("meanFluxUp", "meanFluxDown", "meanFluxAbsorbed") + (("meanIntensity",) if views else ()):
+            np.testing.assert_allclose(got[k], want[k], rtol=6e-3 if k == "meanIntensity" else 1e-3, atol=1e-6,
+                                       err_msg="%s leap=%d" % (k, leap))
+        for k in ("fluxUp", "fluxDown"):
+            a, b = np.asarray(got[k], np.float64), np.asarray(want[k], np.float64)
+            assert np.abs(a - b).sum() <= 2e-2 * np.abs(b).sum(), (leap, k)
+
+
+def test_leap_counters_on_the_cloud_scene():
+    """How much of a photon's path the leaps cover on the C3 cloud scene (counters leaps / leapCells): every leap crosses
+    at least the distance it was taken from, and the cells it crosses are part of the crossings counter."""
+    dom, case = domains.landsat_cloud(ssa=0.99, nxy=64)
+    _, c = _run(dom, case, 1000000)
+    assert c["leaps"] > 0.5 * c["photons"] and c["leapCells"] >= 4 * c["leaps"] and c["leapCells"] < c["crossings"], c
+    print("leaps per photon %.2f, cells per leap %.1f, share of the crossings %.3f" % (
+        c["leaps"] / c["photons"], c["leapCells"] / c["leaps"], c["leapCells"] / c["crossings"]))
