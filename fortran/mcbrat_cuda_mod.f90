@@ -66,6 +66,7 @@ module mcbrat_cuda
             mcb_build_thermal_source, mcb_frequency_distribution, mcb_accumulate_batch,                  &
             mcb_stats_reset, mcb_run_batches, mcb_stats_buffer, mcb_get_statistics,                       &
             mcb_version, mcb_set_stream, mcb_build_forward_table, mcb_get_inverse_table, mcb_get_forward_table,  &
+            mcb_build_inverse_table_legendre, mcb_build_forward_table_general,                           &
             mcb_get_thermal_source, mcb_last_batch_ms, mcb_get_counters, mcb_get_raw_tallies, mcb_run_trace, &
             mcb_debug_philox, mcb_debug_gather_probe, mcb_debug_distance_map,                            &
             mcb_comm_unique_id, mcb_comm_init, mcb_comm_info, mcb_reduce_tallies, mcb_reduce_statistics, mcb_comm_destroy
@@ -256,6 +257,25 @@ module mcbrat_cuda
       integer(c_int), value :: comp, nS, nE
       integer(c_int32_t), intent(in) :: nCoef(*)
       real(c_float), intent(in) :: coefs(*)
+    end function
+    ! computeInversePhaseFuncTable (INV:66-174) for Legendre-stored tables, Lobatto nodes and all, in HBM
+    integer(c_int) function mcb_build_inverse_table_legendre(handle, comp, nS, nE, nCoef, coefs) &
+        bind(C, name="mcb_build_inverse_table_legendre")
+      import :: c_int, c_ptr, c_float, c_int32_t
+      type(c_ptr), value :: handle
+      integer(c_int), value :: comp, nS, nE
+      integer(c_int32_t), intent(in) :: nCoef(*)
+      real(c_float), intent(in) :: coefs(*)
+    end function
+    ! tabulateForwardPhaseFunctions (OPT:1872-1934) for either storage kind, with the hybrid peak (OPT:1936-2050) if asked
+    integer(c_int) function mcb_build_forward_table_general(handle, comp, nS, nE, nCoef, coefs, nAngles, angles, values, &
+        hybridWidthDeg) bind(C, name="mcb_build_forward_table_general")
+      import :: c_int, c_ptr, c_float, c_int32_t
+      type(c_ptr), value :: handle
+      integer(c_int), value :: comp, nS, nE
+      integer(c_int32_t), intent(in) :: nCoef(*), nAngles(*)
+      real(c_float), intent(in) :: coefs(*), angles(*), values(*)
+      real(c_float), value :: hybridWidthDeg
     end function
     integer(c_int) function mcb_get_inverse_table(handle, comp, T, nFloats) bind(C, name="mcb_get_inverse_table")
       import :: c_int, c_ptr, c_float, c_int64_t

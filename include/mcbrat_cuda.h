@@ -133,11 +133,21 @@ int mcb_set_inverse_table(mcb_handle *h, int comp, int nS, int nE, const float *
  * the nS brackets and the analytic inversions run in HBM.  mcb_get_inverse_table reads a staged table back.   */
 int mcb_build_inverse_table(mcb_handle *h, int comp, int nS, int nE, const int32_t *nAngles,
                             const float *mus, const float *values);
+/* The same for a table whose entries are all stored as Legendre moments (entry e: nCoef[e] moments chi_1.., concatenated
+ * in coefs), with nothing evaluated on the host: computeLobattoTerms NUM:27-114 (the max(nMoments,2) abscissas), the
+ * phase function there (SPF:480-498, NUM:187-205) and the inversion all run in HBM.                              */
+int mcb_build_inverse_table_legendre(mcb_handle *h, int comp, int nS, int nE, const int32_t *nCoef, const float *coefs);
 int mcb_get_inverse_table(mcb_handle *h, int comp, float *T, int64_t nFloats);
 /* tabulateForwardPhaseFunctions (OPT:1872-1934) on the device for tables stored as Legendre moments: entry e has
  * nCoef[e] moments chi_1.. (concatenated in coefs; 0 moments = isotropic); fills tabPhase and tabOrigPhase alike
  * (hybrid tables, OPT:1936-2050, and angle/value tables are staged with mcb_set_forward_table).                  */
 int mcb_build_forward_table(mcb_handle *h, int comp, int nS, int nE, const int32_t *nCoef, const float *coefs);
+/* tabulateForwardPhaseFunctions for any table: entry e is stored as Legendre moments (nAngles == NULL or nAngles[e] == 0)
+ * or as nAngles[e] angle / value pairs, interpolated linearly in the cosine of the angle (SPF:499-527; concatenated in
+ * angles / values).  hybridWidthDeg > 0: tabPhase gets the Gaussian forward peak of computeHybridPhaseFunctions
+ * (OPT:1936-2050, hunt + bisection for the transition angle per entry), tabOrigPhase the original values.          */
+int mcb_build_forward_table_general(mcb_handle *h, int comp, int nS, int nE, const int32_t *nCoef, const float *coefs,
+                                    const int32_t *nAngles, const float *angles, const float *values, float hybridWidthDeg);
 int mcb_get_forward_table(mcb_handle *h, int comp, float *T, int64_t nFloats);
 /* getInfo_Domain(tabPhase, tabOrigPhase) INT:1672-1673 <- tabulateForwardPhaseFunctions INT:282 */
 int mcb_set_forward_table(mcb_handle *h, int comp, int nS, int nE, const float *P, const float *Porig);

@@ -67,7 +67,7 @@ assert EVENT_DTYPE.itemsize == 96
 
 # every symbol include/mcbrat_cuda.h declares
 EXPORTS = ["mcb_create", "mcb_destroy", "mcb_last_error", "mcb_version", "mcb_set_stream", "mcb_synchronize",
-           "mcb_set_grid", "mcb_set_optics", "mcb_set_physical", "mcb_assemble_optics", "mcb_get_optics", "mcb_set_inverse_table", "mcb_build_inverse_table", "mcb_get_inverse_table", "mcb_build_forward_table", "mcb_get_forward_table", "mcb_set_forward_table", "mcb_set_views",
+           "mcb_set_grid", "mcb_set_optics", "mcb_set_physical", "mcb_assemble_optics", "mcb_get_optics", "mcb_set_inverse_table", "mcb_build_inverse_table", "mcb_build_inverse_table_legendre", "mcb_get_inverse_table", "mcb_build_forward_table", "mcb_build_forward_table_general", "mcb_get_forward_table", "mcb_set_forward_table", "mcb_set_views",
            "mcb_default_options", "mcb_set_options", "mcb_set_solar_source", "mcb_set_thermal_source",
            "mcb_build_thermal_source", "mcb_get_thermal_source", "mcb_frequency_distribution", "mcb_run_batch", "mcb_accumulate_batch", "mcb_stats_reset", "mcb_run_batches",
            "mcb_stats_buffer", "mcb_get_statistics", "mcb_last_batch_ms",
@@ -106,6 +106,8 @@ def load() -> C.CDLL:
     lib.mcb_build_inverse_table.argtypes = [_vp, C.c_int, C.c_int, C.c_int, _ip, _fp, _fp]
     lib.mcb_get_inverse_table.argtypes = [_vp, C.c_int, _fp, C.c_int64]
     lib.mcb_build_forward_table.argtypes = [_vp, C.c_int, C.c_int, C.c_int, _ip, _fp]
+    lib.mcb_build_inverse_table_legendre.argtypes = [_vp, C.c_int, C.c_int, C.c_int, _ip, _fp]
+    lib.mcb_build_forward_table_general.argtypes = [_vp, C.c_int, C.c_int, C.c_int, _ip, _fp, _ip, _fp, _fp, C.c_float]
     lib.mcb_get_forward_table.argtypes = [_vp, C.c_int, _fp, C.c_int64]
     lib.mcb_set_forward_table.argtypes = [_vp, C.c_int, C.c_int, C.c_int, _fp, _fp]
     lib.mcb_set_views.argtypes = [_vp, C.c_int, _fp]

@@ -23,8 +23,8 @@ void mcb_launch_fast_batch(const DevDomain &P, long long nPhotons, uint64_t seed
 void mcb_launch_philox_kat(uint64_t seed, uint64_t photon, int n, uint32_t *out, cudaStream_t stream);
 double mcb_run_gather_probe(size_t bytes, int inFlight, int blocksPerSM, int iterations, int numSMs, cudaStream_t stream);
 // mcb_stage.cu: device-side packing / validation, normalisation, emission CDF
-void mcb_launch_distance_map(const DevDomain &P, int cap, uint8_t *dist, uint8_t *scratch, int numSMs, cudaStream_t stream);
-void mcb_launch_pack_field(const DevDomain &P, int brick, float *ext, uint32_t *mask, float *layerExt, int *flags, const uint8_t *dist,
+void mcb_launch_distance_map(const DevDomain &P, int cap, uint8_t *dist, uint8_t *scratch, int *leapCount, int numSMs, cudaStream_t stream);
+void mcb_launch_pack_field(const DevDomain &P, int brick, float *ext, uint32_t *mask, float *layerExt, int *flags, const uint8_t *dist, int *leapCount,
                            int numSMs, cudaStream_t stream);
 void mcb_launch_pack_records(const DevDomain &P, uint32_t *rec, int *flags, int numSMs, cudaStream_t stream);
 bool mcb_fast_reads_bricks(const DevDomain &P);
@@ -42,6 +42,11 @@ void mcb_launch_assemble_optics(int nx, int ny, int nz, int nc, const int *kind,
                                 int numSMs, cudaStream_t stream);
 void mcb_launch_inverse_table(const int *offsets, const float *mus, const float *values, int nEntries, int nSteps, float *out,
                               float *cdfScratch, cudaStream_t stream);
+void mcb_launch_lobatto_inputs(const int *coefOff, const float *coefs, const int *nodeOff, int nEntries, long long nNodes,
+                               float *mus, float *values, int numSMs, cudaStream_t stream);
+void mcb_launch_forward_tables(const int *coefOff, const float *coefs, const int *angOff, const float *angles, const float *values,
+                               int nEntries, int nSteps, float hybridWidth, float *orig, float *fwd, float *scratch, int numSMs,
+                               cudaStream_t stream);
 void mcb_launch_forward_table(const int *offsets, const float *coefs, int nEntries, int nSteps, float *out, int numSMs,
                               cudaStream_t stream);
 void mcb_launch_frequency_distribution(const double *cdf, int nLambda, long long totalPhotons, uint64_t seed,
@@ -342,21 +347,40 @@ static int pack_field(mcb_handle *h, bool brick) {
   if (brick ? h->packedBrk : h->packedLin) return 0;
   // Vacuum-distance encoding (mcb_stage.cu): on grids the photon-pool kernels march (uniform, at least a ghost shell
   // wide, field read without the occupancy bitmap) a cell without extinction holds -D, D = its Chebyshev distance to
-  // the nearest cell with extinction; every marcher clamps at 0, the pool kernels leap (march_leap, mcb_march.cuh).
-  const bool encode = P.uniform && P.nx >= MCB_GHOST && P.ny >= MCB_GHOST && !P.lin.mask;
-  if (encode && !h->haveDist) {
+  // the nearest cell with extinction; every marcher clamps at 0, the pool kernels leap (march_leap, mcb_march.cuh) --
+  // provided a fair share of the domain lies deep enough in vacuum to pay for the leap code (P.leap): else the field
+  // stays as it is and the launchers pick the kernels without it.  Bitmap-marched fields: the same decision from the
+  // number of layers that are clear throughout (layer tables, mcb_launch_pack_field).
+#ifdef MCB_NO_LEAP
+  const bool candidate = false;
+#else
+  const bool candidate = P.uniform && P.nx >= MCB_GHOST && P.ny >= MCB_GHOST;
+#endif
+  int *leapCount = h->dFlags + 1;
+  if (candidate && !P.lin.mask && !h->haveDist) {
     const size_t cells = (size_t)P.nx * P.ny * P.nz;
     if (reserve(h, &h->dDist, cells) || reserve(h, &h->dDistScratch, cells)) return 1;
     int cap = MCB_LEAP_CAP;
     cap = cap < P.nx ? cap : P.nx; cap = cap < P.ny ? cap : P.ny;
-    mcb_launch_distance_map(P, cap, (uint8_t *)h->dDist, (uint8_t *)h->dDistScratch, h->numSMs, h->stream);
+    mcb_launch_distance_map(P, cap, (uint8_t *)h->dDist, (uint8_t *)h->dDistScratch, leapCount, h->numSMs, h->stream);
     CK(h, cudaGetLastError());
+    int deep = 0;
+    CK(h, cudaMemcpyAsync(&deep, leapCount, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    if (settle(h)) return 1;
     h->haveDist = true;
+    P.leap = (long long)deep * 32 >= (long long)cells ? 1 : 0;
   }
+  const bool encode = candidate && !P.lin.mask && P.leap;
   mcb_launch_pack_field(P, brick ? 1 : 0, (float *)(brick ? h->dExtBrick : h->dExt32),
                         (uint32_t *)(brick ? P.brk.mask : P.lin.mask), (float *)P.layerExt, h->dFlags,
-                        encode ? (const uint8_t *)h->dDist : nullptr, h->numSMs, h->stream);
+                        encode ? (const uint8_t *)h->dDist : nullptr, leapCount, h->numSMs, h->stream);
   CK(h, cudaGetLastError());
+  if (P.lin.mask) {                                   // layers clear throughout, far enough from the nearest cloudy one
+    int layers = 0;
+    CK(h, cudaMemcpyAsync(&layers, leapCount, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    if (settle(h)) return 1;
+    P.leap = candidate && layers * 16 >= P.nz ? 1 : 0;
+  }
   (brick ? h->packedBrk : h->packedLin) = true;
   return 0;
 }
@@ -384,7 +408,7 @@ static int setup_packed_field(mcb_handle *h) {
     P.layerExt = (const float *)h->dLayerExt; P.layerLeap = P.layerExt + nLayer; P.layerCum = P.layerLeap + nLayer;
   }
   h->maskKnob = knob;
-  h->packedLin = h->packedBrk = false; h->haveDist = false;
+  h->packedLin = h->packedBrk = false; h->haveDist = false; P.leap = 0;
   return pack_field(h, mcb_fast_reads_bricks(P));
 }
 
@@ -575,32 +599,88 @@ int mcb_build_inverse_table(mcb_handle *h, int comp, int nS, int nE, const int32
   return 0;
 }
 
-// tabulateForwardPhaseFunctions OPT:1872-1934 on the device for a table whose entries are stored as Legendre moments
-// (chi_1.. of entry e: nCoef[e] values, concatenated).  Fills both the table and the "original" table (no hybrid peak).
-int mcb_build_forward_table(mcb_handle *h, int comp, int nS, int nE, const int32_t *nCoef, const float *coefs) {
+// computeInversePhaseFuncTable INV:66-174 for a table whose entries are stored as Legendre moments, without any host
+// arithmetic: the Lobatto abscissas (NUM:27-114), the phase function there (SPF:480-498, NUM:187-205) and the inversion
+// all run in HBM; only the moments (chi_1.. of entry e: nCoef[e] values, concatenated) cross PCIe.
+int mcb_build_inverse_table_legendre(mcb_handle *h, int comp, int nS, int nE, const int32_t *nCoef, const float *coefs) {
+  if (!h) return 1;
+  if (!h->haveOptics) FAIL(h, "mcb_build_inverse_table_legendre: call mcb_set_optics first");
+  if (comp < 1 || comp > h->P.nc || nS < 2 || nE < 1 || !nCoef) FAIL(h, "mcb_build_inverse_table_legendre: bad arguments");
+  std::vector<int> off(2 * (nE + 1), 0);                              // coefficient offsets | node offsets
+  int *coefOff = off.data(), *nodeOff = off.data() + nE + 1;
+  for (int e = 0; e < nE; ++e) {
+    if (nCoef[e] < 0) FAIL(h, "mcb_build_inverse_table_legendre: bad arguments");
+    coefOff[e + 1] = coefOff[e] + nCoef[e];
+    nodeOff[e + 1] = nodeOff[e] + (nCoef[e] > 2 ? nCoef[e] : 2);      // INV:103: nAngles = max(nMoments, 2)
+  }
+  const size_t nC = (size_t)coefOff[nE], nN = (size_t)nodeOff[nE];
+  if (nC > 0 && !coefs) FAIL(h, "mcb_build_inverse_table_legendre: bad arguments");
+  const int c = comp - 1;
+  // scratch layout: offsets | coefficients | mus | values | cdf
+  const size_t bOff = (sizeof(int) * off.size() + 15) & ~(size_t)15, bC = (sizeof(float) * (nC ? nC : 1) + 15) & ~(size_t)15,
+               bN = sizeof(float) * nN;
+  if (reserve(h, &h->dScratch, bOff + bC + 3 * bN)) return 1;
+  char *base = (char *)h->dScratch;
+  CK(h, cudaMemcpyAsync(base, off.data(), sizeof(int) * off.size(), cudaMemcpyHostToDevice, h->stream));
+  if (nC) CK(h, cudaMemcpyAsync(base + bOff, coefs, sizeof(float) * nC, cudaMemcpyHostToDevice, h->stream));
+  float *mus = (float *)(base + bOff + bC), *values = mus + nN, *cdf = values + nN;
+  const int *dCoefOff = (const int *)base, *dNodeOff = dCoefOff + nE + 1;
+  mcb_launch_lobatto_inputs(dCoefOff, (const float *)(base + bOff), dNodeOff, nE, (long long)nN, mus, values, h->numSMs, h->stream);
+  if (reserve(h, &h->dInv[c], sizeof(float) * (size_t)nS * nE)) return 1;
+  mcb_launch_inverse_table(dNodeOff, mus, values, nE, nS, (float *)h->dInv[c], cdf, h->stream);
+  CK(h, cudaGetLastError());
+  if (settle(h)) return 1;
+  h->P.inv[c] = (const float *)h->dInv[c]; h->P.invS[c] = nS; h->invE[c] = nE; h->P.invE[c] = nE; h->haveInv[c] = true;
+  return 0;
+}
+
+// tabulateForwardPhaseFunctions OPT:1872-1934 on the device.  Entry e is stored as Legendre moments (nAngles == NULL or
+// nAngles[e] == 0: chi_1.. = nCoef[e] values of coefs) or as nAngles[e] angle / value pairs (SPF:499-527); entries are
+// concatenated in coefs, and in angles / values.  hybridWidthDeg > 0 builds the table with the Gaussian forward peak
+// (computeHybridPhaseFunctions OPT:1936-2050) next to the original one; otherwise the two are the same.
+int mcb_build_forward_table_general(mcb_handle *h, int comp, int nS, int nE, const int32_t *nCoef, const float *coefs,
+                                    const int32_t *nAngles, const float *angles, const float *values, float hybridWidthDeg) {
   if (!h) return 1;
   if (!h->haveOptics) FAIL(h, "mcb_build_forward_table: call mcb_set_optics first");
   if (comp < 1 || comp > h->P.nc || nS < 2 || nE < 1 || !nCoef) FAIL(h, "mcb_build_forward_table: bad arguments");
-  std::vector<int> off(nE + 1, 0);
-  for (int e = 0; e < nE; ++e) { if (nCoef[e] < 0) FAIL(h, "mcb_build_forward_table: bad arguments"); off[e + 1] = off[e] + nCoef[e]; }
-  const size_t total = (size_t)off[nE];
-  if (total > 0 && !coefs) FAIL(h, "mcb_build_forward_table: bad arguments");
+  std::vector<int> off(2 * (nE + 1), 0);                              // coefficient offsets | angle offsets
+  int *coefOff = off.data(), *angOff = off.data() + nE + 1;
+  for (int e = 0; e < nE; ++e) {
+    const int na = nAngles ? nAngles[e] : 0;
+    if (nCoef[e] < 0 || na < 0 || na == 1 || (na > 0 && nCoef[e] > 0)) FAIL(h, "mcb_build_forward_table: bad arguments");
+    coefOff[e + 1] = coefOff[e] + nCoef[e];
+    angOff[e + 1] = angOff[e] + na;
+  }
+  const size_t nC = (size_t)coefOff[nE], nA = (size_t)angOff[nE];
+  if ((nC > 0 && !coefs) || (nA > 0 && (!angles || !values))) FAIL(h, "mcb_build_forward_table: bad arguments");
   const int c = comp - 1;
-  const size_t bOff = (sizeof(int) * (nE + 1) + 15) & ~(size_t)15;
-  if (reserve(h, &h->dScratch, bOff + sizeof(float) * (total ? total : 1))) return 1;
+  // scratch layout: offsets | coefficients | angles | values | 2 nS floats (hybrid: cosines, Gaussian)
+  const size_t bOff = (sizeof(int) * off.size() + 15) & ~(size_t)15, bC = (sizeof(float) * (nC ? nC : 1) + 15) & ~(size_t)15,
+               bA = (sizeof(float) * (nA ? nA : 1) + 15) & ~(size_t)15;
+  if (reserve(h, &h->dScratch, bOff + bC + 2 * bA + sizeof(float) * 2 * (size_t)nS)) return 1;
   char *base = (char *)h->dScratch;
-  CK(h, cudaMemcpyAsync(base, off.data(), sizeof(int) * (nE + 1), cudaMemcpyHostToDevice, h->stream));
-  if (total) CK(h, cudaMemcpyAsync(base + bOff, coefs, sizeof(float) * total, cudaMemcpyHostToDevice, h->stream));
+  CK(h, cudaMemcpyAsync(base, off.data(), sizeof(int) * off.size(), cudaMemcpyHostToDevice, h->stream));
+  if (nC) CK(h, cudaMemcpyAsync(base + bOff, coefs, sizeof(float) * nC, cudaMemcpyHostToDevice, h->stream));
+  if (nA) {
+    CK(h, cudaMemcpyAsync(base + bOff + bC, angles, sizeof(float) * nA, cudaMemcpyHostToDevice, h->stream));
+    CK(h, cudaMemcpyAsync(base + bOff + bC + bA, values, sizeof(float) * nA, cudaMemcpyHostToDevice, h->stream));
+  }
   if (reserve(h, &h->dFwd[c], sizeof(float) * (size_t)nS * nE)) return 1;
   if (reserve(h, &h->dFwdOrig[c], sizeof(float) * (size_t)nS * nE)) return 1;
-  mcb_launch_forward_table((const int *)base, (const float *)(base + bOff), nE, nS, (float *)h->dFwd[c], h->numSMs, h->stream);
+  mcb_launch_forward_tables((const int *)base, (const float *)(base + bOff), (const int *)base + nE + 1,
+                            (const float *)(base + bOff + bC), (const float *)(base + bOff + bC + bA), nE, nS, hybridWidthDeg,
+                            (float *)h->dFwdOrig[c], (float *)h->dFwd[c], (float *)(base + bOff + bC + 2 * bA), h->numSMs, h->stream);
   CK(h, cudaGetLastError());
-  CK(h, cudaMemcpyAsync(h->dFwdOrig[c], h->dFwd[c], sizeof(float) * (size_t)nS * nE, cudaMemcpyDeviceToDevice, h->stream));
   if (settle(h)) return 1;
   h->P.fwd[c] = (const float *)h->dFwd[c]; h->P.fwdOrig[c] = (const float *)h->dFwdOrig[c];
   h->P.fwdS[c] = nS; h->fwdE[c] = nE; h->P.fwdE[c] = nE; h->haveFwd[c] = true;
   h->P.fwdInvDTheta[c] = (float)(nS - 1) / 3.14159265358979312f;
   return 0;
+}
+
+// the Legendre-only form of round 1 (same tables, no hybrid peak)
+int mcb_build_forward_table(mcb_handle *h, int comp, int nS, int nE, const int32_t *nCoef, const float *coefs) {
+  return mcb_build_forward_table_general(h, comp, nS, nE, nCoef, coefs, nullptr, nullptr, nullptr, 0.0f);
 }
 
 int mcb_get_forward_table(mcb_handle *h, int comp, float *T, int64_t nFloats) {
@@ -1194,7 +1274,7 @@ int mcb_debug_gather_probe(mcb_handle *h, int64_t bytes, int loadsInFlight, int 
 int mcb_debug_distance_map(mcb_handle *h, uint8_t *out, int64_t nBytes) {
   if (!h || !out) return 1;
   if (!h->haveGrid || !h->haveOptics) FAIL(h, "mcb_debug_distance_map: problem not completely specified.");
-  if (!h->haveDist) FAIL(h, "mcb_debug_distance_map: this grid is not marched with vacuum leaps");
+  if (!h->haveDist) FAIL(h, "mcb_debug_distance_map: this grid has no vacuum-distance map (narrow, irregular or bitmap-marched)");
   const int64_t cells = (int64_t)h->P.nx * h->P.ny * h->P.nz;
   if (nBytes < cells) FAIL(h, "mcb_debug_distance_map: buffer too small (%lld needed)", (long long)cells);
   CK(h, cudaSetDevice(h->device));

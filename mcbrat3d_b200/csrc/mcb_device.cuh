@@ -14,7 +14,10 @@
 #define MCB_MAX_DIR 32          // view directions kept in the parameter block
 #define MCB_GHOST 8             // ghost cells on every side of the packed extinction field = longest marching burst
 #define MCB_LEAP_MIN 3          // smallest vacuum distance the pool kernels leap from (mcb_options.tuneLeap overrides)
-#define MCB_LEAP_LANES 8        // lanes of a warp that must want a leap for the warp to run the leap code (tuneLeapLanes)
+#define MCB_LEAP_LANES 1        // lanes of a warp that must want a leap for the warp to run the leap code (tuneLeapLanes).
+                                // 8 measured 1 % faster on C3, but then a photon's leaps -- and with them the last bits of its
+                                // positions -- depend on which other photons share its warp: results would no longer be
+                                // independent of the batch split and of the number of GPUs (tests: ..._independent_of_batch_split)
 #define MCB_LEAP_CAP 64         // largest vacuum distance (cells) encoded in the packed field = longest leap of the pool kernels
 
 struct DevDomain {
@@ -59,6 +62,8 @@ struct DevDomain {
   } lin, brk;
   const float *layerExt;                      // nz + 2G (+2) clear-sky values; sign bit set: the WHOLE layer has this value
                                               // (no bitmap look-up needed there)
+  int leap;                                   // the packed fields carry the vacuum distances / the layer tables below are
+                                              // worth leaping with: the pool kernels run their LEAP variants
   const float *layerLeap;                     // nz + 2G (+2): minus the distance, in layers, to the nearest layer that is not
                                               // clear throughout (0 for such a layer): march_leap crosses that many at once
   const float *layerCum;                      // nz + 1: clear-sky optical depth per unit |1/mu| from the surface to each edge
@@ -97,6 +102,7 @@ struct DevDomain {
 // against its array and violations are counted in counters[CNT_BAD] (the access is clamped, not made).  The pool
 // has no compute-sanitizer, so tests/test_gpu_bounds.py runs the cases through this build and asserts zero.
 #ifdef MCB_BOUNDS_CHECK
+#define MCB_LEAP_STATS
 #define MCB_CHECK_INDEX(P, i, n) mcb_checked_index((P), (long long)(i), (long long)(n))
 __device__ __forceinline__ long long mcb_checked_index(const struct DevDomain &P, long long i, long long n);
 #else

@@ -197,7 +197,8 @@ enum { MARCH_ON = ST_MARCH, MARCH_HIT = ST_SCATTER, MARCH_BOTTOM = ST_SURFACE, M
 // Chebyshev distance in cells to the nearest cell that has some, so every gathered value is clamped at 0 before it is
 // used.  vlast (photon-pool kernels): where the burst ends with MARCH_ON it receives a lower bound of -D for the cell
 // the ray is in now (the last gathered value + 1: D changes by at most 1 between neighbours) -- march_leap's input.
-template <bool REG, bool WIDE, int B, bool MASK, bool BRICK, bool RAW = false, bool SPLIT = false>
+// ENC = false (pool kernels on a domain that was staged without the encoding, DevDomain::leap == 0): no clamp.
+template <bool REG, bool WIDE, int B, bool MASK, bool BRICK, bool RAW = false, bool SPLIT = false, bool ENC = true>
 __device__ __forceinline__ int march_burst(Ray &r, const DevDomain &P, const Grid &G,
                                            float &ext, float target, unsigned &crossings, float *vlast = nullptr) {
   const DevDomain::ExtField &F = BRICK ? P.brk : P.lin;
@@ -279,7 +280,11 @@ __device__ __forceinline__ int march_burst(Ray &r, const DevDomain &P, const Gri
         }
       }
     }
-    const float sk = MASK ? sg[k] : fmaxf(sg[k], 0.0f);       // vacuum cells hold -D
+#ifdef MCB_NO_LEAP                                            // A/B build without vacuum leaps (make variant FLAGS=-DMCB_NO_LEAP)
+    const float sk = sg[k];
+#else
+    const float sk = (MASK || !ENC) ? sg[k] : fmaxf(sg[k], 0.0f);       // vacuum cells hold -D
+#endif
     const float en = fmaf(tE[k] - tS, sk, acc);
     const bool h = !found && en > target;
     hS = h ? sk : hS; hC = h ? ck[k] : hC; hK = h ? k : hK;
@@ -343,6 +348,9 @@ __device__ __forceinline__ int march_burst(Ray &r, const DevDomain &P, const Gri
 // divergent code and the extra dependent round trip per iteration cost what the saved bursts had bought.)
 // how far the ray may leap from its cell (0: march): v = what is known about the cell (march_burst's vlast)
 __device__ __forceinline__ int leap_distance(const Ray &r, const DevDomain &P, float v, float leapBelow) {
+#ifdef MCB_NO_LEAP
+  return 0;
+#endif
   if (!(v <= leapBelow)) return 0;
   const int D = min((int)(-v), r.dz >= 0.0f ? P.nz - r.iz : r.iz + 1);
   return D >= 2 ? D : 0;
@@ -351,9 +359,10 @@ __device__ __forceinline__ int leap_distance(const Ray &r, const DevDomain &P, f
 // MASK (fields read through the occupancy bitmap, whose clear sky is not vacuum): D counts layers that are clear
 // throughout (layerLeap), the optical depth of the leap is that of the horizontally uniform clear sky (layerExt,
 // layerCum) -- and if the target falls inside it the leap is not taken (the burst that follows finds the event).
+// stat: two shared-memory counters (leaps taken, cells they crossed), added to once per warp (MCB_LEAP_STATS builds).
 template <bool MASK>
 __device__ __forceinline__ int march_leap(Ray &r, const DevDomain &P, const int D, unsigned &crossings,
-                                          float &ext, const float target) {
+                                          float &ext, const float target, unsigned *stat) {
   const float k = (float)(D - 1);
   const float ax = fabsf(r.rx) * P.fhx, ay = fabsf(r.ry) * P.fhy, az = fabsf(r.rz) * P.fhz;   // path between two faces (inf: axis not moving)
   const float ex = fmaf(k, ax, r.tx), ey = fmaf(k, ay, r.ty), ez = fmaf(k, az, r.tz);          // where the cube ends
@@ -381,6 +390,13 @@ __device__ __forceinline__ int march_leap(Ray &r, const DevDomain &P, const int 
   if (ny) { r.ty = fmaf((float)ny, ay, r.ty); r.iy += r.dy >= 0.0f ? ny : -ny; }
   if (nz) { r.tz = fmaf((float)nz, az, r.tz); r.iz += r.dz >= 0.0f ? nz : -nz; }
   crossings += (unsigned)(nx + ny + nz);
+#ifdef MCB_LEAP_STATS                                          // counters leaps / leapCells: the bounds-checked build only (the
+  {                                                           // reduction costs the 72-register flux kernel 9 % on C3, r02)
+    const unsigned lanes = __activemask();
+    const unsigned cells = __reduce_add_sync(lanes, (unsigned)(nx + ny + nz));
+    if ((threadIdx.x & 31) == __ffs(lanes) - 1) { atomicAdd(&stat[0], (unsigned)__popc(lanes)); atomicAdd(&stat[1], cells); }
+  }
+#endif
   if ((unsigned)r.iz >= (unsigned)P.nz) {                    // landed on the boundary: the leg ends there
     const bool top = r.iz > 0;
     r.t = ((top ? P.fzMax : P.fz0) - r.oz) * r.rz;

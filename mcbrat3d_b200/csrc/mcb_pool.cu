@@ -43,7 +43,7 @@ using namespace mcbfast;
 enum { PW_PX = 0, PW_PY, PW_PZ, PW_DX, PW_DY, PW_DZ, PW_W, PW_TAU, PW_UNEXT, PW_C0, PW_C1, PW_BLK, PW_IXY, PW_IZK,
        PW_TX, PW_TY, PW_TZ };
 
-template <int THREADS, int MINBLOCKS, int BURST, bool SPLIT, bool MASK, bool BRICK>
+template <int THREADS, int MINBLOCKS, int BURST, bool SPLIT, bool MASK, bool BRICK, bool LEAP>
 __global__ void __launch_bounds__(THREADS, MINBLOCKS)
 pool_kernel(const __grid_constant__ DevDomain P, long long nPhotons, uint64_t seed, uint64_t firstPhotonId,
             unsigned long long *workCounter, const SmemPlan plan, const float leapBelow, const int leapLanes) {
@@ -314,16 +314,13 @@ pool_kernel(const __grid_constant__ DevDomain P, long long nPhotons, uint64_t se
     // =========================== march: one burst for every lane ===========================
     // (a lane whose cell is known to lie deep enough in vacuum crosses that in one leap first: march_leap)
     int ev = MARCH_ON;
-    int D = have ? leap_distance(r, P, vcur, leapBelow) : 0;
-    if (leapLanes > 1 && __popc(__ballot_sync(FULL, D > 0)) < leapLanes) D = 0;     // too few lanes to pay for the divergence
-    if (D) {                                                // (implies have)
-      const unsigned before = crossings, lanes = __activemask();
-      ev = march_leap<MASK>(r, P, D, crossings, ext, tau);
-      const unsigned cells = __reduce_add_sync(lanes, crossings - before);      // counters leaps / leapCells: one lane adds
-      const unsigned took = __ballot_sync(lanes, crossings != before);           // (a leap the target falls into is not taken)
-      if (lane == __ffs(lanes) - 1) { atomicAdd(&sCnt[4], (unsigned)__popc(took)); atomicAdd(&sCnt[5], cells); }
+    if (LEAP) {
+      int D = have ? leap_distance(r, P, vcur, leapBelow) : 0;
+      if (leapLanes > 1 && __popc(__ballot_sync(FULL, D > 0)) < leapLanes) D = 0;   // too few lanes to pay for the divergence
+      if (D) ev = march_leap<MASK>(r, P, D, crossings, ext, tau, &sCnt[4]);         // (implies have)
     }
-    if (have && ev == MARCH_ON) ev = march_burst<true, true, BURST, MASK, BRICK, true, SPLIT>(r, P, G, ext, tau, crossings, &vcur);
+    if (have && ev == MARCH_ON)
+      ev = march_burst<true, true, BURST, MASK, BRICK, true, SPLIT, LEAP>(r, P, G, ext, tau, crossings, LEAP ? &vcur : nullptr);
 
     // =========================== photons that reached an event go onto EVENT ===========================
     {
@@ -384,11 +381,11 @@ pool_kernel(const __grid_constant__ DevDomain P, long long nPhotons, uint64_t se
 
 }  // namespace mcbpool
 
-template <int MINBLOCKS, int BURST, bool SPLIT, bool MASK, bool BRICK>
+template <int MINBLOCKS, int BURST, bool SPLIT, bool MASK, bool BRICK, bool LEAP>
 static void launch_pool(const DevDomain &P, long long nPhotons, uint64_t seed, uint64_t firstPhotonId, int numSMs,
                         unsigned long long *workCounter, cudaStream_t stream) {
   constexpr int THREADS = 128;
-  auto kernel = mcbpool::pool_kernel<THREADS, MINBLOCKS, BURST, SPLIT, MASK, BRICK>;
+  auto kernel = mcbpool::pool_kernel<THREADS, MINBLOCKS, BURST, SPLIT, MASK, BRICK, LEAP>;
   const int cols = P.nx * P.ny, cells = cols * P.nz;
   mcbfast::SmemPlan plan{-1, -1, -1, -1, -1, 0, 0, 0};
   int off = 0;
@@ -437,7 +434,11 @@ void mcb_launch_pool_batch(const DevDomain &P, long long nPhotons, uint64_t seed
   // register budget: 8 CTAs/SM = 64 registers (spills), 7 = 72, 6 = 80.  Measured (one B200, r02, photons/s): C3 with split
   // gathers 6: 7.27e8, 7: 7.48e8, 8: 6.0e8; C5 (bitmap, eight gathers up front) 6: 4.41e8, 7: 4.03e8
   const int occ = P.opt.tuneBlocksPerSM ? P.opt.tuneBlocksPerSM : (mask ? 6 : 7);
-#define MCB_POOL_GO(OCC, B, SPLIT, MASK, BRICK) launch_pool<OCC, B, SPLIT, MASK, BRICK>(P, nPhotons, seed, firstPhotonId, numSMs, workCounter, stream)
+  // LEAP variants (vacuum / clear-layer leaps, clamped gathers) only where the staging found space worth leaping (P.leap):
+  // on a scene without any (C3 with a Rayleigh background) the machinery alone costs 7 % (r02: 7.40e8 -> 6.88e8)
+#define MCB_POOL_GO(OCC, B, SPLIT, MASK, BRICK) \
+  do { if (P.leap) launch_pool<OCC, B, SPLIT, MASK, BRICK, true>(P, nPhotons, seed, firstPhotonId, numSMs, workCounter, stream); \
+       else launch_pool<OCC, B, SPLIT, MASK, BRICK, false>(P, nPhotons, seed, firstPhotonId, numSMs, workCounter, stream); } while (0)
 #define MCB_POOL_LAYOUT(OCC, B, SPLIT) \
   do { if (mask) { if (brick) MCB_POOL_GO(OCC, B, SPLIT, true, true); else MCB_POOL_GO(OCC, B, SPLIT, true, false); } \
        else { if (brick) MCB_POOL_GO(OCC, B, SPLIT, false, true); else MCB_POOL_GO(OCC, B, SPLIT, false, false); } } while (0)

@@ -66,7 +66,7 @@ __device__ __forceinline__ float view_phase_value(const DevDomain &P, int compon
   return val * P.viewNorm[dir];                                                        // INT:1726
 }
 
-template <int THREADS, int MINBLOCKS, int BURST, bool MASK, bool BRICK>
+template <int THREADS, int MINBLOCKS, int BURST, bool MASK, bool BRICK, bool LEAP>
 __global__ void __launch_bounds__(THREADS, MINBLOCKS)
 pool_le_kernel(const __grid_constant__ DevDomain P, long long nPhotons, uint64_t seed, uint64_t firstPhotonId,
                unsigned long long *workCounter, const SmemPlan plan, const float leapBelow, const int leapLanes) {
@@ -427,16 +427,13 @@ pool_le_kernel(const __grid_constant__ DevDomain P, long long nPhotons, uint64_t
     // =========================== march: one burst for every lane ===========================
     int ev = MARCH_ON;
     unsigned crossed = 0u;
-    int D = job != JOB_NONE ? leap_distance(r, P, vcur, leapBelow) : 0;
-    if (leapLanes > 1 && __popc(__ballot_sync(FULL, D > 0)) < leapLanes) D = 0;     // too few lanes to pay for the divergence
-    if (D) {                                                   // first through vacuum in one leap where the cell is known to lie
-      const unsigned lanes = __activemask();
-      ev = march_leap<MASK>(r, P, D, crossed, ext, tgt);       // deep in it (implies a job)
-      const unsigned cells = __reduce_add_sync(lanes, crossed);                  // counters leaps / leapCells: one lane adds
-      const unsigned took = __ballot_sync(lanes, crossed != 0u);                 // (a leap the target falls into is not taken)
-      if (lane == __ffs(lanes) - 1) { atomicAdd(&sCnt[4], (unsigned)__popc(took)); atomicAdd(&sCnt[5], cells); }
+    if (LEAP) {                                                // first through vacuum in one leap where the cell is known to lie
+      int D = job != JOB_NONE ? leap_distance(r, P, vcur, leapBelow) : 0;            // deep in it
+      if (leapLanes > 1 && __popc(__ballot_sync(FULL, D > 0)) < leapLanes) D = 0;   // too few lanes to pay for the divergence
+      if (D) ev = march_leap<MASK>(r, P, D, crossed, ext, tgt, &sCnt[4]);
     }
-    if (job != JOB_NONE && ev == MARCH_ON) ev = march_burst<true, true, BURST, MASK, BRICK, true, false>(r, P, G, ext, tgt, crossed, &vcur);
+    if (job != JOB_NONE && ev == MARCH_ON)
+      ev = march_burst<true, true, BURST, MASK, BRICK, true, false, LEAP>(r, P, G, ext, tgt, crossed, LEAP ? &vcur : nullptr);
     if (job == JOB_PHOTON) crossings += crossed; else leCrossings += crossed;
 
     // =========================== rays that ended ===========================
@@ -544,11 +541,11 @@ pool_le_kernel(const __grid_constant__ DevDomain P, long long nPhotons, uint64_t
 
 }  // namespace mcbpoolle
 
-template <int MINBLOCKS, bool MASK, bool BRICK>
+template <int MINBLOCKS, bool MASK, bool BRICK, bool LEAP>
 static void launch_pool_le(const DevDomain &P, long long nPhotons, uint64_t seed, uint64_t firstPhotonId, int numSMs,
                            unsigned long long *workCounter, cudaStream_t stream) {
   constexpr int THREADS = 128;
-  auto kernel = mcbpoolle::pool_le_kernel<THREADS, MINBLOCKS, 8, MASK, BRICK>;
+  auto kernel = mcbpoolle::pool_le_kernel<THREADS, MINBLOCKS, 8, MASK, BRICK, LEAP>;
   const int cols = P.nx * P.ny, cells = cols * P.nz;
   mcbfast::SmemPlan plan{-1, -1, -1, -1, -1, 0, 0, 0};
   int off = 0;
@@ -587,11 +584,13 @@ void mcb_launch_pool_le_batch(const DevDomain &P, long long nPhotons, uint64_t s
   if (nPhotons <= 0) return;
   const bool mask = P.lin.mask != nullptr, brick = mcb_pool_le_reads_bricks(P);
   const int occ = P.opt.tuneBlocksPerSM ? P.opt.tuneBlocksPerSM : 5;
-#define MCB_PLE_GO(OCC) \
-  do { if (mask) { if (brick) launch_pool_le<OCC, true, true>(P, nPhotons, seed, firstPhotonId, numSMs, workCounter, stream); \
-                   else launch_pool_le<OCC, true, false>(P, nPhotons, seed, firstPhotonId, numSMs, workCounter, stream); } \
-       else { if (brick) launch_pool_le<OCC, false, true>(P, nPhotons, seed, firstPhotonId, numSMs, workCounter, stream); \
-              else launch_pool_le<OCC, false, false>(P, nPhotons, seed, firstPhotonId, numSMs, workCounter, stream); } } while (0)
+#define MCB_PLE_ARGS (P, nPhotons, seed, firstPhotonId, numSMs, workCounter, stream)
+#define MCB_PLE_GO2(OCC, LEAP) \
+  do { if (mask) { if (brick) launch_pool_le<OCC, true, true, LEAP> MCB_PLE_ARGS; else launch_pool_le<OCC, true, false, LEAP> MCB_PLE_ARGS; } \
+       else { if (brick) launch_pool_le<OCC, false, true, LEAP> MCB_PLE_ARGS; else launch_pool_le<OCC, false, false, LEAP> MCB_PLE_ARGS; } } while (0)
+#define MCB_PLE_GO(OCC) do { if (P.leap) MCB_PLE_GO2(OCC, true); else MCB_PLE_GO2(OCC, false); } while (0)
   if (occ >= 6) MCB_PLE_GO(6); else if (occ == 5) MCB_PLE_GO(5); else MCB_PLE_GO(4);
 #undef MCB_PLE_GO
+#undef MCB_PLE_GO2
+#undef MCB_PLE_ARGS
 }

@@ -86,7 +86,7 @@ __global__ void layer_min_kernel(const double *__restrict__ totalExt, int cols, 
 // layers, to the nearest layer that is not clear throughout (0 for such a layer and in the ghost layers; cap if there
 // is none within cap), and the clear-sky optical depth per unit |1/mu| from the surface up to every layer edge.
 __global__ void layer_tables_kernel(const float *__restrict__ layerExt, int nz, int G, int cap, float hz,
-                                    float *__restrict__ layerLeap, float *__restrict__ layerCum) {
+                                    float *__restrict__ layerLeap, float *__restrict__ layerCum, int thr, int *count) {
   for (int l = threadIdx.x; l < nz + 2 * G + 2; l += blockDim.x) {
     const int k = l - G;
     int d = 0;
@@ -98,6 +98,7 @@ __global__ void layer_tables_kernel(const float *__restrict__ layerExt, int nz, 
       }
     }
     layerLeap[l] = -(float)d;                                  // the form march_leap's callers keep it in
+    if (d >= thr) atomicAdd(count, 1);                         // layers worth leaping from
   }
   if (threadIdx.x == 0) {
     double c = 0.0;
@@ -155,7 +156,10 @@ __global__ void dist_y_kernel(const uint8_t *__restrict__ in, int nx, int ny, lo
     out[p] = (uint8_t)best;
   }
 }
-__global__ void dist_z_kernel(const uint8_t *__restrict__ in, long long cols, int nz, long long cells, uint8_t *__restrict__ out) {
+// (*count += the cells that lie at least thr deep in vacuum: the launcher leaps only where that is a fair share of the domain)
+__global__ void dist_z_kernel(const uint8_t *__restrict__ in, long long cols, int nz, long long cells, uint8_t *__restrict__ out,
+                              int thr, int *count) {
+  int mine = 0;
   for (long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x; p < cells; p += (long long)gridDim.x * blockDim.x) {
     const int k = (int)(p / cols);
     int best = in[p];
@@ -164,7 +168,10 @@ __global__ void dist_z_kernel(const uint8_t *__restrict__ in, long long cols, in
       best = min(best, max(s, m));
     }
     out[p] = (uint8_t)best;
+    mine += best >= thr ? 1 : 0;
   }
+  for (int o = 16; o > 0; o >>= 1) mine += __shfl_down_sync(0xffffffffu, mine, o);
+  if ((threadIdx.x & 31) == 0 && mine) atomicAdd(count, mine);
 }
 
 __global__ void pack_components_kernel(const double *__restrict__ cumExt, const double *__restrict__ ssa,
@@ -512,6 +519,184 @@ __global__ void forward_table_kernel(const int *__restrict__ offsets, const floa
 }
 
 // ---------------------------------------------------------------------------------------------
+// The rest of the table producers, each bit-identical to its restatement in the test suite's C code:
+//   * lobatto_inputs_kernel: what computeInversePhaseFunction inverts for a Legendre-stored phase function (INV:97-112)
+//     -- the max(nMoments, 2) Lobatto abscissas (computeLobattoTerms NUM:27-114: Newton's method on the zeros of
+//     P'_{n-1}, one thread per node; a node's iterates do not depend on the other nodes, only the weights -- which the
+//     inversion never uses -- do) and the phase function there (SPF:480-498 at cos(acos(mu)), NUM:187-205);
+//   * forward_values_kernel: tabulateForwardPhaseFunctions' values on equal angle steps for either storage kind
+//     (Legendre moments, or angle / value pairs interpolated in the cosine of the angle, SPF:499-527);
+//   * hybrid_*_kernel: computeHybridPhaseFunctions OPT:1936-2050, one block per table entry (the hunt and the bisection
+//     for the transition angle are sequential, each probe two dot products accumulated in order).
+// ---------------------------------------------------------------------------------------------
+__device__ float legendre_series(int nCoef, const float *__restrict__ chi, float mu) {          // SPF:480-498
+  if (nCoef == 0) return 0.5f;                                                                   // SPF:486-491 (quirk q14)
+  float pm1 = 1.0f, pl = mu;
+  float value = 0.0f + (1.0f * 1.0f) * pm1;
+  value = value + (chi[0] * 3.0f) * pl;
+  for (int l = 1; l < nCoef; ++l) {
+    const float pn = (((float)(2 * l + 1) * mu) * pl - (float)l * pm1) / (float)(l + 1);
+    pm1 = pl; pl = pn;
+    value = value + (chi[l] * (float)(2 * (l + 1) + 1)) * pl;
+  }
+  return value;
+}
+
+// P_{n-1}, P_{n-2} at mu by the upward recursion of NUM:187-205 (n >= 2)
+__device__ __forceinline__ void legendre_last_two(int nTerms, float mu, float &pLast, float &pPrev) {
+  float pm1 = 1.0f, pl = mu;                                    // P_0, P_1
+  for (int l = 1; l <= nTerms - 2; ++l) {
+    const float pn = (((float)(2 * l + 1) * mu) * pl - (float)l * pm1) / (float)(l + 1);
+    pm1 = pl; pl = pn;
+  }
+  if (nTerms - 1 == 0) { pLast = 1.0f; pPrev = 0.0f; } else { pLast = pl; pPrev = pm1; }
+}
+
+// the k-th (0-based) positive trial abscissa of n-point Lobatto quadrature after Newton's method, NUM:44-88
+__device__ float lobatto_trial(int nTerms, int k) {
+  const float pi = (float)acos((double)-1.0f);
+  const float c1 = (nTerms % 2 == 1) ? 1.0f : 0.5f;
+  float trial = (float)sin((double)(pi * ((float)(k + 1) - c1) / ((float)nTerms - 1.0f + 0.5f)));
+  float last, d1, d2, pLast, pPrev;
+  legendre_last_two(nTerms, trial, pLast, pPrev);
+  d1 = (float)(nTerms - 1) * (trial * pLast - pPrev) / (trial * trial - 1.0f);
+  d2 = (2.0f * trial * d1 - ((float)(nTerms * (nTerms - 1)) * pLast)) / (1.0f - trial * trial);
+  last = trial;
+  trial = trial - d1 / d2;
+  int i = 0;
+  for (;;) {
+    if (!(fabsf(trial - last) > 3.0f * sp32(trial))) break;
+    legendre_last_two(nTerms, trial, pLast, pPrev);
+    d1 = (float)(nTerms - 1) * (trial * pLast - pPrev) / (trial * trial - 1.0f);
+    d2 = (2.0f * trial * d1 - ((float)(nTerms * (nTerms - 1)) * pLast)) / (1.0f - trial * trial);
+    last = trial;
+    trial = trial - d1 / d2;
+    i = i + 1;
+    if (i > 25) break;
+  }
+  return trial;
+}
+
+__global__ void lobatto_inputs_kernel(const int *__restrict__ coefOff, const float *__restrict__ coefAll,
+                                      const int *__restrict__ nodeOff, int nE, float *__restrict__ musAll,
+                                      float *__restrict__ valuesAll) {
+  const long long total = nodeOff[nE];
+  for (long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x; p < total; p += (long long)gridDim.x * blockDim.x) {
+    int e = 0;
+    while (nodeOff[e + 1] <= p) ++e;                            // tables have a handful of entries
+    const int n = nodeOff[e + 1] - nodeOff[e], j = (int)(p - nodeOff[e]);
+    const int mid = (n + 1) / 2;
+    // NUM:91-110: mus(1) = -1, mus(mid:2:-1) = -trial(:), then the upper half mirrored from the lower one
+    const bool even = (n % 2) == 0;
+    const bool mirrored = even ? j >= mid : j >= mid - 1;
+    const int jj = mirrored ? (even ? 2 * mid - 1 - j : 2 * (mid - 1) - j) : j;
+    float mu = jj == 0 ? -1.0f : -lobatto_trial(n, mid - 1 - jj);
+    if (mirrored) mu = -mu;
+    const int nCoef = coefOff[e + 1] - coefOff[e];
+    const float angle = (float)acos((double)mu);                // INV:108: acos(mus(nAngles:1:-1)), values reversed back
+    musAll[p] = mu;
+    valuesAll[p] = legendre_series(nCoef, coefAll + coefOff[e], (float)cos((double)angle));
+  }
+}
+
+// entry e: Legendre-stored when angOff[e+1] == angOff[e] (coefficients coefAll[coefOff[e]..)), else angle / value pairs
+__global__ void forward_values_kernel(const int *__restrict__ coefOff, const float *__restrict__ coefAll,
+                                      const int *__restrict__ angOff, const float *__restrict__ angAll,
+                                      const float *__restrict__ valAll, int nE, int nS, float *__restrict__ out) {
+  const long long total = (long long)nE * nS;
+  for (long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x; p < total; p += (long long)gridDim.x * blockDim.x) {
+    const int e = (int)(p / nS), i = (int)(p - (long long)e * nS);
+    const float angle = (float)i / (float)(nS - 1) * 3.14159265358979312f;          // OPT:1912-1913
+    const int nStored = angOff[e + 1] - angOff[e];
+    float value;
+    if (nStored == 0) {
+      value = legendre_series(coefOff[e + 1] - coefOff[e], coefAll + coefOff[e], (float)cos((double)angle));
+    } else {                                                                        // SPF:499-527
+      const float *sa = angAll + angOff[e], *sv = valAll + angOff[e];
+      int idx = find_index_real(angle, sa, nStored, 0);
+      idx = idx < 1 ? 1 : (idx > nStored ? nStored : idx);
+      int ip1 = idx + 1;
+      float dMu;
+      if (idx < nStored) dMu = (float)cos((double)sa[ip1 - 1]) - (float)cos((double)sa[idx - 1]);
+      else { dMu = FLT_MAX; ip1 = idx; }
+      const float w = 1.0f - ((float)cos((double)angle) - (float)cos((double)sa[idx - 1])) / dMu;
+      value = w * sv[idx - 1] + (1.0f - w) * sv[ip1 - 1];
+    }
+    out[p] = value;
+  }
+}
+
+// angleCosines | gaussianValues of the nS equally spaced angles (OPT:1952-1958)
+__global__ void hybrid_prepare_kernel(int nS, float width, float *__restrict__ angleCosines, float *__restrict__ gaussianValues) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nS; i += gridDim.x * blockDim.x) {
+    const float angle = (float)i / (float)(nS - 1) * 3.14159265358979312f;
+    angleCosines[i] = (float)cos((double)angle);
+    const float q = angle / width;
+    gaussianValues[i] = (float)exp((double)(-(q * q)));
+  }
+}
+
+__device__ float hybrid_normalization(int nAngles, const float *__restrict__ ac, const float *__restrict__ values,
+                                      const float *__restrict__ gv, int t) {                    // OPT:2027-2050
+  float integralGaus = 0.0f, integralOrig = 0.0f;
+  for (int j = 1; j <= t - 1; ++j) integralGaus = integralGaus + (0.5f * (gv[j - 1] + gv[j])) * (ac[j - 1] - ac[j]);
+  for (int j = t; j <= nAngles - 1; ++j) integralOrig = integralOrig + (0.5f * (values[j - 1] + values[j])) * (ac[j - 1] - ac[j]);
+  if (integralOrig >= 2.0f) return 1.0f / integralGaus;
+  return (2.0f - integralOrig) / integralGaus;
+}
+__device__ float hybrid_diff(int nAngles, const float *ac, const float *values, const float *gv, int t) {  // OPT:2011-2025
+  return hybrid_normalization(nAngles, ac, values, gv, t) * gv[t - 1] - values[t - 1];
+}
+
+// one block per entry: thread 0 finds the transition index (hunt + bisection, OPT:1963-2000), all threads write
+__global__ void hybrid_kernel(const float *__restrict__ orig, int nS, float width, const float *__restrict__ ac,
+                              const float *__restrict__ gv, float *__restrict__ out) {
+  __shared__ int sT;
+  __shared__ float sP0;
+  const float *values = orig + (size_t)blockIdx.x * nS;
+  float *o = out + (size_t)blockIdx.x * nS;
+  if (threadIdx.x == 0) {
+    int transitionIndex = 0;
+    float P0 = 0.0f;
+    // findIndex(width, angles) on angles(i) = (i - 1) / (nS - 1) * pi, evaluated as the table holds them
+    int lo = 0, hi = nS;
+    while (!(lo == nS || hi <= lo + 1)) {
+      const int midPoint = (lo + hi) / 2;
+      const float a = (float)(midPoint - 1) / (float)(nS - 1) * 3.14159265358979312f;
+      if (width >= a) lo = midPoint; else hi = midPoint;
+    }
+    int lowerBound = lo + 1;
+    if (lowerBound < nS - 2) {
+      float lowDiff = hybrid_diff(nS, ac, values, gv, lowerBound), upDiff = 0.0f;
+      int increment = 1, upperBound = lowerBound;
+      bool root = true;
+      for (;;) {
+        upperBound = min(lowerBound + increment, nS - 1);
+        upDiff = hybrid_diff(nS, ac, values, gv, upperBound);
+        if (lowerBound == nS - 1) { root = false; break; }
+        if (lowDiff * upDiff < 0.0f) break;
+        lowerBound = upperBound; lowDiff = upDiff; increment = increment * 2;
+      }
+      if (root) {
+        while (upperBound > lowerBound + 1) {
+          const int midPoint = (lowerBound + upperBound) / 2;
+          const float midDiff = hybrid_diff(nS, ac, values, gv, midPoint);
+          if (midDiff * upDiff < 0.0f) { lowerBound = midPoint; lowDiff = midDiff; }
+          else { upperBound = midPoint; upDiff = midDiff; }
+        }
+        transitionIndex = lowerBound;
+        P0 = hybrid_normalization(nS, ac, values, gv, transitionIndex);
+      }
+    }
+    sT = transitionIndex; sP0 = P0;
+  }
+  __syncthreads();
+  const int t = sT;
+  const float P0 = sP0;
+  for (int i = threadIdx.x; i < nS; i += blockDim.x) o[i] = i < t ? P0 * gv[i] : values[i];
+}
+
+// ---------------------------------------------------------------------------------------------
 // spectral photon allocation: getFrequencyDistr (EMI:552-573) -- totalPhotons draws, each binned by
 // findCDFIndex (NUM:317-348).  The reference draws them one after the other from its sequential generator
 // (1e10 draws for the bench decks); here draw n is word (n mod 4) of the Philox block with counter
@@ -680,7 +865,7 @@ static int stream_grid(long long n, int threads, int numSMs) {
 // One layout of the padded extinction field (mcb_device.cuh) and, for fields too large for L2, its occupancy bitmap.
 // Also runs the extinction argument check and the maxval reduction (flags).
 void mcb_launch_pack_field(const DevDomain &P, int brick, float *ext, uint32_t *mask, float *layerExt, int *flags,
-                           const uint8_t *dist, int numSMs, cudaStream_t stream) {
+                           const uint8_t *dist, int *leapCount, int numSMs, cudaStream_t stream) {
   const DevDomain::ExtField &F = brick ? P.brk : P.lin;
   mcbstage::pack_extinction_kernel<<<stream_grid(F.padded, 256, numSMs), 256, 0, stream>>>(
       P.totalExt, ext, P.nx, P.ny, P.nz, MCB_GHOST, flags, F.nxp, F.nyp, F.padded, brick, dist);
@@ -688,19 +873,23 @@ void mcb_launch_pack_field(const DevDomain &P, int brick, float *ext, uint32_t *
     mcbstage::layer_min_kernel<<<P.nz + 2 * MCB_GHOST + 2, 256, 0, stream>>>(P.totalExt, P.nx * P.ny, P.nz, MCB_GHOST, layerExt);
     int cap = MCB_LEAP_CAP;
     cap = cap < P.nx ? cap : P.nx; cap = cap < P.ny ? cap : P.ny;
-    mcbstage::layer_tables_kernel<<<1, 256, 0, stream>>>(layerExt, P.nz, MCB_GHOST, cap, P.fhz, (float *)P.layerLeap, (float *)P.layerCum);
+    cudaMemsetAsync(leapCount, 0, sizeof(int), stream);
+    mcbstage::layer_tables_kernel<<<1, 256, 0, stream>>>(layerExt, P.nz, MCB_GHOST, cap, P.fhz, (float *)P.layerLeap, (float *)P.layerCum,
+                                                         MCB_LEAP_MIN + 1, leapCount);
     mcbstage::occupancy_mask_kernel<<<stream_grid(F.padded, 256, numSMs), 256, 0, stream>>>(ext, layerExt, F.padded,
                                                                                             F.nxp * F.nyp, mask, brick);
   }
 }
 
 // the vacuum-distance map of the staged domain: dist[cells] (result) and scratch[cells]
-void mcb_launch_distance_map(const DevDomain &P, int cap, uint8_t *dist, uint8_t *scratch, int numSMs, cudaStream_t stream) {
+void mcb_launch_distance_map(const DevDomain &P, int cap, uint8_t *dist, uint8_t *scratch, int *leapCount, int numSMs,
+                             cudaStream_t stream) {
   const long long cols = (long long)P.nx * P.ny, cells = cols * P.nz;
   const int grid = stream_grid(cells, 256, numSMs);
   mcbstage::dist_x_kernel<<<grid, 256, 0, stream>>>(P.totalExt, P.nx, cells, cap, dist);
   mcbstage::dist_y_kernel<<<grid, 256, 0, stream>>>(dist, P.nx, P.ny, cells, scratch);
-  mcbstage::dist_z_kernel<<<grid, 256, 0, stream>>>(scratch, cols, P.nz, cells, dist);
+  cudaMemsetAsync(leapCount, 0, sizeof(int), stream);
+  mcbstage::dist_z_kernel<<<grid, 256, 0, stream>>>(scratch, cols, P.nz, cells, dist, MCB_LEAP_MIN + 1, leapCount);
 }
 
 void mcb_launch_gather_column_cdf(const double *voxelCDF, int nx, int ny, int nz, double *colCDF, int numSMs, cudaStream_t stream) {
@@ -760,6 +949,27 @@ void mcb_launch_stats_finalise(const double *stats, long long n, double solarFlu
 void mcb_launch_inverse_table(const int *offsets, const float *mus, const float *values, int nEntries, int nSteps, float *out,
                               float *cdfScratch, cudaStream_t stream) {
   mcbstage::inverse_table_kernel<<<nEntries, 256, 0, stream>>>(offsets, mus, values, nSteps, out, cdfScratch);
+}
+
+void mcb_launch_lobatto_inputs(const int *coefOff, const float *coefs, const int *nodeOff, int nEntries, long long nNodes,
+                               float *mus, float *values, int numSMs, cudaStream_t stream) {
+  mcbstage::lobatto_inputs_kernel<<<stream_grid(nNodes, 64, numSMs), 64, 0, stream>>>(coefOff, coefs, nodeOff, nEntries, mus, values);
+}
+
+// orig: the phase functions on nSteps equal angle steps; fwd: the same, or with the Gaussian forward peak of hybridWidth
+// degrees (scratch: 2 * nSteps floats)
+void mcb_launch_forward_tables(const int *coefOff, const float *coefs, const int *angOff, const float *angles, const float *values,
+                               int nEntries, int nSteps, float hybridWidth, float *orig, float *fwd, float *scratch, int numSMs,
+                               cudaStream_t stream) {
+  mcbstage::forward_values_kernel<<<stream_grid((long long)nEntries * nSteps, 256, numSMs), 256, 0, stream>>>(
+      coefOff, coefs, angOff, angles, values, nEntries, nSteps, orig);
+  if (hybridWidth > 0.0f) {
+    const float width = hybridWidth * 3.14159265358979312f / 180.0f;
+    mcbstage::hybrid_prepare_kernel<<<stream_grid(nSteps, 256, numSMs), 256, 0, stream>>>(nSteps, width, scratch, scratch + nSteps);
+    mcbstage::hybrid_kernel<<<nEntries, 256, 0, stream>>>(orig, nSteps, width, scratch, scratch + nSteps, fwd);
+  } else {
+    cudaMemcpyAsync(fwd, orig, sizeof(float) * (size_t)nEntries * nSteps, cudaMemcpyDeviceToDevice, stream);
+  }
 }
 
 void mcb_launch_forward_table(const int *offsets, const float *coefs, int nEntries, int nSteps, float *out, int numSMs,

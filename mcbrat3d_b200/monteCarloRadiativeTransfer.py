@@ -212,9 +212,10 @@ def _stage_domain(g: integrator, d: Domain) -> None:
     if not onDevice:
         d.tabulateInversePhaseFunctions(g.minInverseTableSize)
     # forward tables: Legendre-stored components without the hybrid peak can be tabulated in HBM as well
+    # (buildTablesOnDevice: every forward table -- Legendre moments or angle / value pairs, with or without the hybrid
+    # peak -- is tabulated in HBM: mcb_build_forward_table_general)
     hybrid = bool(g.options.useHybridPhaseFunsForIntenCalcs)
-    fwdOnDevice = [onDevice and not hybrid and all(pf.storedAsLegendre() for pf in tab.phaseFunctions)
-                   for tab in d.forwardTables] if g.computeIntensity else []
+    fwdOnDevice = [onDevice for tab in d.forwardTables] if g.computeIntensity else []
     if g.computeIntensity and not all(fwdOnDevice):
         d.tabulateForwardPhaseFunctions(g.minForwardTableSize, hybrid, g.hybridPhaseFunWidth)
     tkey = (key, onDevice, g.minInverseTableSize if onDevice else d.tableToken,
@@ -224,6 +225,14 @@ def _stage_domain(g: integrator, d: Domain) -> None:
         if onDevice:
             from .inversePhaseFunctions import inversion_inputs
             for c, tab in enumerate(d.forwardTables):
+                if all(pf.storedAsLegendre() for pf in tab.phaseFunctions):        # Lobatto nodes and values in HBM too
+                    nCoef = np.array([pf.legendreCoefficients.size for pf in tab.phaseFunctions], dtype=np.int32)
+                    coefs = np.ascontiguousarray(np.concatenate([pf.legendreCoefficients for pf in tab.phaseFunctions]
+                                                                + [np.zeros(0, f32)]), dtype=f32)
+                    g._check(g._lib.mcb_build_inverse_table_legendre(g._h, c + 1, int(g.minInverseTableSize), len(tab.phaseFunctions),
+                                                                     _lib.ptr(nCoef, C.c_int32), _lib.ptr(coefs, C.c_float)),
+                             "tabulateInversePhaseFunctions")
+                    continue
                 pairs = [inversion_inputs(pf) for pf in tab.phaseFunctions]
                 nAng = np.array([m.size for m, _ in pairs], dtype=np.int32)
                 mus = np.ascontiguousarray(np.concatenate([m for m, _ in pairs]), dtype=f32)
@@ -238,12 +247,17 @@ def _stage_domain(g: integrator, d: Domain) -> None:
         if g.computeIntensity:
             for c, tab in enumerate(d.forwardTables):
                 if fwdOnDevice[c]:
-                    nCoef = np.array([pf.legendreCoefficients.size for pf in tab.phaseFunctions], dtype=np.int32)
-                    coefs = np.ascontiguousarray(np.concatenate([pf.legendreCoefficients for pf in tab.phaseFunctions]
-                                                                + [np.zeros(0, f32)]), dtype=f32)
-                    g._check(g._lib.mcb_build_forward_table(g._h, c + 1, int(g.minForwardTableSize), len(tab.phaseFunctions),
-                                                            _lib.ptr(nCoef, C.c_int32), _lib.ptr(coefs, C.c_float)),
-                             "tabulateForwardPhaseFunctions")
+                    leg = [pf.storedAsLegendre() for pf in tab.phaseFunctions]
+                    nCoef = np.array([pf.legendreCoefficients.size if l else 0 for pf, l in zip(tab.phaseFunctions, leg)], dtype=np.int32)
+                    nAng = np.array([0 if l else pf.scatteringAngle.size for pf, l in zip(tab.phaseFunctions, leg)], dtype=np.int32)
+                    z = [np.zeros(0, f32)]
+                    coefs = np.ascontiguousarray(np.concatenate([pf.legendreCoefficients for pf, l in zip(tab.phaseFunctions, leg) if l] + z), dtype=f32)
+                    angs = np.ascontiguousarray(np.concatenate([pf.scatteringAngle for pf, l in zip(tab.phaseFunctions, leg) if not l] + z), dtype=f32)
+                    vals = np.ascontiguousarray(np.concatenate([pf.value for pf, l in zip(tab.phaseFunctions, leg) if not l] + z), dtype=f32)
+                    g._check(g._lib.mcb_build_forward_table_general(
+                        g._h, c + 1, int(g.minForwardTableSize), len(tab.phaseFunctions), _lib.ptr(nCoef, C.c_int32),
+                        _lib.ptr(coefs, C.c_float), _lib.ptr(nAng, C.c_int32), _lib.ptr(angs, C.c_float), _lib.ptr(vals, C.c_float),
+                        C.c_float(g.hybridPhaseFunWidth if hybrid else 0.0)), "tabulateForwardPhaseFunctions")
                 else:
                     Pf, Po = d.tabulatedPhaseFunctions[c], d.tabulatedOrigPhaseFunctions[c]
                     g._check(g._lib.mcb_set_forward_table(g._h, c + 1, Pf.shape[1], Pf.shape[0], _lib.ptr(Pf, C.c_float),

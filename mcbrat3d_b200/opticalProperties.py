@@ -196,7 +196,10 @@ class Domain:
 # computeHybridPhaseFunctions (OPT:1936-2050)
 # ---------------------------------------------------------------------------------------
 def _dot32(a, b):
-    return f32(np.dot(np.asarray(a, dtype=f32), np.asarray(b, dtype=f32)))
+    """dot_product in single precision, accumulated in order (a compiler that keeps IEEE semantics does not
+    reassociate the reduction)."""
+    prod = (np.asarray(a, dtype=f32) * np.asarray(b, dtype=f32)).astype(f32)
+    return f32(np.add.accumulate(prod, dtype=f32)[-1]) if prod.size else f32(0.0)
 
 
 def _computeNormalization(angleCosines, values, gaussianValues, t):     # OPT:2027-2050 (t is 1-based)

@@ -1293,3 +1293,166 @@ void orc_forward_phase_function(int nCoef, const float *legendreCoefficients, in
     values[i] = value;
   }
 }
+
+/* ---- the rest of the table producers: Lobatto nodes, phase-function values for either storage kind,
+ *      the inversion inputs of a Legendre-stored phase function, the hybrid (Gaussian forward peak) tables ---- */
+
+/* computeLegendrePolynomials NUM:187-205 at one mu: P[0..maxL] by upward recursion in single precision */
+static void legendre_polynomials(int maxL, float mu, float *P) {
+  P[0] = 1.0f;
+  P[1] = mu;
+  for (int l = 1; l <= maxL - 1; ++l)
+    P[l + 1] = (((float)(2 * l + 1) * mu) * P[l] - (float)l * P[l - 1]) / (float)(l + 1);
+}
+
+/* computeLobattoTerms NUM:27-114: abscissas and weights of n-point Lobatto quadrature on [-1, 1], Newton's method on
+ * the zeros of P'_{n-1}.  The iteration is global as in the reference: every pass recomputes the polynomials at every
+ * trial point, only the points still moving are updated, the loop ends when none moves (or after 26 passes) -- so the
+ * weights are formed from the polynomials of the last pass.                                                       */
+void orc_lobatto_terms(int n, float *mus, float *weights) {
+  const float relativeAccuracy = 3.0f;
+  const int maxIterations = 25;
+  const float pi = f_acos(-1.0f);
+  const int nTerms = n, midPoint = (nTerms + 1) / 2, m = midPoint - 1;
+  float *trial = (float *)malloc(sizeof(float) * (m + 1)), *last = (float *)malloc(sizeof(float) * (m + 1));
+  float *d1 = (float *)malloc(sizeof(float) * (m + 1)), *d2 = (float *)malloc(sizeof(float) * (m + 1));
+  float *P = (float *)malloc(sizeof(float) * (size_t)(nTerms + 1) * (m + 1));        /* P[k * (nTerms + 1) + l] */
+#define LP(l, k) P[(size_t)(k) * (nTerms + 1) + (l)]
+  const float c1 = (nTerms % 2 == 1) ? 1.0f : 0.5f;
+  for (int k = 0; k < m; ++k) trial[k] = f_sin(pi * ((float)(k + 1) - c1) / ((float)nTerms - 1.0f + 0.5f));
+  for (int k = 0; k < m; ++k) {                                                        /* first Newton step */
+    legendre_polynomials(nTerms - 1, trial[k], &LP(0, k));
+    d1[k] = (float)(nTerms - 1) * (trial[k] * LP(nTerms - 1, k) - LP(nTerms - 2, k)) / (trial[k] * trial[k] - 1.0f);
+    d2[k] = (2.0f * trial[k] * d1[k] - ((float)(nTerms * (nTerms - 1)) * LP(nTerms - 1, k))) / (1.0f - trial[k] * trial[k]);
+    last[k] = trial[k];
+    trial[k] = trial[k] - d1[k] / d2[k];
+  }
+  int i = 0;
+  for (;;) {
+    int moving = 0;
+    for (int k = 0; k < m; ++k) if (fabsf(trial[k] - last[k]) > relativeAccuracy * sp32(trial[k])) moving = 1;
+    if (!moving) break;
+    for (int k = 0; k < m; ++k) legendre_polynomials(nTerms - 1, trial[k], &LP(0, k));
+    for (int k = 0; k < m; ++k)
+      if (fabsf(trial[k] - last[k]) > relativeAccuracy * sp32(trial[k])) {
+        d1[k] = (float)(nTerms - 1) * (trial[k] * LP(nTerms - 1, k) - LP(nTerms - 2, k)) / (trial[k] * trial[k] - 1.0f);
+        d2[k] = (2.0f * trial[k] * d1[k] - ((float)(nTerms * (nTerms - 1)) * LP(nTerms - 1, k))) / (1.0f - trial[k] * trial[k]);
+        last[k] = trial[k];
+        trial[k] = trial[k] - d1[k] / d2[k];
+      }
+    i = i + 1;
+    if (i > maxIterations) break;
+  }
+  mus[0] = -1.0f;
+  weights[0] = 2.0f / (float)(nTerms * (nTerms - 1));
+  for (int k = 0; k < m; ++k) {                                                        /* mus(midPoint:2:-1) = -trialMus(:) */
+    mus[midPoint - 1 - k] = -trial[k];
+    weights[midPoint - 1 - k] = 2.0f / ((float)(nTerms * (nTerms - 1)) * (LP(nTerms - 1, k) * LP(nTerms - 1, k)));
+  }
+  if (nTerms % 2 == 0) {                                                               /* NUM:104-110, right-hand sides first */
+    for (int k = 0; k < midPoint; ++k) { mus[midPoint + k] = -mus[midPoint - 1 - k]; weights[midPoint + k] = weights[midPoint - 1 - k]; }
+  } else {
+    float *tm = (float *)malloc(sizeof(float) * midPoint), *tw = (float *)malloc(sizeof(float) * midPoint);
+    for (int k = 0; k < midPoint; ++k) { tm[k] = -mus[midPoint - 1 - k]; tw[k] = weights[midPoint - 1 - k]; }
+    for (int k = 0; k < midPoint; ++k) { mus[midPoint - 1 + k] = tm[k]; weights[midPoint - 1 + k] = tw[k]; }
+    free(tm); free(tw);
+  }
+#undef LP
+  free(trial); free(last); free(d1); free(d2); free(P);
+}
+
+/* getPhaseFunctionValues_one SPF:448-531 for either storage kind: nCoef >= 0 Legendre coefficients (nStored = 0), or
+ * nStored angle / value pairs (interpolated linearly in the cosine of the angle, findIndex NUM:206-260 without a
+ * first guess, the last interval guarded as SPF:511-520)                                                          */
+void orc_phase_function_values(int nCoef, const float *legendreCoefficients, int nStored, const float *storedAngle,
+                               const float *storedValue, int nAngles, const float *scatteringAngle, float *value) {
+  if (nStored <= 0) {
+    float *P = (float *)malloc(sizeof(float) * (nCoef + 2));
+    for (int i = 0; i < nAngles; ++i) {
+      if (nCoef == 0) { value[i] = 0.5f; continue; }                                   /* SPF:486-491 */
+      legendre_polynomials(nCoef, f_cos(scatteringAngle[i]), P);
+      float v = 0.0f;                                                                  /* matmul, accumulated in order */
+      for (int l = 0; l <= nCoef; ++l) v = v + ((l == 0 ? 1.0f : legendreCoefficients[l - 1]) * (float)(2 * l + 1)) * P[l];
+      value[i] = v;
+    }
+    free(P);
+    return;
+  }
+  for (int i = 0; i < nAngles; ++i) {
+    int idx = findIndexReal(scatteringAngle[i], storedAngle, nStored, 0);
+    idx = idx < 1 ? 1 : (idx > nStored ? nStored : idx);
+    int ip1 = idx + 1;
+    float dMu;
+    if (idx < nStored) dMu = f_cos(storedAngle[ip1 - 1]) - f_cos(storedAngle[idx - 1]);
+    else { dMu = FLT_MAX; ip1 = idx; }
+    const float w = 1.0f - (f_cos(scatteringAngle[i]) - f_cos(storedAngle[idx - 1])) / dMu;
+    value[i] = w * storedValue[idx - 1] + (1.0f - w) * storedValue[ip1 - 1];
+  }
+}
+
+/* INV:97-112: what computeInversePhaseFunction inverts for a Legendre-stored phase function -- its values at the
+ * max(nMoments, 2) Lobatto abscissas, increasing in mu.  mus, values: max(nCoef, 2) entries each.                 */
+void orc_inversion_inputs_legendre(int nCoef, const float *legendreCoefficients, float *mus, float *values) {
+  const int n = nCoef > 2 ? nCoef : 2;
+  float *w = (float *)malloc(sizeof(float) * n), *ang = (float *)malloc(sizeof(float) * n), *v = (float *)malloc(sizeof(float) * n);
+  orc_lobatto_terms(n, mus, w);
+  for (int i = 0; i < n; ++i) ang[i] = f_acos(mus[n - 1 - i]);                         /* acos(mus(nAngles:1:-1)) */
+  orc_phase_function_values(nCoef, legendreCoefficients, 0, NULL, NULL, n, ang, v);
+  for (int i = 0; i < n; ++i) values[i] = v[n - 1 - i];                                /* values = values(nAngles:1:-1) */
+  free(w); free(ang); free(v);
+}
+
+/* computeNormalization OPT:2027-2050 (transitionIndex 1-based; dot products accumulated in order, single precision) */
+static float hybrid_normalization(int nAngles, const float *angleCosines, const float *values, const float *gaussianValues, int t) {
+  float integralGaus = 0.0f, integralOrig = 0.0f;
+  for (int j = 1; j <= t - 1; ++j)
+    integralGaus = integralGaus + (0.5f * (gaussianValues[j - 1] + gaussianValues[j])) * (angleCosines[j - 1] - angleCosines[j]);
+  for (int j = t; j <= nAngles - 1; ++j)
+    integralOrig = integralOrig + (0.5f * (values[j - 1] + values[j])) * (angleCosines[j - 1] - angleCosines[j]);
+  if (integralOrig >= 2.0f) return 1.0f / integralGaus;
+  return (2.0f - integralOrig) / integralGaus;
+}
+static float hybrid_diff(int nAngles, const float *angleCosines, const float *values, const float *gaussianValues, int t) {   /* OPT:2011-2025 */
+  const float P0 = hybrid_normalization(nAngles, angleCosines, values, gaussianValues, t);
+  return P0 * gaussianValues[t - 1] - values[t - 1];
+}
+
+/* computeHybridPhaseFunctions OPT:1936-2009 for one table entry: a Gaussian of gaussianWidth degrees replaces the
+ * forward peak, continuous with the original at the transition angle (hunt + bisection on the difference), scaled so
+ * that the whole stays normalised.  Returns the transition index (0: the entry is left as it is).                  */
+int orc_hybrid_phase_function(int nAngles, const float *angles, const float *values, float gaussianWidth, float *newValues) {
+  float *angleCosines = (float *)malloc(sizeof(float) * nAngles), *gaussianValues = (float *)malloc(sizeof(float) * nAngles);
+  const float width = gaussianWidth * PI32 / 180.0f;
+  for (int i = 0; i < nAngles; ++i) {
+    angleCosines[i] = f_cos(angles[i]);
+    const float q = angles[i] / width;
+    gaussianValues[i] = f_exp(-(q * q));
+  }
+  for (int i = 0; i < nAngles; ++i) newValues[i] = values[i];
+  int transitionIndex = 0;
+  int lowerBound = findIndexReal(width, angles, nAngles, 0) + 1;
+  if (lowerBound < nAngles - 2) {
+    float lowDiff = hybrid_diff(nAngles, angleCosines, values, gaussianValues, lowerBound), upDiff = 0.0f;
+    int increment = 1, upperBound = lowerBound, root = 1;
+    for (;;) {                                                                         /* hunt */
+      upperBound = lowerBound + increment < nAngles - 1 ? lowerBound + increment : nAngles - 1;
+      upDiff = hybrid_diff(nAngles, angleCosines, values, gaussianValues, upperBound);
+      if (lowerBound == nAngles - 1) { root = 0; break; }
+      if (lowDiff * upDiff < 0.0f) break;
+      lowerBound = upperBound; lowDiff = upDiff; increment = increment * 2;
+    }
+    if (root) {
+      while (upperBound > lowerBound + 1) {                                            /* bisection */
+        const int midPoint = (lowerBound + upperBound) / 2;
+        const float midDiff = hybrid_diff(nAngles, angleCosines, values, gaussianValues, midPoint);
+        if (midDiff * upDiff < 0.0f) { lowerBound = midPoint; lowDiff = midDiff; }
+        else { upperBound = midPoint; upDiff = midDiff; }
+      }
+      transitionIndex = lowerBound;
+      const float P0 = hybrid_normalization(nAngles, angleCosines, values, gaussianValues, transitionIndex);
+      for (int i = 0; i < transitionIndex; ++i) newValues[i] = P0 * gaussianValues[i];
+    }
+  }
+  free(angleCosines); free(gaussianValues);
+  return transitionIndex;
+}

@@ -241,6 +241,21 @@ void orc_inverse_phase_function(int nAngles, const float *mus, const float *valu
  * nCoef = 0 is the isotropic special case with value 1/2 (quirk q14).                                              */
 void orc_forward_phase_function(int nCoef, const float *legendreCoefficients, int nS, float *values);
 
+/* computeLobattoTerms NUM:27-114: abscissas (increasing) and weights of n-point Lobatto quadrature on [-1, 1] */
+void orc_lobatto_terms(int n, float *mus, float *weights);
+
+/* getPhaseFunctionValues_one SPF:448-531: Legendre-stored (nStored = 0, nCoef coefficients chi_1..chi_n) or stored as
+ * nStored angle / value pairs (linear in the cosine of the angle)                                                 */
+void orc_phase_function_values(int nCoef, const float *legendreCoefficients, int nStored, const float *storedAngle,
+                               const float *storedValue, int nAngles, const float *scatteringAngle, float *value);
+
+/* INV:97-112: mus (Lobatto abscissas) and the values of a Legendre-stored phase function there: max(nCoef, 2) each */
+void orc_inversion_inputs_legendre(int nCoef, const float *legendreCoefficients, float *mus, float *values);
+
+/* computeHybridPhaseFunctions OPT:1936-2050 for one entry tabulated at nAngles angles (radians); returns the
+ * transition index (0 if the entry keeps its original values)                                                     */
+int orc_hybrid_phase_function(int nAngles, const float *angles, const float *values, float gaussianWidth, float *newValues);
+
 #ifdef __cplusplus
 }
 #endif

@@ -136,6 +136,14 @@ def load():
     lib.orc_inverse_phase_function.restype = None
     lib.orc_forward_phase_function.argtypes = [C.c_int, _fp, C.c_int, _fp]
     lib.orc_forward_phase_function.restype = None
+    lib.orc_lobatto_terms.argtypes = [C.c_int, _fp, _fp]
+    lib.orc_lobatto_terms.restype = None
+    lib.orc_phase_function_values.argtypes = [C.c_int, _fp, C.c_int, _fp, _fp, C.c_int, _fp, _fp]
+    lib.orc_phase_function_values.restype = None
+    lib.orc_inversion_inputs_legendre.argtypes = [C.c_int, _fp, _fp, _fp]
+    lib.orc_inversion_inputs_legendre.restype = None
+    lib.orc_hybrid_phase_function.argtypes = [C.c_int, _fp, _fp, C.c_float, _fp]
+    lib.orc_hybrid_phase_function.restype = C.c_int
     lib.orc_finalise_stats.argtypes = [_dp, C.c_int64, C.c_double, C.c_int64, C.c_int64]
     lib.orc_finalise_stats.restype = None
     lib.orc_march.restype = C.c_float
@@ -364,6 +372,44 @@ def forward_phase_function(legendreCoefficients, nSteps):
     out = np.empty(int(nSteps), dtype=np.float32)
     lib.orc_forward_phase_function(c.size, _p(c, C.c_float), int(nSteps), _p(out, C.c_float))
     return out
+
+
+def lobatto_terms(n):
+    """computeLobattoTerms NUM:27-114: (mus, weights)."""
+    mus = np.empty(int(n), dtype=np.float32); w = np.empty(int(n), dtype=np.float32)
+    load().orc_lobatto_terms(int(n), _p(mus, C.c_float), _p(w, C.c_float))
+    return mus, w
+
+
+def phase_function_values(angles, legendreCoefficients=None, storedAngle=None, storedValue=None):
+    """getPhaseFunctionValues_one SPF:448-531 for a Legendre-stored or an angle / value phase function."""
+    a = np.ascontiguousarray(angles, dtype=np.float32)
+    out = np.empty(a.size, dtype=np.float32)
+    if storedAngle is None:
+        c = np.ascontiguousarray(legendreCoefficients, dtype=np.float32)
+        load().orc_phase_function_values(c.size, _p(c, C.c_float), 0, None, None, a.size, _p(a, C.c_float), _p(out, C.c_float))
+    else:
+        sa = np.ascontiguousarray(storedAngle, dtype=np.float32); sv = np.ascontiguousarray(storedValue, dtype=np.float32)
+        load().orc_phase_function_values(0, None, sa.size, _p(sa, C.c_float), _p(sv, C.c_float), a.size, _p(a, C.c_float),
+                                         _p(out, C.c_float))
+    return out
+
+
+def inversion_inputs_legendre(legendreCoefficients):
+    """INV:97-112: the Lobatto abscissas and the phase function values there that computeInversePhaseFunction inverts."""
+    c = np.ascontiguousarray(legendreCoefficients, dtype=np.float32)
+    n = max(c.size, 2)
+    mus = np.empty(n, dtype=np.float32); v = np.empty(n, dtype=np.float32)
+    load().orc_inversion_inputs_legendre(c.size, _p(c, C.c_float), _p(mus, C.c_float), _p(v, C.c_float))
+    return mus, v
+
+
+def hybrid_phase_function(angles, values, gaussianWidth):
+    """computeHybridPhaseFunctions OPT:1936-2050 for one entry: (new values, transition index)."""
+    a = np.ascontiguousarray(angles, dtype=np.float32); v = np.ascontiguousarray(values, dtype=np.float32)
+    out = np.empty(a.size, dtype=np.float32)
+    t = load().orc_hybrid_phase_function(a.size, _p(a, C.c_float), _p(v, C.c_float), float(gaussianWidth), _p(out, C.c_float))
+    return out, int(t)
 
 
 def finalise(stats: np.ndarray, solarFlux: float, totalNumPhotons: int, batchesCompleted: int):

@@ -6,7 +6,8 @@ D - 1 cells around it.  No optical depth accumulates in vacuum (OPT:1729-1738 ad
 cell-by-cell walk's: (1) the map is checked against a brute-force transform, (2) leaps on / off give the same photon
 histories up to rounding at the landing faces -- event counters (including the cells-crossed counter, which a leap
 advances by the faces it crosses) and tallies agree far inside the Monte Carlo noise, (3) the full-size 1e8-photon
-maps of tests/test_gpu_headline.py run with leaps on (the default)."""
+maps of tests/test_gpu_headline.py run with leaps on (the default), (4) the leap counters, which only the
+bounds-checked build keeps, show that the leaps are taken."""
 import numpy as np
 import pytest
 
@@ -110,7 +111,7 @@ def test_leaps_trace_the_same_histories_up_to_rounding(name, make, n, views):
     want, cw = _run(dom, case, n, views, tuneLeap=-1, **extra)
     assert cw["bad"] == 0
     for leap in (0, 2, 7):                                  # default distance, the smallest, a larger one
-        got, cg = _run(dom, case, n, views, tuneLeap=leap, tuneLeapLanes=1 if leap else 0, **extra)   # every leap / the default gate
+        got, cg = _run(dom, case, n, views, tuneLeap=leap, tuneLeapLanes=8 if leap == 7 else 0, **extra)   # one run with the warp gate
         assert cg["bad"] == 0 and cg["photons"] == cw["photons"]
         # Same random numbers, same directions; positions differ by an ulp of the coordinate once a leap has replaced
         # repeated additions by one multiplication, and a photon that passes within that of a cell edge takes another
@@ -122,7 +123,6 @@ def test_leaps_trace_the_same_histories_up_to_rounding(name, make, n, views):
         for k in ("crossings", "scatters", "surfaceHits", "leRays", "leCrossings"):
             slack = (cw["photons"] + cw["surfaceHits"] if k == "crossings" else cw["leRays"] if k == "leCrossings" else 0)
             assert abs(cg[k] - cw[k]) <= 2e-4 * max(cw[k], 1) + 3 + slack, (leap, k, cg[k], cw[k])
-        assert (cg["leaps"] > 0 or leap > 4) and cg["leapCells"] >= 2 * cg["leaps"], (leap, cg["leaps"], cg["leapCells"])
         for k in ("meanFluxUp", "meanFluxDown", "meanFluxAbsorbed") + (("meanIntensity",) if views else ()):
             np.testing.assert_allclose(got[k], want[k], rtol=6e-3 if k == "meanIntensity" else 1e-3, atol=1e-6,
                                        err_msg="%s leap=%d" % (k, leap))
@@ -131,11 +131,40 @@ def test_leaps_trace_the_same_histories_up_to_rounding(name, make, n, views):
             assert np.abs(a - b).sum() <= 2e-2 * np.abs(b).sum(), (leap, k)
 
 
-def test_leap_counters_on_the_cloud_scene():
-    """How much of a photon's path the leaps cover on the C3 cloud scene (counters leaps / leapCells): every leap crosses
-    at least the distance it was taken from, and the cells it crosses are part of the crossings counter."""
-    dom, case = domains.landsat_cloud(ssa=0.99, nxy=64)
-    _, c = _run(dom, case, 1000000)
-    assert c["leaps"] > 0.5 * c["photons"] and c["leapCells"] >= 4 * c["leaps"] and c["leapCells"] < c["crossings"], c
-    print("leaps per photon %.2f, cells per leap %.1f, share of the crossings %.3f" % (
-        c["leaps"] / c["photons"], c["leapCells"] / c["leaps"], c["leapCells"] / c["crossings"]))
+COUNTER_SCRIPT = r"""
+import json, sys
+sys.path.insert(0, %r); sys.path.insert(0, %r)
+from mcbrat3d_b200 import _lib
+assert _lib.LIB_PATH.endswith("libmcbrat_cuda_dbg.so")
+import test_gpu_leap as T
+out = {}
+for name, make, n, views in T.LEAP_CASES:
+    dom, case = make()
+    extra = dict(tuneLayout=1) if name.endswith("linear") else dict(tuneExtMask=1) if "bitmap" in name else {}
+    _, c = T._run(dom, case, min(n, 100000), views, **extra)
+    out[name] = c
+dom, case = T.domains.landsat_cloud(ssa=0.99, nxy=24, mie=True)      # Rayleigh background: no vacuum anywhere
+_, out["no_vacuum"] = T._run(dom, case, 50000)
+print("RESULT " + json.dumps(out))
+"""
+
+
+def test_leap_counters():
+    """The counters leaps / leapCells exist in the bounds-checked build only (the warp reduction behind them costs the
+    72-register flux kernel 9 %): every case above takes leaps, each crosses at least two cells, the cells are part of
+    the crossings counters, nothing is read out of bounds -- and a scene without vacuum runs the kernels without the
+    leap code (no leaps, same counters as ever)."""
+    import json, os, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    p = subprocess.run([sys.executable, "-c", COUNTER_SCRIPT % (root, os.path.join(root, "tests"))], capture_output=True, text=True,
+                       env=dict(os.environ, MCB_LIB_DEBUG="1"), timeout=900)
+    assert p.returncode == 0, p.stderr[-2000:]
+    res = json.loads([l for l in p.stdout.splitlines() if l.startswith("RESULT ")][0][7:])
+    for name, c in res.items():
+        assert c["bad"] == 0, (name, c)
+        if name == "no_vacuum":
+            assert c["leaps"] == 0 and c["leapCells"] == 0, c
+            continue
+        assert c["leaps"] > 0 and 2 * c["leaps"] <= c["leapCells"] < c["crossings"] + c["leCrossings"], (name, c)
+        print("%s: %.2f leaps per photon, %.1f cells per leap, %.3f of the crossings" % (
+            name, c["leaps"] / c["photons"], c["leapCells"] / c["leaps"], c["leapCells"] / (c["crossings"] + c["leCrossings"])))

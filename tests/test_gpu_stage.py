@@ -302,3 +302,127 @@ def test_forward_tables_built_on_device_match_oracle(orc):
             np.testing.assert_allclose(r_dev["meanIntensity"], r_host["meanIntensity"], rtol=2e-3)
         finally:
             finalize_Integrator(g)
+
+
+def test_every_forward_table_is_built_on_device_and_matches_oracle(orc):
+    """The remainder of SURVEY 8(f) rank 2: forward tables of angle / value phase functions (SPF:499-527) and the hybrid
+    tables with a Gaussian forward peak (computeHybridPhaseFunctions OPT:1936-2050: hunt + bisection for the transition
+    angle) tabulated in HBM by mcb_build_forward_table_general, against the oracle's C restatements."""
+    d, case = domains.landsat_cloud(ssa=0.99, nxy=16, mie=True)          # 16 angle / value entries + the Rayleigh moments
+    nS = 9001
+    angles = (np.arange(nS, dtype=f32) / f32(nS - 1) * f32(np.pi)).astype(f32)
+    for width in (0.0, 7.0):
+        g = new_Integrator(d)
+        try:
+            specifyParameters(g, intensityMus=[1.0, 0.5], intensityPhis=[0.0, 90.0], computeIntensity=True,
+                              minInverseTableSize=9001, minForwardTableSize=nS, buildTablesOnDevice=True,
+                              useHybridPhaseFunsForIntenCalcs=width > 0, hybridPhaseFunWidth=width if width > 0 else None)
+            rs = new_RandomNumberSequence(4)
+            ps = new_PhotonStream(case["solarMu"], case["solarAzimuth"], 20000, rs)
+            assert computeRadiativeTransfer(g, d, rs, ps, 20000) == 20000
+            r_dev = reportResults(g, meanIntensity=True)
+            transitions = 0
+            for c, tab in enumerate(d.forwardTables):
+                got = np.empty((len(tab.phaseFunctions), nS), dtype=f32)
+                g._check(g._lib.mcb_get_forward_table(g.handle, c + 1, _lib.ptr(got, C.c_float), got.size), "get")
+                for e, pf in enumerate(tab.phaseFunctions):
+                    if pf.storedAsLegendre():
+                        orig = orc.phase_function_values(angles, legendreCoefficients=pf.legendreCoefficients)
+                    else:
+                        orig = orc.phase_function_values(angles, storedAngle=pf.scatteringAngle, storedValue=pf.value)
+                    want, t = orc.hybrid_phase_function(angles, orig, width) if width > 0 else (orig, 0)
+                    transitions += t > 0
+                    # cos() / exp() of the device are 1 ulp, not exact: a few values differ in the last place, and the
+                    # normalisation of the Gaussian part (a sum over the whole table) may carry that along
+                    np.testing.assert_allclose(got[e], want, rtol=3e-5, atol=1e-6, err_msg="width %g comp %d entry %d" % (width, c, e))
+                    if t > 0:
+                        assert np.array_equal(got[e][t:], want[t:]) or np.abs(got[e][t:] - want[t:]).max() <= 2e-5 * np.abs(want).max()
+            specifyParameters(g, buildTablesOnDevice=False)               # host mirror: same radiances
+            rs = new_RandomNumberSequence(4)
+            ps = new_PhotonStream(case["solarMu"], case["solarAzimuth"], 20000, rs)
+            computeRadiativeTransfer(g, d, rs, ps, 20000)
+            r_host = reportResults(g, meanIntensity=True)
+            np.testing.assert_allclose(r_dev["meanIntensity"], r_host["meanIntensity"], rtol=2e-3)
+        finally:
+            finalize_Integrator(g)
+
+
+def test_lobatto_inputs_built_on_device_match_oracle(orc):
+    """computeLobattoTerms (NUM:27-114) + the phase function at the nodes (INV:97-112) in HBM: the inverse table of a
+    Legendre-stored entry built by mcb_build_inverse_table_legendre equals the oracle's inversion of the oracle's inputs."""
+    from mcbrat3d_b200.scatteringPhaseFunctions import henyeyGreenstein, new_PhaseFunctionTable, rayleigh
+    d, case = domains.homogeneous_slab(ssa=0.99)
+    g = new_Integrator(d)
+    try:
+        specifyParameters(g, minInverseTableSize=10001)
+        rs = new_RandomNumberSequence(2)
+        ps = new_PhotonStream(case["solarMu"], case["solarAzimuth"], 1000, rs)
+        computeRadiativeTransfer(g, d, rs, ps, 1000)                       # stages the domain
+        pfs = [henyeyGreenstein(0.85, 299), henyeyGreenstein(0.85, 64), henyeyGreenstein(0.6, 5), rayleigh(),
+               henyeyGreenstein(0.9, 128), henyeyGreenstein(0.3, 1)]
+        nCoef = np.array([pf.legendreCoefficients.size for pf in pfs], dtype=np.int32)
+        coefs = np.ascontiguousarray(np.concatenate([pf.legendreCoefficients for pf in pfs]), dtype=f32)
+        g._check(g._lib.mcb_build_inverse_table_legendre(g.handle, 1, 10001, len(pfs), _lib.ptr(nCoef, C.c_int32),
+                                                         _lib.ptr(coefs, C.c_float)), "build")
+        got = np.empty((len(pfs), 10001), dtype=f32)
+        g._check(g._lib.mcb_get_inverse_table(g.handle, 1, _lib.ptr(got, C.c_float), got.size), "get")
+        mismatch = 0
+        for e, pf in enumerate(pfs):
+            mus, vals = orc.inversion_inputs_legendre(pf.legendreCoefficients)
+            want = orc.inverse_phase_function(mus, vals, 10001)
+            bad = got[e] != want
+            mismatch += int(bad.sum())
+            if bad.any():
+                assert np.abs(got[e][bad] - want[bad]).max() <= 2.4e-7 * np.maximum(want[bad], 1.0).max(), e
+        assert mismatch <= 1e-4 * got.size, mismatch
+    finally:
+        finalize_Integrator(g)
+
+
+def test_hybrid_tables_with_a_transition_match_oracle(orc):
+    """Entries peaked enough for computeHybridPhaseFunctions to find a transition angle (HG g >= 0.9 for a 7-degree
+    Gaussian), through the C ABI directly: Legendre-stored and angle / value entries in one table."""
+    from mcbrat3d_b200.scatteringPhaseFunctions import henyeyGreenstein
+    d, case = domains.homogeneous_slab(ssa=0.99)
+    nS = 9001
+    angles = (np.arange(nS, dtype=f32) / f32(nS - 1) * f32(np.pi)).astype(f32)
+    ang = np.linspace(0.0, np.pi, 1441).astype(f32); ang[-1] = f32(np.pi)
+    mu = np.cos(ang.astype(np.float64))
+    hg = lambda gg: (1 - gg * gg) / (1 + gg * gg - 2 * gg * mu) ** 1.5
+    tabulated = [(0.97 * hg(g1) + 0.03 * hg(-0.45)).astype(f32) for g1 in (0.9, 0.97)]
+    legendre = [henyeyGreenstein(0.9, 64).legendreCoefficients, henyeyGreenstein(0.95, 256).legendreCoefficients,
+                henyeyGreenstein(0.85, 64).legendreCoefficients]
+    # entry order: Legendre, tabulated, Legendre, tabulated, Legendre
+    kinds = ["l", "t", "l", "t", "l"]
+    g = new_Integrator(d)
+    try:
+        rs = new_RandomNumberSequence(2)
+        ps = new_PhotonStream(case["solarMu"], case["solarAzimuth"], 1000, rs)
+        computeRadiativeTransfer(g, d, rs, ps, 1000)                       # stages the domain
+        for width in (7.0, 2.0):
+            li = iter(legendre); ti = iter(tabulated)
+            entries = [next(li) if k == "l" else next(ti) for k in kinds]
+            nCoef = np.array([e.size if k == "l" else 0 for e, k in zip(entries, kinds)], dtype=np.int32)
+            nAng = np.array([0 if k == "l" else ang.size for k in kinds], dtype=np.int32)
+            coefs = np.ascontiguousarray(np.concatenate([e for e, k in zip(entries, kinds) if k == "l"]), dtype=f32)
+            angs = np.ascontiguousarray(np.concatenate([ang for k in kinds if k == "t"]), dtype=f32)
+            vals = np.ascontiguousarray(np.concatenate([e for e, k in zip(entries, kinds) if k == "t"]), dtype=f32)
+            g._check(g._lib.mcb_build_forward_table_general(g.handle, 1, nS, len(kinds), _lib.ptr(nCoef, C.c_int32),
+                                                            _lib.ptr(coefs, C.c_float), _lib.ptr(nAng, C.c_int32),
+                                                            _lib.ptr(angs, C.c_float), _lib.ptr(vals, C.c_float), C.c_float(width)), "build")
+            got = np.empty((len(kinds), nS), dtype=f32)
+            g._check(g._lib.mcb_get_forward_table(g.handle, 1, _lib.ptr(got, C.c_float), got.size), "get")
+            found = 0
+            for e, (ent, k) in enumerate(zip(entries, kinds)):
+                orig = (orc.phase_function_values(angles, legendreCoefficients=ent) if k == "l" else
+                        orc.phase_function_values(angles, storedAngle=ang, storedValue=ent))
+                want, t = orc.hybrid_phase_function(angles, orig, width)
+                found += t > 0
+                # the transition index is decided by the sign of a difference of nearly equal numbers: the device's cos()
+                # and exp() are 1 ulp, so it may land one table step away, where the two branches differ by < 1e-3
+                changed = np.nonzero(np.abs(got[e] - want) > 3e-5 * np.abs(want) + 1e-6)[0]
+                assert changed.size <= 2 and (changed.size == 0 or abs(int(changed[0]) - t) <= 2), (width, e, t, changed[:5])
+                np.testing.assert_allclose(got[e], want, rtol=2e-3, atol=1e-6)
+            assert found >= (4 if width == 7.0 else 1), (width, found)
+    finally:
+        finalize_Integrator(g)
