@@ -37,7 +37,7 @@ METRIC_C5 = "photons/sec, I3RC bench SW cloud (C5, one wavelength bin)"
 METRIC_BB = "photons/sec, I3RC bench SW broadband (C5, 32 wavelength bins)"
 WORKLOAD_C5 = ("C5 I3RC bench cloud (synthetic scene, seed 5) 325x325x150 cells 0.0625x0.0625x0.03125 km, HG g=0.85 cloud "
                "(ssa 0.999) + Rayleigh background at 0.55 um (nc=2), mu0=0.5, albedo 0.05; fluxes + column/volume absorption; "
-               "93 MB padded f32 extinction field (> L2) marched through the occupancy bitmap")
+               "78 MB padded f32 extinction field (> L2) marched through the occupancy bitmap")
 WORKLOAD_BB = ("C5 I3RC_bench_SW broadband: 325x325x160 cells, 32 wavelength bins 0.45-2.1 um, per-bin cloud optics interpolated "
                "in effective radius + gas absorption + Rayleigh (nc=3), photons allocated to bins by the flux CDF, mu0=0.5; "
                "a step = one whole spectral run (per-bin assembly, tables, photon allocation, tracing, batch statistics)")
@@ -45,7 +45,7 @@ WORKLOAD = ("C3 I3RC Landsat cloud (synthetic scene, seed 43) 128x128x119 cells 
             "ssa=0.99, mu0=0.5, albedo 0; fluxes + column/volume absorption; nPhaseIntervals=10001")
 L2_NOTE = {"c3": "optical-property arrays are L2-resident by construction (<= 126 MB); a 256 MB buffer is rewritten between "
                  "timed steps (L2 flush), outside the per-step event pairs",
-           "c5": "inputs (93 MB extinction field + 253 MB event records) are larger than L2; a 256 MB buffer is rewritten "
+           "c5": "inputs (78 MB extinction field + 253 MB event records) are larger than L2; a 256 MB buffer is rewritten "
                  "between timed steps (L2 flush), outside the per-step event pairs",
            "broadband": "inputs are larger than L2 and every wavelength bin rebuilds them; a 256 MB buffer is rewritten "
                         "between timed steps (L2 flush), outside the per-step event pairs"}
@@ -306,6 +306,36 @@ class ClockSampler:
                 "source": "nvml" if self.nvml else "nvidia-smi"}
 
 
+def leap_share(args):
+    """Share of the algorithmic crossings that the pool kernels cross in vacuum / clear-layer leaps (never gathered).  The
+    counters behind it exist in the bounds-checked build of the library only (a warp reduction in the 72-register flux
+    kernel costs 9 %), so a short launch of the same workload runs through that build in a child process -- after the
+    timed region, rank 0 of a one-GPU run only."""
+    code = ("import sys, json; sys.path.insert(0, %r); import bench\n"
+            "from mcbrat3d_b200.monteCarloIllumination import new_PhotonStream\n"
+            "from mcbrat3d_b200.monteCarloRadiativeTransfer import *\n"
+            "from mcbrat3d_b200.RandomNumbersForMC import new_RandomNumberSequence\n"
+            "dom, case = bench.make_case(%r, %r)\n"
+            "g = new_Integrator(dom)\n"
+            "if %r: specifyParameters(g, intensityMus=case['intensityMus'], intensityPhis=case['intensityPhis'], computeIntensity=True, useRussianRouletteForIntensity=True, zetaMin=0.3)\n"
+            "specifyParameters(g, minInverseTableSize=10001, minForwardTableSize=10001)\n"
+            "rs = new_RandomNumberSequence([10, 0, 0]); n = %d\n"
+            "ps = new_PhotonStream(case['solarMu'], case['solarAzimuth'], n, rs)\n"
+            "computeRadiativeTransfer(g, dom, rs, ps, n); c = getCounters(g)\n"
+            "print('LEAP ' + json.dumps(dict(leaps_per_photon=c['leaps'] / n, cells_per_leap=c['leapCells'] / max(1, c['leaps']), "
+            "share_of_crossings=c['leapCells'] / max(1, c['crossings'] + c['leCrossings']), bad=c['bad'])))\n"
+            % (ROOT, bool(args.views), args.workload, bool(args.views), 400000 if args.views else 2000000))
+    try:
+        import subprocess
+        out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600,
+                             env=dict(os.environ, MCB_LIB_DEBUG="1")).stdout
+        d = json.loads([l for l in out.splitlines() if l.startswith("LEAP ")][0][5:])
+        d["source"] = "a short launch of this workload through the bounds-checked build (libmcbrat_cuda_dbg.so), which keeps the leap counters"
+        return d
+    except Exception as e:                      # the counters are a note, not part of the measurement
+        return {"unavailable": str(e)[:200]}
+
+
 def algorithmic_bytes(c, nc):
     """SURVEY.md 8(d) accounting with this build's storage (stated in DESIGN.md): 4 B per cell
     crossing (f32 extinction; the reference reads 8 B), per scattering event 4*nc (cumulative
@@ -504,13 +534,13 @@ def run_ours(args):
             for e in json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("entries", []):
                 if (e["workload"], bool(e.get("views", False)), e["kernel"], int(e["photons_per_launch"])) == \
                         (args.workload, bool(args.views), kernel_name.split(" ")[0], P):
-                    traffic = e["dram_bytes_per_launch"]
+                    traffic = e["dram_bytes_per_launch"]            # dram__bytes_read.sum + dram__bytes_write.sum, that launch
         except Exception:
             pass
         gathers = counters["crossings"] + counters["leCrossings"] + counters["scatters"]
         gps = gathers / (kernel_ms * 1e-3)
         # which measured gather ceiling applies: the L2-resident one when the packed field fits L2 (C1-C3), else the
-        # ceiling measured on a buffer of the field's own size (C5: 93 MB, partly L2, partly HBM)
+        # ceiling measured on a buffer of the field's own size (C5: 78 MB, partly L2, partly HBM)
         ceiling = probe["l2_16MB"] if field_bytes <= (48 << 20) else probe["field"]
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -526,10 +556,6 @@ def run_ours(args):
                         "events_per_photon": {"crossings": counters["crossings"] / max(1, counters["photons"]),
                                               "scatters": counters["scatters"] / max(1, counters["photons"]),
                                               "view_ray_crossings": counters["leCrossings"] / max(1, counters["photons"])},
-                        # cells crossed in vacuum / clear-sky leaps (csrc/mcb_march.cuh march_leap): part of the algorithmic
-                        # crossings above (the reference visits them one by one), never gathered
-                        "leaps_per_photon": counters["leaps"] / max(1, counters["photons"]),
-                        "leap_share_of_crossings": counters["leapCells"] / max(1, counters["crossings"] + counters["leCrossings"]),
                         "crossings_per_s": counters["crossings"] / (kernel_ms * 1e-3),
                         "scatters_per_s": counters["scatters"] / (kernel_ms * 1e-3),
                         "bad_photons": counters["bad"], "wall_s_timed_region": t_wall,
@@ -546,9 +572,8 @@ def run_ours(args):
                          # `peak` is the rate at which this GPU serves such gathers from a buffer of the field's residency
                          # class, launched like the flux kernels.  achieved counts ALGORITHMIC gathers (counted crossings
                          # + scatterings, including the cells a leap crosses without a gather), not the extra ones a burst
-                         # issues past an event.  gathers_issued_per_s = the same without the leapt cells.
+                         # issues past an event.  details.leaps: the share of the crossings that is leapt over.
                          "l2_gather": {"achieved": gps, "peak": ceiling, "unit": "gathers/s", "frac": gps / ceiling,
-                                       "gathers_issued_per_s": (gathers - counters["leapCells"]) / (kernel_ms * 1e-3),
                                        "peak_source": "measured in this run: mcb_debug_gather_probe, 8 loads in flight, 8 CTAs/SM, "
                                                       + ("16 MB buffer (L2-resident, like the %.1f MB field)" % (field_bytes / 2.0 ** 20)
                                                          if field_bytes <= (48 << 20) else "%.0f MB buffer (the field's size)" % (field_bytes / 2.0 ** 20)),
@@ -558,9 +583,13 @@ def run_ours(args):
                                   "traffic is far below the algorithmic bytes: the binding ceiling is the L1TEX->L2 sector "
                                   "rate (1 sector per clock per SM, measured), reported as l2_gather (DESIGN.md section 5.4)")
                          if args.workload == "c3" else
-                         ("memory-gather roofline; the 93 MB field exceeds L2: clear-sky cells are resolved from the "
+                         ("memory-gather roofline; the 78 MB field exceeds L2: clear-sky cells are resolved from the "
                           "occupancy bitmap, only cloudy cells are gathered from L2 / HBM (DESIGN.md section 5.2)")},
         }
+        if world == 1 and used_pool:
+            # cells crossed in vacuum / clear-layer leaps (csrc/mcb_march.cuh march_leap): part of the algorithmic
+            # crossings (the reference visits them one by one), never gathered
+            line["details"]["leaps"] = leap_share(args)
         if not args.no_cpu_baseline and world == 1:
             base, _, _ = cpu_rate(dom, case, args.cpu_seconds, args.views)
             line["cpu_baseline"] = base

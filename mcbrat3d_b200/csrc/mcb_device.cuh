@@ -46,7 +46,7 @@ struct DevDomain {
   //                         = 4i - 3(i&1) + cY j - (cY-2)(j&1) + cZ k - (cZ-4)(k&1),   cY = 4 bx, cZ = 4 bx by.
   //          Whatever axis a ray steps along, the next cell is in the same sector half of the time (x-fastest rows:
   //          7/8 of the x steps, none of the others), which is what bounds the flux kernels: L1TEX->XBAR requests.
-  // Fields too large for L2 (C5: 93 MB) also carry an occupancy bitmap per layout: bit p (p = absolute padded address)
+  // Fields too large for L2 (C5: 78 MB) also carry an occupancy bitmap per layout: bit p (p = absolute padded address)
   // is set where the cell's extinction differs from its layer's clear-sky value layerExt[iz + G] (the layer minimum; 0
   // in the ghost layers).  The marcher reads the bitmap (1 bit per cell, L1/L2-resident) and gathers the field only
   // where the bit is set, so clear-sky cells -- most of a cloud scene -- never go to HBM.  Exact: both branches give

@@ -7,7 +7,7 @@
 // the L2 slices can look them up (ncu, round 1).  This kernel measures that rate directly so that the roofline in
 // bench.py is a fraction of a MEASURED peak: same launch shape as the flux kernels (persistent, 128 threads, a given
 // number of CTAs per SM), `inFlight` independent loads per lane per iteration at pseudo-random addresses inside a
-// buffer of `bytes` bytes (16 MB: L2-resident like the C3 field; 93 MB: the C5 field; >= 512 MB: HBM-bound), next
+// buffer of `bytes` bytes (16 MB: L2-resident like the C3 field; 78 MB: the C5 field; >= 512 MB: HBM-bound), next
 // to nothing else (3 integer instructions per address).  A negative `inFlight` issues 16-byte loads (float4) instead.
 #include <cuda_runtime.h>
 #include <stdint.h>
