@@ -24,6 +24,9 @@ void mcb_launch_philox_kat(uint64_t seed, uint64_t photon, int n, uint32_t *out,
 double mcb_run_gather_probe(size_t bytes, int inFlight, int blocksPerSM, int iterations, int numSMs, cudaStream_t stream);
 // mcb_stage.cu: device-side packing / validation, normalisation, emission CDF
 void mcb_launch_distance_map(const DevDomain &P, int cap, uint8_t *dist, uint8_t *scratch, int *leapCount, int numSMs, cudaStream_t stream);
+void mcb_launch_column_ranges(const DevDomain &P, uint32_t *range, int *count, int *offset, int *sum, int numSMs, cudaStream_t stream);
+void mcb_launch_column_fill(const DevDomain &P, const uint32_t *range, const int *offset, float *extC, uint32_t *recC,
+                            uint32_t *cellC, uint2 *colTab, int numSMs, cudaStream_t stream);
 void mcb_launch_pack_field(const DevDomain &P, int brick, float *ext, uint32_t *mask, float *layerExt, int *flags, const uint8_t *dist, int *leapCount,
                            int numSMs, cudaStream_t stream);
 void mcb_launch_pack_records(const DevDomain &P, uint32_t *rec, int *flags, int numSMs, cudaStream_t stream);
@@ -79,6 +82,8 @@ struct mcb_handle {
   void *dExt32 = nullptr, *dExtBrick = nullptr, *dRec = nullptr;
   void *dExtMask = nullptr, *dExtMaskBrick = nullptr, *dLayerExt = nullptr;     // occupancy bitmap of fields too large for L2
   void *dDist = nullptr, *dDistScratch = nullptr;   // vacuum-distance map (u8 per cell) the packed fields are encoded with
+  void *dColRange = nullptr, *dColCount = nullptr, *dColOffset = nullptr, *dColTab = nullptr;   // column-compressed storage
+  void *dExtC = nullptr, *dRecC = nullptr, *dCellC = nullptr;
   void *dInv[MCB_MAX_COMP] = {nullptr}, *dFwd[MCB_MAX_COMP] = {nullptr}, *dFwdOrig[MCB_MAX_COMP] = {nullptr};
   int invE[MCB_MAX_COMP] = {0}, fwdE[MCB_MAX_COMP] = {0};
   void *dColCDF = nullptr, *dVoxelCDF = nullptr, *dTemps = nullptr, *dScratch = nullptr, *dResults = nullptr;
@@ -216,7 +221,8 @@ int mcb_destroy(mcb_handle *h) {
                    h->dExt32, h->dRec, h->dVoxelCDF, h->dTally, h->dCounters,
                    h->dTemps, h->dScratch, h->dResults, (void *)h->dFlags, h->dStats, h->dStatsOut,
                    h->dMassConc, h->dReff, h->dNumConc, h->dAsmTables, h->dExtMask, h->dLayerExt,
-                   h->dExtBrick, h->dExtMaskBrick, h->dColCDF, h->dDist, h->dDistScratch};
+                   h->dExtBrick, h->dExtMaskBrick, h->dColCDF, h->dDist, h->dDistScratch,
+                   h->dColRange, h->dColCount, h->dColOffset, h->dColTab, h->dExtC, h->dRecC, h->dCellC};
   for (void *p : slots) if (p) cudaFree(p);
   for (int c = 0; c < MCB_MAX_COMP; ++c) {
     if (h->dInv[c]) cudaFree(h->dInv[c]);
@@ -312,6 +318,8 @@ int mcb_set_grid(mcb_handle *h, int nx, int ny, int nz,
     F.origin = MCB_GHOST + F.nxp * (MCB_GHOST + F.nyp * MCB_GHOST);
     magic_divisor((uint32_t)F.nxp * (uint32_t)F.nyp, &F.divSliceM, &F.divSliceS);
     magic_divisor((uint32_t)F.nxp, &F.divRowM, &F.divRowS);
+    magic_divisor((uint32_t)nx * (uint32_t)ny, &P.divColsM, &P.divColsS);       // unpadded cell index -> (ix, iy, iz)
+    magic_divisor((uint32_t)nx, &P.divNxM, &P.divNxS);
   }
   {                                                  // 2x2x2 bricks: padded dimensions rounded up to even
     DevDomain::ExtField &F = P.brk;
@@ -448,6 +456,30 @@ static int finish_optics(mcb_handle *h, int nc, double albedo, bool zeroFlags) {
   if (setup_packed_field(h)) return 1;
   mcb_launch_pack_records(P, (uint32_t *)h->dRec, h->dFlags, h->numSMs, h->stream);
   CK(h, cudaGetLastError());
+  // Column-compressed storage for the pool flux kernel (fields marched through the bitmap, i.e. too large for L2): the
+  // cells inside the per-column ranges -- extinction, event record, cell index -- densely, column by column.
+  P.colTab = nullptr; P.extC = nullptr; P.recC = nullptr; P.cellC = nullptr; P.nCompact = 0;
+  if (P.lin.mask && P.uniform && P.nx >= MCB_GHOST && P.ny >= MCB_GHOST && P.nz <= 65535) {
+    const size_t cols = (size_t)P.nx * P.ny;
+    if (reserve(h, &h->dColRange, sizeof(uint32_t) * cols) || reserve(h, &h->dColCount, sizeof(int) * cols) ||
+        reserve(h, &h->dColOffset, sizeof(int) * cols) || reserve(h, &h->dColTab, sizeof(uint2) * (size_t)P.lin.nxp * P.lin.nyp))
+      return 1;
+    int *dSum = h->dFlags + 1;
+    mcb_launch_column_ranges(P, (uint32_t *)h->dColRange, (int *)h->dColCount, (int *)h->dColOffset, dSum, h->numSMs, h->stream);
+    CK(h, cudaGetLastError());
+    int nCompact = 0;
+    CK(h, cudaMemcpyAsync(&nCompact, dSum, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    if (settle(h)) return 1;
+    const size_t n = nCompact > 0 ? (size_t)nCompact : 1;
+    if (reserve(h, &h->dExtC, sizeof(float) * n) || reserve(h, &h->dRecC, sizeof(uint32_t) * (n << recShift)) ||
+        reserve(h, &h->dCellC, sizeof(uint32_t) * n))
+      return 1;
+    mcb_launch_column_fill(P, (const uint32_t *)h->dColRange, (const int *)h->dColOffset, (float *)h->dExtC, (uint32_t *)h->dRecC,
+                           (uint32_t *)h->dCellC, (uint2 *)h->dColTab, h->numSMs, h->stream);
+    CK(h, cudaGetLastError());
+    P.colTab = (const uint2 *)h->dColTab; P.extC = (const float *)h->dExtC; P.recC = (const uint32_t *)h->dRecC;
+    P.cellC = (const uint32_t *)h->dCellC; P.nCompact = nCompact;
+  }
   int flags4[4] = {0, 0, 0, 0};
   CK(h, cudaMemcpyAsync(flags4, h->dFlags, sizeof(flags4), cudaMemcpyDeviceToHost, h->stream));
   if (settle(h)) return 1;

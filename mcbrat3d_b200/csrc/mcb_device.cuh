@@ -67,6 +67,18 @@ struct DevDomain {
   const float *layerLeap;                     // nz + 2G (+2): minus the distance, in layers, to the nearest layer that is not
                                               // clear throughout (0 for such a layer): march_leap crosses that many at once
   const float *layerCum;                      // nz + 1: clear-sky optical depth per unit |1/mu| from the surface to each edge
+  // Column-compressed storage (photon-pool flux kernel on fields too large for L2, built next to the bitmap): per padded
+  // column the range of layers [lo, hi) outside which every cell has its layer's clear-sky value, and for the cells
+  // inside the ranges -- a few per cent of a cloud scene, small enough to stay in L2 -- the extinction, the event record
+  // and the cell they belong to, stored densely column by column.  A crossing then costs one 8-byte look-up in a table
+  // of a few hundred KB (L1 / L2) plus, inside the range only, one gather that L2 serves: the 78 MB field and its
+  // 253 MB of event records (C5) are not touched at all.
+  const uint2 *colTab;                        // lin.nxp x lin.nyp: .x = compact index of layer lo, .y = lo | hi << 16
+  const float *extC;                          // nCompact: (float)totalExt
+  const uint32_t *recC;                       // nCompact << recShift: the cells' event records
+  const uint32_t *cellC;                      // nCompact: ix + nx * (iy + ny * iz)
+  long long nCompact;
+  uint32_t divColsM, divNxM; int divColsS, divNxS;   // unpadded cell -> (ix, iy, iz): division by nx * ny and by nx
   // one record per cell with everything a scattering event reads, so an event costs ONE gather (a 32 B sector for
   // nc <= 3) instead of a dependent chain through three arrays: 2^recShift u32 words =
   // [f32 cumExt(c), c = 1..nc-1][f32 ssa(c), c = 1..nc][u16 phase index pairs], zero-padded

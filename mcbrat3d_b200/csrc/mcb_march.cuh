@@ -198,9 +198,14 @@ enum { MARCH_ON = ST_MARCH, MARCH_HIT = ST_SCATTER, MARCH_BOTTOM = ST_SURFACE, M
 // used.  vlast (photon-pool kernels): where the burst ends with MARCH_ON it receives a lower bound of -D for the cell
 // the ray is in now (the last gathered value + 1: D changes by at most 1 between neighbours) -- march_leap's input.
 // ENC = false (pool kernels on a domain that was staged without the encoding, DevDomain::leap == 0): no clamp.
-template <bool REG, bool WIDE, int B, bool MASK, bool BRICK, bool RAW = false, bool SPLIT = false, bool ENC = true>
+//
+// COLS (pool flux kernel, fields too large for L2; MASK = BRICK = false): column-compressed storage (mcb_device.cuh).
+// The geometry loop looks the cell's column up -- one 8-byte entry of a table that L1 / L2 hold -- and the gather goes
+// to the compact array, only for cells inside the column's range; a hit hands back the compact index (-1: a clear cell).
+template <bool REG, bool WIDE, int B, bool MASK, bool BRICK, bool RAW = false, bool SPLIT = false, bool ENC = true, bool COLS = false>
 __device__ __forceinline__ int march_burst(Ray &r, const DevDomain &P, const Grid &G,
                                            float &ext, float target, unsigned &crossings, float *vlast = nullptr) {
+  static_assert(!COLS || (RAW && REG && !MASK && !BRICK), "column-compressed storage: pool flux kernel on uniform grids");
   const DevDomain::ExtField &F = BRICK ? P.brk : P.lin;
   float tE[B], sg[B];
   int ck[B];
@@ -216,7 +221,15 @@ __device__ __forceinline__ int march_burst(Ray &r, const DevDomain &P, const Gri
 #pragma unroll
   for (int k = 0; k < B; ++k) {
     const float tmin = fminf(fminf(r.tx, r.ty), r.tz);
-    ck[k] = BRICK ? a : r.ix + F.nxp * (r.iy + F.nyp * r.iz);
+    if (COLS) {
+      const float lv = __ldg(P.layerExt + MCB_CHECK_INDEX(P, r.iz + GH, P.nz + 2 * GH));
+      const uint2 ct = __ldg(P.colTab + MCB_CHECK_INDEX(P, (r.ix + GH) + F.nxp * (r.iy + GH), F.nxp * F.nyp));
+      const unsigned lo = ct.y & 0xffffu, rel = (unsigned)r.iz - lo;           // (ghost layers: rel wraps to a huge number)
+      sg[k] = fabsf(lv);
+      ck[k] = rel < (ct.y >> 16) - lo ? (int)(ct.x + rel) : -1;
+    } else {
+      ck[k] = BRICK ? a : r.ix + F.nxp * (r.iy + F.nyp * r.iz);
+    }
     tE[k] = tmin;
     if (MASK) {
       // the layer's clear-sky extinction; its sign bit says that the whole layer has that value, so the bitmap word is
@@ -261,7 +274,9 @@ __device__ __forceinline__ int march_burst(Ray &r, const DevDomain &P, const Gri
   constexpr int H = SPLIT ? B / 2 : B;                 // gathers issued up front
 #pragma unroll
   for (int k = 0; k < H; ++k) {
-    if (MASK) {                                        // bit p of the bitmap: the shift count wraps modulo 32
+    if (COLS) {
+      if (ck[k] >= 0) sg[k] = __ldg(P.extC + MCB_CHECK_INDEX(P, ck[k], P.nCompact));
+    } else if (MASK) {                                 // bit p of the bitmap: the shift count wraps modulo 32
       if (__funnelshift_r(mw[k], 0u, (uint32_t)(ck[k] + F.origin)) & 1u) sg[k] = EXT_AT(P, F, ck[k]);
     } else {
       sg[k] = EXT_AT(P, F, ck[k]);
@@ -272,7 +287,9 @@ __device__ __forceinline__ int march_burst(Ray &r, const DevDomain &P, const Gri
     if (SPLIT && k == H) {                             // second half: only where the first half did not reach the target
 #pragma unroll
       for (int j = H; j < B; ++j) {
-        if (MASK) {
+        if (COLS) {
+          if (!found && ck[j] >= 0) sg[j] = __ldg(P.extC + MCB_CHECK_INDEX(P, ck[j], P.nCompact));
+        } else if (MASK) {
           if (!found && (__funnelshift_r(mw[j], 0u, (uint32_t)(ck[j] + F.origin)) & 1u)) sg[j] = EXT_AT(P, F, ck[j]);
         } else {
           sg[j] = 0.0f;
@@ -283,7 +300,7 @@ __device__ __forceinline__ int march_burst(Ray &r, const DevDomain &P, const Gri
 #ifdef MCB_NO_LEAP                                            // A/B build without vacuum leaps (make variant FLAGS=-DMCB_NO_LEAP)
     const float sk = sg[k];
 #else
-    const float sk = (MASK || !ENC) ? sg[k] : fmaxf(sg[k], 0.0f);       // vacuum cells hold -D
+    const float sk = (MASK || COLS || !ENC) ? sg[k] : fmaxf(sg[k], 0.0f);       // vacuum cells hold -D
 #endif
     const float en = fmaf(tE[k] - tS, sk, acc);
     const bool h = !found && en > target;
@@ -321,7 +338,7 @@ __device__ __forceinline__ int march_burst(Ray &r, const DevDomain &P, const Gri
   }
   crossings += (unsigned)B;
   r.t = tS;
-  if (vlast) *vlast = MASK ? __ldg(P.layerLeap + r.iz + GH) : sg[B - 1] + 1.0f;
+  if (vlast) *vlast = (MASK || COLS) ? __ldg(P.layerLeap + r.iz + GH) : sg[B - 1] + 1.0f;
   if (REG) {
     r.ix = wrap_index<WIDE>(r.ix, P.nx);
     r.iy = wrap_index<WIDE>(r.iy, P.ny);
@@ -368,10 +385,14 @@ __device__ __forceinline__ int march_leap(Ray &r, const DevDomain &P, const int 
   const float ex = fmaf(k, ax, r.tx), ey = fmaf(k, ay, r.ty), ez = fmaf(k, az, r.tz);          // where the cube ends
   const float te = fminf(fminf(ex, ey), ez);
   // faces crossed on the way: all D along the axis the ray leaves through, fewer along the others
-  int nx = 0, ny = 0, nz = 0;
-  if (r.tx <= te) nx = ex == te ? D : min((int)((te - r.tx) * (fabsf(r.dx) * P.finvhx)) + 1, D);
-  if (r.ty <= te) ny = ey == te ? D : min((int)((te - r.ty) * (fabsf(r.dy) * P.finvhy)) + 1, D);
-  if (r.tz <= te) nz = ez == te ? D : min((int)((te - r.tz) * (fabsf(r.dz) * P.finvhz)) + 1, D);
+  // (selects, not branches: the lanes in here are few enough as it is; an axis that does not move has t = FLT_MAX,
+  // its quotient converts to a large negative integer and is discarded)
+  int nx = ex == te ? D : min(__float2int_rz((te - r.tx) * (fabsf(r.dx) * P.finvhx)) + 1, D);
+  int ny = ey == te ? D : min(__float2int_rz((te - r.ty) * (fabsf(r.dy) * P.finvhy)) + 1, D);
+  int nz = ez == te ? D : min(__float2int_rz((te - r.tz) * (fabsf(r.dz) * P.finvhz)) + 1, D);
+  nx = r.tx <= te ? nx : 0;
+  ny = r.ty <= te ? ny : 0;
+  nz = r.tz <= te ? nz : 0;
   if (MASK) {                                                // clear-sky optical depth from r.t to te
     const float *L = P.layerExt + GH;
     const bool up = r.dz >= 0.0f;

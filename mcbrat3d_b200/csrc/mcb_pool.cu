@@ -32,6 +32,13 @@
 // the same order per photon), so their tallies agree to summation order -- tests/test_gpu_pool.py.
 #include "mcb_march.cuh"
 
+#ifndef MCB_COLS_OCC
+#define MCB_COLS_OCC 6            // column-compressed variant: CTAs per SM and split gathers by default
+#endif
+#ifndef MCB_COLS_SPLIT
+#define MCB_COLS_SPLIT false
+#endif
+
 namespace mcbpool {
 
 using namespace mcbfast;
@@ -43,7 +50,7 @@ using namespace mcbfast;
 enum { PW_PX = 0, PW_PY, PW_PZ, PW_DX, PW_DY, PW_DZ, PW_W, PW_TAU, PW_UNEXT, PW_C0, PW_C1, PW_BLK, PW_IXY, PW_IZK,
        PW_TX, PW_TY, PW_TZ };
 
-template <int THREADS, int MINBLOCKS, int BURST, bool SPLIT, bool MASK, bool BRICK, bool LEAP>
+template <int THREADS, int MINBLOCKS, int BURST, bool SPLIT, bool MASK, bool BRICK, bool LEAP, bool COLS>
 __global__ void __launch_bounds__(THREADS, MINBLOCKS)
 pool_kernel(const __grid_constant__ DevDomain P, long long nPhotons, uint64_t seed, uint64_t firstPhotonId,
             unsigned long long *workCounter, const SmemPlan plan, const float leapBelow, const int leapLanes) {
@@ -93,13 +100,14 @@ pool_kernel(const __grid_constant__ DevDomain P, long long nPhotons, uint64_t se
       int state = ST_DONE;
       float px = 0.0f, py = 0.0f, pz = 0.0f, dx = 0.0f, dy = 0.0f, dz = 1.0f, ew = 0.0f, eNext = 0.0f, eTau = 0.0f;
       int ix = 0, iy = 0, iz = 0;
+      int raw = -1;
       Rng rng;
       rng.c0 = rng.c1 = rng.blk = 0u;
       if (lane < cnt) {
         const int izk = __float_as_int(pool[PW_IZK * POOL_SLOTS + slot]);
         state = (int)((uint32_t)izk >> 28);
         if (state != ST_DEAD) {
-          const int raw = __float_as_int(pool[PW_IXY * POOL_SLOTS + slot]);
+          raw = __float_as_int(pool[PW_IXY * POOL_SLOTS + slot]);
           const float t = pool[PW_TAU * POOL_SLOTS + slot];
           px = pool[PW_PX * POOL_SLOTS + slot]; py = pool[PW_PY * POOL_SLOTS + slot]; pz = pool[PW_PZ * POOL_SLOTS + slot];
           dx = pool[PW_DX * POOL_SLOTS + slot]; dy = pool[PW_DY * POOL_SLOTS + slot]; dz = pool[PW_DZ * POOL_SLOTS + slot];
@@ -110,7 +118,20 @@ pool_kernel(const __grid_constant__ DevDomain P, long long nPhotons, uint64_t se
           px = fmaf(t, dx, px); py = fmaf(t, dy, py); pz = fmaf(t, dz, pz);
           px -= P.fLx * floorf((px - P.fx0) * P.finvLx);
           py -= P.fLy * floorf((py - P.fy0) * P.finvLy);
-          if (state == ST_SCATTER) {
+          if (state == ST_SCATTER && COLS) {
+            // column-compressed storage: the compact index knows its cell; an event in a clear cell (raw < 0: molecular
+            // scattering between the clouds) is located by its position
+            if (raw >= 0) {
+              const uint32_t c = __ldg(P.cellC + MCB_CHECK_INDEX(P, raw, P.nCompact));
+              const uint32_t z = (uint32_t)(((uint64_t)P.divColsM * c) >> P.divColsS), rem = c - z * (uint32_t)cols;
+              const uint32_t y = (uint32_t)(((uint64_t)P.divNxM * rem) >> P.divNxS);
+              ix = (int)(rem - y * (uint32_t)P.nx); iy = (int)y; iz = (int)z;
+            } else {
+              ix = min(max((int)((px - P.fx0) * P.finvhx), 0), P.nx - 1);
+              iy = min(max((int)((py - P.fy0) * P.finvhy), 0), P.ny - 1);
+              iz = min(max((int)((pz - P.fz0) * P.finvhz), 0), P.nz - 1);
+            }
+          } else if (state == ST_SCATTER) {
             cell_decode<true, BRICK>(P, raw, ix, iy, iz);
           } else {                                         // left through the top / reached the surface: column of the exit point
             ix = min(max((int)((px - P.fx0) * P.finvhx), 0), P.nx - 1);
@@ -138,7 +159,8 @@ pool_kernel(const __grid_constant__ DevDomain P, long long nPhotons, uint64_t se
         const int cell = ix + P.nx * (iy + P.ny * iz);
         float lo = 0.0f, hi = 1.0f, ssa;
         {                                                                        // the cell's event record: ONE gather
-          const uint32_t *R = P.rec + ((size_t)MCB_CHECK_INDEX(P, cell, cells) << P.recShift);
+          const uint32_t *R = (COLS && raw >= 0) ? P.recC + ((size_t)MCB_CHECK_INDEX(P, raw, P.nCompact) << P.recShift)
+                                                 : P.rec + ((size_t)MCB_CHECK_INDEX(P, cell, cells) << P.recShift);
           if (P.nc == 1) {
             const uint2 v = __ldg(reinterpret_cast<const uint2 *>(R));
             ssa = __uint_as_float(v.x); pidx = (int)(v.y & 0xffffu);
@@ -317,10 +339,10 @@ pool_kernel(const __grid_constant__ DevDomain P, long long nPhotons, uint64_t se
     if (LEAP) {
       int D = have ? leap_distance(r, P, vcur, leapBelow) : 0;
       if (leapLanes > 1 && __popc(__ballot_sync(FULL, D > 0)) < leapLanes) D = 0;   // too few lanes to pay for the divergence
-      if (D) ev = march_leap<MASK>(r, P, D, crossings, ext, tau, &sCnt[4]);         // (implies have)
+      if (D) ev = march_leap<MASK || COLS>(r, P, D, crossings, ext, tau, &sCnt[4]); // (implies have)
     }
     if (have && ev == MARCH_ON)
-      ev = march_burst<true, true, BURST, MASK, BRICK, true, SPLIT, LEAP>(r, P, G, ext, tau, crossings, LEAP ? &vcur : nullptr);
+      ev = march_burst<true, true, BURST, MASK, BRICK, true, SPLIT, LEAP, COLS>(r, P, G, ext, tau, crossings, LEAP ? &vcur : nullptr);
 
     // =========================== photons that reached an event go onto EVENT ===========================
     {
@@ -381,11 +403,11 @@ pool_kernel(const __grid_constant__ DevDomain P, long long nPhotons, uint64_t se
 
 }  // namespace mcbpool
 
-template <int MINBLOCKS, int BURST, bool SPLIT, bool MASK, bool BRICK, bool LEAP>
+template <int MINBLOCKS, int BURST, bool SPLIT, bool MASK, bool BRICK, bool LEAP, bool COLS = false>
 static void launch_pool(const DevDomain &P, long long nPhotons, uint64_t seed, uint64_t firstPhotonId, int numSMs,
                         unsigned long long *workCounter, cudaStream_t stream) {
   constexpr int THREADS = 128;
-  auto kernel = mcbpool::pool_kernel<THREADS, MINBLOCKS, BURST, SPLIT, MASK, BRICK, LEAP>;
+  auto kernel = mcbpool::pool_kernel<THREADS, MINBLOCKS, BURST, SPLIT, MASK, BRICK, LEAP, COLS>;
   const int cols = P.nx * P.ny, cells = cols * P.nz;
   mcbfast::SmemPlan plan{-1, -1, -1, -1, -1, 0, 0, 0};
   int off = 0;
@@ -442,6 +464,18 @@ void mcb_launch_pool_batch(const DevDomain &P, long long nPhotons, uint64_t seed
 #define MCB_POOL_LAYOUT(OCC, B, SPLIT) \
   do { if (mask) { if (brick) MCB_POOL_GO(OCC, B, SPLIT, true, true); else MCB_POOL_GO(OCC, B, SPLIT, true, false); } \
        else { if (brick) MCB_POOL_GO(OCC, B, SPLIT, false, true); else MCB_POOL_GO(OCC, B, SPLIT, false, false); } } while (0)
+  // column-compressed storage instead of the bitmap (fields too large for L2; tuneExtMask = 1 keeps the bitmap)
+  if (mask && P.colTab && P.opt.tuneExtMask != 1) {
+#define MCB_POOL_COLS(OCC, SPLIT) \
+  do { if (P.leap) launch_pool<OCC, 8, SPLIT, false, false, true, true>(P, nPhotons, seed, firstPhotonId, numSMs, workCounter, stream); \
+       else launch_pool<OCC, 8, SPLIT, false, false, false, true>(P, nPhotons, seed, firstPhotonId, numSMs, workCounter, stream); } while (0)
+    const int occC = P.opt.tuneBlocksPerSM ? P.opt.tuneBlocksPerSM : MCB_COLS_OCC;
+    const bool splitC = P.opt.tuneBurst ? P.opt.tuneBurst == 44 : MCB_COLS_SPLIT;
+    if (occC >= 7) { if (splitC) MCB_POOL_COLS(7, true); else MCB_POOL_COLS(7, false); }
+    else { if (splitC) MCB_POOL_COLS(6, true); else MCB_POOL_COLS(6, false); }
+#undef MCB_POOL_COLS
+    return;
+  }
   if (occ >= 8) { if (burst == 44) MCB_POOL_LAYOUT(8, 8, true); else MCB_POOL_LAYOUT(8, 8, false); }
   else if (occ == 7) { if (burst == 44) MCB_POOL_LAYOUT(7, 8, true); else MCB_POOL_LAYOUT(7, 8, false); }
   else { if (burst == 4) MCB_POOL_LAYOUT(6, 4, false); else if (burst == 44) MCB_POOL_LAYOUT(6, 8, true); else MCB_POOL_LAYOUT(6, 8, false); }

@@ -106,6 +106,69 @@ __global__ void layer_tables_kernel(const float *__restrict__ layerExt, int nz, 
   }
 }
 
+// ---- column-compressed storage (mcb_device.cuh): ranges, offsets, compact arrays, padded column table ----
+// per column the first and one-past-the-last layer whose extinction differs from the layer's clear-sky value
+__global__ void col_range_kernel(const double *__restrict__ totalExt, const float *__restrict__ layerExt, int cols, int nz, int G,
+                                 uint32_t *__restrict__ range, int *__restrict__ count) {
+  for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < cols; c += gridDim.x * blockDim.x) {
+    int lo = nz, hi = 0;
+    for (int k = 0; k < nz; ++k)
+      if ((float)totalExt[c + (long long)cols * k] != fabsf(layerExt[k + G])) { lo = min(lo, k); hi = k + 1; }
+    if (hi == 0) lo = 0;
+    range[c] = (uint32_t)lo | ((uint32_t)hi << 16);
+    count[c] = hi - lo;
+  }
+}
+// exclusive prefix sum of count[0..n) in one block (n ~ 1e5: a few hundred microseconds, once per staging); total -> *sum
+__global__ void col_scan_kernel(const int *__restrict__ count, int n, int *__restrict__ offset, int *sum) {
+  __shared__ int part[1024];
+  __shared__ int carry;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  for (int base = 0; base < n; base += 1024) {
+    const int i = base + threadIdx.x;
+    const int v = i < n ? count[i] : 0;
+    part[threadIdx.x] = v;
+    __syncthreads();
+    for (int o = 1; o < 1024; o <<= 1) {                       // Hillis-Steele inclusive scan
+      const int t = (int)threadIdx.x >= o ? part[threadIdx.x - o] : 0;
+      __syncthreads();
+      part[threadIdx.x] += t;
+      __syncthreads();
+    }
+    if (i < n) offset[i] = carry + part[threadIdx.x] - v;
+    __syncthreads();
+    if (threadIdx.x == 1023) carry += part[1023];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *sum = carry;
+}
+// the cells inside the ranges: extinction, event record, cell index, column by column
+__global__ void col_fill_kernel(const double *__restrict__ totalExt, const uint32_t *__restrict__ rec, int recShift,
+                                const uint32_t *__restrict__ range, const int *__restrict__ offset, int cols, long long cells,
+                                float *__restrict__ extC, uint32_t *__restrict__ recC, uint32_t *__restrict__ cellC) {
+  for (long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x; p < cells; p += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(p % cols), k = (int)(p / cols);
+    const uint32_t rg = range[c];
+    const int lo = (int)(rg & 0xffffu), hi = (int)(rg >> 16);
+    if (k < lo || k >= hi) continue;
+    const long long i = (long long)offset[c] + (k - lo);
+    extC[i] = (float)totalExt[p];
+    cellC[i] = (uint32_t)p;
+    for (int w = 0; w < (1 << recShift); ++w) recC[(i << recShift) + w] = rec[(p << recShift) + w];
+  }
+}
+// the column table in the padded x-fastest column space (periodic replicas in the ghost shell)
+__global__ void col_table_kernel(const uint32_t *__restrict__ range, const int *__restrict__ offset, int nx, int ny, int G,
+                                 int nxp, int nyp, uint2 *__restrict__ colTab) {
+  for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < nxp * nyp; p += gridDim.x * blockDim.x) {
+    int mx = (p % nxp - G) % nx; mx += mx < 0 ? nx : 0;
+    int my = (p / nxp - G) % ny; my += my < 0 ? ny : 0;
+    const int c = mx + nx * my;
+    colTab[p] = make_uint2((uint32_t)offset[c], range[c]);
+  }
+}
+
 // occupancy bitmap of the padded field: bit p set where e32[p] differs from its layer's clear-sky value.
 // One warp builds one 32-bit word per iteration with a ballot (coalesced read, one store per warp).
 __global__ void occupancy_mask_kernel(const float *__restrict__ e32, const float *__restrict__ layerExt, long long total,
@@ -879,6 +942,24 @@ void mcb_launch_pack_field(const DevDomain &P, int brick, float *ext, uint32_t *
     mcbstage::occupancy_mask_kernel<<<stream_grid(F.padded, 256, numSMs), 256, 0, stream>>>(ext, layerExt, F.padded,
                                                                                             F.nxp * F.nyp, mask, brick);
   }
+}
+
+// column-compressed storage, step 1: ranges, per-column counts, offsets and the total (-> *sum, read by the host, which
+// sizes the compact arrays); layerExt must have been built (mcb_launch_pack_field with a mask)
+void mcb_launch_column_ranges(const DevDomain &P, uint32_t *range, int *count, int *offset, int *sum, int numSMs, cudaStream_t stream) {
+  const int cols = P.nx * P.ny;
+  mcbstage::col_range_kernel<<<stream_grid(cols, 128, numSMs), 128, 0, stream>>>(P.totalExt, P.layerExt, cols, P.nz, MCB_GHOST, range, count);
+  mcbstage::col_scan_kernel<<<1, 1024, 0, stream>>>(count, cols, offset, sum);
+}
+// step 2: the compact arrays and the padded column table
+void mcb_launch_column_fill(const DevDomain &P, const uint32_t *range, const int *offset, float *extC, uint32_t *recC,
+                            uint32_t *cellC, uint2 *colTab, int numSMs, cudaStream_t stream) {
+  const int cols = P.nx * P.ny;
+  const long long cells = (long long)cols * P.nz;
+  mcbstage::col_fill_kernel<<<stream_grid(cells, 256, numSMs), 256, 0, stream>>>(P.totalExt, P.rec, P.recShift, range, offset, cols,
+                                                                              cells, extC, recC, cellC);
+  mcbstage::col_table_kernel<<<stream_grid((long long)P.lin.nxp * P.lin.nyp, 256, numSMs), 256, 0, stream>>>(
+      range, offset, P.nx, P.ny, MCB_GHOST, P.lin.nxp, P.lin.nyp, colTab);
 }
 
 // the vacuum-distance map of the staged domain: dist[cells] (result) and scratch[cells]

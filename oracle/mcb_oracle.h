@@ -9,7 +9,11 @@
  *
  * PARITY STATUS: "parity unpinned".  The reference ships no tests, golden
  * vectors or fixtures for this path and cannot be
- * compiled in this image (no Fortran compiler, MPI or netCDF).  What IS pinned:
+ * compiled in this image nor on the GPU box (no Fortran front end on either:
+ * profiles/r02_compiler_probe_gpu_box.log).  oracle/ref_build/ holds the recipe
+ * that compiles the UNMODIFIED reference sources into oracle/_ref and turns its
+ * per-photon output into tests/golden/ref_trace_*.npz; tests/test_ref_fixtures.py
+ * is the pin once those fixtures exist.  What IS pinned until then:
  *   - the RNG against the published MT19937 known-answer vectors
  *     (RandomNumbersForMC.f95:8-10 declares identity with mt19937ar-cok.c);
  *   - physical invariants (energy closure, Beer's law direct beam, isothermal
