@@ -24,6 +24,7 @@ void mcb_launch_philox_kat(uint64_t seed, uint64_t photon, int n, uint32_t *out,
 double mcb_run_gather_probe(size_t bytes, int inFlight, int blocksPerSM, int iterations, int numSMs, cudaStream_t stream);
 // mcb_stage.cu: device-side packing / validation, normalisation, emission CDF
 void mcb_launch_distance_map(const DevDomain &P, int cap, uint8_t *dist, uint8_t *scratch, int *leapCount, int numSMs, cudaStream_t stream);
+void mcb_launch_pack_crop(const DevDomain &P, float *ext, int numSMs, cudaStream_t stream);
 void mcb_launch_column_ranges(const DevDomain &P, uint32_t *range, int *count, int *offset, int *sum, int numSMs, cudaStream_t stream);
 void mcb_launch_column_fill(const DevDomain &P, const uint32_t *range, const int *offset, float *extC, uint32_t *recC,
                             uint32_t *cellC, uint2 *colTab, int numSMs, cudaStream_t stream);
@@ -83,7 +84,7 @@ struct mcb_handle {
   void *dExtMask = nullptr, *dExtMaskBrick = nullptr, *dLayerExt = nullptr;     // occupancy bitmap of fields too large for L2
   void *dDist = nullptr, *dDistScratch = nullptr;   // vacuum-distance map (u8 per cell) the packed fields are encoded with
   void *dColRange = nullptr, *dColCount = nullptr, *dColOffset = nullptr, *dColTab = nullptr;   // column-compressed storage
-  void *dExtC = nullptr, *dRecC = nullptr, *dCellC = nullptr;
+  void *dExtC = nullptr, *dRecC = nullptr, *dCellC = nullptr, *dExtCrop = nullptr, *dTallyC = nullptr;
   void *dInv[MCB_MAX_COMP] = {nullptr}, *dFwd[MCB_MAX_COMP] = {nullptr}, *dFwdOrig[MCB_MAX_COMP] = {nullptr};
   int invE[MCB_MAX_COMP] = {0}, fwdE[MCB_MAX_COMP] = {0};
   void *dColCDF = nullptr, *dVoxelCDF = nullptr, *dTemps = nullptr, *dScratch = nullptr, *dResults = nullptr;
@@ -222,7 +223,7 @@ int mcb_destroy(mcb_handle *h) {
                    h->dTemps, h->dScratch, h->dResults, (void *)h->dFlags, h->dStats, h->dStatsOut,
                    h->dMassConc, h->dReff, h->dNumConc, h->dAsmTables, h->dExtMask, h->dLayerExt,
                    h->dExtBrick, h->dExtMaskBrick, h->dColCDF, h->dDist, h->dDistScratch,
-                   h->dColRange, h->dColCount, h->dColOffset, h->dColTab, h->dExtC, h->dRecC, h->dCellC};
+                   h->dColRange, h->dColCount, h->dColOffset, h->dColTab, h->dExtC, h->dRecC, h->dCellC, h->dExtCrop, h->dTallyC};
   for (void *p : slots) if (p) cudaFree(p);
   for (int c = 0; c < MCB_MAX_COMP; ++c) {
     if (h->dInv[c]) cudaFree(h->dInv[c]);
@@ -458,7 +459,8 @@ static int finish_optics(mcb_handle *h, int nc, double albedo, bool zeroFlags) {
   CK(h, cudaGetLastError());
   // Column-compressed storage for the pool flux kernel (fields marched through the bitmap, i.e. too large for L2): the
   // cells inside the per-column ranges -- extinction, event record, cell index -- densely, column by column.
-  P.colTab = nullptr; P.extC = nullptr; P.recC = nullptr; P.cellC = nullptr; P.nCompact = 0;
+  P.colTab = nullptr; P.extC = nullptr; P.recC = nullptr; P.cellC = nullptr; P.nCompact = 0; P.tallyC = nullptr;
+  P.crp.ext = nullptr; P.cropLo = 0; P.cropN = 0;
   if (P.lin.mask && P.uniform && P.nx >= MCB_GHOST && P.ny >= MCB_GHOST && P.nz <= 65535) {
     const size_t cols = (size_t)P.nx * P.ny;
     if (reserve(h, &h->dColRange, sizeof(uint32_t) * cols) || reserve(h, &h->dColCount, sizeof(int) * cols) ||
@@ -472,13 +474,36 @@ static int finish_optics(mcb_handle *h, int nc, double albedo, bool zeroFlags) {
     if (settle(h)) return 1;
     const size_t n = nCompact > 0 ? (size_t)nCompact : 1;
     if (reserve(h, &h->dExtC, sizeof(float) * n) || reserve(h, &h->dRecC, sizeof(uint32_t) * (n << recShift)) ||
-        reserve(h, &h->dCellC, sizeof(uint32_t) * n))
+        reserve(h, &h->dCellC, sizeof(uint32_t) * n) || reserve(h, &h->dTallyC, sizeof(double) * n))
       return 1;
+    CK(h, cudaMemsetAsync(h->dTallyC, 0, sizeof(double) * n, h->stream));
     mcb_launch_column_fill(P, (const uint32_t *)h->dColRange, (const int *)h->dColOffset, (float *)h->dExtC, (uint32_t *)h->dRecC,
                            (uint32_t *)h->dCellC, (uint2 *)h->dColTab, h->numSMs, h->stream);
     CK(h, cudaGetLastError());
     P.colTab = (const uint2 *)h->dColTab; P.extC = (const float *)h->dExtC; P.recC = (const uint32_t *)h->dRecC;
-    P.cellC = (const uint32_t *)h->dCellC; P.nCompact = nCompact;
+    P.cellC = (const uint32_t *)h->dCellC; P.nCompact = nCompact; P.tallyC = (double *)h->dTallyC;
+    // The layer-cropped field: the band of layers that hold cloud somewhere (the sign bits of layerExt mark the layers
+    // that are clear throughout), bricked, if it is small enough to stay in L2 (same 48 MB limit as the bitmap decision).
+    std::vector<float> layer((size_t)P.nz + 2 * MCB_GHOST);
+    CK(h, cudaMemcpyAsync(layer.data(), P.layerExt, sizeof(float) * layer.size(), cudaMemcpyDeviceToHost, h->stream));
+    if (settle(h)) return 1;
+    int lo = P.nz, hi = 0;
+    for (int k = 0; k < P.nz; ++k) if (!std::signbit(layer[(size_t)k + MCB_GHOST])) { lo = lo < k ? lo : k; hi = k + 1; }
+    if (hi > lo) {
+      lo &= ~1; hi = (hi + 1) & ~1;
+      DevDomain::ExtField &F = P.crp;
+      F = P.brk;                                               // same padded row / slice geometry and divisors
+      F.mask = nullptr; F.ext = nullptr;
+      F.padded = (long long)F.nxp * F.nyp * (hi - lo);
+      F.origin = (int)mcb_brick_address(MCB_GHOST, MCB_GHOST, 0, F.nxp / 2, F.nyp / 2);
+      if (sizeof(float) * (size_t)F.padded <= ((size_t)48 << 20)) {
+        if (reserve(h, &h->dExtCrop, sizeof(float) * (size_t)F.padded)) return 1;
+        P.cropLo = lo; P.cropN = hi - lo;
+        mcb_launch_pack_crop(P, (float *)h->dExtCrop, h->numSMs, h->stream);
+        CK(h, cudaGetLastError());
+        F.ext = (const float *)h->dExtCrop + F.origin;
+      }
+    }
   }
   int flags4[4] = {0, 0, 0, 0};
   CK(h, cudaMemcpyAsync(flags4, h->dFlags, sizeof(flags4), cudaMemcpyDeviceToHost, h->stream));

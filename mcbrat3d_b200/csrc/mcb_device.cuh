@@ -59,7 +59,11 @@ struct DevDomain {
     uint32_t divSliceM, divRowM;              // address -> (ix,iy,iz): q = (M * n) >> S, exact for n < 2^31
     int divSliceS, divRowS;
     long long padded;                         // number of padded cells
-  } lin, brk;
+  } lin, brk, crp;
+  // crp: fields too large for L2 whose cloud occupies a band of layers -- the bricked field of the layers
+  // [cropLo, cropLo + cropN) only (both even; periodic ghost shell in x and y, none in z), small enough to stay in L2.
+  // Outside the band every layer is clear throughout and the marcher takes layerExt.  ext == nullptr: not built.
+  int cropLo, cropN;
   const float *layerExt;                      // nz + 2G (+2) clear-sky values; sign bit set: the WHOLE layer has this value
                                               // (no bitmap look-up needed there)
   int leap;                                   // the packed fields carry the vacuum distances / the layer tables below are
@@ -67,16 +71,17 @@ struct DevDomain {
   const float *layerLeap;                     // nz + 2G (+2): minus the distance, in layers, to the nearest layer that is not
                                               // clear throughout (0 for such a layer): march_leap crosses that many at once
   const float *layerCum;                      // nz + 1: clear-sky optical depth per unit |1/mu| from the surface to each edge
-  // Column-compressed storage (photon-pool flux kernel on fields too large for L2, built next to the bitmap): per padded
-  // column the range of layers [lo, hi) outside which every cell has its layer's clear-sky value, and for the cells
-  // inside the ranges -- a few per cent of a cloud scene, small enough to stay in L2 -- the extinction, the event record
-  // and the cell they belong to, stored densely column by column.  A crossing then costs one 8-byte look-up in a table
-  // of a few hundred KB (L1 / L2) plus, inside the range only, one gather that L2 serves: the 78 MB field and its
-  // 253 MB of event records (C5) are not touched at all.
+  // Column-compressed event records (photon-pool flux kernel on fields too large for L2): per padded column the range
+  // of layers [lo, hi) outside which every cell has its layer's clear-sky value, and for the cells inside the ranges --
+  // a few per cent of a cloud scene -- the event record (and the extinction and the cell index), stored densely column by
+  // column: 35 MB instead of 253 MB on C5, so the records of the scattering cells stay in L2 next to the cropped field.
+  // (Measured, r02: marching on this storage as well -- one table look-up per crossing, then the gather -- was 5 % SLOWER
+  // than the bitmap: what bounds C5 is the dependent look-up -> gather chain of a crossing, not where the gather is served.)
   const uint2 *colTab;                        // lin.nxp x lin.nyp: .x = compact index of layer lo, .y = lo | hi << 16
   const float *extC;                          // nCompact: (float)totalExt
   const uint32_t *recC;                       // nCompact << recShift: the cells' event records
   const uint32_t *cellC;                      // nCompact: ix + nx * (iy + ny * iz)
+  double *tallyC;                             // nCompact: volume-absorption tally of those cells (added into tally after a launch)
   long long nCompact;
   uint32_t divColsM, divNxM; int divColsS, divNxS;   // unpadded cell -> (ix, iy, iz): division by nx * ny and by nx
   // one record per cell with everything a scattering event reads, so an event costs ONE gather (a 32 B sector for

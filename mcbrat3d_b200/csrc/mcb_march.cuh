@@ -128,8 +128,13 @@ __device__ __forceinline__ int wrap_index(int i, int n) {
 // launch-invariant divisors with the precomputed multipliers of the parameter block (exact for every
 // padded cell index < 2^31); x, y come back folded into the domain.
 template <bool WIDE, bool BRICK>
+__device__ __forceinline__ void cell_decode(const DevDomain &P, const DevDomain::ExtField &F, int rel, int &ix, int &iy, int &iz);
+template <bool WIDE, bool BRICK>
 __device__ __forceinline__ void cell_decode(const DevDomain &P, int rel, int &ix, int &iy, int &iz) {
-  const DevDomain::ExtField &F = BRICK ? P.brk : P.lin;
+  cell_decode<WIDE, BRICK>(P, BRICK ? P.brk : P.lin, rel, ix, iy, iz);
+}
+template <bool WIDE, bool BRICK>
+__device__ __forceinline__ void cell_decode(const DevDomain &P, const DevDomain::ExtField &F, int rel, int &ix, int &iy, int &iz) {
   const uint32_t c = (uint32_t)(rel + F.origin);
   if (BRICK) {
     const uint32_t b = c >> 3;                                                  // brick; the low three bits are (z, y, x) inside it
@@ -199,14 +204,15 @@ enum { MARCH_ON = ST_MARCH, MARCH_HIT = ST_SCATTER, MARCH_BOTTOM = ST_SURFACE, M
 // the ray is in now (the last gathered value + 1: D changes by at most 1 between neighbours) -- march_leap's input.
 // ENC = false (pool kernels on a domain that was staged without the encoding, DevDomain::leap == 0): no clamp.
 //
-// COLS (pool flux kernel, fields too large for L2; MASK = BRICK = false): column-compressed storage (mcb_device.cuh).
-// The geometry loop looks the cell's column up -- one 8-byte entry of a table that L1 / L2 hold -- and the gather goes
-// to the compact array, only for cells inside the column's range; a hit hands back the compact index (-1: a clear cell).
-template <bool REG, bool WIDE, int B, bool MASK, bool BRICK, bool RAW = false, bool SPLIT = false, bool ENC = true, bool COLS = false>
+// CROP (pool flux kernel, fields too large for L2; BRICK, no MASK): the layer-cropped field P.crp (mcb_device.cuh).  A
+// cell inside the cropped layers is gathered from it like any cell of an L2-resident field -- address by arithmetic, ONE
+// round trip per burst; a cell outside takes its layer's clear-sky value from the (L1-resident) layer table, and the two
+// loads do not depend on each other.  A hit outside the crop hands back INT_MIN instead of an address.
+template <bool REG, bool WIDE, int B, bool MASK, bool BRICK, bool RAW = false, bool SPLIT = false, bool ENC = true, bool CROP = false>
 __device__ __forceinline__ int march_burst(Ray &r, const DevDomain &P, const Grid &G,
                                            float &ext, float target, unsigned &crossings, float *vlast = nullptr) {
-  static_assert(!COLS || (RAW && REG && !MASK && !BRICK), "column-compressed storage: pool flux kernel on uniform grids");
-  const DevDomain::ExtField &F = BRICK ? P.brk : P.lin;
+  static_assert(!CROP || (RAW && REG && !MASK && BRICK), "layer-cropped field: pool flux kernel on uniform grids, bricked");
+  const DevDomain::ExtField &F = CROP ? P.crp : BRICK ? P.brk : P.lin;
   float tE[B], sg[B];
   int ck[B];
   uint32_t mw[MASK ? B : 1];
@@ -214,21 +220,17 @@ __device__ __forceinline__ int march_burst(Ray &r, const DevDomain &P, const Gri
   const int sx = r.dx >= 0.0f ? 1 : -1, sy = r.dy >= 0.0f ? 1 : -1, sz = r.dz >= 0.0f ? 1 : -1;
   int a = 0, dax = 0, day = 0, daz = 0, SX = 0, SY = 0, SZ = 0;
   if (BRICK) {
-    a = brick_rel(F, r.ix, r.iy, r.iz);
+    a = brick_rel(F, r.ix, r.iy, CROP ? r.iz - P.cropLo : r.iz);          // (cropLo is even: parities carry over)
     SX = 8 * sx; SY = 2 * F.cY * sy; SZ = 2 * F.cZ * sz;
     dax = brick_step(r.ix & 1, sx, 1, 8); day = brick_step(r.iy & 1, sy, 2, 2 * F.cY); daz = brick_step(r.iz & 1, sz, 4, 2 * F.cZ);
   }
 #pragma unroll
   for (int k = 0; k < B; ++k) {
     const float tmin = fminf(fminf(r.tx, r.ty), r.tz);
-    if (COLS) {
-      const float lv = __ldg(P.layerExt + MCB_CHECK_INDEX(P, r.iz + GH, P.nz + 2 * GH));
-      const uint2 ct = __ldg(P.colTab + MCB_CHECK_INDEX(P, (r.ix + GH) + F.nxp * (r.iy + GH), F.nxp * F.nyp));
-      const unsigned lo = ct.y & 0xffffu, rel = (unsigned)r.iz - lo;           // (ghost layers: rel wraps to a huge number)
-      sg[k] = fabsf(lv);
-      ck[k] = rel < (ct.y >> 16) - lo ? (int)(ct.x + rel) : -1;
-    } else {
-      ck[k] = BRICK ? a : r.ix + F.nxp * (r.iy + F.nyp * r.iz);
+    ck[k] = BRICK ? a : r.ix + F.nxp * (r.iy + F.nyp * r.iz);
+    if (CROP && (unsigned)(r.iz - P.cropLo) >= (unsigned)P.cropN) {           // outside the cropped layers: clear sky
+      ck[k] = INT_MIN;
+      sg[k] = fabsf(__ldg(P.layerExt + MCB_CHECK_INDEX(P, r.iz + GH, P.nz + 2 * GH)));
     }
     tE[k] = tmin;
     if (MASK) {
@@ -274,8 +276,8 @@ __device__ __forceinline__ int march_burst(Ray &r, const DevDomain &P, const Gri
   constexpr int H = SPLIT ? B / 2 : B;                 // gathers issued up front
 #pragma unroll
   for (int k = 0; k < H; ++k) {
-    if (COLS) {
-      if (ck[k] >= 0) sg[k] = __ldg(P.extC + MCB_CHECK_INDEX(P, ck[k], P.nCompact));
+    if (CROP) {
+      if (ck[k] != INT_MIN) sg[k] = EXT_AT(P, F, ck[k]);
     } else if (MASK) {                                 // bit p of the bitmap: the shift count wraps modulo 32
       if (__funnelshift_r(mw[k], 0u, (uint32_t)(ck[k] + F.origin)) & 1u) sg[k] = EXT_AT(P, F, ck[k]);
     } else {
@@ -287,8 +289,8 @@ __device__ __forceinline__ int march_burst(Ray &r, const DevDomain &P, const Gri
     if (SPLIT && k == H) {                             // second half: only where the first half did not reach the target
 #pragma unroll
       for (int j = H; j < B; ++j) {
-        if (COLS) {
-          if (!found && ck[j] >= 0) sg[j] = __ldg(P.extC + MCB_CHECK_INDEX(P, ck[j], P.nCompact));
+        if (CROP) {
+          if (ck[j] != INT_MIN) { sg[j] = 0.0f; if (!found) sg[j] = EXT_AT(P, F, ck[j]); }
         } else if (MASK) {
           if (!found && (__funnelshift_r(mw[j], 0u, (uint32_t)(ck[j] + F.origin)) & 1u)) sg[j] = EXT_AT(P, F, ck[j]);
         } else {
@@ -300,7 +302,7 @@ __device__ __forceinline__ int march_burst(Ray &r, const DevDomain &P, const Gri
 #ifdef MCB_NO_LEAP                                            // A/B build without vacuum leaps (make variant FLAGS=-DMCB_NO_LEAP)
     const float sk = sg[k];
 #else
-    const float sk = (MASK || COLS || !ENC) ? sg[k] : fmaxf(sg[k], 0.0f);       // vacuum cells hold -D
+    const float sk = (MASK || CROP || !ENC) ? sg[k] : fmaxf(sg[k], 0.0f);       // vacuum cells hold -D
 #endif
     const float en = fmaf(tE[k] - tS, sk, acc);
     const bool h = !found && en > target;
@@ -338,7 +340,7 @@ __device__ __forceinline__ int march_burst(Ray &r, const DevDomain &P, const Gri
   }
   crossings += (unsigned)B;
   r.t = tS;
-  if (vlast) *vlast = (MASK || COLS) ? __ldg(P.layerLeap + r.iz + GH) : sg[B - 1] + 1.0f;
+  if (vlast) *vlast = (MASK || CROP) ? __ldg(P.layerLeap + r.iz + GH) : sg[B - 1] + 1.0f;
   if (REG) {
     r.ix = wrap_index<WIDE>(r.ix, P.nx);
     r.iy = wrap_index<WIDE>(r.iy, P.ny);

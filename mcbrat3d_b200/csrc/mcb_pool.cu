@@ -32,11 +32,12 @@
 // the same order per photon), so their tallies agree to summation order -- tests/test_gpu_pool.py.
 #include "mcb_march.cuh"
 
-#ifndef MCB_COLS_OCC
-#define MCB_COLS_OCC 6            // column-compressed variant: CTAs per SM and split gathers by default
+#ifndef MCB_CROP_OCC
+#define MCB_CROP_OCC 6            // layer-cropped variant: 80 registers (C5, r02: 6 CTAs/SM 4.86e8, 7 CTAs/SM with spills 4.30e8),
+                                  // gathers in two halves as on the other L2-resident fields (4.86e8 vs 4.78e8)
 #endif
-#ifndef MCB_COLS_SPLIT
-#define MCB_COLS_SPLIT false
+#ifndef MCB_CROP_SPLIT
+#define MCB_CROP_SPLIT true
 #endif
 
 namespace mcbpool {
@@ -50,7 +51,7 @@ using namespace mcbfast;
 enum { PW_PX = 0, PW_PY, PW_PZ, PW_DX, PW_DY, PW_DZ, PW_W, PW_TAU, PW_UNEXT, PW_C0, PW_C1, PW_BLK, PW_IXY, PW_IZK,
        PW_TX, PW_TY, PW_TZ };
 
-template <int THREADS, int MINBLOCKS, int BURST, bool SPLIT, bool MASK, bool BRICK, bool LEAP, bool COLS>
+template <int THREADS, int MINBLOCKS, int BURST, bool SPLIT, bool MASK, bool BRICK, bool LEAP, bool CROP>
 __global__ void __launch_bounds__(THREADS, MINBLOCKS)
 pool_kernel(const __grid_constant__ DevDomain P, long long nPhotons, uint64_t seed, uint64_t firstPhotonId,
             unsigned long long *workCounter, const SmemPlan plan, const float leapBelow, const int leapLanes) {
@@ -118,14 +119,12 @@ pool_kernel(const __grid_constant__ DevDomain P, long long nPhotons, uint64_t se
           px = fmaf(t, dx, px); py = fmaf(t, dy, py); pz = fmaf(t, dz, pz);
           px -= P.fLx * floorf((px - P.fx0) * P.finvLx);
           py -= P.fLy * floorf((py - P.fy0) * P.finvLy);
-          if (state == ST_SCATTER && COLS) {
-            // column-compressed storage: the compact index knows its cell; an event in a clear cell (raw < 0: molecular
-            // scattering between the clouds) is located by its position
-            if (raw >= 0) {
-              const uint32_t c = __ldg(P.cellC + MCB_CHECK_INDEX(P, raw, P.nCompact));
-              const uint32_t z = (uint32_t)(((uint64_t)P.divColsM * c) >> P.divColsS), rem = c - z * (uint32_t)cols;
-              const uint32_t y = (uint32_t)(((uint64_t)P.divNxM * rem) >> P.divNxS);
-              ix = (int)(rem - y * (uint32_t)P.nx); iy = (int)y; iz = (int)z;
+          if (state == ST_SCATTER && CROP) {
+            // layer-cropped field: the address knows its cell; an event outside the cropped layers (raw = INT_MIN:
+            // molecular scattering in a layer that is clear throughout) is located by its position
+            if (raw != INT_MIN) {
+              cell_decode<true, true>(P, P.crp, raw, ix, iy, iz);
+              iz += GH + P.cropLo;                             // (the cropped field has no ghost layers)
             } else {
               ix = min(max((int)((px - P.fx0) * P.finvhx), 0), P.nx - 1);
               iy = min(max((int)((py - P.fy0) * P.finvhy), 0), P.ny - 1);
@@ -157,10 +156,18 @@ pool_kernel(const __grid_constant__ DevDomain P, long long nPhotons, uint64_t se
       } else if (state == ST_SCATTER) {                                          // INT:703-811
         scatters++;
         const int cell = ix + P.nx * (iy + P.ny * iz);
+        int ci = -1;                                     // CROP: the cell's index in the column-compressed arrays
         float lo = 0.0f, hi = 1.0f, ssa;
         {                                                                        // the cell's event record: ONE gather
-          const uint32_t *R = (COLS && raw >= 0) ? P.recC + ((size_t)MCB_CHECK_INDEX(P, raw, P.nCompact) << P.recShift)
-                                                 : P.rec + ((size_t)MCB_CHECK_INDEX(P, cell, cells) << P.recShift);
+          const uint32_t *R = P.rec + ((size_t)MCB_CHECK_INDEX(P, cell, cells) << P.recShift);
+          if (CROP) {                                // the column-compressed copy of the records (stays in L2)
+            const uint2 ct = __ldg(P.colTab + MCB_CHECK_INDEX(P, (ix + GH) + P.lin.nxp * (iy + GH), P.lin.nxp * P.lin.nyp));
+            const unsigned lo = ct.y & 0xffffu, rel = (unsigned)iz - lo;
+            if (rel < (ct.y >> 16) - lo) {
+              ci = (int)MCB_CHECK_INDEX(P, ct.x + rel, P.nCompact);
+              R = P.recC + ((size_t)ci << P.recShift);
+            }
+          }
           if (P.nc == 1) {
             const uint2 v = __ldg(reinterpret_cast<const uint2 *>(R));
             ssa = __uint_as_float(v.x); pidx = (int)(v.y & 0xffffu);
@@ -182,7 +189,11 @@ pool_kernel(const __grid_constant__ DevDomain P, long long nPhotons, uint64_t se
         }
         pidx = max(pidx, 1);                   // entry 0 marks a cell the component is absent from: never index before the table
         if (ssa < 1.0f) {                                                        // INT:765-771
-          add_vol(P, T, cell, ew * (1.0f - ssa));          // fluxAbsorbed = column sum of this tally (column_absorption_kernel)
+          // fluxAbsorbed = column sum of this tally (column_absorption_kernel).  CROP: the absorbing cells are the cells of
+          // the column ranges, and their f64 tally lives in the compact array too (18 MB on C5, L2-resident; the dense
+          // 127 MB array drew 10 GB of DRAM traffic per 1e7 photons and pushed the field out of L2): expanded after the launch
+          if (CROP && ci >= 0) atomicAdd(&P.tallyC[ci], (double)(ew * (1.0f - ssa)));
+          else add_vol(P, T, cell, ew * (1.0f - ssa));
           ew *= ssa;
         }
         if (P.opt.useRussianRoulette && ew < P.opt.russianRouletteW * 0.5f) {    // INT:805-811
@@ -339,10 +350,10 @@ pool_kernel(const __grid_constant__ DevDomain P, long long nPhotons, uint64_t se
     if (LEAP) {
       int D = have ? leap_distance(r, P, vcur, leapBelow) : 0;
       if (leapLanes > 1 && __popc(__ballot_sync(FULL, D > 0)) < leapLanes) D = 0;   // too few lanes to pay for the divergence
-      if (D) ev = march_leap<MASK || COLS>(r, P, D, crossings, ext, tau, &sCnt[4]); // (implies have)
+      if (D) ev = march_leap<MASK || CROP>(r, P, D, crossings, ext, tau, &sCnt[4]); // (implies have)
     }
     if (have && ev == MARCH_ON)
-      ev = march_burst<true, true, BURST, MASK, BRICK, true, SPLIT, LEAP, COLS>(r, P, G, ext, tau, crossings, LEAP ? &vcur : nullptr);
+      ev = march_burst<true, true, BURST, MASK, BRICK, true, SPLIT, LEAP, CROP>(r, P, G, ext, tau, crossings, LEAP ? &vcur : nullptr);
 
     // =========================== photons that reached an event go onto EVENT ===========================
     {
@@ -403,11 +414,11 @@ pool_kernel(const __grid_constant__ DevDomain P, long long nPhotons, uint64_t se
 
 }  // namespace mcbpool
 
-template <int MINBLOCKS, int BURST, bool SPLIT, bool MASK, bool BRICK, bool LEAP, bool COLS = false>
+template <int MINBLOCKS, int BURST, bool SPLIT, bool MASK, bool BRICK, bool LEAP, bool CROP = false>
 static void launch_pool(const DevDomain &P, long long nPhotons, uint64_t seed, uint64_t firstPhotonId, int numSMs,
                         unsigned long long *workCounter, cudaStream_t stream) {
   constexpr int THREADS = 128;
-  auto kernel = mcbpool::pool_kernel<THREADS, MINBLOCKS, BURST, SPLIT, MASK, BRICK, LEAP, COLS>;
+  auto kernel = mcbpool::pool_kernel<THREADS, MINBLOCKS, BURST, SPLIT, MASK, BRICK, LEAP, CROP>;
   const int cols = P.nx * P.ny, cells = cols * P.nz;
   mcbfast::SmemPlan plan{-1, -1, -1, -1, -1, 0, 0, 0};
   int off = 0;
@@ -430,6 +441,8 @@ static void launch_pool(const DevDomain &P, long long nPhotons, uint64_t seed, u
   const float leapBelow = P.opt.tuneLeap < 0 ? -FLT_MAX : -(float)(P.opt.tuneLeap >= 2 ? P.opt.tuneLeap : MCB_LEAP_MIN);
   kernel<<<blocks, THREADS, smem, stream>>>(P, nPhotons, seed, firstPhotonId, workCounter, plan, leapBelow, P.opt.tuneLeapLanes > 0 ? P.opt.tuneLeapLanes : MCB_LEAP_LANES);
 }
+
+void mcb_launch_expand_compact_tally(const DevDomain &P, int numSMs, cudaStream_t stream);     // mcb_stage.cu
 
 // the pool kernel covers flux-only runs on uniform grids at least a ghost shell wide
 bool mcb_pool_covers(const DevDomain &P) {
@@ -464,16 +477,18 @@ void mcb_launch_pool_batch(const DevDomain &P, long long nPhotons, uint64_t seed
 #define MCB_POOL_LAYOUT(OCC, B, SPLIT) \
   do { if (mask) { if (brick) MCB_POOL_GO(OCC, B, SPLIT, true, true); else MCB_POOL_GO(OCC, B, SPLIT, true, false); } \
        else { if (brick) MCB_POOL_GO(OCC, B, SPLIT, false, true); else MCB_POOL_GO(OCC, B, SPLIT, false, false); } } while (0)
-  // column-compressed storage instead of the bitmap (fields too large for L2; tuneExtMask = 1 keeps the bitmap)
-  if (mask && P.colTab && P.opt.tuneExtMask != 1) {
-#define MCB_POOL_COLS(OCC, SPLIT) \
-  do { if (P.leap) launch_pool<OCC, 8, SPLIT, false, false, true, true>(P, nPhotons, seed, firstPhotonId, numSMs, workCounter, stream); \
-       else launch_pool<OCC, 8, SPLIT, false, false, false, true>(P, nPhotons, seed, firstPhotonId, numSMs, workCounter, stream); } while (0)
-    const int occC = P.opt.tuneBlocksPerSM ? P.opt.tuneBlocksPerSM : MCB_COLS_OCC;
-    const bool splitC = P.opt.tuneBurst ? P.opt.tuneBurst == 44 : MCB_COLS_SPLIT;
-    if (occC >= 7) { if (splitC) MCB_POOL_COLS(7, true); else MCB_POOL_COLS(7, false); }
-    else { if (splitC) MCB_POOL_COLS(6, true); else MCB_POOL_COLS(6, false); }
-#undef MCB_POOL_COLS
+  // the layer-cropped field instead of the bitmap (fields too large for L2 whose cloud band fits; tuneExtMask = 1 keeps
+  // the bitmap)
+  if (mask && P.crp.ext && P.colTab && P.opt.tuneExtMask != 1) {
+#define MCB_POOL_CROP(OCC, SPLIT) \
+  do { if (P.leap) launch_pool<OCC, 8, SPLIT, false, true, true, true>(P, nPhotons, seed, firstPhotonId, numSMs, workCounter, stream); \
+       else launch_pool<OCC, 8, SPLIT, false, true, false, true>(P, nPhotons, seed, firstPhotonId, numSMs, workCounter, stream); } while (0)
+    const int occC = P.opt.tuneBlocksPerSM ? P.opt.tuneBlocksPerSM : MCB_CROP_OCC;
+    const bool splitC = P.opt.tuneBurst ? P.opt.tuneBurst == 44 : MCB_CROP_SPLIT;
+    if (occC >= 7) { if (splitC) MCB_POOL_CROP(7, true); else MCB_POOL_CROP(7, false); }
+    else { if (splitC) MCB_POOL_CROP(6, true); else MCB_POOL_CROP(6, false); }
+#undef MCB_POOL_CROP
+    mcb_launch_expand_compact_tally(P, numSMs, stream);
     return;
   }
   if (occ >= 8) { if (burst == 44) MCB_POOL_LAYOUT(8, 8, true); else MCB_POOL_LAYOUT(8, 8, false); }

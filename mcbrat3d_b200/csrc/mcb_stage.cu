@@ -106,6 +106,19 @@ __global__ void layer_tables_kernel(const float *__restrict__ layerExt, int nz, 
   }
 }
 
+// the bricked field of the layers [cropLo, cropLo + cropN) (mcb_device.cuh: crp): periodic ghost shell in x and y, none in z
+__global__ void pack_crop_kernel(const double *__restrict__ totalExt, float *__restrict__ e32, int nx, int ny, int G,
+                                 int nxp, int nyp, int cropLo, long long total) {
+  for (long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x; p < total; p += (long long)gridDim.x * blockDim.x) {
+    const int bx = nxp >> 1, by = nyp >> 1, low = (int)(p & 7);
+    const long long b = p >> 3, b2 = b / bx;
+    const int i = 2 * (int)(b % bx) + (low & 1), j = 2 * (int)(b2 % by) + ((low >> 1) & 1), k = 2 * (int)(b2 / by) + (low >> 2);
+    int mx = (i - G) % nx; mx += mx < 0 ? nx : 0;
+    int my = (j - G) % ny; my += my < 0 ? ny : 0;
+    e32[p] = (float)totalExt[mx + (long long)nx * (my + (long long)ny * (k + cropLo))];
+  }
+}
+
 // ---- column-compressed storage (mcb_device.cuh): ranges, offsets, compact arrays, padded column table ----
 // per column the first and one-past-the-last layer whose extinction differs from the layer's clear-sky value
 __global__ void col_range_kernel(const double *__restrict__ totalExt, const float *__restrict__ layerExt, int cols, int nz, int G,
@@ -156,6 +169,14 @@ __global__ void col_fill_kernel(const double *__restrict__ totalExt, const uint3
     extC[i] = (float)totalExt[p];
     cellC[i] = (uint32_t)p;
     for (int w = 0; w < (1 << recShift); ++w) recC[(i << recShift) + w] = rec[(p << recShift) + w];
+  }
+}
+// the compact volume-absorption tally of a launch goes into the dense tally buffer and is cleared for the next one
+__global__ void expand_compact_tally_kernel(double *__restrict__ tallyC, const uint32_t *__restrict__ cellC, long long n,
+                                            double *__restrict__ volAbs) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const double v = tallyC[i];
+    if (v != 0.0) { volAbs[cellC[i]] += v; tallyC[i] = 0.0; }
   }
 }
 // the column table in the padded x-fastest column space (periodic replicas in the ghost shell)
@@ -942,6 +963,18 @@ void mcb_launch_pack_field(const DevDomain &P, int brick, float *ext, uint32_t *
     mcbstage::occupancy_mask_kernel<<<stream_grid(F.padded, 256, numSMs), 256, 0, stream>>>(ext, layerExt, F.padded,
                                                                                             F.nxp * F.nyp, mask, brick);
   }
+}
+
+void mcb_launch_expand_compact_tally(const DevDomain &P, int numSMs, cudaStream_t stream) {
+  if (!P.tallyC || P.nCompact <= 0) return;
+  mcbstage::expand_compact_tally_kernel<<<stream_grid(P.nCompact, 256, numSMs), 256, 0, stream>>>(P.tallyC, P.cellC, P.nCompact,
+                                                                                              P.tally + P.offVolAbs);
+}
+
+void mcb_launch_pack_crop(const DevDomain &P, float *ext, int numSMs, cudaStream_t stream) {
+  const DevDomain::ExtField &F = P.crp;
+  mcbstage::pack_crop_kernel<<<stream_grid(F.padded, 256, numSMs), 256, 0, stream>>>(P.totalExt, ext, P.nx, P.ny, MCB_GHOST, F.nxp,
+                                                                                 F.nyp, P.cropLo, F.padded);
 }
 
 // column-compressed storage, step 1: ranges, per-column counts, offsets and the total (-> *sum, read by the host, which

@@ -38,6 +38,8 @@ cases["T_irr_LW_views"] = ((domains.irregular_test_domain()[0], dict(lw=True, su
                                                                     intensityPhis=[0.0, 45.0, 200.0])), True, 60000)
 for name in ("C3_small_mie", "C5_small", "C5_small_odd", "C5_small_odd_bitmap"):      # the photon-pool kernel as well
     cases[name + "_pool"] = cases[name]
+cases["C5_small_odd_columns_pool"] = cases["C5_small_odd"]                              # ... on column-compressed storage
+cases["C5_taller_columns_pool"] = (domains.bench_domain(nxy=24, nz=96), False, 100000)
 cases["C3_small_views_pool"] = (domains.landsat_cloud(ssa=0.99, nxy=24, mie=True), True, 30000)        # ... and its view rays
 cases["C5_small_bitmap_views_pool"] = cases["C5_small_bitmap_views"]
 cases["C4_LW_views_pool"] = cases["C4_LW_views"]
@@ -49,7 +51,7 @@ for name, ((dom, case), views, n) in cases.items():
         specifyParameters(g, intensityMus=case.get("intensityMus", [1.0, 0.5]), intensityPhis=case.get("intensityPhis", [0.0, 0.0]),
                           computeIntensity=True, useRussianRouletteForIntensity=True, zetaMin=0.3)
     specifyParameters(g, minInverseTableSize=9001, minForwardTableSize=9001, LW_flag=1.0 if case.get("lw") else -1.0,
-                      tuneExtMask=1 if "bitmap" in name else 0,       # occupancy-bitmap variants of the marcher
+                      tuneExtMask=1 if "bitmap" in name else 2 if "columns" in name else 0,   # bitmap / column-compressed variants
                       tuneKernel=MCB_KERNEL_POOL if name.endswith("_pool") else MCB_KERNEL_PARK)
     rs = new_RandomNumberSequence([3, 1, 0])
     if case.get("lw"):

@@ -144,3 +144,26 @@ def test_local_estimate_maps_match_reference_kernel_on_c3():
         rms, mean = float(np.sqrt(np.mean(z ** 2))), float(z.mean())
         assert rms < 1.1, (d, rms)
         assert abs(mean) < 5.0 / np.sqrt(z.size) + 0.02, (d, mean)
+
+
+def test_column_compressed_storage_matches_reference_kernel_maps():
+    """The pool flux kernel on column-compressed storage (what fields too large for L2 run on: C5) against the
+    reference-arithmetic kernel on the small C5 scene, 1e8 photons, same criteria as above."""
+    name, make, photons = CASES[2]
+    dom, case = make()
+    nb = 16
+    n = photons // nb
+    want = ("fluxUp", "fluxDown", "absorbedProfile", "meanFluxUp", "meanFluxDown", "meanFluxAbsorbed")
+    fast = _gpu_rows(dom, case, nb, n, (10, 1, 0), want=want, arithmetic=MCB_ARITH_FAST, tuneKernel=MCB_KERNEL_POOL, tuneExtMask=2)
+    if name not in _REF:
+        _REF[name] = _gpu_rows(dom, case, nb, n, (77, 3, 0), want=want, arithmetic=MCB_ARITH_REFERENCE)
+    ref = _REF[name]
+    for q in ("meanFluxUp", "meanFluxDown", "meanFluxAbsorbed"):
+        (ma, ea), (mb, eb) = _mean_err(fast[q]), _mean_err(ref[q])
+        assert_within("%s %s columns vs reference kernel" % (name, q), ma, ea, mb, eb, 3.5)
+    for q in ("fluxUp", "fluxDown"):
+        z, *_ = _zmap(fast[q], ref[q])
+        rms, mean = float(np.sqrt(np.mean(z ** 2))), float(z.mean())
+        assert rms < 1.1 and abs(mean) < 5.0 / np.sqrt(z.size) + 0.02 and np.abs(z).max() < 6.0, (q, rms, mean)
+    z, *_ = _zmap(fast["absorbedProfile"].reshape(nb, -1), ref["absorbedProfile"].reshape(nb, -1))
+    assert np.abs(z).max() < 4.5 and np.sqrt(np.mean(z ** 2)) < 1.4

@@ -99,6 +99,7 @@ LEAP_CASES = [("C3_small", lambda: domains.landsat_cloud(ssa=0.99, nxy=32), 4000
               ("C3_small_linear", lambda: domains.landsat_cloud(ssa=0.99, nxy=32), 300000, None),
               ("sparse", sparse_domain, 400000, None),
               ("C5_small_bitmap", lambda: domains.bench_domain(nxy=40, nz=96), 300000, None),   # whole clear layers, not vacuum
+              ("C5_small_columns", lambda: domains.bench_domain(nxy=40, nz=96), 300000, None),  # the same on column-compressed storage
               ("C5_small_bitmap_views", lambda: domains.bench_domain(nxy=24, nz=96), 40000, ([1.0, 0.5, -0.5], [0.0, 0.0, 180.0])),
               ("C3_small_views", lambda: domains.landsat_cloud(ssa=0.99, nxy=32), 60000, (domains.I3RC_VIEWS_MU, domains.I3RC_VIEWS_PHI)),
               ("sparse_views", sparse_domain, 60000, ([1.0, 0.5, -0.6], [0.0, 70.0, 200.0]))]
@@ -107,7 +108,7 @@ LEAP_CASES = [("C3_small", lambda: domains.landsat_cloud(ssa=0.99, nxy=32), 4000
 @pytest.mark.parametrize("name,make,n,views", LEAP_CASES, ids=[c[0] for c in LEAP_CASES])
 def test_leaps_trace_the_same_histories_up_to_rounding(name, make, n, views):
     dom, case = make()
-    extra = dict(tuneLayout=1) if name.endswith("linear") else dict(tuneExtMask=1) if "bitmap" in name else {}
+    extra = dict(tuneLayout=1) if name.endswith("linear") else dict(tuneExtMask=1) if "bitmap" in name else dict(tuneExtMask=2) if "columns" in name else {}
     want, cw = _run(dom, case, n, views, tuneLeap=-1, **extra)
     assert cw["bad"] == 0
     for leap in (0, 2, 7):                                  # default distance, the smallest, a larger one
@@ -140,7 +141,7 @@ import test_gpu_leap as T
 out = {}
 for name, make, n, views in T.LEAP_CASES:
     dom, case = make()
-    extra = dict(tuneLayout=1) if name.endswith("linear") else dict(tuneExtMask=1) if "bitmap" in name else {}
+    extra = dict(tuneLayout=1) if name.endswith("linear") else dict(tuneExtMask=1) if "bitmap" in name else dict(tuneExtMask=2) if "columns" in name else {}
     _, c = T._run(dom, case, min(n, 100000), views, **extra)
     out[name] = c
 dom, case = T.domains.landsat_cloud(ssa=0.99, nxy=24, mie=True)      # Rayleigh background: no vacuum anywhere

@@ -26,6 +26,8 @@ CASES = [
     ("C3_small_mie", lambda: domains.landsat_cloud(ssa=0.99, nxy=24, mie=True), 300000, {}),
     ("C3_small_linear", lambda: domains.landsat_cloud(ssa=0.99, nxy=32), 300000, dict(tuneLayout=MCB_LAYOUT_LINEAR)),
     ("C5_small_bitmap", lambda: domains.bench_domain(nxy=41, nz=47), 300000, dict(tuneExtMask=1)),
+    ("C5_small_columns", lambda: domains.bench_domain(nxy=41, nz=47), 300000, dict(tuneExtMask=2)),   # column-compressed storage
+    ("C5_columns_taller", lambda: domains.bench_domain(nxy=24, nz=96), 200000, dict(tuneExtMask=2)),
     ("C5_small", lambda: domains.bench_domain(nxy=40, nz=48), 300000, {}),
     ("C1", lambda: domains.homogeneous_slab(ssa=0.99), 400000, {}),                 # tallies privatised in shared memory
     ("C4_LW", lambda: domains.homogeneous_lw(), 400000, {}),                        # thermal source, emission bookkeeping
