@@ -25,7 +25,8 @@ double mcb_run_gather_probe(size_t bytes, int inFlight, int blocksPerSM, int ite
 // mcb_stage.cu: device-side packing / validation, normalisation, emission CDF
 void mcb_launch_distance_map(const DevDomain &P, int cap, uint8_t *dist, uint8_t *scratch, int *leapCount, int numSMs, cudaStream_t stream);
 void mcb_launch_pack_crop(const DevDomain &P, float *ext, int numSMs, cudaStream_t stream);
-void mcb_launch_column_ranges(const DevDomain &P, uint32_t *range, int *count, int *offset, int *sum, int numSMs, cudaStream_t stream);
+void mcb_launch_column_ranges(const DevDomain &P, uint32_t *range, int *count, int *offset, int *tileSum, int *sum, int numSMs,
+                              cudaStream_t stream);
 void mcb_launch_column_fill(const DevDomain &P, const uint32_t *range, const int *offset, float *extC, uint32_t *recC,
                             uint32_t *cellC, uint2 *colTab, int numSMs, cudaStream_t stream);
 void mcb_launch_pack_field(const DevDomain &P, int brick, float *ext, uint32_t *mask, float *layerExt, int *flags, const uint8_t *dist, int *leapCount,
@@ -84,6 +85,8 @@ struct mcb_handle {
   void *dExtMask = nullptr, *dExtMaskBrick = nullptr, *dLayerExt = nullptr;     // occupancy bitmap of fields too large for L2
   void *dDist = nullptr, *dDistScratch = nullptr;   // vacuum-distance map (u8 per cell) the packed fields are encoded with
   void *dColRange = nullptr, *dColCount = nullptr, *dColOffset = nullptr, *dColTab = nullptr;   // column-compressed storage
+  void *dColTiles = nullptr;
+  std::vector<float> hLayer;                     // host copy of layerExt (read with the leap count: the crop decision needs it)
   void *dExtC = nullptr, *dRecC = nullptr, *dCellC = nullptr, *dExtCrop = nullptr, *dTallyC = nullptr;
   void *dInv[MCB_MAX_COMP] = {nullptr}, *dFwd[MCB_MAX_COMP] = {nullptr}, *dFwdOrig[MCB_MAX_COMP] = {nullptr};
   int invE[MCB_MAX_COMP] = {0}, fwdE[MCB_MAX_COMP] = {0};
@@ -223,7 +226,7 @@ int mcb_destroy(mcb_handle *h) {
                    h->dTemps, h->dScratch, h->dResults, (void *)h->dFlags, h->dStats, h->dStatsOut,
                    h->dMassConc, h->dReff, h->dNumConc, h->dAsmTables, h->dExtMask, h->dLayerExt,
                    h->dExtBrick, h->dExtMaskBrick, h->dColCDF, h->dDist, h->dDistScratch,
-                   h->dColRange, h->dColCount, h->dColOffset, h->dColTab, h->dExtC, h->dRecC, h->dCellC, h->dExtCrop, h->dTallyC};
+                   h->dColRange, h->dColCount, h->dColOffset, h->dColTab, h->dColTiles, h->dExtC, h->dRecC, h->dCellC, h->dExtCrop, h->dTallyC};
   for (void *p : slots) if (p) cudaFree(p);
   for (int c = 0; c < MCB_MAX_COMP; ++c) {
     if (h->dInv[c]) cudaFree(h->dInv[c]);
@@ -339,6 +342,7 @@ int mcb_set_grid(mcb_handle *h, int nx, int ny, int nz,
 
 static int finish_optics(mcb_handle *h, int nc, double albedo, bool zeroFlags = true);
 static int setup_packed_field(mcb_handle *h);
+static int setup_compact_storage(mcb_handle *h);
 
 // the thermal source's CDF is in HBM: derive the compact column weights and publish the pointers
 static int finish_thermal_source(mcb_handle *h, double fracAtmsPower) {
@@ -386,7 +390,9 @@ static int pack_field(mcb_handle *h, bool brick) {
   CK(h, cudaGetLastError());
   if (P.lin.mask) {                                   // layers clear throughout, far enough from the nearest cloudy one
     int layers = 0;
+    h->hLayer.resize((size_t)P.nz + 2 * MCB_GHOST);
     CK(h, cudaMemcpyAsync(&layers, leapCount, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CK(h, cudaMemcpyAsync(h->hLayer.data(), P.layerExt, sizeof(float) * h->hLayer.size(), cudaMemcpyDeviceToHost, h->stream));
     if (settle(h)) return 1;
     P.leap = candidate && layers * 16 >= P.nz ? 1 : 0;
   }
@@ -441,39 +447,30 @@ int mcb_set_optics(mcb_handle *h, int nc, const double *totalExt, const double *
   return finish_optics(h, nc, albedo);
 }
 
-// The dense f64 arrays are in HBM (uploaded by mcb_set_optics or built by mcb_assemble_optics): derive the packed
-// single-precision copies, run the argument checks, find maxval(totalExt), publish the pointers.
-static int finish_optics(mcb_handle *h, int nc, double albedo, bool zeroFlags) {
+// Column-compressed event data and the layer-cropped field for the pool flux kernel (mcb_device.cuh); needs the packed
+// field's layer table (setup_packed_field) and the event records.
+static int setup_compact_storage(mcb_handle *h) {
   DevDomain &P = h->P;
-  const size_t cells = (size_t)P.nx * P.ny * P.nz;
-  int recShift = 0;                                   // event record: (nc-1) + nc + ceil(nc/2) words, padded to 2^recShift
-  while ((1 << recShift) < 2 * nc - 1 + (nc + 1) / 2) ++recShift;
-  if (reserve(h, &h->dRec, sizeof(uint32_t) * (cells << recShift))) return 1;
-  P.nc = nc; P.albedo = albedo;
-  P.totalExt = (const double *)h->dTotalExt; P.cumExt = (const double *)h->dCumExt;
-  P.ssa = (const double *)h->dSsa; P.phaseIdx = (const int32_t *)h->dPhaseIdx;
-  P.rec = (const uint32_t *)h->dRec; P.recShift = recShift;
-  if (zeroFlags) CK(h, cudaMemsetAsync(h->dFlags, 0, sizeof(int) * 4, h->stream));
-  if (setup_packed_field(h)) return 1;
-  mcb_launch_pack_records(P, (uint32_t *)h->dRec, h->dFlags, h->numSMs, h->stream);
-  CK(h, cudaGetLastError());
   // Column-compressed storage for the pool flux kernel (fields marched through the bitmap, i.e. too large for L2): the
   // cells inside the per-column ranges -- extinction, event record, cell index -- densely, column by column.
   P.colTab = nullptr; P.extC = nullptr; P.recC = nullptr; P.cellC = nullptr; P.nCompact = 0; P.tallyC = nullptr;
   P.crp.ext = nullptr; P.cropLo = 0; P.cropN = 0;
-  if (P.lin.mask && P.uniform && P.nx >= MCB_GHOST && P.ny >= MCB_GHOST && P.nz <= 65535) {
+  // (tuneExtMask = 1 keeps the run on the bitmap: nothing of this is built)
+  if (P.lin.mask && P.opt.tuneExtMask != 1 && P.uniform && P.nx >= MCB_GHOST && P.ny >= MCB_GHOST && P.nz <= 65535) {
     const size_t cols = (size_t)P.nx * P.ny;
     if (reserve(h, &h->dColRange, sizeof(uint32_t) * cols) || reserve(h, &h->dColCount, sizeof(int) * cols) ||
-        reserve(h, &h->dColOffset, sizeof(int) * cols) || reserve(h, &h->dColTab, sizeof(uint2) * (size_t)P.lin.nxp * P.lin.nyp))
+        reserve(h, &h->dColOffset, sizeof(int) * cols) || reserve(h, &h->dColTab, sizeof(uint2) * (size_t)P.lin.nxp * P.lin.nyp) ||
+        reserve(h, &h->dColTiles, sizeof(int) * ((cols + 1023) / 1024 + 1)))
       return 1;
     int *dSum = h->dFlags + 1;
-    mcb_launch_column_ranges(P, (uint32_t *)h->dColRange, (int *)h->dColCount, (int *)h->dColOffset, dSum, h->numSMs, h->stream);
+    mcb_launch_column_ranges(P, (uint32_t *)h->dColRange, (int *)h->dColCount, (int *)h->dColOffset, (int *)h->dColTiles, dSum,
+                             h->numSMs, h->stream);
     CK(h, cudaGetLastError());
     int nCompact = 0;
     CK(h, cudaMemcpyAsync(&nCompact, dSum, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
     if (settle(h)) return 1;
     const size_t n = nCompact > 0 ? (size_t)nCompact : 1;
-    if (reserve(h, &h->dExtC, sizeof(float) * n) || reserve(h, &h->dRecC, sizeof(uint32_t) * (n << recShift)) ||
+    if (reserve(h, &h->dExtC, sizeof(float) * n) || reserve(h, &h->dRecC, sizeof(uint32_t) * (n << P.recShift)) ||
         reserve(h, &h->dCellC, sizeof(uint32_t) * n) || reserve(h, &h->dTallyC, sizeof(double) * n))
       return 1;
     CK(h, cudaMemsetAsync(h->dTallyC, 0, sizeof(double) * n, h->stream));
@@ -484,9 +481,7 @@ static int finish_optics(mcb_handle *h, int nc, double albedo, bool zeroFlags) {
     P.cellC = (const uint32_t *)h->dCellC; P.nCompact = nCompact; P.tallyC = (double *)h->dTallyC;
     // The layer-cropped field: the band of layers that hold cloud somewhere (the sign bits of layerExt mark the layers
     // that are clear throughout), bricked, if it is small enough to stay in L2 (same 48 MB limit as the bitmap decision).
-    std::vector<float> layer((size_t)P.nz + 2 * MCB_GHOST);
-    CK(h, cudaMemcpyAsync(layer.data(), P.layerExt, sizeof(float) * layer.size(), cudaMemcpyDeviceToHost, h->stream));
-    if (settle(h)) return 1;
+    const std::vector<float> &layer = h->hLayer;               // read back with the leap count (pack_field)
     int lo = P.nz, hi = 0;
     for (int k = 0; k < P.nz; ++k) if (!std::signbit(layer[(size_t)k + MCB_GHOST])) { lo = lo < k ? lo : k; hi = k + 1; }
     if (hi > lo) {
@@ -505,6 +500,26 @@ static int finish_optics(mcb_handle *h, int nc, double albedo, bool zeroFlags) {
       }
     }
   }
+  return 0;
+}
+
+// The dense f64 arrays are in HBM (uploaded by mcb_set_optics or built by mcb_assemble_optics): derive the packed
+// single-precision copies, run the argument checks, find maxval(totalExt), publish the pointers.
+static int finish_optics(mcb_handle *h, int nc, double albedo, bool zeroFlags) {
+  DevDomain &P = h->P;
+  const size_t cells = (size_t)P.nx * P.ny * P.nz;
+  int recShift = 0;                                   // event record: (nc-1) + nc + ceil(nc/2) words, padded to 2^recShift
+  while ((1 << recShift) < 2 * nc - 1 + (nc + 1) / 2) ++recShift;
+  if (reserve(h, &h->dRec, sizeof(uint32_t) * (cells << recShift))) return 1;
+  P.nc = nc; P.albedo = albedo;
+  P.totalExt = (const double *)h->dTotalExt; P.cumExt = (const double *)h->dCumExt;
+  P.ssa = (const double *)h->dSsa; P.phaseIdx = (const int32_t *)h->dPhaseIdx;
+  P.rec = (const uint32_t *)h->dRec; P.recShift = recShift;
+  if (zeroFlags) CK(h, cudaMemsetAsync(h->dFlags, 0, sizeof(int) * 4, h->stream));
+  if (setup_packed_field(h)) return 1;
+  mcb_launch_pack_records(P, (uint32_t *)h->dRec, h->dFlags, h->numSMs, h->stream);
+  CK(h, cudaGetLastError());
+  if (setup_compact_storage(h)) return 1;
   int flags4[4] = {0, 0, 0, 0};
   CK(h, cudaMemcpyAsync(flags4, h->dFlags, sizeof(flags4), cudaMemcpyDeviceToHost, h->stream));
   if (settle(h)) return 1;
@@ -795,7 +810,7 @@ int mcb_set_options(mcb_handle *h, const mcb_options *o) {
   h->P.opt = *o;
   if (h->haveOptics && o->tuneExtMask != h->maskKnob) {          // the knob changed after staging: pack again
     CK(h, cudaSetDevice(h->device));
-    if (setup_packed_field(h) || settle(h)) return 1;
+    if (setup_packed_field(h) || setup_compact_storage(h) || settle(h)) return 1;
   }
   return 0;
 }

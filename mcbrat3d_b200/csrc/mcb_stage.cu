@@ -132,29 +132,47 @@ __global__ void col_range_kernel(const double *__restrict__ totalExt, const floa
     count[c] = hi - lo;
   }
 }
-// exclusive prefix sum of count[0..n) in one block (n ~ 1e5: a few hundred microseconds, once per staging); total -> *sum
-__global__ void col_scan_kernel(const int *__restrict__ count, int n, int *__restrict__ offset, int *sum) {
+// exclusive prefix sum of count[0..n) in three small launches: per-tile sums (tiles of 1024), one block scanning the tile
+// sums (n ~ 1e5 columns: ~100 tiles), tiles scanned with their offset; total -> *sum
+__device__ __forceinline__ int block_inclusive_scan_1024(int v, int *part) {
+  part[threadIdx.x] = v;
+  __syncthreads();
+  for (int o = 1; o < 1024; o <<= 1) {                         // Hillis-Steele
+    const int t = (int)threadIdx.x >= o ? part[threadIdx.x - o] : 0;
+    __syncthreads();
+    part[threadIdx.x] += t;
+    __syncthreads();
+  }
+  return part[threadIdx.x];
+}
+__global__ void col_tile_sum_kernel(const int *__restrict__ count, int n, int *__restrict__ tileSum) {
+  __shared__ int part[1024];
+  const int i = blockIdx.x * 1024 + threadIdx.x;
+  const int s = block_inclusive_scan_1024(i < n ? count[i] : 0, part);
+  if (threadIdx.x == 1023) tileSum[blockIdx.x] = s;
+}
+__global__ void col_tile_scan_kernel(int *__restrict__ tileSum, int nTiles, int *sum) {      // one block, exclusive, in place
   __shared__ int part[1024];
   __shared__ int carry;
   if (threadIdx.x == 0) carry = 0;
   __syncthreads();
-  for (int base = 0; base < n; base += 1024) {
+  for (int base = 0; base < nTiles; base += 1024) {
     const int i = base + threadIdx.x;
-    const int v = i < n ? count[i] : 0;
-    part[threadIdx.x] = v;
+    const int v = i < nTiles ? tileSum[i] : 0;
+    const int s = block_inclusive_scan_1024(v, part);
+    if (i < nTiles) tileSum[i] = carry + s - v;
     __syncthreads();
-    for (int o = 1; o < 1024; o <<= 1) {                       // Hillis-Steele inclusive scan
-      const int t = (int)threadIdx.x >= o ? part[threadIdx.x - o] : 0;
-      __syncthreads();
-      part[threadIdx.x] += t;
-      __syncthreads();
-    }
-    if (i < n) offset[i] = carry + part[threadIdx.x] - v;
-    __syncthreads();
-    if (threadIdx.x == 1023) carry += part[1023];
+    if (threadIdx.x == 1023) carry += s;
     __syncthreads();
   }
   if (threadIdx.x == 0) *sum = carry;
+}
+__global__ void col_scan_kernel(const int *__restrict__ count, int n, const int *__restrict__ tileOffset, int *__restrict__ offset) {
+  __shared__ int part[1024];
+  const int i = blockIdx.x * 1024 + threadIdx.x;
+  const int v = i < n ? count[i] : 0;
+  const int s = block_inclusive_scan_1024(v, part);
+  if (i < n) offset[i] = tileOffset[blockIdx.x] + s - v;
 }
 // the cells inside the ranges: extinction, event record, cell index, column by column
 __global__ void col_fill_kernel(const double *__restrict__ totalExt, const uint32_t *__restrict__ rec, int recShift,
@@ -979,10 +997,13 @@ void mcb_launch_pack_crop(const DevDomain &P, float *ext, int numSMs, cudaStream
 
 // column-compressed storage, step 1: ranges, per-column counts, offsets and the total (-> *sum, read by the host, which
 // sizes the compact arrays); layerExt must have been built (mcb_launch_pack_field with a mask)
-void mcb_launch_column_ranges(const DevDomain &P, uint32_t *range, int *count, int *offset, int *sum, int numSMs, cudaStream_t stream) {
-  const int cols = P.nx * P.ny;
+void mcb_launch_column_ranges(const DevDomain &P, uint32_t *range, int *count, int *offset, int *tileSum, int *sum, int numSMs,
+                              cudaStream_t stream) {
+  const int cols = P.nx * P.ny, tiles = (cols + 1023) / 1024;
   mcbstage::col_range_kernel<<<stream_grid(cols, 128, numSMs), 128, 0, stream>>>(P.totalExt, P.layerExt, cols, P.nz, MCB_GHOST, range, count);
-  mcbstage::col_scan_kernel<<<1, 1024, 0, stream>>>(count, cols, offset, sum);
+  mcbstage::col_tile_sum_kernel<<<tiles, 1024, 0, stream>>>(count, cols, tileSum);
+  mcbstage::col_tile_scan_kernel<<<1, 1024, 0, stream>>>(tileSum, tiles, sum);
+  mcbstage::col_scan_kernel<<<tiles, 1024, 0, stream>>>(count, cols, tileSum, offset);
 }
 // step 2: the compact arrays and the padded column table
 void mcb_launch_column_fill(const DevDomain &P, const uint32_t *range, const int *offset, float *extC, uint32_t *recC,

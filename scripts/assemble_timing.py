@@ -8,7 +8,7 @@ from mcbrat3d_b200.opticalProperties import read_SSPTable
 common, tables, case = domains.broadband_problem(nxy=325, nz=160, nLambda=8)
 d0 = read_SSPTable(tables, 1, common, setup=True)
 g = new_Integrator(d0)
-specifyParameters(g, minInverseTableSize=9001, buildTablesOnDevice=True)
+specifyParameters(g, minInverseTableSize=9001, buildTablesOnDevice=True, tuneExtMask=int(sys.argv[1]) if len(sys.argv) > 1 else 0)
 for i in range(1, 7):
     t0 = time.perf_counter(); d = read_SSPTable(tables, i, common, calcRayl=True, thisIntegrator=g); t1 = time.perf_counter()
     _stage_domain(g, d); t2 = time.perf_counter()

@@ -14,6 +14,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--nxy", type=int, default=325); ap.add_argument("--nz", type=int, default=160)
 ap.add_argument("--lambdas", type=int, default=32); ap.add_argument("--photons", type=float, default=3.2e8)
 ap.add_argument("--batch", type=float, default=5e6); ap.add_argument("--lw", action="store_true")
+ap.add_argument("--ext-mask", type=int, default=0)       # mcb_options.tuneExtMask: 1 = bitmap marcher, 0 / 2 = the library's choice
 a = ap.parse_args()
 world, rank = mpx.initializeProcesses()
 local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -22,7 +23,7 @@ common, tables, case = domains.broadband_problem(nxy=a.nxy, nz=a.nz, nLambda=a.l
 t1 = time.perf_counter()
 d0 = read_SSPTable(tables, 1, common, setup=True)                    # grid only: new_Integrator needs the edges
 g = new_Integrator(d0, device=local)
-specifyParameters(g, minInverseTableSize=9001)
+specifyParameters(g, minInverseTableSize=9001, tuneExtMask=a.ext_mask)
 rs = new_RandomNumberSequence([10, 0, 0])
 src = 2.0e3 * np.exp(-((np.linspace(0.45, 2.1, a.lambdas) - 0.5) / 0.6) ** 2)
 if world > 1:                                                           # create the NCCL communicator outside the timed run
