@@ -126,3 +126,45 @@ def test_oracle_forward_builder_matches_numpy_mirror(orc):
             for e, pf in enumerate(tab.phaseFunctions):
                 assert np.array_equal(orc.forward_phase_function(pf.legendreCoefficients, 9001), d.tabulatedOrigPhaseFunctions[c][e])
     assert np.all(orc.forward_phase_function(np.zeros(0, np.float32), 11) == 0.5)          # quirk q14
+
+
+def test_oracle_lobatto_values_and_hybrid_equal_the_host_mirror(orc):
+    """The C restatements of the remaining table producers -- computeLobattoTerms (NUM:27-114), getPhaseFunctionValues
+    for both storage kinds (SPF:448-531), the inversion inputs of INV:97-112 and computeHybridPhaseFunctions
+    (OPT:1936-2050) -- against the NumPy mirror, bit for bit."""
+    from mcbrat3d_b200.inversePhaseFunctions import inversion_inputs
+    from mcbrat3d_b200.numericUtilities import computeLobattoTerms
+    from mcbrat3d_b200.opticalProperties import computeHybridPhaseFunctions
+    from mcbrat3d_b200.scatteringPhaseFunctions import (getPhaseFunctionValues, henyeyGreenstein, new_PhaseFunction, rayleigh)
+    f32 = np.float32
+    for n in (2, 3, 4, 5, 16, 64, 65, 128, 299):
+        mus, w = orc.lobatto_terms(n)
+        m2, w2 = computeLobattoTerms(n)
+        assert np.array_equal(mus, m2) and np.array_equal(w, w2), n
+        assert mus[0] == -1 and mus[-1] == 1 and np.all(np.diff(mus) > 0) and abs(float(w.sum()) - 2.0) < 1e-4
+    for pf in (henyeyGreenstein(0.85, 64), henyeyGreenstein(0.85, 299), rayleigh(), henyeyGreenstein(0.6, 3), henyeyGreenstein(0.3, 1)):
+        mus, vals = orc.inversion_inputs_legendre(pf.legendreCoefficients)
+        m2, v2 = inversion_inputs(pf)
+        assert np.array_equal(mus, m2) and np.array_equal(vals, v2)
+    nS = 9001
+    angles = (np.arange(nS, dtype=f32) / f32(nS - 1) * f32(np.pi)).astype(f32)
+    ang = np.linspace(0.0, np.pi, 721).astype(f32); ang[-1] = f32(np.pi)
+    mu = np.cos(ang.astype(np.float64))
+    hg = lambda gg: (1 - gg * gg) / (1 + gg * gg - 2 * gg * mu) ** 1.5
+    tab = new_PhaseFunction(scatteringAngle=ang, value=(0.97 * hg(0.9) + 0.03 * hg(-0.45)).astype(f32))
+    a = orc.phase_function_values(angles, storedAngle=tab.scatteringAngle, storedValue=tab.value)
+    assert np.array_equal(a, getPhaseFunctionValues(tab, angles))
+    found = 0
+    for pf, width in ((henyeyGreenstein(0.9, 64), 7.0), (henyeyGreenstein(0.95, 256), 7.0), (henyeyGreenstein(0.85, 64), 7.0),
+                      (tab, 7.0), (tab, 2.0)):
+        orig = getPhaseFunctionValues(pf, angles)
+        want = computeHybridPhaseFunctions(angles, orig[None, :], width)[0]
+        got, t = orc.hybrid_phase_function(angles, orig, width)
+        assert np.array_equal(got, want), (width, t)
+        if t > 0:                                        # Gaussian below the transition, the original above, still normalised
+            found += 1
+            assert np.array_equal(got[t:], orig[t:]) and not np.array_equal(got[:t], orig[:t])
+            cs = np.cos(angles.astype(np.float64))
+            integral = float(np.sum(0.5 * (got[:-1] + got[1:]).astype(np.float64) * (cs[:-1] - cs[1:])))
+            assert abs(integral - 2.0) < 2e-3, integral
+    assert found >= 3
