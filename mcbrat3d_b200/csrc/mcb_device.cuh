@@ -13,7 +13,8 @@
 #define MCB_MAX_COMP 8          // optical components per domain (the reference's decks use <= 4)
 #define MCB_MAX_DIR 32          // view directions kept in the parameter block
 #define MCB_GHOST 8             // ghost cells on every side of the packed extinction field = longest marching burst
-#define MCB_LEAP_MIN 3          // smallest vacuum distance the pool kernels leap from (mcb_options.tuneLeap overrides)
+#define MCB_LEAP_MIN 2          // smallest vacuum distance the pool kernels leap from (mcb_options.tuneLeap overrides); one
+                                // B200, r02, C3: 2 -> 7.84e8, 3 -> 7.77e8, 4 -> 7.69e8 photons/s (C3 + views 1.101e8 / 1.093e8)
 #define MCB_LEAP_LANES 1        // lanes of a warp that must want a leap for the warp to run the leap code (tuneLeapLanes).
                                 // 8 measured 1 % faster on C3, but then a photon's leaps -- and with them the last bits of its
                                 // positions -- depend on which other photons share its warp: results would no longer be

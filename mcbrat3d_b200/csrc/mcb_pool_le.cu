@@ -30,6 +30,12 @@ namespace mcbpoolle {
 
 using namespace mcbfast;
 
+#ifndef MCB_PLE_SPLIT
+#define MCB_PLE_SPLIT false       // gathers of a burst in two halves (A/B: make variant FLAGS=-DMCB_PLE_SPLIT=true)
+#endif
+#ifndef MCB_PLE_BURST
+#define MCB_PLE_BURST 8
+#endif
 #define PLE_WORDS 17
 #define PLE_SLOTS 64
 #define PLE_REQS 32
@@ -433,7 +439,7 @@ pool_le_kernel(const __grid_constant__ DevDomain P, long long nPhotons, uint64_t
       if (D) ev = march_leap<MASK>(r, P, D, crossed, ext, tgt, &sCnt[4]);
     }
     if (job != JOB_NONE && ev == MARCH_ON)
-      ev = march_burst<true, true, BURST, MASK, BRICK, true, false, LEAP>(r, P, G, ext, tgt, crossed, LEAP ? &vcur : nullptr);
+      ev = march_burst<true, true, BURST, MASK, BRICK, true, MCB_PLE_SPLIT, LEAP>(r, P, G, ext, tgt, crossed, LEAP ? &vcur : nullptr);
     if (job == JOB_PHOTON) crossings += crossed; else leCrossings += crossed;
 
     // =========================== rays that ended ===========================
@@ -545,7 +551,7 @@ template <int MINBLOCKS, bool MASK, bool BRICK, bool LEAP>
 static void launch_pool_le(const DevDomain &P, long long nPhotons, uint64_t seed, uint64_t firstPhotonId, int numSMs,
                            unsigned long long *workCounter, cudaStream_t stream) {
   constexpr int THREADS = 128;
-  auto kernel = mcbpoolle::pool_le_kernel<THREADS, MINBLOCKS, 8, MASK, BRICK, LEAP>;
+  auto kernel = mcbpoolle::pool_le_kernel<THREADS, MINBLOCKS, MCB_PLE_BURST, MASK, BRICK, LEAP>;
   const int cols = P.nx * P.ny, cells = cols * P.nz;
   mcbfast::SmemPlan plan{-1, -1, -1, -1, -1, 0, 0, 0};
   int off = 0;
