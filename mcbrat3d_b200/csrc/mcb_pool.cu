@@ -70,6 +70,15 @@ pool_kernel(const __grid_constant__ DevDomain P, long long nPhotons, uint64_t se
   if (threadIdx.x < 6) sCnt[threadIdx.x] = 0u;
   __syncthreads();
 
+#ifdef MCB_POOL_SMEM_INV         // A/B build: the inverse table of a one-component, one-entry domain staged in shared memory
+  const float *sInv = nullptr;
+  if (plan.intOff >= 0) {
+    float *t = smem + plan.intOff;
+    for (int i = threadIdx.x; i < P.invS[0]; i += THREADS) t[i] = __ldg(P.inv[0] + i);
+    __syncthreads();
+    sInv = t;
+  }
+#endif
   const int lane = threadIdx.x & 31;
   const unsigned below = (1u << lane) - 1u;
   float *pool = smem + plan.poolOff + (threadIdx.x >> 5) * (POOL_WORDS * POOL_SLOTS);   // word-major: pool[word * 64 + slot]
@@ -276,6 +285,11 @@ pool_kernel(const __grid_constant__ DevDomain P, long long nPhotons, uint64_t se
           const float rn = u.x;                                                  // computeScatteringAngle INT:1594-1621
           const int k = (int)(rn * (float)nS) + 1;
           float theta;
+#ifdef MCB_POOL_SMEM_INV
+          if (sInv) {
+            theta = k < nS ? (1.0f - (rn - (float)(k - 1) / (float)nS)) * sInv[k - 1] + (rn - (float)(k - 1) / (float)nS) * sInv[k] : sInv[nS - 1];
+          } else
+#endif
           if (k < nS) {
             const float left = rn - (float)(k - 1) / (float)nS;
             theta = (1.0f - left) * __ldg(&tab[MCB_CHECK_INDEX(P, k - 1, nS)]) + left * __ldg(&tab[MCB_CHECK_INDEX(P, k, nS)]);
@@ -426,6 +440,9 @@ static void launch_pool(const DevDomain &P, long long nPhotons, uint64_t seed, u
   const int budgetFloats = 9 * 1024;             // small grids are atomic hot spots: privatise (as mcb_fast.cu does)
   if (cols <= 1024 && 2 * cols <= budgetFloats) { plan.fluxOff = off; off += 2 * cols; }
   if (cells <= 8192 && (plan.fluxOff >= 0 ? 2 * cols : 0) + cells <= budgetFloats) { plan.volOff = off; off += cells; }
+#ifdef MCB_POOL_SMEM_INV
+  if (P.nc == 1 && P.invE[0] == 1 && P.invS[0] <= 10240) { plan.intOff = off; off += P.invS[0]; }
+#endif
   plan.totalFloats = off;
   const size_t smem = sizeof(float) * (size_t)off;
   cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
