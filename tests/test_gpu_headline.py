@@ -167,3 +167,25 @@ def test_column_compressed_storage_matches_reference_kernel_maps():
         assert rms < 1.1 and abs(mean) < 5.0 / np.sqrt(z.size) + 0.02 and np.abs(z).max() < 6.0, (q, rms, mean)
     z, *_ = _zmap(fast["absorbedProfile"].reshape(nb, -1), ref["absorbedProfile"].reshape(nb, -1))
     assert np.abs(z).max() < 4.5 and np.sqrt(np.mean(z ** 2)) < 1.4
+
+
+def test_full_size_c5_default_path_matches_reference_kernel():
+    """The configuration `bench.py --workload c5` measures, at full size (325 x 325 x 150, nc = 2), on the path the library
+    picks by itself there -- layer-cropped field, column-compressed records and tally, clear-layer leaps -- against the
+    reference-arithmetic kernel: 3.2e7 photons a side, domain means within 3.5 sigma, per-column flux maps and the
+    absorption profile as unit-normal z-scores."""
+    dom, case = domains.bench_domain()
+    nb, n = 16, 2_000_000
+    want = ("fluxUp", "fluxDown", "absorbedProfile", "meanFluxUp", "meanFluxDown", "meanFluxAbsorbed")
+    fast = _gpu_rows(dom, case, nb, n, (10, 1, 0), want=want, arithmetic=MCB_ARITH_FAST)
+    ref = _gpu_rows(dom, case, nb, n, (77, 3, 0), want=want, arithmetic=MCB_ARITH_REFERENCE)
+    for q in ("meanFluxUp", "meanFluxDown", "meanFluxAbsorbed"):
+        (ma, ea), (mb, eb) = _mean_err(fast[q]), _mean_err(ref[q])
+        assert_within("C5 full %s fast vs reference kernel" % q, ma, ea, mb, eb, 3.5)
+    for q in ("fluxUp", "fluxDown"):
+        z, *_ = _zmap(fast[q], ref[q])
+        assert z.size > 0.5 * dom.numX * dom.numY
+        rms, mean = float(np.sqrt(np.mean(z ** 2))), float(z.mean())
+        assert rms < 1.1 and abs(mean) < 5.0 / np.sqrt(z.size) + 0.02 and np.abs(z).max() < 6.5, (q, rms, mean, np.abs(z).max())
+    z, *_ = _zmap(fast["absorbedProfile"].reshape(nb, -1), ref["absorbedProfile"].reshape(nb, -1))
+    assert np.abs(z).max() < 4.5 and np.sqrt(np.mean(z ** 2)) < 1.4
