@@ -632,6 +632,7 @@ bool mcb_pool_preferred(const DevDomain &P);
 void mcb_launch_pool_batch(const DevDomain &P, long long nPhotons, uint64_t seed, uint64_t firstPhotonId,
                            int numSMs, unsigned long long *workCounter, cudaStream_t stream);
 bool mcb_pool_le_covers(const DevDomain &P);
+bool mcb_pool_le_preferred(const DevDomain &P);
 bool mcb_pool_le_reads_bricks(const DevDomain &P);
 void mcb_launch_pool_le_batch(const DevDomain &P, long long nPhotons, uint64_t seed, uint64_t firstPhotonId,
                               int numSMs, unsigned long long *workCounter, cudaStream_t stream);
@@ -642,7 +643,8 @@ void mcb_launch_pool_le_batch(const DevDomain &P, long long nPhotons, uint64_t s
 // which of the two organisations traces this run: mcb_options.tuneKernel, or where none is asked for the one that
 // measured faster (flux-only: mcb_pool_preferred)
 static bool runs_on_pool(const DevDomain &P) {
-  if (P.nDir > 0) return mcb_pool_le_covers(P) && (P.opt.tuneKernel ? P.opt.tuneKernel == MCB_KERNEL_POOL : MCB_POOL_LE_DEFAULT != 0);
+  if (P.nDir > 0) return mcb_pool_le_covers(P) && (P.opt.tuneKernel ? P.opt.tuneKernel == MCB_KERNEL_POOL
+                                                                     : MCB_POOL_LE_DEFAULT != 0 && mcb_pool_le_preferred(P));
   return mcb_pool_covers(P) && (P.opt.tuneKernel ? P.opt.tuneKernel == MCB_KERNEL_POOL : mcb_pool_preferred(P));
 }
 

@@ -72,7 +72,9 @@ __device__ __forceinline__ float view_phase_value(const DevDomain &P, int compon
   return val * P.viewNorm[dir];                                                        // INT:1726
 }
 
-template <int THREADS, int MINBLOCKS, int BURST, bool MASK, bool BRICK, bool LEAP>
+// WIDE = false: grids with a period shorter than the ghost shell (the 32 x 1 x 32 step cloud): indices that ran into the
+// shell are folded with a remainder instead of one conditional add; x-fastest field, no bitmap, no leaps.
+template <int THREADS, int MINBLOCKS, int BURST, bool MASK, bool BRICK, bool LEAP, bool WIDE = true>
 __global__ void __launch_bounds__(THREADS, MINBLOCKS)
 pool_le_kernel(const __grid_constant__ DevDomain P, long long nPhotons, uint64_t seed, uint64_t firstPhotonId,
                unsigned long long *workCounter, const SmemPlan plan, const float leapBelow, const int leapLanes) {
@@ -155,7 +157,7 @@ pool_le_kernel(const __grid_constant__ DevDomain P, long long nPhotons, uint64_t
           px -= P.fLx * floorf((px - P.fx0) * P.finvLx);
           py -= P.fLy * floorf((py - P.fy0) * P.finvLy);
           if (state == ST_SCATTER) {
-            cell_decode<true, BRICK>(P, raw, ix, iy, iz);
+            cell_decode<WIDE, BRICK>(P, raw, ix, iy, iz);
           } else {
             ix = min(max((int)((px - P.fx0) * P.finvhx), 0), P.nx - 1);
             iy = min(max((int)((py - P.fy0) * P.finvhy), 0), P.ny - 1);
@@ -439,7 +441,7 @@ pool_le_kernel(const __grid_constant__ DevDomain P, long long nPhotons, uint64_t
       if (D) ev = march_leap<MASK>(r, P, D, crossed, ext, tgt, &sCnt[4]);
     }
     if (job != JOB_NONE && ev == MARCH_ON)
-      ev = march_burst<true, true, BURST, MASK, BRICK, true, MCB_PLE_SPLIT, LEAP>(r, P, G, ext, tgt, crossed, LEAP ? &vcur : nullptr);
+      ev = march_burst<true, WIDE, BURST, MASK, BRICK, true, MCB_PLE_SPLIT, LEAP>(r, P, G, ext, tgt, crossed, LEAP ? &vcur : nullptr);
     if (job == JOB_PHOTON) crossings += crossed; else leCrossings += crossed;
 
     // =========================== rays that ended ===========================
@@ -458,7 +460,7 @@ pool_le_kernel(const __grid_constant__ DevDomain P, long long nPhotons, uint64_t
           float qx, qy, qz;
           const int raw = r.ix;
           ray_position(r, P, qx, qy, qz);
-          cell_decode<true, BRICK>(P, raw, r.ix, r.iy, r.iz);
+          cell_decode<WIDE, BRICK>(P, raw, r.ix, r.iy, r.iz);
           r.ox = qx; r.oy = qy; r.oz = qz;
           ray_start<true>(r, P, G);
           ext = 0.0f; vcur = 0.0f; tgt = tauFree; job = JOB_E14B;
@@ -547,11 +549,11 @@ pool_le_kernel(const __grid_constant__ DevDomain P, long long nPhotons, uint64_t
 
 }  // namespace mcbpoolle
 
-template <int MINBLOCKS, bool MASK, bool BRICK, bool LEAP>
+template <int MINBLOCKS, bool MASK, bool BRICK, bool LEAP, bool WIDE = true>
 static void launch_pool_le(const DevDomain &P, long long nPhotons, uint64_t seed, uint64_t firstPhotonId, int numSMs,
                            unsigned long long *workCounter, cudaStream_t stream) {
   constexpr int THREADS = 128;
-  auto kernel = mcbpoolle::pool_le_kernel<THREADS, MINBLOCKS, MCB_PLE_BURST, MASK, BRICK, LEAP>;
+  auto kernel = mcbpoolle::pool_le_kernel<THREADS, MINBLOCKS, MCB_PLE_BURST, MASK, BRICK, LEAP, WIDE>;
   const int cols = P.nx * P.ny, cells = cols * P.nz;
   mcbfast::SmemPlan plan{-1, -1, -1, -1, -1, 0, 0, 0};
   int off = 0;
@@ -578,8 +580,18 @@ static void launch_pool_le(const DevDomain &P, long long nPhotons, uint64_t seed
 
 // runs with view directions on uniform grids at least a ghost shell wide, up to MCB_POOL_LE_MAXDIR directions
 bool mcb_pool_le_covers(const DevDomain &P) {
-  return P.uniform && P.nx >= MCB_GHOST && P.ny >= MCB_GHOST && P.nDir > 0 && P.nDir <= MCB_POOL_LE_MAXDIR &&
-         P.nx <= 65535 && P.ny <= 65535 && P.nz <= 65535;
+  const bool wide = P.nx >= MCB_GHOST && P.ny >= MCB_GHOST;
+  return P.uniform && P.nDir > 0 && P.nDir <= MCB_POOL_LE_MAXDIR && P.nx <= 65535 && P.ny <= 65535 && P.nz <= 65535 &&
+         (wide || (P.lin.mask == nullptr && P.opt.tuneLayout != MCB_LAYOUT_BRICKS));       // narrow grids: plain x-fastest field
+}
+
+// ... and is the default where it measured faster: grids at least a ghost shell wide (C3 + 5 views: 1.11e8 against the task
+// queue's 8.5e7).  Narrow grids (the 32 x 1 x 32 step cloud): MCB_PLE_NARROW_DEFAULT.
+#ifndef MCB_PLE_NARROW_DEFAULT
+#define MCB_PLE_NARROW_DEFAULT 1            // C2 step cloud + 5 views, one B200, r02: 1.67e8 against the task queue's 1.59e8
+#endif
+bool mcb_pool_le_preferred(const DevDomain &P) {
+  return (P.nx >= MCB_GHOST && P.ny >= MCB_GHOST) || MCB_PLE_NARROW_DEFAULT != 0;
 }
 
 // which layout of the extinction field this kernel reads (mcb_api.cu packs that one)
@@ -591,6 +603,12 @@ void mcb_launch_pool_le_batch(const DevDomain &P, long long nPhotons, uint64_t s
   const bool mask = P.lin.mask != nullptr, brick = mcb_pool_le_reads_bricks(P);
   const int occ = P.opt.tuneBlocksPerSM ? P.opt.tuneBlocksPerSM : 5;
 #define MCB_PLE_ARGS (P, nPhotons, seed, firstPhotonId, numSMs, workCounter, stream)
+  if (!(P.nx >= MCB_GHOST && P.ny >= MCB_GHOST)) {          // a period shorter than the ghost shell
+    if (occ >= 6) launch_pool_le<6, false, false, false, false> MCB_PLE_ARGS;
+    else if (occ == 5) launch_pool_le<5, false, false, false, false> MCB_PLE_ARGS;
+    else launch_pool_le<4, false, false, false, false> MCB_PLE_ARGS;
+    return;
+  }
 #define MCB_PLE_GO2(OCC, LEAP) \
   do { if (mask) { if (brick) launch_pool_le<OCC, true, true, LEAP> MCB_PLE_ARGS; else launch_pool_le<OCC, true, false, LEAP> MCB_PLE_ARGS; } \
        else { if (brick) launch_pool_le<OCC, false, true, LEAP> MCB_PLE_ARGS; else launch_pool_le<OCC, false, false, LEAP> MCB_PLE_ARGS; } } while (0)

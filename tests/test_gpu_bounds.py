@@ -43,6 +43,8 @@ cases["C5_taller_columns_pool"] = (domains.bench_domain(nxy=24, nz=96), False, 1
 cases["C3_small_views_pool"] = (domains.landsat_cloud(ssa=0.99, nxy=24, mie=True), True, 30000)        # ... and its view rays
 cases["C5_small_bitmap_views_pool"] = cases["C5_small_bitmap_views"]
 cases["C4_LW_views_pool"] = cases["C4_LW_views"]
+cases["C2_views_pool"] = cases["C2_views"]                                                # narrow grid on the pool LE kernel
+cases["narrow_views_pool"] = ((_tiny_domain(2, 9, 3), dict(solarMu=0.3, solarAzimuth=315.0)), True, 40000)
 out = {}
 from mcbrat3d_b200.emissionAndBroadBandWeights import Weights, emission_weighting
 for name, ((dom, case), views, n) in cases.items():

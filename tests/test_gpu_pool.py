@@ -147,6 +147,9 @@ LE_CASES = [
      dict(useRussianRouletteForIntensity=True, zetaMin=0.3), ([1.0, 0.5, -0.5], [0.0, 0.0, 180.0])),     # odd count, one looking down
     ("C4_LW_views", lambda: domains.homogeneous_lw(), 60000, dict(useRussianRouletteForIntensity=True, zetaMin=0.3),
      ([1.0, 0.5, -0.5], [0.0, 0.0, 90.0])),                                                               # births post requests too
+    ("C2_step_cloud_rr", lambda: domains.step_cloud(ssa=0.99, solarMu=0.5), 60000,                       # 32 x 1 x 32: narrower
+     dict(useRussianRouletteForIntensity=True, zetaMin=0.3), None),                                       # than the ghost shell
+    ("C2_step_cloud_plain", lambda: domains.step_cloud(ssa=1.0, solarMu=1.0), 40000, dict(useRussianRouletteForIntensity=False), None),
     ("reflecting_plain", lambda: domains.homogeneous_slab(ssa=0.9, tau=2.0, albedo=0.5, n=9, delta=0.125), 40000,
      dict(useRussianRouletteForIntensity=False), ([1.0, 0.866], [0.0, 0.0])),                             # surface requests
 ]
