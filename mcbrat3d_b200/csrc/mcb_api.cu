@@ -27,7 +27,7 @@ void mcb_launch_distance_map(const DevDomain &P, int cap, uint8_t *dist, uint8_t
 void mcb_launch_pack_crop(const DevDomain &P, float *ext, int numSMs, cudaStream_t stream);
 void mcb_launch_column_ranges(const DevDomain &P, uint32_t *range, int *count, int *offset, int *tileSum, int *sum, int numSMs,
                               cudaStream_t stream);
-void mcb_launch_column_fill(const DevDomain &P, const uint32_t *range, const int *offset, float *extC, uint32_t *recC,
+void mcb_launch_column_fill(const DevDomain &P, const uint32_t *range, const int *offset, uint32_t *recC,
                             uint32_t *cellC, uint2 *colTab, int numSMs, cudaStream_t stream);
 void mcb_launch_pack_field(const DevDomain &P, int brick, float *ext, uint32_t *mask, float *layerExt, int *flags, const uint8_t *dist, int *leapCount,
                            int numSMs, cudaStream_t stream);
@@ -87,7 +87,7 @@ struct mcb_handle {
   void *dColRange = nullptr, *dColCount = nullptr, *dColOffset = nullptr, *dColTab = nullptr;   // column-compressed storage
   void *dColTiles = nullptr;
   std::vector<float> hLayer;                     // host copy of layerExt (read with the leap count: the crop decision needs it)
-  void *dExtC = nullptr, *dRecC = nullptr, *dCellC = nullptr, *dExtCrop = nullptr, *dTallyC = nullptr;
+  void *dRecC = nullptr, *dCellC = nullptr, *dExtCrop = nullptr, *dTallyC = nullptr;
   void *dInv[MCB_MAX_COMP] = {nullptr}, *dFwd[MCB_MAX_COMP] = {nullptr}, *dFwdOrig[MCB_MAX_COMP] = {nullptr};
   int invE[MCB_MAX_COMP] = {0}, fwdE[MCB_MAX_COMP] = {0};
   void *dColCDF = nullptr, *dVoxelCDF = nullptr, *dTemps = nullptr, *dScratch = nullptr, *dResults = nullptr;
@@ -226,7 +226,7 @@ int mcb_destroy(mcb_handle *h) {
                    h->dTemps, h->dScratch, h->dResults, (void *)h->dFlags, h->dStats, h->dStatsOut,
                    h->dMassConc, h->dReff, h->dNumConc, h->dAsmTables, h->dExtMask, h->dLayerExt,
                    h->dExtBrick, h->dExtMaskBrick, h->dColCDF, h->dDist, h->dDistScratch,
-                   h->dColRange, h->dColCount, h->dColOffset, h->dColTab, h->dColTiles, h->dExtC, h->dRecC, h->dCellC, h->dExtCrop, h->dTallyC};
+                   h->dColRange, h->dColCount, h->dColOffset, h->dColTab, h->dColTiles, h->dRecC, h->dCellC, h->dExtCrop, h->dTallyC};
   for (void *p : slots) if (p) cudaFree(p);
   for (int c = 0; c < MCB_MAX_COMP; ++c) {
     if (h->dInv[c]) cudaFree(h->dInv[c]);
@@ -451,9 +451,9 @@ int mcb_set_optics(mcb_handle *h, int nc, const double *totalExt, const double *
 // field's layer table (setup_packed_field) and the event records.
 static int setup_compact_storage(mcb_handle *h) {
   DevDomain &P = h->P;
-  // Column-compressed storage for the pool flux kernel (fields marched through the bitmap, i.e. too large for L2): the
-  // cells inside the per-column ranges -- extinction, event record, cell index -- densely, column by column.
-  P.colTab = nullptr; P.extC = nullptr; P.recC = nullptr; P.cellC = nullptr; P.nCompact = 0; P.tallyC = nullptr;
+  // Column-compressed event data for the pool flux kernel (fields marched through the bitmap, i.e. too large for L2): for
+  // the cells inside the per-column ranges the event record, the cell index and an absorption tally, densely, column by column.
+  P.colTab = nullptr; P.recC = nullptr; P.cellC = nullptr; P.nCompact = 0; P.tallyC = nullptr;
   P.crp.ext = nullptr; P.cropLo = 0; P.cropN = 0;
   // (tuneExtMask = 1 keeps the run on the bitmap: nothing of this is built)
   if (P.lin.mask && P.opt.tuneExtMask != 1 && P.uniform && P.nx >= MCB_GHOST && P.ny >= MCB_GHOST && P.nz <= 65535) {
@@ -470,14 +470,14 @@ static int setup_compact_storage(mcb_handle *h) {
     CK(h, cudaMemcpyAsync(&nCompact, dSum, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
     if (settle(h)) return 1;
     const size_t n = nCompact > 0 ? (size_t)nCompact : 1;
-    if (reserve(h, &h->dExtC, sizeof(float) * n) || reserve(h, &h->dRecC, sizeof(uint32_t) * (n << P.recShift)) ||
+    if (reserve(h, &h->dRecC, sizeof(uint32_t) * (n << P.recShift)) ||
         reserve(h, &h->dCellC, sizeof(uint32_t) * n) || reserve(h, &h->dTallyC, sizeof(double) * n))
       return 1;
     CK(h, cudaMemsetAsync(h->dTallyC, 0, sizeof(double) * n, h->stream));
-    mcb_launch_column_fill(P, (const uint32_t *)h->dColRange, (const int *)h->dColOffset, (float *)h->dExtC, (uint32_t *)h->dRecC,
+    mcb_launch_column_fill(P, (const uint32_t *)h->dColRange, (const int *)h->dColOffset, (uint32_t *)h->dRecC,
                            (uint32_t *)h->dCellC, (uint2 *)h->dColTab, h->numSMs, h->stream);
     CK(h, cudaGetLastError());
-    P.colTab = (const uint2 *)h->dColTab; P.extC = (const float *)h->dExtC; P.recC = (const uint32_t *)h->dRecC;
+    P.colTab = (const uint2 *)h->dColTab; P.recC = (const uint32_t *)h->dRecC;
     P.cellC = (const uint32_t *)h->dCellC; P.nCompact = nCompact; P.tallyC = (double *)h->dTallyC;
     // The layer-cropped field: the band of layers that hold cloud somewhere (the sign bits of layerExt mark the layers
     // that are clear throughout), bricked, if it is small enough to stay in L2 (same 48 MB limit as the bitmap decision).

@@ -74,12 +74,11 @@ struct DevDomain {
   const float *layerCum;                      // nz + 1: clear-sky optical depth per unit |1/mu| from the surface to each edge
   // Column-compressed event records (photon-pool flux kernel on fields too large for L2): per padded column the range
   // of layers [lo, hi) outside which every cell has its layer's clear-sky value, and for the cells inside the ranges --
-  // a few per cent of a cloud scene -- the event record (and the extinction and the cell index), stored densely column by
+  // a few per cent of a cloud scene -- the event record, the cell index and an f64 absorption tally, stored densely column by
   // column: 35 MB instead of 253 MB on C5, so the records of the scattering cells stay in L2 next to the cropped field.
   // (Measured, r02: marching on this storage as well -- one table look-up per crossing, then the gather -- was 5 % SLOWER
   // than the bitmap: what bounds C5 is the dependent look-up -> gather chain of a crossing, not where the gather is served.)
   const uint2 *colTab;                        // lin.nxp x lin.nyp: .x = compact index of layer lo, .y = lo | hi << 16
-  const float *extC;                          // nCompact: (float)totalExt
   const uint32_t *recC;                       // nCompact << recShift: the cells' event records
   const uint32_t *cellC;                      // nCompact: ix + nx * (iy + ny * iz)
   double *tallyC;                             // nCompact: volume-absorption tally of those cells (added into tally after a launch)

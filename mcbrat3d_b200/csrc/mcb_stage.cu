@@ -174,17 +174,16 @@ __global__ void col_scan_kernel(const int *__restrict__ count, int n, const int 
   const int s = block_inclusive_scan_1024(v, part);
   if (i < n) offset[i] = tileOffset[blockIdx.x] + s - v;
 }
-// the cells inside the ranges: extinction, event record, cell index, column by column
-__global__ void col_fill_kernel(const double *__restrict__ totalExt, const uint32_t *__restrict__ rec, int recShift,
+// the cells inside the ranges: event record and cell index, column by column
+__global__ void col_fill_kernel(const uint32_t *__restrict__ rec, int recShift,
                                 const uint32_t *__restrict__ range, const int *__restrict__ offset, int cols, long long cells,
-                                float *__restrict__ extC, uint32_t *__restrict__ recC, uint32_t *__restrict__ cellC) {
+                                uint32_t *__restrict__ recC, uint32_t *__restrict__ cellC) {
   for (long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x; p < cells; p += (long long)gridDim.x * blockDim.x) {
     const int c = (int)(p % cols), k = (int)(p / cols);
     const uint32_t rg = range[c];
     const int lo = (int)(rg & 0xffffu), hi = (int)(rg >> 16);
     if (k < lo || k >= hi) continue;
     const long long i = (long long)offset[c] + (k - lo);
-    extC[i] = (float)totalExt[p];
     cellC[i] = (uint32_t)p;
     for (int w = 0; w < (1 << recShift); ++w) recC[(i << recShift) + w] = rec[(p << recShift) + w];
   }
@@ -1006,12 +1005,12 @@ void mcb_launch_column_ranges(const DevDomain &P, uint32_t *range, int *count, i
   mcbstage::col_scan_kernel<<<tiles, 1024, 0, stream>>>(count, cols, tileSum, offset);
 }
 // step 2: the compact arrays and the padded column table
-void mcb_launch_column_fill(const DevDomain &P, const uint32_t *range, const int *offset, float *extC, uint32_t *recC,
+void mcb_launch_column_fill(const DevDomain &P, const uint32_t *range, const int *offset, uint32_t *recC,
                             uint32_t *cellC, uint2 *colTab, int numSMs, cudaStream_t stream) {
   const int cols = P.nx * P.ny;
   const long long cells = (long long)cols * P.nz;
-  mcbstage::col_fill_kernel<<<stream_grid(cells, 256, numSMs), 256, 0, stream>>>(P.totalExt, P.rec, P.recShift, range, offset, cols,
-                                                                              cells, extC, recC, cellC);
+  mcbstage::col_fill_kernel<<<stream_grid(cells, 256, numSMs), 256, 0, stream>>>(P.rec, P.recShift, range, offset, cols,
+                                                                              cells, recC, cellC);
   mcbstage::col_table_kernel<<<stream_grid((long long)P.lin.nxp * P.lin.nyp, 256, numSMs), 256, 0, stream>>>(
       range, offset, P.nx, P.ny, MCB_GHOST, P.lin.nxp, P.lin.nyp, colTab);
 }
