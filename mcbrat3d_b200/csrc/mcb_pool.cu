@@ -26,8 +26,16 @@
 // distances), so a lane that pops a READY leg only loads it.  (First version: decode and leg set-up ran in the march
 // loop with the ~12 lanes that had just arrived -- 200 warp-instructions per burst at 12 of 32 lanes, ncu r02.)
 //
+// Variants (template parameters, chosen by mcb_launch_pool_batch from what the staging found):
+//   LEAP  -- the domain has vacuum (or, on bitmap-marched fields, layers that are clear throughout) worth leaping: a lane
+//            whose last gather says that its cell lies D >= 2 cells deep in it starts its iteration with march_leap
+//            (mcb_march.cuh) and then runs its burst from the landing cell;
+//   MASK  -- fields too large for L2, marched through the occupancy bitmap;
+//   CROP  -- fields too large for L2 whose cloud occupies a band of layers: the band as its own bricked, L2-resident field;
+//            event records and the absorption tally of the cells inside the per-column ranges in compact arrays
+//            (DevDomain::colTab / recC / tallyC), the tally added into the dense one after the launch.
 // Scope: flux / absorption runs (no view directions) on uniform grids at least a ghost shell wide -- C1, C3, C4, C5.
-// Everything else stays on mcb_fast.cu.  Statistical parity with the reference arithmetic (criterion (b)) is tested
+// Everything else stays on mcb_fast.cu (view directions: mcb_pool_le.cu).  Statistical parity with the reference arithmetic (criterion (b)) is tested
 // like the park kernel's; with the same seed the two kernels trace the SAME photon histories (same Philox blocks in
 // the same order per photon), so their tallies agree to summation order -- tests/test_gpu_pool.py.
 #include "mcb_march.cuh"

@@ -22,8 +22,9 @@
 //
 // Same physics, same random numbers per photon and per (event, direction) as le_run: with the same seed the two
 // kernels trace the same photon histories and the same view rays (tests/test_gpu_pool.py compares ray counts exactly
-// and radiances to summation order).  Scope: uniform grids at least a ghost shell wide, up to MCB_POOL_LE_MAXDIR view
-// directions; everything else stays on mcb_fast.cu.
+// and radiances to summation order).  Scope: uniform grids, up to MCB_POOL_LE_MAXDIR view directions -- grids at least a
+// ghost shell wide with every field variant of mcb_pool.cu except CROP (vacuum / clear-layer leaps for photon legs AND
+// view rays), narrower ones (the 32 x 1 x 32 step cloud) on the plain x-fastest field; everything else stays on mcb_fast.cu.
 #include "mcb_march.cuh"
 
 namespace mcbpoolle {
