@@ -37,7 +37,8 @@ METRIC_C5 = "photons/sec, I3RC bench SW cloud (C5, one wavelength bin)"
 METRIC_BB = "photons/sec, I3RC bench SW broadband (C5, 32 wavelength bins)"
 WORKLOAD_C5 = ("C5 I3RC bench cloud (synthetic scene, seed 5) 325x325x150 cells 0.0625x0.0625x0.03125 km, HG g=0.85 cloud "
                "(ssa 0.999) + Rayleigh background at 0.55 um (nc=2), mu0=0.5, albedo 0.05; fluxes + column/volume absorption; "
-               "78 MB padded f32 extinction field (> L2) marched through the occupancy bitmap")
+               "78 MB padded f32 extinction field (> L2): the cloud band of layers packed as its own L2-resident field, event records "
+               "and absorption tally of the cloudy columns' cells in compact arrays, clear layers leapt over")
 WORKLOAD_BB = ("C5 I3RC_bench_SW broadband: 325x325x160 cells, 32 wavelength bins 0.45-2.1 um, per-bin cloud optics interpolated "
                "in effective radius + gas absorption + Rayleigh (nc=3), photons allocated to bins by the flux CDF, mu0=0.5; "
                "a step = one whole spectral run (per-bin assembly, tables, photon allocation, tracing, batch statistics)")
