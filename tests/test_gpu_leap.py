@@ -169,3 +169,26 @@ def test_leap_counters():
         assert c["leaps"] > 0 and 2 * c["leaps"] <= c["leapCells"] < c["crossings"] + c["leCrossings"], (name, c)
         print("%s: %.2f leaps per photon, %.1f cells per leap, %.3f of the crossings" % (
             name, c["leaps"] / c["photons"], c["leapCells"] / c["leaps"], c["leapCells"] / (c["crossings"] + c["leCrossings"])))
+
+
+def test_an_empty_domain_is_crossed_in_leaps():
+    """Nothing but vacuum: every photon goes straight to the surface (flux down exactly 1), 30 % come back up and leave
+    through the top -- leaps on or off, and the leaps land on the boundaries exactly (same crossings up to the one cell
+    per exit that a burst may count beyond the boundary)."""
+    from mcbrat3d_b200.opticalProperties import Domain
+    from mcbrat3d_b200.scatteringPhaseFunctions import henyeyGreenstein, new_PhaseFunctionTable
+    nx, ny, nz = 24, 16, 40
+    d = Domain(0.25 * np.arange(nx + 1), 0.25 * np.arange(ny + 1), 0.125 * np.arange(nz + 1), surfaceAlbedo=0.3)
+    z = np.zeros((nz, ny, nx))
+    d.addOpticalComponent("nothing", z, z, np.zeros((nz, ny, nx), np.int32), new_PhaseFunctionTable([henyeyGreenstein(0.8, 16)], key=[1.0]))
+    d.getOpticalPropertiesByComponent()
+    case = dict(solarMu=0.4, solarAzimuth=33.0)
+    n = 200000
+    res = {}
+    for leap in (-1, 0):
+        r, c = _run(d, case, n, tuneLeap=leap)
+        assert c["bad"] == 0 and c["scatters"] == 0 and c["surfaceHits"] == n, c
+        assert abs(float(r["meanFluxDown"]) - 1.0) < 1e-6 and abs(float(r["meanFluxUp"]) - 0.3) < 1e-6, r
+        assert abs(float(r["meanFluxAbsorbed"])) < 1e-9
+        res[leap] = c
+    assert abs(res[0]["crossings"] - res[-1]["crossings"]) <= 2 * n + 2e-4 * res[-1]["crossings"], res
