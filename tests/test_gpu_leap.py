@@ -192,3 +192,45 @@ def test_an_empty_domain_is_crossed_in_leaps():
         assert abs(float(r["meanFluxAbsorbed"])) < 1e-9
         res[leap] = c
     assert abs(res[0]["crossings"] - res[-1]["crossings"]) <= 2 * n + 2e-4 * res[-1]["crossings"], res
+
+
+def test_thermal_source_below_vacuum_leaps():
+    """Emission bookkeeping with leaps: an emitting, scattering layer under an empty upper half of the domain, thermal
+    source (births inside the layer and at the surface, INT:504-508 decrements where a photon is born).  Leaps on / off
+    and the park/regroup kernel agree to the rounding-level differences of the other cases."""
+    from mcbrat3d_b200.emissionAndBroadBandWeights import Weights, emission_weighting
+    from mcbrat3d_b200.monteCarloRadiativeTransfer import MCB_KERNEL_PARK
+    from mcbrat3d_b200.opticalProperties import Domain
+    from mcbrat3d_b200.scatteringPhaseFunctions import henyeyGreenstein, new_PhaseFunctionTable
+    n3 = 24
+    edges = 0.0625 * np.arange(n3 + 1, dtype=np.float64)
+    d = Domain(edges, edges, edges, temps=np.full((n3, n3, n3), 285.0), surfaceAlbedo=0.1, lambda_um=10.0)
+    rng = np.random.default_rng(12)
+    ext = np.zeros((n3, n3, n3)); ext[:10] = rng.uniform(2.0, 12.0, (10, n3, n3)); ext[4:7, 5:9, 3:8] = 0.0    # a hole as well
+    ssa = np.where(ext > 0, 0.6, 0.0); idx = np.where(ext > 0, 1, 0).astype(np.int32)
+    d.addOpticalComponent("cloud", ext, ssa, idx, new_PhaseFunctionTable([henyeyGreenstein(0.8, 32)], key=[1.0]))
+    d.getOpticalPropertiesByComponent()
+    n = 400000
+    out = {}
+    for tag, knobs in (("park", dict(tuneKernel=MCB_KERNEL_PARK)), ("pool", dict(tuneKernel=MCB_KERNEL_POOL, tuneLeap=-1)),
+                       ("leap", dict(tuneKernel=MCB_KERNEL_POOL))):
+        g = new_Integrator(d)
+        try:
+            specifyParameters(g, minInverseTableSize=10001, LW_flag=1.0, **knobs)
+            rs = new_RandomNumberSequence([10, 1, 0])
+            w = Weights()
+            emission_weighting(d, w, 300.0, thisIntegrator=g)
+            ps = new_PhotonStream(theseWeights=w, numberOfPhotons=n, randomNumbers=rs)
+            assert computeRadiativeTransfer(g, d, rs, ps, n) == n
+            out[tag] = (reportResults(g, meanFluxUp=True, meanFluxDown=True, meanFluxAbsorbed=True, absorbedProfile=True),
+                        getCounters(g))
+        finally:
+            finalize_Integrator(g)
+    (rp, cp), (ro, co), (rl, cl) = out["park"], out["pool"], out["leap"]
+    assert cp["bad"] == co["bad"] == cl["bad"] == 0 and co["scatters"] == cp["scatters"]
+    for k in ("meanFluxUp", "meanFluxDown", "meanFluxAbsorbed"):
+        assert abs(float(ro[k]) - float(rp[k])) < 2e-6, k                       # same histories: summation order only
+        assert abs(float(rl[k]) - float(rp[k])) < 1e-3 * max(abs(float(rp[k])), 0.1), (k, float(rl[k]), float(rp[k]))
+    assert abs(cl["scatters"] - cp["scatters"]) <= 3e-4 * cp["scatters"] + 3
+    np.testing.assert_allclose(rl["absorbedProfile"], rp["absorbedProfile"], rtol=5e-3, atol=2e-4)
+    assert float(rp["meanFluxUp"]) > 0 and abs(float(rp["absorbedProfile"][12:].sum())) < 1e-12   # nothing is absorbed in vacuum
