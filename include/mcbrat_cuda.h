@@ -55,7 +55,9 @@ typedef struct {
   int32_t tuneBlocksPerSM;                  /* resident CTAs per SM of the flux kernels                       */
   int32_t tuneParkThreshold;                /* parked lanes that trigger an event phase (park kernel)         */
   int32_t tuneLeCarry;                      /* view rays parked between queue rounds: < 0 off, > 0 threshold  */
-  int32_t tuneExtMask;                      /* occupancy bitmap of the extinction field: < 0 off, > 0 on      */
+  int32_t tuneExtMask;                      /* treatment of fields too large for L2: < 0 off, > 0 on (default: on
+                                             * above 48 MB); 1 = occupancy bitmap only, 2 = also the layer-cropped
+                                             * field + compact event data of the pool flux kernel (what "on" means) */
   int32_t tuneBurst;                        /* cells per marching burst of the pool kernel (4 or 8)           */
   int32_t tuneLeap;                         /* vacuum leaps of the pool kernels: < 0 off, > 0 smallest distance */
   int32_t tuneLeapLanes;                    /* lanes of a warp that must want a leap for the warp to take one   */
