@@ -260,8 +260,8 @@ inline void specifyParameters(integrator &g, Status &status, const std::vector<f
   if (mcb_set_views(g.gpu, g.numDirections, dirs.empty() ? nullptr : dirs.data()) || mcb_set_options(g.gpu, &g.options))
     status.setStateToFailure(g.lastMessage("specifyParameters"));
 }
-// the per-batch getInfo_Domain copies of INT:434-443 become one staging per domain; the inverse tables of
-// INT:280 are built in HBM from the phase functions at their Lobatto nodes (INV:87-112 on the host, INV:113-168 on the device)
+// the per-batch getInfo_Domain copies of INT:434-443 become one staging per domain; the tables of INT:280-285 are
+// built in HBM
 inline void stageDomain(integrator &g, Domain &d, Status &status) {
   if (g.stagedDomain == &d) return;
   if (d.totalExt.empty()) getOpticalPropertiesByComponent(d, status);
@@ -269,35 +269,23 @@ inline void stageDomain(integrator &g, Domain &d, Status &status) {
   const int nc = (int)d.components.size();
   if (mcb_set_optics(g.gpu, nc, d.totalExt.data(), d.cumulativeExt.data(), d.ssa.data(), d.phaseFunctionIndex.data(), d.surfaceAlbedo))
     return status.setStateToFailure(g.lastMessage("computeRadiativeTransfer"));
+  // Every table is built in HBM from the Legendre moments alone (round 2): the Lobatto abscissas, the phase function
+  // there and the inversion (INV:66-174: mcb_build_inverse_table_legendre), and the equal-angle forward tables of
+  // tabulateForwardPhaseFunctions OPT:1872-1934 (mcb_build_forward_table_general; no hybrid peak asked for here).
+  // computeLobattoMus / getPhaseFunctionValuesAtMus above remain as the host-side statement of the same arithmetic.
   for (int c = 0; c < nc; ++c) {
-    std::vector<int32_t> nAngles; std::vector<float> musAll, valuesAll;
+    std::vector<int32_t> nCoef; std::vector<float> coefs;
     for (const phaseFunction &pf : d.components[c].table.phaseFunctions) {
-      const int n = std::max((int)pf.legendreCoefficients.size(), 2);                 // INV:107-112
-      const std::vector<float> mus = computeLobattoMus(n);
-      std::vector<float> back(mus.rbegin(), mus.rend());                            // acos(mus(n:1:-1)) then reversed again = values at mus
-      std::vector<float> cosAng(back.size());
-      for (size_t i = 0; i < back.size(); ++i) cosAng[i] = (float)std::cos((double)(float)std::acos((double)back[i]));
-      std::vector<float> v = getPhaseFunctionValuesAtMus(pf, cosAng);
-      std::reverse(v.begin(), v.end());
-      nAngles.push_back(n); musAll.insert(musAll.end(), mus.begin(), mus.end()); valuesAll.insert(valuesAll.end(), v.begin(), v.end());
+      nCoef.push_back((int32_t)pf.legendreCoefficients.size());
+      coefs.insert(coefs.end(), pf.legendreCoefficients.begin(), pf.legendreCoefficients.end());
     }
-    if (mcb_build_inverse_table(g.gpu, c + 1, g.minInverseTableSize, (int)nAngles.size(), nAngles.data(), musAll.data(), valuesAll.data()))
+    if (mcb_build_inverse_table_legendre(g.gpu, c + 1, g.minInverseTableSize, (int)nCoef.size(), nCoef.data(),
+                                         coefs.empty() ? nullptr : coefs.data()))
       return status.setStateToFailure(g.lastMessage("tabulateInversePhaseFunctions"));
-  }
-  if (g.numDirections > 0) {                            // tabulateForwardPhaseFunctions OPT:1872-1934 (no hybrid peak)
-    const int nS = g.minForwardTableSize;
-    std::vector<float> cosAng(nS);
-    const float Pi = 3.14159265358979312f;
-    for (int i = 0; i < nS; ++i) cosAng[i] = (float)std::cos((double)((float)i / (float)(nS - 1) * Pi));   // OPT:1912-1913
-    for (int c = 0; c < nc; ++c) {
-      std::vector<float> tab;
-      for (const phaseFunction &pf : d.components[c].table.phaseFunctions) {
-        const std::vector<float> v = getPhaseFunctionValuesAtMus(pf, cosAng);
-        tab.insert(tab.end(), v.begin(), v.end());
-      }
-      if (mcb_set_forward_table(g.gpu, c + 1, nS, (int)d.components[c].table.phaseFunctions.size(), tab.data(), nullptr))
-        return status.setStateToFailure(g.lastMessage("tabulateForwardPhaseFunctions"));
-    }
+    if (g.numDirections > 0 &&
+        mcb_build_forward_table_general(g.gpu, c + 1, g.minForwardTableSize, (int)nCoef.size(), nCoef.data(),
+                                        coefs.empty() ? nullptr : coefs.data(), nullptr, nullptr, nullptr, 0.0f))
+      return status.setStateToFailure(g.lastMessage("tabulateForwardPhaseFunctions"));
   }
   g.numComps = nc; g.stagedDomain = &d;
 }
