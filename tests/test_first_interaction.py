@@ -17,9 +17,6 @@ import pytest
 import first_interaction as fi
 from independent_3d import Medium, phase_value
 
-EV_BIRTH, EV_SCATTER, EV_SURFACE, EV_KILLED_SURFACE, EV_KILLED_ROULETTE, EV_LE = 1, 2, 3, 5, 6, 8
-
-
 # ---- the solver itself: closed forms of a homogeneous slab ------------------------------------------------------------
 def test_solver_reproduces_the_homogeneous_slab_closed_forms():
     nx, ny, nz = 3, 2, 5
@@ -68,39 +65,6 @@ def test_fixture_is_what_the_solver_computes(kind):
 
 
 # ---- the oracle's photon histories, first interaction taken out of the event trace --------------------------------------
-def first_interaction_of_trace(ev, n, nDir, med):
-    """(first-collision counts per cell, uncollided surface arrivals per column, sum of first-order local-estimate
-    contributions (nDir, ncol), same for the surface-reflected direct beam) of n traced photons."""
-    ncol = med.nx * med.ny
-    le = ev["kind"] == EV_LE
-    major = ~le & (ev["kind"] != EV_BIRTH)
-    c = np.cumsum(major)
-    base = np.zeros(len(ev), np.int64)
-    birth = ev["kind"] == EV_BIRTH
-    base[birth] = c[birth]
-    k = c - np.maximum.accumulate(base)                  # major events of this photon so far (events are in photon order)
-    fe = ev[major & (k == 1)]                            # every photon's first event after its birth
-    coll = (fe["kind"] == EV_SCATTER) | (fe["kind"] == EV_KILLED_ROULETTE)
-    surf = (fe["kind"] == EV_SURFACE) | (fe["kind"] == EV_KILLED_SURFACE)
-    assert coll.sum() + surf.sum() == n, np.unique(fe["kind"], return_counts=True)
-    cell = (fe["ix"] - 1) + med.nx * ((fe["iy"] - 1) + med.ny * (fe["iz"] - 1))
-    cells = np.bincount(cell[coll], minlength=med.sigma.size)
-    cols = np.bincount(((fe["ix"] - 1) + med.nx * (fe["iy"] - 1))[surf], minlength=ncol)
-    firstKind = np.zeros(n, np.int32)
-    firstKind[fe["photon"]] = fe["kind"]
-    out = []
-    # local-estimate events precede their scattering event and follow their surface event (INT:681-700, 776-790)
-    for sel in (le & (k == 0), le & (k == 1) & (ev["order"] == 1) & (firstKind[ev["photon"]] == EV_SURFACE)):
-        e = ev[sel]
-        idx = (e["component"] - 1) * ncol + (e["ix"] - 1) + med.nx * (e["iy"] - 1)
-        out.append(np.bincount(idx, weights=e["weight"].astype(np.float64), minlength=nDir * ncol).reshape(nDir, ncol))
-    return cells, cols, out[0], out[1]
-
-
-def z_stats(z):
-    return float(np.sqrt(np.mean(z ** 2))), float(z.mean()), float(np.abs(z).max())
-
-
 @pytest.mark.parametrize("rr", [0, 1], ids=["le", "le_rr"])
 @pytest.mark.parametrize("kind", fi.KINDS)
 def test_oracle_first_interaction_matches_the_independent_solver(orc, kind, rr):
@@ -119,36 +83,28 @@ def test_oracle_first_interaction_matches_the_independent_solver(orc, kind, rr):
         # enough random numbers for the birth, the first leg, the first event and its view rays; the photon then runs out
         rn = np.random.default_rng(1000 * rr + 100 + b).random((n, 10 + 3 * nDir), dtype=np.float32)
         ev = g.trace(rn, 0, fi.SOLAR_MU, fi.SOLAR_AZIMUTH, maxEvents=n * (6 + 4 * nDir))
-        c, s, l1, l0 = first_interaction_of_trace(ev, n, nDir, med)
+        c, s, l1, l0 = fi.first_interaction_of_trace(ev, n, nDir, med)
         cells += c; cols += s; L1[b] = l1 / n; L0[b] = l0 / n
 
-    # where the first collision happens: multinomial counts against Beer's law along the slant paths
-    p = fx["first"].ravel()
-    assert cells[p == 0].sum() == 0                         # nothing collides in empty cells
-    ok = N * p > 25
-    rms, mean, worst = z_stats((cells - N * p)[ok] / np.sqrt(N * p * (1 - p))[ok])
-    assert ok.sum() > 250 and rms < 1.12 and abs(mean) < 4.0 / np.sqrt(ok.sum()) and worst < 4.8, (kind, rms, mean, worst)
-    for axis, what in (((1, 2), "layers"), ((0, 2), "rows"), ((0, 1), "x-slabs")):   # aggregated: sigma ~ 0.3 % relative
-        q = fx["first"].sum(axis=axis)
-        zz = (cells.reshape(fx["first"].shape).sum(axis=axis) - N * q)[q > 0] / np.sqrt(N * q * (1 - q))[q > 0]
-        assert np.abs(zz).max() < 4.0, (kind, what, zz)
-    # where the uncollided beam lands
-    q = fx["surf"].ravel()
-    rms, mean, worst = z_stats((cols - N * q) / np.sqrt(N * q * (1 - q)))
-    assert rms < 1.35 and abs(mean) < 0.6 and worst < 4.5, (kind, "surface", rms, mean, worst)
-    assert abs(cols.sum() - N * q.sum()) < 4.0 * np.sqrt(N * q.sum())
+    fi.check_first_interaction(kind, albedo, rr, cells, cols, L1, L0, N)
 
-    # first-order radiance and the surface-reflected direct beam, per view direction and exit column
-    for i, mu in enumerate(fi.VIEW_MUS):
-        for what, L, E in (("E1", L1[:, i], fx["E1"][i].ravel()), ("E0", L0[:, i], albedo * fx["E0"][i].ravel())):
-            if rr and mu < 0:                               # the roulette form only counts rays that reach the TOP (INT:1768-1800)
-                assert L.sum() == 0.0
-                continue
-            m, se = L.mean(axis=0), L.std(axis=0, ddof=1) / np.sqrt(B)
-            tot = L.sum(axis=1)
-            zt = (tot.mean() - E.sum()) / (tot.std(ddof=1) / np.sqrt(B))
-            assert abs(zt) < 4.2, (kind, what, i, tot.mean(), E.sum(), zt)
-            if what == "E1":                                # (surface arrivals are too few per column and batch for a z-map)
-                rms, mean, worst = z_stats((m - E) / se)    # Student t, 19 degrees of freedom: rms 1.06 if unbiased
-                assert rms < 1.45 and abs(mean) < 0.65 and worst < 6.5, (kind, what, i, rms, mean, worst)
-                assert abs(tot.mean() / E.sum() - 1.0) < 0.012
+
+def test_absorber_checker_accepts_an_unbiased_sampler_and_sees_a_small_bias():
+    """The statistical check the GPU pure-absorber test applies (fi.check_absorber), exercised on CPU with multinomial
+    samples of the committed probabilities at the GPU test's photon count: it passes an unbiased sampler and fails one
+    that moves 0.2 % of one layer's collisions into the layer below (the power the GPU test has)."""
+    fx = fi.fixture("irregular")
+    nb, n = 16, 2_500_000
+    for bias in (0.0, 2e-3):
+        p = fx["first"].copy()
+        moved = bias * p[5].sum()
+        p[5] *= 1.0 - bias; p[4] *= 1.0 + moved / p[4].sum()
+        pAll = np.concatenate([p.ravel(), fx["surf"].ravel()])
+        counts = np.random.default_rng(8).multinomial(n, pAll / pAll.sum(), size=nb) / n
+        first = counts[:, :p.size].reshape((nb,) + p.shape)
+        surf = counts[:, p.size:].reshape((nb,) + fx["surf"].shape)
+        if bias == 0.0:
+            fi.check_absorber("synthetic", first, surf, fx)
+        else:
+            with pytest.raises(AssertionError):
+                fi.check_absorber("synthetic biased", first, surf, fx)

@@ -22,7 +22,7 @@ import first_interaction as fi
 from mcbrat3d_b200.monteCarloIllumination import new_PhotonStream
 from mcbrat3d_b200.monteCarloRadiativeTransfer import (MCB_ARITH_REFERENCE, MCB_KERNEL_PARK, MCB_KERNEL_POOL,
                                                        computeRadiativeTransfer, finalize_Integrator, getCounters,
-                                                       new_Integrator, reportResults, specifyParameters)
+                                                       new_Integrator, reportResults, specifyParameters, tracePhotons)
 from mcbrat3d_b200.RandomNumbersForMC import new_RandomNumberSequence
 
 pytestmark = pytest.mark.gpu
@@ -56,8 +56,35 @@ def area_fraction(dom):
     return np.outer(np.diff(y), np.diff(x)) / ((x[-1] - x[0]) * (y[-1] - y[0]))
 
 
-def z_stats(z):
-    return float(np.sqrt(np.mean(z ** 2))), float(z.mean()), float(np.abs(z).max())
+z_stats = fi.z_stats
+
+
+@pytest.mark.parametrize("rr", [False, True], ids=["le", "le_rr"])
+@pytest.mark.parametrize("kind", fi.KINDS)
+def test_trace_kernel_first_interaction_matches_the_independent_solver(kind, rr):
+    """The reference-arithmetic CUDA kernel's own event trace (mcbref::trace_kernel), taken apart exactly like the
+    oracle's in tests/test_first_interaction.py: first-collision cells, landing columns, first-order radiance maps and
+    the surface term against the deterministic answers."""
+    albedo = 0.25
+    dom, med = fi.scene(kind, albedo=albedo)
+    nDir, ncol = len(fi.VIEW_MUS), med.nx * med.ny
+    B, n = 20, 15000
+    g = new_Integrator(dom)
+    try:
+        specifyParameters(g, intensityMus=fi.VIEW_MUS, intensityPhis=fi.VIEW_PHIS, computeIntensity=True,
+                          useRussianRouletteForIntensity=rr, zetaMin=0.3, minInverseTableSize=9001, minForwardTableSize=9001)
+        rs = new_RandomNumberSequence([10, 1, 0])
+        ps = new_PhotonStream(fi.SOLAR_MU, fi.SOLAR_AZIMUTH, n, rs)
+        cells, cols = np.zeros(med.sigma.size), np.zeros(ncol)
+        L1, L0 = np.zeros((B, nDir, ncol)), np.zeros((B, nDir, ncol))
+        for b in range(B):
+            rn = np.random.default_rng(5000 + 1000 * rr + b).random((n, 10 + 3 * nDir), dtype=np.float32)
+            ev, _ = tracePhotons(g, dom, ps, rn, maxEventsPerPhoton=8 + 6 * nDir)
+            c, s, l1, l0 = fi.first_interaction_of_trace(ev, n, nDir, med)
+            cells += c; cols += s; L1[b] = l1 / n; L0[b] = l0 / n
+    finally:
+        finalize_Integrator(g)
+    fi.check_first_interaction(kind, albedo, int(rr), cells, cols, L1, L0, B * n)
 
 
 ABSORBER = [("regular", (1, 1), {}), ("regular_pool", (2, 2), dict(tuneKernel=MCB_KERNEL_POOL)),
@@ -82,21 +109,7 @@ def test_pure_absorber_matches_beers_law_along_slant_paths(name, tiles, params):
     assert np.all(rows["fluxUp"] == 0.0)
     assert np.all(first[:, fx["first"] == 0] == 0.0)                                            # nothing is absorbed in empty cells
     np.testing.assert_allclose(first.sum(axis=(1, 2, 3)) + surf.sum(axis=(1, 2)), 1.0, atol=1e-5)   # every photon ends somewhere
-    quad = 3e-5                                            # the fixture's own quadrature error, relative to the largest entry
-    for what, got, want, minP in (("cells", first, fx["first"], 2e-4), ("surface", surf, fx["surf"], 0.0)):
-        m, se = got.mean(axis=0), got.std(axis=0, ddof=1) / np.sqrt(NB)
-        ok = want > minP
-        z = (m - want)[ok] / np.sqrt(se[ok] ** 2 + (quad * want.max()) ** 2)
-        rms, mean, worst = z_stats(z)                       # Student t, 15 degrees of freedom: rms 1.07 if unbiased
-        print("%s %s: n %d rms %.3f mean %+.3f max %.2f" % (name, what, z.size, rms, mean, worst))
-        assert rms < (1.25 if what == "cells" else 1.45) and abs(mean) < 4.5 / np.sqrt(z.size) and worst < 6.0, (name, what, rms, mean, worst)
-    # aggregated (sigma ~ 2e-4 relative): the absorption profile and the total transmission
-    layers, want = first.sum(axis=(2, 3)), fx["first"].sum(axis=(1, 2))
-    z = (layers.mean(axis=0) - want) / np.sqrt(layers.var(axis=0, ddof=1) / NB + (quad * want.max()) ** 2)
-    print("%s layers: z %s rel %s" % (name, np.round(z, 2), np.round(layers.mean(axis=0) / want - 1, 5)))
-    assert np.abs(z).max() < 4.5, (name, z)
-    t = surf.sum(axis=(1, 2))
-    assert abs(t.mean() - fx["surf"].sum()) < 4.5 * t.std(ddof=1) / np.sqrt(NB) + quad * fx["surf"].sum(), (name, t.mean(), fx["surf"].sum())
+    fi.check_absorber(name, first, surf, fx)
 
 
 RADIANCE = [("regular", (1, 1), {}), ("regular_park", (1, 1), dict(tuneKernel=MCB_KERNEL_PARK)),
