@@ -194,16 +194,17 @@ __device__ void le_run(const DevDomain &P, const Grid &G, const Tally &T, uint32
       } else if ((cnt.leCrossings += crossed, ev != MARCH_ON)) {
         float contribution = 0.0f;
         bool finished = true;
-        if (phase == PH_PLAIN) {
-          contribution = w * npf * __expf(-ext);
+        if (phase == PH_PLAIN) {                         // "extinction values < 0" signal a failed trace: no contribution (INT:1745-1751)
+          contribution = ext < -1.0e-3f ? 0.0f : w * npf * __expf(-ext);
         } else if (phase == PH_E13) {
           contribution = (ev == MARCH_TOP && uTest <= PI32 * npf / P.opt.zetaMin) ? w * P.opt.zetaMin / PI32 : 0.0f;
         } else if (phase == PH_E14A) {
           if (ev == MARCH_TOP) {
-            contribution = w * npf * __expf(-ext);
+            contribution = ext < -1.0e-3f ? 0.0f : w * npf * __expf(-ext);
           } else if (ev == MARCH_HIT) {                  // continue from where the first trace stopped (INT:1793-1795)
             float qx, qy, qz;
             ray_position(r, P, qx, qy, qz);
+            if (!REG) seam_fix(P, G, r.ix, r.iy, qx, qy);
             r.ox = qx; r.oy = qy; r.oz = qz;
             ray_start<REG>(r, P, G);
             ext = 0.0f; tgt = tauFree; phase = PH_E14B;
@@ -358,6 +359,7 @@ batch_kernel(const __grid_constant__ DevDomain P, long long nPhotons, uint64_t s
         w *= ssa;
       }
       ray_position(r, P, px, py, pz);
+      if (!REG) seam_fix(P, G, r.ix, r.iy, px, py);
       if (LE && P.nDir > 0) { le_post(sle, lane, P, rng, r, px, py, pz, w, comp, comp, order, pidx); posted = true; }   // INT:776-800
       if (P.opt.useRussianRoulette && w < P.opt.russianRouletteW * 0.5f) {     // INT:805-811
         const float uRR = P.nc > 1 ? __fdividef(uNext - lo, fmaxf(hi - lo, TINY32)) : uNext;

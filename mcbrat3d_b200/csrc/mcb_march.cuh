@@ -103,6 +103,20 @@ __device__ __forceinline__ void ray_position(const Ray &r, const DevDomain &P, f
   py -= P.fLy * floorf((py - P.fy0) * P.finvLy);
 }
 
+// Edge-table grids: make an event's folded position agree with its cell.  ray_position() folds by the rounded quotient
+// (p - x0) / L, the marcher wraps the integer cell index; for an event within rounding of the periodic seam (~1e-7 of
+// the events) the two can disagree by one whole period -- position at one end of the domain, cell at the other.  On
+// uniform grids the next leg then merely flies one period too far inside that cell (face distances advance by whole
+// cell widths from the first, clamped one); with edge tables every face distance is recomputed from the absolute edge,
+// so the first steps of the leg get NEGATIVE lengths, its optical depth goes negative and a local-estimate
+// contribution w * P * exp(-tau) blows up (seen once in 3.7e8 scatterings: tests/test_gpu_first_interaction.py).
+// The position is moved by the one period that puts it next to its cell.
+__device__ __forceinline__ void seam_fix(const DevDomain &P, const Grid &G, int ix, int iy, float &px, float &py) {
+  const float ex = px - 0.5f * (G.sx[ix] + G.sx[ix + 1]), ey = py - 0.5f * (G.sy[iy] + G.sy[iy + 1]);
+  px -= ex > 0.5f * P.fLx ? P.fLx : (ex < -0.5f * P.fLx ? -P.fLx : 0.0f);
+  py -= ey > 0.5f * P.fLy ? P.fLy : (ey < -0.5f * P.fLy ? -P.fLy : 0.0f);
+}
+
 __device__ __forceinline__ int find_cell(const float *e, int n, float x) {
   int lo = 0, hi = n;                      // e[lo] <= x < e[hi]
   while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (x >= e[mid]) lo = mid; else hi = mid; }
