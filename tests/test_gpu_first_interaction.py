@@ -120,6 +120,8 @@ RADIANCE = [("regular", (1, 1), {}), ("regular_park", (1, 1), dict(tuneKernel=MC
 @pytest.mark.parametrize("rr", [False, True], ids=["le", "le_rr"])
 @pytest.mark.parametrize("name,tiles,params", RADIANCE, ids=[c[0] for c in RADIANCE])
 def test_first_order_radiances_match_the_independent_solver(name, tiles, params, rr):
+    """(The "stretched-le" case is also the regression test of mcb_march.cuh::seam_fix: photon batch 8 of the second run
+    holds the event at the periodic seam that, before the fix, put 1e11 ... inf into three radiance maps.)"""
     kind = name.split("_")[0]
     fx = fi.fixture(kind)
     s, n = 0.005, 2_000_000
