@@ -21,7 +21,7 @@ NX, NY, NZ = 8, 6, 7
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 
-def scene(kind="irregular", albedo=0.25, ssaScale=1.0, tiles=(1, 1), seed=3):
+def scene(kind="irregular", albedo=0.25, ssaScale=1.0, tiles=(1, 1), seed=3, temps=None, lambda_um=0.0):
     """(Domain, Medium of ONE tile).  ``tiles`` repeats the scene periodically in x and y — the same physics on a
     larger grid (results fold back onto the tile), which is how the kernels for wide grids see this scene."""
     nx, ny, nz = NX, NY, NZ
@@ -29,6 +29,9 @@ def scene(kind="irregular", albedo=0.25, ssaScale=1.0, tiles=(1, 1), seed=3):
         xE = 0.0625 * np.arange(nx + 1); yE = 0.03125 * np.arange(ny + 1); zE = 0.03125 * np.arange(nz + 1)
     elif kind == "irregular":
         xE = 0.05 * np.arange(nx + 1); yE = 0.03 * np.arange(ny + 1); zE = 0.04 * np.arange(nz + 1)
+    elif kind == "zstretched":                   # uniform columns, stretched layers (the usual LES grid)
+        xE = 0.05 * np.arange(nx + 1); yE = 0.03 * np.arange(ny + 1)
+        zE = np.concatenate([[0.0], np.cumsum(0.025 * 1.15 ** np.arange(nz))])
     elif kind == "stretched":
         xE = np.concatenate([[0.0], np.cumsum(0.05 * (1 + 0.3 * np.sin(1.0 + np.arange(nx))))])
         yE = np.concatenate([[0.0], np.cumsum(0.03 * (1 + 0.25 * np.cos(0.5 + np.arange(ny))))])
@@ -59,7 +62,7 @@ def scene(kind="irregular", albedo=0.25, ssaScale=1.0, tiles=(1, 1), seed=3):
         else:
             xE = (xE[1] - xE[0]) * np.arange(nx * tx + 1); yE = (yE[1] - yE[0]) * np.arange(ny * ty + 1)
         ext1, ssa1, idx1 = (np.tile(a, (1, ty, tx)) for a in (ext1, ssa1, idx1))
-    d = Domain(xE, yE, zE, surfaceAlbedo=albedo)
+    d = Domain(xE, yE, zE, temps=temps, surfaceAlbedo=albedo, lambda_um=lambda_um)
     d.addOpticalComponent("cloud", ext1, ssa1, idx1,
                           new_PhaseFunctionTable([new_PhaseFunction(legendreCoefficients=c) for c in hg], key=[1.0, 2.0]))
     d.addOpticalComponent("gas", profile, np.full(4, 0.4 * ssaScale), np.ones(4, np.int32),

@@ -169,3 +169,46 @@ class Medium:
         E0 = np.bincount(col, weights=w * self.albedo / np.pi * np.exp(-self.optical_depth(foot, -sun) - tauView),
                          minlength=self.nx * self.ny)
         return E1.reshape(self.ny, self.nx), E0.reshape(self.ny, self.nx)
+
+
+# ---- thermal emission: where photons are born and what they contribute at birth (zeroth order) ----------------------------
+def planck(lambda_um, T):
+    """Spectral radiance of a black body (any constant factor cancels: only ratios of powers are used)."""
+    h, c, k = 6.62606957e-34, 2.99792458e8, 1.3806488e-23
+    lam = lambda_um * 1.0e-6
+    return 2.0 * h * c * c / lam ** 5 / np.expm1(h * c / (lam * k * np.asarray(T, dtype=np.float64)))
+
+
+def thermal_source(med, temps, lambda_um, sfcTemp):
+    """Kirchhoff: a cell emits 4 pi kappa_abs B(T) V isotropically, the Lambertian surface pi (1 - albedo) B(T_s) A.
+    Returns (probability that a photon is born in each cell (nz, ny, nx), probability that it is born at the surface,
+    kappa_abs B per cell / p and emissivity B_s / p, with p the total power per unit area)."""
+    kappa = (med.ext * (1.0 - med.ssa)).sum(axis=0)                        # (nz, ny, nx), per km
+    B = planck(lambda_um, temps)
+    dz = np.diff(med.zE)[:, None, None]
+    cellPower = 4.0 * np.pi * kappa * B * dz * med.area[None, :, :]          # per unit domain area
+    sfcPower = np.pi * (1.0 - med.albedo) * float(planck(lambda_um, sfcTemp))
+    p = cellPower.sum() + sfcPower
+    return cellPower / p, sfcPower / p, kappa * B / p, (1.0 - med.albedo) * float(planck(lambda_um, sfcTemp)) / p
+
+
+def emission_radiance(med, temps, lambda_um, sfcTemp, muV, phiV, m=24):
+    """Expected local-estimate contribution AT BIRTH per photon, by exit column (ny, nx): the emission integral
+    int kappa_abs B exp(-tau) ds along the line of sight plus the transmitted surface emission, over the total power
+    (INT:513-542, 1695-1696: isotropic emission contributes weight / (4 pi |mu|) exp(-tau), the surface weight / pi
+    exp(-tau); a downward view "ray" from the surface leaves at once, tau = 0).  Every piece is integrated exactly
+    (source and extinction are constant in a cell)."""
+    _, _, src, sfc = thermal_source(med, temps, lambda_um, sfcTemp)
+    src = src.ravel()
+    view = direction(muV, phiV)
+    e, col = med.sub_grid(m, med.zE[-1] if view[2] > 0 else med.zE[0])
+    w = med.area.ravel()[col] / (m * m)
+    t, cell, _ = med.pieces(e, -view)
+    dt = np.diff(t, axis=1)
+    sig = med.sigma[cell]
+    dtau = dt * sig
+    before = dtau.cumsum(axis=1) - dtau
+    seg = np.where(sig > 0, -np.expm1(-dtau) / np.where(sig > 0, sig, 1.0), dt)      # int_0^L exp(-sigma s) ds
+    line = (src[cell] * np.exp(-before) * seg).sum(axis=1)
+    line += sfc * (np.exp(-dtau.sum(axis=1)) if view[2] > 0 else 1.0)
+    return np.bincount(col, weights=w * line, minlength=med.nx * med.ny).reshape(med.ny, med.nx)

@@ -15,7 +15,7 @@ import numpy as np
 import pytest
 
 import first_interaction as fi
-from independent_3d import Medium, phase_value
+from independent_3d import Medium, emission_radiance, phase_value, thermal_source
 
 # ---- the solver itself: closed forms of a homogeneous slab ------------------------------------------------------------
 def test_solver_reproduces_the_homogeneous_slab_closed_forms():
@@ -108,3 +108,63 @@ def test_absorber_checker_accepts_an_unbiased_sampler_and_sees_a_small_bias():
         else:
             with pytest.raises(AssertionError):
                 fi.check_absorber("synthetic biased", first, surf, fx)
+
+
+# ---- thermal source: where photons are born and the emission they contribute at birth ---------------------------------------
+@pytest.mark.parametrize("kind", ["regular", "irregular", "zstretched"])
+def test_oracle_thermal_births_and_emission_radiance_match_the_independent_solver(orc, kind):
+    """Kirchhoff's law and the emission integral in a 3-D scene with a temperature that differs from cell to cell: the
+    share of the atmosphere in the emitted power (emission_weighting, EMI:424-550: equal to 1e-12), the cell every
+    photon is born in (findCDFIndex on the voxel CDF, ILL:481-515), the surface births, and the local-estimate
+    contribution at birth per view direction and exit column (INT:513-542, 1695-1696) against
+    int kappa_abs B exp(-tau) ds + transmitted surface emission, integrated exactly piece by piece along sorted plane
+    crossings (tests/independent_3d.py).  Grids with uniform columns only: the reference's voxel weights carry no cell
+    area (EMI:489-496 weighs a cell by 4 pi B kappa dz).  One reference behaviour shows up and is asserted: a photon born
+    AT the surface contributes nothing to a downward view (its view ray has no first step; the marcher signals an error
+    and INT:1745-1751 drops the contribution) although a photon REFLECTED there does (tests above)."""
+    albedo, lam, sfcT = 0.25, 10.0, 300.0
+    temps = 250.0 + 40.0 * np.random.default_rng(5).random((fi.NZ, fi.NY, fi.NX))
+    dom, med = fi.scene(kind, albedo=albedo, temps=temps, lambda_um=lam)
+    od = orc.OracleDomain(dom, tableSize=9001, forward=True)
+    frac, cdf, _ = od.emission_weighting(temps, lam, sfcT)
+    pCell, pSfc, _, sfcTerm = thermal_source(med, temps, lam, sfcT)
+    assert abs(frac - pCell.sum()) < 1e-12 and abs(pCell.sum() + pSfc - 1.0) < 1e-12
+    g = orc.OracleIntegrator(od, LW_flag=1.0)
+    g.set_views(fi.VIEW_MUS, fi.VIEW_PHIS)
+    nDir, ncol = len(fi.VIEW_MUS), med.nx * med.ny
+    B, n = 20, 15000
+    N = B * n
+    births, sfcBirths, L = np.zeros(med.sigma.size), np.zeros(ncol), np.zeros((B, nDir, ncol))
+    for b in range(B):
+        rn = np.random.default_rng(300 + b).random((n, 9), dtype=np.float32)       # birth: 7 numbers; the photon soon runs out
+        ev = g.trace(rn, 1, 1.0, 0.0, fracAtmsPower=frac, voxelCDF=cdf, maxEvents=n * (4 + 3 * nDir))
+        bi = ev[ev["kind"] == fi.EV_BIRTH]
+        assert len(bi) == n
+        atSurface = bi["z"] == 0.0
+        cell = (bi["ix"] - 1) + med.nx * ((bi["iy"] - 1) + med.ny * (bi["iz"] - 1))
+        births += np.bincount(cell[~atSurface], minlength=births.size)
+        sfcBirths += np.bincount(((bi["ix"] - 1) + med.nx * (bi["iy"] - 1))[atSurface], minlength=ncol)
+        le = ev[(ev["kind"] == fi.EV_LE) & (ev["order"] == 0)]
+        idx = (le["component"] - 1) * ncol + (le["ix"] - 1) + med.nx * (le["iy"] - 1)
+        L[b] = np.bincount(idx, weights=le["weight"].astype(np.float64), minlength=nDir * ncol).reshape(nDir, ncol) / n
+    p = pCell.ravel()
+    assert births[p == 0].sum() == 0                       # no photon is born where nothing absorbs
+    ok = N * p > 25
+    rms, mean, worst = fi.z_stats((births - N * p)[ok] / np.sqrt(N * p * (1 - p))[ok])
+    print("%s: births over %d cells: z rms %.3f mean %+.3f max %.2f" % (kind, ok.sum(), rms, mean, worst))
+    assert ok.sum() > 250 and rms < 1.12 and abs(mean) < 4.0 / np.sqrt(ok.sum()) and worst < 4.8, (kind, rms, mean, worst)
+    q = pSfc * med.area.ravel()
+    rms, mean, worst = fi.z_stats((sfcBirths - N * q) / np.sqrt(N * q * (1 - q)))
+    assert rms < 1.35 and abs(mean) < 0.6 and worst < 4.5, (kind, "surface births", rms, mean, worst)
+    for i, (mu, phi) in enumerate(zip(fi.VIEW_MUS, fi.VIEW_PHIS)):
+        E = emission_radiance(med, temps, lam, sfcT, mu, phi, m=32).ravel()
+        if mu < 0:
+            E = E - sfcTerm * med.area.ravel()             # surface-born photons and downward views: see the docstring
+        m, se = L[:, i].mean(axis=0), L[:, i].std(axis=0, ddof=1) / np.sqrt(B)
+        tot = L[:, i].sum(axis=1)
+        zt = (tot.mean() - E.sum()) / (tot.std(ddof=1) / np.sqrt(B))
+        rms, mean, worst = fi.z_stats((m - E) / se)
+        print("%s view %d: total %.6g vs %.6g (rel %+.2e, z %+.2f); columns z rms %.3f mean %+.3f max %.2f" % (
+            kind, i, tot.mean(), E.sum(), tot.mean() / E.sum() - 1, zt, rms, mean, worst))
+        assert abs(zt) < 4.2 and abs(tot.mean() / E.sum() - 1.0) < 0.01, (kind, i, tot.mean(), E.sum(), zt)
+        assert rms < 1.45 and abs(mean) < 0.65 and worst < 6.5, (kind, i, rms, mean, worst)
