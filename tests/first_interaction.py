@@ -62,6 +62,7 @@ def scene(kind="irregular", albedo=0.25, ssaScale=1.0, tiles=(1, 1), seed=3, tem
         else:
             xE = (xE[1] - xE[0]) * np.arange(nx * tx + 1); yE = (yE[1] - yE[0]) * np.arange(ny * ty + 1)
         ext1, ssa1, idx1 = (np.tile(a, (1, ty, tx)) for a in (ext1, ssa1, idx1))
+        temps = None if temps is None else np.tile(temps, (1, ty, tx))
     d = Domain(xE, yE, zE, temps=temps, surfaceAlbedo=albedo, lambda_um=lambda_um)
     d.addOpticalComponent("cloud", ext1, ssa1, idx1,
                           new_PhaseFunctionTable([new_PhaseFunction(legendreCoefficients=c) for c in hg], key=[1.0, 2.0]))

@@ -19,6 +19,8 @@ import numpy as np
 import pytest
 
 import first_interaction as fi
+from independent_3d import emission_radiance, thermal_source
+from mcbrat3d_b200.emissionAndBroadBandWeights import Weights, emission_weighting
 from mcbrat3d_b200.monteCarloIllumination import new_PhotonStream
 from mcbrat3d_b200.monteCarloRadiativeTransfer import (MCB_ARITH_REFERENCE, MCB_KERNEL_PARK, MCB_KERNEL_POOL,
                                                        computeRadiativeTransfer, finalize_Integrator, getCounters,
@@ -148,3 +150,58 @@ def test_first_order_radiances_match_the_independent_solver(name, tiles, params,
             name, rr, i, tot[i], E.sum(), tot[i] / E.sum() - 1, zt, rms, mean, worst))
         assert abs(zt) < 4.5 and abs(tot[i] / E.sum() - 1.0) < 0.01, (name, rr, i, tot[i], E.sum(), zt)
         assert rms < 1.4 and abs(mean) < 0.7 and worst < 6.5, (name, rr, i, rms, mean, worst)
+
+
+THERMAL = [("regular", (1, 1), {}), ("irregular_tiled", (5, 5), {}), ("irregular_tiled_park", (5, 5), dict(tuneKernel=MCB_KERNEL_PARK)),
+           ("zstretched", (1, 1), {}), ("irregular_reference_arithmetic", (1, 1), dict(arithmetic=MCB_ARITH_REFERENCE))]
+
+
+@pytest.mark.parametrize("name,tiles,params", THERMAL, ids=[c[0] for c in THERMAL])
+def test_thermal_emission_radiance_matches_the_emission_integral(name, tiles, params):
+    """Thermal source in a purely absorbing 3-D scene with a temperature that differs from cell to cell, over a black
+    (emissivity 1) surface: every radiance is emission at birth, so the maps must equal the emission integral
+    int kappa B exp(-tau) ds + transmitted surface emission of tests/independent_3d.py (exact per piece), and the
+    emission CDF built on the device must give Kirchhoff's share of the atmosphere.  Downward view: the reference drops
+    the contribution of photons born AT the surface (tests/test_first_interaction.py); the reference-arithmetic kernel
+    must do the same, the throughput kernels may count it (tau = 0: weight / pi) -- which one is printed."""
+    kind = name.split("_")[0]
+    lam, sfcT = 10.0, 300.0
+    temps = 250.0 + 40.0 * np.random.default_rng(5).random((fi.NZ, fi.NY, fi.NX))
+    dom, med = fi.scene(kind, albedo=0.0, ssaScale=0.0, tiles=tiles, temps=temps, lambda_um=lam)
+    reference = params.get("arithmetic", 0) == MCB_ARITH_REFERENCE
+    n = 1_000_000 if not reference else 250_000
+    g = new_Integrator(dom)
+    try:
+        specifyParameters(g, intensityMus=fi.VIEW_MUS, intensityPhis=fi.VIEW_PHIS, computeIntensity=True,
+                          useRussianRouletteForIntensity=False)
+        specifyParameters(g, minInverseTableSize=9001, minForwardTableSize=9001, LW_flag=1.0, **params)
+        w = Weights()
+        emission_weighting(dom, w, sfcT, thisIntegrator=g)
+        pCell, pSfc, _, sfcTerm = thermal_source(med, temps, lam, sfcT)
+        assert abs(w.fracAtmsPower - pCell.sum()) < 1e-9
+        rs = new_RandomNumberSequence([41, 6, 0])
+        rows = []
+        for _ in range(NB):
+            ps = new_PhotonStream(theseWeights=w, numberOfPhotons=n, randomNumbers=rs)
+            assert computeRadiativeTransfer(g, dom, rs, ps, n) == n
+            rows.append(np.asarray(reportResults(g, intensity=True)["intensity"], np.float64).copy())
+        assert getCounters(g)["bad"] <= (2e-5 * n if reference else 0)
+    finally:
+        finalize_Integrator(g)
+    got = fi.fold(np.array(rows) * area_fraction(dom), tiles)                     # (NB, nDir, ny, nx): E[contribution at birth]
+    m, se = got.mean(axis=0), got.std(axis=0, ddof=1) / np.sqrt(NB)
+    tot = got.sum(axis=(2, 3))
+    for i, (mu, phi) in enumerate(zip(fi.VIEW_MUS, fi.VIEW_PHIS)):
+        E = emission_radiance(med, temps, lam, sfcT, mu, phi, m=32)
+        if mu < 0:
+            dropped = E - sfcTerm * med.area
+            counts = abs(tot[:, i].mean() - E.sum()) < abs(tot[:, i].mean() - dropped.sum())
+            print("%s downward view: surface-born photons %s" % (name, "COUNTED (tau = 0)" if counts else "dropped, as in the reference"))
+            assert not (reference and counts)
+            E = E if counts else dropped
+        zt = (tot[:, i].mean() - E.sum()) / np.sqrt(tot[:, i].var(ddof=1) / NB + (2e-4 * E.sum()) ** 2)
+        rms, mean, worst = z_stats(((m[i] - E) / np.sqrt(se[i] ** 2 + (1e-3 * E.max()) ** 2)).ravel())
+        print("%s view %d: total %.6g vs %.6g (rel %+.2e, z %+.2f); columns rms %.3f mean %+.3f max %.2f" % (
+            name, i, tot[:, i].mean(), E.sum(), tot[:, i].mean() / E.sum() - 1, zt, rms, mean, worst))
+        assert abs(zt) < 4.5 and abs(tot[:, i].mean() / E.sum() - 1.0) < 0.01, (name, i, tot[:, i].mean(), E.sum(), zt)
+        assert rms < 1.4 and abs(mean) < 0.7 and worst < 6.5, (name, i, rms, mean, worst)
