@@ -129,7 +129,10 @@ __device__ void le_run(const DevDomain &P, const Grid &G, const Tally &T, uint32
         r.ix = ixy & 0xffff; r.iy = (int)((uint32_t)ixy >> 16); r.iz = izo & 0xffff;
         w = sle[LE_W * 32 + s];
         if (component == 0) {
-          npf = 1.0f / PI32;                                                       // INT:1694
+          // INT:1694.  A photon BORN at the surface (thermal source, scattering order 0) gives nothing to a downward view:
+          // its view ray has no first step, the reference's marcher signals an error and INT:1745-1751 drop the
+          // contribution (a photon REFLECTED there, order >= 1, does contribute weight / pi) -- tests/test_first_interaction.py
+          npf = (order == 0 && vz < 0.0f) ? 0.0f : 1.0f / PI32;
         } else if (component < 0) {
           npf = P.viewNorm[dir];                                                   // INT:1696
         } else {

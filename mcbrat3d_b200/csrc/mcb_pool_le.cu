@@ -53,7 +53,9 @@ enum { JOB_NONE = 0, JOB_PHOTON = 1, JOB_PLAIN = 2, JOB_E13 = 3, JOB_E14A = 4, J
 // normalised phase function value of one (event, view direction) pair: INT:1694-1726
 __device__ __forceinline__ float view_phase_value(const DevDomain &P, int component, int pidx, int order, int dir,
                                                   float dx, float dy, float dz) {
-  if (component == 0) return 1.0f / PI32;                                              // Lambertian surface, INT:1694
+  // Lambertian surface, INT:1694; born AT the surface (order 0) and viewed from below: nothing, as in the reference, whose
+  // marcher signals an error for the zero-length view ray (INT:1745-1751; tests/test_first_interaction.py)
+  if (component == 0) return (order == 0 && P.viewDir[3 * dir + 2] < 0.0f) ? 0.0f : 1.0f / PI32;
   if (component < 0) return P.viewNorm[dir];                                           // isotropic emission, INT:1696
   float proj = dx * P.viewDir[3 * dir] + dy * P.viewDir[3 * dir + 1] + dz * P.viewDir[3 * dir + 2];   // INT:1704-1706
   proj = fminf(fmaxf(proj, -1.0f), 1.0f);
