@@ -168,3 +168,37 @@ def test_oracle_thermal_births_and_emission_radiance_match_the_independent_solve
             kind, i, tot.mean(), E.sum(), tot.mean() / E.sum() - 1, zt, rms, mean, worst))
         assert abs(zt) < 4.2 and abs(tot.mean() / E.sum() - 1.0) < 0.01, (kind, i, tot.mean(), E.sum(), zt)
         assert rms < 1.45 and abs(mean) < 0.65 and worst < 6.5, (kind, i, rms, mean, worst)
+
+
+def test_periodic_seam_fold_can_disagree_with_the_cell_and_seam_fix_repairs_it():
+    """Single-precision emulation of what csrc/mcb_march.cuh does at an event on an edge-table grid: ray_position() folds the
+    position with floor((p - x0) / L) computed as a rounded product, the marcher wraps the integer cell index.  On the
+    stretched grid of these tests a position exactly AT the seam (p = L, cell nx wrapped to 0) is NOT folded -- position at
+    the far end of the domain, cell at the near end: the state that blew up the radiances.  seam_fix moves
+    the position by the one period that puts it next to its cell; positions that agree with their cell are left alone."""
+    f32 = np.float32
+    dom, _ = fi.scene("stretched")
+    xE = np.asarray(dom.xPosition, dtype=f32)
+    L, x0 = f32(xE[-1] - xE[0]), f32(xE[0])
+    invL = f32(1.0) / L
+
+    def fold(p):                                  # ray_position
+        return f32(p - L * np.floor(f32(f32(p - x0) * invL)))
+
+    def seam_fix(p, ix):                          # mcb_march.cuh::seam_fix
+        e = f32(p - f32(0.5) * f32(xE[ix] + xE[ix + 1]))
+        return f32(p - (L if e > f32(0.5) * L else (-L if e < f32(-0.5) * L else f32(0.0))))
+
+    p = fold(L)                                   # the marcher says: ghost cell nx, i.e. cell 0 after the wrap
+    assert p == L                                 # ... but the fold leaves the position at the far end
+    assert abs(float(seam_fix(p, 0))) < 1e-6      # repaired: at the left edge of cell 0
+    below = np.nextafter(L, f32(0))               # just inside the last cell: consistent, must stay
+    assert fold(below) == below and seam_fix(fold(below), fi.NX - 1) == below
+    rng = np.random.default_rng(0)
+    for _ in range(2000):                         # consistent (position, cell) pairs anywhere are never moved
+        ix = int(rng.integers(0, fi.NX))
+        q = f32(xE[ix] + rng.random() * (xE[ix + 1] - xE[ix]))
+        assert seam_fix(q, ix) == q
+    for ix, q in ((fi.NX - 1, f32(-1e-9)), (0, L), (0, np.nextafter(L, f32(1)))):   # the three ways to be one period off
+        fixed = float(seam_fix(q, ix))
+        assert xE[ix] - 1e-6 <= fixed <= xE[ix + 1] + 1e-6
