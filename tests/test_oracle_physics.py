@@ -310,3 +310,46 @@ def test_nadir_radiance_with_anisotropic_scattering_matches_adding_doubling(orc,
     a = slab_fluxes(tau, omega, table_moments(d.inversePhaseFunctions[0]), mu0, albedo, nStreams=96, muOut=[1.0])[3][0]
     b = slab_fluxes(tau, omega, g ** np.arange(64), mu0, albedo, nStreams=96, muOut=[1.0])[3][0]
     assert abs(got - 0.5 * (a + b)) < 4.0 * err + abs(a - b) + 1e-3 * a, (got, a, b, err)
+
+
+@pytest.mark.parametrize("grid", ["irregular", "stretched"])
+def test_layered_fluxes_do_not_depend_on_the_3d_grid(orc, grid):
+    """Multiple scattering through the 3-D machinery against the plane-parallel solver: a horizontally homogeneous stack
+    (layers of different optical depth and albedo, one empty) laid out on grids the reference marches on its IRREGULAR
+    path -- spacings not representable in single precision (q1-q3) and spacings that differ from cell to cell in x, y and
+    z -- with 8 x 6 columns and an oblique sun at 30 degrees azimuth, so photons wrap around both periodic boundaries many
+    times between scatterings.  Whatever the grid, the domain-mean fluxes must be the doubling + adding solution for
+    the stack (tests/adding_doubling.py::layered_fluxes): 4 sigma + 2e-4 at 2e5 photons."""
+    from adding_doubling import layered_fluxes, table_moments
+    from mcbrat3d_b200.opticalProperties import Domain
+    from mcbrat3d_b200.scatteringPhaseFunctions import henyeyGreenstein, new_PhaseFunctionTable
+    nx, ny, nz, mu0, albedo = 8, 6, 7, 0.6, 0.3
+    if grid == "irregular":
+        xE = 0.05 * np.arange(nx + 1); yE = 0.03 * np.arange(ny + 1); zE = 0.04 * np.arange(nz + 1)
+    else:
+        xE = np.concatenate([[0.0], np.cumsum(0.05 * (1 + 0.3 * np.sin(1.0 + np.arange(nx))))])
+        yE = np.concatenate([[0.0], np.cumsum(0.03 * (1 + 0.25 * np.cos(0.5 + np.arange(ny))))])
+        zE = np.concatenate([[0.0], np.cumsum(0.025 * 1.15 ** np.arange(nz))])
+    layers = [(1.5, 0.95, 2), (0.0, 0.0, 1), (2.5, 0.8, 3), (0.7, 1.0, 1)]            # (tau, omega, cells), TOP FIRST
+    d = Domain(xE, yE, zE, surfaceAlbedo=albedo)
+    ext = np.zeros((nz, ny, nx)); ssa = np.zeros((nz, ny, nx)); idx = np.zeros((nz, ny, nx), np.int32)
+    k = nz
+    for tau, omega, cells in layers:                                                  # z index 0 is the bottom layer
+        k -= cells
+        ext[k:k + cells] = tau / (zE[k + cells] - zE[k]); ssa[k:k + cells] = omega; idx[k:k + cells] = 1 if tau > 0 else 0
+    assert k == 0
+    d.addOpticalComponent("cloud", ext, ssa, idx, new_PhaseFunctionTable([henyeyGreenstein(0.85, 64)], key=[1.0]))
+    d.getOpticalPropertiesByComponent()
+    og = orc.OracleIntegrator(orc.OracleDomain(d, tableSize=10001))
+    nb = 40
+    tot, st = og.run_batches(nb, 5000, solarMu=mu0, solarAzimuth=30.0, iseed=10, rank=1, thread=0)
+    d.tabulateInversePhaseFunctions(10001)
+    want = layered_fluxes([(t, w) for t, w, _ in layers], table_moments(d.inversePhaseFunctions[0]), mu0, albedo, nStreams=96)
+    for key, w in zip(("meanFluxUpStats", "meanFluxDownStats", "meanFluxAbsorbedStats"), want):
+        m, e = _fin(orc, st, key, tot, nb)
+        assert abs(m[0] - w) < 4.0 * e[0] + 2e-4, (grid, key, m[0], w, e[0])
+    # ... and no column is special: the per-column maps scatter about the domain mean like noise
+    for key in ("fluxUpStats", "fluxDownStats"):
+        m, e = orc.finalise(st[key], 1.0, tot, nb)
+        z = (m - m.mean()) / e
+        assert np.sqrt(np.mean(z ** 2)) < 1.5 and np.abs(z).max() < 4.5, (grid, key, z)
