@@ -13,6 +13,9 @@ The throughput kernels write no event trace, so the first interaction is isolate
   below 1e-4 of I1.  Photon roulette is off for these runs (it would trade the s^2 term's size for variance), the
   local estimate runs in its plain and its Russian-roulette form.
 
+* **thermal emission** (last test): a purely absorbing scene with a temperature that differs from cell to cell over a black
+  surface -- every radiance is emission at birth, so the maps must equal the emission integral along the line of sight.
+
 The scene is also run TILED 5 x 5 (same physics, results folded back onto one tile): 40 x 30 columns is what brings in
 the photon-pool kernels with their ghost shell, bricked field and vacuum leaps."""
 import numpy as np
